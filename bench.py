@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- measurements/s of one full residual + Jacobian evaluation (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload H1]
+
+A "step" is one evaluation of every measurement of the workload at a fixed parameter point.
+  value        : device-resident throughput (inputs, knots and outputs in HBM; K steps between two CUDA events on the
+                 launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e          : the same through ktk_evaluate with HOST buffers (H2D of the parameter point, D2H of every residual and
+                 Jacobian row inside the timed region)
+  roofline     : dominant kernel (static-RS rows) timed with CUDA events inside the library, against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (restated reference, Ceres-style stride-4 autodiff, all host threads) on a bounded sample
+With N > 1 (torchrun) every rank evaluates its own full-size shard (measurements are independent: no data-path
+collective, weak scaling).  --impl reference times the CPU oracle only (the reference itself cannot be built here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "measurements/s (residual+Jacobian eval)"
+UNIT = "measurements/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="H1")
+    ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(name, cfg):
+    from kontiki_b200 import synthetic as syn
+    return {"workload": f"{name}: UniformSE3SplineTrajectory {len(cfg['knots'])} knots dt={cfg['dt']}, "
+                        f"{len(cfg['gyro']['t']) if cfg['gyro'] else 0} gyro + {len(cfg['accel']['t']) if cfg['accel'] else 0} accel (BasicImu) + "
+                        f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} StaticRsCamera (Pinhole, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
+            "measurements_per_step_per_gpu": syn.num_measurements(cfg),
+            "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
+            "jacobian": "ambient (7 per SE3 knot), Huber corrector applied to camera rows",
+            "l2": "per-step working set (outputs + records) >> 126 MB L2; no flush",
+            "sharding": "measurements sharded across ranks, knots replicated, no data-path collective"}
+
+
+# ---- CPU oracle leg (cpu_baseline and --impl reference) ------------------------------------------------------------
+def oracle_sample(cfg, frac, seed=0):
+    """A bounded random sample of the workload with the same mix of measurement types."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for k in ("gyro", "accel"):
+        if cfg[k]:
+            n = len(cfg[k]["t"])
+            sel = rng.permutation(n)[:max(1, int(n * frac))]
+            out[k] = {a: v[sel] for a, v in cfg[k].items()}
+    if cfg["cam"]:
+        c = cfg["cam"]
+        n = len(c["lm_idx"])
+        sel = rng.permutation(n)[:max(1, int(n * frac))]
+        out["cam"] = dict(c, **{a: c[a][sel] for a in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "weight", "huber_c")})
+    return out
+
+
+def oracle_step(cfg, sample):
+    """One residual+Jacobian evaluation of the sample with the CPU oracle; returns (rows, seconds inside Evaluate)."""
+    from oracle import kto
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    rows, secs = 0, 0.0
+    imu = kto.Sensor()
+    for which, k in ((0, "gyro"), (1, "accel")):
+        if k in sample:
+            m = sample[k]
+            res = kto.imu_residuals(traj, imu, which, m["t"], m["y"], m["weight"], jac_mode=1)
+            rows += len(m["t"]); secs += res["eval_seconds"]
+    if "cam" in sample:
+        c = sample["cam"]
+        ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"])
+        res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24)
+        rows += len(c["lm_idx"]); secs += res["eval_seconds"]
+    return rows, secs
+
+
+def cpu_baseline(cfg, frac, steps=1, warmup=1, budget_s=12.0):
+    from oracle import kto
+    if frac is None:      # pilot on 0.5 % of the workload, then size the sample for ~budget_s seconds of CPU work in total
+        r, s = oracle_step(cfg, oracle_sample(cfg, 0.005, seed=1))
+        n_total = sum(len(cfg[k]["t"]) for k in ("gyro", "accel") if cfg[k]) + (len(cfg["cam"]["lm_idx"]) if cfg["cam"] else 0)
+        frac = float(min(1.0, max(0.005, budget_s / max(steps + warmup, 1) * (r / s) / n_total)))
+    sample = oracle_sample(cfg, frac)
+    for _ in range(warmup):
+        oracle_step(cfg, sample)
+    rows, secs = 0, 0.0
+    for _ in range(steps):
+        r, s = oracle_step(cfg, sample)
+        rows += r; secs += s
+    return {"value": rows / secs, "unit": UNIT, "cores": kto.num_threads(), "kind": "port",
+            "sample": f"{rows // steps} rows per step ({frac:.3g} of the workload, same type mix), {steps} step(s), "
+                      "time inside the per-block Evaluate loop only (problem construction excluded), OpenMP over blocks"}, rows, secs
+
+
+# ---- clocks --------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from kontiki_b200 import synthetic as syn
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cfg = syn.make_config(a.workload)
+        base, rows, secs = cpu_baseline(cfg, a.cpu_sample, steps=a.steps, warmup=1 if a.warmup > 0 else 0, budget_s=90.0)
+        line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": workload_config(a.workload, cfg), "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "restated reference on host cores: the reference needs Ceres 1.x + Sophus + Eigen, none installable here (oracle/README.md)"}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from kontiki_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (kontiki_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = syn.make_config(a.workload)
+    if world > 1:      # every rank owns a different, equally sized shard of measurements (independent seeds), knots replicated
+        n_knots = len(cfg["knots"])
+        if cfg["gyro"]:
+            cfg["gyro"] = syn.make_imu(len(cfg["gyro"]["t"]), n_knots, cfg["dt"], seed=100 + rank)
+        if cfg["accel"]:
+            cfg["accel"] = syn.make_imu(len(cfg["accel"]["t"]), n_knots, cfg["dt"], seed=200 + rank, accel=True)
+        if cfg["cam"]:
+            cfg["cam"] = syn.make_static_rs(cfg["knots"], cfg["dt"], len(cfg["cam"]["rho"]), seed=300 + rank)
+    n_meas = syn.num_measurements(cfg)
+    alg_bytes = syn.algorithmic_bytes(cfg)
+
+    p = _lib.Problem(local_rank)
+    stream = torch.cuda.current_stream()
+    p.set_stream(stream.cuda_stream)
+    p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+    imu = _lib.make_sensor()
+    groups = {}
+    if cfg["gyro"]:
+        groups["gyro"] = p.add_gyroscope(imu, cfg["gyro"]["t"], cfg["gyro"]["y"], cfg["gyro"]["weight"])
+    if cfg["accel"]:
+        groups["accel"] = p.add_accelerometer(imu, cfg["accel"]["t"], cfg["accel"]["y"], cfg["accel"]["weight"])
+    rho = None
+    if cfg["cam"]:
+        c = cfg["cam"]
+        rho = c["rho"]
+        groups["cam"] = p.add_static_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"]), c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"],
+                                        c["lm_idx"], c["weight"], c["huber_c"])
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST
+
+    # ---- device-resident leg -------------------------------------------------------------------------------------
+    dev = torch.device("cuda", local_rank)
+    d_knots = torch.from_numpy(cfg["knots"]).to(dev)
+    d_rho = torch.from_numpy(rho).to(dev) if rho is not None else None
+    d_outs, keep = [], []
+    for g in range(p.num_groups):
+        n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
+        r = torch.empty((n, 2 if cam else 3), dtype=torch.float64, device=dev)
+        J = torch.empty((n, _lib.CAM_ROW if cam else _lib.IMU_ROW), dtype=torch.float64, device=dev)
+        i0 = torch.empty(n, dtype=torch.int32, device=dev)
+        i0b = torch.empty(n, dtype=torch.int32, device=dev)
+        keep.append((r, J, i0, i0b))
+        d_outs.append(dict(r=r.data_ptr(), J=J.data_ptr(), i0=i0.data_ptr(), i0_b=i0b.data_ptr() if cam else None))
+
+    def step_device():
+        p.evaluate_device(d_knots.data_ptr(), d_rho.data_ptr() if d_rho is not None else 0, 0 if rho is None else len(rho), flags, d_outs)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    p.synchronize()
+    p.read_profile(0)
+    barrier()
+    p.set_profiling(True)
+    l0 = p.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        e0.record(stream)
+        for _ in range(a.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        if a.steps * (ms_total / max(a.steps, 1)) < 1500.0:      # keep the GPU under load long enough for a few clock samples
+            t_end = time.time() + 1.5
+            p.set_profiling(False)
+            while time.time() < t_end:
+                step_device()
+                torch.cuda.synchronize()
+            p.set_profiling(True)
+    launches = p.launch_count - l0
+    p.synchronize()
+    prof = {name: p.read_profile(g) for name, g in groups.items()}
+    p.set_profiling(False)
+    ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / a.steps
+    value = world * n_meas / (ms_step * 1e-3)
+
+    # ---- end-to-end leg: host buffers through ktk_evaluate ---------------------------------------------------------
+    h_knots = torch.from_numpy(cfg["knots"]).pin_memory()
+    h_rho = torch.from_numpy(rho).pin_memory() if rho is not None else None
+    h_outs, d2h = [], 0
+    for g in range(p.num_groups):
+        n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
+        o = dict(r=torch.empty((n, 2 if cam else 3), dtype=torch.float64).pin_memory(),
+                 J=torch.empty((n, _lib.CAM_ROW if cam else _lib.IMU_ROW), dtype=torch.float64).pin_memory(),
+                 i0=torch.empty(n, dtype=torch.int32).pin_memory())
+        if cam:
+            o["i0_b"] = torch.empty(n, dtype=torch.int32).pin_memory()
+        d2h += sum(t.numel() * t.element_size() for t in o.values())
+        h_outs.append({k: v.numpy() for k, v in o.items()})
+        keep.append(o)
+    h2d = h_knots.numel() * 8 + (h_rho.numel() * 8 if h_rho is not None else 0)
+    e2e_steps = max(3, min(a.steps, 10))
+    for _ in range(2):
+        p.evaluate(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        p.evaluate(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_meas * e2e_steps / float(e2e_s.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    dom = "cam" if "cam" in groups else ("accel" if "accel" in groups else "gyro")
+    dom_ms, dom_n = prof[dom]
+    dom_rows = p.group_size(groups[dom])
+    dom_bytes = dom_rows * (1012 if dom == "cam" else 740)
+    achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get({"cam": "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom])
+    except Exception:
+        pass
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a.workload, cfg),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": {"bound": "hbm", "kernel": {"cam": "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
+                         "kernel_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in prof.items()}}}
+    if not a.no_cpu_baseline:
+        base, _, _ = cpu_baseline(cfg, a.cpu_sample)
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,152 @@
+/* kontiki_b200 -- C ABI of the B200-native residual + Jacobian evaluation path of hovren/kontiki.
+ *
+ * This is the drop-in boundary.  In the reference every measurement is one
+ * ceres::DynamicAutoDiffCostFunction whose operator is
+ *     bool Residual::operator()(T const* const* params, T* residual)
+ *         cpplib/include/kontiki/measurements/gyroscope_measurement.h:58-68
+ *         cpplib/include/kontiki/measurements/accelerometer_measurement.h:60-70
+ *         cpplib/include/kontiki/measurements/static_rscamera_measurement.h:112-123
+ * registered by  *Measurement::AddToEstimator  (gyroscope_measurement.h:75-105, accelerometer_measurement.h:77-108,
+ * static_rscamera_measurement.h:130-198) and called by Ceres as
+ *     CostFunction::Evaluate(double const* const* parameters, double* residuals, double** jacobians)
+ * once per measurement per evaluation from  TrajectoryEstimator::Solve  (cpplib/include/kontiki/trajectory_estimator.h:38-64).
+ * The functions below replace that per-measurement operator by ONE batched evaluation per parameter point -- the
+ * shape of ceres::EvaluationCallback::PrepareForEvaluation(evaluate_jacobians, new_evaluation_point) -- after which
+ * each cost function only copies its slice out.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Plain C: pointers and sizes only; no exceptions cross the boundary (std::range_error / std::runtime_error of the
+ * reference become KTK_ERANGE / KTK_ERUNTIME, text in ktk_last_error()).
+ *
+ * Layouts (all fp64, quaternions stored x,y,z,w = Eigen coefficient order, as the reference's parameter blocks):
+ *   SE3 knot           : 7 doubles [qx qy qz qw tx ty tz]            (uniform_se3_spline_trajectory.h:27,57)
+ *   gyro / accel row   : r[3];  J[4][3][7] = d r / d knot(i0+k), k = 0..3, each block row-major 3 x 7 exactly like
+ *                        Ceres' jacobians[k] of the 4 knot parameter blocks (locked IMU: the segment has exactly
+ *                        those 4 knots, spline_base.h:371-403);  i0 = index of the first active knot
+ *   static-RS row      : r[2];  J[114] = [ref window: 4 x (2 x 7)] [obs window: 4 x (2 x 7)] [d r / d rho (2)];
+ *                        i0_ref, i0_obs = first active knot of the two spline evaluations.  A knot that is in both
+ *                        windows receives the SUM of its two blocks (one parameter block in the reference);
+ *                        ktk_expand_static_rs() produces the reference's structural per-block layout.
+ * Rows are returned in the caller's order of insertion, whatever order the device processes them in.
+ */
+#ifndef KONTIKI_B200_H_
+#define KONTIKI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ktk_problem ktk_problem;
+
+enum {
+  KTK_OK = 0,
+  KTK_ERANGE = -1,        /* std::range_error in the reference (time outside the trajectory / no segment found) */
+  KTK_ERUNTIME = -2,      /* std::runtime_error / std::domain_error in the reference */
+  KTK_EINVAL = -3,        /* bad argument at the boundary */
+  KTK_ECUDA = -4,         /* CUDA runtime failure, or no usable sm_100 device */
+  KTK_EUNSUPPORTED = -5   /* a reference feature outside the built path (see DESIGN.md "out of scope") */
+};
+
+enum {
+  KTK_EVAL_RESIDUALS = 1u,
+  KTK_EVAL_JACOBIANS = 2u,
+  KTK_EVAL_ROBUST = 4u    /* apply ceres::HuberLoss(huber_c) + Corrector to static-RS rows, as Ceres does after Evaluate
+                             (static_rscamera_measurement.h:195-197) */
+};
+
+enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2 };
+
+/* sensors/sensors.h:91-109: relative pose + time offset; *_locked as the reference's lock flags (default locked). */
+typedef struct {
+  double q_ct[4];            /* x y z w */
+  double p_ct[3];
+  double time_offset;
+  double max_time_offset;    /* sensors.h:107, default 0.1 */
+  int32_t q_locked, p_locked, time_offset_locked;
+} ktk_sensor;
+
+/* sensors/camera.h:24-28 + sensors/pinhole_camera.h:25 */
+typedef struct {
+  ktk_sensor base;
+  int32_t rows, cols;
+  double readout;
+  double K[9];               /* row-major 3x3 */
+} ktk_pinhole_camera;
+
+/* Per measurement group output pointers (any may be NULL).  Host pointers for ktk_evaluate, device pointers for
+ * ktk_evaluate_device.  Sizes for n rows: r n*3 (IMU) / n*2 (camera); J n*84 / n*114; i0 n; i0_b n (camera: obs). */
+typedef struct {
+  double* r;
+  double* J;
+  int32_t* i0;       /* IMU: i0;  camera: i0_ref */
+  int32_t* i0_b;     /* camera: i0_obs; unused for IMU */
+} ktk_group_out;
+
+const char* ktk_last_error(void);
+
+/* Creates an empty problem on CUDA device `device`.  Fails with KTK_ECUDA when there is no CUDA device: there is no
+ * CPU fallback.  device = -1 creates a host-only handle that answers ktk_get_structure / ktk_expand_static_rs
+ * (problem-structure bookkeeping) and refuses every evaluation call with KTK_ECUDA. */
+int ktk_problem_create(int device, ktk_problem** out);
+void ktk_problem_destroy(ktk_problem* p);
+
+/* The stream all device work of this problem is enqueued on (a cudaStream_t; NULL = the legacy default stream). */
+int ktk_set_stream(ktk_problem* p, void* cuda_stream);
+
+/* UniformSE3SplineTrajectory(dt, t0) with n_knots control points (spline_base.h:30-62).  compat_zero_dB = 1 reproduces
+ * the reference's Jet-path accelerometer on SE3 (dB left at zero, uniform_se3_spline_trajectory.h:138-141 vs :166-169). */
+int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, int32_t compat_zero_dB);
+
+/* *Measurement::AddToEstimator, batched: returns the group id (>= 0) or a negative status.  Arrays are copied.
+ *   gyroscope / accelerometer: t[n], y[3n], weight[n] (NULL = 1)   (gyroscope_measurement.h:18-20)
+ *   static RS: obs_uv[2n], obs_t0[n] (view t0 of the observation), ref_uv[2n], ref_t0[n] (of the landmark's reference
+ *   observation), lm_idx[n] into the rho array given to ktk_evaluate, weight[n] (NULL = 1), huber_c[n] (NULL = 5,
+ *   static_rscamera_measurement.h:68-69). */
+int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
+int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
+int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
+                      const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
+
+int32_t ktk_num_groups(const ktk_problem* p);
+int64_t ktk_group_size(const ktk_problem* p, int32_t group);
+int32_t ktk_group_kind(const ktk_problem* p, int32_t group);
+
+/* One batched evaluation at the parameter point (knots[n_knots*7], rho[n_rho]) with HOST buffers: uploads the point,
+ * runs the kernels, downloads every non-NULL output of outs[0..num_groups), returns when they are complete.
+ * Returns KTK_ERANGE if any measurement falls outside the trajectory (the reference throws at AddToEstimator,
+ * trajectory_estimator.h:97-122, or inside Evaluate, spline_base.h:196-201). */
+int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs);
+
+/* Same with DEVICE buffers, asynchronous on the problem's stream; ktk_synchronize() waits and reports the status. */
+int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_rho, int64_t n_rho, uint32_t flags,
+                        const ktk_group_out* d_outs);
+int ktk_synchronize(ktk_problem* p);
+
+/* Number of kernel launches ktk_evaluate_device enqueued since the problem was created. */
+int64_t ktk_launch_count(const ktk_problem* p);
+
+/* Kernel timing for bench.py's roofline: while on, every kernel launch of a measurement group is bracketed by CUDA
+ * events on the problem's stream; ktk_read_profile synchronises, returns the summed device time (ms) and the number
+ * of launches of that group's kernel since the last read, and clears the record. */
+int ktk_set_profiling(ktk_problem* p, int32_t on);
+int ktk_read_profile(ktk_problem* p, int32_t group, double* total_ms, int64_t* launches);
+
+/* Page-locked host memory for ktk_evaluate's buffers (cudaHostAlloc); optional. */
+void* ktk_host_alloc(int64_t bytes);
+void ktk_host_free(void* ptr);
+
+/* Structure of one residual block as *Measurement::AddToEstimator would have registered it
+ * (spline_base.h:361-404 knot range / segment rule): knot ids in parameter-block order, -1 padded to `cap`.
+ * n_ids[i] = number of knot blocks.  Host-side, no device work.  Returns KTK_EINVAL if cap is too small. */
+int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids);
+
+/* Packed static-RS rows -> the reference's structural blocks: out[n][cap][2][7] for the knot ids of ktk_get_structure
+ * (zero for knots in the segment that are not active).  Host-side helper for Ceres-style consumers. */
+int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const int32_t* knot_ids, const double* J_packed,
+                         const int32_t* i0_ref, const int32_t* i0_obs, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* KONTIKI_B200_H_ */

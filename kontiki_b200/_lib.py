@@ -1,0 +1,251 @@
+"""ctypes binding of the C ABI declared in include/kontiki_b200.h (libkontiki_b200.so, CUDA sm_100a).
+
+There is no CPU path: if the library is missing, or no sm_100 device is present, every entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST = 1, 2, 4
+GYROSCOPE, ACCELEROMETER, STATIC_RS = 0, 1, 2
+IMU_ROW, CAM_ROW = 84, 114
+
+
+class Sensor(C.Structure):
+    _fields_ = [("q_ct", C.c_double * 4), ("p_ct", C.c_double * 3), ("time_offset", C.c_double), ("max_time_offset", C.c_double),
+                ("q_locked", C.c_int32), ("p_locked", C.c_int32), ("time_offset_locked", C.c_int32)]
+
+
+class PinholeCamera(C.Structure):
+    _fields_ = [("base", Sensor), ("rows", C.c_int32), ("cols", C.c_int32), ("readout", C.c_double), ("K", C.c_double * 9)]
+
+
+class GroupOut(C.Structure):
+    _fields_ = [("r", C.c_void_p), ("J", C.c_void_p), ("i0", C.c_void_p), ("i0_b", C.c_void_p)]
+
+
+EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_set_stream", "ktk_set_se3_spline", "ktk_add_gyroscope",
+           "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
+           "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
+           "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile"]
+
+_lib = None
+
+
+class KontikiError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def lib():
+    """Loads the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                              "kontiki_b200 has no CPU fallback.")
+        L = C.CDLL(path)
+        L.ktk_last_error.restype = C.c_char_p
+        L.ktk_group_size.restype = C.c_int64
+        L.ktk_launch_count.restype = C.c_int64
+        L.ktk_host_alloc.restype = C.c_void_p
+        L.ktk_host_alloc.argtypes = [C.c_int64]
+        L.ktk_host_free.argtypes = [C.c_void_p]
+        L.ktk_problem_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.ktk_problem_destroy.argtypes = [C.c_void_p]
+        L.ktk_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.ktk_set_se3_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32]
+        L.ktk_add_gyroscope.argtypes = [C.c_void_p, C.POINTER(Sensor), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_add_accelerometer.argtypes = L.ktk_add_gyroscope.argtypes
+        L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(PinholeCamera), C.c_int64] + [C.c_void_p] * 7
+        L.ktk_num_groups.argtypes = [C.c_void_p]
+        L.ktk_group_size.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_group_kind.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.POINTER(GroupOut)]
+        L.ktk_evaluate_device.argtypes = L.ktk_evaluate.argtypes
+        L.ktk_synchronize.argtypes = [C.c_void_p]
+        L.ktk_launch_count.argtypes = [C.c_void_p]
+        L.ktk_get_structure.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.ktk_expand_static_rs.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
+        L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        _lib = L
+    return _lib
+
+
+def check(code):
+    """Maps C statuses to the exceptions pybind11 gives the reference's (std::range_error -> ValueError, ...)."""
+    if code >= 0:
+        return code
+    msg = lib().ktk_last_error().decode()
+    if code == ERANGE:
+        raise ValueError(msg)
+    if code == EINVAL:
+        raise ValueError(msg)
+    if code == EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise KontikiError(code, msg)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_sensor(q_ct=(0, 0, 0, 1), p_ct=(0, 0, 0), time_offset=0.0, max_time_offset=0.1, q_locked=True, p_locked=True, time_offset_locked=True):
+    s = Sensor()
+    s.q_ct[:] = [float(x) for x in q_ct]
+    s.p_ct[:] = [float(x) for x in p_ct]
+    s.time_offset, s.max_time_offset = float(time_offset), float(max_time_offset)
+    s.q_locked, s.p_locked, s.time_offset_locked = int(q_locked), int(p_locked), int(time_offset_locked)
+    return s
+
+
+def make_camera(rows, cols, readout, K, **sensor_kw):
+    c = PinholeCamera()
+    c.base = make_sensor(**sensor_kw)
+    c.rows, c.cols, c.readout = int(rows), int(cols), float(readout)
+    c.K[:] = [float(x) for x in np.asarray(K, float).reshape(-1)]
+    return c
+
+
+class Problem:
+    """Thin object wrapper of ktk_problem (one CUDA device, one SE3 spline, any number of measurement groups)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        check(lib().ktk_problem_create(int(device), C.byref(self._h)))
+        self.device = device
+        self.n_knots = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().ktk_problem_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        check(lib().ktk_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_se3_spline(self, dt, t0, n_knots, compat_zero_dB=False):
+        check(lib().ktk_set_se3_spline(self._h, float(dt), float(t0), int(n_knots), int(compat_zero_dB)))
+        self.n_knots = int(n_knots)
+
+    def _add_imu(self, fn, sensor, t, y, weight):
+        t, y = _f64(t), _f64(y).reshape(-1, 3)
+        if len(t) != len(y):
+            raise ValueError("t and y differ in length")
+        w = None if weight is None else _f64(weight)
+        return check(fn(self._h, C.byref(sensor), len(t), _ptr(t), _ptr(y), _ptr(w)))
+
+    def add_gyroscope(self, sensor, t, y, weight=None):
+        return self._add_imu(lib().ktk_add_gyroscope, sensor, t, y, weight)
+
+    def add_accelerometer(self, sensor, t, y, weight=None):
+        return self._add_imu(lib().ktk_add_accelerometer, sensor, t, y, weight)
+
+    def add_static_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
+        obs_uv, ref_uv = _f64(obs_uv).reshape(-1, 2), _f64(ref_uv).reshape(-1, 2)
+        obs_t0, ref_t0 = _f64(obs_t0), _f64(ref_t0)
+        lm = np.ascontiguousarray(lm_idx, np.int32)
+        n = len(obs_t0)
+        if not (len(obs_uv) == len(ref_uv) == len(ref_t0) == len(lm) == n):
+            raise ValueError("static-RS arrays differ in length")
+        w = None if weight is None else _f64(weight)
+        h = None if huber_c is None else _f64(huber_c)
+        return check(lib().ktk_add_static_rs(self._h, C.byref(camera), n, _ptr(obs_uv), _ptr(obs_t0), _ptr(ref_uv), _ptr(ref_t0), _ptr(lm),
+                                             _ptr(w), _ptr(h)))
+
+    @property
+    def num_groups(self):
+        return lib().ktk_num_groups(self._h)
+
+    def group_size(self, g):
+        return lib().ktk_group_size(self._h, g)
+
+    def group_kind(self, g):
+        return lib().ktk_group_kind(self._h, g)
+
+    @property
+    def launch_count(self):
+        return lib().ktk_launch_count(self._h)
+
+    def alloc_outputs(self, jacobians=True):
+        """Host (numpy) output arrays for every group, in the C ABI's packed layouts."""
+        outs = []
+        for g in range(self.num_groups):
+            n, cam = self.group_size(g), self.group_kind(g) == STATIC_RS
+            o = dict(r=np.zeros((n, 2 if cam else 3)), i0=np.full(n, -1, np.int32))
+            if jacobians:
+                o["J"] = np.zeros((n, CAM_ROW)) if cam else np.zeros((n, 4, 3, 7))
+            if cam:
+                o["i0_b"] = np.full(n, -1, np.int32)
+            outs.append(o)
+        return outs
+
+    @staticmethod
+    def _out_array(outs, getptr):
+        arr = (GroupOut * max(len(outs), 1))()
+        for i, o in enumerate(outs):
+            arr[i].r = getptr(o.get("r"))
+            arr[i].J = getptr(o.get("J"))
+            arr[i].i0 = getptr(o.get("i0"))
+            arr[i].i0_b = getptr(o.get("i0_b"))
+        return arr
+
+    def evaluate(self, knots, rho=None, flags=EVAL_RESIDUALS | EVAL_JACOBIANS, outs=None):
+        """Host-buffer evaluation (ktk_evaluate).  knots: (n_knots, 7) [qx qy qz qw tx ty tz]; returns the list of group outputs."""
+        knots = _f64(knots)
+        if knots.shape != (self.n_knots, 7):
+            raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
+        rho = None if rho is None else _f64(rho)
+        if outs is None:
+            outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS))
+        arr = self._out_array(outs, _ptr)
+        check(lib().ktk_evaluate(self._h, _ptr(knots), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
+        return outs
+
+    def evaluate_device(self, d_knots_ptr, d_rho_ptr, n_rho, flags, d_outs):
+        """Device-buffer evaluation (ktk_evaluate_device): pointers are raw device addresses (e.g. torch data_ptr())."""
+        arr = self._out_array(d_outs, lambda p: None if p is None else int(p))
+        check(lib().ktk_evaluate_device(self._h, C.c_void_p(int(d_knots_ptr)), None if not d_rho_ptr else C.c_void_p(int(d_rho_ptr)), int(n_rho),
+                                        int(flags), arr))
+
+    def set_profiling(self, on):
+        check(lib().ktk_set_profiling(self._h, int(bool(on))))
+
+    def read_profile(self, g):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(lib().ktk_read_profile(self._h, g, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def synchronize(self):
+        check(lib().ktk_synchronize(self._h))
+
+    def get_structure(self, g, cap=16):
+        n = self.group_size(g)
+        ids, nids = np.full((n, cap), -1, np.int32), np.zeros(n, np.int32)
+        check(lib().ktk_get_structure(self._h, g, cap, _ptr(ids), _ptr(nids)))
+        return ids, nids
+
+    def expand_static_rs(self, g, ids, J, i0_ref, i0_obs):
+        n, cap = ids.shape
+        out = np.zeros((n, cap, 2, 7))
+        J = _f64(J).reshape(n, CAM_ROW)
+        check(lib().ktk_expand_static_rs(self._h, g, cap, _ptr(np.ascontiguousarray(ids, np.int32)), _ptr(J), _ptr(np.ascontiguousarray(i0_ref, np.int32)),
+                                         _ptr(np.ascontiguousarray(i0_obs, np.int32)), _ptr(out)))
+        return out

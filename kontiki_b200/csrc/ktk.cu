@@ -1,0 +1,506 @@
+// kontiki_b200 -- CUDA kernels (sm_100a) and the C ABI of include/kontiki_b200.h.
+//
+// Kernels per evaluation point:
+//   k_pack_knots     n_knots x 7 (reference layout) -> 64-B knot records
+//   k_pair_prepass   K0: omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian, one thread per (pair, direction)
+//   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
+//   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1))
+// Measurement records are sorted once (at add time) by their first active knot so that a warp touches one or two
+// knot windows; each thread builds its Jacobian row in shared memory and hands it to the TMA (cp.async.bulk
+// shared -> global) as ONE contiguous 672-B / 912-B store at the caller's row index, so rows come out in the caller's
+// order at full sector efficiency without a second pass.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/kontiki_b200.h"
+#include "spline_math.cuh"
+
+using namespace kb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define KTK_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(KTK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+constexpr int kThreads = 64;            // measurement rows per CTA (one per thread)
+constexpr int kImuRow = 84, kImuRowStride = 86;     // doubles; stride keeps rows 16-B aligned and off the same banks
+constexpr int kCamRow = 114, kCamRowStride = 114;
+
+// ---- TMA bulk store of one shared-memory row to global memory ----------------------------------------------------
+__device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc, unsigned bytes) {
+  // writes of this thread to its row (generic proxy) must be visible to the async proxy before the copy is issued
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+__global__ void k_pack_knots(const double* __restrict__ k7, int n, double* __restrict__ k8) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kKnotStride) return;
+  const int k = i / kKnotStride, c = i % kKnotStride;
+  k8[i] = c < 7 ? k7[(size_t)k * 7 + c] : 0.0;
+}
+
+__global__ void k_pair_prepass(const double* __restrict__ knots, int n_knots, double* __restrict__ pairs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = 1 + i / 15, dir = i % 15;
+  if (p >= n_knots) return;
+  pair_prepass_item(knots, p, dir, pairs);
+}
+
+struct ImuArgs {
+  SplineConst sp; ImuConst imu;
+  const double* knots; const double* pairs;
+  const double* t; const double* y; const double* w; const int* perm;
+  int n; uint32_t flags;
+  double* r; double* J; int* i0; int* err;
+};
+
+template <int WHICH>
+__global__ void __launch_bounds__(kThreads) k_imu(const ImuArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.n) return;
+  double* row = smem + threadIdx.x * kImuRowStride;
+  const double y[3] = {a.y[3 * (size_t)i], a.y[3 * (size_t)i + 1], a.y[3 * (size_t)i + 2]};
+  double r[3];
+  int i0 = -1;
+  const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, a.t[i], y, a.w[i], r, row, &i0);
+  const size_t dst = (size_t)a.perm[i];
+  if (st != 0) {
+    atomicMin(a.err, st);
+    r[0] = r[1] = r[2] = nan("");
+    for (int c = 0; c < kImuRow; ++c) row[c] = nan("");
+  }
+  if (a.J && (a.flags & KTK_EVAL_JACOBIANS)) bulk_store_row(a.J + dst * kImuRow, row, kImuRow * 8);
+  if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+  if (a.i0) a.i0[dst] = i0;
+  bulk_store_wait();
+}
+
+struct CamArgs {
+  SplineConst sp; CameraConst cam;
+  const double* knots; const double* pairs; const double* rho;
+  const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
+  const int* perm;
+  int n; uint32_t flags;
+  double* r; double* J; int* i0r; int* i0o; int* err;
+};
+
+__global__ void __launch_bounds__(kThreads) k_static_rs(const CamArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.n) return;
+  double* row = smem + threadIdx.x * kCamRowStride;
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+  const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+  double r[2];
+  int ir = -1, io = -1;
+  const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
+  const int st = static_rs_row(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i], hub, r, row, &ir, &io);
+  const size_t dst = (size_t)a.perm[i];
+  if (st != 0) {
+    atomicMin(a.err, st);
+    r[0] = r[1] = nan("");
+    for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+  }
+  if (a.J && (a.flags & KTK_EVAL_JACOBIANS)) bulk_store_row(a.J + dst * kCamRow, row, kCamRow * 8);
+  if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+  if (a.i0r) a.i0r[dst] = ir;
+  if (a.i0o) a.i0o[dst] = io;
+  bulk_store_wait();
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+template <class T> struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int resize(size_t m) { if (m <= n && p) return KTK_OK; if (p) cudaFree(p); p = nullptr; n = 0; KTK_CUDA(cudaMalloc(&p, std::max<size_t>(m, 1) * sizeof(T))); n = m; return KTK_OK; }
+  int upload(const std::vector<T>& v, cudaStream_t s) { int st = resize(v.size()); if (st) return st; if (!v.empty()) KTK_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s)); return KTK_OK; }
+};
+
+struct Group {
+  int kind = 0; int64_t n = 0;
+  ktk_sensor sensor{}; ktk_pinhole_camera cam{};
+  // caller-order host copies (structure queries) and sorted device copies
+  std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
+  std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
+  DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_uv, d_ref_t0, d_huber;
+  DevBuf<int> d_lm, d_perm;
+  // device-side outputs used by the host-buffer path
+  DevBuf<double> o_r, o_J; DevBuf<int> o_i0, o_i0b;
+  bool uploaded = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;   // one event pair per profiled launch of this group's kernel
+  ~Group() { for (auto& e : prof) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } }
+};
+
+}  // namespace
+
+struct ktk_problem {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool have_spline = false;
+  SplineConst sp{0.0, 1.0, 0, 0};
+  std::vector<Group*> groups;
+  DevBuf<double> d_knots7, d_knots8, d_pairs, d_rho;
+  DevBuf<int> d_err;
+  int* h_err = nullptr;   // pinned
+  int64_t launches = 0;
+  bool profiling = false;
+  ~ktk_problem() { for (auto g : groups) delete g; if (h_err) cudaFreeHost(h_err); }
+};
+
+namespace {
+
+void fill_sensor_consts(const ktk_sensor& s, ImuConst& c) { c.time_offset = s.time_offset; c.max_time_offset = s.max_time_offset; c.time_offset_locked = s.time_offset_locked; }
+
+void fill_camera_consts(const ktk_pinhole_camera& cm, CameraConst& c) {
+  for (int i = 0; i < 9; ++i) c.K[i] = cm.K[i];
+  // Eigen fixed-size 3x3 inverse = cofactors / determinant (pinhole_camera.h:63-67 inverts K per call)
+  const double* a = cm.K; double k[9];
+  k[0] = a[4] * a[8] - a[5] * a[7]; k[1] = a[2] * a[7] - a[1] * a[8]; k[2] = a[1] * a[5] - a[2] * a[4];
+  k[3] = a[5] * a[6] - a[3] * a[8]; k[4] = a[0] * a[8] - a[2] * a[6]; k[5] = a[2] * a[3] - a[0] * a[5];
+  k[6] = a[3] * a[7] - a[4] * a[6]; k[7] = a[1] * a[6] - a[0] * a[7]; k[8] = a[0] * a[4] - a[1] * a[3];
+  const double det = a[0] * k[0] + a[1] * k[3] + a[2] * k[6];
+  for (int i = 0; i < 9; ++i) c.Kinv[i] = k[i] / det;
+  for (int i = 0; i < 4; ++i) c.q_ct[i] = cm.base.q_ct[i];
+  for (int i = 0; i < 3; ++i) c.p_ct[i] = cm.base.p_ct[i];
+  c.time_offset = cm.base.time_offset; c.max_time_offset = cm.base.max_time_offset; c.time_offset_locked = cm.base.time_offset_locked;
+  c.readout = cm.readout; c.row_delta = cm.readout / (double)cm.rows;
+}
+
+int check_sensor(const ktk_sensor* s) {
+  if (!s) return fail(KTK_EINVAL, "sensor is NULL");
+  if (!s->q_locked || !s->p_locked || !s->time_offset_locked)
+    return fail(KTK_EUNSUPPORTED, "unlocked sensor parameters (relative pose / time offset Jacobians) are not built yet");
+  return KTK_OK;
+}
+
+// Sort key = first active knot of the (first) spline evaluation; host arithmetic identical to the device's.
+std::vector<int> sort_perm(const std::vector<int>& key) {
+  std::vector<int> perm(key.size());
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a] < key[b]; });
+  return perm;
+}
+template <class T> std::vector<T> gather(const std::vector<T>& v, const std::vector<int>& perm, int width) {
+  std::vector<T> o(v.size());
+  for (size_t i = 0; i < perm.size(); ++i) for (int c = 0; c < width; ++c) o[i * width + c] = v[(size_t)perm[i] * width + c];
+  return o;
+}
+
+int upload_group(ktk_problem* p, Group& g) {
+  if (g.uploaded) return KTK_OK;
+  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
+  const SplineConst& sp = p->sp;
+  std::vector<int> key((size_t)g.n);
+  if (g.kind == KTK_STATIC_RS) {
+    const double row_delta = g.cam.readout / (double)g.cam.rows;
+    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.obs_t0[i] + g.cam.base.time_offset + g.obs_uv[2 * i + 1] * row_delta, sp.t0, sp.dt);
+  } else {
+    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.t[i] + g.sensor.time_offset, sp.t0, sp.dt);
+  }
+  g.perm = sort_perm(key);
+  int st;
+  cudaStream_t s = p->stream;
+  if ((st = g.d_perm.upload(g.perm, s))) return st;
+  if ((st = g.d_w.upload(gather(g.w, g.perm, 1), s))) return st;
+  if (g.kind == KTK_STATIC_RS) {
+    if ((st = g.d_obs_uv.upload(gather(g.obs_uv, g.perm, 2), s))) return st;
+    if ((st = g.d_obs_t0.upload(gather(g.obs_t0, g.perm, 1), s))) return st;
+    if ((st = g.d_ref_uv.upload(gather(g.ref_uv, g.perm, 2), s))) return st;
+    if ((st = g.d_ref_t0.upload(gather(g.ref_t0, g.perm, 1), s))) return st;
+    if ((st = g.d_huber.upload(gather(g.huber, g.perm, 1), s))) return st;
+    if ((st = g.d_lm.upload(gather(g.lm, g.perm, 1), s))) return st;
+  } else {
+    if ((st = g.d_t.upload(gather(g.t, g.perm, 1), s))) return st;
+    if ((st = g.d_y.upload(gather(g.y, g.perm, 3), s))) return st;
+  }
+  KTK_CUDA(cudaStreamSynchronize(s));   // the gathered host vectors are temporaries
+  g.uploaded = true;
+  return KTK_OK;
+}
+
+int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) {
+  if (!p) return fail(KTK_EINVAL, "problem is NULL");
+  int st = check_sensor(imu); if (st) return st;
+  if (n < 0 || (n > 0 && (!t || !y))) return fail(KTK_EINVAL, "bad measurement arrays");
+  if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
+  Group* g = new Group; g->kind = kind; g->n = n; g->sensor = *imu;
+  g->t.assign(t, t + n); g->y.assign(y, y + 3 * n);
+  if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
+  p->groups.push_back(g);
+  return (int)p->groups.size() - 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ktk_last_error(void) { return g_err.c_str(); }
+
+int ktk_problem_create(int device, ktk_problem** out) {
+  if (!out) return fail(KTK_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (device < 0) { ktk_problem* hp = new ktk_problem; hp->device = -1; *out = hp; return KTK_OK; }   // structure queries only
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(KTK_ECUDA, std::string("no CUDA device (kontiki_b200 has no CPU path): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(KTK_EINVAL, "device index out of range");
+  KTK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KTK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(KTK_ECUDA, std::string("kontiki_b200 is built for sm_100a only; device is ") + prop.name);
+  ktk_problem* p = new ktk_problem; p->device = device;
+  int st = p->d_err.resize(1);
+  if (st) { delete p; return st; }
+  if (cudaHostAlloc(&p->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { delete p; return fail(KTK_ECUDA, "cudaHostAlloc failed"); }
+  // opt in to the shared-memory carve-out the row staging needs
+  cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kCamRowStride * 8);
+  *out = p;
+  return KTK_OK;
+}
+
+void ktk_problem_destroy(ktk_problem* p) { if (p) { if (p->device >= 0) cudaSetDevice(p->device); delete p; } }
+
+int ktk_set_stream(ktk_problem* p, void* s) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->stream = (cudaStream_t)s; return KTK_OK; }
+
+int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, int32_t compat) {
+  if (!p) return fail(KTK_EINVAL, "problem is NULL");
+  if (!(dt > 0.0)) return fail(KTK_EINVAL, "dt must be positive");
+  if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
+  p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
+  p->have_spline = true;
+  for (auto g : p->groups) g->uploaded = false;   // the sort key depends on (t0, dt)
+  return KTK_OK;
+}
+
+int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_GYROSCOPE, imu, n, t, y, w); }
+int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_ACCELEROMETER, imu, n, t, y, w); }
+
+int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
+                      const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
+  if (!p) return fail(KTK_EINVAL, "problem is NULL");
+  if (!cam) return fail(KTK_EINVAL, "camera is NULL");
+  int st = check_sensor(&cam->base); if (st) return st;
+  if (cam->rows <= 0 || cam->cols <= 0) return fail(KTK_EINVAL, "camera rows/cols must be positive");
+  if (n < 0 || (n > 0 && (!obs_uv || !obs_t0 || !ref_uv || !ref_t0 || !lm_idx))) return fail(KTK_EINVAL, "bad measurement arrays");
+  if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
+  Group* g = new Group; g->kind = KTK_STATIC_RS; g->n = n; g->cam = *cam; g->sensor = cam->base;
+  g->obs_uv.assign(obs_uv, obs_uv + 2 * n); g->obs_t0.assign(obs_t0, obs_t0 + n);
+  g->ref_uv.assign(ref_uv, ref_uv + 2 * n); g->ref_t0.assign(ref_t0, ref_t0 + n);
+  g->lm.assign(lm_idx, lm_idx + n);
+  for (int l : g->lm) { g->lm_max = std::max(g->lm_max, l); g->lm_min = std::min(g->lm_min, l); }
+  if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
+  if (huber_c) g->huber.assign(huber_c, huber_c + n); else g->huber.assign((size_t)n, 5.0);
+  p->groups.push_back(g);
+  return (int)p->groups.size() - 1;
+}
+
+int32_t ktk_num_groups(const ktk_problem* p) { return p ? (int32_t)p->groups.size() : 0; }
+int64_t ktk_group_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->n : -1; }
+int32_t ktk_group_kind(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->kind : -1; }
+int64_t ktk_launch_count(const ktk_problem* p) { return p ? p->launches : 0; }
+
+int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs) {
+  if (!p || !d_knots || !outs) return fail(KTK_EINVAL, "NULL argument");
+  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
+  if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device (structure queries only); there is no CPU evaluation path");
+  KTK_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  int st;
+  for (auto g : p->groups) {
+    if ((st = upload_group(p, *g))) return st;
+    if (g->kind == KTK_STATIC_RS) {
+      if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
+      if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
+    }
+  }
+  const int nk = p->sp.n_knots;
+  if ((st = p->d_knots8.resize((size_t)nk * kKnotStride))) return st;
+  if ((st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
+  KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
+  k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(d_knots, nk, p->d_knots8.p);
+  k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
+  p->launches += 2;
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    if (g.n == 0) continue;
+    const ktk_group_out& o = outs[gi];
+    const int blocks = (int)((g.n + kThreads - 1) / kThreads);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
+    if (g.kind == KTK_STATIC_RS) {
+      CamArgs a;
+      a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
+      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
+      a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
+      a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+      a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
+      k_static_rs<<<blocks, kThreads, kThreads * kCamRowStride * 8, s>>>(a);
+    } else {
+      ImuArgs a;
+      a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
+      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
+      a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+      a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
+      if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
+      else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
+    }
+    if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
+    p->launches += 1;
+  }
+  KTK_CUDA(cudaGetLastError());
+  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  return KTK_OK;
+}
+
+int ktk_synchronize(ktk_problem* p) {
+  if (!p) return fail(KTK_EINVAL, "problem is NULL");
+  if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
+  KTK_CUDA(cudaSetDevice(p->device));
+  KTK_CUDA(cudaStreamSynchronize(p->stream));
+  const int e = *p->h_err;
+  if (e == kStatusRange) return fail(KTK_ERANGE, "a measurement time is out of range for the trajectory (its output rows are NaN)");
+  if (e != 0) return fail(KTK_ERUNTIME, "device-side evaluation error");
+  return KTK_OK;
+}
+
+int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs) {
+  if (!p || !knots || !outs) return fail(KTK_EINVAL, "NULL argument");
+  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
+  if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device (structure queries only); there is no CPU evaluation path");
+  KTK_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  int st;
+  if ((st = p->d_knots7.resize((size_t)p->sp.n_knots * 7))) return st;
+  KTK_CUDA(cudaMemcpyAsync(p->d_knots7.p, knots, (size_t)p->sp.n_knots * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (rho && n_rho > 0) {
+    if ((st = p->d_rho.resize((size_t)n_rho))) return st;
+    KTK_CUDA(cudaMemcpyAsync(p->d_rho.p, rho, (size_t)n_rho * sizeof(double), cudaMemcpyHostToDevice, s));
+  }
+  std::vector<ktk_group_out> dev(p->groups.size());
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    const ktk_group_out& o = outs[gi];
+    const bool cam = g.kind == KTK_STATIC_RS;
+    dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr};
+    if (o.r) { if ((st = g.o_r.resize((size_t)g.n * (cam ? 2 : 3)))) return st; dev[gi].r = g.o_r.p; }
+    if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize((size_t)g.n * (cam ? kCamRow : kImuRow)))) return st; dev[gi].J = g.o_J.p; }
+    if (o.i0) { if ((st = g.o_i0.resize((size_t)g.n))) return st; dev[gi].i0 = g.o_i0.p; }
+    if (o.i0_b && cam) { if ((st = g.o_i0b.resize((size_t)g.n))) return st; dev[gi].i0_b = g.o_i0b.p; }
+  }
+  if ((st = ktk_evaluate_device(p, p->d_knots7.p, (rho && n_rho > 0) ? p->d_rho.p : nullptr, n_rho, flags, dev.data()))) return st;
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    const ktk_group_out& o = outs[gi];
+    const bool cam = g.kind == KTK_STATIC_RS;
+    if (dev[gi].r) KTK_CUDA(cudaMemcpyAsync(o.r, dev[gi].r, (size_t)g.n * (cam ? 2 : 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, (size_t)g.n * (cam ? kCamRow : kImuRow) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0) KTK_CUDA(cudaMemcpyAsync(o.i0, dev[gi].i0, (size_t)g.n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0_b) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, (size_t)g.n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
+  return ktk_synchronize(p);
+}
+
+int ktk_set_profiling(ktk_problem* p, int32_t on) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->profiling = on != 0; return KTK_OK; }
+
+int ktk_read_profile(ktk_problem* p, int32_t group, double* total_ms, int64_t* launches) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !total_ms || !launches) return fail(KTK_EINVAL, "bad argument");
+  KTK_CUDA(cudaSetDevice(p->device));
+  KTK_CUDA(cudaStreamSynchronize(p->stream));
+  Group& g = *p->groups[group];
+  double sum = 0.0;
+  for (auto& e : g.prof) { float ms = 0.f; KTK_CUDA(cudaEventElapsedTime(&ms, e.first, e.second)); sum += ms; cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  *total_ms = sum; *launches = (int64_t)g.prof.size();
+  g.prof.clear();
+  return KTK_OK;
+}
+
+void* ktk_host_alloc(int64_t bytes) { void* ptr = nullptr; if (cudaHostAlloc(&ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) { g_err = "cudaHostAlloc failed"; return nullptr; } return ptr; }
+void ktk_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// ---- structure (host only) ---------------------------------------------------------------------------------------
+// *Measurement::AddToEstimator -> TrajectoryEstimator::AddTrajectoryForTimes -> SplineEntity::AddToProblem
+// (gyroscope_measurement.h:82-92, static_rscamera_measurement.h:137-168, spline_base.h:361-404)
+static int group_segments(const ktk_problem* p, const Group& g, int64_t i, Segment& s0, Segment& s1) {
+  const SplineConst& sp = p->sp;
+  const double tmax = spline_max_time(sp);
+  if (g.kind == KTK_STATIC_RS) {
+    double t1, t2;
+    if (g.ref_t0[i] <= g.obs_t0[i]) { t1 = g.ref_t0[i]; t2 = g.obs_t0[i]; } else { t1 = g.obs_t0[i]; t2 = g.ref_t0[i]; }
+    if (!g.sensor.time_offset_locked) { t1 -= g.sensor.max_time_offset; t2 += g.sensor.max_time_offset; }
+    const double margin = 1e-3;
+    const double a1 = t1 - margin, b1 = t1 + g.cam.readout + margin, a2 = t2 - margin, b2 = t2 + g.cam.readout + margin;
+    if (!(a1 >= sp.t0) || !(b1 < tmax) || !(a2 >= sp.t0) || !(b2 < tmax) || a1 > b1 || a2 > b2 || a2 < a1) return 0;
+    return segments_two_spans(a1, b1, a2, b2, sp.t0, sp.dt, s0, s1);
+  }
+  double ta = g.t[i], tb = g.t[i];
+  if (!g.sensor.time_offset_locked) { ta -= g.sensor.max_time_offset; tb += g.sensor.max_time_offset; }
+  if (!(ta >= sp.t0) || !(tb < tmax)) return 0;
+  segments_one_span(ta, tb, sp.t0, sp.dt, s0);
+  return 1;
+}
+
+int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !knot_ids || !n_ids) return fail(KTK_EINVAL, "bad argument");
+  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called first");
+  const Group& g = *p->groups[group];
+  int worst = KTK_OK;
+  for (int64_t i = 0; i < g.n; ++i) {
+    Segment s0{0, 0}, s1{0, 0};
+    const int nseg = group_segments(p, g, i, s0, s1);
+    int32_t* ids = knot_ids + (size_t)i * cap;
+    for (int c = 0; c < cap; ++c) ids[c] = -1;
+    if (nseg == 0) { n_ids[i] = 0; worst = KTK_ERANGE; continue; }
+    const int total = s0.n + (nseg == 2 ? s1.n : 0);
+    if (total > cap) return fail(KTK_EINVAL, "cap too small for the knot blocks of a residual");
+    int c = 0;
+    for (int k = 0; k < s0.n; ++k) ids[c++] = s0.start + k;
+    if (nseg == 2) for (int k = 0; k < s1.n; ++k) ids[c++] = s1.start + k;
+    n_ids[i] = total;
+  }
+  if (worst == KTK_ERANGE) return fail(KTK_ERANGE, "Time span out of range for trajectory");
+  return KTK_OK;
+}
+
+int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const int32_t* knot_ids, const double* Jp, const int32_t* i0r,
+                         const int32_t* i0o, double* out) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !knot_ids || !Jp || !i0r || !i0o || !out) return fail(KTK_EINVAL, "bad argument");
+  const Group& g = *p->groups[group];
+  if (g.kind != KTK_STATIC_RS) return fail(KTK_EINVAL, "not a static-RS group");
+  std::memset(out, 0, sizeof(double) * (size_t)g.n * cap * 14);
+  for (int64_t i = 0; i < g.n; ++i) {
+    const int32_t* ids = knot_ids + (size_t)i * cap;
+    for (int w = 0; w < 2; ++w) {
+      const int base = w == 0 ? i0r[i] : i0o[i];
+      for (int k = 0; k < 4; ++k) {
+        int pos = -1;
+        for (int c = 0; c < cap && ids[c] >= 0; ++c) if (ids[c] == base + k) { pos = c; break; }
+        if (pos < 0) return fail(KTK_EINVAL, "active knot not in the structural block list");
+        const double* src = Jp + (size_t)i * kCamRow + w * 56 + k * 14;
+        double* dst = out + ((size_t)i * cap + pos) * 14;
+        for (int c = 0; c < 14; ++c) dst[c] += src[c];
+      }
+    }
+  }
+  return KTK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+// TEST HARNESS ONLY (built by tests/hostcheck.py into tests/_build/libhostcheck.so, never shipped, never loaded by
+// kontiki_b200/).  Compiles the __host__ __device__ mathematics of kontiki_b200/csrc/spline_math.cuh for the host so
+// that the CPU-only test suite can compare the exact text the CUDA kernels execute against the CPU oracle.
+#include <cstddef>
+#include <vector>
+
+#include "../kontiki_b200/csrc/spline_math.cuh"
+
+using namespace kb;
+
+extern "C" {
+
+// knots7: n x 7 (reference layout) -> padded records + pair records (what ktk_evaluate's pack + K0 do on the device)
+void hc_prepass(const double* knots7, int n, double* knots8, double* pairs) {
+  for (int i = 0; i < n; ++i) { for (int c = 0; c < 7; ++c) knots8[(size_t)i * kKnotStride + c] = knots7[(size_t)i * 7 + c]; knots8[(size_t)i * kKnotStride + 7] = 0.0; }
+  for (int c = 0; c < kPairStride; ++c) pairs[c] = 0.0;
+  for (int p = 1; p < n; ++p) for (int dir = 0; dir <= 14; ++dir) pair_prepass_item(knots8, p, dir, pairs);
+}
+
+void hc_imu(int which, double t0, double dt, int n_knots, int compat, double time_offset, double max_time_offset, int locked,
+            const double* knots8, const double* pairs, int n, const double* t, const double* y, const double* w, double* r, double* J,
+            int* i0, int* status) {
+  SplineConst sp{t0, dt, n_knots, compat};
+  ImuConst imu{time_offset, max_time_offset, locked};
+  for (int i = 0; i < n; ++i) {
+    i0[i] = -1;
+    status[i] = imu_row(which, sp, imu, knots8, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)84 * i, i0 + i);
+  }
+}
+
+void hc_static_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
+                  double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
+                  const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
+                  const int* lm_idx, const double* rho, const double* w, const double* huber_c, double* r, double* J, int* i0_ref,
+                  int* i0_obs, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
+  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  for (int i = 0; i < n; ++i) {
+    i0_ref[i] = -1; i0_obs[i] = -1;
+    status[i] = static_rs_row(sp, cam, knots8, pairs, obs_uv + 2 * i, obs_t0[i], ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], w[i],
+                              huber_c ? huber_c[i] : 0.0, r + 2 * i, J + (size_t)114 * i, i0_ref + i, i0_obs + i);
+  }
+}
+
+}  // extern "C"

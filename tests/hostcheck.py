@@ -1,0 +1,85 @@
+"""Builds and binds tests/host_check.cpp: the product's __host__ __device__ mathematics compiled for the host.
+
+TEST HARNESS ONLY -- lets the CPU-only suite (-m "not gpu") compare the exact formulas the CUDA kernels run with
+the oracle.  The product package never loads this library.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "host_check.cpp")
+_CSRC = os.path.join(os.path.dirname(_HERE), "kontiki_b200", "csrc")
+_OUT = os.path.join(_HERE, "_build", "libhostcheck.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "lie_math.cuh", "dualnum.cuh")]
+        if not os.path.exists(_OUT) or any(os.path.getmtime(d) > os.path.getmtime(_OUT) for d in deps):
+            os.makedirs(os.path.dirname(_OUT), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", _SRC, "-o", _OUT])
+        _lib = C.CDLL(_OUT)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def prepass(knots7):
+    knots7 = _f(knots7)
+    n = len(knots7)
+    k8, pairs = np.zeros((n, 8)), np.zeros((n, 92))
+    lib().hc_prepass(_p(knots7), n, _p(k8), _p(pairs))
+    return k8, pairs
+
+
+def imu(which, knots7, dt, t0, t, y, w=None, compat=False, time_offset=0.0, max_time_offset=0.1, locked=True):
+    k8, pairs = prepass(knots7)
+    t, y = _f(t), _f(y).reshape(-1, 3)
+    n = len(t)
+    w = np.ones(n) if w is None else _f(w)
+    r, J = np.zeros((n, 3)), np.zeros((n, 4, 3, 7))
+    i0, st = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().hc_imu(int(which), C.c_double(t0), C.c_double(dt), len(k8), int(compat), C.c_double(time_offset), C.c_double(max_time_offset),
+                 int(locked), _p(k8), _p(pairs), n, _p(t), _p(y), _p(w), _p(r), _p(J), _p(i0), _p(st))
+    return dict(r=r, J=J, i0=i0, status=st)
+
+
+def kinv_cofactor(K):
+    """pinhole_camera.h:63-67 inverts K per call (Eigen fixed 3x3 inverse = cofactors / determinant)."""
+    a = np.asarray(K, float).reshape(3, 3)
+    c = np.empty((3, 3))
+    c[0, 0] = a[1, 1] * a[2, 2] - a[1, 2] * a[2, 1]; c[0, 1] = a[0, 2] * a[2, 1] - a[0, 1] * a[2, 2]; c[0, 2] = a[0, 1] * a[1, 2] - a[0, 2] * a[1, 1]
+    c[1, 0] = a[1, 2] * a[2, 0] - a[1, 0] * a[2, 2]; c[1, 1] = a[0, 0] * a[2, 2] - a[0, 2] * a[2, 0]; c[1, 2] = a[0, 2] * a[1, 0] - a[0, 0] * a[1, 2]
+    c[2, 0] = a[1, 0] * a[2, 1] - a[1, 1] * a[2, 0]; c[2, 1] = a[0, 1] * a[2, 0] - a[0, 0] * a[2, 1]; c[2, 2] = a[0, 0] * a[1, 1] - a[0, 1] * a[1, 0]
+    det = a[0, 0] * c[0, 0] + a[0, 1] * c[1, 0] + a[0, 2] * c[2, 0]
+    return c / det
+
+
+def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    """cam: oracle.kto.Camera-like (K, q_ct, p_ct, time_offset, max_time_offset, d_locked, readout, rows)."""
+    k8, pairs = prepass(knots7)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    r, J = np.zeros((n, 2)), np.zeros((n, 114))
+    ir, io, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().hc_static_rs(C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset),
+                       C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows), _p(k8), _p(pairs), n,
+                       _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc), _p(r), _p(J), _p(ir), _p(io), _p(st))
+    return dict(r=r, J=J, i0_ref=ir, i0_obs=io, status=st)

@@ -1,0 +1,192 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs;
+plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import fixtures_ref as fx
+import parity
+from kontiki_b200 import _lib, synthetic as syn
+from oracle import kto
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(cfg, compat=False):
+    p = _lib.Problem(0)
+    p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]), compat_zero_dB=compat)
+    groups = {}
+    imu = _lib.make_sensor()
+    if cfg["gyro"]:
+        groups["gyro"] = p.add_gyroscope(imu, cfg["gyro"]["t"], cfg["gyro"]["y"], cfg["gyro"]["weight"])
+    if cfg["accel"]:
+        groups["accel"] = p.add_accelerometer(imu, cfg["accel"]["t"], cfg["accel"]["y"], cfg["accel"]["weight"])
+    if cfg["cam"]:
+        c = cfg["cam"]
+        cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], q_ct=c.get("q_ct", (0, 0, 0, 1)), p_ct=c.get("p_ct", (0, 0, 0)))
+        groups["cam"] = p.add_static_rs(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
+    return p, groups
+
+
+def _check_imu(out, o):
+    assert (out["i0"] == o["i0"]).all()                               # bit-exact indexing
+    assert parity.rel_err(out["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(out["J"], o["J"]) < parity.TOL
+
+
+def _check_cam(p, g, out, cfg, robust):
+    c = cfg["cam"]
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], q_ct=c.get("q_ct", (0, 0, 0, 1)), p_ct=c.get("p_ct", (0, 0, 0)))
+    o = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=2, cap=24)
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_b"] == o["i0_obs_a"]).all()
+    ids, nids = p.get_structure(g, cap=24)
+    assert (ids == o["ids_a"]).all()
+    Js = p.expand_static_rs(g, ids, out["J"], out["i0"], out["i0_b"])
+    Jrho = out["J"][:, 112:114]
+    if not robust:
+        assert np.abs(out["r"] - o["r"]).max() < parity.TOL * 1e3
+        assert parity.rel_err(Js, o["Ja"]) < parity.TOL
+        assert parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+        return
+    for i in range(len(c["lm_idx"])):
+        m = int(nids[i])
+        Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+        _, r2, J2 = kto.huber_correct(c["huber_c"][i], o["r"][i], Jfull)
+        Jmine = np.concatenate([Js[i, k] for k in range(m)] + [Jrho[i].reshape(2, 1)], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(out["r"][i] - r2).max() <= parity.TOL * 1e3
+
+
+def test_c1_gyro_matches_oracle():
+    """BASELINE.json configs[0]: SE3, 200 knots, 5k gyroscope measurements."""
+    cfg = syn.make_config("C1")
+    p, g = _problem(cfg)
+    outs = p.evaluate(cfg["knots"])
+    o = parity.oracle_imu(kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"]), 0, cfg["gyro"]["t"], cfg["gyro"]["y"], cfg["gyro"]["weight"])
+    _check_imu(outs[g["gyro"]], o)
+
+
+@pytest.mark.parametrize("compat", [False, True])
+def test_c2_scaled_gyro_accel_match_oracle(compat):
+    cfg = syn.make_config("C2", scale=0.05)
+    rng = np.random.default_rng(12)
+    cfg["gyro"]["weight"] = rng.uniform(0.5, 2, len(cfg["gyro"]["t"]))
+    cfg["accel"]["weight"] = rng.uniform(0.5, 2, len(cfg["accel"]["t"]))
+    p, g = _problem(cfg, compat)
+    outs = p.evaluate(cfg["knots"])
+    traj = kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"], compat_zero_dB=compat)
+    _check_imu(outs[g["gyro"]], parity.oracle_imu(traj, 0, cfg["gyro"]["t"], cfg["gyro"]["y"], cfg["gyro"]["weight"]))
+    _check_imu(outs[g["accel"]], parity.oracle_imu(traj, 1, cfg["accel"]["t"], cfg["accel"]["y"], cfg["accel"]["weight"]))
+
+
+def test_reference_fixture_knots():
+    """The reference's SE3 fixture (python/tests/conftest.py:83-105): large relative rotations between knots."""
+    t = np.linspace(fx.SE3_T0, fx.SE3_T0 + 3 * fx.SE3_DT - 1e-9, 257)
+    y = np.random.default_rng(3).uniform(-1, 1, (257, 3))
+    cfg = dict(knots=fx.SE3_KNOTS, dt=fx.SE3_DT, t0=fx.SE3_T0, gyro=dict(t=t, y=y, weight=np.ones(257)), accel=dict(t=t, y=y, weight=np.ones(257)), cam=None)
+    p, g = _problem(cfg)
+    outs = p.evaluate(cfg["knots"])
+    traj = kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS)
+    _check_imu(outs[g["gyro"]], parity.oracle_imu(traj, 0, t, y))
+    _check_imu(outs[g["accel"]], parity.oracle_imu(traj, 1, t, y))
+
+
+@pytest.mark.parametrize("robust", [False, True])
+@pytest.mark.parametrize("rel_pose", [False, True])
+def test_h1_scaled_matches_oracle(robust, rel_pose):
+    """North-star problem (C3 + IMU) at 1/100 scale: 5k static-RS + 1k IMU rows, with gross outliers for the Huber branch."""
+    cfg = syn.make_config("H1", scale=0.01)
+    c = cfg["cam"]
+    rng = np.random.default_rng(21)
+    out = rng.random(len(c["lm_idx"])) < 0.2
+    c["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    c["weight"] = rng.uniform(0.5, 2, len(c["lm_idx"]))
+    if rel_pose:
+        c["q_ct"] = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05]))
+        c["p_ct"] = np.array([0.05, -0.02, 0.1])
+    p, g = _problem(cfg)
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    outs = p.evaluate(cfg["knots"], c["rho"], flags)
+    traj = kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"])
+    _check_imu(outs[g["gyro"]], parity.oracle_imu(traj, 0, cfg["gyro"]["t"], cfg["gyro"]["y"]))
+    _check_imu(outs[g["accel"]], parity.oracle_imu(traj, 1, cfg["accel"]["t"], cfg["accel"]["y"]))
+    _check_cam(p, g["cam"], outs[g["cam"]], cfg, robust)
+
+
+def test_out_of_range_is_an_error_not_garbage():
+    cfg = syn.make_config("C1", scale=0.01)
+    cfg["gyro"]["t"][7] = 19.71                 # valid time is [0, 19.7)
+    p, g = _problem(cfg)
+    with pytest.raises(ValueError):
+        p.evaluate(cfg["knots"])
+
+
+def test_empty_and_ragged_groups():
+    cfg = syn.make_config("C1", scale=0.0134)   # 67 rows: one full CTA + a ragged tail
+    p = _lib.Problem(0)
+    p.set_se3_spline(cfg["dt"], 0.0, len(cfg["knots"]))
+    imu = _lib.make_sensor()
+    g0 = p.add_gyroscope(imu, np.zeros(0), np.zeros((0, 3)))
+    g1 = p.add_gyroscope(imu, cfg["gyro"]["t"], cfg["gyro"]["y"])
+    outs = p.evaluate(cfg["knots"])
+    assert outs[g0]["r"].shape == (0, 3)
+    o = parity.oracle_imu(kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"]), 0, cfg["gyro"]["t"], cfg["gyro"]["y"])
+    _check_imu(outs[g1], o)
+
+
+def test_full_size_properties_h1():
+    """At full H1 size (600k rows) the oracle is too slow; use size-independent properties:
+    (1) rows are independent of the batch they are evaluated in and of its order (a random 2k subset evaluated alone, in
+        shuffled order, gives bit-identical rows), (2) that subset matches the oracle, (3) residuals scale linearly with
+        the weight (reference test_measurements.py:73-89), (4) J is the derivative of r: r(x + h d) - r(x - h d) ~ 2h J d."""
+    cfg = syn.make_config("H1")
+    c = cfg["cam"]
+    p, g = _problem(cfg)
+    outs = p.evaluate(cfg["knots"], c["rho"])
+    assert all(np.isfinite(o["r"]).all() and np.isfinite(o["J"]).all() for o in outs)
+    rng = np.random.default_rng(5)
+    # (1) + (2): subsets
+    sel = rng.permutation(len(cfg["gyro"]["t"]))[:2000]
+    sub = dict(cfg, gyro={k: v[sel] for k, v in cfg["gyro"].items()}, accel={k: v[sel] for k, v in cfg["accel"].items()}, cam=None)
+    p2, g2 = _problem(sub)
+    outs2 = p2.evaluate(cfg["knots"])
+    for name in ("gyro", "accel"):
+        assert np.array_equal(outs2[g2[name]]["r"], outs[g[name]]["r"][sel])
+        assert np.array_equal(outs2[g2[name]]["J"], outs[g[name]]["J"][sel])
+        assert np.array_equal(outs2[g2[name]]["i0"], outs[g[name]]["i0"][sel])
+    traj = kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"])
+    _check_imu(outs2[g2["gyro"]], parity.oracle_imu(traj, 0, sub["gyro"]["t"], sub["gyro"]["y"]))
+    _check_imu(outs2[g2["accel"]], parity.oracle_imu(traj, 1, sub["accel"]["t"], sub["accel"]["y"]))
+    csel = rng.permutation(len(c["lm_idx"]))[:3000]
+    csub = dict(c, **{k: c[k][csel] for k in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "weight", "huber_c")})
+    sub = dict(cfg, gyro=None, accel=None, cam=csub)
+    p3, g3 = _problem(sub)
+    outs3 = p3.evaluate(cfg["knots"], c["rho"])
+    for k in ("r", "J", "i0", "i0_b"):
+        assert np.array_equal(outs3[g3["cam"]][k], outs[g["cam"]][k][csel])
+    _check_cam(p3, g3["cam"], outs3[g3["cam"]], sub, robust=False)
+    # (3) weight linearity, exact in fp64 for a power-of-two factor
+    cfg4 = dict(cfg, gyro=dict(cfg["gyro"], weight=cfg["gyro"]["weight"] * 4.0), accel=None, cam=dict(c, weight=c["weight"] * 0.5))
+    p4, g4 = _problem(cfg4)
+    outs4 = p4.evaluate(cfg["knots"], c["rho"])
+    assert np.array_equal(outs4[g4["gyro"]]["r"], 4.0 * outs[g["gyro"]]["r"])
+    assert np.array_equal(outs4[g4["cam"]]["r"], 0.5 * outs[g["cam"]]["r"])
+    # (4) directional derivative along a random tangent-space direction of all knots and all rho
+    h = 1e-6
+    d = rng.normal(0, 1, cfg["knots"].shape)
+    drho = rng.normal(0, 1, c["rho"].shape) * c["rho"]
+    op = p.evaluate(cfg["knots"] + h * d, c["rho"] + h * drho, _lib.EVAL_RESIDUALS)
+    om = p.evaluate(cfg["knots"] - h * d, c["rho"] - h * drho, _lib.EVAL_RESIDUALS)
+    for name in ("gyro", "accel"):
+        o = outs[g[name]]
+        idx = o["i0"][:, None] + np.arange(4)[None, :]
+        Jd = np.einsum("nkrc,nkc->nr", o["J"], d[idx])
+        num = (op[g[name]]["r"] - om[g[name]]["r"]) / (2 * h)
+        assert np.abs(Jd - num).max() < 1e-5 * max(1.0, np.abs(num).max())
+    o = outs[g["cam"]]
+    Jr = o["J"][:, :56].reshape(-1, 4, 2, 7)
+    Jo = o["J"][:, 56:112].reshape(-1, 4, 2, 7)
+    Jd = np.einsum("nkrc,nkc->nr", Jr, d[o["i0"][:, None] + np.arange(4)]) + np.einsum("nkrc,nkc->nr", Jo, d[o["i0_b"][:, None] + np.arange(4)])
+    Jd += o["J"][:, 112:114] * drho[c["lm_idx"]][:, None]
+    num = (op[g["cam"]]["r"] - om[g["cam"]]["r"]) / (2 * h)
+    assert np.abs(Jd - num).max() < 1e-5 * max(1.0, np.abs(num).max())

@@ -1,0 +1,105 @@
+"""The product's __host__ __device__ mathematics (kontiki_b200/csrc/spline_math.cuh -- the text the CUDA kernels execute),
+compiled for the host by tests/hostcheck.py, against the CPU oracle.  Runs without a GPU; the same comparisons are
+repeated through the C ABI on the device in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import fixtures_ref as fx
+import hostcheck as hc
+import parity
+from kontiki_b200 import synthetic as syn
+from oracle import kto
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("compat", [False, True])
+def test_imu_rows_match_oracle(which, compat):
+    knots = fx.smooth_se3_knots(60, 0.1)
+    rng = np.random.default_rng(which)
+    t = rng.uniform(0.0, 5.69, 300)
+    y, w = rng.uniform(-1, 1, (300, 3)), rng.uniform(0.5, 2, 300)
+    o = parity.oracle_imu(kto.Traj(kto.SE3, 0.1, 0.0, knots, compat_zero_dB=compat), which, t, y, w)
+    h = hc.imu(which, knots, 0.1, 0.0, t, y, w, compat=compat)
+    assert (h["status"] == 0).all()
+    assert (h["i0"] == o["i0"]).all()
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(h["J"], o["J"]) < parity.TOL
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_imu_rows_reference_fixture(which):
+    """The reference's own SE3 fixture (python/tests/conftest.py:83-105): large relative rotations between knots."""
+    t = np.linspace(fx.SE3_T0, fx.SE3_T0 + 3 * fx.SE3_DT - 1e-9, 64)
+    y = np.random.default_rng(3).uniform(-1, 1, (64, 3))
+    o = parity.oracle_imu(kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS), which, t, y)
+    h = hc.imu(which, fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t, y)
+    assert (h["i0"] == o["i0"]).all()
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(h["J"], o["J"]) < parity.TOL
+
+
+def test_imu_out_of_range_status():
+    knots = fx.smooth_se3_knots(20, 0.1)
+    h = hc.imu(0, knots, 0.1, 0.0, [-0.01, 1.71, 1.6999], np.zeros((3, 3)))
+    assert list(h["status"]) == [-1, -1, 0]
+    with pytest.raises(kto.OracleError):
+        kto.imu_residuals(kto.Traj(kto.SE3, 0.1, 0.0, knots), kto.Sensor(), 0, [1.71], np.zeros((1, 3)))
+
+
+def _camera_case(dt, seed, q_ct=None, p_ct=None, n_lm=40):
+    knots = syn.smooth_se3_knots(150, dt)
+    s = syn.make_static_rs(knots, dt, n_lm, obs_per_landmark=6, seed=seed, noise_px=1.0)
+    rng = np.random.default_rng(seed)
+    out = rng.random(len(s["lm_idx"])) < 0.2           # 20 % gross outliers: beyond the Huber threshold
+    s["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    s["weight"] = rng.uniform(0.5, 2, len(s["lm_idx"]))
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], q_ct=(0, 0, 0, 1) if q_ct is None else q_ct, p_ct=(0, 0, 0) if p_ct is None else p_ct)
+    return knots, s, cam
+
+
+@pytest.mark.parametrize("dt", [0.02, 0.1])
+@pytest.mark.parametrize("rel_pose", [False, True])
+def test_static_rs_rows_match_oracle(dt, rel_pose):
+    q_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])) if rel_pose else None
+    p_ct = np.array([0.05, -0.02, 0.1]) if rel_pose else None
+    knots, s, cam = _camera_case(dt, 5, q_ct, p_ct)
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    h = hc.static_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
+    assert (h["status"] == 0).all()
+    assert (h["i0_ref"] == o["i0_ref_a"]).all() and (h["i0_obs"] == o["i0_obs_a"]).all()
+    # residuals are differences of ~1e3 px coordinates: tolerance relative to the pixel scale, Jacobians to their block norm
+    assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+    Js, Jrho = parity.scatter_cam(h["J"], h["i0_ref"], h["i0_obs"], o["ids_a"])
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL
+    assert parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+
+
+def test_static_rs_huber_corrector_matches_oracle():
+    dt = 0.05
+    knots, s, cam = _camera_case(dt, 9)
+    n = len(s["lm_idx"])
+    c = np.full(n, 5.0)
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    h = hc.static_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], huber_c=c)
+    n_out = 0
+    for i in range(n):
+        m = int((o["ids_a"][i] >= 0).sum())
+        Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+        _, r2, J2 = kto.huber_correct(5.0, o["r"][i], Jfull)
+        Js, Jr = parity.scatter_cam(h["J"][i:i + 1], h["i0_ref"][i:i + 1], h["i0_obs"][i:i + 1], o["ids_a"][i:i + 1])
+        Jmine = np.concatenate([Js[0, k] for k in range(m)] + [Jr[0].reshape(2, 1)], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(h["r"][i] - r2).max() <= parity.TOL * 1e3
+        n_out += np.linalg.norm(o["r"][i]) > 5.0
+    assert 5 < n_out < n - 5          # both branches of the loss exercised
+
+
+def test_pair_prepass_small_angle_branch():
+    """Identical adjacent knots: log hits Sophus' small-angle branches; values and derivatives must stay finite."""
+    k = np.tile(np.array([0.1, -0.2, 0.3, 0.0, 1.0, 2.0, 3.0]), (6, 1))
+    k[:, 3] = np.sqrt(1 - (k[0, :3] ** 2).sum())
+    k8, pairs = hc.prepass(k)
+    assert np.isfinite(pairs).all()
+    assert np.abs(pairs[1:, :6]).max() < 1e-15
