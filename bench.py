@@ -242,6 +242,7 @@ def main():
             step_device()
         e1.record(stream)
         barrier()
+        launches = p.launch_count - l0
         ms_total = e0.elapsed_time(e1)
         if a.steps * (ms_total / max(a.steps, 1)) < 1500.0:      # keep the GPU under load long enough for a few clock samples
             t_end = time.time() + 1.5
@@ -250,7 +251,6 @@ def main():
                 step_device()
                 torch.cuda.synchronize()
             p.set_profiling(True)
-    launches = p.launch_count - l0
     p.synchronize()
     prof = {name: p.read_profile(g) for name, g in groups.items()}
     p.set_profiling(False)

@@ -4,7 +4,9 @@
 //   k_pack_knots     n_knots x 7 (reference layout) -> 64-B knot records
 //   k_pair_prepass   K0: omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian, one thread per (pair, direction)
 //   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
-//   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1))
+//   k_landmark_ref   reference side of the static-RS rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
+//   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); each thread pulls its
+//                    landmark record into its row buffer with a TMA bulk load that overlaps the observation-pose math
 // Measurement records are sorted once (at add time) by their first active knot so that a warp touches one or two
 // knot windows; each thread builds its Jacobian row in shared memory and hands it to the TMA (cp.async.bulk
 // shared -> global) as ONE contiguous 672-B / 912-B store at the caller's row index, so rows come out in the caller's
@@ -17,6 +19,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kontiki_b200.h"
@@ -47,6 +50,32 @@ __device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc,
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---- TMA bulk load global -> shared, completion on an mbarrier ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_row(double* sdst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(sdst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+struct MbarWait {
+  unsigned long long* bar;
+  KB_HD void operator()() const {
+#if defined(__CUDA_ARCH__)
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(addr), "r"(0u) : "memory");
+    }
+#endif
+  }
+};
 
 __global__ void k_pack_knots(const double* __restrict__ k7, int n, double* __restrict__ k8) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,10 +121,33 @@ __global__ void __launch_bounds__(kThreads) k_imu(const ImuArgs a) {
   bulk_store_wait();
 }
 
-struct CamArgs {
+struct RefArgs {
   SplineConst sp; CameraConst cam;
   const double* knots; const double* pairs; const double* rho;
-  const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
+  const double* ref_uv; const double* ref_t0; const int* seg_start; const int* seg_n; const int* lm;
+  int n; double* recs; int* err;
+};
+
+__global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= a.n) return;
+  double* row = smem + threadIdx.x * kRefStride;
+  const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+  const int st = landmark_ref_row(a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.seg_start[i], a.seg_n[i], a.rho[a.lm[i]], row);
+  if (st != 0) {
+    atomicMin(a.err, st);
+    for (int c = 0; c < kRefStride; ++c) row[c] = nan("");
+    row[7] = -1.0;
+  }
+  bulk_store_row(a.recs + (size_t)i * kRefStride, row, kRefStride * 8);
+  bulk_store_wait();
+}
+
+struct CamArgs {
+  SplineConst sp; CameraConst cam;
+  const double* knots; const double* pairs; const double* recs;
+  const double* obs_uv; const double* obs_t0; const double* ref_t0; const int* ref_idx; const double* w; const double* huber;
   const int* perm;
   int n; uint32_t flags;
   double* r; double* J; int* i0r; int* i0o; int* err;
@@ -103,19 +155,29 @@ struct CamArgs {
 
 __global__ void __launch_bounds__(kThreads) k_static_rs(const CamArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int i = blockIdx.x * kThreads + threadIdx.x;
+  __shared__ __align__(8) unsigned long long bar;
+  const int base = blockIdx.x * kThreads;
+  const int i = base + threadIdx.x;
+  const int active = min(kThreads, a.n - base);
+  if (threadIdx.x == 0) mbar_init(&bar, active);
+  __syncthreads();
   if (i >= a.n) return;
   double* row = smem + threadIdx.x * kCamRowStride;
+  const int ridx = a.ref_idx[i];
+  mbar_arrive_expect_tx(&bar, ridx >= 0 ? kRefStride * 8 : 0);
+  if (ridx >= 0) bulk_load_row(row + kRefInRow, a.recs + (size_t)ridx * kRefStride, kRefStride * 8, &bar);
   const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
-  const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
   double r[2];
   int ir = -1, io = -1;
   const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
-  const int st = static_rs_row(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i], hub, r, row, &ir, &io);
+  int st = kStatusRange;
+  MbarWait wait{&bar};
+  if (ridx >= 0) st = static_rs_row(a.sp, a.cam, a.knots, a.pairs, row + kRefInRow, ouv, a.obs_t0[i], a.ref_t0[i], a.w[i], hub, r, row, &ir, &io, wait);
+  else wait();
   const size_t dst = (size_t)a.perm[i];
   if (st != 0) {
     atomicMin(a.err, st);
-    r[0] = r[1] = nan("");
+    r[0] = r[1] = nan(""); ir = io = -1;
     for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
   }
   if (a.J && (a.flags & KTK_EVAL_JACOBIANS)) bulk_store_row(a.J + dst * kCamRow, row, kCamRow * 8);
@@ -139,8 +201,12 @@ struct Group {
   // caller-order host copies (structure queries) and sorted device copies
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
-  DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_uv, d_ref_t0, d_huber;
-  DevBuf<int> d_lm, d_perm;
+  DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_t0, d_huber;
+  DevBuf<int> d_perm, d_ref_idx;
+  // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
+  int64_t n_ref = 0;
+  DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
+  DevBuf<int> d_rr_start, d_rr_n, d_rr_lm;
   // device-side outputs used by the host-buffer path
   DevBuf<double> o_r, o_J; DevBuf<int> o_i0, o_i0b;
   bool uploaded = false;
@@ -220,12 +286,48 @@ int upload_group(ktk_problem* p, Group& g) {
   if ((st = g.d_perm.upload(g.perm, s))) return st;
   if ((st = g.d_w.upload(gather(g.w, g.perm, 1), s))) return st;
   if (g.kind == KTK_STATIC_RS) {
+    // Landmark-reference table.  The reference evaluation of a residual happens in the segment (of that residual's two
+    // spans) that holds t_ref; its origin is what fixes (i0_ref, u_ref) bit-exactly.  Observations of one landmark
+    // share it whenever the reference view is the earlier one; otherwise they get their own record.
+    CameraConst cc; fill_camera_consts(g.cam, cc);
+    std::unordered_map<uint64_t, int> index;
+    std::vector<double> rr_uv, rr_t0; std::vector<int> rr_start, rr_n, rr_lm, ref_idx((size_t)g.n, -1);
+    for (int64_t i = 0; i < g.n; ++i) {
+      Segment s0{0, 0}, s1{0, 0};
+      const int nseg = static_rs_segments(sp, cc, g.ref_t0[i], g.obs_t0[i], s0, s1);
+      if (nseg == 0) continue;
+      int ir; double ur;
+      const int which = locate_in_segments(nseg, s0, s1, static_rs_time(cc, g.ref_t0[i], g.ref_uv[2 * i + 1]), sp.t0, sp.dt, ir, ur);
+      if (which < 0) continue;
+      const Segment& sr = which == 0 ? s0 : s1;
+      // two observations of a landmark always share (ref_uv, ref_t0): the landmark has ONE reference observation
+      const uint64_t key = ((uint64_t)(uint32_t)g.lm[i] << 32) | (uint32_t)sr.start;
+      auto it = index.find(key);
+      if (it == index.end()) {
+        it = index.emplace(key, (int)rr_lm.size()).first;
+        rr_uv.push_back(g.ref_uv[2 * i]); rr_uv.push_back(g.ref_uv[2 * i + 1]); rr_t0.push_back(g.ref_t0[i]);
+        rr_start.push_back(sr.start); rr_n.push_back(sr.n); rr_lm.push_back(g.lm[i]);
+      } else if (rr_uv[2 * it->second] != g.ref_uv[2 * i] || rr_uv[2 * it->second + 1] != g.ref_uv[2 * i + 1] || rr_t0[it->second] != g.ref_t0[i]) {
+        return fail(KTK_EINVAL, "observations of one landmark disagree on its reference observation");
+      }
+      ref_idx[i] = it->second;
+    }
+    // order the records by their first knot (locality of the pair table), remap
+    std::vector<int> rperm = sort_perm(rr_start), rinv(rperm.size());
+    for (size_t k = 0; k < rperm.size(); ++k) rinv[rperm[k]] = (int)k;
+    for (auto& v : ref_idx) if (v >= 0) v = rinv[v];
+    g.n_ref = (int64_t)rr_lm.size();
+    if ((st = g.d_rr_uv.upload(gather(rr_uv, rperm, 2), s))) return st;
+    if ((st = g.d_rr_t0.upload(gather(rr_t0, rperm, 1), s))) return st;
+    if ((st = g.d_rr_start.upload(gather(rr_start, rperm, 1), s))) return st;
+    if ((st = g.d_rr_n.upload(gather(rr_n, rperm, 1), s))) return st;
+    if ((st = g.d_rr_lm.upload(gather(rr_lm, rperm, 1), s))) return st;
+    if ((st = g.d_recs.resize((size_t)g.n_ref * kRefStride))) return st;
+    if ((st = g.d_ref_idx.upload(gather(ref_idx, g.perm, 1), s))) return st;
     if ((st = g.d_obs_uv.upload(gather(g.obs_uv, g.perm, 2), s))) return st;
     if ((st = g.d_obs_t0.upload(gather(g.obs_t0, g.perm, 1), s))) return st;
-    if ((st = g.d_ref_uv.upload(gather(g.ref_uv, g.perm, 2), s))) return st;
     if ((st = g.d_ref_t0.upload(gather(g.ref_t0, g.perm, 1), s))) return st;
     if ((st = g.d_huber.upload(gather(g.huber, g.perm, 1), s))) return st;
-    if ((st = g.d_lm.upload(gather(g.lm, g.perm, 1), s))) return st;
   } else {
     if ((st = g.d_t.upload(gather(g.t, g.perm, 1), s))) return st;
     if ((st = g.d_y.upload(gather(g.y, g.perm, 3), s))) return st;
@@ -273,6 +375,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kCamRowStride * 8);
+  cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   *out = p;
   return KTK_OK;
 }
@@ -347,10 +450,16 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
     if (g.kind == KTK_STATIC_RS) {
+      RefArgs ra;
+      ra.sp = p->sp; fill_camera_consts(g.cam, ra.cam);
+      ra.knots = p->d_knots8.p; ra.pairs = p->d_pairs.p; ra.rho = d_rho;
+      ra.ref_uv = g.d_rr_uv.p; ra.ref_t0 = g.d_rr_t0.p; ra.seg_start = g.d_rr_start.p; ra.seg_n = g.d_rr_n.p; ra.lm = g.d_rr_lm.p;
+      ra.n = (int)g.n_ref; ra.recs = g.d_recs.p; ra.err = p->d_err.p;
+      if (g.n_ref > 0) { k_landmark_ref<<<(int)((g.n_ref + kThreads - 1) / kThreads), kThreads, kThreads * kRefStride * 8, s>>>(ra); p->launches += 1; }
       CamArgs a;
-      a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
-      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
-      a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
+      a.sp = p->sp; a.cam = ra.cam;
+      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.recs = g.d_recs.p;
+      a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
       k_static_rs<<<blocks, kThreads, kThreads * kCamRowStride * 8, s>>>(a);

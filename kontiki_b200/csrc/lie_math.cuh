@@ -20,7 +20,8 @@
 namespace kb {
 
 struct V3 { double x, y, z; };
-struct M3 { double a[9]; };   // row-major
+template <int N> struct Mr { double a[3 * N]; };   // N x 3, row-major
+using M3 = Mr<3>;
 
 KB_HD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 KB_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -89,6 +90,42 @@ KB_HD M3 hat_mul(V3 v, const M3& A) {
     const double ax = A.a[j], ay = A.a[3 + j], az = A.a[6 + j];
     r.a[j] = v.y * az - v.z * ay; r.a[3 + j] = v.z * ax - v.x * az; r.a[6 + j] = v.x * ay - v.y * ax; }
   return r; }
+
+// ---- N x 3 row blocks (adjoint rows of an N-row residual) -----------------------------------------------------------
+template <int N> KB_HD Mr<N> rmul(const Mr<N>& A, const M3& B) {        // A * B
+  Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.a[3 * i + j] = A.a[3 * i] * B.a[j] + A.a[3 * i + 1] * B.a[3 + j] + A.a[3 * i + 2] * B.a[6 + j];
+  return r; }
+template <int N> KB_HD Mr<N> rmul_nt(const Mr<N>& A, const M3& B) {     // A * B^T
+  Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.a[3 * i + j] = A.a[3 * i] * B.a[3 * j] + A.a[3 * i + 1] * B.a[3 * j + 1] + A.a[3 * i + 2] * B.a[3 * j + 2];
+  return r; }
+template <int N> KB_HD Mr<N> rmul_hat(const Mr<N>& A, V3 v) {            // A * hat(v): every row crossed with v
+  Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double ax = A.a[3 * i], ay = A.a[3 * i + 1], az = A.a[3 * i + 2];
+    r.a[3 * i] = ay * v.z - az * v.y; r.a[3 * i + 1] = az * v.x - ax * v.z; r.a[3 * i + 2] = ax * v.y - ay * v.x; }
+  return r; }
+template <int N> KB_HD Mr<N> radd(const Mr<N>& A, const Mr<N>& B) { Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < 3 * N; ++i) r.a[i] = A.a[i] + B.a[i]; return r; }
+template <int N> KB_HD Mr<N> rsub(const Mr<N>& A, const Mr<N>& B) { Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < 3 * N; ++i) r.a[i] = A.a[i] - B.a[i]; return r; }
+template <int N> KB_HD Mr<N> rscale(double s, const Mr<N>& A) { Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < 3 * N; ++i) r.a[i] = s * A.a[i]; return r; }
+template <int N> KB_HD V3 rrow(const Mr<N>& A, int i) { return v3(A.a[3 * i], A.a[3 * i + 1], A.a[3 * i + 2]); }
+template <int N> KB_HD Mr<N> rzero() { Mr<N> r;
+#pragma unroll
+  for (int i = 0; i < 3 * N; ++i) r.a[i] = 0.0; return r; }
 
 // Rotation matrix of a unit quaternion (x,y,z,w) -- same polynomial as Eigen's toRotationMatrix.
 KB_HD M3 quat_to_rot(double x, double y, double z, double w) {

@@ -207,64 +207,69 @@ KB_HD void exp_part(const double* om, double B, bool need_trans, bool need_q, Ex
   else { e.rho = v3(0, 0, 0); e.a = v3(0, 0, 0); }
 }
 
-// rows of a 3x3 as vectors
-KB_HD V3 row(const M3& A, int i) { return v3(A.a[3 * i], A.a[3 * i + 1], A.a[3 * i + 2]); }
-KB_HD void set_row(M3& A, int i, V3 v) { A.a[3 * i] = v.x; A.a[3 * i + 1] = v.y; A.a[3 * i + 2] = v.z; }
-
-// A 3x6 (or 2x6, third row unused) adjoint block  [U | W]  acting on a twist [upsilon; phi].
-struct G6 { M3 U, W; };
+// An N x 6 adjoint block  [U | W]  acting on a twist [upsilon; phi]  (N = rows of the residual: 3 IMU, 2 camera).
+template <int N> struct G6 { Mr<N> U, W; };
 // G * ad(x),  ad([xu; xw]) = [[hat xw, hat xu], [0, hat xw]]
-KB_HD G6 mul_ad(const G6& g, V3 xu, V3 xw) { G6 r; r.U = mul_hat(g.U, xw); r.W = mul_hat(g.U, xu) + mul_hat(g.W, xw); return r; }
+template <int N> KB_HD G6<N> mul_ad(const G6<N>& g, V3 xu, V3 xw) {
+  G6<N> r; r.U = rmul_hat(g.U, xw); r.W = radd(rmul_hat(g.U, xu), rmul_hat(g.W, xw)); return r; }
 // G * Ad(A^-1),  Ad(A^-1) = [[E^T, -E^T hat(a)], [0, E^T]]
-KB_HD G6 mul_Adinv(const G6& g, const M3& E, V3 a) { G6 r; r.U = mul_nt(g.U, E); r.W = mul_nt(g.W, E) - mul_hat(r.U, a); return r; }
+template <int N> KB_HD G6<N> mul_Adinv(const G6<N>& g, const M3& E, V3 a) {
+  G6<N> r; r.U = rmul_nt(g.U, E); r.W = rsub(rmul_nt(g.W, E), rmul_hat(r.U, a)); return r; }
 // G * B * Jr6(B omega),  Jr6 = [[Jr, Qr], [0, Jr]],  Jr = V^T
-KB_HD G6 mul_Jr6(const G6& g, const ExpPart& e, double B) {
+template <int N> KB_HD G6<N> mul_Jr6(const G6<N>& g, const ExpPart& e, double B) {
   const M3 Qr = se3_q_block(e.rho, e.th, e.c, e.x, -1.0);
-  G6 r; r.U = B * mul_nt(g.U, e.V); r.W = B * (g.U * Qr + mul_nt(g.W, e.V)); return r; }
-KB_HD G6 operator+(const G6& a, const G6& b) { G6 r; r.U = a.U + b.U; r.W = a.W + b.W; return r; }
-KB_HD G6 operator*(double s, const G6& a) { G6 r; r.U = s * a.U; r.W = s * a.W; return r; }
+  G6<N> r; r.U = rscale(B, rmul_nt(g.U, e.V)); r.W = rscale(B, radd(rmul(g.U, Qr), rmul_nt(g.W, e.V))); return r; }
+template <int N> KB_HD G6<N> gadd(const G6<N>& a, const G6<N>& b) { G6<N> r; r.U = radd(a.U, b.U); r.W = radd(a.W, b.W); return r; }
+template <int N> KB_HD G6<N> gscale(double s, const G6<N>& a) { G6<N> r; r.U = rscale(s, a.U); r.W = rscale(s, a.W); return r; }
 
-// J_block(nrow x 7) (+)= scale * [G.U | G.W](nrow x 6) * D[:, off:off+7],  D = 6 x 14 row-major
-template <int NROW, bool ACC>
-KB_HD void contract_pair(double* J, const G6& g, const double* D, int off, double scale) {
+// J_block(N x 7) (+)= scale * [G.U | G.W](N x 6) * D[:, off:off+7],  D = 6 x 14 row-major
+template <int N, bool ACC>
+KB_HD void contract_pair(double* J, const G6<N>& g, const double* D, int off, double scale) {
 #pragma unroll
-  for (int r = 0; r < NROW; ++r)
+  for (int c = 0; c < 7; ++c) {
+    double d[6];
 #pragma unroll
-    for (int c = 0; c < 7; ++c) {
+    for (int m = 0; m < 6; ++m) d[m] = D[m * 14 + off + c];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
       double s = 0.0;
 #pragma unroll
-      for (int m = 0; m < 3; ++m) s += g.U.a[3 * r + m] * D[m * 14 + off + c] + g.W.a[3 * r + m] * D[(3 + m) * 14 + off + c];
+      for (int m = 0; m < 3; ++m) s += g.U.a[3 * r + m] * d[m] + g.W.a[3 * r + m] * d[3 + m];
       if (ACC) J[r * 7 + c] += scale * s; else J[r * 7 + c] = scale * s;
     }
+  }
 }
-// rotation-only version: G (nrow x 3) * D[3:6, off:off+4]; translation columns of phi rows are identically zero
-template <int NROW, bool ACC>
-KB_HD void contract_pair_rot(double* J, const M3& G, const double* D, int off, double scale) {
+// rotation-only version: G (N x 3) * D[3:6, off:off+4]; translation columns of the phi rows are identically zero
+template <int N, bool ACC>
+KB_HD void contract_pair_rot(double* J, const Mr<N>& G, const double* D, int off, double scale) {
 #pragma unroll
-  for (int r = 0; r < NROW; ++r) {
+  for (int c = 0; c < 4; ++c) {
+    double d[3];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      double s = 0.0;
+    for (int m = 0; m < 3; ++m) d[m] = D[(3 + m) * 14 + off + c];
 #pragma unroll
-      for (int m = 0; m < 3; ++m) s += G.a[3 * r + m] * D[(3 + m) * 14 + off + c];
+    for (int r = 0; r < N; ++r) {
+      const double s = G.a[3 * r] * d[0] + G.a[3 * r + 1] * d[1] + G.a[3 * r + 2] * d[2];
       if (ACC) J[r * 7 + c] += scale * s; else J[r * 7 + c] = scale * s;
     }
-    if (!ACC) { J[r * 7 + 4] = 0.0; J[r * 7 + 5] = 0.0; J[r * 7 + 6] = 0.0; }
+  }
+  if (!ACC) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) { J[r * 7 + 4] = 0.0; J[r * 7 + 5] = 0.0; J[r * 7 + 6] = 0.0; }
   }
 }
 // quaternion block of knot i0: J[r, 0:4] += scale * (g_theta[r] * dtheta/dq + g_rad[r] * q^T)
-template <int NROW>
-KB_HD void add_q0_block(double* J, const M3& Gth, V3 grad, const double* q, double scale) {
+template <int N>
+KB_HD void add_q0_block(double* J, const Mr<N>& Gth, const double* grad, const double* q, double scale) {
   const V3 v = v3(q[0], q[1], q[2]); const double w = q[3];
 #pragma unroll
-  for (int r = 0; r < NROW; ++r) {
-    const V3 g = row(Gth, r);
+  for (int r = 0; r < N; ++r) {
+    const V3 g = rrow(Gth, r);
     const V3 t = 2.0 * (w * g - cross(g, v));
-    const double gr = (r == 0 ? grad.x : (r == 1 ? grad.y : grad.z));
-    J[r * 7 + 0] += scale * (t.x + gr * q[0]);
-    J[r * 7 + 1] += scale * (t.y + gr * q[1]);
-    J[r * 7 + 2] += scale * (t.z + gr * q[2]);
-    J[r * 7 + 3] += scale * (-2.0 * dot(g, v) + gr * q[3]);
+    J[r * 7 + 0] += scale * (t.x + grad[r] * q[0]);
+    J[r * 7 + 1] += scale * (t.y + grad[r] * q[1]);
+    J[r * 7 + 2] += scale * (t.z + grad[r] * q[2]);
+    J[r * 7 + 3] += scale * (-2.0 * dot(g, v) + grad[r] * q[3]);
   }
 }
 
@@ -301,7 +306,9 @@ KB_HD void gyro_se3(const double* knot0, const double* p1, const double* p2, con
   const V3 ww = R * wb;
   const M3 Mm = mul_tn(R0, hat(ww));
   const V3 dw = 2.0 * ww - v3(Mm.a[7] - Mm.a[5], Mm.a[2] - Mm.a[6], Mm.a[3] - Mm.a[1]);
-  add_q0_block<3>(J, m3_zero(), mul_t(R, dw), knot0, sc);
+  const V3 rad = mul_t(R, dw);
+  const double radv[3] = {rad.x, rad.y, rad.z};
+  add_q0_block<3>(J, m3_zero(), radv, knot0, sc);
 }
 
 // ---- accelerometer on SE3 (imu.h:55-59, accelerometer_measurement.h:37-39) ---------------------------------------
@@ -342,31 +349,31 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
   const V3 acc = fb + gb;
   r[0] = weight * (y[0] - acc.x); r[1] = weight * (y[1] - acc.y); r[2] = weight * (y[2] - acc.z);
   // reverse
-  G6 gs, gd;                       // adjoints of s3 and s3'
+  G6<3> gs, gd;                    // adjoints of s3 and s3'
   gs.U = hat(wb); gs.W = (-1.0) * hat(vb);
   gd.U = m3_identity(); gd.W = m3_zero();
   const M3 hgb = hat(gb);          // d(R^T g) = hat(R^T g) dtheta_body
-  G6 g3, g2, g1;
+  G6<3> g3, g2, g1;
   {
-    const G6 gy = gs + (-bs.dB[2]) * mul_ad(gd, u3, f3);
-    g3 = bs.dB[2] * gs + bs.d2B[2] * gd + bs.dB[2] * mul_ad(gd, y3u, y3w);
-    G6 t = mul_ad(gy, y3u, y3w) + mul_ad(gd, z3u, z3w);
+    const G6<3> gy = gadd(gs, gscale(-bs.dB[2], mul_ad(gd, u3, f3)));
+    g3 = gadd(gadd(gscale(bs.dB[2], gs), gscale(bs.d2B[2], gd)), gscale(bs.dB[2], mul_ad(gd, y3u, y3w)));
+    G6<3> t = gadd(mul_ad(gy, y3u, y3w), mul_ad(gd, z3u, z3w));
     t.W = t.W + hgb;               // F3^T F3 = I
-    g3 = g3 + mul_Jr6(t, e3, bs.B[2]);
+    g3 = gadd(g3, mul_Jr6(t, e3, bs.B[2]));
     gs = mul_Adinv(gy, e3.E, e3.a);
     gd = mul_Adinv(gd, e3.E, e3.a);
   }
   {
-    const G6 gy = gs + (-bs.dB[1]) * mul_ad(gd, u2, f2);
-    g2 = bs.dB[1] * gs + bs.d2B[1] * gd + bs.dB[1] * mul_ad(gd, y2u, y2w);
-    G6 t = mul_ad(gy, y2u, y2w) + mul_ad(gd, z2u, z2w);
+    const G6<3> gy = gadd(gs, gscale(-bs.dB[1], mul_ad(gd, u2, f2)));
+    g2 = gadd(gadd(gscale(bs.dB[1], gs), gscale(bs.d2B[1], gd)), gscale(bs.dB[1], mul_ad(gd, y2u, y2w)));
+    G6<3> t = gadd(mul_ad(gy, y2u, y2w), mul_ad(gd, z2u, z2w));
     t.W = t.W + mul_nt(hgb, e3.E);   // F3^T F2 = E3^T
-    g2 = g2 + mul_Jr6(t, e2, bs.B[1]);
+    g2 = gadd(g2, mul_Jr6(t, e2, bs.B[1]));
     gs = mul_Adinv(gy, e2.E, e2.a);
     gd = mul_Adinv(gd, e2.E, e2.a);
   }
   {
-    g1 = bs.dB[0] * gs + bs.d2B[0] * gd;
+    g1 = gadd(gscale(bs.dB[0], gs), gscale(bs.d2B[0], gd));
     // rotation of A1 only enters through R^T g:  F3^T F1 = (E2 E3)^T
     g1.W = g1.W + bs.B[0] * mul_nt(mul_nt(hgb, E23), e1.V);
   }
@@ -379,7 +386,8 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
   contract_pair<3, false>(J + 63, g3, p3 + kPairDOff, 7, sc);
   // knot i0 directly: tangent through R^T g, radial through P'' = R(q0 raw) M2 (uniform_se3_spline_trajectory.h:187-190)
   const V3 rad = 2.0 * (fb - mul_t(R, E123 * fb));
-  add_q0_block<3>(J, mul_nt(hgb, E123), rad, knot0, sc);
+  const double radv[3] = {rad.x, rad.y, rad.z};
+  add_q0_block<3>(J, mul_nt(hgb, E123), radv, knot0, sc);
 }
 
 // ---- pose (position + orientation) of the cumulative spline and its reverse sweep ---------------------------------
@@ -395,88 +403,41 @@ KB_HD void pose_forward(const double* knot0, const double* p1, const double* p2,
   P.c1 = P.e1.a + P.e1.E * P.c2;
   P.p = v3(knot0[4], knot0[5], knot0[6]) + P.R0 * P.c1;
 }
-// Given NROW row-adjoints with respect to p (world, additive) and to a body-frame rotation perturbation R <- R Exp(d),
-// writes scale * d(row)/d(knots i0..i0+3) into J ([4][NROW][7]), accumulating if ACC.
-template <int NROW>
+// Given N row-adjoints with respect to p (world, additive) and to a body-frame rotation perturbation R <- R Exp(d),
+// writes scale * d(row)/d(knots i0..i0+3) into J ([4][N][7]).
+template <int N>
 KB_HD void pose_backward(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, const Pose& P,
-                         const M3& Gp, const M3& Gth, double scale, double* J) {
-  G6 g1, g2, g3, t;
+                         const Mr<N>& Gp, const Mr<N>& Gth, double scale, double* J) {
+  G6<N> g, t;
   // eps_j = B_j Jr6 d(omega_j):  d/d(eps_rho_j) = Gp F_j,  d/d(eps_theta_j) = -(Gp F_j) hat(c_{j+1}) + Gth F3^T F_j
-  t.U = Gp * P.R;  t.W = Gth;
-  g3 = mul_Jr6(t, P.e3, bs.B[2]);
-  t.U = Gp * P.F2; t.W = mul_nt(Gth, P.e3.E) - mul_hat(t.U, P.e3.a);
-  g2 = mul_Jr6(t, P.e2, bs.B[1]);
   const M3 E23 = P.e2.E * P.e3.E;
-  t.U = Gp * P.F1; t.W = mul_nt(Gth, E23) - mul_hat(t.U, P.c2);
-  g1 = mul_Jr6(t, P.e1, bs.B[0]);
-  contract_pair<NROW, false>(J + 0 * NROW * 7, g1, p1 + kPairDOff, 0, scale);
-  contract_pair<NROW, false>(J + 1 * NROW * 7, g1, p1 + kPairDOff, 7, scale);
-  contract_pair<NROW, true>(J + 1 * NROW * 7, g2, p2 + kPairDOff, 0, scale);
-  contract_pair<NROW, false>(J + 2 * NROW * 7, g2, p2 + kPairDOff, 7, scale);
-  contract_pair<NROW, true>(J + 2 * NROW * 7, g3, p3 + kPairDOff, 0, scale);
-  contract_pair<NROW, false>(J + 3 * NROW * 7, g3, p3 + kPairDOff, 7, scale);
+  t.U = rmul(Gp, P.F1); t.W = rsub(rmul_nt(Gth, E23), rmul_hat(t.U, P.c2));
+  g = mul_Jr6(t, P.e1, bs.B[0]);
+  contract_pair<N, false>(J + 0 * N * 7, g, p1 + kPairDOff, 0, scale);
+  contract_pair<N, false>(J + 1 * N * 7, g, p1 + kPairDOff, 7, scale);
+  t.U = rmul(Gp, P.F2); t.W = rsub(rmul_nt(Gth, P.e3.E), rmul_hat(t.U, P.e3.a));
+  g = mul_Jr6(t, P.e2, bs.B[1]);
+  contract_pair<N, true>(J + 1 * N * 7, g, p2 + kPairDOff, 0, scale);
+  contract_pair<N, false>(J + 2 * N * 7, g, p2 + kPairDOff, 7, scale);
+  t.U = rmul(Gp, P.R); t.W = Gth;
+  g = mul_Jr6(t, P.e3, bs.B[2]);
+  contract_pair<N, true>(J + 2 * N * 7, g, p3 + kPairDOff, 0, scale);
+  contract_pair<N, false>(J + 3 * N * 7, g, p3 + kPairDOff, 7, scale);
   // knot i0 directly: t0 additive; R0 <- R0 Exp(d): dp = -R0 hat(c1) d, dtheta_body = (E1 E2 E3)^T d;
   // radial: P.t = t0 + q0 * a1 + ... with Eigen's polynomial q*v  =>  dp/ds = 2 (R0 - I) a1
-  const M3 GpR0 = Gp * P.R0;
-  const M3 Gth0 = mul_nt(Gth, P.e1.E * E23) - mul_hat(GpR0, P.c1);
+  const Mr<N> GpR0 = rmul(Gp, P.R0);
+  const Mr<N> Gth0 = rsub(rmul_nt(Gth, P.e1.E * E23), rmul_hat(GpR0, P.c1));
   const V3 dps = 2.0 * (P.R0 * P.e1.a - P.e1.a);
-  const V3 grad = Gp * dps;
-  add_q0_block<NROW>(J, Gth0, grad, knot0, scale);
+  double grad[N];
 #pragma unroll
-  for (int r = 0; r < NROW; ++r) { J[r * 7 + 4] += scale * Gp.a[3 * r]; J[r * 7 + 5] += scale * Gp.a[3 * r + 1]; J[r * 7 + 6] += scale * Gp.a[3 * r + 2]; }
+  for (int r = 0; r < N; ++r) grad[r] = dot(rrow(Gp, r), dps);
+  add_q0_block<N>(J, Gth0, grad, knot0, scale);
+#pragma unroll
+  for (int r = 0; r < N; ++r) { J[r * 7 + 4] += scale * Gp.a[3 * r]; J[r * 7 + 5] += scale * Gp.a[3 * r + 1]; J[r * 7 + 6] += scale * Gp.a[3 * r + 2]; }
 }
 
-// ---- static rolling-shutter camera on SE3 (static_rscamera_measurement.h:21-55, :89-94) ---------------------------
-struct CameraConst {
-  double K[9], Kinv[9];     // pinhole_camera.h:25 (meta, not optimised); Kinv by cofactors once instead of per call (:63-67)
-  double q_ct[4], p_ct[3];  // sensors.h:36-57 relative pose (x,y,z,w)
-  double time_offset, row_delta;   // row_delta = readout / rows (static_rscamera_measurement.h:30)
-  double readout, max_time_offset;
-  int time_offset_locked;
-};
-// J: [ref: 4 knots][2][7] (56) | [obs: 4 knots][2][7] (56) | d r / d rho (2)
-KB_HD void static_rs_se3(const CameraConst& cam, const double* k0r, const double* r1, const double* r2, const double* r3, const Basis& br,
-                         const double* k0o, const double* o1, const double* o2, const double* o3, const Basis& bo,
-                         const double* ref_uv, const double* obs_uv, double rho, double weight, double* r, double* J) {
-  Pose Pr, Po;
-  pose_forward(k0r, r1, r2, r3, br, Pr);
-  pose_forward(k0o, o1, o2, o3, bo, Po);
-  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
-  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  M3 Ki; for (int i = 0; i < 9; ++i) Ki.a[i] = cam.Kinv[i];
-  M3 Km; for (int i = 0; i < 9; ++i) Km.a[i] = cam.K[i];
-  const V3 yh = Ki * v3(ref_uv[0], ref_uv[1], 1.0);
-  const V3 Xref = mul_t(Rct, yh - rho * pct);
-  const V3 RX = Pr.R * Xref;
-  const V3 X = RX + rho * Pr.p;
-  const V3 Xobs = mul_t(Po.R, X - rho * Po.p);
-  const V3 Xc = Rct * Xobs + rho * pct;
-  const V3 pr = Km * Xc;
-  const double iz = 1.0 / pr.z;
-  const double y0 = pr.x * iz, y1 = pr.y * iz;
-  r[0] = weight * (obs_uv[0] - y0); r[1] = weight * (obs_uv[1] - y1);
-  // d y / d Xc (2x3), third row zero
-  M3 Jp;
-  Jp.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); Jp.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); Jp.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
-  Jp.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); Jp.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); Jp.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
-  Jp.a[6] = 0.0; Jp.a[7] = 0.0; Jp.a[8] = 0.0;
-  const M3 Go = Jp * Rct;                       // d y / d Xobs
-  const M3 GX = mul_nt(Go, Po.R);               // d y / d X
-  const double sc = -weight;
-  // obs pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
-  pose_backward<2>(k0o, o1, o2, o3, bo, Po, (-rho) * GX, mul_hat(Go, Xobs), sc, J + 56);
-  // ref pose: X = R_r Xref + rho p_r:  d/dp_r = rho GX,  d/dtheta_r = -GX R_r hat(Xref)
-  pose_backward<2>(k0r, r1, r2, r3, br, Pr, rho * GX, (-1.0) * mul_hat(GX * Pr.R, Xref), sc, J);
-  // inverse depth: dXc/drho = R_ct R_o^T (-R_r R_ct^T p_ct + p_r - p_o) + p_ct
-  const V3 dX = Pr.p - Po.p - Pr.R * mul_t(Rct, pct);
-  const V3 dXc = Rct * mul_t(Po.R, dX) + pct;
-  const V3 dy = Jp * dXc;
-  J[112] = sc * dy.x; J[113] = sc * dy.y;
-}
-
-// ceres::HuberLoss(a) + ceres::internal::Corrector (un-vendored Ceres 1.x) applied to one
-// residual block in place: r (NRES) and J (NRES x ncols, row stride `ld`; here blocks of [NRES][7] so the caller
-// passes every block).  Returns rho(s).  Split in two so that the block loop stays with the caller.
+// ceres::HuberLoss(a) + ceres::internal::Corrector (un-vendored Ceres 1.x): scale factors for one
+// residual block with squared norm s.  Ceres applies them to r and J after Evaluate.
 struct HuberScale { double sqrt_rho1, residual_scaling, alpha_sq_norm, rho0; };
 KB_HD HuberScale huber_scale(double a, double s) {
   HuberScale h; const double b = a * a; double rho1, rho2;
@@ -488,10 +449,106 @@ KB_HD HuberScale huber_scale(double a, double s) {
   return h;
 }
 
+// ---- static rolling-shutter camera on SE3 (static_rscamera_measurement.h:21-55, :89-94) ---------------------------
+struct CameraConst {
+  double K[9], Kinv[9];     // pinhole_camera.h:25 (meta, not optimised); Kinv by cofactors once instead of per call (:63-67)
+  double q_ct[4], p_ct[3];  // sensors.h:36-57 relative pose (x,y,z,w)
+  double time_offset, row_delta;   // row_delta = readout / rows (static_rscamera_measurement.h:30)
+  double readout, max_time_offset;
+  int time_offset_locked;
+};
+KB_HD M3 load_m3(const double* a) { M3 m;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m.a[i] = a[i]; return m; }
+
+// Reference side, ONCE PER LANDMARK REFERENCE (hoisted: the reference re-evaluates it for every observation).
+// All observations of a landmark share the reference observation (landmark.h:19-54), hence
+//   X = R_r R_ct^T (K^-1 [u v 1] - rho p_ct) + rho p_r            (static_rscamera_measurement.h:43-46)
+// and its derivatives with respect to the 4 reference-window knots and to rho.
+// record (kRefStride doubles): X(3) | dX/drho(3) | rho | i0_ref (as double) | dX/dknots [4][3][7]
+constexpr int kRefStride = 92;
+constexpr int kRefDOff = 8;
+KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const double* p1, const double* p2, const double* p3, const Basis& bs,
+                            const double* ref_uv, double rho, int i0, double* rec) {
+  Pose P;
+  pose_forward(k0, p1, p2, p3, bs, P);
+  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  const V3 yh = load_m3(cam.Kinv) * v3(ref_uv[0], ref_uv[1], 1.0);
+  const V3 Xref = mul_t(Rct, yh - rho * pct);
+  const V3 X = P.R * Xref + rho * P.p;
+  const V3 dXr = P.p - P.R * mul_t(Rct, pct);
+  rec[0] = X.x; rec[1] = X.y; rec[2] = X.z; rec[3] = dXr.x; rec[4] = dXr.y; rec[5] = dXr.z; rec[6] = rho; rec[7] = (double)i0;
+  // X = R_r Xref + rho p_r:  dX/dp_r = rho I,  dX/dtheta_r = -R_r hat(Xref)
+  pose_backward<3>(k0, p1, p2, p3, bs, P, rho * m3_identity(), (-1.0) * mul_hat(P.R, Xref), 1.0, rec + kRefDOff);
+}
+
+// Observation side, per measurement.  `ref` is the landmark record above; its dX/dknots part may alias J (the row
+// buffer) at J + kRefInRow: the reference-window blocks are produced front to back, each read before it is overwritten.
+// J: [ref window: 4 knots][2][7] (56) | [obs window: 4 knots][2][7] (56) | d r / d rho (2)
+constexpr int kRefInRow = 22;      // 22 + 92 = 114 = row length; block k is read at 30 + 21 k and written at 14 k
+struct NoWait { KB_HD void operator()() const {} };
+template <class WaitFn>
+KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const double* p1, const double* p2, const double* p3, const Basis& bs,
+                             const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J, int* i0_ref,
+                             const WaitFn& wait_ref) {
+  Pose P;
+  pose_forward(k0, p1, p2, p3, bs, P);
+  wait_ref();                                  // the landmark record may still be in flight (TMA) up to here
+  *i0_ref = (int)ref[7];
+  const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
+  const double rho = ref[6];
+  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  const M3 Km = load_m3(cam.K);
+  const V3 Xobs = mul_t(P.R, X - rho * P.p);                 // static_rscamera_measurement.h:49
+  const V3 Xc = Rct * Xobs + rho * pct;                      // :52
+  const V3 pr = Km * Xc;                                     // pinhole_camera.h:47-51
+  const double iz = 1.0 / pr.z;
+  const double y0 = pr.x * iz, y1 = pr.y * iz;
+  double r0 = weight * (obs_uv[0] - y0), r1 = weight * (obs_uv[1] - y1);
+  // ceres::HuberLoss + Corrector folded into the row scale: J <- sqrt(rho') (J - alpha/|r|^2 r r^T J), r <- r * scaling
+  // (2x2 matrix C applied to the two rows; identity when the loss is off or in its quadratic region)
+  double c00 = 1.0, c01 = 0.0, c10 = 0.0, c11 = 1.0, rs = 1.0;
+  if (huber_c > 0.0) {
+    const HuberScale h = huber_scale(huber_c, r0 * r0 + r1 * r1);
+    c00 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * r0 * r0); c01 = -h.sqrt_rho1 * h.alpha_sq_norm * r0 * r1;
+    c10 = c01; c11 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * r1 * r1);
+    rs = h.residual_scaling;
+  }
+  r[0] = rs * r0; r[1] = rs * r1;
+  // d r / d Xc = -weight * C * d y / d Xc   (2 x 3)
+  Mr<2> Jp0;
+  Jp0.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); Jp0.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); Jp0.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
+  Jp0.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); Jp0.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); Jp0.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
+  Mr<2> Jp;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
+  const Mr<2> Go = rmul(Jp, Rct);               // d r / d Xobs
+  const Mr<2> GX = rmul_nt(Go, P.R);            // d r / d X
+  // reference-window blocks: GX (2x3) * dX/dknot_k (3x7), in place (see kRefInRow)
+  const double* dXk = ref + kRefDOff;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double blk[21];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) blk[i] = dXk[21 * k + i];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 7; ++c) J[14 * k + 7 * rr + c] = GX.a[3 * rr] * blk[c] + GX.a[3 * rr + 1] * blk[7 + c] + GX.a[3 * rr + 2] * blk[14 + c];
+  }
+  // inverse depth: dXc/drho = R_ct R_o^T (dX/drho - p_o) + p_ct
+  const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
+  const double jr0 = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z, jr1 = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
+  // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
+  pose_backward<2>(k0, p1, p2, p3, bs, P, rscale(-rho, GX), rmul_hat(Go, Xobs), 1.0, J + 56);
+  J[112] = jr0; J[113] = jr1;
+}
 
 // =================================================================================================================
 // Row drivers: everything one measurement does, from its record to its residual / packed Jacobian row.
-// `knots` / `pairs` are indexable by GLOBAL knot index (the kernels pass window-relative base pointers).
+// `knots` / `pairs` are indexable by GLOBAL knot index.
 // Return 0, or a negative ktk status where the reference would have thrown (trajectory_estimator.h:97-122,
 // spline_base.h:196-201, uniform_se3_spline_trajectory.h:121-127).
 // =================================================================================================================
@@ -523,11 +580,9 @@ KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const d
   return 0;
 }
 
-// static RS camera; static_rscamera_measurement.h:130-198 builds the two spans, :112-123 / :21-55 evaluate.
-// huber_c > 0 applies ceres::HuberLoss + Corrector to (r, J) as Ceres does after Evaluate.
-KB_HD int static_rs_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs,
-                        const double* obs_uv, double obs_t0, const double* ref_uv, double ref_t0, double rho, double weight,
-                        double huber_c, double* r, double* J, int* i0_ref_out, int* i0_obs_out) {
+// The two spans of a static-RS residual (static_rscamera_measurement.h:137-166) and their segments
+// (spline_base.h:371-403).  Returns the number of segments, 0 where CheckTimeSpans (trajectory_estimator.h:97-122) throws.
+KB_HD int static_rs_segments(const SplineConst& sp, const CameraConst& cam, double ref_t0, double obs_t0, Segment& s0, Segment& s1) {
   double t1, t2;
   if (ref_t0 <= obs_t0) { t1 = ref_t0; t2 = obs_t0; } else { t1 = obs_t0; t2 = ref_t0; }
   if (!cam.time_offset_locked) { t1 = sub_rn(t1, cam.max_time_offset); t2 = add_rn(t2, cam.max_time_offset); }
@@ -535,34 +590,50 @@ KB_HD int static_rs_row(const SplineConst& sp, const CameraConst& cam, const dou
   const double a1 = sub_rn(t1, margin), b1 = add_rn(add_rn(t1, cam.readout), margin);
   const double a2 = sub_rn(t2, margin), b2 = add_rn(add_rn(t2, cam.readout), margin);
   const double tmax = spline_max_time(sp);
-  if (sp.n_knots < 4 || !(a1 >= sp.t0) || !(b1 < tmax) || !(a2 >= sp.t0) || !(b2 < tmax) || a1 > b1 || a2 > b2 || a2 < a1) return kStatusRange;
+  if (sp.n_knots < 4 || !(a1 >= sp.t0) || !(b1 < tmax) || !(a2 >= sp.t0) || !(b2 < tmax) || a1 > b1 || a2 > b2 || a2 < a1) return 0;
+  return segments_two_spans(a1, b1, a2, b2, sp.t0, sp.dt, s0, s1);
+}
+// Evaluation time of an observation: t0_view + time_offset + v * row_delta (static_rscamera_measurement.h:30-33)
+KB_HD double static_rs_time(const CameraConst& cam, double view_t0, double v) { return add_rn(add_rn(view_t0, cam.time_offset), mul_rn(v, cam.row_delta)); }
+// SplineView::Evaluate over the (at most two) segments: first segment that holds t (spline_base.h:188-202).
+// Returns the index of that segment (0/1) or -1.
+KB_HD int locate_in_segments(int nseg, const Segment& s0, const Segment& s1, double t, double t0, double dt, int& i0, double& u) {
+  if (segment_locate(s0, t, t0, dt, i0, u)) return 0;
+  if (nseg == 2 && segment_locate(s1, t, t0, dt, i0, u)) return 1;
+  return -1;
+}
+
+// One landmark-reference record: the spline evaluation at the reference observation's time inside the segment whose
+// first knot is `seg_start` with `seg_n` knots (found on the host from the residual's two spans; identical for all
+// observations of a landmark whose reference view is the earlier one).
+KB_HD int landmark_ref_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref_uv,
+                           double ref_t0, int seg_start, int seg_n, double rho, double* rec) {
+  Segment s; s.start = seg_start; s.n = seg_n;
+  int i0; double u;
+  if (!segment_locate(s, static_rs_time(cam, ref_t0, ref_uv[1]), sp.t0, sp.dt, i0, u)) return kStatusRange;
+  if (i0 < 0 || i0 + 3 >= sp.n_knots) return kStatusRange;
+  const Basis bs = cumulative_basis(u, sp.dt);
+  const double* p1 = pairs + (size_t)(i0 + 1) * kPairStride;
+  landmark_ref_se3(cam, knots + (size_t)i0 * kKnotStride, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, ref_uv, rho, i0, rec);
+  return 0;
+}
+
+// static RS camera row; static_rscamera_measurement.h:130-198 builds the two spans, :112-123 / :21-55 evaluate.
+// huber_c > 0 applies ceres::HuberLoss + Corrector to (r, J) as Ceres does after Evaluate.
+template <class WaitFn>
+KB_HD int static_rs_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref,
+                        const double* obs_uv, double obs_t0, double ref_t0, double weight, double huber_c, double* r, double* J,
+                        int* i0_ref_out, int* i0_obs_out, const WaitFn& wait_ref) {
   Segment s0, s1;
-  const int nseg = segments_two_spans(a1, b1, a2, b2, sp.t0, sp.dt, s0, s1);
-  const double t_ref = add_rn(add_rn(ref_t0, cam.time_offset), mul_rn(ref_uv[1], cam.row_delta));
-  const double t_obs = add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(obs_uv[1], cam.row_delta));
-  int ir, io; double ur, uo;
-  if (!segment_locate(s0, t_ref, sp.t0, sp.dt, ir, ur) && !(nseg == 2 && segment_locate(s1, t_ref, sp.t0, sp.dt, ir, ur))) return kStatusRange;
-  if (!segment_locate(s0, t_obs, sp.t0, sp.dt, io, uo) && !(nseg == 2 && segment_locate(s1, t_obs, sp.t0, sp.dt, io, uo))) return kStatusRange;
-  const Basis br = cumulative_basis(ur, sp.dt), bo = cumulative_basis(uo, sp.dt);
-  const double* pr1 = pairs + (size_t)(ir + 1) * kPairStride;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  int io = -1; double uo = 0.0;
+  if (nseg == 0 || locate_in_segments(nseg, s0, s1, static_rs_time(cam, obs_t0, obs_uv[1]), sp.t0, sp.dt, io, uo) < 0) { wait_ref(); return kStatusRange; }
+  const Basis bo = cumulative_basis(uo, sp.dt);
   const double* po1 = pairs + (size_t)(io + 1) * kPairStride;
-  static_rs_se3(cam, knots + (size_t)ir * kKnotStride, pr1, pr1 + kPairStride, pr1 + 2 * kPairStride, br,
-                knots + (size_t)io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, bo, ref_uv, obs_uv, rho, weight, r, J);
-  if (huber_c > 0.0) {
-    const HuberScale h = huber_scale(huber_c, r[0] * r[0] + r[1] * r[1]);
-    for (int b = 0; b < 8; ++b) {
-      double* Jb = J + b * 14;
-      for (int c = 0; c < 7; ++c) {
-        const double rtj = Jb[c] * r[0] + Jb[7 + c] * r[1];
-        Jb[c] = h.sqrt_rho1 * (Jb[c] - h.alpha_sq_norm * r[0] * rtj);
-        Jb[7 + c] = h.sqrt_rho1 * (Jb[7 + c] - h.alpha_sq_norm * r[1] * rtj);
-      }
-    }
-    const double rtj = J[112] * r[0] + J[113] * r[1];
-    J[112] = h.sqrt_rho1 * (J[112] - h.alpha_sq_norm * r[0] * rtj);
-    J[113] = h.sqrt_rho1 * (J[113] - h.alpha_sq_norm * r[1] * rtj);
-    r[0] *= h.residual_scaling; r[1] *= h.residual_scaling;
-  }
+  int ir;
+  static_rs_obs_se3(cam, knots + (size_t)io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, bo, ref, obs_uv, weight, huber_c, r, J,
+                    &ir, wait_ref);
+  if (ir < 0) return kStatusRange;                 // the landmark record itself was out of range
   *i0_ref_out = ir; *i0_obs_out = io;
   return 0;
 }

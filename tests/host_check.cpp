@@ -42,8 +42,21 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
   cam.time_offset_locked = locked;
   for (int i = 0; i < n; ++i) {
     i0_ref[i] = -1; i0_obs[i] = -1;
-    status[i] = static_rs_row(sp, cam, knots8, pairs, obs_uv + 2 * i, obs_t0[i], ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], w[i],
-                              huber_c ? huber_c[i] : 0.0, r + 2 * i, J + (size_t)114 * i, i0_ref + i, i0_obs + i);
+    double* row = J + (size_t)114 * i;
+    double* rec = row + kRefInRow;                // the landmark record lands inside the row buffer, exactly as in the kernel
+    // host part of the pipeline (ktk.cu upload_group): which segment of this residual holds the reference evaluation
+    Segment s0, s1;
+    const int nseg = static_rs_segments(sp, cam, ref_t0[i], obs_t0[i], s0, s1);
+    int ir; double ur;
+    const int which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, static_rs_time(cam, ref_t0[i], ref_uv[2 * i + 1]), sp.t0, sp.dt, ir, ur);
+    if (which < 0) { status[i] = kStatusRange; continue; }
+    const Segment& sr = which == 0 ? s0 : s1;
+    // K_lm: landmark reference record
+    status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
+    if (status[i] != 0) continue;
+    // K_obs: the observation row
+    status[i] = static_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row,
+                              i0_ref + i, i0_obs + i, NoWait());
   }
 }
 

@@ -174,6 +174,11 @@ def test_full_size_properties_h1():
     # (4) directional derivative along a random tangent-space direction of all knots and all rho
     h = 1e-6
     d = rng.normal(0, 1, cfg["knots"].shape)
+    # quaternion part: tangent directions only (d_q orthogonal to q).  The residual is defined on unit quaternions; along
+    # q itself the reference's polynomial R(q) / q*v arithmetic gives the Jacobian a component (reproduced, see
+    # spline_math.cuh "radial") that a finite difference of the closed-form residual does not see.
+    q = cfg["knots"][:, :4]
+    d[:, :4] -= (d[:, :4] * q).sum(1, keepdims=True) * q
     drho = rng.normal(0, 1, c["rho"].shape) * c["rho"]
     op = p.evaluate(cfg["knots"] + h * d, c["rho"] + h * drho, _lib.EVAL_RESIDUALS)
     om = p.evaluate(cfg["knots"] - h * d, c["rho"] - h * drho, _lib.EVAL_RESIDUALS)
