@@ -46,7 +46,7 @@ def lib():
     """Loads the CUDA library; raises (never falls back) when it has not been built."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
+        path = os.environ.get("KTK_LIB", _build.LIB_PATH)
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
                               "kontiki_b200 has no CPU fallback.")

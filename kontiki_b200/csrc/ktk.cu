@@ -5,11 +5,11 @@
 //   k_pair_prepass   K0: omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian, one thread per (pair, direction)
 //   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
 //   k_landmark_ref   reference side of the static-RS rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
-//   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); each thread pulls its
-//                    landmark record into its row buffer with a TMA bulk load that overlaps the observation-pose math
-// Measurement records are sorted once (at add time) by their first active knot so that a warp touches one or two
-// knot windows; each thread builds its Jacobian row in shared memory and hands it to the TMA (cp.async.bulk
-// shared -> global) as ONE contiguous 672-B / 912-B store at the caller's row index, so rows come out in the caller's
+//   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); the warp gathers its 32
+//                    landmark records into the row buffers with LDGSTS copies that overlap the observation-pose math
+// Measurement records are sorted once (first evaluation) by their first active knot so that a warp touches one or two
+// knot windows; each thread builds its Jacobian row in shared memory, then the warp writes the 32 rows cooperatively
+// (16-byte chunks, one contiguous 672-B / 912-B run per row) at the CALLER's row indices, so rows come out in insertion
 // order at full sector efficiency without a second pass.
 #include <cuda_runtime.h>
 
@@ -37,45 +37,53 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
     if (e_ != cudaSuccess) return fail(KTK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
   } while (0)
 
-constexpr int kThreads = 64;            // measurement rows per CTA (one per thread)
+#ifndef KTK_THREADS
+#define KTK_THREADS 64
+#endif
+#ifndef KTK_CAM_THREADS
+#define KTK_CAM_THREADS 32
+#endif
+#ifndef KTK_CAM_MINB
+#define KTK_CAM_MINB 1
+#endif
+constexpr int kThreads = KTK_THREADS;            // measurement rows per CTA (one per thread), IMU and landmark kernels
+constexpr int kCamThreads = KTK_CAM_THREADS;     // ... static-RS observation kernel
 constexpr int kImuRow = 84, kImuRowStride = 86;     // doubles; stride keeps rows 16-B aligned and off the same banks
 constexpr int kCamRow = 114, kCamRowStride = 114;
+constexpr int kCamWarpSmem = 32 * kCamRowStride;     // doubles of shared memory per warp: 32 row buffers
 
-// ---- TMA bulk store of one shared-memory row to global memory ----------------------------------------------------
-__device__ __forceinline__ void bulk_store_row(double* gdst, const double* ssrc, unsigned bytes) {
-  // writes of this thread to its row (generic proxy) must be visible to the async proxy before the copy is issued
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// ---- data movement helpers ---------------------------------------------------------------------------------------
+// One TMA bulk store shared -> global (issued by ONE lane for a whole warp tile; UBLKCP is a uniform-datapath
+// instruction, per-lane issue serialises the warp).
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, unsigned bytes) {
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous copy global -> shared (LDGSTS)
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// ---- TMA bulk load global -> shared, completion on an mbarrier ---------------------------------------------------
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_load_row(double* sdst, const double* gsrc, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(sdst)),
-               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-struct MbarWait {
-  unsigned long long* bar;
-  KB_HD void operator()() const {
-#if defined(__CUDA_ARCH__)
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
-    unsigned done = 0;
-    while (!done) {
-      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(addr), "r"(0u) : "memory");
-    }
-#endif
+// Warp-cooperative scatter of the warp's 32 staged rows (ROW doubles each, STRIDE apart in shared memory) to their
+// rows in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store instruction
+// writes one contiguous run.  dst_row < 0 skips a row (ragged tail).
+template <int ROW, int STRIDE>
+__device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, long long dst_row, int lane) {
+  constexpr int kChunks = ROW / 2;     // 16-byte chunks per row
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
+    if (d < 0) continue;
+    const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
+    double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * ROW);
+#pragma unroll
+    for (int c = lane; c < kChunks; c += 32) dst[c] = src[c];
   }
-};
+}
 
 __global__ void k_pack_knots(const double* __restrict__ k7, int n, double* __restrict__ k8) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -91,6 +99,10 @@ __global__ void k_pair_prepass(const double* __restrict__ knots, int n_knots, do
   pair_prepass_item(knots, p, dir, pairs);
 }
 
+// One warp = one tile of 32 consecutive sorted rows; CTAs are small (1-2 warps) and one-shot: the hardware CTA scheduler
+// balances them better than a persistent loop did (measured: profiles/README.md "experiments").
+__device__ __forceinline__ int warp_tile() { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
+
 struct ImuArgs {
   SplineConst sp; ImuConst imu;
   const double* knots; const double* pairs;
@@ -98,27 +110,39 @@ struct ImuArgs {
   int n; uint32_t flags;
   double* r; double* J; int* i0; int* err;
 };
+struct ImuIn { double t, y0, y1, y2, w; int perm; };
+__device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
+  ImuIn in; in.perm = -1; in.t = 0; in.y0 = in.y1 = in.y2 = 0; in.w = 0;
+  if (i < a.n) { in.t = a.t[i]; in.y0 = a.y[3 * (size_t)i]; in.y1 = a.y[3 * (size_t)i + 1]; in.y2 = a.y[3 * (size_t)i + 2]; in.w = a.w[i]; in.perm = a.perm[i]; }
+  return in;
+}
 
 template <int WHICH>
 __global__ void __launch_bounds__(kThreads) k_imu(const ImuArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.n) return;
-  double* row = smem + threadIdx.x * kImuRowStride;
-  const double y[3] = {a.y[3 * (size_t)i], a.y[3 * (size_t)i + 1], a.y[3 * (size_t)i + 2]};
-  double r[3];
-  int i0 = -1;
-  const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, a.t[i], y, a.w[i], r, row, &i0);
-  const size_t dst = (size_t)a.perm[i];
-  if (st != 0) {
-    atomicMin(a.err, st);
-    r[0] = r[1] = r[2] = nan("");
-    for (int c = 0; c < kImuRow; ++c) row[c] = nan("");
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kImuRowStride;
+  double* row = wbase + lane * kImuRowStride;
+  const int tile = warp_tile();
+  if (tile * 32 >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const ImuIn cur = imu_load(a, tile * 32 + lane);
+  if (cur.perm >= 0) {
+    const double y[3] = {cur.y0, cur.y1, cur.y2};
+    double r[3];
+    int i0 = -1;
+    const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, cur.t, y, cur.w, r, row, &i0);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = r[2] = nan("");
+      for (int c = 0; c < kImuRow; ++c) row[c] = nan("");
+    }
+    const size_t dst = (size_t)cur.perm;
+    if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+    if (a.i0) a.i0[dst] = i0;
   }
-  if (a.J && (a.flags & KTK_EVAL_JACOBIANS)) bulk_store_row(a.J + dst * kImuRow, row, kImuRow * 8);
-  if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
-  if (a.i0) a.i0[dst] = i0;
-  bulk_store_wait();
+  __syncwarp();
+  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride>(wbase, a.J, (long long)cur.perm, lane);
 }
 
 struct RefArgs {
@@ -128,20 +152,31 @@ struct RefArgs {
   int n; double* recs; int* err;
 };
 
+// Landmark-reference records come out in record order: a warp's 32 records are one contiguous 32 x 736 B block,
+// written with a single TMA bulk store issued by lane 0.
 __global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
   extern __shared__ __align__(16) double smem[];
-  const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (i >= a.n) return;
-  double* row = smem + threadIdx.x * kRefStride;
-  const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
-  const int st = landmark_ref_row(a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.seg_start[i], a.seg_n[i], a.rho[a.lm[i]], row);
-  if (st != 0) {
-    atomicMin(a.err, st);
-    for (int c = 0; c < kRefStride; ++c) row[c] = nan("");
-    row[7] = -1.0;
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kRefStride;
+  double* row = wbase + lane * kRefStride;
+  const int base = (blockIdx.x * kThreads + threadIdx.x) & ~31;
+  const int i = base + lane;
+  if (base >= a.n) return;
+  if (i < a.n) {
+    const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+    const int st = landmark_ref_row(a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.seg_start[i], a.seg_n[i], a.rho[a.lm[i]], row);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      for (int c = 0; c < kRefStride; ++c) row[c] = nan("");
+      row[7] = -1.0;
+    }
   }
-  bulk_store_row(a.recs + (size_t)i * kRefStride, row, kRefStride * 8);
-  bulk_store_wait();
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(a.recs + (size_t)base * kRefStride, wbase, (unsigned)(min(32, a.n - base) * kRefStride * 8));
+    bulk_store_wait_read();
+  }
 }
 
 struct CamArgs {
@@ -152,39 +187,60 @@ struct CamArgs {
   int n; uint32_t flags;
   double* r; double* J; int* i0r; int* i0o; int* err;
 };
-
-__global__ void __launch_bounds__(kThreads) k_static_rs(const CamArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  __shared__ __align__(8) unsigned long long bar;
-  const int base = blockIdx.x * kThreads;
-  const int i = base + threadIdx.x;
-  const int active = min(kThreads, a.n - base);
-  if (threadIdx.x == 0) mbar_init(&bar, active);
-  __syncthreads();
-  if (i >= a.n) return;
-  double* row = smem + threadIdx.x * kCamRowStride;
-  const int ridx = a.ref_idx[i];
-  mbar_arrive_expect_tx(&bar, ridx >= 0 ? kRefStride * 8 : 0);
-  if (ridx >= 0) bulk_load_row(row + kRefInRow, a.recs + (size_t)ridx * kRefStride, kRefStride * 8, &bar);
-  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
-  double r[2];
-  int ir = -1, io = -1;
-  const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
-  int st = kStatusRange;
-  MbarWait wait{&bar};
-  if (ridx >= 0) st = static_rs_row(a.sp, a.cam, a.knots, a.pairs, row + kRefInRow, ouv, a.obs_t0[i], a.ref_t0[i], a.w[i], hub, r, row, &ir, &io, wait);
-  else wait();
-  const size_t dst = (size_t)a.perm[i];
-  if (st != 0) {
-    atomicMin(a.err, st);
-    r[0] = r[1] = nan(""); ir = io = -1;
-    for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+struct CamIn { double u, v, obs_t0, ref_t0, w, huber; int ridx, perm; };
+__device__ __forceinline__ CamIn cam_load(const CamArgs& a, int i) {
+  CamIn in; in.perm = -1; in.ridx = -1; in.u = in.v = in.obs_t0 = in.ref_t0 = in.w = in.huber = 0;
+  if (i < a.n) {
+    in.u = a.obs_uv[2 * (size_t)i]; in.v = a.obs_uv[2 * (size_t)i + 1]; in.obs_t0 = a.obs_t0[i]; in.ref_t0 = a.ref_t0[i]; in.w = a.w[i];
+    in.huber = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0; in.ridx = a.ref_idx[i]; in.perm = a.perm[i];
   }
-  if (a.J && (a.flags & KTK_EVAL_JACOBIANS)) bulk_store_row(a.J + dst * kCamRow, row, kCamRow * 8);
-  if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
-  if (a.i0r) a.i0r[dst] = ir;
-  if (a.i0o) a.i0o[dst] = io;
-  bulk_store_wait();
+  return in;
+}
+
+__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const CamArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kCamWarpSmem;
+  double* row = wbase + lane * kCamRowStride;
+  const int tile = warp_tile();
+  if (tile * 32 >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const CamIn cur = cam_load(a, tile * 32 + lane);
+  // gather the 32 landmark records of this tile into the row buffers (cooperative 16-B LDGSTS: every instruction moves
+  // one contiguous 512-B run), in flight during the observation-pose evaluation below
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const int ridx = __shfl_sync(0xffffffffu, cur.ridx, rr);
+    if (ridx < 0) continue;
+    const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ridx * kRefStride);
+    double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRowStride + kRefInRow);
+#pragma unroll
+    for (int c = lane; c < kRefStride / 2; c += 32) cp_async16(dst + c, src + c);
+  }
+  const double ouv[2] = {cur.u, cur.v};
+  ObsForward f; f.status = kStatusRange; f.io = -1;
+  if (cur.perm >= 0 && cur.ridx >= 0) {
+    static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
+    static_rs_row_pose(a.knots, a.pairs, f);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  if (cur.perm >= 0) {
+    double r[2];
+    int ir = -1, io = -1;
+    const int st = static_rs_row_finish(a.cam, a.knots, a.pairs, f, row + kRefInRow, ouv, cur.w, cur.huber, r, row, &ir, &io);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = nan(""); ir = io = -1;
+      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+    }
+    const size_t dst = (size_t)cur.perm;
+    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+    if (a.i0r) a.i0r[dst] = ir;
+    if (a.i0o) a.i0o[dst] = io;
+  }
+  __syncwarp();
+  if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)cur.perm, lane);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -374,7 +430,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   // opt in to the shared-memory carve-out the row staging needs
   cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
-  cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kCamRowStride * 8);
+  cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   *out = p;
   return KTK_OK;
@@ -446,7 +502,8 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
     Group& g = *p->groups[gi];
     if (g.n == 0) continue;
     const ktk_group_out& o = outs[gi];
-    const int blocks = (int)((g.n + kThreads - 1) / kThreads);
+    const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
+    const int blocks = (int)((g.n + tpb - 1) / tpb);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
     if (g.kind == KTK_STATIC_RS) {
@@ -462,7 +519,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
-      k_static_rs<<<blocks, kThreads, kThreads * kCamRowStride * 8, s>>>(a);
+      k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {
       ImuArgs a;
       a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);

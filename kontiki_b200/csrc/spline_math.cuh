@@ -29,10 +29,13 @@ namespace kb {
 
 // ---- device data layout ------------------------------------------------------------------------------------------
 // knot record  : 8 doubles  [qx qy qz qw tx ty tz pad]            (64 B, any window start is 16-B aligned for TMA)
-// pair record  : 92 doubles [omega(6) pad(2) D(6x14 row-major)]   (736 B); slot p holds the pair (knot p-1, knot p)
+// pair record  : 104 doubles [omega(6) pad(2) Da(6x8) Db(6x8)]     (832 B); slot p holds the pair (knot p-1, knot p);
+//                Da / Db = d omega / d knot p-1 / d knot p (6 x 7, rows padded to 8 so that every row is 16-B aligned)
 constexpr int kKnotStride = 8;
-constexpr int kPairStride = 92;
+constexpr int kPairStride = 104;
 constexpr int kPairDOff = 8;
+constexpr int kPairSide = 48;      // doubles between Da and Db
+struct alignas(16) Dbl2 { double x, y; };
 constexpr double kGravity = 9.80665;   // constants.h:13,24
 constexpr double kSophusEps = 1e-10;   // Sophus::Constants<double>::epsilon()
 
@@ -181,7 +184,10 @@ KB_HD void pair_prepass_item(const double* knots, int p, int dir, double* pairs)
   D1 a[7], b[7], om[6];
   for (int i = 0; i < 7; ++i) { a[i] = D1(ka[i], dir == i ? 1.0 : 0.0); b[i] = D1(kb_[i], dir == 7 + i ? 1.0 : 0.0); }
   pair_log<D1>(a, b, om);
-  for (int i = 0; i < 6; ++i) rec[kPairDOff + i * 14 + dir] = om[i].d;
+  double* D = rec + kPairDOff + (dir >= 7 ? kPairSide : 0);
+  const int c = dir >= 7 ? dir - 7 : dir;
+  for (int i = 0; i < 6; ++i) D[i * 8 + c] = om[i].d;
+  if (c == 6) for (int i = 0; i < 6; ++i) D[i * 8 + 7] = 0.0;
 }
 
 // =================================================================================================================
@@ -222,40 +228,59 @@ template <int N> KB_HD G6<N> mul_Jr6(const G6<N>& g, const ExpPart& e, double B)
 template <int N> KB_HD G6<N> gadd(const G6<N>& a, const G6<N>& b) { G6<N> r; r.U = radd(a.U, b.U); r.W = radd(a.W, b.W); return r; }
 template <int N> KB_HD G6<N> gscale(double s, const G6<N>& a) { G6<N> r; r.U = rscale(s, a.U); r.W = rscale(s, a.W); return r; }
 
-// J_block(N x 7) (+)= scale * [G.U | G.W](N x 6) * D[:, off:off+7],  D = 6 x 14 row-major
+// J_block(N x 7) (+)= scale * [G.U | G.W](N x 6) * D,   D = one side (6 x 8 padded) of a pair record, 16-B aligned
 template <int N, bool ACC>
-KB_HD void contract_pair(double* J, const G6<N>& g, const double* D, int off, double scale) {
+KB_HD void contract_pair(double* J, const G6<N>& g, const double* D, double scale) {
 #pragma unroll
-  for (int c = 0; c < 7; ++c) {
-    double d[6];
+  for (int h = 0; h < 2; ++h) {            // columns 0..3, then 4..6 (+ pad): N x 4 accumulators at a time
+    double acc[N][4];
 #pragma unroll
-    for (int m = 0; m < 6; ++m) d[m] = D[m * 14 + off + c];
+    for (int r = 0; r < N; ++r)
 #pragma unroll
-    for (int r = 0; r < N; ++r) {
-      double s = 0.0;
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 #pragma unroll
-      for (int m = 0; m < 3; ++m) s += g.U.a[3 * r + m] * d[m] + g.W.a[3 * r + m] * d[3 + m];
-      if (ACC) J[r * 7 + c] += scale * s; else J[r * 7 + c] = scale * s;
+    for (int m = 0; m < 6; ++m) {
+      const Dbl2* d2 = reinterpret_cast<const Dbl2*>(D + m * 8 + 4 * h);
+      const Dbl2 v0 = d2[0], v1 = d2[1];
+      const double d[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        const double gm = m < 3 ? g.U.a[3 * r + m] : g.W.a[3 * r + m - 3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] += gm * d[c];
+      }
     }
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < (h == 0 ? 4 : 3); ++c) {
+        if (ACC) J[r * 7 + 4 * h + c] += scale * acc[r][c]; else J[r * 7 + 4 * h + c] = scale * acc[r][c];
+      }
   }
 }
-// rotation-only version: G (N x 3) * D[3:6, off:off+4]; translation columns of the phi rows are identically zero
+// rotation-only version: G (N x 3) * D[3:6, 0:4]; translation columns of the phi rows are identically zero
 template <int N, bool ACC>
-KB_HD void contract_pair_rot(double* J, const Mr<N>& G, const double* D, int off, double scale) {
+KB_HD void contract_pair_rot(double* J, const Mr<N>& G, const double* D, double scale) {
+  double acc[N][4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    double d[3];
+  for (int r = 0; r < N; ++r)
 #pragma unroll
-    for (int m = 0; m < 3; ++m) d[m] = D[(3 + m) * 14 + off + c];
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 #pragma unroll
-    for (int r = 0; r < N; ++r) {
-      const double s = G.a[3 * r] * d[0] + G.a[3 * r + 1] * d[1] + G.a[3 * r + 2] * d[2];
-      if (ACC) J[r * 7 + c] += scale * s; else J[r * 7 + c] = scale * s;
-    }
+  for (int m = 0; m < 3; ++m) {
+    const Dbl2* d2 = reinterpret_cast<const Dbl2*>(D + (3 + m) * 8);
+    const Dbl2 v0 = d2[0], v1 = d2[1];
+    const double d[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] += G.a[3 * r + m] * d[c];
   }
-  if (!ACC) {
 #pragma unroll
-    for (int r = 0; r < N; ++r) { J[r * 7 + 4] = 0.0; J[r * 7 + 5] = 0.0; J[r * 7 + 6] = 0.0; }
+  for (int r = 0; r < N; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { if (ACC) J[r * 7 + c] += scale * acc[r][c]; else J[r * 7 + c] = scale * acc[r][c]; }
+    if (!ACC) { J[r * 7 + 4] = 0.0; J[r * 7 + 5] = 0.0; J[r * 7 + 6] = 0.0; }
   }
 }
 // quaternion block of knot i0: J[r, 0:4] += scale * (g_theta[r] * dtheta/dq + g_rad[r] * q^T)
@@ -294,12 +319,12 @@ KB_HD void gyro_se3(const double* knot0, const double* p1, const double* p2, con
   const M3 G2 = mul_tn(e3.E, T2);
   const M3 G1 = bs.dB[0] * mul_tn(e3.E, transpose(e2.E));
   const double sc = -weight;
-  contract_pair_rot<3, false>(J + 0, G1, p1 + kPairDOff, 0, sc);
-  contract_pair_rot<3, false>(J + 21, G1, p1 + kPairDOff, 7, sc);
-  contract_pair_rot<3, true>(J + 21, G2, p2 + kPairDOff, 0, sc);
-  contract_pair_rot<3, false>(J + 42, G2, p2 + kPairDOff, 7, sc);
-  contract_pair_rot<3, true>(J + 42, G3, p3 + kPairDOff, 0, sc);
-  contract_pair_rot<3, false>(J + 63, G3, p3 + kPairDOff, 7, sc);
+  contract_pair_rot<3, false>(J + 0, G1, p1 + kPairDOff, sc);
+  contract_pair_rot<3, false>(J + 21, G1, p1 + kPairDOff + kPairSide, sc);
+  contract_pair_rot<3, true>(J + 21, G2, p2 + kPairDOff, sc);
+  contract_pair_rot<3, false>(J + 42, G2, p2 + kPairDOff + kPairSide, sc);
+  contract_pair_rot<3, true>(J + 42, G3, p3 + kPairDOff, sc);
+  contract_pair_rot<3, false>(J + 63, G3, p3 + kPairDOff + kPairSide, sc);
   // radial: P' = R(q0 raw) * M1 (uniform_se3_spline_trajectory.h:178-183) => d(R' R^T)/ds = 2 (I - R0^T) hat(w_world)
   const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
   const M3 R = R0 * (e1.E * (e2.E * e3.E));
@@ -322,112 +347,132 @@ KB_HD void gyro_se3(const double* knot0, const double* p1, const double* p2, con
 // Reverse sweep carries 3x6 adjoints.  J: [4 knots][3][7].
 KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, double weight,
                      const double* y, double* r, double* J) {
-  ExpPart e1, e2, e3;
-  exp_part(p1, bs.B[0], false, false, e1);
-  exp_part(p2, bs.B[1], true, true, e2);
-  exp_part(p3, bs.B[2], true, true, e3);
   const V3 u1 = v3(p1[0], p1[1], p1[2]), f1 = v3(p1[3], p1[4], p1[5]);
   const V3 u2 = v3(p2[0], p2[1], p2[2]), f2 = v3(p2[3], p2[4], p2[5]);
   const V3 u3 = v3(p3[0], p3[1], p3[2]), f3 = v3(p3[3], p3[4], p3[5]);
-  // forward
+  ExpPart e;
+  // forward (exp parts are rebuilt in the reverse sweep instead of being kept alive)
   const V3 s1u = bs.dB[0] * u1, s1w = bs.dB[0] * f1, d1u = bs.d2B[0] * u1, d1w = bs.d2B[0] * f1;
-  const V3 y2w = mul_t(e2.E, s1w), y2u = mul_t(e2.E, s1u - cross(e2.a, s1w));
-  const V3 z2w = mul_t(e2.E, d1w), z2u = mul_t(e2.E, d1u - cross(e2.a, d1w));
+  exp_part(p2, bs.B[1], true, false, e);
+  const M3 E2 = e.E;
+  const V3 y2w = mul_t(e.E, s1w), y2u = mul_t(e.E, s1u - cross(e.a, s1w));
+  const V3 z2w = mul_t(e.E, d1w), z2u = mul_t(e.E, d1u - cross(e.a, d1w));
   const V3 s2u = y2u + bs.dB[1] * u2, s2w = y2w + bs.dB[1] * f2;
   const V3 d2u = z2u - bs.dB[1] * (cross(f2, y2u) + cross(u2, y2w)) + bs.d2B[1] * u2;
   const V3 d2w = z2w - bs.dB[1] * cross(f2, y2w) + bs.d2B[1] * f2;
-  const V3 y3w = mul_t(e3.E, s2w), y3u = mul_t(e3.E, s2u - cross(e3.a, s2w));
-  const V3 z3w = mul_t(e3.E, d2w), z3u = mul_t(e3.E, d2u - cross(e3.a, d2w));
+  exp_part(p3, bs.B[2], true, false, e);
+  const V3 y3w = mul_t(e.E, s2w), y3u = mul_t(e.E, s2u - cross(e.a, s2w));
+  const V3 z3w = mul_t(e.E, d2w), z3u = mul_t(e.E, d2u - cross(e.a, d2w));
   const V3 vb = y3u + bs.dB[2] * u3, wb = y3w + bs.dB[2] * f3;
   const V3 dvb = z3u - bs.dB[2] * (cross(f3, y3u) + cross(u3, y3w)) + bs.d2B[2] * u3;
   const V3 fb = cross(wb, vb) + dvb;
+  M3 T = E2 * e.E;                                        // E2 E3
+  exp_part(p1, bs.B[0], false, false, e);
+  T = e.E * T;                                            // E1 E2 E3
   const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
-  const M3 E23 = e2.E * e3.E;
-  const M3 E123 = e1.E * E23;
-  const M3 R = R0 * E123;
-  const V3 gb = mul_t(R, v3(0.0, 0.0, -kGravity));
+  const V3 gb = mul_t(T, mul_t(R0, v3(0.0, 0.0, -kGravity)));     // R^T g
   const V3 acc = fb + gb;
   r[0] = weight * (y[0] - acc.x); r[1] = weight * (y[1] - acc.y); r[2] = weight * (y[2] - acc.z);
-  // reverse
-  G6<3> gs, gd;                    // adjoints of s3 and s3'
+  // knot i0 directly: tangent through R^T g (d(R^T g) = hat(R^T g) dtheta_body, dtheta_body = T0^T d),
+  // radial through P'' = R(q0 raw) M2 (uniform_se3_spline_trajectory.h:187-190): 2 (f_b - R^T T0 f_b)
+  const double sc = -weight;
+  const M3 hgb = hat(gb);
+  const V3 Tf = T * fb;
+  const V3 rad = 2.0 * (fb - mul_t(T, mul_t(R0, Tf)));
+  // reverse: 3x6 adjoints of (s_j, s_j'), from the last factor to the first; T = E_{j+1}..E_3 rebuilt on the way
+  G6<3> gs, gd, gj, t;
   gs.U = hat(wb); gs.W = (-1.0) * hat(vb);
   gd.U = m3_identity(); gd.W = m3_zero();
-  const M3 hgb = hat(gb);          // d(R^T g) = hat(R^T g) dtheta_body
-  G6<3> g3, g2, g1;
   {
+    exp_part(p3, bs.B[2], true, true, e);
     const G6<3> gy = gadd(gs, gscale(-bs.dB[2], mul_ad(gd, u3, f3)));
-    g3 = gadd(gadd(gscale(bs.dB[2], gs), gscale(bs.d2B[2], gd)), gscale(bs.dB[2], mul_ad(gd, y3u, y3w)));
-    G6<3> t = gadd(mul_ad(gy, y3u, y3w), mul_ad(gd, z3u, z3w));
-    t.W = t.W + hgb;               // F3^T F3 = I
-    g3 = gadd(g3, mul_Jr6(t, e3, bs.B[2]));
-    gs = mul_Adinv(gy, e3.E, e3.a);
-    gd = mul_Adinv(gd, e3.E, e3.a);
+    gj = gadd(gadd(gscale(bs.dB[2], gs), gscale(bs.d2B[2], gd)), gscale(bs.dB[2], mul_ad(gd, y3u, y3w)));
+    t = gadd(mul_ad(gy, y3u, y3w), mul_ad(gd, z3u, z3w));
+    t.W = t.W + hgb;                 // F3^T F3 = I
+    gj = gadd(gj, mul_Jr6(t, e, bs.B[2]));
+    contract_pair<3, false>(J + 63, gj, p3 + kPairDOff + kPairSide, sc);
+    contract_pair<3, false>(J + 42, gj, p3 + kPairDOff, sc);
+    gs = mul_Adinv(gy, e.E, e.a);
+    gd = mul_Adinv(gd, e.E, e.a);
+    T = e.E;
   }
   {
+    exp_part(p2, bs.B[1], true, true, e);
     const G6<3> gy = gadd(gs, gscale(-bs.dB[1], mul_ad(gd, u2, f2)));
-    g2 = gadd(gadd(gscale(bs.dB[1], gs), gscale(bs.d2B[1], gd)), gscale(bs.dB[1], mul_ad(gd, y2u, y2w)));
-    G6<3> t = gadd(mul_ad(gy, y2u, y2w), mul_ad(gd, z2u, z2w));
-    t.W = t.W + mul_nt(hgb, e3.E);   // F3^T F2 = E3^T
-    g2 = gadd(g2, mul_Jr6(t, e2, bs.B[1]));
-    gs = mul_Adinv(gy, e2.E, e2.a);
-    gd = mul_Adinv(gd, e2.E, e2.a);
+    gj = gadd(gadd(gscale(bs.dB[1], gs), gscale(bs.d2B[1], gd)), gscale(bs.dB[1], mul_ad(gd, y2u, y2w)));
+    t = gadd(mul_ad(gy, y2u, y2w), mul_ad(gd, z2u, z2w));
+    t.W = t.W + mul_nt(hgb, T);      // F3^T F2 = E3^T
+    gj = gadd(gj, mul_Jr6(t, e, bs.B[1]));
+    contract_pair<3, true>(J + 42, gj, p2 + kPairDOff + kPairSide, sc);
+    contract_pair<3, false>(J + 21, gj, p2 + kPairDOff, sc);
+    gs = mul_Adinv(gy, e.E, e.a);
+    gd = mul_Adinv(gd, e.E, e.a);
+    T = e.E * T;
   }
   {
-    g1 = gadd(gscale(bs.dB[0], gs), gscale(bs.d2B[0], gd));
+    exp_part(p1, bs.B[0], false, false, e);
+    gj = gadd(gscale(bs.dB[0], gs), gscale(bs.d2B[0], gd));
     // rotation of A1 only enters through R^T g:  F3^T F1 = (E2 E3)^T
-    g1.W = g1.W + bs.B[0] * mul_nt(mul_nt(hgb, E23), e1.V);
+    gj.W = gj.W + bs.B[0] * mul_nt(mul_nt(hgb, T), e.V);
+    contract_pair<3, true>(J + 21, gj, p1 + kPairDOff + kPairSide, sc);
+    contract_pair<3, false>(J + 0, gj, p1 + kPairDOff, sc);
+    T = e.E * T;
   }
-  const double sc = -weight;
-  contract_pair<3, false>(J + 0, g1, p1 + kPairDOff, 0, sc);
-  contract_pair<3, false>(J + 21, g1, p1 + kPairDOff, 7, sc);
-  contract_pair<3, true>(J + 21, g2, p2 + kPairDOff, 0, sc);
-  contract_pair<3, false>(J + 42, g2, p2 + kPairDOff, 7, sc);
-  contract_pair<3, true>(J + 42, g3, p3 + kPairDOff, 0, sc);
-  contract_pair<3, false>(J + 63, g3, p3 + kPairDOff, 7, sc);
-  // knot i0 directly: tangent through R^T g, radial through P'' = R(q0 raw) M2 (uniform_se3_spline_trajectory.h:187-190)
-  const V3 rad = 2.0 * (fb - mul_t(R, E123 * fb));
   const double radv[3] = {rad.x, rad.y, rad.z};
-  add_q0_block<3>(J, mul_nt(hgb, E123), radv, knot0, sc);
+  add_q0_block<3>(J, mul_nt(hgb, T), radv, knot0, sc);
 }
 
 // ---- pose (position + orientation) of the cumulative spline and its reverse sweep ---------------------------------
-//   R = R0 E1 E2 E3,  p = t0 + R0 (a1 + E1 (a2 + E2 a3))
-struct Pose { ExpPart e1, e2, e3; M3 R0, F1, F2, R; V3 c1, c2, p; };
+//   R = R0 E1 E2 E3,  p = t0 + R0 c1,  c1 = a1 + E1 c2,  c2 = a2 + E2 a3
+// Both sweeps run from the last factor to the first and carry only the body-frame tail T = E_{j+1} ... E_3 and
+// c = c_{j+1}; the exp parts are rebuilt per level in the reverse sweep, which is far cheaper than keeping
+// 3 x 33 doubles (plus the partial products) alive in registers between the sweeps.
+struct Pose { M3 R; V3 p; };
 KB_HD void pose_forward(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, Pose& P) {
-  exp_part(p1, bs.B[0], true, true, P.e1);
-  exp_part(p2, bs.B[1], true, true, P.e2);
-  exp_part(p3, bs.B[2], true, true, P.e3);
-  P.R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
-  P.F1 = P.R0 * P.e1.E; P.F2 = P.F1 * P.e2.E; P.R = P.F2 * P.e3.E;
-  P.c2 = P.e2.a + P.e2.E * P.e3.a;
-  P.c1 = P.e1.a + P.e1.E * P.c2;
-  P.p = v3(knot0[4], knot0[5], knot0[6]) + P.R0 * P.c1;
+  ExpPart e;
+  exp_part(p3, bs.B[2], true, false, e);
+  M3 T = e.E; V3 c = e.a;
+  exp_part(p2, bs.B[1], true, false, e);
+  c = e.a + e.E * c; T = e.E * T;
+  exp_part(p1, bs.B[0], true, false, e);
+  c = e.a + e.E * c; T = e.E * T;
+  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
+  P.R = R0 * T;
+  P.p = v3(knot0[4], knot0[5], knot0[6]) + R0 * c;
 }
-// Given N row-adjoints with respect to p (world, additive) and to a body-frame rotation perturbation R <- R Exp(d),
-// writes scale * d(row)/d(knots i0..i0+3) into J ([4][N][7]).
+// Given N row-adjoints Gp with respect to p (world, additive; GpR = Gp * R is passed too because the callers have it
+// for free) and Gth to a body-frame rotation perturbation R <- R Exp(d), writes scale * d(row)/d(knots i0..i0+3)
+// into J ([4][N][7]).  With F_j = R0 E1..E_j = R T_j^T:
+//   eps_j = B_j Jr6(B_j w_j) d(w_j):  d/d(eps_rho_j) = Gp F_j = GpR T_j^T,  d/d(eps_theta_j) = Gth T_j^T - (GpR T_j^T) hat(c_{j+1})
 template <int N>
-KB_HD void pose_backward(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, const Pose& P,
-                         const Mr<N>& Gp, const Mr<N>& Gth, double scale, double* J) {
+KB_HD void pose_backward(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs,
+                         const Mr<N>& Gp, const Mr<N>& GpR, const Mr<N>& Gth, double scale, double* J) {
   G6<N> g, t;
-  // eps_j = B_j Jr6 d(omega_j):  d/d(eps_rho_j) = Gp F_j,  d/d(eps_theta_j) = -(Gp F_j) hat(c_{j+1}) + Gth F3^T F_j
-  const M3 E23 = P.e2.E * P.e3.E;
-  t.U = rmul(Gp, P.F1); t.W = rsub(rmul_nt(Gth, E23), rmul_hat(t.U, P.c2));
-  g = mul_Jr6(t, P.e1, bs.B[0]);
-  contract_pair<N, false>(J + 0 * N * 7, g, p1 + kPairDOff, 0, scale);
-  contract_pair<N, false>(J + 1 * N * 7, g, p1 + kPairDOff, 7, scale);
-  t.U = rmul(Gp, P.F2); t.W = rsub(rmul_nt(Gth, P.e3.E), rmul_hat(t.U, P.e3.a));
-  g = mul_Jr6(t, P.e2, bs.B[1]);
-  contract_pair<N, true>(J + 1 * N * 7, g, p2 + kPairDOff, 0, scale);
-  contract_pair<N, false>(J + 2 * N * 7, g, p2 + kPairDOff, 7, scale);
-  t.U = rmul(Gp, P.R); t.W = Gth;
-  g = mul_Jr6(t, P.e3, bs.B[2]);
-  contract_pair<N, true>(J + 2 * N * 7, g, p3 + kPairDOff, 0, scale);
-  contract_pair<N, false>(J + 3 * N * 7, g, p3 + kPairDOff, 7, scale);
-  // knot i0 directly: t0 additive; R0 <- R0 Exp(d): dp = -R0 hat(c1) d, dtheta_body = (E1 E2 E3)^T d;
+  ExpPart e;
+  exp_part(p3, bs.B[2], true, true, e);
+  t.U = GpR; t.W = Gth;
+  g = mul_Jr6(t, e, bs.B[2]);
+  contract_pair<N, false>(J + 3 * N * 7, g, p3 + kPairDOff + kPairSide, scale);
+  contract_pair<N, false>(J + 2 * N * 7, g, p3 + kPairDOff, scale);
+  M3 T = e.E; V3 c = e.a;
+  exp_part(p2, bs.B[1], true, true, e);
+  t.U = rmul_nt(GpR, T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
+  g = mul_Jr6(t, e, bs.B[1]);
+  contract_pair<N, true>(J + 2 * N * 7, g, p2 + kPairDOff + kPairSide, scale);
+  contract_pair<N, false>(J + 1 * N * 7, g, p2 + kPairDOff, scale);
+  c = e.a + e.E * c; T = e.E * T;
+  exp_part(p1, bs.B[0], true, true, e);
+  t.U = rmul_nt(GpR, T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
+  g = mul_Jr6(t, e, bs.B[0]);
+  contract_pair<N, true>(J + 1 * N * 7, g, p1 + kPairDOff + kPairSide, scale);
+  contract_pair<N, false>(J + 0 * N * 7, g, p1 + kPairDOff, scale);
+  c = e.a + e.E * c; T = e.E * T;
+  // knot i0 directly: t0 additive; R0 <- R0 Exp(d): dp = -R0 hat(c1) d, dtheta_body = T0^T d;
   // radial: P.t = t0 + q0 * a1 + ... with Eigen's polynomial q*v  =>  dp/ds = 2 (R0 - I) a1
-  const Mr<N> GpR0 = rmul(Gp, P.R0);
-  const Mr<N> Gth0 = rsub(rmul_nt(Gth, P.e1.E * E23), rmul_hat(GpR0, P.c1));
-  const V3 dps = 2.0 * (P.R0 * P.e1.a - P.e1.a);
+  const Mr<N> GpR0 = rmul_nt(GpR, T);
+  const Mr<N> Gth0 = rsub(rmul_nt(Gth, T), rmul_hat(GpR0, c));
+  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
+  const V3 dps = 2.0 * (R0 * e.a - e.a);
   double grad[N];
 #pragma unroll
   for (int r = 0; r < N; ++r) grad[r] = dot(rrow(Gp, r), dps);
@@ -480,21 +525,18 @@ KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const doub
   const V3 dXr = P.p - P.R * mul_t(Rct, pct);
   rec[0] = X.x; rec[1] = X.y; rec[2] = X.z; rec[3] = dXr.x; rec[4] = dXr.y; rec[5] = dXr.z; rec[6] = rho; rec[7] = (double)i0;
   // X = R_r Xref + rho p_r:  dX/dp_r = rho I,  dX/dtheta_r = -R_r hat(Xref)
-  pose_backward<3>(k0, p1, p2, p3, bs, P, rho * m3_identity(), (-1.0) * mul_hat(P.R, Xref), 1.0, rec + kRefDOff);
+  pose_backward<3>(k0, p1, p2, p3, bs, rho * m3_identity(), rho * P.R, (-1.0) * mul_hat(P.R, Xref), 1.0, rec + kRefDOff);
 }
 
 // Observation side, per measurement.  `ref` is the landmark record above; its dX/dknots part may alias J (the row
 // buffer) at J + kRefInRow: the reference-window blocks are produced front to back, each read before it is overwritten.
 // J: [ref window: 4 knots][2][7] (56) | [obs window: 4 knots][2][7] (56) | d r / d rho (2)
 constexpr int kRefInRow = 22;      // 22 + 92 = 114 = row length; block k is read at 30 + 21 k and written at 14 k
-struct NoWait { KB_HD void operator()() const {} };
-template <class WaitFn>
+// (the observation pose P is evaluated by the caller first: it does not need the landmark record, so the kernels
+//  overlap the record gather with it)
 KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const double* p1, const double* p2, const double* p3, const Basis& bs,
-                             const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J, int* i0_ref,
-                             const WaitFn& wait_ref) {
-  Pose P;
-  pose_forward(k0, p1, p2, p3, bs, P);
-  wait_ref();                                  // the landmark record may still be in flight (TMA) up to here
+                             const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J,
+                             int* i0_ref) {
   *i0_ref = (int)ref[7];
   const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
   const double rho = ref[6];
@@ -542,7 +584,7 @@ KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const dou
   const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
   const double jr0 = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z, jr1 = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
   // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
-  pose_backward<2>(k0, p1, p2, p3, bs, P, rscale(-rho, GX), rmul_hat(Go, Xobs), 1.0, J + 56);
+  pose_backward<2>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, J + 56);
   J[112] = jr0; J[113] = jr1;
 }
 
@@ -620,21 +662,33 @@ KB_HD int landmark_ref_row(const SplineConst& sp, const CameraConst& cam, const 
 
 // static RS camera row; static_rscamera_measurement.h:130-198 builds the two spans, :112-123 / :21-55 evaluate.
 // huber_c > 0 applies ceres::HuberLoss + Corrector to (r, J) as Ceres does after Evaluate.
-template <class WaitFn>
-KB_HD int static_rs_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref,
-                        const double* obs_uv, double obs_t0, double ref_t0, double weight, double huber_c, double* r, double* J,
-                        int* i0_ref_out, int* i0_obs_out, const WaitFn& wait_ref) {
+// Part 1 (no landmark record needed): spans, segment lookup and basis, then the observation pose.  The two halves are
+// separate so that a kernel can choose where `pairs` points (global table or a staged window) once i0 is known.
+struct ObsForward { int status, io; Basis bo; Pose P; };
+KB_HD void static_rs_row_locate(const SplineConst& sp, const CameraConst& cam, const double* obs_uv, double obs_t0, double ref_t0, ObsForward& f) {
   Segment s0, s1;
   const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
-  int io = -1; double uo = 0.0;
-  if (nseg == 0 || locate_in_segments(nseg, s0, s1, static_rs_time(cam, obs_t0, obs_uv[1]), sp.t0, sp.dt, io, uo) < 0) { wait_ref(); return kStatusRange; }
-  const Basis bo = cumulative_basis(uo, sp.dt);
-  const double* po1 = pairs + (size_t)(io + 1) * kPairStride;
+  double uo = 0.0;
+  f.io = -1;
+  if (nseg == 0 || locate_in_segments(nseg, s0, s1, static_rs_time(cam, obs_t0, obs_uv[1]), sp.t0, sp.dt, f.io, uo) < 0) { f.status = kStatusRange; f.io = -1; return; }
+  f.status = 0;
+  f.bo = cumulative_basis(uo, sp.dt);
+}
+KB_HD void static_rs_row_pose(const double* knots, const double* pairs, ObsForward& f) {
+  if (f.status != 0) return;
+  const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
+  pose_forward(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, f.P);
+}
+// Part 2: projection, residual, Jacobian row (ref = landmark record, may alias J + kRefInRow).
+KB_HD int static_rs_row_finish(const CameraConst& cam, const double* knots, const double* pairs, const ObsForward& f, const double* ref,
+                               const double* obs_uv, double weight, double huber_c, double* r, double* J, int* i0_ref_out, int* i0_obs_out) {
+  if (f.status != 0) return f.status;
+  const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
   int ir;
-  static_rs_obs_se3(cam, knots + (size_t)io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, bo, ref, obs_uv, weight, huber_c, r, J,
-                    &ir, wait_ref);
+  static_rs_obs_se3(cam, knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, f.P, ref, obs_uv, weight, huber_c,
+                    r, J, &ir);
   if (ir < 0) return kStatusRange;                 // the landmark record itself was out of range
-  *i0_ref_out = ir; *i0_obs_out = io;
+  *i0_ref_out = ir; *i0_obs_out = f.io;
   return 0;
 }
 

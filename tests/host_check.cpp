@@ -55,8 +55,10 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
     if (status[i] != 0) continue;
     // K_obs: the observation row
-    status[i] = static_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row,
-                              i0_ref + i, i0_obs + i, NoWait());
+    ObsForward f;
+    static_rs_row_locate(sp, cam, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
+    static_rs_row_pose(knots8, pairs, f);
+    status[i] = static_rs_row_finish(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, i0_ref + i, i0_obs + i);
   }
 }
 

@@ -38,7 +38,7 @@ def _f(a):
 def prepass(knots7):
     knots7 = _f(knots7)
     n = len(knots7)
-    k8, pairs = np.zeros((n, 8)), np.zeros((n, 92))
+    k8, pairs = np.zeros((n, 8)), np.zeros((n, 104))
     lib().hc_prepass(_p(knots7), n, _p(k8), _p(pairs))
     return k8, pairs
 
