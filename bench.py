@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NTHREADS = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)      # the CPU arm uses every host core explicitly (torchrun exports OMP_NUM_THREADS=1)
 METRIC = "measurements/s (residual+Jacobian eval)"
 UNIT = "measurements/s"
 
@@ -81,12 +82,13 @@ def oracle_step(cfg, sample):
     for which, k in ((0, "gyro"), (1, "accel")):
         if k in sample:
             m = sample[k]
-            res = kto.imu_residuals(traj, imu, which, m["t"], m["y"], m["weight"], jac_mode=1)
+            res = kto.imu_residuals(traj, imu, which, m["t"], m["y"], m["weight"], jac_mode=1, nthreads=NTHREADS)
             rows += len(m["t"]); secs += res["eval_seconds"]
     if "cam" in sample:
         c = sample["cam"]
         ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"])
-        res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24)
+        res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24,
+                                      nthreads=NTHREADS)
         rows += len(c["lm_idx"]); secs += res["eval_seconds"]
     return rows, secs
 
@@ -104,7 +106,7 @@ def cpu_baseline(cfg, frac, steps=1, warmup=1, budget_s=12.0):
     for _ in range(steps):
         r, s = oracle_step(cfg, sample)
         rows += r; secs += s
-    return {"value": rows / secs, "unit": UNIT, "cores": kto.num_threads(), "kind": "port",
+    return {"value": rows / secs, "unit": UNIT, "cores": NTHREADS, "kind": "port",
             "sample": f"{rows // steps} rows per step ({frac:.3g} of the workload, same type mix), {steps} step(s), "
                       "time inside the per-block Evaluate loop only (problem construction excluded), OpenMP over blocks"}, rows, secs
 
@@ -166,6 +168,9 @@ def main():
         print(json.dumps(line))
         return
 
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner) write to fd 1 during the run
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     from kontiki_b200 import _lib
     if not torch.cuda.is_available():
@@ -321,10 +326,12 @@ def main():
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
                          "kernel_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in prof.items()}}}
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:
         base, _, _ = cpu_baseline(cfg, a.cpu_sample)
         line["cpu_baseline"] = base
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
