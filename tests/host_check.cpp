@@ -4,7 +4,7 @@
 #include <cstddef>
 #include <vector>
 
-#include "../kontiki_b200/csrc/spline_math.cuh"
+#include "../kontiki_b200/csrc/split_math.cuh"
 
 using namespace kb;
 
@@ -59,6 +59,59 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     static_rs_row_locate(sp, cam, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
     static_rs_row_pose(knots8, pairs, f);
     status[i] = static_rs_row_finish(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, i0_ref + i, i0_obs + i);
+  }
+}
+
+
+// ---- split (R3 + SO3) trajectory ----------------------------------------------------------------------------------------
+void hc_split_prepass(const double* vecs3, int n_r3, const double* quats, int n_so3, double* vecs4, double* pairs, int* status) {
+  for (int i = 0; i < n_r3; ++i) { for (int c = 0; c < 3; ++c) vecs4[(size_t)i * kVecStride + c] = vecs3[(size_t)i * 3 + c]; vecs4[(size_t)i * kVecStride + 3] = 0.0; }
+  for (int c = 0; c < kSo3PairStride; ++c) pairs[c] = 0.0;
+  *status = 0;
+  for (int p = 1; p < n_so3; ++p) for (int dir = 0; dir <= 8; ++dir) { const int st = so3_pair_prepass_item(quats, p, dir, pairs); if (st) *status = st; }
+}
+
+void hc_imu_split(int which, double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, double time_offset,
+                  double max_time_offset, int locked, const double* vecs4, const double* quats, const double* pairs, int n, const double* t,
+                  const double* y, const double* w, double* r, double* J, int* i0_r3, int* i0_so3, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  ImuConst imu{time_offset, max_time_offset, locked};
+  const int row = which == 0 ? 48 : 84;
+  for (int i = 0; i < n; ++i) {
+    i0_r3[i] = -1; i0_so3[i] = -1;
+    status[i] = imu_row_split(which, sp, imu, vecs4, quats, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)row * i, i0_r3 + i, i0_so3 + i);
+  }
+}
+
+void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, const double* K, const double* Kinv,
+                        const double* q_ct, const double* p_ct, double time_offset, double max_time_offset, int locked, double readout, int rows,
+                        const double* vecs4, const double* quats, const double* pairs, int n, const double* obs_uv, const double* obs_t0,
+                        const double* ref_uv, const double* ref_t0, const int* lm_idx, const double* rho, const double* w, const double* huber_c,
+                        double* r, double* J, int* idx /*[n][4]: ref R3, obs R3, ref SO3, obs SO3*/, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
+  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  for (int i = 0; i < n; ++i) {
+    for (int c = 0; c < 4; ++c) idx[4 * i + c] = -1;
+    double* row = J + (size_t)114 * i;
+    double* rec = row + kRefSplitInRow;
+    const double tr = static_rs_time(cam, ref_t0[i], ref_uv[2 * i + 1]);
+    Segment a0, a1, b0, b1; int ia, ib; double ua, ub;
+    const int na = static_rs_segments_split(sp, cam, ref_t0[i], obs_t0[i], sp.t0_r3, sp.dt_r3, a0, a1);
+    const int nb = static_rs_segments_split(sp, cam, ref_t0[i], obs_t0[i], sp.t0_so3, sp.dt_so3, b0, b1);
+    const int wa = na == 0 ? -1 : locate_in_segments(na, a0, a1, tr, sp.t0_r3, sp.dt_r3, ia, ua);
+    const int wb = nb == 0 ? -1 : locate_in_segments(nb, b0, b1, tr, sp.t0_so3, sp.dt_so3, ib, ub);
+    if (wa < 0 || wb < 0) { status[i] = kStatusRange; continue; }
+    const Segment& sa = wa == 0 ? a0 : a1; const Segment& sb = wb == 0 ? b0 : b1;
+    status[i] = landmark_ref_row_split(sp, cam, vecs4, quats, pairs, ref_uv + 2 * i, ref_t0[i], sa.start, sa.n, sb.start, sb.n, rho[lm_idx[i]], rec);
+    if (status[i] != 0) continue;
+    ObsForwardSplit f;
+    static_rs_row_forward_split(sp, cam, quats, pairs, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
+    status[i] = static_rs_row_finish_split(cam, vecs4, quats, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, idx + 4 * i);
   }
 }
 

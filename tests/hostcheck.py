@@ -19,7 +19,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "lie_math.cuh", "dualnum.cuh")]
+        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "split_math.cuh", "lie_math.cuh", "dualnum.cuh")]
         if not os.path.exists(_OUT) or any(os.path.getmtime(d) > os.path.getmtime(_OUT) for d in deps):
             os.makedirs(os.path.dirname(_OUT), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", _SRC, "-o", _OUT])
@@ -83,3 +83,44 @@ def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
                        C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows), _p(k8), _p(pairs), n,
                        _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc), _p(r), _p(J), _p(ir), _p(io), _p(st))
     return dict(r=r, J=J, i0_ref=ir, i0_obs=io, status=st)
+
+
+# ---- split (R3 + SO3) trajectory ----------------------------------------------------------------------------------------
+def split_prepass(vecs3, quats):
+    vecs3, quats = _f(vecs3), _f(quats)
+    v4, pairs = np.zeros((len(vecs3), 4)), np.zeros((len(quats), 28))
+    st = C.c_int(0)
+    lib().hc_split_prepass(_p(vecs3), len(vecs3), _p(quats), len(quats), _p(v4), _p(pairs), C.byref(st))
+    return v4, quats, pairs, st.value
+
+
+def imu_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, y, w=None, time_offset=0.0, max_time_offset=0.1, locked=True):
+    v4, q4, pairs, st0 = split_prepass(vecs3, quats)
+    t, y = _f(t), _f(y).reshape(-1, 3)
+    n = len(t)
+    w = np.ones(n) if w is None else _f(w)
+    r = np.zeros((n, 3))
+    J = np.zeros((n, 48)) if which == 0 else np.zeros((n, 84))
+    ia, ib, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().hc_imu_split(int(which), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), C.c_double(time_offset),
+                       C.c_double(max_time_offset), int(locked), _p(v4), _p(q4), _p(pairs), n, _p(t), _p(y), _p(w), _p(r), _p(J), _p(ia), _p(ib), _p(st))
+    return dict(r=r, J=J, i0_r3=ia, i0_so3=ib, status=st, prepass_status=st0)
+
+
+def static_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    v4, q4, pairs, st0 = split_prepass(vecs3, quats)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    r, J = np.zeros((n, 2)), np.zeros((n, 114))
+    idx, st = np.zeros((n, 4), np.int32), np.zeros(n, np.int32)
+    lib().hc_static_rs_split(C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(K), _p(Kinv),
+                             _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked),
+                             C.c_double(cam.readout), int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0),
+                             _p(lm_idx), _p(rho), _p(w), _p(hc), _p(r), _p(J), _p(idx), _p(st))
+    return dict(r=r, J=J, idx=idx, status=st)
