@@ -26,6 +26,11 @@
  *                        i0_ref, i0_obs = first active knot of the two spline evaluations.  A knot that is in both
  *                        windows receives the SUM of its two blocks (one parameter block in the reference);
  *                        ktk_expand_static_rs() produces the reference's structural per-block layout.
+ * Split trajectory (UniformR3SplineTrajectory + UniformSO3SplineTrajectory, split_trajectory.h): knots are passed as
+ *   [R3 knots: n_r3 x 3 | SO3 knots: n_so3 x 4 (x,y,z,w)], the parameter order of SplitEntity (split_trajectory.h:34-39);
+ *   gyro row  : J[4 SO3 knots][3][4] (48);          the R3 blocks of the residual are structurally present but zero
+ *   accel row : J[4 R3 knots][3][3] (36) | [4 SO3 knots][3][4] (48)
+ *   static RS : J[ref R3 4x(2x3)] (24) | [ref SO3 4x(2x4)] (32) | [obs R3] (24) | [obs SO3] (32) | [d r/d rho] (2)
  * Rows are returned in the caller's order of insertion, whatever order the device processes them in.
  */
 #ifndef KONTIKI_B200_H_
@@ -79,8 +84,10 @@ typedef struct {
 typedef struct {
   double* r;
   double* J;
-  int32_t* i0;       /* IMU: i0;  camera: i0_ref */
-  int32_t* i0_b;     /* camera: i0_obs; unused for IMU */
+  int32_t* i0;       /* SE3 (or the R3 part of a split trajectory): IMU i0;  camera i0_ref */
+  int32_t* i0_b;     /*                                             camera i0_obs; unused for IMU */
+  int32_t* i0_c;     /* SO3 part of a split trajectory: IMU i0;  camera i0_ref   (unused for SE3) */
+  int32_t* i0_d;     /*                                 camera i0_obs */
 } ktk_group_out;
 
 const char* ktk_last_error(void);
@@ -98,6 +105,10 @@ int ktk_set_stream(ktk_problem* p, void* cuda_stream);
  * the reference's Jet-path accelerometer on SE3 (dB left at zero, uniform_se3_spline_trajectory.h:138-141 vs :166-169). */
 int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, int32_t compat_zero_dB);
 
+/* SplitTrajectory(UniformR3SplineTrajectory(dt_r3, t0_r3), UniformSO3SplineTrajectory(dt_so3, t0_so3))
+ * (split_trajectory.h:87-105; valid time = intersection of the two, :60-66). */
+int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r3, double dt_so3, double t0_so3, int32_t n_so3);
+
 /* *Measurement::AddToEstimator, batched: returns the group id (>= 0) or a negative status.  Arrays are copied.
  *   gyroscope / accelerometer: t[n], y[3n], weight[n] (NULL = 1)   (gyroscope_measurement.h:18-20)
  *   static RS: obs_uv[2n], obs_t0[n] (view t0 of the observation), ref_uv[2n], ref_t0[n] (of the landmark's reference
@@ -111,6 +122,8 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, 
 int32_t ktk_num_groups(const ktk_problem* p);
 int64_t ktk_group_size(const ktk_problem* p, int32_t group);
 int32_t ktk_group_kind(const ktk_problem* p, int32_t group);
+int32_t ktk_group_row_size(const ktk_problem* p, int32_t group);   /* doubles per packed Jacobian row (84 / 114 / 48) */
+int64_t ktk_num_knot_doubles(const ktk_problem* p);                /* length of the `knots` argument of ktk_evaluate */
 
 /* One batched evaluation at the parameter point (knots[n_knots*7], rho[n_rho]) with HOST buffers: uploads the point,
  * runs the kernels, downloads every non-NULL output of outs[0..num_groups), returns when they are complete.
@@ -140,6 +153,9 @@ void ktk_host_free(void* ptr);
  * (spline_base.h:361-404 knot range / segment rule): knot ids in parameter-block order, -1 padded to `cap`.
  * n_ids[i] = number of knot blocks.  Host-side, no device work.  Returns KTK_EINVAL if cap is too small. */
 int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids);
+/* Split trajectory: ktk_get_structure answers for the R3 spline, this one for the SO3 spline (the residual's parameter
+ * blocks are all R3 knots, then all SO3 knots, split_trajectory.h:117-123). */
+int ktk_get_structure_so3(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids);
 
 /* Packed static-RS rows -> the reference's structural blocks: out[n][cap][2][7] for the knot ids of ktk_get_structure
  * (zero for knots in the segment that are not active).  Host-side helper for Ceres-style consumers. */

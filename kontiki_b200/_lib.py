@@ -25,13 +25,14 @@ class PinholeCamera(C.Structure):
 
 
 class GroupOut(C.Structure):
-    _fields_ = [("r", C.c_void_p), ("J", C.c_void_p), ("i0", C.c_void_p), ("i0_b", C.c_void_p)]
+    _fields_ = [("r", C.c_void_p), ("J", C.c_void_p), ("i0", C.c_void_p), ("i0_b", C.c_void_p), ("i0_c", C.c_void_p), ("i0_d", C.c_void_p)]
 
 
 EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_set_stream", "ktk_set_se3_spline", "ktk_add_gyroscope",
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
-           "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile"]
+           "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
+           "ktk_get_structure_so3"]
 
 _lib = None
 
@@ -73,6 +74,11 @@ def lib():
         L.ktk_launch_count.argtypes = [C.c_void_p]
         L.ktk_get_structure.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.ktk_expand_static_rs.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
+        L.ktk_set_split_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32]
+        L.ktk_group_row_size.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_num_knot_doubles.argtypes = [C.c_void_p]
+        L.ktk_num_knot_doubles.restype = C.c_int64
+        L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         _lib = L
@@ -126,6 +132,7 @@ class Problem:
         check(lib().ktk_problem_create(int(device), C.byref(self._h)))
         self.device = device
         self.n_knots = 0
+        self.split = False
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -144,6 +151,13 @@ class Problem:
     def set_se3_spline(self, dt, t0, n_knots, compat_zero_dB=False):
         check(lib().ktk_set_se3_spline(self._h, float(dt), float(t0), int(n_knots), int(compat_zero_dB)))
         self.n_knots = int(n_knots)
+
+    def set_split_spline(self, dt_r3, t0_r3, n_r3, dt_so3, t0_so3, n_so3):
+        check(lib().ktk_set_split_spline(self._h, float(dt_r3), float(t0_r3), int(n_r3), float(dt_so3), float(t0_so3), int(n_so3)))
+        self.split, self.n_r3, self.n_so3 = True, int(n_r3), int(n_so3)
+
+    def group_row_size(self, g):
+        return lib().ktk_group_row_size(self._h, g)
 
     def _add_imu(self, fn, sensor, t, y, weight):
         t, y = _f64(t), _f64(y).reshape(-1, 3)
@@ -191,9 +205,13 @@ class Problem:
             n, cam = self.group_size(g), self.group_kind(g) == STATIC_RS
             o = dict(r=np.zeros((n, 2 if cam else 3)), i0=np.full(n, -1, np.int32))
             if jacobians:
-                o["J"] = np.zeros((n, CAM_ROW)) if cam else np.zeros((n, 4, 3, 7))
+                o["J"] = np.zeros((n, 4, 3, 7)) if (not cam and not self.split) else np.zeros((n, self.group_row_size(g)))
             if cam:
                 o["i0_b"] = np.full(n, -1, np.int32)
+            if self.split:
+                o["i0_c"] = np.full(n, -1, np.int32)
+                if cam:
+                    o["i0_d"] = np.full(n, -1, np.int32)
             outs.append(o)
         return outs
 
@@ -205,13 +223,21 @@ class Problem:
             arr[i].J = getptr(o.get("J"))
             arr[i].i0 = getptr(o.get("i0"))
             arr[i].i0_b = getptr(o.get("i0_b"))
+            arr[i].i0_c = getptr(o.get("i0_c"))
+            arr[i].i0_d = getptr(o.get("i0_d"))
         return arr
 
     def evaluate(self, knots, rho=None, flags=EVAL_RESIDUALS | EVAL_JACOBIANS, outs=None):
         """Host-buffer evaluation (ktk_evaluate).  knots: (n_knots, 7) [qx qy qz qw tx ty tz]; returns the list of group outputs."""
-        knots = _f64(knots)
-        if knots.shape != (self.n_knots, 7):
-            raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
+        if self.split:      # (r3 knots (n_r3,3), so3 knots (n_so3,4) x,y,z,w) -> [R3 | SO3], the order of split_trajectory.h:34-39
+            r3, so3 = _f64(knots[0]), _f64(knots[1])
+            if r3.shape != (self.n_r3, 3) or so3.shape != (self.n_so3, 4):
+                raise ValueError(f"knots must be ((n_r3={self.n_r3}, 3), (n_so3={self.n_so3}, 4))")
+            knots = np.concatenate([r3.reshape(-1), so3.reshape(-1)])
+        else:
+            knots = _f64(knots)
+            if knots.shape != (self.n_knots, 7):
+                raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
         rho = None if rho is None else _f64(rho)
         if outs is None:
             outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS))
@@ -240,6 +266,12 @@ class Problem:
         n = self.group_size(g)
         ids, nids = np.full((n, cap), -1, np.int32), np.zeros(n, np.int32)
         check(lib().ktk_get_structure(self._h, g, cap, _ptr(ids), _ptr(nids)))
+        return ids, nids
+
+    def get_structure_so3(self, g, cap=16):
+        n = self.group_size(g)
+        ids, nids = np.full((n, cap), -1, np.int32), np.zeros(n, np.int32)
+        check(lib().ktk_get_structure_so3(self._h, g, cap, _ptr(ids), _ptr(nids)))
         return ids, nids
 
     def expand_static_rs(self, g, ids, J, i0_ref, i0_obs):

@@ -23,7 +23,7 @@
 #include <vector>
 
 #include "../../include/kontiki_b200.h"
-#include "spline_math.cuh"
+#include "split_math.cuh"
 
 using namespace kb;
 
@@ -243,6 +243,152 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)cur.perm, lane);
 }
 
+// =====================================================================================================================
+// Split trajectory (R3 + SO3) kernels: same tiling and data movement as above, rows of 48 / 84 / 114 doubles.
+// =====================================================================================================================
+constexpr int kGyroSplitRow = 48, kGyroSplitStride = 50;
+constexpr int kAccelSplitRow = 84, kAccelSplitStride = 86;
+
+__global__ void k_pack_vecs(const double* __restrict__ v3, int n, double* __restrict__ v4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kVecStride) return;
+  const int k = i / kVecStride, c = i % kVecStride;
+  v4[i] = c < 3 ? v3[(size_t)k * 3 + c] : 0.0;
+}
+__global__ void k_so3_pair_prepass(const double* __restrict__ quats, int n, double* __restrict__ pairs, int* err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = 1 + i / 9, dir = i % 9;
+  if (p >= n) return;
+  const int st = so3_pair_prepass_item(quats, p, dir, pairs);
+  if (st != 0) atomicMin(err, st);
+}
+
+struct ImuSplitArgs {
+  SplitConst sp; ImuConst imu;
+  const double* vecs; const double* quats; const double* pairs;
+  const double* t; const double* y; const double* w; const int* perm;
+  int n; uint32_t flags;
+  double* r; double* J; int* i0_r3; int* i0_so3; int* err;
+};
+template <int WHICH>
+__global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
+  constexpr int ROW = WHICH == 0 ? kGyroSplitRow : kAccelSplitRow;
+  constexpr int STRIDE = WHICH == 0 ? kGyroSplitStride : kAccelSplitStride;
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * STRIDE;
+  double* row = wbase + lane * STRIDE;
+  const int tile = warp_tile();
+  if (tile * 32 >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const int i = tile * 32 + lane;
+  int perm = -1;
+  if (i < a.n) {
+    perm = a.perm[i];
+    const double y[3] = {a.y[3 * (size_t)i], a.y[3 * (size_t)i + 1], a.y[3 * (size_t)i + 2]};
+    double r[3];
+    int ia = -1, ib = -1;
+    const int st = imu_row_split(WHICH, a.sp, a.imu, a.vecs, a.quats, a.pairs, a.t[i], y, a.w[i], r, row, &ia, &ib);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = r[2] = nan(""); ia = ib = -1;
+      for (int c = 0; c < ROW; ++c) row[c] = nan("");
+    }
+    const size_t dst = (size_t)perm;
+    if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+    if (a.i0_r3) a.i0_r3[dst] = ia;
+    if (a.i0_so3) a.i0_so3[dst] = ib;
+  }
+  __syncwarp();
+  if (wantJ) warp_scatter_rows<ROW, STRIDE>(wbase, a.J, (long long)perm, lane);
+}
+
+struct RefSplitArgs {
+  SplitConst sp; CameraConst cam;
+  const double* vecs; const double* quats; const double* pairs; const double* rho;
+  const double* ref_uv; const double* ref_t0; const int* r3_start; const int* r3_n; const int* so3_start; const int* so3_n; const int* lm;
+  int n; double* recs; int* err;
+};
+__global__ void __launch_bounds__(kThreads) k_landmark_ref_split(const RefSplitArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kRefSplitStride;
+  double* row = wbase + lane * kRefSplitStride;
+  const int base = (blockIdx.x * kThreads + threadIdx.x) & ~31;
+  const int i = base + lane;
+  if (base >= a.n) return;
+  if (i < a.n) {
+    const double ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+    const int st = landmark_ref_row_split(a.sp, a.cam, a.vecs, a.quats, a.pairs, ruv, a.ref_t0[i], a.r3_start[i], a.r3_n[i], a.so3_start[i], a.so3_n[i],
+                                          a.rho[a.lm[i]], row);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      for (int c = 0; c < kRefSplitStride; ++c) row[c] = nan("");
+      row[7] = -1.0; row[8] = -1.0;
+    }
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_store(a.recs + (size_t)base * kRefSplitStride, wbase, (unsigned)(min(32, a.n - base) * kRefSplitStride * 8));
+    bulk_store_wait_read();
+  }
+}
+
+struct CamSplitArgs {
+  SplitConst sp; CameraConst cam;
+  const double* vecs; const double* quats; const double* pairs; const double* recs;
+  const double* obs_uv; const double* obs_t0; const double* ref_t0; const int* ref_idx; const double* w; const double* huber;
+  const int* perm;
+  int n; uint32_t flags;
+  double* r; double* J; int* idx[4]; int* err;
+};
+__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(const CamSplitArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kCamWarpSmem;
+  double* row = wbase + lane * kCamRowStride;
+  const int tile = warp_tile();
+  if (tile * 32 >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const int i = tile * 32 + lane;
+  const int perm = i < a.n ? a.perm[i] : -1;
+  const int myridx = i < a.n ? a.ref_idx[i] : -1;
+#pragma unroll 4
+  for (int rr = 0; rr < 32; ++rr) {
+    const int ridx = __shfl_sync(0xffffffffu, myridx, rr);
+    if (ridx < 0) continue;
+    const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ridx * kRefSplitStride);
+    double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRowStride + kRefSplitInRow);
+    if (lane < kRefSplitStride / 2) cp_async16(dst + lane, src + lane);
+  }
+  double ouv[2] = {0.0, 0.0};
+  ObsForwardSplit f; f.status = kStatusRange; f.ia = f.ib = -1;
+  if (perm >= 0 && myridx >= 0) {
+    ouv[0] = a.obs_uv[2 * (size_t)i]; ouv[1] = a.obs_uv[2 * (size_t)i + 1];
+    static_rs_row_forward_split(a.sp, a.cam, a.quats, a.pairs, ouv, a.obs_t0[i], a.ref_t0[i], f);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  if (perm >= 0) {
+    double r[2];
+    int idx[4] = {-1, -1, -1, -1};
+    const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
+    const int st = static_rs_row_finish_split(a.cam, a.vecs, a.quats, a.pairs, f, row + kRefSplitInRow, ouv, a.w[i], hub, r, row, idx);
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = nan(""); idx[0] = idx[1] = idx[2] = idx[3] = -1;
+      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+    }
+    const size_t dst = (size_t)perm;
+    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
+  }
+  __syncwarp();
+  if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)perm, lane);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -262,7 +408,8 @@ struct Group {
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
   DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
-  DevBuf<int> d_rr_start, d_rr_n, d_rr_lm;
+  DevBuf<int> d_rr_start, d_rr_n, d_rr_lm, d_rr_start_b, d_rr_n_b;
+  DevBuf<int> o_i0c, o_i0d;
   // device-side outputs used by the host-buffer path
   DevBuf<double> o_r, o_J; DevBuf<int> o_i0, o_i0b;
   bool uploaded = false;
@@ -276,9 +423,11 @@ struct ktk_problem {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool have_spline = false;
+  int traj = 0;                    // 0: UniformSE3SplineTrajectory, 1: SplitTrajectory (R3 + SO3)
   SplineConst sp{0.0, 1.0, 0, 0};
+  SplitConst spl{0.0, 1.0, 0, 0.0, 1.0, 0};
   std::vector<Group*> groups;
-  DevBuf<double> d_knots7, d_knots8, d_pairs, d_rho;
+  DevBuf<double> d_knots7, d_knots8, d_pairs, d_rho, d_vecs4, d_so3pairs;
   DevBuf<int> d_err;
   int* h_err = nullptr;   // pinned
   int64_t launches = 0;
@@ -327,14 +476,16 @@ template <class T> std::vector<T> gather(const std::vector<T>& v, const std::vec
 
 int upload_group(ktk_problem* p, Group& g) {
   if (g.uploaded) return KTK_OK;
-  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
-  const SplineConst& sp = p->sp;
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory (ktk_set_se3_spline / ktk_set_split_spline) must be set before evaluation");
+  const bool split = p->traj == 1;
+  // the spline whose first active knot orders the rows: SE3, or the SO3 part of a split trajectory
+  const double kt0 = split ? p->spl.t0_so3 : p->sp.t0, kdt = split ? p->spl.dt_so3 : p->sp.dt;
   std::vector<int> key((size_t)g.n);
   if (g.kind == KTK_STATIC_RS) {
     const double row_delta = g.cam.readout / (double)g.cam.rows;
-    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.obs_t0[i] + g.cam.base.time_offset + g.obs_uv[2 * i + 1] * row_delta, sp.t0, sp.dt);
+    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.obs_t0[i] + g.cam.base.time_offset + g.obs_uv[2 * i + 1] * row_delta, kt0, kdt);
   } else {
-    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.t[i] + g.sensor.time_offset, sp.t0, sp.dt);
+    for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.t[i] + g.sensor.time_offset, kt0, kdt);
   }
   g.perm = sort_perm(key);
   int st;
@@ -345,31 +496,44 @@ int upload_group(ktk_problem* p, Group& g) {
     // Landmark-reference table.  The reference evaluation of a residual happens in the segment (of that residual's two
     // spans) that holds t_ref; its origin is what fixes (i0_ref, u_ref) bit-exactly.  Observations of one landmark
     // share it whenever the reference view is the earlier one; otherwise they get their own record.
+    // (Split trajectory: one segment per spline, R3 in rr_start/rr_n and SO3 in rr_start_b/rr_n_b.)
     CameraConst cc; fill_camera_consts(g.cam, cc);
     std::unordered_map<uint64_t, int> index;
-    std::vector<double> rr_uv, rr_t0; std::vector<int> rr_start, rr_n, rr_lm, ref_idx((size_t)g.n, -1);
+    std::vector<double> rr_uv, rr_t0; std::vector<int> rr_start, rr_n, rr_start_b, rr_n_b, rr_lm, ref_idx((size_t)g.n, -1);
     for (int64_t i = 0; i < g.n; ++i) {
-      Segment s0{0, 0}, s1{0, 0};
-      const int nseg = static_rs_segments(sp, cc, g.ref_t0[i], g.obs_t0[i], s0, s1);
-      if (nseg == 0) continue;
+      Segment s0{0, 0}, s1{0, 0}, sa{0, 0}, sb{0, 0};
+      const double tr = static_rs_time(cc, g.ref_t0[i], g.ref_uv[2 * i + 1]);
       int ir; double ur;
-      const int which = locate_in_segments(nseg, s0, s1, static_rs_time(cc, g.ref_t0[i], g.ref_uv[2 * i + 1]), sp.t0, sp.dt, ir, ur);
-      if (which < 0) continue;
-      const Segment& sr = which == 0 ? s0 : s1;
+      if (!split) {
+        const int nseg = static_rs_segments(p->sp, cc, g.ref_t0[i], g.obs_t0[i], s0, s1);
+        const int which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, tr, p->sp.t0, p->sp.dt, ir, ur);
+        if (which < 0) continue;
+        sa = which == 0 ? s0 : s1;
+      } else {
+        int nseg = static_rs_segments_split(p->spl, cc, g.ref_t0[i], g.obs_t0[i], p->spl.t0_r3, p->spl.dt_r3, s0, s1);
+        int which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, tr, p->spl.t0_r3, p->spl.dt_r3, ir, ur);
+        if (which < 0) continue;
+        sa = which == 0 ? s0 : s1;
+        nseg = static_rs_segments_split(p->spl, cc, g.ref_t0[i], g.obs_t0[i], p->spl.t0_so3, p->spl.dt_so3, s0, s1);
+        which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, tr, p->spl.t0_so3, p->spl.dt_so3, ir, ur);
+        if (which < 0) continue;
+        sb = which == 0 ? s0 : s1;
+      }
+      if (g.lm[i] >= (1 << 24) || sa.start >= (1 << 20) || sb.start >= (1 << 20)) return fail(KTK_EUNSUPPORTED, "more than 2^24 landmarks or 2^20 knots");
       // two observations of a landmark always share (ref_uv, ref_t0): the landmark has ONE reference observation
-      const uint64_t key = ((uint64_t)(uint32_t)g.lm[i] << 32) | (uint32_t)sr.start;
+      const uint64_t key = ((uint64_t)(uint32_t)g.lm[i] << 40) | ((uint64_t)(uint32_t)sa.start << 20) | (uint64_t)(uint32_t)sb.start;
       auto it = index.find(key);
       if (it == index.end()) {
         it = index.emplace(key, (int)rr_lm.size()).first;
         rr_uv.push_back(g.ref_uv[2 * i]); rr_uv.push_back(g.ref_uv[2 * i + 1]); rr_t0.push_back(g.ref_t0[i]);
-        rr_start.push_back(sr.start); rr_n.push_back(sr.n); rr_lm.push_back(g.lm[i]);
+        rr_start.push_back(sa.start); rr_n.push_back(sa.n); rr_start_b.push_back(sb.start); rr_n_b.push_back(sb.n); rr_lm.push_back(g.lm[i]);
       } else if (rr_uv[2 * it->second] != g.ref_uv[2 * i] || rr_uv[2 * it->second + 1] != g.ref_uv[2 * i + 1] || rr_t0[it->second] != g.ref_t0[i]) {
         return fail(KTK_EINVAL, "observations of one landmark disagree on its reference observation");
       }
       ref_idx[i] = it->second;
     }
     // order the records by their first knot (locality of the pair table), remap
-    std::vector<int> rperm = sort_perm(rr_start), rinv(rperm.size());
+    std::vector<int> rperm = sort_perm(split ? rr_start_b : rr_start), rinv(rperm.size());
     for (size_t k = 0; k < rperm.size(); ++k) rinv[rperm[k]] = (int)k;
     for (auto& v : ref_idx) if (v >= 0) v = rinv[v];
     g.n_ref = (int64_t)rr_lm.size();
@@ -377,8 +541,10 @@ int upload_group(ktk_problem* p, Group& g) {
     if ((st = g.d_rr_t0.upload(gather(rr_t0, rperm, 1), s))) return st;
     if ((st = g.d_rr_start.upload(gather(rr_start, rperm, 1), s))) return st;
     if ((st = g.d_rr_n.upload(gather(rr_n, rperm, 1), s))) return st;
+    if ((st = g.d_rr_start_b.upload(gather(rr_start_b, rperm, 1), s))) return st;
+    if ((st = g.d_rr_n_b.upload(gather(rr_n_b, rperm, 1), s))) return st;
     if ((st = g.d_rr_lm.upload(gather(rr_lm, rperm, 1), s))) return st;
-    if ((st = g.d_recs.resize((size_t)g.n_ref * kRefStride))) return st;
+    if ((st = g.d_recs.resize((size_t)g.n_ref * (split ? kRefSplitStride : kRefStride)))) return st;
     if ((st = g.d_ref_idx.upload(gather(ref_idx, g.perm, 1), s))) return st;
     if ((st = g.d_obs_uv.upload(gather(g.obs_uv, g.perm, 2), s))) return st;
     if ((st = g.d_obs_t0.upload(gather(g.obs_t0, g.perm, 1), s))) return st;
@@ -392,6 +558,14 @@ int upload_group(ktk_problem* p, Group& g) {
   g.uploaded = true;
   return KTK_OK;
 }
+
+// doubles per packed Jacobian row / per residual of a group (include/kontiki_b200.h "Layouts")
+int row_doubles(const ktk_problem* p, const Group& g) {
+  if (g.kind == KTK_STATIC_RS) return kCamRow;
+  if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? kGyroSplitRow : kAccelSplitRow;
+  return kImuRow;
+}
+int res_doubles(const Group& g) { return g.kind == KTK_STATIC_RS ? 2 : 3; }
 
 int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
@@ -432,6 +606,10 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
+  cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
+  cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
+  cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
+  cudaFuncSetAttribute(k_landmark_ref_split, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefSplitStride * 8);
   *out = p;
   return KTK_OK;
 }
@@ -445,8 +623,18 @@ int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, in
   if (!(dt > 0.0)) return fail(KTK_EINVAL, "dt must be positive");
   if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
-  p->have_spline = true;
+  p->traj = 0; p->have_spline = true;
   for (auto g : p->groups) g->uploaded = false;   // the sort key depends on (t0, dt)
+  return KTK_OK;
+}
+
+int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r3, double dt_so3, double t0_so3, int32_t n_so3) {
+  if (!p) return fail(KTK_EINVAL, "problem is NULL");
+  if (!(dt_r3 > 0.0) || !(dt_so3 > 0.0)) return fail(KTK_EINVAL, "dt must be positive");
+  if (n_r3 < 4 || n_so3 < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
+  p->spl = SplitConst{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  p->traj = 1; p->have_spline = true;
+  for (auto g : p->groups) g->uploaded = false;
   return KTK_OK;
 }
 
@@ -476,10 +664,67 @@ int32_t ktk_num_groups(const ktk_problem* p) { return p ? (int32_t)p->groups.siz
 int64_t ktk_group_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->n : -1; }
 int32_t ktk_group_kind(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->kind : -1; }
 int64_t ktk_launch_count(const ktk_problem* p) { return p ? p->launches : 0; }
+int32_t ktk_group_row_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? row_doubles(p, *p->groups[g]) : -1; }
+int64_t ktk_num_knot_doubles(const ktk_problem* p) {
+  if (!p || !p->have_spline) return 0;
+  return p->traj == 1 ? (int64_t)3 * p->spl.n_r3 + (int64_t)4 * p->spl.n_so3 : (int64_t)7 * p->sp.n_knots;
+}
+
+// ktk_evaluate_device for a split trajectory: d_knots = [R3 knots (3 n_r3) | SO3 knots (4 n_so3)], the parameter order of
+// SplitEntity (split_trajectory.h:34-39, 117-123).
+static int evaluate_device_split(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs) {
+  cudaStream_t s = p->stream;
+  int st;
+  const SplitConst& sp = p->spl;
+  const double* d_quats = d_knots + (size_t)3 * sp.n_r3;      // 4-double records already
+  if ((st = p->d_vecs4.resize((size_t)sp.n_r3 * kVecStride))) return st;
+  if ((st = p->d_so3pairs.resize((size_t)sp.n_so3 * kSo3PairStride))) return st;
+  KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
+  k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(d_knots, sp.n_r3, p->d_vecs4.p);
+  k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
+  p->launches += 2;
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    if (g.n == 0) continue;
+    const ktk_group_out& o = outs[gi];
+    const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
+    const int blocks = (int)((g.n + tpb - 1) / tpb);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
+    if (g.kind == KTK_STATIC_RS) {
+      RefSplitArgs ra;
+      ra.sp = sp; fill_camera_consts(g.cam, ra.cam);
+      ra.vecs = p->d_vecs4.p; ra.quats = d_quats; ra.pairs = p->d_so3pairs.p; ra.rho = d_rho;
+      ra.ref_uv = g.d_rr_uv.p; ra.ref_t0 = g.d_rr_t0.p; ra.r3_start = g.d_rr_start.p; ra.r3_n = g.d_rr_n.p; ra.so3_start = g.d_rr_start_b.p; ra.so3_n = g.d_rr_n_b.p;
+      ra.lm = g.d_rr_lm.p; ra.n = (int)g.n_ref; ra.recs = g.d_recs.p; ra.err = p->d_err.p;
+      if (g.n_ref > 0) { k_landmark_ref_split<<<(int)((g.n_ref + kThreads - 1) / kThreads), kThreads, kThreads * kRefSplitStride * 8, s>>>(ra); p->launches += 1; }
+      CamSplitArgs a;
+      a.sp = sp; a.cam = ra.cam;
+      a.vecs = p->d_vecs4.p; a.quats = d_quats; a.pairs = p->d_so3pairs.p; a.recs = g.d_recs.p;
+      a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
+      a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+      a.r = o.r; a.J = o.J; a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d; a.err = p->d_err.p;
+      k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
+    } else {
+      ImuSplitArgs a;
+      a.sp = sp; fill_sensor_consts(g.sensor, a.imu);
+      a.vecs = p->d_vecs4.p; a.quats = d_quats; a.pairs = p->d_so3pairs.p;
+      a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+      a.r = o.r; a.J = o.J; a.i0_r3 = o.i0; a.i0_so3 = o.i0_c; a.err = p->d_err.p;
+      if (g.kind == KTK_GYROSCOPE) k_imu_split<0><<<blocks, kThreads, kThreads * kGyroSplitStride * 8, s>>>(a);
+      else k_imu_split<1><<<blocks, kThreads, kThreads * kAccelSplitStride * 8, s>>>(a);
+    }
+    if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
+    p->launches += 1;
+  }
+  KTK_CUDA(cudaGetLastError());
+  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  return KTK_OK;
+}
 
 int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs) {
   if (!p || !d_knots || !outs) return fail(KTK_EINVAL, "NULL argument");
-  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set before evaluation");
   if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device (structure queries only); there is no CPU evaluation path");
   KTK_CUDA(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
@@ -491,6 +736,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
     }
   }
+  if (p->traj == 1) return evaluate_device_split(p, d_knots, d_rho, flags, outs);
   const int nk = p->sp.n_knots;
   if ((st = p->d_knots8.resize((size_t)nk * kKnotStride))) return st;
   if ((st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
@@ -544,19 +790,21 @@ int ktk_synchronize(ktk_problem* p) {
   KTK_CUDA(cudaStreamSynchronize(p->stream));
   const int e = *p->h_err;
   if (e == kStatusRange) return fail(KTK_ERANGE, "a measurement time is out of range for the trajectory (its output rows are NaN)");
+  if (e == kStatusRuntime) return fail(KTK_ERUNTIME, "logq: Only implemented for unit quaternions (a SO3 knot pair is not unit norm)");
   if (e != 0) return fail(KTK_ERUNTIME, "device-side evaluation error");
   return KTK_OK;
 }
 
 int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs) {
   if (!p || !knots || !outs) return fail(KTK_EINVAL, "NULL argument");
-  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called before evaluation");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set before evaluation");
   if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device (structure queries only); there is no CPU evaluation path");
   KTK_CUDA(cudaSetDevice(p->device));
   cudaStream_t s = p->stream;
   int st;
-  if ((st = p->d_knots7.resize((size_t)p->sp.n_knots * 7))) return st;
-  KTK_CUDA(cudaMemcpyAsync(p->d_knots7.p, knots, (size_t)p->sp.n_knots * 7 * sizeof(double), cudaMemcpyHostToDevice, s));
+  const size_t nkd = (size_t)ktk_num_knot_doubles(p);
+  if ((st = p->d_knots7.resize(nkd))) return st;
+  KTK_CUDA(cudaMemcpyAsync(p->d_knots7.p, knots, nkd * sizeof(double), cudaMemcpyHostToDevice, s));
   if (rho && n_rho > 0) {
     if ((st = p->d_rho.resize((size_t)n_rho))) return st;
     KTK_CUDA(cudaMemcpyAsync(p->d_rho.p, rho, (size_t)n_rho * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -565,22 +813,27 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
     Group& g = *p->groups[gi];
     const ktk_group_out& o = outs[gi];
-    const bool cam = g.kind == KTK_STATIC_RS;
-    dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr};
-    if (o.r) { if ((st = g.o_r.resize((size_t)g.n * (cam ? 2 : 3)))) return st; dev[gi].r = g.o_r.p; }
-    if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize((size_t)g.n * (cam ? kCamRow : kImuRow)))) return st; dev[gi].J = g.o_J.p; }
-    if (o.i0) { if ((st = g.o_i0.resize((size_t)g.n))) return st; dev[gi].i0 = g.o_i0.p; }
-    if (o.i0_b && cam) { if ((st = g.o_i0b.resize((size_t)g.n))) return st; dev[gi].i0_b = g.o_i0b.p; }
+    const size_t n = (size_t)g.n;
+    dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (o.r) { if ((st = g.o_r.resize(n * res_doubles(g)))) return st; dev[gi].r = g.o_r.p; }
+    if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize(n * row_doubles(p, g)))) return st; dev[gi].J = g.o_J.p; }
+    if (o.i0) { if ((st = g.o_i0.resize(n))) return st; dev[gi].i0 = g.o_i0.p; }
+    if (o.i0_b) { if ((st = g.o_i0b.resize(n))) return st; dev[gi].i0_b = g.o_i0b.p; }
+    if (o.i0_c) { if ((st = g.o_i0c.resize(n))) return st; dev[gi].i0_c = g.o_i0c.p; }
+    if (o.i0_d) { if ((st = g.o_i0d.resize(n))) return st; dev[gi].i0_d = g.o_i0d.p; }
   }
   if ((st = ktk_evaluate_device(p, p->d_knots7.p, (rho && n_rho > 0) ? p->d_rho.p : nullptr, n_rho, flags, dev.data()))) return st;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
     Group& g = *p->groups[gi];
     const ktk_group_out& o = outs[gi];
-    const bool cam = g.kind == KTK_STATIC_RS;
-    if (dev[gi].r) KTK_CUDA(cudaMemcpyAsync(o.r, dev[gi].r, (size_t)g.n * (cam ? 2 : 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, (size_t)g.n * (cam ? kCamRow : kImuRow) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dev[gi].i0) KTK_CUDA(cudaMemcpyAsync(o.i0, dev[gi].i0, (size_t)g.n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (dev[gi].i0_b) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, (size_t)g.n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    const size_t n = (size_t)g.n;
+    const bool cam = g.kind == KTK_STATIC_RS, split = p->traj == 1;
+    if (dev[gi].r) KTK_CUDA(cudaMemcpyAsync(o.r, dev[gi].r, n * res_doubles(g) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, n * row_doubles(p, g) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0) KTK_CUDA(cudaMemcpyAsync(o.i0, dev[gi].i0, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0_b && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0_c && split) KTK_CUDA(cudaMemcpyAsync(o.i0_c, dev[gi].i0_c, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].i0_d && split && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_d, dev[gi].i0_d, n * sizeof(int), cudaMemcpyDeviceToHost, s));
   }
   return ktk_synchronize(p);
 }
@@ -605,33 +858,37 @@ void ktk_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 // ---- structure (host only) ---------------------------------------------------------------------------------------
 // *Measurement::AddToEstimator -> TrajectoryEstimator::AddTrajectoryForTimes -> SplineEntity::AddToProblem
 // (gyroscope_measurement.h:82-92, static_rscamera_measurement.h:137-168, spline_base.h:361-404)
-static int group_segments(const ktk_problem* p, const Group& g, int64_t i, Segment& s0, Segment& s1) {
-  const SplineConst& sp = p->sp;
-  const double tmax = spline_max_time(sp);
+// which: 0 = the SE3 spline / the R3 part of a split trajectory, 1 = the SO3 part of a split trajectory
+static int group_segments(const ktk_problem* p, const Group& g, int64_t i, int which, Segment& s0, Segment& s1) {
+  const bool split = p->traj == 1;
+  const double t0 = !split ? p->sp.t0 : (which == 0 ? p->spl.t0_r3 : p->spl.t0_so3);
+  const double dt = !split ? p->sp.dt : (which == 0 ? p->spl.dt_r3 : p->spl.dt_so3);
+  const double tmin = split ? split_min_time(p->spl) : p->sp.t0;
+  const double tmax = split ? split_max_time(p->spl) : spline_max_time(p->sp);
   if (g.kind == KTK_STATIC_RS) {
     double t1, t2;
     if (g.ref_t0[i] <= g.obs_t0[i]) { t1 = g.ref_t0[i]; t2 = g.obs_t0[i]; } else { t1 = g.obs_t0[i]; t2 = g.ref_t0[i]; }
     if (!g.sensor.time_offset_locked) { t1 -= g.sensor.max_time_offset; t2 += g.sensor.max_time_offset; }
     const double margin = 1e-3;
     const double a1 = t1 - margin, b1 = t1 + g.cam.readout + margin, a2 = t2 - margin, b2 = t2 + g.cam.readout + margin;
-    if (!(a1 >= sp.t0) || !(b1 < tmax) || !(a2 >= sp.t0) || !(b2 < tmax) || a1 > b1 || a2 > b2 || a2 < a1) return 0;
-    return segments_two_spans(a1, b1, a2, b2, sp.t0, sp.dt, s0, s1);
+    if (!(a1 >= tmin) || !(b1 < tmax) || !(a2 >= tmin) || !(b2 < tmax) || a1 > b1 || a2 > b2 || a2 < a1) return 0;
+    return segments_two_spans(a1, b1, a2, b2, t0, dt, s0, s1);
   }
   double ta = g.t[i], tb = g.t[i];
   if (!g.sensor.time_offset_locked) { ta -= g.sensor.max_time_offset; tb += g.sensor.max_time_offset; }
-  if (!(ta >= sp.t0) || !(tb < tmax)) return 0;
-  segments_one_span(ta, tb, sp.t0, sp.dt, s0);
+  if (!(ta >= tmin) || !(tb < tmax)) return 0;
+  segments_one_span(ta, tb, t0, dt, s0);
   return 1;
 }
 
-int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids) {
+static int structure_of(const ktk_problem* p, int32_t group, int which, int32_t cap, int32_t* knot_ids, int32_t* n_ids) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !knot_ids || !n_ids) return fail(KTK_EINVAL, "bad argument");
-  if (!p->have_spline) return fail(KTK_EINVAL, "ktk_set_se3_spline must be called first");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set first");
   const Group& g = *p->groups[group];
   int worst = KTK_OK;
   for (int64_t i = 0; i < g.n; ++i) {
     Segment s0{0, 0}, s1{0, 0};
-    const int nseg = group_segments(p, g, i, s0, s1);
+    const int nseg = group_segments(p, g, i, which, s0, s1);
     int32_t* ids = knot_ids + (size_t)i * cap;
     for (int c = 0; c < cap; ++c) ids[c] = -1;
     if (nseg == 0) { n_ids[i] = 0; worst = KTK_ERANGE; continue; }
@@ -646,11 +903,18 @@ int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t*
   return KTK_OK;
 }
 
+int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids) { return structure_of(p, group, 0, cap, knot_ids, n_ids); }
+int ktk_get_structure_so3(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids) {
+  if (p && p->traj != 1) return fail(KTK_EINVAL, "not a split trajectory");
+  return structure_of(p, group, 1, cap, knot_ids, n_ids);
+}
+
 int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const int32_t* knot_ids, const double* Jp, const int32_t* i0r,
                          const int32_t* i0o, double* out) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !knot_ids || !Jp || !i0r || !i0o || !out) return fail(KTK_EINVAL, "bad argument");
   const Group& g = *p->groups[group];
   if (g.kind != KTK_STATIC_RS) return fail(KTK_EINVAL, "not a static-RS group");
+  if (p->traj != 0) return fail(KTK_EINVAL, "ktk_expand_static_rs is for the SE3 layout");
   std::memset(out, 0, sizeof(double) * (size_t)g.n * cap * 14);
   for (int64_t i = 0; i < g.n; ++i) {
     const int32_t* ids = knot_ids + (size_t)i * cap;

@@ -195,3 +195,108 @@ def test_full_size_properties_h1():
     Jd += o["J"][:, 112:114] * drho[c["lm_idx"]][:, None]
     num = (op[g["cam"]]["r"] - om[g["cam"]]["r"]) / (2 * h)
     assert np.abs(Jd - num).max() < 1e-5 * max(1.0, np.abs(num).max())
+
+
+# ---- split (R3 + SO3) trajectory: BASELINE.json configs[4] ---------------------------------------------------------------
+def _split_case(n_knots=400, dt=0.02, scale_imu=3000, n_lm=300, seed=31, same_grid=True):
+    k = syn.smooth_se3_knots(n_knots, dt)
+    vecs = k[:, 4:7].copy()
+    if same_grid:
+        quats, dt_b, t0_b = k[:, :4].copy(), dt, 0.0
+    else:      # different knot spacing / origin for the orientation spline (split_trajectory.h allows it)
+        dt_b, t0_b = dt * 0.8, 0.003
+        quats = syn.smooth_se3_knots(int(n_knots / 0.8) + 2, dt_b)[:, :4].copy()
+    cam = syn.make_static_rs(k, dt, n_lm, obs_per_landmark=8, seed=seed, noise_px=1.0)
+    rng = np.random.default_rng(seed)
+    lo = max(0.0, t0_b) + 0.01
+    hi = min((n_knots - 3) * dt, t0_b + (len(quats) - 3) * dt_b) - 0.05
+    keep = (np.minimum(cam["ref_t0"], cam["obs_t0"]) > lo) & (np.maximum(cam["ref_t0"], cam["obs_t0"]) + cam["readout"] < hi)
+    for key in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "weight", "huber_c"):
+        cam[key] = cam[key][keep]
+    out = rng.random(len(cam["lm_idx"])) < 0.2
+    cam["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    cam["weight"] = rng.uniform(0.5, 2, len(cam["lm_idx"]))
+    t = rng.uniform(lo, hi, scale_imu)
+    return dict(vecs=vecs, dt_a=dt, t0_a=0.0, quats=quats, dt_b=dt_b, t0_b=t0_b, cam=cam, t=t, y=rng.uniform(-1, 1, (scale_imu, 3)),
+                w=rng.uniform(0.5, 2, scale_imu))
+
+
+@pytest.mark.parametrize("same_grid", [True, False])
+@pytest.mark.parametrize("robust", [False, True])
+def test_split_trajectory_matches_oracle(same_grid, robust):
+    c = _split_case(same_grid=same_grid)
+    cam = c["cam"]
+    p = _lib.Problem(0)
+    p.set_split_spline(c["dt_a"], c["t0_a"], len(c["vecs"]), c["dt_b"], c["t0_b"], len(c["quats"]))
+    imu = _lib.make_sensor()
+    gg = p.add_gyroscope(imu, c["t"], c["y"], c["w"])
+    ga = p.add_accelerometer(imu, c["t"], c["y"], c["w"])
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    gc = p.add_static_rs(_lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"], q_ct=q_ct, p_ct=p_ct), cam["obs_uv"], cam["obs_t0"],
+                         cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["weight"], cam["huber_c"])
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    outs = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags)
+    traj = kto.Traj(kto.SPLIT, c["dt_a"], c["t0_a"], c["vecs"], c["dt_b"], c["t0_b"], c["quats"])
+    # IMU
+    for g, which in ((gg, 0), (ga, 1)):
+        o = kto.imu_residuals(traj, kto.Sensor(), which, c["t"], c["y"], c["w"], jac_mode=2)
+        out = outs[g]
+        assert (out["i0_c"] == o["i0_b"]).all()
+        assert parity.rel_err(out["r"], o["r"]) < parity.TOL
+        assert parity.rel_err(out["J"][:, -48:].reshape(-1, 4, 3, 4), o["Jb"][:, :4]) < parity.TOL
+        if which == 1:
+            assert (out["i0"] == o["i0_a"]).all()
+            assert parity.rel_err(out["J"][:, :36].reshape(-1, 4, 3, 3), o["Ja"][:, :4]) < parity.TOL
+        else:
+            assert np.abs(o["Ja"]).max() == 0.0        # gyro: R3 blocks structurally present, identically zero
+        ids_a, _ = p.get_structure(g, cap=4)
+        ids_b, _ = p.get_structure_so3(g, cap=4)
+        assert (ids_a == o["ids_a"]).all() and (ids_b == o["ids_b"]).all()
+    # camera
+    ocam = kto.Camera(cam["rows"], cam["cols"], cam["readout"], K=cam["K"], q_ct=q_ct, p_ct=p_ct)
+    o = kto.static_rs_residuals(traj, ocam, cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["rho"], cam["weight"],
+                                jac_mode=2, cap=24)
+    out = outs[gc]
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_b"] == o["i0_obs_a"]).all()
+    assert (out["i0_c"] == o["i0_ref_b"]).all() and (out["i0_d"] == o["i0_obs_b"]).all()
+    ids_a, _ = p.get_structure(gc, cap=24)
+    ids_b, _ = p.get_structure_so3(gc, cap=24)
+    assert (ids_a == o["ids_a"]).all() and (ids_b == o["ids_b"]).all()
+    n = len(cam["lm_idx"])
+    Ja, Jb = np.zeros_like(o["Ja"]), np.zeros_like(o["Jb"])
+    for i in range(n):
+        pa = {int(k): j for j, k in enumerate(o["ids_a"][i]) if k >= 0}
+        pb = {int(k): j for j, k in enumerate(o["ids_b"][i]) if k >= 0}
+        J = out["J"][i]
+        for k in range(4):
+            Ja[i, pa[out["i0"][i] + k]] += J[6 * k:6 * k + 6].reshape(2, 3)
+            Ja[i, pa[out["i0_b"][i] + k]] += J[56 + 6 * k:62 + 6 * k].reshape(2, 3)
+            Jb[i, pb[out["i0_c"][i] + k]] += J[24 + 8 * k:32 + 8 * k].reshape(2, 4)
+            Jb[i, pb[out["i0_d"][i] + k]] += J[80 + 8 * k:88 + 8 * k].reshape(2, 4)
+    Jrho = out["J"][:, 112:114]
+    if not robust:
+        assert np.abs(out["r"] - o["r"]).max() < parity.TOL * 1e3
+        assert parity.rel_err(Ja, o["Ja"]) < parity.TOL and parity.rel_err(Jb, o["Jb"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+        return
+    n_out = 0
+    for i in range(n):
+        ma, mb = int((o["ids_a"][i] >= 0).sum()), int((o["ids_b"][i] >= 0).sum())
+        Jfull = np.concatenate([o["Ja"][i, k] for k in range(ma)] + [o["Jb"][i, k] for k in range(mb)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+        _, r2, J2 = kto.huber_correct(cam["huber_c"][i], o["r"][i], Jfull)
+        Jmine = np.concatenate([Ja[i, k] for k in range(ma)] + [Jb[i, k] for k in range(mb)] + [Jrho[i].reshape(2, 1)], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(out["r"][i] - r2).max() <= parity.TOL * 1e3
+        n_out += np.linalg.norm(o["r"][i]) > cam["huber_c"][i]
+    assert n_out > 5
+
+
+def test_split_non_unit_quaternion_is_a_runtime_error():
+    """quaternion_math.h:19-23: logq throws std::runtime_error on a non-unit quaternion -> RuntimeError in Python."""
+    c = _split_case(n_knots=60, scale_imu=64, n_lm=5)
+    q = c["quats"].copy()
+    q[20] *= 1.01
+    p = _lib.Problem(0)
+    p.set_split_spline(c["dt_a"], 0.0, len(c["vecs"]), c["dt_b"], c["t0_b"], len(q))
+    p.add_gyroscope(_lib.make_sensor(), c["t"][:64], c["y"][:64])
+    with pytest.raises(RuntimeError):
+        p.evaluate((c["vecs"], q))

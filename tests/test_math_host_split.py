@@ -1,0 +1,85 @@
+"""Split (R3 + SO3) trajectory mathematics (kontiki_b200/csrc/split_math.cuh), compiled for the host, against the oracle."""
+import numpy as np
+import pytest
+
+import fixtures_ref as fx
+import hostcheck as hc
+import parity
+from kontiki_b200 import synthetic as syn
+from oracle import kto
+
+
+def _traj(dt_b=0.04, t0_b=0.01):
+    k = syn.smooth_se3_knots(150, 0.05)
+    vecs = k[:, 4:7].copy()
+    quats = syn.smooth_se3_knots(190, dt_b)[:, :4].copy()
+    return vecs, quats, kto.Traj(kto.SPLIT, 0.05, 0.0, vecs, dt_b, t0_b, quats), k
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_split_imu_rows_match_oracle(which):
+    vecs, quats, traj, _ = _traj()
+    rng = np.random.default_rng(which)
+    t, y, w = rng.uniform(0.02, 7.2, 300), rng.uniform(-1, 1, (300, 3)), rng.uniform(0.5, 2, 300)
+    o = kto.imu_residuals(traj, kto.Sensor(), which, t, y, w, jac_mode=2)
+    h = hc.imu_split(which, vecs, 0.05, 0.0, quats, 0.04, 0.01, t, y, w)
+    assert (h["status"] == 0).all() and h["prepass_status"] == 0
+    assert (h["i0_so3"] == o["i0_b"]).all()
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(h["J"][:, -48:].reshape(-1, 4, 3, 4), o["Jb"][:, :4]) < parity.TOL
+    if which == 1:
+        assert (h["i0_r3"] == o["i0_a"]).all()
+        assert parity.rel_err(h["J"][:, :36].reshape(-1, 4, 3, 3), o["Ja"][:, :4]) < parity.TOL
+
+
+def test_split_reference_fixtures():
+    """The reference's R3 / SO3 fixtures (python/tests/conftest.py:32-45, :52-67): constant-rate rotation => gyro == rate."""
+    t = np.linspace(max(fx.R3_T0, fx.SO3_T0) + 1e-6, fx.SO3_T0 + (len(fx.SO3_KNOTS) - 3) * fx.SO3_DT - 1e-6, 50)
+    h = hc.imu_split(0, fx.R3_KNOTS, fx.R3_DT, fx.R3_T0, fx.SO3_KNOTS, fx.SO3_DT, fx.SO3_T0, t, np.zeros((50, 3)))
+    assert (h["status"] == 0).all()
+    assert np.abs(-h["r"] - fx.SO3_RATE * fx.SO3_AXIS).max() < 1e-12     # body rate of a constant rotation about a fixed axis
+    traj = kto.Traj(kto.SPLIT, fx.R3_DT, fx.R3_T0, fx.R3_KNOTS, fx.SO3_DT, fx.SO3_T0, fx.SO3_KNOTS)
+    for which in (0, 1):
+        o = kto.imu_residuals(traj, kto.Sensor(), which, t, np.zeros((50, 3)), jac_mode=2)
+        h = hc.imu_split(which, fx.R3_KNOTS, fx.R3_DT, fx.R3_T0, fx.SO3_KNOTS, fx.SO3_DT, fx.SO3_T0, t, np.zeros((50, 3)))
+        assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+        assert parity.rel_err(h["J"][:, -48:].reshape(-1, 4, 3, 4), o["Jb"][:, :4]) < parity.TOL
+
+
+def test_split_camera_rows_match_oracle():
+    vecs, quats, traj, k = _traj(dt_b=0.04, t0_b=0.0)
+    s = syn.make_static_rs(k, 0.05, 40, obs_per_landmark=6, seed=5, noise_px=1.0)
+    rng = np.random.default_rng(1)
+    n = len(s["lm_idx"])
+    out = rng.random(n) < 0.2
+    s["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    w = rng.uniform(0.5, 2, n)
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], q_ct=fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), p_ct=np.array([0.05, -0.02, 0.1]))
+    o = kto.static_rs_residuals(traj, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], w, jac_mode=2, cap=24)
+    h = hc.static_rs_split(vecs, 0.05, 0.0, quats, 0.04, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], w)
+    assert (h["status"] == 0).all()
+    idx = h["idx"]
+    assert (idx[:, 0] == o["i0_ref_a"]).all() and (idx[:, 1] == o["i0_obs_a"]).all()
+    assert (idx[:, 2] == o["i0_ref_b"]).all() and (idx[:, 3] == o["i0_obs_b"]).all()
+    assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+    Ja, Jb = np.zeros_like(o["Ja"]), np.zeros_like(o["Jb"])
+    for i in range(n):
+        pa = {int(kk): j for j, kk in enumerate(o["ids_a"][i]) if kk >= 0}
+        pb = {int(kk): j for j, kk in enumerate(o["ids_b"][i]) if kk >= 0}
+        J = h["J"][i]
+        for k4 in range(4):
+            Ja[i, pa[idx[i, 0] + k4]] += J[6 * k4:6 * k4 + 6].reshape(2, 3)
+            Ja[i, pa[idx[i, 1] + k4]] += J[56 + 6 * k4:62 + 6 * k4].reshape(2, 3)
+            Jb[i, pb[idx[i, 2] + k4]] += J[24 + 8 * k4:32 + 8 * k4].reshape(2, 4)
+            Jb[i, pb[idx[i, 3] + k4]] += J[80 + 8 * k4:88 + 8 * k4].reshape(2, 4)
+    assert parity.rel_err(Ja, o["Ja"]) < parity.TOL
+    assert parity.rel_err(Jb, o["Jb"]) < parity.TOL
+    assert parity.rel_err(h["J"][:, 112:114], o["Jrho"]) < parity.TOL
+
+
+def test_split_non_unit_quaternion_flags_runtime_error():
+    vecs, quats, traj, _ = _traj()
+    q = quats.copy()
+    q[10] *= 1.001
+    _, _, _, st = hc.split_prepass(vecs, q)
+    assert st == -2        # std::runtime_error in the reference (quaternion_math.h:19-23)
