@@ -45,12 +45,13 @@ def parse():
 
 def workload_config(name, cfg):
     from kontiki_b200 import synthetic as syn
-    return {"workload": f"{name}: UniformSE3SplineTrajectory {len(cfg['knots'])} knots dt={cfg['dt']}, "
+    traj = "SplitTrajectory (UniformR3 + UniformSO3)" if cfg.get("split") else "UniformSE3SplineTrajectory"
+    return {"workload": f"{name}: {traj} {len(cfg['knots'])} knots dt={cfg['dt']}, "
                         f"{len(cfg['gyro']['t']) if cfg['gyro'] else 0} gyro + {len(cfg['accel']['t']) if cfg['accel'] else 0} accel (BasicImu) + "
                         f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} StaticRsCamera (Pinhole, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
             "measurements_per_step_per_gpu": syn.num_measurements(cfg),
             "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
-            "jacobian": "ambient (7 per SE3 knot), Huber corrector applied to camera rows",
+            "jacobian": "ambient (7 per SE3 knot; 3 + 4 per split knot), Huber corrector applied to camera rows",
             "l2": "per-step working set (outputs + records) >> 126 MB L2; no flush",
             "sharding": "measurements sharded across ranks, knots replicated, no data-path collective"}
 
@@ -76,7 +77,10 @@ def oracle_sample(cfg, frac, seed=0):
 def oracle_step(cfg, sample):
     """One residual+Jacobian evaluation of the sample with the CPU oracle; returns (rows, seconds inside Evaluate)."""
     from oracle import kto
-    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    if cfg.get("split"):
+        traj = kto.Traj(kto.SPLIT, cfg["dt"], cfg["t0"], cfg["r3"], cfg["dt"], cfg["t0"], cfg["so3"])
+    else:
+        traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
     rows, secs = 0, 0.0
     imu = kto.Sensor()
     for which, k in ((0, "gyro"), (1, "accel")):
@@ -196,7 +200,12 @@ def main():
     p = _lib.Problem(local_rank)
     stream = torch.cuda.current_stream()
     p.set_stream(stream.cuda_stream)
-    p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+    if cfg.get("split"):
+        p.set_split_spline(cfg["dt"], cfg["t0"], len(cfg["r3"]), cfg["dt"], cfg["t0"], len(cfg["so3"]))
+        knots_flat = np.concatenate([cfg["r3"].reshape(-1), cfg["so3"].reshape(-1)])
+    else:
+        p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+        knots_flat = cfg["knots"].reshape(-1)
     imu = _lib.make_sensor()
     groups = {}
     if cfg["gyro"]:
@@ -213,17 +222,17 @@ def main():
 
     # ---- device-resident leg -------------------------------------------------------------------------------------
     dev = torch.device("cuda", local_rank)
-    d_knots = torch.from_numpy(cfg["knots"]).to(dev)
+    d_knots = torch.from_numpy(knots_flat).to(dev)
     d_rho = torch.from_numpy(rho).to(dev) if rho is not None else None
     d_outs, keep = [], []
     for g in range(p.num_groups):
         n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
         r = torch.empty((n, 2 if cam else 3), dtype=torch.float64, device=dev)
-        J = torch.empty((n, _lib.CAM_ROW if cam else _lib.IMU_ROW), dtype=torch.float64, device=dev)
-        i0 = torch.empty(n, dtype=torch.int32, device=dev)
-        i0b = torch.empty(n, dtype=torch.int32, device=dev)
-        keep.append((r, J, i0, i0b))
-        d_outs.append(dict(r=r.data_ptr(), J=J.data_ptr(), i0=i0.data_ptr(), i0_b=i0b.data_ptr() if cam else None))
+        J = torch.empty((n, p.group_row_size(g)), dtype=torch.float64, device=dev)
+        idx = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
+        keep.append((r, J, idx))
+        d_outs.append(dict(r=r.data_ptr(), J=J.data_ptr(), i0=idx[0].data_ptr(), i0_b=idx[1].data_ptr() if cam else None,
+                           i0_c=idx[2].data_ptr() if cfg.get("split") else None, i0_d=idx[3].data_ptr() if (cfg.get("split") and cam) else None))
 
     def step_device():
         p.evaluate_device(d_knots.data_ptr(), d_rho.data_ptr() if d_rho is not None else 0, 0 if rho is None else len(rho), flags, d_outs)
@@ -266,27 +275,34 @@ def main():
     value = world * n_meas / (ms_step * 1e-3)
 
     # ---- end-to-end leg: host buffers through ktk_evaluate ---------------------------------------------------------
-    h_knots = torch.from_numpy(cfg["knots"]).pin_memory()
+    h_knots = torch.from_numpy(knots_flat.copy()).pin_memory()
     h_rho = torch.from_numpy(rho).pin_memory() if rho is not None else None
     h_outs, d2h = [], 0
     for g in range(p.num_groups):
         n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
         o = dict(r=torch.empty((n, 2 if cam else 3), dtype=torch.float64).pin_memory(),
-                 J=torch.empty((n, _lib.CAM_ROW if cam else _lib.IMU_ROW), dtype=torch.float64).pin_memory(),
+                 J=torch.empty((n, p.group_row_size(g)), dtype=torch.float64).pin_memory(),
                  i0=torch.empty(n, dtype=torch.int32).pin_memory())
         if cam:
             o["i0_b"] = torch.empty(n, dtype=torch.int32).pin_memory()
+        if cfg.get("split"):
+            o["i0_c"] = torch.empty(n, dtype=torch.int32).pin_memory()
+            if cam:
+                o["i0_d"] = torch.empty(n, dtype=torch.int32).pin_memory()
         d2h += sum(t.numel() * t.element_size() for t in o.values())
         h_outs.append({k: v.numpy() for k, v in o.items()})
         keep.append(o)
     h2d = h_knots.numel() * 8 + (h_rho.numel() * 8 if h_rho is not None else 0)
     e2e_steps = max(3, min(a.steps, 10))
+    def step_host():
+        p.evaluate_flat(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
+
     for _ in range(2):
-        p.evaluate(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
+        step_host()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        p.evaluate(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
+        step_host()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -307,7 +323,8 @@ def main():
     dom = "cam" if "cam" in groups else ("accel" if "accel" in groups else "gyro")
     dom_ms, dom_n = prof[dom]
     dom_rows = p.group_size(groups[dom])
-    dom_bytes = dom_rows * (1012 if dom == "cam" else 740)
+    per_row = ({"cam": 1020, "accel": 744, "gyro": 452} if cfg.get("split") else {"cam": 1012, "accel": 740, "gyro": 740})[dom]
+    dom_bytes = dom_rows * per_row
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_ms > 0 else None
     traffic = None
     try:

@@ -245,6 +245,14 @@ class Problem:
         check(lib().ktk_evaluate(self._h, _ptr(knots), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
         return outs
 
+    def evaluate_flat(self, knots_flat, rho, flags, outs):
+        """ktk_evaluate on an already flattened float64 knot array (the C ABI's layout); outs as from alloc_outputs()."""
+        if knots_flat.dtype != np.float64 or knots_flat.size != lib().ktk_num_knot_doubles(self._h):
+            raise ValueError("knots_flat must be float64 with ktk_num_knot_doubles() elements")
+        arr = self._out_array(outs, _ptr)
+        check(lib().ktk_evaluate(self._h, _ptr(knots_flat), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
+        return outs
+
     def evaluate_device(self, d_knots_ptr, d_rho_ptr, n_rho, flags, d_outs):
         """Device-buffer evaluation (ktk_evaluate_device): pointers are raw device addresses (e.g. torch data_ptr())."""
         arr = self._out_array(d_outs, lambda p: None if p is None else int(p))

@@ -163,7 +163,9 @@ CONFIGS = {
     "C3": (5_000, 0.02, 0, 0, 50_000, 10),
     "C4": (5_000, 0.02, 100_000, 100_000, 50_000, 10),
     "H1": (5_000, 0.02, 50_000, 50_000, 50_000, 10),    # north-star headline: 100k IMU + 500k reprojection
+    "C5": (10_000, 0.01, 250_000, 250_000, 25_000, 20),  # split R3 + SO3 trajectory, 1M mixed measurements
 }
+SPLIT_CONFIGS = {"C5"}
 
 
 def make_config(name, scale=1.0):
@@ -171,7 +173,9 @@ def make_config(name, scale=1.0):
     n_knots, dt, ng, na, nl, opl = CONFIGS[name]
     ng, na, nl = int(ng * scale), int(na * scale), int(nl * scale)
     knots = smooth_se3_knots(n_knots, dt)
-    out = dict(name=name, knots=knots, dt=dt, t0=0.0, gyro=None, accel=None, cam=None)
+    out = dict(name=name, knots=knots, dt=dt, t0=0.0, gyro=None, accel=None, cam=None, split=name in SPLIT_CONFIGS)
+    if out["split"]:      # R3 knots from the positions, SO3 knots from the (sign-continuous) orientations of the same smooth motion
+        out["r3"], out["so3"] = knots[:, 4:7].copy(), knots[:, 0:4].copy()
     seeds = {"C1": (1, 0), "C2": (2, 3)}.get(name, (5, 6))
     if ng:
         out["gyro"] = make_imu(ng, n_knots, dt, seed=seeds[0])
@@ -183,10 +187,13 @@ def make_config(name, scale=1.0):
 
 
 def algorithmic_bytes(cfg):
-    """SURVEY.md section 8d contract figure: 740 B per IMU row, 1012 B per static-RS row."""
-    n_imu = (len(cfg["gyro"]["t"]) if cfg["gyro"] else 0) + (len(cfg["accel"]["t"]) if cfg["accel"] else 0)
+    """SURVEY.md section 8d contract figures: SE3 740 B per IMU row, 1012 B per static-RS row; split 452 / 744 / 1020 B."""
+    ng = len(cfg["gyro"]["t"]) if cfg["gyro"] else 0
+    na = len(cfg["accel"]["t"]) if cfg["accel"] else 0
     n_cam = len(cfg["cam"]["lm_idx"]) if cfg["cam"] else 0
-    return 740 * n_imu + 1012 * n_cam
+    if cfg.get("split"):
+        return 452 * ng + 744 * na + 1020 * n_cam
+    return 740 * (ng + na) + 1012 * n_cam
 
 
 def num_measurements(cfg):
