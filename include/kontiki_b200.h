@@ -136,6 +136,13 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
                         const ktk_group_out* d_outs);
 int ktk_synchronize(ktk_problem* p);
 
+/* Point queries on the whole trajectory -- trajectory.position(t) / velocity / acceleration / orientation /
+ * angular_velocity of the reference's Python API (python/src/kontiki/trajectories/trajectory_helper.h:12-34 ->
+ * trajectories/trajectory.h:98-132).  Host buffers; out[16 n] = position(3) | velocity(3) | acceleration(3) |
+ * orientation x,y,z,w (4) | angular velocity in the world frame (3); status[n] per time (KTK_ERANGE where the reference
+ * throws std::range_error, rows NaN).  Returns the worst status. */
+int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status);
+
 /* Number of kernel launches ktk_evaluate_device enqueued since the problem was created. */
 int64_t ktk_launch_count(const ktk_problem* p);
 

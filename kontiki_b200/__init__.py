@@ -7,3 +7,6 @@ from . import _lib  # noqa: F401
 from ._lib import Problem, KontikiError  # noqa: F401
 
 __version__ = "0.1.0"
+
+from . import measurements, sensors, sfm, trajectories  # noqa: F401,E402
+from .estimator import CallbackReturnType, IterationSummary, Summary, TerminationType, TrajectoryEstimator  # noqa: F401,E402

@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate"]
 
 _lib = None
 
@@ -79,6 +79,7 @@ def lib():
         L.ktk_num_knot_doubles.argtypes = [C.c_void_p]
         L.ktk_num_knot_doubles.restype = C.c_int64
         L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
+        L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         _lib = L
@@ -244,6 +245,25 @@ class Problem:
         arr = self._out_array(outs, _ptr)
         check(lib().ktk_evaluate(self._h, _ptr(knots), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
         return outs
+
+    def _flat_knots(self, knots):
+        if self.split:
+            r3, so3 = _f64(knots[0]), _f64(knots[1])
+            if r3.shape != (self.n_r3, 3) or so3.shape != (self.n_so3, 4):
+                raise ValueError(f"knots must be ((n_r3={self.n_r3}, 3), (n_so3={self.n_so3}, 4))")
+            return np.concatenate([r3.reshape(-1), so3.reshape(-1)])
+        knots = _f64(knots)
+        if knots.shape != (self.n_knots, 7):
+            raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
+        return knots.reshape(-1)
+
+    def traj_evaluate(self, knots, t):
+        """ktk_traj_evaluate: dict of position / velocity / acceleration / orientation (x,y,z,w) / angular_velocity at times t."""
+        kf = self._flat_knots(knots)
+        t = _f64(np.atleast_1d(t))
+        out, st = np.zeros((len(t), 16)), np.zeros(len(t), np.int32)
+        check(lib().ktk_traj_evaluate(self._h, _ptr(kf), len(t), _ptr(t), _ptr(out), _ptr(st)))
+        return dict(position=out[:, 0:3], velocity=out[:, 3:6], acceleration=out[:, 6:9], orientation=out[:, 9:13], angular_velocity=out[:, 13:16])
 
     def evaluate_flat(self, knots_flat, rho, flags, outs):
         """ktk_evaluate on an already flattened float64 knot array (the C ABI's layout); outs as from alloc_outputs()."""

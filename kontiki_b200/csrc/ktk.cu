@@ -389,6 +389,25 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
   if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)perm, lane);
 }
 
+__global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,
+                                double* __restrict__ out, int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double o[16];
+  const int st = traj_eval_se3(sp, knots, pairs, t[i], o);
+  for (int c = 0; c < 16; ++c) out[16 * (size_t)i + c] = st == 0 ? o[c] : nan("");
+  status[i] = st;
+}
+__global__ void k_traj_eval_split(SplitConst sp, const double* __restrict__ vecs, const double* __restrict__ quats, const double* __restrict__ pairs, int n,
+                                  const double* __restrict__ t, double* __restrict__ out, int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double o[16];
+  const int st = traj_eval_split(sp, vecs, quats, pairs, t[i], o);
+  for (int c = 0; c < 16; ++c) out[16 * (size_t)i + c] = st == 0 ? o[c] : nan("");
+  status[i] = st;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -836,6 +855,46 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     if (dev[gi].i0_d && split && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_d, dev[gi].i0_d, n * sizeof(int), cudaMemcpyDeviceToHost, s));
   }
   return ktk_synchronize(p);
+}
+
+int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status) {
+  if (!p || !knots || (n > 0 && (!t || !out || !status))) return fail(KTK_EINVAL, "NULL argument");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set before evaluation");
+  if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device; there is no CPU evaluation path");
+  if (n == 0) return KTK_OK;
+  KTK_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  int st;
+  const size_t nkd = (size_t)ktk_num_knot_doubles(p);
+  DevBuf<double> d_t, d_out; DevBuf<int> d_st;
+  if ((st = p->d_knots7.resize(nkd)) || (st = d_t.resize((size_t)n)) || (st = d_out.resize((size_t)n * 16)) || (st = d_st.resize((size_t)n))) return st;
+  KTK_CUDA(cudaMemcpyAsync(p->d_knots7.p, knots, nkd * sizeof(double), cudaMemcpyHostToDevice, s));
+  KTK_CUDA(cudaMemcpyAsync(d_t.p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+  KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
+  const int blocks = (int)((n + 127) / 128);
+  if (p->traj == 0) {
+    const int nk = p->sp.n_knots;
+    if ((st = p->d_knots8.resize((size_t)nk * kKnotStride)) || (st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
+    k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p);
+    k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
+    k_traj_eval_se3<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
+  } else {
+    const SplitConst& sp = p->spl;
+    const double* d_quats = p->d_knots7.p + (size_t)3 * sp.n_r3;
+    if ((st = p->d_vecs4.resize((size_t)sp.n_r3 * kVecStride)) || (st = p->d_so3pairs.resize((size_t)sp.n_so3 * kSo3PairStride))) return st;
+    k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, sp.n_r3, p->d_vecs4.p);
+    k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
+    k_traj_eval_split<<<blocks, 128, 0, s>>>(sp, p->d_vecs4.p, d_quats, p->d_so3pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
+  }
+  p->launches += 3;
+  KTK_CUDA(cudaGetLastError());
+  KTK_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  KTK_CUDA(cudaMemcpyAsync(status, d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
+  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+  KTK_CUDA(cudaStreamSynchronize(s));
+  if (*p->h_err == kStatusRuntime) return fail(KTK_ERUNTIME, "logq: Only implemented for unit quaternions (a SO3 knot pair is not unit norm)");
+  for (int64_t i = 0; i < n; ++i) if (status[i] == kStatusRange) return fail(KTK_ERANGE, "t is out of range for the spline");
+  return KTK_OK;
 }
 
 int ktk_set_profiling(ktk_problem* p, int32_t on) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->profiling = on != 0; return KTK_OK; }

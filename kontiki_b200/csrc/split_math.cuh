@@ -389,4 +389,93 @@ KB_HD int static_rs_row_finish_split(const CameraConst& cam, const double* vecs,
   return 0;
 }
 
+
+// =================================================================================================================
+// Point queries: trajectory.position(t) / velocity / acceleration / orientation / angular_velocity on the WHOLE spline
+// (python/src/kontiki/trajectories/trajectory_helper.h:12-34 -> trajectory.h:98-132; the owning entity is one segment).
+// out[16] = position(3) | velocity(3) | acceleration(3) | orientation x,y,z,w (4) | angular velocity, world frame (3)
+// =================================================================================================================
+KB_HD void quat_mul(const double* a, const double* b, double* o) {
+  const double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  const double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+  const double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+  const double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+  o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+// unit quaternion of Exp(theta), theta a rotation vector
+KB_HD void quat_exp(V3 th, double* q) {
+  const double x = dot(th, th);
+  double k, c;
+  if (x < 1e-8) { k = 0.5 - x / 48.0; c = 1.0 - x / 8.0 + x * x / 384.0; }
+  else { const double a = sqrt(x); k = sin(0.5 * a) / a; c = cos(0.5 * a); }
+  q[0] = k * th.x; q[1] = k * th.y; q[2] = k * th.z; q[3] = c;
+}
+// body twist of the cumulative SE3 spline and its time derivative (the forward half of accel_se3)
+KB_HD void se3_body_twist(const double* p1, const double* p2, const double* p3, const Basis& bs, V3& vb, V3& wb, V3& dvb) {
+  const V3 u1 = v3(p1[0], p1[1], p1[2]), f1 = v3(p1[3], p1[4], p1[5]);
+  const V3 u2 = v3(p2[0], p2[1], p2[2]), f2 = v3(p2[3], p2[4], p2[5]);
+  const V3 u3 = v3(p3[0], p3[1], p3[2]), f3 = v3(p3[3], p3[4], p3[5]);
+  ExpPart e;
+  const V3 s1u = bs.dB[0] * u1, s1w = bs.dB[0] * f1, d1u = bs.d2B[0] * u1, d1w = bs.d2B[0] * f1;
+  exp_part(p2, bs.B[1], true, false, e);
+  const V3 y2w = mul_t(e.E, s1w), y2u = mul_t(e.E, s1u - cross(e.a, s1w));
+  const V3 z2w = mul_t(e.E, d1w), z2u = mul_t(e.E, d1u - cross(e.a, d1w));
+  const V3 s2u = y2u + bs.dB[1] * u2, s2w = y2w + bs.dB[1] * f2;
+  const V3 d2u = z2u - bs.dB[1] * (cross(f2, y2u) + cross(u2, y2w)) + bs.d2B[1] * u2;
+  const V3 d2w = z2w - bs.dB[1] * cross(f2, y2w) + bs.d2B[1] * f2;
+  exp_part(p3, bs.B[2], true, false, e);
+  const V3 y3w = mul_t(e.E, s2w), y3u = mul_t(e.E, s2u - cross(e.a, s2w));
+  const V3 z3u = mul_t(e.E, d2u - cross(e.a, d2w));
+  vb = y3u + bs.dB[2] * u3; wb = y3w + bs.dB[2] * f3;
+  dvb = z3u - bs.dB[2] * (cross(f3, y3u) + cross(u3, y3w)) + bs.d2B[2] * u3;
+}
+KB_HD int traj_eval_se3(const SplineConst& sp, const double* knots, const double* pairs, double t, double* out) {
+  Segment s; s.start = 0; s.n = sp.n_knots;
+  int i0; double u;
+  if (!segment_locate(s, t, sp.t0, sp.dt, i0, u)) return kStatusRange;
+  const Basis bs = cumulative_basis(u, sp.dt);
+  const double* k0 = knots + (size_t)i0 * kKnotStride;
+  const double* p1 = pairs + (size_t)(i0 + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  Pose P; pose_forward(k0, p1, p2, p3, bs, P);
+  V3 vb, wb, dvb;
+  se3_body_twist(p1, p2, p3, bs, vb, wb, dvb);
+  const V3 v = P.R * vb, w = P.R * wb;
+  V3 a;
+  if (sp.compat_zero_dB) { Basis b0 = bs; b0.dB[0] = b0.dB[1] = b0.dB[2] = 0.0; V3 v0, w0, d0; se3_body_twist(p1, p2, p3, b0, v0, w0, d0); a = P.R * d0; }
+  else a = P.R * (cross(wb, vb) + dvb);
+  double q[4] = {k0[0], k0[1], k0[2], k0[3]}, e[4];
+  quat_exp(bs.B[0] * v3(p1[3], p1[4], p1[5]), e); quat_mul(q, e, q);
+  quat_exp(bs.B[1] * v3(p2[3], p2[4], p2[5]), e); quat_mul(q, e, q);
+  quat_exp(bs.B[2] * v3(p3[3], p3[4], p3[5]), e); quat_mul(q, e, q);
+  const double qn = 1.0 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);     // Sophus renormalises
+  out[0] = P.p.x; out[1] = P.p.y; out[2] = P.p.z; out[3] = v.x; out[4] = v.y; out[5] = v.z; out[6] = a.x; out[7] = a.y; out[8] = a.z;
+  out[9] = q[0] * qn; out[10] = q[1] * qn; out[11] = q[2] * qn; out[12] = q[3] * qn; out[13] = w.x; out[14] = w.y; out[15] = w.z;
+  return 0;
+}
+KB_HD int traj_eval_split(const SplitConst& sp, const double* vecs, const double* quats, const double* pairs, double t, double* out) {
+  Segment s; int ia, ib; double ua, ub;
+  s.start = 0; s.n = sp.n_r3;
+  if (!segment_locate(s, t, sp.t0_r3, sp.dt_r3, ia, ua)) return kStatusRange;
+  s.start = 0; s.n = sp.n_so3;
+  if (!segment_locate(s, t, sp.t0_so3, sp.dt_so3, ib, ub)) return kStatusRange;
+  const BasisR3 br = r3_basis(ua, sp.dt_r3);
+  const Basis bs = cumulative_basis(ub, sp.dt_so3);
+  const double* c0 = vecs + (size_t)ia * kVecStride;
+  const V3 p = r3_combine(c0, br.Bp), v = r3_combine(c0, br.Bv), a = r3_combine(c0, br.Ba);
+  const double* q0 = quats + (size_t)ib * kQuatStride;
+  const double* p1 = pairs + (size_t)(ib + 1) * kSo3PairStride; const double* p2 = p1 + kSo3PairStride; const double* p3 = p2 + kSo3PairStride;
+  ExpPart e2, e3;
+  so3_exp_part(p2, bs.B[1], e2); so3_exp_part(p3, bs.B[2], e3);
+  const V3 f1 = v3(2.0 * p1[0], 2.0 * p1[1], 2.0 * p1[2]), f2 = v3(2.0 * p2[0], 2.0 * p2[1], 2.0 * p2[2]), f3 = v3(2.0 * p3[0], 2.0 * p3[1], 2.0 * p3[2]);
+  const V3 wb = mul_t(e3.E, mul_t(e2.E, bs.dB[0] * f1) + bs.dB[1] * f2) + bs.dB[2] * f3;
+  const V3 w = so3_forward(q0, p1, bs) * wb;
+  double q[4] = {q0[0], q0[1], q0[2], q0[3]}, e[4];
+  quat_exp(bs.B[0] * f1, e); quat_mul(q, e, q);
+  quat_exp(bs.B[1] * f2, e); quat_mul(q, e, q);
+  quat_exp(bs.B[2] * f3, e); quat_mul(q, e, q);                                             // Eigen: no renormalisation
+  out[0] = p.x; out[1] = p.y; out[2] = p.z; out[3] = v.x; out[4] = v.y; out[5] = v.z; out[6] = a.x; out[7] = a.y; out[8] = a.z;
+  out[9] = q[0]; out[10] = q[1]; out[11] = q[2]; out[12] = q[3]; out[13] = w.x; out[14] = w.y; out[15] = w.z;
+  return 0;
+}
+
 }  // namespace kb

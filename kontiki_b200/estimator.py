@@ -1,0 +1,449 @@
+"""TrajectoryEstimator with the reference's Python surface (python/src/kontiki/py_trajectory_estimator.cc:59-79,
+cpplib/include/kontiki/trajectory_estimator.h): add_measurement() collects measurements into batched groups, every
+residual + Jacobian evaluation runs on the GPU through the C ABI, solve() is a Levenberg-Marquardt loop around it.
+
+The reference delegates solve() to Ceres (SPARSE_SCHUR trust region).  Here the evaluation -- the hot path this repository
+is about -- is the CUDA library; the linear algebra of the step is host-side sparse Cholesky (scipy), i.e. the control
+plane stays on the host exactly as in the reference.  SURVEY.md section 8f-1 ("next"): normal equations on the device.
+"""
+import enum
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import _lib
+from .measurements import AccelerometerMeasurement, GyroscopeMeasurement, StaticRsCameraMeasurement, _problem_for
+from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
+
+
+class CallbackReturnType(enum.Enum):       # py_ceres.cc:61-66
+    Abort = 0
+    Continue = 1
+    TerminateSuccessfully = 2
+
+
+class TerminationType(enum.Enum):          # py_ceres.cc:96-103
+    Convergence = 0
+    NoConvergence = 1
+    Failure = 2
+    UserSuccess = 3
+    UserFailure = 4
+
+
+class IterationSummary:                    # py_ceres.cc:68-93
+    def __init__(self, **kw):
+        self.iteration = 0
+        self.step_is_valid = self.step_is_successful = True
+        self.step_is_nonmonotonic = False
+        self.cost = self.cost_change = self.gradient_max_norm = self.gradient_norm = self.step_norm = 0.0
+        self.relative_decrease = self.trust_region_radius = self.eta = self.step_size = 0.0
+        self.line_search_function_evaluations = self.line_search_gradient_evaluations = self.line_search_iterations = 0
+        self.linear_solver_iterations = 0
+        self.iteration_time_in_seconds = self.step_solver_time_in_seconds = self.cumulative_time_in_seconds = 0.0
+        self.__dict__.update(kw)
+
+
+class Summary:                             # py_ceres.cc:15-58 (the fields this solver can fill)
+    def __init__(self):
+        self.message = ""
+        self.initial_cost = self.final_cost = self.fixed_cost = 0.0
+        self.iterations = []
+        self.termination_type = TerminationType.NoConvergence
+        self.num_successful_steps = self.num_unsuccessful_steps = self.num_inner_iteration_steps = 0
+        self.preprocessor_time_in_seconds = self.minimizer_time_in_seconds = self.postprocessor_time_in_seconds = 0.0
+        self.total_time_in_seconds = self.linear_solver_time_in_seconds = 0.0
+        self.residual_evaluation_time_in_seconds = self.jacobian_evaluation_time_in_seconds = 0.0
+        self.num_parameter_blocks = self.num_parameters = self.num_effective_parameters = 0
+        self.num_residual_blocks = self.num_residuals = 0
+        self.num_parameter_blocks_reduced = self.num_parameters_reduced = self.num_effective_parameters_reduced = 0
+        self.num_residual_blocks_reduced = self.num_residuals_reduced = 0
+        self.is_constrained = False
+        self.num_threads_given = self.num_threads_used = 1
+
+    def IsSolutionUsable(self):
+        return self.termination_type in (TerminationType.Convergence, TerminationType.NoConvergence, TerminationType.UserSuccess)
+
+    def BriefReport(self):
+        return (f"kontiki_b200 LM report: Iterations: {len(self.iterations)}, Initial cost: {self.initial_cost:e}, "
+                f"Final cost: {self.final_cost:e}, Termination: {self.termination_type.name}")
+
+    def FullReport(self):
+        lines = [self.BriefReport(), f"Parameters {self.num_parameters} (reduced {self.num_parameters_reduced}), residuals {self.num_residuals}",
+                 f"Time: residual eval {self.residual_evaluation_time_in_seconds:.4f} s, jacobian eval {self.jacobian_evaluation_time_in_seconds:.4f} s, "
+                 f"linear solver {self.linear_solver_time_in_seconds:.4f} s, total {self.total_time_in_seconds:.4f} s", self.message]
+        return "\n".join(lines)
+
+
+def _se3_plus_jacobian(cp):
+    """d Plus(T, delta)/d delta at 0 for Plus = T * exp([upsilon; omega]) (uniform_se3_spline_trajectory.h:25-48): (n, 7, 6)."""
+    n = len(cp)
+    P = np.zeros((n, 7, 6))
+    x, y, z, w = cp[:, 0], cp[:, 1], cp[:, 2], cp[:, 3]
+    # quaternion rows (x,y,z,w) x omega columns: 1/2 (w I + hat(v)) ; -1/2 v^T
+    P[:, 0, 3], P[:, 0, 4], P[:, 0, 5] = 0.5 * w, -0.5 * z, 0.5 * y
+    P[:, 1, 3], P[:, 1, 4], P[:, 1, 5] = 0.5 * z, 0.5 * w, -0.5 * x
+    P[:, 2, 3], P[:, 2, 4], P[:, 2, 5] = -0.5 * y, 0.5 * x, 0.5 * w
+    P[:, 3, 3], P[:, 3, 4], P[:, 3, 5] = -0.5 * x, -0.5 * y, -0.5 * z
+    # translation rows x upsilon columns: R
+    P[:, 4, 0] = 1 - 2 * (y * y + z * z); P[:, 4, 1] = 2 * (x * y - w * z); P[:, 4, 2] = 2 * (x * z + w * y)
+    P[:, 5, 0] = 2 * (x * y + w * z); P[:, 5, 1] = 1 - 2 * (x * x + z * z); P[:, 5, 2] = 2 * (y * z - w * x)
+    P[:, 6, 0] = 2 * (x * z - w * y); P[:, 6, 1] = 2 * (y * z + w * x); P[:, 6, 2] = 1 - 2 * (x * x + y * y)
+    return P
+
+
+def _se3_plus(cp, delta):
+    """T * exp(delta), delta (n,6) = [upsilon; omega] (Sophus order)."""
+    from .synthetic import _so3_exp, quat_to_rot, so3_exp_quat
+    ups, om = delta[:, :3], delta[:, 3:]
+    _, V = _so3_exp(om)
+    R = quat_to_rot(cp[:, :4])
+    t = cp[:, 4:7] + (R @ (V @ ups[..., None]))[..., 0]
+    dq = so3_exp_quat(om)
+    a, b = cp[:, :4], dq
+    q = np.stack([a[:, 3] * b[:, 0] + a[:, 0] * b[:, 3] + a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1],
+                  a[:, 3] * b[:, 1] + a[:, 1] * b[:, 3] + a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                  a[:, 3] * b[:, 2] + a[:, 2] * b[:, 3] + a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0],
+                  a[:, 3] * b[:, 3] - a[:, 0] * b[:, 0] - a[:, 1] * b[:, 1] - a[:, 2] * b[:, 2]], 1)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return np.concatenate([q, t], 1)
+
+
+def _quat_plus_jacobian(q):
+    """ceres::EigenQuaternionParameterization: Plus(q, d) = q_d * q, q_d = (sin|d| d/|d|, cos|d|): d q/d d at 0, (n, 4, 3)."""
+    n = len(q)
+    P = np.zeros((n, 4, 3))
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    P[:, 0, 0], P[:, 0, 1], P[:, 0, 2] = w, z, -y          # vec = d w + d x v  => w I - hat(v)
+    P[:, 1, 0], P[:, 1, 1], P[:, 1, 2] = -z, w, x
+    P[:, 2, 0], P[:, 2, 1], P[:, 2, 2] = y, -x, w
+    P[:, 3, 0], P[:, 3, 1], P[:, 3, 2] = -x, -y, -z
+    return P
+
+
+def _quat_plus(q, d):
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    k = np.where(nrm > 0, np.sin(nrm) / np.maximum(nrm, 1e-300), 1.0)
+    a = np.concatenate([k * d, np.cos(nrm)], 1)
+    b = q
+    out = np.stack([a[:, 3] * b[:, 0] + a[:, 0] * b[:, 3] + a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1],
+                    a[:, 3] * b[:, 1] + a[:, 1] * b[:, 3] + a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                    a[:, 3] * b[:, 2] + a[:, 2] * b[:, 3] + a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0],
+                    a[:, 3] * b[:, 3] - a[:, 0] * b[:, 0] - a[:, 1] * b[:, 1] - a[:, 2] * b[:, 2]], 1)
+    return out / np.linalg.norm(out, axis=1, keepdims=True)
+
+
+class TrajectoryEstimator:
+    """TrajectoryEstimator(trajectory) -- same surface as the reference; `device` selects the GPU."""
+
+    def __init__(self, trajectory, device=0):
+        if not isinstance(trajectory, (UniformSE3SplineTrajectory, SplitTrajectory)):
+            raise TypeError(f"No TrajectoryEstimator declared for {type(trajectory)}")
+        self._trajectory, self._device = trajectory, device
+        self._measurements = []
+        self._callbacks = []
+        self._problem = None
+
+    trajectory = property(lambda self: self._trajectory)
+
+    def add_measurement(self, m):
+        if not isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement, StaticRsCameraMeasurement)):
+            raise TypeError(f"unsupported measurement type {type(m).__name__}")
+        # AddToEstimator checks the time span when the measurement is added (trajectory_estimator.h:97-122)
+        tr = self._trajectory
+        if isinstance(m, StaticRsCameraMeasurement):
+            ref = m.observation.landmark.reference
+            t1, t2 = sorted([ref.view.t0, m.observation.view.t0])
+            spans = [(t1 - 1e-3, t1 + m.camera.readout + 1e-3), (t2 - 1e-3, t2 + m.camera.readout + 1e-3)]
+        else:
+            spans = [(m.t, m.t)]
+        for a, b in spans:
+            if a < tr.min_time or b >= tr.max_time:
+                raise ValueError("Time span out of range for trajectory")
+        self._measurements.append(m)
+        self._problem = None
+
+    def add_callback(self, callback, update_state=False):
+        self._callbacks.append((callback, bool(update_state)))
+
+    # ---- flattening ------------------------------------------------------------------------
+    def _build(self):
+        if self._problem is not None:
+            return
+        p, _ = _problem_for(self._trajectory)
+        p.close()
+        p = _lib.Problem(self._device)
+        tr = self._trajectory
+        if isinstance(tr, UniformSE3SplineTrajectory):
+            p.set_se3_spline(tr.dt, tr.t0, len(tr), tr.compat_zero_dB)
+        else:
+            p.set_split_spline(tr.R3_spline.dt, tr.R3_spline.t0, len(tr.R3_spline), tr.SO3_spline.dt, tr.SO3_spline.t0, len(tr.SO3_spline))
+        groups, self._landmarks, lm_index = {}, [], {}
+        for i, m in enumerate(self._measurements):
+            kind = type(m)
+            sensor = m.camera if kind is StaticRsCameraMeasurement else m.imu
+            groups.setdefault((kind, id(sensor)), (sensor, []))[1].append(i)
+        self._groups = []
+        for (kind, _), (sensor, rows) in groups.items():
+            ms = [self._measurements[i] for i in rows]
+            if kind is StaticRsCameraMeasurement:
+                lm = []
+                for m in ms:
+                    L = m.observation.landmark
+                    if id(L) not in lm_index:
+                        lm_index[id(L)] = len(self._landmarks)
+                        self._landmarks.append(L)
+                    lm.append(lm_index[id(L)])
+                g = p.add_static_rs(sensor._c_camera(), np.array([m.observation.uv for m in ms]), [m.observation.view.t0 for m in ms],
+                                    np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
+                                    lm, [m.weight for m in ms], [m.huber_c for m in ms])
+                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64)))
+            else:
+                fn = p.add_gyroscope if kind is GyroscopeMeasurement else p.add_accelerometer
+                g = fn(sensor._c_sensor(), [m.t for m in ms], np.array([m._x for m in ms]), [m.weight for m in ms])
+                self._groups.append(dict(g=g, kind="gyro" if kind is GyroscopeMeasurement else "accel", rows=rows))
+        self._problem = p
+
+    def _point(self):
+        tr = self._trajectory
+        knots = tr.control_points if isinstance(tr, UniformSE3SplineTrajectory) else (tr.R3_spline.control_points, tr.SO3_spline.control_points)
+        rho = np.array([L.inverse_depth for L in self._landmarks]) if self._landmarks else None
+        return knots, rho
+
+    def evaluate(self, jacobians=True, robust=True):
+        """One batched residual (+ Jacobian) evaluation at the current state; list of per-group outputs (C ABI layouts)."""
+        self._build()
+        knots, rho = self._point()
+        flags = _lib.EVAL_RESIDUALS | (_lib.EVAL_JACOBIANS if jacobians else 0) | (_lib.EVAL_ROBUST if robust else 0)
+        return self._problem.evaluate(knots, rho, flags)
+
+    # ---- local (tangent) sparse Jacobian ----------------------------------------------------------------------------------
+    def _columns(self):
+        tr = self._trajectory
+        if isinstance(tr, UniformSE3SplineTrajectory):
+            blocks = [("se3", tr, 6)]
+        else:
+            blocks = [("r3", tr.R3_spline, 3), ("so3", tr.SO3_spline, 3)]
+        off, layout = 0, {}
+        for name, spl, dof in blocks:
+            layout[name] = (off, dof, spl)
+            off += dof * len(spl) if not spl.locked else 0
+        layout["rho"] = (off, 1, None)
+        free_lm = np.array([not L.locked for L in self._landmarks], bool) if self._landmarks else np.zeros(0, bool)
+        self._lm_col = np.full(len(self._landmarks), -1, np.int64)
+        self._lm_col[free_lm] = off + np.arange(free_lm.sum())
+        return layout, off + int(free_lm.sum())
+
+    def _sparse_system(self, outs):
+        """r (stacked) and J in local coordinates as scipy CSR, from the packed device rows."""
+        layout, ncols = self._columns()
+        tr = self._trajectory
+        rs, rows_i, cols_i, vals = [], [], [], []
+        row0 = 0
+
+        def add_blocks(Jb, first_knot, width_amb, name, nres):
+            """Jb: (n, 4, nres, width_amb) ambient blocks at knots first_knot + k."""
+            off, dof, spl = layout[name]
+            if spl.locked:
+                return
+            n = len(Jb)
+            cp = spl.control_points
+            if name == "se3":
+                P = _se3_plus_jacobian(cp)
+            elif name == "so3":
+                P = _quat_plus_jacobian(cp)
+            else:
+                P = None
+            for k in range(4):
+                kn = first_knot + k
+                Jl = Jb[:, k] if P is None else np.einsum("nra,nad->nrd", Jb[:, k], P[kn])
+                r_idx = (row0 + nres * np.arange(n)[:, None, None] + np.arange(nres)[None, :, None]) + np.zeros((1, 1, dof), np.int64)
+                c_idx = (off + dof * kn)[:, None, None] + np.arange(dof)[None, None, :] + np.zeros((1, nres, 1), np.int64)
+                rows_i.append(r_idx.reshape(-1)); cols_i.append(c_idx.reshape(-1)); vals.append(Jl.reshape(-1))
+
+        split = isinstance(tr, SplitTrajectory)
+        for grp in self._groups:
+            o = outs[grp["g"]]
+            n = len(o["r"])
+            if grp["kind"] == "cam":
+                J = o["J"].reshape(n, 114)
+                if not split:
+                    add_blocks(J[:, :56].reshape(n, 4, 2, 7), o["i0"], 7, "se3", 2)
+                    add_blocks(J[:, 56:112].reshape(n, 4, 2, 7), o["i0_b"], 7, "se3", 2)
+                else:
+                    add_blocks(J[:, 0:24].reshape(n, 4, 2, 3), o["i0"], 3, "r3", 2)
+                    add_blocks(J[:, 24:56].reshape(n, 4, 2, 4), o["i0_c"], 4, "so3", 2)
+                    add_blocks(J[:, 56:80].reshape(n, 4, 2, 3), o["i0_b"], 3, "r3", 2)
+                    add_blocks(J[:, 80:112].reshape(n, 4, 2, 4), o["i0_d"], 4, "so3", 2)
+                col = self._lm_col[grp["lm"]]
+                free = col >= 0
+                r_idx = (row0 + 2 * np.arange(n)[:, None] + np.arange(2)[None, :])[free]
+                rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(col[free], 2)); vals.append(J[free, 112:114].reshape(-1))
+                nres = 2
+            else:
+                nres = 3
+                if not split:
+                    add_blocks(o["J"].reshape(n, 4, 3, 7), o["i0"], 7, "se3", 3)
+                elif grp["kind"] == "gyro":
+                    add_blocks(o["J"].reshape(n, 4, 3, 4), o["i0_c"], 4, "so3", 3)
+                else:
+                    add_blocks(o["J"][:, :36].reshape(n, 4, 3, 3), o["i0"], 3, "r3", 3)
+                    add_blocks(o["J"][:, 36:].reshape(n, 4, 3, 4), o["i0_c"], 4, "so3", 3)
+            rs.append(o["r"].reshape(-1))
+            row0 += nres * n
+        r = np.concatenate(rs) if rs else np.zeros(0)
+        if vals:
+            J = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows_i), np.concatenate(cols_i))), shape=(row0, ncols))
+        else:
+            J = sp.csr_matrix((row0, ncols))
+        return r, J, layout
+
+    def _apply_step(self, delta, layout, rho_lower=0.0):
+        for name in ("se3", "r3", "so3"):
+            if name not in layout:
+                continue
+            off, dof, spl = layout[name]
+            if spl.locked:
+                continue
+            d = delta[off:off + dof * len(spl)].reshape(len(spl), dof)
+            cp = spl.control_points
+            if name == "se3":
+                cp[:] = _se3_plus(cp, d)
+            elif name == "so3":
+                cp[:] = _quat_plus(cp, d)
+            else:
+                cp[:] = cp + d
+        for L, c in zip(self._landmarks, self._lm_col):
+            if c >= 0:
+                L.inverse_depth = max(rho_lower, L.inverse_depth + delta[c])      # lower bound 0, static_rscamera_measurement.h:178-181
+
+    def _snapshot(self):
+        tr = self._trajectory
+        spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
+        return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks]
+
+    def _restore(self, snap):
+        tr = self._trajectory
+        spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
+        for s, c in zip(spl, snap[0]):
+            s.control_points[:] = c
+        for L, v in zip(self._landmarks, snap[1]):
+            L.inverse_depth = v
+
+    @staticmethod
+    def _cost(outs, groups, hubers):
+        """1/2 sum rho(|r|^2); with the corrector applied |r_corrected|^2 == rho(s) for Huber."""
+        return 0.5 * sum(float((outs[g["g"]]["r"] ** 2).sum()) for g in groups)
+
+    def solve(self, max_iterations=50, progress=True, num_threads=-1):
+        """Levenberg-Marquardt on the GPU-evaluated residuals/Jacobians; returns a Summary (py_ceres.cc:15-58 fields)."""
+        t_start = time.perf_counter()
+        s = Summary()
+        self._build()
+        layout, ncols = self._columns()
+        tr = self._trajectory
+        n_knot_params = (7 * len(tr)) if isinstance(tr, UniformSE3SplineTrajectory) else (3 * len(tr.R3_spline) + 4 * len(tr.SO3_spline))
+        n_sensors = len(self._groups)        # one sensor per group: q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
+        s.num_parameters = n_knot_params + len(self._landmarks) + 8 * n_sensors
+        s.num_parameter_blocks = n_knot_params // (7 if isinstance(tr, UniformSE3SplineTrajectory) else 1) + len(self._landmarks) + 3 * n_sensors
+        s.num_parameters_reduced = ncols + self._ambient_free(layout)      # ambient sizes of the non-constant blocks
+        s.num_effective_parameters_reduced = ncols
+        s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)
+        t0 = time.perf_counter()
+        outs = self.evaluate(jacobians=True)
+        s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
+        cost = self._cost(outs, self._groups, None)
+        s.initial_cost = cost
+        s.num_residuals = s.num_residuals_reduced = sum(outs[g["g"]]["r"].size for g in self._groups)
+        radius, nu = 1e4, 2.0                               # Ceres defaults: initial_trust_region_radius 1e4
+        term = TerminationType.NoConvergence
+        if progress:
+            print("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius")
+        if ncols == 0:
+            s.final_cost, s.termination_type, s.message = cost, TerminationType.Convergence, "no free parameters"
+            return s
+        for it in range(max_iterations + 1):
+            t_it = time.perf_counter()
+            r, J, layout = self._sparse_system(outs)
+            g = J.T @ r
+            gmax = float(np.abs(g).max()) if g.size else 0.0
+            isum = IterationSummary(iteration=it, cost=cost, gradient_max_norm=gmax, gradient_norm=float(np.linalg.norm(g)), trust_region_radius=radius)
+            if it == 0:
+                s.iterations.append(isum)
+                if progress:
+                    print(f"{it:4d}  {cost:12.6e}  {0.0:10.2e}  {gmax:10.2e}  {0.0:9.2e}  {0.0:9.2e}  {radius:9.2e}")
+            if gmax < 1e-10:                                # Ceres gradient_tolerance
+                term, s.message = TerminationType.Convergence, "Gradient tolerance reached"
+                break
+            if it == max_iterations:
+                s.message = "Maximum number of iterations reached"
+                break
+            H = (J.T @ J).tocsc()
+            D = H.diagonal()
+            t_ls = time.perf_counter()
+            try:
+                delta = spla.spsolve(H + sp.diags(np.clip(D, 1e-6, 1e32) / radius), -g)
+            except Exception as e:      # noqa: BLE001
+                term, s.message = TerminationType.Failure, f"linear solver failed: {e}"
+                break
+            s.linear_solver_time_in_seconds += time.perf_counter() - t_ls
+            snap = self._snapshot()
+            self._apply_step(delta, layout)
+            t0 = time.perf_counter()
+            try:
+                outs_new = self.evaluate(jacobians=True)
+                cost_new = self._cost(outs_new, self._groups, None)
+            except ValueError:
+                cost_new, outs_new = np.inf, None
+            s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
+            model = -float(delta @ (g + 0.5 * (H @ delta)))
+            rho_ratio = (cost - cost_new) / model if model > 0 else -1.0
+            step_norm = float(np.linalg.norm(delta))
+            ok = np.isfinite(cost_new) and rho_ratio > 1e-3
+            isum = IterationSummary(iteration=it + 1, cost=cost_new if ok else cost, cost_change=cost - cost_new, step_norm=step_norm, relative_decrease=rho_ratio,
+                                    trust_region_radius=radius, step_is_successful=bool(ok), gradient_max_norm=gmax,
+                                    iteration_time_in_seconds=time.perf_counter() - t_it, cumulative_time_in_seconds=time.perf_counter() - t_start)
+            if ok:
+                rel = (cost - cost_new) / max(cost, 1e-300)
+                cost, outs = cost_new, outs_new
+                radius = radius / max(1.0 / 3.0, 1.0 - (2.0 * rho_ratio - 1.0) ** 3)
+                nu = 2.0
+                s.num_successful_steps += 1
+            else:
+                self._restore(snap)
+                radius, nu = radius / nu, 2 * nu
+                s.num_unsuccessful_steps += 1
+                rel = 1.0
+            s.iterations.append(isum)
+            if progress:
+                print(f"{it + 1:4d}  {isum.cost:12.6e}  {isum.cost_change:10.2e}  {gmax:10.2e}  {step_norm:9.2e}  {rho_ratio:9.2e}  {radius:9.2e}")
+            stop = None
+            for cb, _ in self._callbacks:
+                res = cb(isum)
+                if res is not None and res is not CallbackReturnType.Continue:
+                    stop = res
+            if stop is CallbackReturnType.Abort:
+                term, s.message = TerminationType.UserFailure, "User callback returned SOLVER_ABORT"
+                break
+            if stop is CallbackReturnType.TerminateSuccessfully:
+                term, s.message = TerminationType.UserSuccess, "User callback returned SOLVER_TERMINATE_SUCCESSFULLY"
+                break
+            if ok and rel < 1e-6:                           # Ceres function_tolerance
+                term, s.message = TerminationType.Convergence, "Function tolerance reached"
+                break
+            if radius < 1e-32:
+                term, s.message = TerminationType.Failure, "Trust region radius collapsed"
+                break
+        s.final_cost = cost
+        s.termination_type = term
+        s.total_time_in_seconds = s.minimizer_time_in_seconds = time.perf_counter() - t_start
+        return s
+
+    def _ambient_free(self, layout):
+        """Ceres' num_parameters_reduced counts AMBIENT sizes of the non-constant blocks (7 per SE3 knot, ...)."""
+        extra = 0
+        for name, amb in (("se3", 7), ("r3", 3), ("so3", 4)):
+            if name in layout and not layout[name][2].locked:
+                extra += (amb - layout[name][1]) * len(layout[name][2])
+        return extra

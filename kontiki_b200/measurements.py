@@ -1,0 +1,81 @@
+"""Measurement classes with the reference's Python surface (python/src/kontiki/measurements/py_gyroscope_measurement.cc:23-32,
+py_accelerometer_measurement.cc, py_static_rscamera_measurement.cc:41-56, measurement_helper.h:19-25).  error / measure /
+project evaluate ONE row through the CUDA library; the batched path is TrajectoryEstimator."""
+import numpy as np
+
+from . import _lib
+from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
+
+
+def _problem_for(traj):
+    """A ktk problem bound to `traj` and the knots argument for it."""
+    p = _lib.Problem(0)
+    if isinstance(traj, UniformSE3SplineTrajectory):
+        traj._check()
+        p.set_se3_spline(traj.dt, traj.t0, len(traj), traj.compat_zero_dB)
+        return p, traj.control_points
+    if isinstance(traj, SplitTrajectory):
+        r, s = traj.R3_spline, traj.SO3_spline
+        r._check()
+        s._check()
+        p.set_split_spline(r.dt, r.t0, len(r), s.dt, s.t0, len(s))
+        return p, (r.control_points, s.control_points)
+    raise TypeError(f"No CUDA evaluation path for {type(traj).__name__} (UniformSE3SplineTrajectory and SplitTrajectory are built)")
+
+
+class _ImuMeasurement:
+    _add = None
+
+    def __init__(self, imu, t, x, weight=1.0):
+        self.imu, self.t, self.weight = imu, float(t), float(weight)
+        self._x = np.asarray(x, float).reshape(3).copy()
+
+    def error(self, trajectory):
+        p, knots = _problem_for(trajectory)
+        getattr(p, self._add)(self.imu._c_sensor(), [self.t], self._x[None, :], [self.weight])
+        return p.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0]
+
+    def measure(self, trajectory):
+        # error = weight (x - measure)   (gyroscope_measurement.h:36-38)
+        p, knots = _problem_for(trajectory)
+        getattr(p, self._add)(self.imu._c_sensor(), [self.t], np.zeros((1, 3)), [1.0])
+        return -p.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0]
+
+
+class GyroscopeMeasurement(_ImuMeasurement):
+    """GyroscopeMeasurement(imu, t, w[, weight])"""
+    _add = "add_gyroscope"
+    w = property(lambda self: self._x.copy())
+
+
+class AccelerometerMeasurement(_ImuMeasurement):
+    """AccelerometerMeasurement(imu, t, a[, weight])"""
+    _add = "add_accelerometer"
+    a = property(lambda self: self._x.copy())
+
+
+class StaticRsCameraMeasurement:
+    """StaticRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (static_rscamera_measurement.h:62-69)"""
+
+    def __init__(self, camera, observation, huber_c=5.0, weight=1.0):
+        self.camera, self.observation, self.huber_c, self.weight = camera, observation, float(huber_c), float(weight)
+
+    def _row(self):
+        obs = self.observation
+        ref = obs.landmark.reference
+        return dict(obs_uv=obs.uv[None, :], obs_t0=[obs.view.t0], ref_uv=ref.uv[None, :], ref_t0=[ref.view.t0], rho=obs.landmark.inverse_depth)
+
+    def _residual(self, trajectory, weight):
+        p, knots = _problem_for(trajectory)
+        r = self._row()
+        p.add_static_rs(self.camera._c_camera(), r["obs_uv"], r["obs_t0"], r["ref_uv"], r["ref_t0"], [0], [weight])
+        return p.evaluate(knots, np.array([r["rho"]]), _lib.EVAL_RESIDUALS)[0]["r"][0]      # no loss: error() is the raw residual
+
+    def error(self, trajectory):
+        return self._residual(trajectory, self.weight)
+
+    def project(self, trajectory):
+        # error = weight (uv - project)   (static_rscamera_measurement.h:89-94)
+        return self.observation.uv - self._residual(trajectory, 1.0)
+
+    measure = project

@@ -1,0 +1,66 @@
+"""Sensor classes with the reference's Python surface (python/src/kontiki/sensors/sensors_helper.h:12-35, camera_help.h:25-49,
+py_pinhole_camera.cc, py_basic_imu.cc).  Only what the built path needs is implemented: BasicImu and PinholeCamera with
+locked relative pose / time offset (sensors/sensors.h:91-109 defaults)."""
+import numpy as np
+
+from . import _lib
+
+
+class _Sensor:
+    def __init__(self):
+        self._q_ct = np.array([0.0, 0.0, 0.0, 1.0])          # x, y, z, w
+        self._p_ct = np.zeros(3)
+        self.time_offset = 0.0
+        self.max_time_offset = 0.1                           # sensors.h:107
+        self.relative_orientation_locked = True
+        self.relative_position_locked = True
+        self.time_offset_locked = True
+
+    @property
+    def relative_pose(self):
+        q = self._q_ct
+        return (np.array([q[3], q[0], q[1], q[2]]), self._p_ct.copy())      # (w, x, y, z), p
+
+    @relative_pose.setter
+    def relative_pose(self, pose):
+        q, p = pose
+        q = np.asarray(q, float)
+        self._q_ct = np.array([q[1], q[2], q[3], q[0]])
+        self._p_ct = np.asarray(p, float).copy()
+
+    def from_trajectory(self, X):                            # sensors.h:79-81
+        from .trajectories import _quat_xyzw_to_rot
+        return _quat_xyzw_to_rot(self._q_ct) @ np.asarray(X, float) + self._p_ct
+
+    def to_trajectory(self, X):                              # sensors.h:83-85
+        from .trajectories import _quat_xyzw_to_rot
+        return _quat_xyzw_to_rot(self._q_ct).T @ (np.asarray(X, float) - self._p_ct)
+
+    def _c_sensor(self):
+        return _lib.make_sensor(self._q_ct, self._p_ct, self.time_offset, self.max_time_offset, self.relative_orientation_locked,
+                                self.relative_position_locked, self.time_offset_locked)
+
+
+class BasicImu(_Sensor):
+    """sensors/basic_imu.h:26-33."""
+
+
+class PinholeCamera(_Sensor):
+    """sensors/pinhole_camera.h; PinholeCamera(rows, cols, readout[, camera_matrix])."""
+
+    def __init__(self, rows, cols, readout, camera_matrix=None):
+        super().__init__()
+        self.rows, self.cols, self.readout = int(rows), int(cols), float(readout)
+        self.camera_matrix = np.eye(3) if camera_matrix is None else np.asarray(camera_matrix, float).reshape(3, 3).copy()
+
+    def project(self, X):                                    # pinhole_camera.h:47-51
+        p = self.camera_matrix @ np.asarray(X, float)
+        return p[:2] / p[2]
+
+    def unproject(self, y):                                  # pinhole_camera.h:63-67
+        return np.linalg.inv(self.camera_matrix) @ np.array([y[0], y[1], 1.0])
+
+    def _c_camera(self):
+        return _lib.make_camera(self.rows, self.cols, self.readout, self.camera_matrix, q_ct=self._q_ct, p_ct=self._p_ct, time_offset=self.time_offset,
+                                max_time_offset=self.max_time_offset, q_locked=self.relative_orientation_locked,
+                                p_locked=self.relative_position_locked, time_offset_locked=self.time_offset_locked)

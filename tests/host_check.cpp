@@ -115,4 +115,15 @@ void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
   }
 }
 
+
+void hc_traj_eval_se3(double t0, double dt, int n_knots, int compat, const double* knots8, const double* pairs, int n, const double* t, double* out, int* status) {
+  SplineConst sp{t0, dt, n_knots, compat};
+  for (int i = 0; i < n; ++i) status[i] = traj_eval_se3(sp, knots8, pairs, t[i], out + 16 * i);
+}
+void hc_traj_eval_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, const double* vecs4, const double* quats,
+                        const double* pairs, int n, const double* t, double* out, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  for (int i = 0; i < n; ++i) status[i] = traj_eval_split(sp, vecs4, quats, pairs, t[i], out + 16 * i);
+}
+
 }  // extern "C"

@@ -124,3 +124,20 @@ def static_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs
                              C.c_double(cam.readout), int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0),
                              _p(lm_idx), _p(rho), _p(w), _p(hc), _p(r), _p(J), _p(idx), _p(st))
     return dict(r=r, J=J, idx=idx, status=st)
+
+
+def traj_eval_se3(knots7, dt, t0, t, compat=False):
+    k8, pairs = prepass(knots7)
+    t = _f(np.atleast_1d(t))
+    out, st = np.zeros((len(t), 16)), np.zeros(len(t), np.int32)
+    lib().hc_traj_eval_se3(C.c_double(t0), C.c_double(dt), len(k8), int(compat), _p(k8), _p(pairs), len(t), _p(t), _p(out), _p(st))
+    return out, st
+
+
+def traj_eval_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t):
+    v4, q4, pairs, _ = split_prepass(vecs3, quats)
+    t = _f(np.atleast_1d(t))
+    out, st = np.zeros((len(t), 16)), np.zeros(len(t), np.int32)
+    lib().hc_traj_eval_split(C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(v4), _p(q4), _p(pairs),
+                             len(t), _p(t), _p(out), _p(st))
+    return out, st

@@ -1,0 +1,214 @@
+"""The reference's Python surface on top of the CUDA path: restated versions of the reference's own tests
+(python/tests/test_measurements.py, trajectories/test_general.py, test_estimator.py) -- all need the GPU."""
+import numpy as np
+import pytest
+
+import fixtures_ref as fx
+import kontiki_b200 as kontiki
+from kontiki_b200 import sfm
+from kontiki_b200.measurements import AccelerometerMeasurement, GyroscopeMeasurement, StaticRsCameraMeasurement
+from kontiki_b200.sensors import BasicImu, PinholeCamera
+from kontiki_b200.trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory
+
+pytestmark = pytest.mark.gpu
+
+
+def se3_fixture():
+    traj = UniformSE3SplineTrajectory(fx.SE3_DT, fx.SE3_T0)
+    for cp in fx.SE3_KNOTS:
+        T = np.eye(4)
+        T[:3, :3] = fx.rot_xyzw(cp[:4])
+        T[:3, 3] = cp[4:7]
+        traj.append_knot(T)
+    return traj
+
+
+def split_fixture():
+    traj = SplitTrajectory(fx.R3_DT, fx.SO3_DT, fx.R3_T0, fx.SO3_T0)
+    for cp in fx.R3_KNOTS:
+        traj.R3_spline.append_knot(cp)
+    for q in fx.SO3_KNOTS:
+        traj.SO3_spline.append_knot(fx.xyzw_to_wxyz(q))
+    return traj
+
+
+def smooth_se3(n=60, dt=0.1):
+    from kontiki_b200 import synthetic as syn
+    traj = UniformSE3SplineTrajectory(dt, 0.0)
+    traj._cp = syn.smooth_se3_knots(n, dt)
+    return traj
+
+
+@pytest.mark.parametrize("make", [se3_fixture, split_fixture])
+def test_velocity_and_angular_velocity_numerical(make):
+    """trajectories/test_general.py:155-161, 177-189."""
+    traj = make()
+    for t in np.linspace(traj.min_time + 0.05, traj.max_time - 0.05, 7):
+        h = 1e-6
+        v_num = (traj.position(t + h) - traj.position(t - h)) / (2 * h)
+        assert np.allclose(traj.velocity(t), v_num, atol=1e-5)
+        q = fx.wxyz_to_xyzw(traj.orientation(t))
+        dq = (fx.wxyz_to_xyzw(traj.orientation(t + h)) - fx.wxyz_to_xyzw(traj.orientation(t - h))) / (2 * h)
+        w_num = 2 * fx.qmul_xyzw(dq, fx.qconj_xyzw(q))
+        assert np.allclose(traj.angular_velocity(t), w_num[:3], atol=1e-4)
+
+
+def test_world_frame_round_trip_and_convention():
+    """trajectories/test_general.py:133-152: x_w = q x_b + p."""
+    traj = se3_fixture()
+    t = traj.min_time + 1.3
+    X = np.array([0.3, -1.2, 2.0])
+    R = fx.quat_to_rotation_matrix(traj.orientation(t))
+    assert np.allclose(traj.to_world(X, t), R @ X + traj.position(t), atol=1e-12)
+    assert np.allclose(traj.from_world(traj.to_world(X, t), t), X, atol=1e-12)
+
+
+def test_spline_container_api_and_errors():
+    """spline_helpers.h:26-48; std::range_error / std::domain_error -> ValueError (test_spline_trajectories.py:151-155,227-253)."""
+    traj = UniformR3SplineTrajectory(0.5, 1.0)
+    with pytest.raises(ValueError):
+        traj.min_time                       # fewer than 4 knots
+    traj.extend_to(3.0, np.zeros(3))
+    assert len(traj) >= 4 and traj.max_time >= 3.0
+    traj[1] = [1, 2, 3]
+    assert np.array_equal(traj[1], [1, 2, 3]) and np.array_equal(traj[-len(traj) + 1], [1, 2, 3])
+    with pytest.raises(IndexError):
+        traj[len(traj)]
+    so3 = UniformSO3SplineTrajectory()
+    with pytest.raises(ValueError):
+        so3.append_knot([1, 1, 0, 0])       # not unit
+    se3 = UniformSE3SplineTrajectory()
+    bad = np.eye(4); bad[0, 0] = 2
+    with pytest.raises(ValueError):
+        se3.append_knot(bad)
+    c = se3_fixture()
+    d = c.clone()
+    d[0] = np.eye(4)
+    assert not np.allclose(c[0], d[0])      # clone independence (test_general.py:198-226)
+    with pytest.raises(ValueError):
+        c.position(c.max_time + 1.0)        # out of range
+
+
+@pytest.mark.parametrize("make", [se3_fixture, split_fixture])
+def test_imu_measurements(make):
+    """test_measurements.py:108-153 (gyro/accel body-frame identities), :73-89 (weight linearity)."""
+    traj = make()
+    imu = BasicImu()
+    rng = np.random.default_rng(0)
+    for t in np.linspace(traj.min_time + 0.05, traj.max_time - 0.05, 5):
+        R = fx.quat_to_rotation_matrix(traj.orientation(t))
+        g = GyroscopeMeasurement(imu, t, rng.uniform(-1, 1, 3))
+        assert np.allclose(g.measure(traj), R.T @ traj.angular_velocity(t), atol=1e-10)
+        a = AccelerometerMeasurement(imu, t, rng.uniform(-1, 1, 3))
+        assert np.allclose(a.measure(traj), R.T @ (traj.acceleration(t) - np.array([0, 0, 9.80665])), atol=1e-9)
+        e1 = GyroscopeMeasurement(imu, t, g.w, 1.0).error(traj)
+        e2 = GyroscopeMeasurement(imu, t, g.w, 4.0).error(traj)
+        assert np.array_equal(e2, 4.0 * e1)
+        assert np.allclose(e1, g.w - g.measure(traj), atol=1e-12)
+
+
+def _small_sfm(traj, camera, n_lm=8, n_views=6, seed=3):
+    from kontiki_b200 import synthetic as syn
+    s = syn.make_static_rs(traj.control_points, traj.dt, n_lm, obs_per_landmark=n_views - 1, t0=traj.t0, seed=seed, noise_px=0.0, rows=camera.rows,
+                           cols=camera.cols, readout=camera.readout, K=camera.camera_matrix)
+    views, landmarks = {}, []
+    for lm in range(n_lm):
+        L = sfm.Landmark()
+        sel = np.nonzero(s["lm_idx"] == lm)[0]
+        t_ref = s["ref_t0"][sel[0]]
+        vr = views.setdefault(t_ref, sfm.View(len(views), t_ref))
+        L.reference = vr.create_observation(L, s["ref_uv"][sel[0]])
+        L.inverse_depth = s["rho"][lm]
+        for i in sel:
+            v = views.setdefault(s["obs_t0"][i], sfm.View(len(views), s["obs_t0"][i]))
+            v.create_observation(L, s["obs_uv"][i])
+        landmarks.append(L)
+    return landmarks
+
+
+def test_static_rs_projection_consistency_and_sfm_graph():
+    """test_measurements.py:16-32: project(traj) ~ obs.uv on RS-consistent structure; pysfm surface."""
+    traj = smooth_se3()
+    cam = PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    lms = _small_sfm(traj, cam)
+    n = 0
+    for L in lms:
+        assert L.reference.is_reference and len(L.observations) == 6
+        for obs in L.observations:
+            if obs.is_reference:
+                continue
+            m = StaticRsCameraMeasurement(cam, obs)
+            assert np.abs(m.project(traj) - obs.uv).max() < 0.5          # 3 fixed-point iterations in the generator
+            assert np.allclose(m.error(traj), obs.uv - m.project(traj), atol=1e-9)
+            n += 1
+    assert n == 40
+    with pytest.raises(RuntimeError):
+        sfm.Landmark().reference
+
+
+def test_estimator_solve_gyro_c1_like():
+    """BASELINE.json configs[0] in miniature: gyroscope-only solve() recovers a perturbed trajectory's angular rates."""
+    from kontiki_b200 import synthetic as syn
+    dt, n = 0.1, 40
+    truth = UniformSE3SplineTrajectory(dt, 0.0)
+    truth._cp = syn.smooth_se3_knots(n, dt, noise=0.0)
+    imu = BasicImu()
+    rng = np.random.default_rng(1)
+    times = rng.uniform(truth.min_time, truth.max_time - 1e-6, 400)
+    est_traj = truth.clone()
+    est_traj._cp = syn.smooth_se3_knots(n, dt, seed=7, noise=2e-2)     # perturbed start
+    est = kontiki.TrajectoryEstimator(est_traj)
+    ms = [GyroscopeMeasurement(imu, t, GyroscopeMeasurement(imu, t, np.zeros(3)).measure(truth)) for t in times[:60]]
+    p, knots = kontiki.measurements._problem_for(truth)          # batched generation of the rest (one GPU call)
+    g = p.add_gyroscope(imu._c_sensor(), times, np.zeros((len(times), 3)))
+    w_true = -p.evaluate(knots, None, 1)[g]["r"]
+    ms = [GyroscopeMeasurement(imu, t, w) for t, w in zip(times, w_true)]
+    for m in ms:
+        est.add_measurement(m)
+    seen = []
+    est.add_callback(lambda it: seen.append(it.iteration))
+    summary = est.solve(max_iterations=30, progress=False)
+    assert summary.num_parameters > 0 and summary.num_parameters_reduced == 7 * n
+    assert summary.final_cost < 1e-12 * max(1.0, summary.initial_cost) or summary.final_cost < 1e-16
+    assert summary.IsSolutionUsable() and len(seen) >= 1
+    assert "Final cost" in summary.FullReport()
+    # locked trajectory: nothing to optimise (test_estimator.py:55-75)
+    est_traj.locked = True
+    est2 = kontiki.TrajectoryEstimator(est_traj)
+    for m in ms[:10]:
+        est2.add_measurement(m)
+    assert est2.solve(progress=False).num_parameters_reduced == 0
+    with pytest.raises(ValueError):
+        est.add_measurement(GyroscopeMeasurement(imu, truth.max_time + 1.0, np.zeros(3)))
+
+
+def test_estimator_solve_camera_reduces_cost():
+    """test_estimator.py:48-52 ("solve_camera_nocrash") + the cost must go down from a perturbed start."""
+    traj = smooth_se3(n=40, dt=0.1)
+    cam = PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    lms = _small_sfm(traj, cam, n_lm=30, n_views=6, seed=5)
+    rng = np.random.default_rng(2)
+    for L in lms:
+        L.inverse_depth *= 1.0 + 0.1 * rng.normal()
+    est = kontiki.TrajectoryEstimator(traj)
+    for L in lms:
+        for obs in L.observations:
+            if not obs.is_reference:
+                est.add_measurement(StaticRsCameraMeasurement(cam, obs))
+    traj.locked = True              # structure-only refinement: optimise the inverse depths
+    summary = est.solve(max_iterations=20, progress=False)
+    assert summary.num_parameters > 0
+    assert summary.final_cost < 0.05 * summary.initial_cost
+    assert all(L.inverse_depth >= 0 for L in lms)
+
+
+def test_callback_can_stop_the_solver():
+    """test_estimator.py:122-207."""
+    traj = smooth_se3(n=30)
+    imu = BasicImu()
+    est = kontiki.TrajectoryEstimator(traj)
+    for t in np.linspace(traj.min_time, traj.max_time - 1e-3, 50):
+        est.add_measurement(GyroscopeMeasurement(imu, t, np.array([0.3, 0.1, -0.2])))
+    est.add_callback(lambda it: kontiki.CallbackReturnType.TerminateSuccessfully)
+    s = est.solve(progress=False)
+    assert s.termination_type is kontiki.TerminationType.UserSuccess and len(s.iterations) == 2
