@@ -49,8 +49,14 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 constexpr int kThreads = KTK_THREADS;            // measurement rows per CTA (one per thread), IMU and landmark kernels
 constexpr int kCamThreads = KTK_CAM_THREADS;     // ... static-RS observation kernel
 constexpr int kImuRow = 84, kImuRowStride = 86;     // doubles; stride keeps rows 16-B aligned and off the same banks
-constexpr int kCamRow = 114, kCamRowStride = 114;
-constexpr int kCamWarpSmem = 32 * kCamRowStride;     // doubles of shared memory per warp: 32 row buffers
+constexpr int kCamRow = 114;                          // packed camera row in global memory: 112 knot-block doubles + d r/d rho (2)
+#ifndef KTK_CAM_STRIDE
+#define KTK_CAM_STRIDE 114
+#endif
+// ... of which 112 are staged in shared memory.  The row stride decides how many warps of rows fit an SM: 112 -> 8 warps
+// but only 4 KB of L1 left for the pair table (measured 0.40 ms); 114 -> 7 warps and 24 KB of L1 (0.27 ms).
+constexpr int kCamStage = 112, kCamRowStride = KTK_CAM_STRIDE;
+constexpr int kCamWarpSmem = 32 * kCamRowStride;      // doubles of shared memory per warp: 32 row buffers
 
 // ---- data movement helpers ---------------------------------------------------------------------------------------
 // One TMA bulk store shared -> global (issued by ONE lane for a whole warp tile; UBLKCP is a uniform-datapath
@@ -68,20 +74,55 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Warp-cooperative scatter of the warp's 32 staged rows (ROW doubles each, STRIDE apart in shared memory) to their
-// rows in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store instruction
-// writes one contiguous run.  dst_row < 0 skips a row (ragged tail).
-template <int ROW, int STRIDE>
+// Warp-cooperative scatter of the warp's 32 staged rows (STAGE doubles each, STRIDE apart in shared memory) to their
+// rows (GROW doubles apart) in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store
+// instruction writes one contiguous run.  dst_row < 0 skips a row (ragged tail / nothing to write).
+template <int STAGE, int STRIDE, int GROW>
 __device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, long long dst_row, int lane) {
-  constexpr int kChunks = ROW / 2;     // 16-byte chunks per row
-#pragma unroll 4
-  for (int rr = 0; rr < 32; ++rr) {
-    const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
-    if (d < 0) continue;
-    const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
-    double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * ROW);
-#pragma unroll
-    for (int c = lane; c < kChunks; c += 32) dst[c] = src[c];
+  constexpr int kChunks = STAGE / 2;     // 16-byte chunks per row
+  static_assert(kChunks <= 64, "at most two passes of 32 lanes");
+  const bool full = __all_sync(0xffffffffu, dst_row >= 0);
+  if (full) {
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
+      const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
+      double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * GROW);
+      if (kChunks >= 32 || lane < kChunks) dst[lane] = src[lane];
+      if (kChunks > 32 && lane < kChunks - 32) dst[32 + lane] = src[32 + lane];
+    }
+  } else {
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
+      if (d < 0) continue;
+      const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
+      double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * GROW);
+      for (int c = lane; c < kChunks; c += 32) dst[c] = src[c];
+    }
+  }
+}
+// ... and the gather of 32 records (REC doubles each) from global memory into the row buffers at offset OFF (LDGSTS).
+template <int REC, int STRIDE, int OFF>
+__device__ __forceinline__ void warp_gather_records(double* wbase, const double* recs, int ridx, int lane) {
+  constexpr int kChunks = REC / 2;
+  const bool full = __all_sync(0xffffffffu, ridx >= 0);
+  if (full) {
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) {
+      const int ri = __shfl_sync(0xffffffffu, ridx, rr);
+      const double2* src = reinterpret_cast<const double2*>(recs + (size_t)ri * REC);
+      double2* dst = reinterpret_cast<double2*>(wbase + rr * STRIDE + OFF);
+      if (kChunks >= 32 || lane < kChunks) cp_async16(dst + lane, src + lane);
+      if (kChunks > 32 && lane < kChunks - 32) cp_async16(dst + 32 + lane, src + 32 + lane);
+    }
+  } else {
+    for (int rr = 0; rr < 32; ++rr) {
+      const int ri = __shfl_sync(0xffffffffu, ridx, rr);
+      if (ri < 0) continue;
+      const double2* src = reinterpret_cast<const double2*>(recs + (size_t)ri * REC);
+      double2* dst = reinterpret_cast<double2*>(wbase + rr * STRIDE + OFF);
+      for (int c = lane; c < kChunks; c += 32) cp_async16(dst + c, src + c);
+    }
   }
 }
 
@@ -142,7 +183,7 @@ __global__ void __launch_bounds__(kThreads) k_imu(const ImuArgs a) {
     if (a.i0) a.i0[dst] = i0;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride>(wbase, a.J, (long long)cur.perm, lane);
+  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, (long long)cur.perm, lane);
 }
 
 struct RefArgs {
@@ -208,15 +249,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   const CamIn cur = cam_load(a, tile * 32 + lane);
   // gather the 32 landmark records of this tile into the row buffers (cooperative 16-B LDGSTS: every instruction moves
   // one contiguous 512-B run), in flight during the observation-pose evaluation below
-#pragma unroll 4
-  for (int rr = 0; rr < 32; ++rr) {
-    const int ridx = __shfl_sync(0xffffffffu, cur.ridx, rr);
-    if (ridx < 0) continue;
-    const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ridx * kRefStride);
-    double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRowStride + kRefInRow);
-#pragma unroll
-    for (int c = lane; c < kRefStride / 2; c += 32) cp_async16(dst + c, src + c);
-  }
+  warp_gather_records<kRefStride, kCamRowStride, kRefInRow>(wbase, a.recs, cur.ridx, lane);
   const double ouv[2] = {cur.u, cur.v};
   ObsForward f; f.status = kStatusRange; f.io = -1;
   if (cur.perm >= 0 && cur.ridx >= 0) {
@@ -228,19 +261,21 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   if (cur.perm >= 0) {
     double r[2];
     int ir = -1, io = -1;
-    const int st = static_rs_row_finish(a.cam, a.knots, a.pairs, f, row + kRefInRow, ouv, cur.w, cur.huber, r, row, &ir, &io);
+    double jrho[2];
+    const int st = static_rs_row_finish(a.cam, a.knots, a.pairs, f, row + kRefInRow, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io);
     if (st != 0) {
       atomicMin(a.err, st);
-      r[0] = r[1] = nan(""); ir = io = -1;
-      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+      r[0] = r[1] = jrho[0] = jrho[1] = nan(""); ir = io = -1;
+      for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
     }
     const size_t dst = (size_t)cur.perm;
+    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
     if (a.i0r) a.i0r[dst] = ir;
     if (a.i0o) a.i0o[dst] = io;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)cur.perm, lane);
+  if (wantJ) warp_scatter_rows<kCamStage, kCamRowStride, kCamRow>(wbase, a.J, (long long)cur.perm, lane);
 }
 
 // =====================================================================================================================
@@ -300,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
     if (a.i0_so3) a.i0_so3[dst] = ib;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<ROW, STRIDE>(wbase, a.J, (long long)perm, lane);
+  if (wantJ) warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, (long long)perm, lane);
 }
 
 struct RefSplitArgs {
@@ -354,14 +389,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
   const int i = tile * 32 + lane;
   const int perm = i < a.n ? a.perm[i] : -1;
   const int myridx = i < a.n ? a.ref_idx[i] : -1;
-#pragma unroll 4
-  for (int rr = 0; rr < 32; ++rr) {
-    const int ridx = __shfl_sync(0xffffffffu, myridx, rr);
-    if (ridx < 0) continue;
-    const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ridx * kRefSplitStride);
-    double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRowStride + kRefSplitInRow);
-    if (lane < kRefSplitStride / 2) cp_async16(dst + lane, src + lane);
-  }
+  warp_gather_records<kRefSplitStride, kCamRowStride, kRefSplitInRow>(wbase, a.recs, myridx, lane);
   double ouv[2] = {0.0, 0.0};
   ObsForwardSplit f; f.status = kStatusRange; f.ia = f.ib = -1;
   if (perm >= 0 && myridx >= 0) {
@@ -374,19 +402,21 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
     double r[2];
     int idx[4] = {-1, -1, -1, -1};
     const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
-    const int st = static_rs_row_finish_split(a.cam, a.vecs, a.quats, a.pairs, f, row + kRefSplitInRow, ouv, a.w[i], hub, r, row, idx);
+    double jrho[2];
+    const int st = static_rs_row_finish_split(a.cam, a.vecs, a.quats, a.pairs, f, row + kRefSplitInRow, ouv, a.w[i], hub, r, row, jrho, idx);
     if (st != 0) {
       atomicMin(a.err, st);
-      r[0] = r[1] = nan(""); idx[0] = idx[1] = idx[2] = idx[3] = -1;
-      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+      r[0] = r[1] = jrho[0] = jrho[1] = nan(""); idx[0] = idx[1] = idx[2] = idx[3] = -1;
+      for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
     }
     const size_t dst = (size_t)perm;
+    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamRow, kCamRowStride>(wbase, a.J, (long long)perm, lane);
+  if (wantJ) warp_scatter_rows<kCamStage, kCamRowStride, kCamRow>(wbase, a.J, (long long)perm, lane);
 }
 
 __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,

@@ -530,13 +530,14 @@ KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const doub
 
 // Observation side, per measurement.  `ref` is the landmark record above; its dX/dknots part may alias J (the row
 // buffer) at J + kRefInRow: the reference-window blocks are produced front to back, each read before it is overwritten.
-// J: [ref window: 4 knots][2][7] (56) | [obs window: 4 knots][2][7] (56) | d r / d rho (2)
-constexpr int kRefInRow = 22;      // 22 + 92 = 114 = row length; block k is read at 30 + 21 k and written at 14 k
+// J: [ref window: 4 knots][2][7] (56) | [obs window: 4 knots][2][7] (56);  Jrho: d r / d rho (2) -- the last two doubles of
+// the packed 114-double row, kept separate so that the kernels stage 112 doubles per row (8 warps of rows per SM).
+constexpr int kRefInRow = 20;      // 20 + 92 = 112 = staged row length; block k is read at 28 + 21 k and written at 14 k
 // (the observation pose P is evaluated by the caller first: it does not need the landmark record, so the kernels
 //  overlap the record gather with it)
 KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const double* p1, const double* p2, const double* p3, const Basis& bs,
                              const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J,
-                             int* i0_ref) {
+                             double* Jrho, int* i0_ref) {
   *i0_ref = (int)ref[7];
   const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
   const double rho = ref[6];
@@ -585,7 +586,7 @@ KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const dou
   const double jr0 = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z, jr1 = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
   // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
   pose_backward<2>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, J + 56);
-  J[112] = jr0; J[113] = jr1;
+  Jrho[0] = jr0; Jrho[1] = jr1;
 }
 
 // =================================================================================================================
@@ -681,12 +682,13 @@ KB_HD void static_rs_row_pose(const double* knots, const double* pairs, ObsForwa
 }
 // Part 2: projection, residual, Jacobian row (ref = landmark record, may alias J + kRefInRow).
 KB_HD int static_rs_row_finish(const CameraConst& cam, const double* knots, const double* pairs, const ObsForward& f, const double* ref,
-                               const double* obs_uv, double weight, double huber_c, double* r, double* J, int* i0_ref_out, int* i0_obs_out) {
+                               const double* obs_uv, double weight, double huber_c, double* r, double* J, double* Jrho, int* i0_ref_out,
+                               int* i0_obs_out) {
   if (f.status != 0) return f.status;
   const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
   int ir;
   static_rs_obs_se3(cam, knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, f.P, ref, obs_uv, weight, huber_c,
-                    r, J, &ir);
+                    r, J, Jrho, &ir);
   if (ir < 0) return kStatusRange;                 // the landmark record itself was out of range
   *i0_ref_out = ir; *i0_obs_out = f.io;
   return 0;

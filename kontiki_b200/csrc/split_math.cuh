@@ -233,13 +233,13 @@ KB_HD void landmark_ref_split(const CameraConst& cam, const double* c0, const Ba
   const double radv[3] = {rad.x, rad.y, rad.z};
   so3_backward<3>(q0, p1, bs, (-1.0) * mul_hat(R, Xref), radv, 1.0, rec + kRefSplitDq);
 }
-// Observation side.  J: [ref R3 4x(2x3)] (24) | [ref SO3 4x(2x4)] (32) | [obs R3] (24) | [obs SO3] (32) | d r/d rho (2)
+// Observation side.  J: [ref R3 4x(2x3)] (24) | [ref SO3 4x(2x4)] (32) | [obs R3] (24) | [obs SO3] (32);  Jrho: d r/d rho (2)
 // `ref` may alias J + kRefSplitInRow (the kernels gather the record into the row buffer): its fields are consumed
 // front to back before the positions they occupy are written.
-constexpr int kRefSplitInRow = 50;      // 50 + 64 = 114
+constexpr int kRefSplitInRow = 48;      // 48 + 64 = 112 = staged row length
 KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const BasisR3& br, const double* q0, const double* p1, const Basis& bs,
                                const M3& R, const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J,
-                               int* i0_ref_r3, int* i0_ref_so3) {
+                               double* Jrho, int* i0_ref_r3, int* i0_ref_so3) {
   *i0_ref_r3 = (int)ref[7]; *i0_ref_so3 = (int)ref[8];
   const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
   const double rho = ref[6];
@@ -271,7 +271,7 @@ KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const B
   for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
   const Mr<2> Go = rmul(Jp, Rct);               // d r / d Xobs
   const Mr<2> GX = rmul_nt(Go, R);              // d r / d X
-  // reference SO3 window: GX (2x3) * dX/dq_k (3x4), in place: block k read at 50+16+12k, written at 24+8k
+  // reference SO3 window: GX (2x3) * dX/dq_k (3x4), in place: block k read at 48+16+12k, written at 24+8k
   const double* dq = ref + kRefSplitDq;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -295,7 +295,7 @@ KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const B
   const V3 radx = 2.0 * (Xobs - Xw);
   const double radv[2] = {Go.a[0] * radx.x + Go.a[1] * radx.y + Go.a[2] * radx.z, Go.a[3] * radx.x + Go.a[4] * radx.y + Go.a[5] * radx.z};
   so3_backward<2>(q0, p1, bs, rmul_hat(Go, Xobs), radv, 1.0, J + 80);
-  J[112] = jr0; J[113] = jr1;
+  Jrho[0] = jr0; Jrho[1] = jr1;
 }
 
 // =================================================================================================================
@@ -379,11 +379,12 @@ KB_HD void static_rs_row_forward_split(const SplitConst& sp, const CameraConst& 
   f.R = so3_forward(quats + (size_t)f.ib * kQuatStride, pairs + (size_t)(f.ib + 1) * kSo3PairStride, f.bs);
 }
 KB_HD int static_rs_row_finish_split(const CameraConst& cam, const double* vecs, const double* quats, const double* pairs, const ObsForwardSplit& f,
-                                     const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J, int* idx /*[4]*/) {
+                                     const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J, double* Jrho,
+                                     int* idx /*[4]*/) {
   if (f.status != 0) return f.status;
   int ira, irb;
   static_rs_obs_split(cam, vecs + (size_t)f.ia * kVecStride, f.br, quats + (size_t)f.ib * kQuatStride, pairs + (size_t)(f.ib + 1) * kSo3PairStride,
-                      f.bs, f.R, ref, obs_uv, weight, huber_c, r, J, &ira, &irb);
+                      f.bs, f.R, ref, obs_uv, weight, huber_c, r, J, Jrho, &ira, &irb);
   if (ira < 0) return kStatusRange;
   idx[0] = ira; idx[1] = f.ia; idx[2] = irb; idx[3] = f.ib;      // ref R3, obs R3, ref SO3, obs SO3
   return 0;

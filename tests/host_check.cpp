@@ -58,7 +58,7 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     ObsForward f;
     static_rs_row_locate(sp, cam, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
     static_rs_row_pose(knots8, pairs, f);
-    status[i] = static_rs_row_finish(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, i0_ref + i, i0_obs + i);
+    status[i] = static_rs_row_finish(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, i0_ref + i, i0_obs + i);
   }
 }
 
@@ -111,7 +111,7 @@ void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
     if (status[i] != 0) continue;
     ObsForwardSplit f;
     static_rs_row_forward_split(sp, cam, quats, pairs, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
-    status[i] = static_rs_row_finish_split(cam, vecs4, quats, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, idx + 4 * i);
+    status[i] = static_rs_row_finish_split(cam, vecs4, quats, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, idx + 4 * i);
   }
 }
 
