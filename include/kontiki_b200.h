@@ -146,6 +146,27 @@ int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const doub
 /* Number of kernel launches ktk_evaluate_device enqueued since the problem was created. */
 int64_t ktk_launch_count(const ktk_problem* p);
 
+/* Gauss-Newton contraction, matrix-free, on the packed rows a ktk_evaluate_device call left in device memory
+ * (d_outs = the same array of device pointers, with J and every index array non-NULL).  The reference leaves this to
+ * Ceres (SPARSE_SCHUR requested at trajectory_estimator.h:40); here the normal equations are applied, not formed.
+ * Parameter vectors are AMBIENT and laid out [knots as in ktk_evaluate | rho (n_rho)], length ktk_num_parameters():
+ *   ktk_j_apply      : d_u[g][row*nres + r]  = (J v)           for every group g  (nres = 3 IMU, 2 camera)
+ *   ktk_jt_apply     : d_y                  += J^T u            (d_y is NOT cleared; fp64 atomics, order not fixed)
+ *   ktk_jtj_diagonal : d_y                  += squared entries of the packed blocks, column by column (equals diag(J^T J)
+ *                                              except where a camera row's two windows share a knot; the exact diagonal, in
+ *                                              local coordinates, is ktk_jtj_diagonal_local)
+ * All asynchronous on the problem's stream.  With rows sharded over several GPUs, the sum over ranks of d_y is the
+ * full product: one ncclAllReduce of ktk_num_parameters() doubles per product (kontiki_b200/gn.py). */
+int64_t ktk_num_parameters(const ktk_problem* p, int64_t n_rho);
+int ktk_j_apply(ktk_problem* p, const ktk_group_out* d_outs, const double* d_v, double* const* d_u);
+int ktk_jt_apply(ktk_problem* p, const ktk_group_out* d_outs, double* const* d_u, double* d_y);
+int ktk_jtj_diagonal(ktk_problem* p, const ktk_group_out* d_outs, double* d_y);
+/* diag(P^T J^T J P) in LOCAL (tangent) coordinates, laid out [6 per SE3 knot | rho] or [3 per R3 knot | 3 per SO3 knot |
+ * rho]: d_Pa = d Plus/d delta of every SE3 knot (n x 7 x 6, row-major; LocalParameterizationSE3,
+ * uniform_se3_spline_trajectory.h:25-48), d_Pb = the same for SO3 knots (n_so3 x 4 x 3; ceres::EigenQuaternionParameterization,
+ * uniform_so3_spline_trajectory.h:21); NULL where the trajectory has no such spline. */
+int ktk_jtj_diagonal_local(ktk_problem* p, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y);
+
 /* Kernel timing for bench.py's roofline: while on, every kernel launch of a measurement group is bracketed by CUDA
  * events on the problem's stream; ktk_read_profile synchronises, returns the summed device time (ms) and the number
  * of launches of that group's kernel since the last read, and clears the record. */

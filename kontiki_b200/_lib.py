@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local"]
 
 _lib = None
 
@@ -79,6 +79,12 @@ def lib():
         L.ktk_num_knot_doubles.argtypes = [C.c_void_p]
         L.ktk_num_knot_doubles.restype = C.c_int64
         L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
+        L.ktk_num_parameters.argtypes = [C.c_void_p, C.c_int64]
+        L.ktk_num_parameters.restype = C.c_int64
+        L.ktk_j_apply.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ktk_jt_apply.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.POINTER(C.c_void_p), C.c_void_p]
+        L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p]
+        L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -286,6 +292,29 @@ class Problem:
         ms, n = C.c_double(0), C.c_int64(0)
         check(lib().ktk_read_profile(self._h, g, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    # ---- matrix-free Gauss-Newton products on device pointers (see kontiki_b200/gn.py) ----------------------------------
+    def num_parameters(self, n_rho):
+        return lib().ktk_num_parameters(self._h, int(n_rho))
+
+    def _ptr_array(self, ptrs):
+        arr = (C.c_void_p * max(len(ptrs), 1))()
+        for i, q in enumerate(ptrs):
+            arr[i] = None if not q else int(q)
+        return arr
+
+    def j_apply(self, d_outs, d_v, d_u):
+        check(lib().ktk_j_apply(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_v)), self._ptr_array(d_u)))
+
+    def jt_apply(self, d_outs, d_u, d_y):
+        check(lib().ktk_jt_apply(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), self._ptr_array(d_u), C.c_void_p(int(d_y))))
+
+    def jtj_diagonal(self, d_outs, d_y):
+        check(lib().ktk_jtj_diagonal(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_y))))
+
+    def jtj_diagonal_local(self, d_outs, d_Pa, d_Pb, d_y):
+        check(lib().ktk_jtj_diagonal_local(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), None if not d_Pa else C.c_void_p(int(d_Pa)),
+                                           None if not d_Pb else C.c_void_p(int(d_Pb)), C.c_void_p(int(d_y))))
 
     def synchronize(self):
         check(lib().ktk_synchronize(self._h))

@@ -438,6 +438,130 @@ __global__ void k_traj_eval_split(SplitConst sp, const double* __restrict__ vecs
   status[i] = st;
 }
 
+// =====================================================================================================================
+// Gauss-Newton contraction, matrix-free: products with the packed Jacobian rows that an
+// evaluation left in device memory.  Parameter vector (ambient): SE3 [knots 7 n | rho]; split [R3 3 n_r3 | SO3 4 n_so3 | rho].
+//   k_j_apply : u[row] = J[row] . v          (gather, no atomics)
+//   k_jt_apply: y += J[row]^T u[row]          (scatter with fp64 RED; mode 1: y += J[row]^2 elementwise = diag(J^T J))
+// Forming J^T J explicitly would need ~1650 scattered atomics per camera row (the ref x obs cross blocks are unique per
+// row); a product needs 57, so the normal equations are applied, not formed, and solved by PCG (kontiki_b200/gn.py).
+// =====================================================================================================================
+struct RowWindows {            // where the blocks of a packed row live in the parameter vector
+  int nwin;                    // number of 4-knot windows
+  int j_off[4], width[4], col_off[4], slot[4];     // offset in the row, knot width, first column of that spline, index array
+  int nres, row_len, rho_off_in_row;                // residuals per row, doubles per row, offset of d r/d rho (-1: none)
+  long long rho_col0;                               // first column of rho
+};
+struct ApplyArgs {
+  RowWindows w; int n; const double* J; const int* idx[4]; const int* lm;
+  const double* v; double* u; double* y; int mode;
+  // diag(P^T J^T J P) in LOCAL coordinates: P blocks (width x lwidth, row-major) per knot of each window's spline
+  const double* P[4]; int lwidth[4]; long long lcol_off[4]; long long lrho_col0;
+};
+__global__ void k_j_apply(const ApplyArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double* Jr = a.J + (size_t)i * a.w.row_len;
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int w = 0; w < a.w.nwin; ++w) {
+    const int wd = a.w.width[w];
+    const double* vv = a.v + a.w.col_off[w] + (size_t)wd * a.idx[a.w.slot[w]][i];
+    const double* Jw = Jr + a.w.j_off[w];
+    for (int k = 0; k < 4; ++k)
+      for (int r = 0; r < a.w.nres; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < wd; ++c) s += Jw[(k * a.w.nres + r) * wd + c] * vv[k * wd + c];
+        acc[r] += s;
+      }
+  }
+  if (a.w.rho_off_in_row >= 0) {
+    const double vr = a.v[a.w.rho_col0 + a.lm[i]];
+    for (int r = 0; r < a.w.nres; ++r) acc[r] += Jr[a.w.rho_off_in_row + r] * vr;
+  }
+  for (int r = 0; r < a.w.nres; ++r) a.u[(size_t)i * a.w.nres + r] = acc[r];
+}
+// (J P) of one window: t[k][r][c], k = 0..3 knots, r < nres, c < lw
+__device__ __forceinline__ void window_JP(const ApplyArgs& a, int w, const double* Jr, int i, double* t) {
+  const int wd = a.w.width[w], lw = a.lwidth[w];
+  const int k0 = a.idx[a.w.slot[w]][i];
+  const double* Jw = Jr + a.w.j_off[w];
+  for (int k = 0; k < 4; ++k) {
+    const double* Pk = a.P[w] ? a.P[w] + (size_t)(k0 + k) * wd * lw : nullptr;
+    for (int r = 0; r < a.w.nres; ++r)
+      for (int c = 0; c < lw; ++c) {
+        double s = 0.0;
+        if (Pk) for (int m = 0; m < wd; ++m) s += Jw[(k * a.w.nres + r) * wd + m] * Pk[m * lw + c];
+        else s = Jw[(k * a.w.nres + r) * wd + c];
+        t[(k * 3 + r) * 6 + c] = s;
+      }
+  }
+}
+__global__ void k_jtj_diag_local(const ApplyArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double* Jr = a.J + (size_t)i * a.w.row_len;
+  double tA[72], tB[72];
+  // windows come in (reference, observation) pairs on the same spline: w and w + nwin/2 (camera); a knot that is in both
+  // windows is ONE parameter block, its column of J is the sum of the two blocks
+  const int npair = a.w.rho_off_in_row >= 0 ? a.w.nwin / 2 : 0;
+  for (int w = 0; w < (npair ? npair : a.w.nwin); ++w) {
+    const int lw = a.lwidth[w];
+    window_JP(a, w, Jr, i, tA);
+    const int kA = a.idx[a.w.slot[w]][i];
+    int kB = 0x3fffffff;
+    if (npair) { window_JP(a, w + npair, Jr, i, tB); kB = a.idx[a.w.slot[w + npair]][i]; }
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < lw; ++c) {
+        double s = 0.0;
+        const int kb = kA + k - kB;          // position of this knot in the other window
+        for (int r = 0; r < a.w.nres; ++r) {
+          double v = tA[(k * 3 + r) * 6 + c];
+          if (npair && kb >= 0 && kb < 4) v += tB[(kb * 3 + r) * 6 + c];
+          s += v * v;
+        }
+        atomicAdd(a.y + a.lcol_off[w] + (size_t)lw * (kA + k) + c, s);
+      }
+    if (npair)
+      for (int k = 0; k < 4; ++k) {
+        const int ka = kB + k - kA;
+        if (ka >= 0 && ka < 4) continue;     // already counted with window A
+        for (int c = 0; c < lw; ++c) {
+          double s = 0.0;
+          for (int r = 0; r < a.w.nres; ++r) { const double v = tB[(k * 3 + r) * 6 + c]; s += v * v; }
+          atomicAdd(a.y + a.lcol_off[w] + (size_t)lw * (kB + k) + c, s);
+        }
+      }
+  }
+  if (a.w.rho_off_in_row >= 0) {
+    double s = 0.0;
+    for (int r = 0; r < a.w.nres; ++r) { const double j = Jr[a.w.rho_off_in_row + r]; s += j * j; }
+    atomicAdd(a.y + a.lrho_col0 + a.lm[i], s);
+  }
+}
+__global__ void k_jt_apply(const ApplyArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const double* Jr = a.J + (size_t)i * a.w.row_len;
+  double ur[3] = {1.0, 1.0, 1.0};
+  if (a.mode == 0) for (int r = 0; r < a.w.nres; ++r) ur[r] = a.u[(size_t)i * a.w.nres + r];
+  for (int w = 0; w < a.w.nwin; ++w) {
+    const int wd = a.w.width[w];
+    double* yy = a.y + a.w.col_off[w] + (size_t)wd * a.idx[a.w.slot[w]][i];
+    const double* Jw = Jr + a.w.j_off[w];
+    for (int k = 0; k < 4; ++k)
+      for (int c = 0; c < wd; ++c) {
+        double s = 0.0;
+        for (int r = 0; r < a.w.nres; ++r) { const double j = Jw[(k * a.w.nres + r) * wd + c]; s += a.mode == 0 ? j * ur[r] : j * j; }
+        atomicAdd(yy + k * wd + c, s);
+      }
+  }
+  if (a.w.rho_off_in_row >= 0) {
+    double s = 0.0;
+    for (int r = 0; r < a.w.nres; ++r) { const double j = Jr[a.w.rho_off_in_row + r]; s += a.mode == 0 ? j * ur[r] : j * j; }
+    atomicAdd(a.y + a.w.rho_col0 + a.lm[i], s);
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -453,7 +577,7 @@ struct Group {
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
   DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_t0, d_huber;
-  DevBuf<int> d_perm, d_ref_idx;
+  DevBuf<int> d_perm, d_ref_idx, d_lm_caller;
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
   DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
@@ -925,6 +1049,76 @@ int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const doub
   if (*p->h_err == kStatusRuntime) return fail(KTK_ERUNTIME, "logq: Only implemented for unit quaternions (a SO3 knot pair is not unit norm)");
   for (int64_t i = 0; i < n; ++i) if (status[i] == kStatusRange) return fail(KTK_ERANGE, "t is out of range for the spline");
   return KTK_OK;
+}
+
+// ---- matrix-free Gauss-Newton products -------------------------------------------------------------------------------
+static RowWindows row_windows(const ktk_problem* p, const Group& g) {
+  RowWindows w{};
+  const bool split = p->traj == 1;
+  const int n_a = split ? p->spl.n_r3 : p->sp.n_knots, n_b = split ? p->spl.n_so3 : 0;
+  const int colB = split ? 3 * n_a : 0;
+  w.rho_col0 = split ? (long long)3 * n_a + (long long)4 * n_b : (long long)7 * n_a;
+  w.rho_off_in_row = -1;
+  w.nres = g.kind == KTK_STATIC_RS ? 2 : 3;
+  w.row_len = row_doubles(p, g);
+  auto set = [&](int i, int off, int width, int col, int slot) { w.j_off[i] = off; w.width[i] = width; w.col_off[i] = col; w.slot[i] = slot; };
+  if (!split) {
+    if (g.kind == KTK_STATIC_RS) { w.nwin = 2; set(0, 0, 7, 0, 0); set(1, 56, 7, 0, 1); w.rho_off_in_row = 112; }
+    else { w.nwin = 1; set(0, 0, 7, 0, 0); }
+  } else if (g.kind == KTK_STATIC_RS) {
+    w.nwin = 4; set(0, 0, 3, 0, 0); set(1, 24, 4, colB, 2); set(2, 56, 3, 0, 1); set(3, 80, 4, colB, 3); w.rho_off_in_row = 112;
+  } else if (g.kind == KTK_GYROSCOPE) { w.nwin = 1; set(0, 0, 4, colB, 2); }
+  else { w.nwin = 2; set(0, 0, 3, 0, 0); set(1, 36, 4, colB, 2); }
+  return w;
+}
+int64_t ktk_num_parameters(const ktk_problem* p, int64_t n_rho) { return p ? ktk_num_knot_doubles(p) + n_rho : 0; }
+
+// mode 0: u = J v ; mode 1: y += J^T u ; mode 2: y += diag(J^T J) ; mode 3: y_local += diag(P^T J^T J P)
+static int apply_products(ktk_problem* p, int mode, const ktk_group_out* d_outs, const double* d_v, double* const* d_u, double* d_y,
+                          const double* d_Pa = nullptr, const double* d_Pb = nullptr) {
+  if (!p || !d_outs || (mode == 0 && (!d_v || !d_u)) || (mode == 1 && (!d_u || !d_y)) || (mode >= 2 && !d_y)) return fail(KTK_EINVAL, "NULL argument");
+  if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
+  KTK_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    if (g.n == 0) continue;
+    const ktk_group_out& o = d_outs[gi];
+    if (!o.J) return fail(KTK_EINVAL, "the group has no Jacobian rows in device memory");
+    ApplyArgs a{};
+    a.w = row_windows(p, g); a.n = (int)g.n; a.J = o.J;
+    a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d;
+    for (int w = 0; w < a.w.nwin; ++w) if (!a.idx[a.w.slot[w]]) return fail(KTK_EINVAL, "the group's index arrays are missing");
+    if (g.kind == KTK_STATIC_RS) {
+      if (g.d_lm_caller.n != (size_t)g.n) { int st = g.d_lm_caller.upload(g.lm, s); if (st) return st; KTK_CUDA(cudaStreamSynchronize(s)); }
+      a.lm = g.d_lm_caller.p;
+    }
+    a.v = d_v; a.u = d_u ? d_u[gi] : nullptr; a.y = d_y; a.mode = mode == 2 ? 1 : 0;
+    if ((mode == 0 || mode == 1) && !a.u) return fail(KTK_EINVAL, "u is NULL for a non-empty group");
+    const int blocks = (int)((g.n + 127) / 128);
+    if (mode == 3) {
+      const bool split = p->traj == 1;
+      const long long n_a = split ? p->spl.n_r3 : p->sp.n_knots, n_b = split ? p->spl.n_so3 : 0;
+      for (int w = 0; w < a.w.nwin; ++w) {
+        const bool isB = split && a.w.width[w] == 4;
+        a.P[w] = split ? (isB ? d_Pb : nullptr) : d_Pa;            // R3 knots are their own tangent space
+        a.lwidth[w] = split ? 3 : 6;
+        a.lcol_off[w] = isB ? 3 * n_a : 0;
+        if ((!split || isB) && !a.P[w]) return fail(KTK_EINVAL, "tangent basis P is NULL");
+      }
+      a.lrho_col0 = split ? 3 * n_a + 3 * n_b : 6 * n_a;
+      k_jtj_diag_local<<<blocks, 128, 0, s>>>(a);
+    } else if (mode == 0) k_j_apply<<<blocks, 128, 0, s>>>(a); else k_jt_apply<<<blocks, 128, 0, s>>>(a);
+    p->launches += 1;
+  }
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+int ktk_j_apply(ktk_problem* p, const ktk_group_out* d_outs, const double* d_v, double* const* d_u) { return apply_products(p, 0, d_outs, d_v, d_u, nullptr); }
+int ktk_jt_apply(ktk_problem* p, const ktk_group_out* d_outs, double* const* d_u, double* d_y) { return apply_products(p, 1, d_outs, nullptr, d_u, d_y); }
+int ktk_jtj_diagonal(ktk_problem* p, const ktk_group_out* d_outs, double* d_y) { return apply_products(p, 2, d_outs, nullptr, nullptr, d_y); }
+int ktk_jtj_diagonal_local(ktk_problem* p, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y) {
+  return apply_products(p, 3, d_outs, nullptr, nullptr, d_y, d_Pa, d_Pb);
 }
 
 int ktk_set_profiling(ktk_problem* p, int32_t on) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->profiling = on != 0; return KTK_OK; }

@@ -336,8 +336,18 @@ class TrajectoryEstimator:
         """1/2 sum rho(|r|^2); with the corrector applied |r_corrected|^2 == rho(s) for Huber."""
         return 0.5 * sum(float((outs[g["g"]]["r"] ** 2).sum()) for g in groups)
 
-    def solve(self, max_iterations=50, progress=True, num_threads=-1):
-        """Levenberg-Marquardt on the GPU-evaluated residuals/Jacobians; returns a Summary (py_ceres.cc:15-58 fields)."""
+    def solve(self, max_iterations=50, progress=True, num_threads=-1, linear_solver="auto"):
+        """Levenberg-Marquardt on the GPU-evaluated residuals/Jacobians; returns a Summary (py_ceres.cc:15-58 fields).
+
+        linear_solver: "host_cholesky" (rows copied to the host, sparse Cholesky with scipy -- the reference's split: Ceres
+        does its linear algebra on the host too), "device_pcg" (rows stay on the GPU, matrix-free PCG, kontiki_b200/gn.py;
+        multi-GPU aware), or "auto" (device_pcg above 20 000 measurements)."""
+        if linear_solver == "auto":
+            linear_solver = "device_pcg" if len(self._measurements) > 20000 else "host_cholesky"
+        if linear_solver == "device_pcg":
+            return self._solve_device(max_iterations, progress)
+        if linear_solver != "host_cholesky":
+            raise ValueError("linear_solver must be 'auto', 'host_cholesky' or 'device_pcg'")
         t_start = time.perf_counter()
         s = Summary()
         self._build()
@@ -438,6 +448,139 @@ class TrajectoryEstimator:
         s.final_cost = cost
         s.termination_type = term
         s.total_time_in_seconds = s.minimizer_time_in_seconds = time.perf_counter() - t_start
+        return s
+
+    # ---- device-side normal equations (kontiki_b200/gn.py) ------------------------------------------------------------------
+    def _solve_device(self, max_iterations, progress, pcg_tol=1e-6, pcg_max_iter=300):
+        import torch
+        from . import gn
+        t_start = time.perf_counter()
+        s = Summary()
+        self._build()
+        tr = self._trajectory
+        split = isinstance(tr, SplitTrajectory)
+        spl_a = tr.R3_spline if split else tr
+        spl_b = tr.SO3_spline if split else None
+        n_a, n_b, n_rho = len(spl_a), (len(spl_b) if split else 0), len(self._landmarks)
+        ne = gn.DeviceNormalEquations(self._problem, split, n_a, n_b, n_rho, self._device)
+        free = np.ones(ne.n_loc)
+        da = 3 if split else 6
+        if spl_a.locked:
+            free[:da * n_a] = 0
+        if split and spl_b.locked:
+            free[da * n_a:da * n_a + 3 * n_b] = 0
+        free[da * n_a + 3 * n_b:] = [0.0 if L.locked else 1.0 for L in self._landmarks]
+        ne.free = torch.from_numpy(free).to(ne.dev)
+        n_free = int(free.sum())
+        layout, ncols = self._columns()
+        s.num_parameters = ne.n_amb + 8 * len(self._groups)
+        s.num_parameters_reduced = ncols + self._ambient_free(layout)
+        s.num_effective_parameters_reduced = n_free
+        s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)
+        s.num_residuals = s.num_residuals_reduced = sum(self._problem.group_size(g["g"]) * (2 if g["kind"] == "cam" else 3) for g in self._groups)
+
+        def load_point():
+            if split:
+                kf = np.concatenate([spl_a.control_points.reshape(-1), spl_b.control_points.reshape(-1)])
+                ne.set_point(kf, np.array([L.inverse_depth for L in self._landmarks]), None, _quat_plus_jacobian(spl_b.control_points))
+            else:
+                ne.set_point(spl_a.control_points.reshape(-1), np.array([L.inverse_depth for L in self._landmarks]), _se3_plus_jacobian(spl_a.control_points), None)
+
+        def apply(delta):
+            d = delta.cpu().numpy()
+            if not spl_a.locked:
+                blk = d[:da * n_a].reshape(n_a, da)
+                spl_a.control_points[:] = (spl_a.control_points + blk) if split else _se3_plus(spl_a.control_points, blk)
+            if split and not spl_b.locked:
+                spl_b.control_points[:] = _quat_plus(spl_b.control_points, d[da * n_a:da * n_a + 3 * n_b].reshape(n_b, 3))
+            for L, dv in zip(self._landmarks, d[da * n_a + 3 * n_b:]):
+                if not L.locked:
+                    L.inverse_depth = max(0.0, L.inverse_depth + dv)
+
+        t0 = time.perf_counter()
+        load_point()
+        cost = ne.evaluate()
+        s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
+        s.initial_cost = cost
+        radius, nu, term = 1e4, 2.0, TerminationType.NoConvergence
+        if progress:
+            print("iter      cost      cost_change  |gradient|   |step|    tr_ratio  tr_radius  pcg")
+        if n_free == 0:
+            s.final_cost, s.termination_type, s.message = cost, TerminationType.Convergence, "no free parameters"
+            return s
+        for it in range(max_iterations + 1):
+            t_it = time.perf_counter()
+            g = ne.gradient()
+            gmax = float(g.abs().max())
+            if it == 0:
+                s.iterations.append(IterationSummary(iteration=0, cost=cost, gradient_max_norm=gmax, gradient_norm=float(torch.linalg.vector_norm(g)), trust_region_radius=radius))
+                if progress:
+                    print(f"{0:4d}  {cost:12.6e}  {0.0:10.2e}  {gmax:10.2e}  {0.0:9.2e}  {0.0:9.2e}  {radius:9.2e}")
+            if gmax < 1e-10:
+                term, s.message = TerminationType.Convergence, "Gradient tolerance reached"
+                break
+            if it == max_iterations:
+                s.message = "Maximum number of iterations reached"
+                break
+            D = ne.hessian_diagonal()
+            damp = torch.clamp(D, 1e-6, 1e32) / radius * ne.free
+            Minv = ne.free / torch.clamp(D + damp, min=1e-300)
+            t_ls = time.perf_counter()
+            delta, n_cg = gn.pcg(lambda v: ne.hessian_apply(v) + damp * v, -g, Minv, tol=pcg_tol, max_iter=pcg_max_iter)
+            s.linear_solver_time_in_seconds += time.perf_counter() - t_ls
+            Hd = ne.hessian_apply(delta)
+            model = -float(torch.dot(delta, g + 0.5 * Hd))
+            snap = self._snapshot()
+            apply(delta)
+            t0 = time.perf_counter()
+            try:
+                load_point()
+                cost_new = ne.evaluate()
+            except ValueError:
+                cost_new = np.inf
+            s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
+            rho_ratio = (cost - cost_new) / model if model > 0 else -1.0
+            step_norm = float(torch.linalg.vector_norm(delta))
+            ok = np.isfinite(cost_new) and rho_ratio > 1e-3
+            isum = IterationSummary(iteration=it + 1, cost=cost_new if ok else cost, cost_change=cost - cost_new, step_norm=step_norm, relative_decrease=rho_ratio,
+                                    trust_region_radius=radius, step_is_successful=bool(ok), gradient_max_norm=gmax, linear_solver_iterations=n_cg,
+                                    iteration_time_in_seconds=time.perf_counter() - t_it, cumulative_time_in_seconds=time.perf_counter() - t_start)
+            if ok:
+                rel = (cost - cost_new) / max(cost, 1e-300)
+                cost = cost_new
+                radius = radius / max(1.0 / 3.0, 1.0 - (2.0 * rho_ratio - 1.0) ** 3)
+                nu = 2.0
+                s.num_successful_steps += 1
+            else:
+                self._restore(snap)
+                load_point()
+                ne.evaluate()
+                radius, nu = radius / nu, 2 * nu
+                s.num_unsuccessful_steps += 1
+                rel = 1.0
+            s.iterations.append(isum)
+            if progress:
+                print(f"{it + 1:4d}  {isum.cost:12.6e}  {isum.cost_change:10.2e}  {gmax:10.2e}  {step_norm:9.2e}  {rho_ratio:9.2e}  {radius:9.2e}  {n_cg}")
+            stop = None
+            for cb, _ in self._callbacks:
+                res = cb(isum)
+                if res is not None and res is not CallbackReturnType.Continue:
+                    stop = res
+            if stop is CallbackReturnType.Abort:
+                term, s.message = TerminationType.UserFailure, "User callback returned SOLVER_ABORT"
+                break
+            if stop is CallbackReturnType.TerminateSuccessfully:
+                term, s.message = TerminationType.UserSuccess, "User callback returned SOLVER_TERMINATE_SUCCESSFULLY"
+                break
+            if ok and rel < 1e-6:
+                term, s.message = TerminationType.Convergence, "Function tolerance reached"
+                break
+            if radius < 1e-32:
+                term, s.message = TerminationType.Failure, "Trust region radius collapsed"
+                break
+        s.final_cost, s.termination_type = cost, term
+        s.total_time_in_seconds = s.minimizer_time_in_seconds = time.perf_counter() - t_start
+        self._problem.set_stream(0)
         return s
 
     def _ambient_free(self, layout):

@@ -212,3 +212,88 @@ def test_callback_can_stop_the_solver():
     est.add_callback(lambda it: kontiki.CallbackReturnType.TerminateSuccessfully)
     s = est.solve(progress=False)
     assert s.termination_type is kontiki.TerminationType.UserSuccess and len(s.iterations) == 2
+
+
+def _vi_problem(split, seed=11):
+    """A small visual-inertial problem (gyro + accel + static RS) with a perturbed start."""
+    from kontiki_b200 import synthetic as syn
+    dt, n = 0.1, 40
+    k_true = syn.smooth_se3_knots(n, dt, noise=0.0)
+    k_start = syn.smooth_se3_knots(n, dt, seed=seed, noise=5e-3)
+
+    def make(k):
+        if not split:
+            t = UniformSE3SplineTrajectory(dt, 0.0)
+            t._cp = k.copy()
+            return t
+        t = SplitTrajectory(dt, dt, 0.0, 0.0)
+        t.R3_spline._cp, t.SO3_spline._cp = k[:, 4:7].copy(), k[:, :4].copy()
+        return t
+    truth, start = make(k_true), make(k_start)
+    imu, cam = BasicImu(), PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    rng = np.random.default_rng(seed)
+    times = rng.uniform(truth.min_time, truth.max_time - 1e-6, 300)
+    p, knots = kontiki.measurements._problem_for(truth)
+    gg = p.add_gyroscope(imu._c_sensor(), times, np.zeros((300, 3)))
+    ga = p.add_accelerometer(imu._c_sensor(), times, np.zeros((300, 3)))
+    o = p.evaluate(knots, None, 1)
+    ms = [GyroscopeMeasurement(imu, t, w) for t, w in zip(times, -o[gg]["r"])] + [AccelerometerMeasurement(imu, t, a) for t, a in zip(times, -o[ga]["r"])]
+    se3_for_sfm = UniformSE3SplineTrajectory(dt, 0.0)
+    se3_for_sfm._cp = k_true.copy()
+    lms = _small_sfm(se3_for_sfm, cam, n_lm=40, n_views=6, seed=seed)
+    for L in lms:
+        L.inverse_depth *= 1.0 + 0.05 * rng.normal()
+        ms += [StaticRsCameraMeasurement(cam, obs) for obs in L.observations if not obs.is_reference]
+    return start, ms, lms
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_device_normal_equation_products_match_host_sparse(split):
+    """k_j_apply / k_jt_apply / k_jtj_diag_local against scipy products with the host-assembled local Jacobian."""
+    import torch
+    from kontiki_b200 import gn
+    from kontiki_b200.estimator import _quat_plus_jacobian, _se3_plus_jacobian
+    start, ms, lms = _vi_problem(split)
+    est = kontiki.TrajectoryEstimator(start)
+    for m in ms:
+        est.add_measurement(m)
+    outs = est.evaluate(jacobians=True)
+    r, J, layout = est._sparse_system(outs)
+    if split:
+        a, b = start.R3_spline, start.SO3_spline
+        kf = np.concatenate([a.control_points.reshape(-1), b.control_points.reshape(-1)])
+        Pa, Pb, n_a, n_b = None, _quat_plus_jacobian(b.control_points), len(a), len(b)
+    else:
+        kf, Pa, Pb, n_a, n_b = start.control_points.reshape(-1), _se3_plus_jacobian(start.control_points), None, len(start), 0
+    ne = gn.DeviceNormalEquations(est._problem, split, n_a, n_b, len(lms), 0)
+    ne.set_point(kf, np.array([L.inverse_depth for L in lms]), Pa, Pb)
+    cost = ne.evaluate()
+    assert np.isclose(cost, 0.5 * float(r @ r), rtol=1e-12)
+    g = ne.gradient().cpu().numpy()
+    g_ref = J.T @ r
+    assert np.abs(g - g_ref).max() <= 1e-9 * np.abs(g_ref).max()
+    v = np.random.default_rng(0).normal(size=J.shape[1])
+    Hv = ne.hessian_apply(torch.from_numpy(v).to(ne.dev)).cpu().numpy()
+    Hv_ref = J.T @ (J @ v)
+    assert np.abs(Hv - Hv_ref).max() <= 1e-9 * np.abs(Hv_ref).max()
+    d = ne.hessian_diagonal().cpu().numpy()
+    d_ref = np.asarray(J.multiply(J).sum(0)).reshape(-1)
+    assert np.abs(d - d_ref).max() <= 1e-9 * np.abs(d_ref).max()
+    est._problem.set_stream(0)
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_device_pcg_solve_converges_like_host_cholesky(split):
+    """The matrix-free device solver (inexact PCG steps) and the host sparse-Cholesky solver reach the same optimum."""
+    results = []
+    for solver in ("host_cholesky", "device_pcg"):
+        start, ms, lms = _vi_problem(split)
+        est = kontiki.TrajectoryEstimator(start)
+        for m in ms:
+            est.add_measurement(m)
+        s = est.solve(max_iterations=15, progress=False, linear_solver=solver)
+        results.append(s)
+    sh, sd = results
+    assert sh.final_cost < 1e-6 * sh.initial_cost and sd.final_cost < 1e-5 * sd.initial_cost
+    assert sd.iterations[1].cost < 1e-3 * sd.initial_cost            # first LM step already takes almost all of the decrease
+    assert max(i.linear_solver_iterations for i in sd.iterations) > 0
