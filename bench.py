@@ -198,7 +198,8 @@ def main():
     alg_bytes = syn.algorithmic_bytes(cfg)
 
     p = _lib.Problem(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()             # a real (non-default) stream: the library replays each step as one CUDA graph on it
+    torch.cuda.set_stream(stream)
     p.set_stream(stream.cuda_stream)
     if cfg.get("split"):
         p.set_split_spline(cfg["dt"], cfg["t0"], len(cfg["r3"]), cfg["dt"], cfg["t0"], len(cfg["so3"]))
@@ -245,12 +246,11 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step_device()
     p.synchronize()
-    p.read_profile(0)
     barrier()
-    p.set_profiling(True)
     l0 = p.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        # (1) the timed region: EXACTLY K steps between two events on the launching stream (each step = one CUDA-graph launch)
         e0.record(stream)
         for _ in range(a.steps):
             step_device()
@@ -258,16 +258,18 @@ def main():
         barrier()
         launches = p.launch_count - l0
         ms_total = e0.elapsed_time(e1)
-        if a.steps * (ms_total / max(a.steps, 1)) < 1500.0:      # keep the GPU under load long enough for a few clock samples
-            t_end = time.time() + 1.5
-            p.set_profiling(False)
-            while time.time() < t_end:
-                step_device()
-                torch.cuda.synchronize()
-            p.set_profiling(True)
-    p.synchronize()
-    prof = {name: p.read_profile(g) for name, g in groups.items()}
-    p.set_profiling(False)
+        # (2) the same K steps again with every kernel launch bracketed by CUDA events inside the library (plain stream
+        #     launches, no graph): per-kernel device time for the roofline of the dominant kernel
+        p.set_profiling(True)
+        for _ in range(a.steps):
+            step_device()
+        p.synchronize()
+        prof = {name: p.read_profile(g) for name, g in groups.items()}
+        p.set_profiling(False)
+        t_end = time.time() + 1.0                                 # keep the GPU under load long enough for a few clock samples
+        while time.time() < t_end:
+            step_device()
+            torch.cuda.synchronize()
     ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -101,6 +101,10 @@ void ktk_problem_destroy(ktk_problem* p);
 /* The stream all device work of this problem is enqueued on (a cudaStream_t; NULL = the legacy default stream). */
 int ktk_set_stream(ktk_problem* p, void* cuda_stream);
 
+/* ktk_evaluate_device replays its kernel sequence as ONE CUDA graph when it is called again with the same buffers on a
+ * non-default stream (default on; event-timed runs -- ktk_set_profiling -- are never captured). */
+int ktk_set_graphs(ktk_problem* p, int32_t on);
+
 /* UniformSE3SplineTrajectory(dt, t0) with n_knots control points (spline_base.h:30-62).  compat_zero_dB = 1 reproduces
  * the reference's Jet-path accelerometer on SE3 (dB left at zero, uniform_se3_spline_trajectory.h:138-141 vs :166-169). */
 int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, int32_t compat_zero_dB);

@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs"]
 
 _lib = None
 
@@ -85,6 +85,7 @@ def lib():
         L.ktk_jt_apply.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.POINTER(C.c_void_p), C.c_void_p]
         L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p]
         L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_set_graphs.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -154,6 +155,9 @@ class Problem:
 
     def set_stream(self, cuda_stream):
         check(lib().ktk_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_graphs(self, on):
+        check(lib().ktk_set_graphs(self._h, int(bool(on))))
 
     def set_se3_spline(self, dt, t0, n_knots, compat_zero_dB=False):
         check(lib().ktk_set_se3_spline(self._h, float(dt), float(t0), int(n_knots), int(compat_zero_dB)))

@@ -605,7 +605,11 @@ struct ktk_problem {
   int* h_err = nullptr;   // pinned
   int64_t launches = 0;
   bool profiling = false;
-  ~ktk_problem() { for (auto g : groups) delete g; if (h_err) cudaFreeHost(h_err); }
+  bool graphs_enabled = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<uint64_t> graph_key;
+  int64_t graph_launches = 0;
+  ~ktk_problem() { if (graph_exec) cudaGraphExecDestroy(graph_exec); for (auto g : groups) delete g; if (h_err) cudaFreeHost(h_err); }
 };
 
 namespace {
@@ -749,6 +753,8 @@ int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const do
   g->t.assign(t, t + n); g->y.assign(y, y + 3 * n);
   if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
   p->groups.push_back(g);
+  if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+  p->graph_key.clear();
   return (int)p->groups.size() - 1;
 }
 
@@ -789,14 +795,16 @@ int ktk_problem_create(int device, ktk_problem** out) {
 
 void ktk_problem_destroy(ktk_problem* p) { if (p) { if (p->device >= 0) cudaSetDevice(p->device); delete p; } }
 
-int ktk_set_stream(ktk_problem* p, void* s) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->stream = (cudaStream_t)s; return KTK_OK; }
+static void drop_graph(ktk_problem* p) { if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; } p->graph_key.clear(); }
+int ktk_set_stream(ktk_problem* p, void* s) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); drop_graph(p); p->stream = (cudaStream_t)s; return KTK_OK; }
+int ktk_set_graphs(ktk_problem* p, int32_t on) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); drop_graph(p); p->graphs_enabled = on != 0; return KTK_OK; }
 
 int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, int32_t compat) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
   if (!(dt > 0.0)) return fail(KTK_EINVAL, "dt must be positive");
   if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
-  p->traj = 0; p->have_spline = true;
+  p->traj = 0; p->have_spline = true; drop_graph(p);
   for (auto g : p->groups) g->uploaded = false;   // the sort key depends on (t0, dt)
   return KTK_OK;
 }
@@ -806,7 +814,7 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
   if (!(dt_r3 > 0.0) || !(dt_so3 > 0.0)) return fail(KTK_EINVAL, "dt must be positive");
   if (n_r3 < 4 || n_so3 < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->spl = SplitConst{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
-  p->traj = 1; p->have_spline = true;
+  p->traj = 1; p->have_spline = true; drop_graph(p);
   for (auto g : p->groups) g->uploaded = false;
   return KTK_OK;
 }
@@ -829,6 +837,7 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, 
   for (int l : g->lm) { g->lm_max = std::max(g->lm_max, l); g->lm_min = std::min(g->lm_min, l); }
   if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
   if (huber_c) g->huber.assign(huber_c, huber_c + n); else g->huber.assign((size_t)n, 5.0);
+  drop_graph(p);
   p->groups.push_back(g);
   return (int)p->groups.size() - 1;
 }
@@ -843,15 +852,14 @@ int64_t ktk_num_knot_doubles(const ktk_problem* p) {
   return p->traj == 1 ? (int64_t)3 * p->spl.n_r3 + (int64_t)4 * p->spl.n_so3 : (int64_t)7 * p->sp.n_knots;
 }
 
+static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs);
+
 // ktk_evaluate_device for a split trajectory: d_knots = [R3 knots (3 n_r3) | SO3 knots (4 n_so3)], the parameter order of
 // SplitEntity (split_trajectory.h:34-39, 117-123).
 static int evaluate_device_split(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs) {
   cudaStream_t s = p->stream;
-  int st;
   const SplitConst& sp = p->spl;
   const double* d_quats = d_knots + (size_t)3 * sp.n_r3;      // 4-double records already
-  if ((st = p->d_vecs4.resize((size_t)sp.n_r3 * kVecStride))) return st;
-  if ((st = p->d_so3pairs.resize((size_t)sp.n_so3 * kSo3PairStride))) return st;
   KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
   k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(d_knots, sp.n_r3, p->d_vecs4.p);
   k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
@@ -909,10 +917,52 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
     }
   }
-  if (p->traj == 1) return evaluate_device_split(p, d_knots, d_rho, flags, outs);
+  // scratch buffers are sized outside any stream capture
+  if (p->traj == 1) {
+    if ((st = p->d_vecs4.resize((size_t)p->spl.n_r3 * kVecStride))) return st;
+    if ((st = p->d_so3pairs.resize((size_t)p->spl.n_so3 * kSo3PairStride))) return st;
+  } else {
+    if ((st = p->d_knots8.resize((size_t)p->sp.n_knots * kKnotStride))) return st;
+    if ((st = p->d_pairs.resize((size_t)p->sp.n_knots * kPairStride))) return st;
+  }
+  // CUDA graph: one evaluation is 5-8 small stream operations; with the same buffers as last time the whole sequence is
+  // replayed as one graph launch (launch-bound for small problems: C1 is 12 us of kernels).  Event-timed runs are not captured.
+  std::vector<uint64_t> key;
+  const bool use_graph = p->graphs_enabled && !p->profiling && s != nullptr;
+  if (use_graph) {
+    key = {(uint64_t)flags, (uint64_t)d_knots, (uint64_t)d_rho, (uint64_t)n_rho, (uint64_t)p->traj};
+    for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+      const ktk_group_out& o = outs[gi];
+      for (const void* q : {(const void*)o.r, (const void*)o.J, (const void*)o.i0, (const void*)o.i0_b, (const void*)o.i0_c, (const void*)o.i0_d}) key.push_back((uint64_t)q);
+      key.push_back((uint64_t)p->groups[gi]->n);
+    }
+    if (p->graph_exec && key == p->graph_key) {
+      KTK_CUDA(cudaGraphLaunch(p->graph_exec, s));
+      p->launches += p->graph_launches;
+      return KTK_OK;
+    }
+    if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
+    KTK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  }
+  const int64_t launches_before = p->launches;
+  st = p->traj == 1 ? evaluate_device_split(p, d_knots, d_rho, flags, outs) : evaluate_device_se3(p, d_knots, d_rho, flags, outs);
+  if (use_graph) {
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    if (st) { if (graph) cudaGraphDestroy(graph); return st; }
+    if (ce != cudaSuccess) return fail(KTK_ECUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    KTK_CUDA(cudaGraphInstantiate(&p->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    p->graph_key = key;
+    p->graph_launches = p->launches - launches_before;
+    KTK_CUDA(cudaGraphLaunch(p->graph_exec, s));
+  }
+  return st;
+}
+
+static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs) {
+  cudaStream_t s = p->stream;
   const int nk = p->sp.n_knots;
-  if ((st = p->d_knots8.resize((size_t)nk * kKnotStride))) return st;
-  if ((st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
   KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
   k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(d_knots, nk, p->d_knots8.p);
   k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
