@@ -38,7 +38,13 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 #ifndef KTK_THREADS
-#define KTK_THREADS 64
+#define KTK_THREADS 32
+#endif
+#ifndef KTK_GYRO_MINB
+#define KTK_GYRO_MINB 1
+#endif
+#ifndef KTK_ACCEL_MINB
+#define KTK_ACCEL_MINB 1
 #endif
 #ifndef KTK_CAM_THREADS
 #define KTK_CAM_THREADS 32
@@ -51,12 +57,16 @@ constexpr int kCamThreads = KTK_CAM_THREADS;     // ... static-RS observation ke
 constexpr int kImuRow = 84, kImuRowStride = 86;     // doubles; stride keeps rows 16-B aligned and off the same banks
 constexpr int kCamRow = 114;                          // packed camera row in global memory: 112 knot-block doubles + d r/d rho (2)
 #ifndef KTK_CAM_STRIDE
-#define KTK_CAM_STRIDE 114
+#define KTK_CAM_STRIDE 92
 #endif
-// ... of which 112 are staged in shared memory.  The row stride decides how many warps of rows fit an SM: 112 -> 8 warps
-// but only 4 KB of L1 left for the pair table (measured 0.40 ms); 114 -> 7 warps and 24 KB of L1 (0.27 ms).
-constexpr int kCamStage = 112, kCamRowStride = KTK_CAM_STRIDE;
+// The SE3 camera kernel stages a row in two halves through ONE 92-double buffer per row (the landmark record lands in
+// it, the reference-window half is produced in place and scattered, then the observation-window half re-uses it):
+// 23 KB per warp => 8 warps of rows per SM (register-limited) AND ~40 KB of L1 left for the pair table.  L1 matters:
+// with 4 KB left (8 warps x 28 KB) the kernel took 0.40 ms, with 24 KB (7 x 29 KB) 0.27 ms (profiles/README.md).
+constexpr int kCamHalf = 56, kCamRowStride = KTK_CAM_STRIDE;
+constexpr int kCamStage = 112, kCamSplitStride = 114;  // the split-trajectory kernel still stages the whole row
 constexpr int kCamWarpSmem = 32 * kCamRowStride;      // doubles of shared memory per warp: 32 row buffers
+constexpr int kCamSplitWarpSmem = 32 * kCamSplitStride;
 
 // ---- data movement helpers ---------------------------------------------------------------------------------------
 // One TMA bulk store shared -> global (issued by ONE lane for a whole warp tile; UBLKCP is a uniform-datapath
@@ -78,7 +88,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // rows (GROW doubles apart) in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store
 // instruction writes one contiguous run.  dst_row < 0 skips a row (ragged tail / nothing to write).
 template <int STAGE, int STRIDE, int GROW>
-__device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, long long dst_row, int lane) {
+__device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, long long dst_row, int lane) {   // gJ may carry a column offset
   constexpr int kChunks = STAGE / 2;     // 16-byte chunks per row
   static_assert(kChunks <= 64, "at most two passes of 32 lanes");
   const bool full = __all_sync(0xffffffffu, dst_row >= 0);
@@ -159,7 +169,7 @@ __device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
 }
 
 template <int WHICH>
-__global__ void __launch_bounds__(kThreads) k_imu(const ImuArgs a) {
+__global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACCEL_MINB) k_imu(const ImuArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kImuRowStride;
@@ -258,24 +268,32 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   }
   cp_async_wait_all();
   __syncwarp();
+  ObsAdjoint adj;
+  int st = 0;
   if (cur.perm >= 0) {
-    double r[2];
+    double r[2], jrho[2];
     int ir = -1, io = -1;
-    double jrho[2];
-    const int st = static_rs_row_finish(a.cam, a.knots, a.pairs, f, row + kRefInRow, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io);
+    st = static_rs_row_ref_half(a.cam, f, row + kRefInRow, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io, adj);
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = jrho[0] = jrho[1] = nan(""); ir = io = -1;
-      for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
+      for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
     }
     const size_t dst = (size_t)cur.perm;
-    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
     if (a.i0r) a.i0r[dst] = ir;
     if (a.i0o) a.i0o[dst] = io;
+    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamStage, kCamRowStride, kCamRow>(wbase, a.J, (long long)cur.perm, lane);
+  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, (long long)cur.perm, lane);              // reference-window half
+  __syncwarp();
+  if (cur.perm >= 0) {
+    if (st == 0) static_rs_row_obs_half(a.knots, a.pairs, f, adj, row);
+    else for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
+  }
+  __syncwarp();
+  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J + kCamHalf, (long long)cur.perm, lane);   // observation-window half
 }
 
 // =====================================================================================================================
@@ -381,15 +399,15 @@ struct CamSplitArgs {
 __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(const CamSplitArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
-  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kCamWarpSmem;
-  double* row = wbase + lane * kCamRowStride;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kCamSplitWarpSmem;
+  double* row = wbase + lane * kCamSplitStride;
   const int tile = warp_tile();
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const int i = tile * 32 + lane;
   const int perm = i < a.n ? a.perm[i] : -1;
   const int myridx = i < a.n ? a.ref_idx[i] : -1;
-  warp_gather_records<kRefSplitStride, kCamRowStride, kRefSplitInRow>(wbase, a.recs, myridx, lane);
+  warp_gather_records<kRefSplitStride, kCamSplitStride, kRefSplitInRow>(wbase, a.recs, myridx, lane);
   double ouv[2] = {0.0, 0.0};
   ObsForwardSplit f; f.status = kStatusRange; f.ia = f.ib = -1;
   if (perm >= 0 && myridx >= 0) {
@@ -416,7 +434,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
     for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamStage, kCamRowStride, kCamRow>(wbase, a.J, (long long)perm, lane);
+  if (wantJ) warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, (long long)perm, lane);
 }
 
 __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,
@@ -787,7 +805,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
-  cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
+  cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamSplitWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref_split, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefSplitStride * 8);
   *out = p;
   return KTK_OK;
@@ -885,7 +903,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d; a.err = p->d_err.p;
-      k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
+      k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamSplitWarpSmem * 8, s>>>(a);
     } else {
       ImuSplitArgs a;
       a.sp = sp; fill_sensor_consts(g.sensor, a.imu);

@@ -532,12 +532,14 @@ KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const doub
 // buffer) at J + kRefInRow: the reference-window blocks are produced front to back, each read before it is overwritten.
 // J: [ref window: 4 knots][2][7] (56) | [obs window: 4 knots][2][7] (56);  Jrho: d r / d rho (2) -- the last two doubles of
 // the packed 114-double row, kept separate so that the kernels stage 112 doubles per row (8 warps of rows per SM).
-constexpr int kRefInRow = 20;      // 20 + 92 = 112 = staged row length; block k is read at 28 + 21 k and written at 14 k
+constexpr int kRefInRow = 0;       // the record fills the row buffer: block k is read at 8 + 21 k (into registers) and written at 14 k
 // (the observation pose P is evaluated by the caller first: it does not need the landmark record, so the kernels
 //  overlap the record gather with it)
-KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const double* p1, const double* p2, const double* p3, const Basis& bs,
-                             const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c, double* r, double* J,
-                             double* Jrho, int* i0_ref) {
+// The adjoints of the observation pose that the second half needs (18 doubles carried across the first scatter).
+struct ObsAdjoint { Mr<2> Gp, GpR, Gth; };
+// First half: projection, residual, reference-window blocks Jref[56] (may alias `ref`, see kRefInRow) and d r / d rho.
+KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c,
+                                  double* r, double* Jref, double* Jrho, int* i0_ref, ObsAdjoint& adj) {
   *i0_ref = (int)ref[7];
   const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
   const double rho = ref[6];
@@ -569,6 +571,11 @@ KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const dou
   for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
   const Mr<2> Go = rmul(Jp, Rct);               // d r / d Xobs
   const Mr<2> GX = rmul_nt(Go, P.R);            // d r / d X
+  // inverse depth: dXc/drho = R_ct R_o^T (dX/drho - p_o) + p_ct
+  const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
+  Jrho[0] = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z; Jrho[1] = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
+  // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
+  adj.Gp = rscale(-rho, GX); adj.GpR = rscale(-rho, Go); adj.Gth = rmul_hat(Go, Xobs);
   // reference-window blocks: GX (2x3) * dX/dknot_k (3x7), in place (see kRefInRow)
   const double* dXk = ref + kRefDOff;
 #pragma unroll
@@ -579,14 +586,8 @@ KB_HD void static_rs_obs_se3(const CameraConst& cam, const double* k0, const dou
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-      for (int c = 0; c < 7; ++c) J[14 * k + 7 * rr + c] = GX.a[3 * rr] * blk[c] + GX.a[3 * rr + 1] * blk[7 + c] + GX.a[3 * rr + 2] * blk[14 + c];
+      for (int c = 0; c < 7; ++c) Jref[14 * k + 7 * rr + c] = GX.a[3 * rr] * blk[c] + GX.a[3 * rr + 1] * blk[7 + c] + GX.a[3 * rr + 2] * blk[14 + c];
   }
-  // inverse depth: dXc/drho = R_ct R_o^T (dX/drho - p_o) + p_ct
-  const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
-  const double jr0 = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z, jr1 = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
-  // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
-  pose_backward<2>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, J + 56);
-  Jrho[0] = jr0; Jrho[1] = jr1;
 }
 
 // =================================================================================================================
@@ -680,18 +681,20 @@ KB_HD void static_rs_row_pose(const double* knots, const double* pairs, ObsForwa
   const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
   pose_forward(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, f.P);
 }
-// Part 2: projection, residual, Jacobian row (ref = landmark record, may alias J + kRefInRow).
-KB_HD int static_rs_row_finish(const CameraConst& cam, const double* knots, const double* pairs, const ObsForward& f, const double* ref,
-                               const double* obs_uv, double weight, double huber_c, double* r, double* J, double* Jrho, int* i0_ref_out,
-                               int* i0_obs_out) {
+// Part 2: projection, residual, reference-window half of the row (ref = landmark record, may alias Jref).
+KB_HD int static_rs_row_ref_half(const CameraConst& cam, const ObsForward& f, const double* ref, const double* obs_uv, double weight, double huber_c,
+                                 double* r, double* Jref, double* Jrho, int* i0_ref_out, int* i0_obs_out, ObsAdjoint& adj) {
   if (f.status != 0) return f.status;
-  const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
   int ir;
-  static_rs_obs_se3(cam, knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, f.P, ref, obs_uv, weight, huber_c,
-                    r, J, Jrho, &ir);
+  static_rs_obs_ref_half(cam, f.P, ref, obs_uv, weight, huber_c, r, Jref, Jrho, &ir, adj);
   if (ir < 0) return kStatusRange;                 // the landmark record itself was out of range
   *i0_ref_out = ir; *i0_obs_out = f.io;
   return 0;
+}
+// Part 3: observation-window blocks Jobs[56] from the adjoints.
+KB_HD void static_rs_row_obs_half(const double* knots, const double* pairs, const ObsForward& f, const ObsAdjoint& adj, double* Jobs) {
+  const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
+  pose_backward<2>(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, adj.Gp, adj.GpR, adj.Gth, 1.0, Jobs);
 }
 
 }  // namespace kb

@@ -58,7 +58,9 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     ObsForward f;
     static_rs_row_locate(sp, cam, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
     static_rs_row_pose(knots8, pairs, f);
-    status[i] = static_rs_row_finish(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, i0_ref + i, i0_obs + i);
+    ObsAdjoint adj;
+    status[i] = static_rs_row_ref_half(cam, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, i0_ref + i, i0_obs + i, adj);
+    if (status[i] == 0) static_rs_row_obs_half(knots8, pairs, f, adj, row + 56);
   }
 }
 
