@@ -56,8 +56,10 @@ enum {
 enum {
   KTK_EVAL_RESIDUALS = 1u,
   KTK_EVAL_JACOBIANS = 2u,
-  KTK_EVAL_ROBUST = 4u    /* apply ceres::HuberLoss(huber_c) + Corrector to static-RS rows, as Ceres does after Evaluate
+  KTK_EVAL_ROBUST = 4u,   /* apply ceres::HuberLoss(huber_c) + Corrector to static-RS rows, as Ceres does after Evaluate
                              (static_rscamera_measurement.h:195-197) */
+  KTK_EVAL_SENSOR_JACOBIANS = 8u   /* also fill ktk_group_out.Js: the columns of the sensor's own parameter blocks
+                             (sensors/sensors.h:135-165), needed when one of them is unlocked */
 };
 
 enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2 };
@@ -88,6 +90,10 @@ typedef struct {
   int32_t* i0_b;     /*                                             camera i0_obs; unused for IMU */
   int32_t* i0_c;     /* SO3 part of a split trajectory: IMU i0;  camera i0_ref   (unused for SE3) */
   int32_t* i0_d;     /*                                 camera i0_obs */
+  double* Js;        /* KTK_EVAL_SENSOR_JACOBIANS.  IMU rows: d r / d time_offset (3 per row); the relative pose of an IMU is not
+                        applied by the reference (TODO.md:6) so those columns are zero, and d r / d bias = -weight I for a
+                        ConstantBiasImu (constant_bias_imu.h:52-61).  Camera rows (SE3): 16 per row =
+                        d r/d q_ct (2x4) | d r/d p_ct (2x3) | d r/d time_offset (2x1) | pad (2), each block row-major as Ceres'. */
 } ktk_group_out;
 
 const char* ktk_last_error(void);
@@ -122,6 +128,12 @@ int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const do
 int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
 int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
+
+/* The sensor parameters are part of the evaluation point when they are unlocked: update them between evaluations.
+ * (Changing the time offset re-sorts the group on the next evaluation.)  ktk_set_group_bias: accelerometer / gyroscope bias of
+ * a ConstantBiasImu, r = weight (y - (model + bias)). */
+int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor);
+int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias);
 
 int32_t ktk_num_groups(const ktk_problem* p);
 int64_t ktk_group_size(const ktk_problem* p, int32_t group);

@@ -10,7 +10,7 @@ import numpy as np
 from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST = 1, 2, 4
+EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS = 1, 2, 4, 8
 GYROSCOPE, ACCELEROMETER, STATIC_RS = 0, 1, 2
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -25,14 +25,14 @@ class PinholeCamera(C.Structure):
 
 
 class GroupOut(C.Structure):
-    _fields_ = [("r", C.c_void_p), ("J", C.c_void_p), ("i0", C.c_void_p), ("i0_b", C.c_void_p), ("i0_c", C.c_void_p), ("i0_d", C.c_void_p)]
+    _fields_ = [("r", C.c_void_p), ("J", C.c_void_p), ("i0", C.c_void_p), ("i0_b", C.c_void_p), ("i0_c", C.c_void_p), ("i0_d", C.c_void_p), ("Js", C.c_void_p)]
 
 
 EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_set_stream", "ktk_set_se3_spline", "ktk_add_gyroscope",
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias"]
 
 _lib = None
 
@@ -86,6 +86,8 @@ def lib():
         L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p]
         L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_graphs.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_set_group_sensor.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Sensor)]
+        L.ktk_set_group_bias.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -209,7 +211,14 @@ class Problem:
     def launch_count(self):
         return lib().ktk_launch_count(self._h)
 
-    def alloc_outputs(self, jacobians=True):
+    def set_group_sensor(self, g, sensor):
+        check(lib().ktk_set_group_sensor(self._h, int(g), C.byref(sensor)))
+
+    def set_group_bias(self, g, bias):
+        b = _f64(bias).reshape(3)
+        check(lib().ktk_set_group_bias(self._h, int(g), _ptr(b)))
+
+    def alloc_outputs(self, jacobians=True, sensor_jacobians=False):
         """Host (numpy) output arrays for every group, in the C ABI's packed layouts."""
         outs = []
         for g in range(self.num_groups):
@@ -223,6 +232,8 @@ class Problem:
                 o["i0_c"] = np.full(n, -1, np.int32)
                 if cam:
                     o["i0_d"] = np.full(n, -1, np.int32)
+            if sensor_jacobians:
+                o["Js"] = np.zeros((n, 16 if cam else 3))
             outs.append(o)
         return outs
 
@@ -236,6 +247,7 @@ class Problem:
             arr[i].i0_b = getptr(o.get("i0_b"))
             arr[i].i0_c = getptr(o.get("i0_c"))
             arr[i].i0_d = getptr(o.get("i0_d"))
+            arr[i].Js = getptr(o.get("Js"))
         return arr
 
     def evaluate(self, knots, rho=None, flags=EVAL_RESIDUALS | EVAL_JACOBIANS, outs=None):
@@ -251,7 +263,7 @@ class Problem:
                 raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
         rho = None if rho is None else _f64(rho)
         if outs is None:
-            outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS))
+            outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS), bool(flags & EVAL_SENSOR_JACOBIANS))
         arr = self._out_array(outs, _ptr)
         check(lib().ktk_evaluate(self._h, _ptr(knots), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
         return outs

@@ -23,7 +23,7 @@
 #include <vector>
 
 #include "../../include/kontiki_b200.h"
-#include "split_math.cuh"
+#include "sensor_jac.cuh"
 
 using namespace kb;
 
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const ImuIn cur = imu_load(a, tile * 32 + lane);
   if (cur.perm >= 0) {
-    const double y[3] = {cur.y0, cur.y1, cur.y2};
+    const double y[3] = {cur.y0 - a.imu.bias[0], cur.y1 - a.imu.bias[1], cur.y2 - a.imu.bias[2]};   // r = w (y - (model + bias))
     double r[3];
     int i0 = -1;
     const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, cur.t, y, cur.w, r, row, &i0);
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
   int perm = -1;
   if (i < a.n) {
     perm = a.perm[i];
-    const double y[3] = {a.y[3 * (size_t)i], a.y[3 * (size_t)i + 1], a.y[3 * (size_t)i + 2]};
+    const double y[3] = {a.y[3 * (size_t)i] - a.imu.bias[0], a.y[3 * (size_t)i + 1] - a.imu.bias[1], a.y[3 * (size_t)i + 2] - a.imu.bias[2]};
     double r[3];
     int ia = -1, ib = -1;
     const int st = imu_row_split(WHICH, a.sp, a.imu, a.vecs, a.quats, a.pairs, a.t[i], y, a.w[i], r, row, &ia, &ib);
@@ -580,6 +580,43 @@ __global__ void k_jt_apply(const ApplyArgs a) {
   }
 }
 
+// =====================================================================================================================
+// Sensor-block Jacobians (cold path, only with KTK_EVAL_SENSOR_JACOBIANS): one thread per row, rows written straight to
+// the caller's row index (3 or 16 doubles).
+// =====================================================================================================================
+struct ImuSensorArgs {
+  int traj, which; SplineConst sp; SplitConst spl; ImuConst imu;
+  const double* knots; const double* pairs; const double* vecs; const double* quats; const double* so3pairs;
+  const double* t; const double* w; const int* perm; int n; double* Js; int* err;
+};
+__global__ void k_imu_sensor(const ImuSensorArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  double o[3];
+  const int st = a.traj == 0 ? imu_time_offset_jac_se3(a.which, a.sp, a.imu, a.knots, a.pairs, a.t[i], a.w[i], o)
+                             : imu_time_offset_jac_split(a.which, a.spl, a.imu, a.vecs, a.quats, a.so3pairs, a.t[i], a.w[i], o);
+  if (st != 0) { atomicMin(a.err, st); o[0] = o[1] = o[2] = nan(""); }
+  double* dst = a.Js + 3 * (size_t)a.perm[i];
+  dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+}
+struct CamSensorArgs {
+  SplineConst sp; CameraConst cam; const double* knots; const double* pairs; const double* rho;
+  const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
+  const int* perm; int n; uint32_t flags; double* Js; int* err;
+};
+__global__ void k_static_rs_sensor(const CamSensorArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  double o[16];
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]}, ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+  o[14] = o[15] = 0.0;
+  const int st = static_rs_sensor_jac_se3(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i],
+                                          (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, o);
+  if (st != 0) { atomicMin(a.err, st); for (int c = 0; c < 16; ++c) o[c] = nan(""); }
+  double* dst = a.Js + 16 * (size_t)a.perm[i];
+  for (int c = 0; c < 16; ++c) dst[c] = o[c];
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -595,7 +632,10 @@ struct Group {
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
   DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_t0, d_huber;
-  DevBuf<int> d_perm, d_ref_idx, d_lm_caller;
+  DevBuf<int> d_perm, d_ref_idx, d_lm_caller, d_lm_sorted;
+  DevBuf<double> d_ref_uv_sorted;
+  double bias[3] = {0.0, 0.0, 0.0};
+  DevBuf<double> o_Js;
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
   DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
@@ -632,7 +672,10 @@ struct ktk_problem {
 
 namespace {
 
-void fill_sensor_consts(const ktk_sensor& s, ImuConst& c) { c.time_offset = s.time_offset; c.max_time_offset = s.max_time_offset; c.time_offset_locked = s.time_offset_locked; }
+void fill_sensor_consts(const ktk_sensor& s, ImuConst& c) {
+  c.time_offset = s.time_offset; c.max_time_offset = s.max_time_offset; c.time_offset_locked = s.time_offset_locked;
+  c.bias[0] = c.bias[1] = c.bias[2] = 0.0;
+}
 
 void fill_camera_consts(const ktk_pinhole_camera& cm, CameraConst& c) {
   for (int i = 0; i < 9; ++i) c.K[i] = cm.K[i];
@@ -651,8 +694,7 @@ void fill_camera_consts(const ktk_pinhole_camera& cm, CameraConst& c) {
 
 int check_sensor(const ktk_sensor* s) {
   if (!s) return fail(KTK_EINVAL, "sensor is NULL");
-  if (!s->q_locked || !s->p_locked || !s->time_offset_locked)
-    return fail(KTK_EUNSUPPORTED, "unlocked sensor parameters (relative pose / time offset Jacobians) are not built yet");
+  if (!(s->max_time_offset >= 0.0)) return fail(KTK_EINVAL, "max_time_offset must be non-negative");
   return KTK_OK;
 }
 
@@ -745,6 +787,10 @@ int upload_group(ktk_problem* p, Group& g) {
     if ((st = g.d_obs_t0.upload(gather(g.obs_t0, g.perm, 1), s))) return st;
     if ((st = g.d_ref_t0.upload(gather(g.ref_t0, g.perm, 1), s))) return st;
     if ((st = g.d_huber.upload(gather(g.huber, g.perm, 1), s))) return st;
+    if (!g.sensor.q_locked || !g.sensor.p_locked || !g.sensor.time_offset_locked) {     // inputs of the sensor-Jacobian kernel
+      if ((st = g.d_ref_uv_sorted.upload(gather(g.ref_uv, g.perm, 2), s))) return st;
+      if ((st = g.d_lm_sorted.upload(gather(g.lm, g.perm, 1), s))) return st;
+    }
   } else {
     if ((st = g.d_t.upload(gather(g.t, g.perm, 1), s))) return st;
     if ((st = g.d_y.upload(gather(g.y, g.perm, 3), s))) return st;
@@ -860,6 +906,24 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, 
   return (int)p->groups.size() - 1;
 }
 
+int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor) {
+  if (!p || group < 0 || group >= (int)p->groups.size()) return fail(KTK_EINVAL, "bad group");
+  int st = check_sensor(sensor); if (st) return st;
+  Group& g = *p->groups[group];
+  g.sensor = *sensor; g.cam.base = *sensor;
+  g.uploaded = false;            // the row order and the landmark-reference table depend on the time offset
+  drop_graph(p);
+  return KTK_OK;
+}
+int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !bias) return fail(KTK_EINVAL, "bad argument");
+  Group& g = *p->groups[group];
+  if (g.kind == KTK_STATIC_RS) return fail(KTK_EINVAL, "a camera has no bias");
+  for (int c = 0; c < 3; ++c) g.bias[c] = bias[c];
+  drop_graph(p);
+  return KTK_OK;
+}
+
 int32_t ktk_num_groups(const ktk_problem* p) { return p ? (int32_t)p->groups.size() : 0; }
 int64_t ktk_group_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->n : -1; }
 int32_t ktk_group_kind(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->kind : -1; }
@@ -868,6 +932,31 @@ int32_t ktk_group_row_size(const ktk_problem* p, int32_t g) { return (p && g >= 
 int64_t ktk_num_knot_doubles(const ktk_problem* p) {
   if (!p || !p->have_spline) return 0;
   return p->traj == 1 ? (int64_t)3 * p->spl.n_r3 + (int64_t)4 * p->spl.n_so3 : (int64_t)7 * p->sp.n_knots;
+}
+
+// cold path: sensor-block Jacobians of one group (KTK_EVAL_SENSOR_JACOBIANS)
+static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out& o, uint32_t flags, const double* d_rho, const double* d_quats) {
+  if (!(flags & KTK_EVAL_SENSOR_JACOBIANS) || !o.Js || g.n == 0) return KTK_OK;
+  cudaStream_t s = p->stream;
+  const int blocks = (int)((g.n + 127) / 128);
+  if (g.kind == KTK_STATIC_RS) {
+    if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
+    if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
+    CamSensorArgs a;
+    a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
+    a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
+    a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv_sorted.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm_sorted.p; a.w = g.d_w.p;
+    a.huber = g.d_huber.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags; a.Js = o.Js; a.err = p->d_err.p;
+    k_static_rs_sensor<<<blocks, 128, 0, s>>>(a);
+  } else {
+    ImuSensorArgs a;
+    a.traj = p->traj; a.which = g.kind == KTK_GYROSCOPE ? 0 : 1; a.sp = p->sp; a.spl = p->spl; fill_sensor_consts(g.sensor, a.imu);
+    a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.vecs = p->d_vecs4.p; a.quats = d_quats; a.so3pairs = p->d_so3pairs.p;
+    a.t = g.d_t.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.Js = o.Js; a.err = p->d_err.p;
+    k_imu_sensor<<<blocks, 128, 0, s>>>(a);
+  }
+  p->launches += 1;
+  return KTK_OK;
 }
 
 static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs);
@@ -907,6 +996,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     } else {
       ImuSplitArgs a;
       a.sp = sp; fill_sensor_consts(g.sensor, a.imu);
+      for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
       a.vecs = p->d_vecs4.p; a.quats = d_quats; a.pairs = p->d_so3pairs.p;
       a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0_r3 = o.i0; a.i0_so3 = o.i0_c; a.err = p->d_err.p;
@@ -915,6 +1005,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
     p->launches += 1;
+    { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, d_quats); if (sj) return sj; }
   }
   KTK_CUDA(cudaGetLastError());
   KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -951,7 +1042,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
     key = {(uint64_t)flags, (uint64_t)d_knots, (uint64_t)d_rho, (uint64_t)n_rho, (uint64_t)p->traj};
     for (size_t gi = 0; gi < p->groups.size(); ++gi) {
       const ktk_group_out& o = outs[gi];
-      for (const void* q : {(const void*)o.r, (const void*)o.J, (const void*)o.i0, (const void*)o.i0_b, (const void*)o.i0_c, (const void*)o.i0_d}) key.push_back((uint64_t)q);
+      for (const void* q : {(const void*)o.r, (const void*)o.J, (const void*)o.i0, (const void*)o.i0_b, (const void*)o.i0_c, (const void*)o.i0_d, (const void*)o.Js}) key.push_back((uint64_t)q);
       key.push_back((uint64_t)p->groups[gi]->n);
     }
     if (p->graph_exec && key == p->graph_key) {
@@ -1010,6 +1101,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     } else {
       ImuArgs a;
       a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
+      for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
       a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
       a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
@@ -1018,6 +1110,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
     p->launches += 1;
+    { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, nullptr); if (sj) return sj; }
   }
   KTK_CUDA(cudaGetLastError());
   KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1055,13 +1148,14 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     Group& g = *p->groups[gi];
     const ktk_group_out& o = outs[gi];
     const size_t n = (size_t)g.n;
-    dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (o.r) { if ((st = g.o_r.resize(n * res_doubles(g)))) return st; dev[gi].r = g.o_r.p; }
     if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize(n * row_doubles(p, g)))) return st; dev[gi].J = g.o_J.p; }
     if (o.i0) { if ((st = g.o_i0.resize(n))) return st; dev[gi].i0 = g.o_i0.p; }
     if (o.i0_b) { if ((st = g.o_i0b.resize(n))) return st; dev[gi].i0_b = g.o_i0b.p; }
     if (o.i0_c) { if ((st = g.o_i0c.resize(n))) return st; dev[gi].i0_c = g.o_i0c.p; }
     if (o.i0_d) { if ((st = g.o_i0d.resize(n))) return st; dev[gi].i0_d = g.o_i0d.p; }
+    if (o.Js && (flags & KTK_EVAL_SENSOR_JACOBIANS)) { if ((st = g.o_Js.resize(n * (g.kind == KTK_STATIC_RS ? 16 : 3)))) return st; dev[gi].Js = g.o_Js.p; }
   }
   if ((st = ktk_evaluate_device(p, p->d_knots7.p, (rho && n_rho > 0) ? p->d_rho.p : nullptr, n_rho, flags, dev.data()))) return st;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
@@ -1075,6 +1169,7 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     if (dev[gi].i0_b && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_c && split) KTK_CUDA(cudaMemcpyAsync(o.i0_c, dev[gi].i0_c, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_d && split && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_d, dev[gi].i0_d, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].Js) KTK_CUDA(cudaMemcpyAsync(o.Js, dev[gi].Js, n * (cam ? 16 : 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
   return ktk_synchronize(p);
 }

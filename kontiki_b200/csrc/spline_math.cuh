@@ -601,7 +601,7 @@ constexpr int kStatusRange = -1;      // std::range_error in the reference
 
 KB_HD double spline_max_time(const SplineConst& sp) { return add_rn(sp.t0, mul_rn((double)(sp.n_knots - 3), sp.dt)); }
 
-struct ImuConst { double time_offset, max_time_offset; int time_offset_locked; };
+struct ImuConst { double time_offset, max_time_offset; int time_offset_locked; double bias[3]; };   // bias: ConstantBiasImu (constant_bias_imu.h:52-61), 0 for BasicImu
 
 // gyroscope (which = 0) / accelerometer (which = 1); gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
 KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const double* knots, const double* pairs,

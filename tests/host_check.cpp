@@ -4,7 +4,7 @@
 #include <cstddef>
 #include <vector>
 
-#include "../kontiki_b200/csrc/split_math.cuh"
+#include "../kontiki_b200/csrc/sensor_jac.cuh"
 
 using namespace kb;
 
@@ -21,7 +21,7 @@ void hc_imu(int which, double t0, double dt, int n_knots, int compat, double tim
             const double* knots8, const double* pairs, int n, const double* t, const double* y, const double* w, double* r, double* J,
             int* i0, int* status) {
   SplineConst sp{t0, dt, n_knots, compat};
-  ImuConst imu{time_offset, max_time_offset, locked};
+  ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
   for (int i = 0; i < n; ++i) {
     i0[i] = -1;
     status[i] = imu_row(which, sp, imu, knots8, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)84 * i, i0 + i);
@@ -77,7 +77,7 @@ void hc_imu_split(int which, double t0_r3, double dt_r3, int n_r3, double t0_so3
                   double max_time_offset, int locked, const double* vecs4, const double* quats, const double* pairs, int n, const double* t,
                   const double* y, const double* w, double* r, double* J, int* i0_r3, int* i0_so3, int* status) {
   SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
-  ImuConst imu{time_offset, max_time_offset, locked};
+  ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
   const int row = which == 0 ? 48 : 84;
   for (int i = 0; i < n; ++i) {
     i0_r3[i] = -1; i0_so3[i] = -1;
@@ -126,6 +126,37 @@ void hc_traj_eval_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
                         const double* pairs, int n, const double* t, double* out, int* status) {
   SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   for (int i = 0; i < n; ++i) status[i] = traj_eval_split(sp, vecs4, quats, pairs, t[i], out + 16 * i);
+}
+
+
+// ---- sensor-block Jacobians ---------------------------------------------------------------------------------------------
+void hc_imu_time_offset_se3(int which, double t0, double dt, int n_knots, int compat, double time_offset, double max_time_offset, int locked,
+                            const double* knots8, const double* pairs, int n, const double* t, const double* w, double* out, int* status) {
+  SplineConst sp{t0, dt, n_knots, compat};
+  ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
+  for (int i = 0; i < n; ++i) status[i] = imu_time_offset_jac_se3(which, sp, imu, knots8, pairs, t[i], w[i], out + 3 * i);
+}
+void hc_imu_time_offset_split(int which, double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, double time_offset,
+                              double max_time_offset, int locked, const double* vecs4, const double* quats, const double* pairs, int n, const double* t,
+                              const double* w, double* out, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
+  for (int i = 0; i < n; ++i) status[i] = imu_time_offset_jac_split(which, sp, imu, vecs4, quats, pairs, t[i], w[i], out + 3 * i);
+}
+void hc_static_rs_sensor_se3(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
+                             double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
+                             const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
+                             const int* lm_idx, const double* rho, const double* w, const double* huber_c, double* out, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
+  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  for (int i = 0; i < n; ++i)
+    status[i] = static_rs_sensor_jac_se3(sp, cam, knots8, pairs, obs_uv + 2 * i, obs_t0[i], ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], w[i],
+                                         huber_c ? huber_c[i] : 0.0, out + 16 * i);
 }
 
 }  // extern "C"

@@ -19,7 +19,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "split_math.cuh", "lie_math.cuh", "dualnum.cuh")]
+        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "split_math.cuh", "sensor_jac.cuh", "lie_math.cuh", "dualnum.cuh")]
         if not os.path.exists(_OUT) or any(os.path.getmtime(d) > os.path.getmtime(_OUT) for d in deps):
             os.makedirs(os.path.dirname(_OUT), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", _SRC, "-o", _OUT])
@@ -140,4 +140,44 @@ def traj_eval_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t):
     out, st = np.zeros((len(t), 16)), np.zeros(len(t), np.int32)
     lib().hc_traj_eval_split(C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(v4), _p(q4), _p(pairs),
                              len(t), _p(t), _p(out), _p(st))
+    return out, st
+
+
+# ---- sensor-block Jacobians ---------------------------------------------------------------------------------------------
+def imu_time_offset_se3(which, knots7, dt, t0, t, w=None, compat=False, time_offset=0.0, max_time_offset=0.1, locked=True):
+    k8, pairs = prepass(knots7)
+    t = _f(t)
+    n = len(t)
+    w = np.ones(n) if w is None else _f(w)
+    out, st = np.zeros((n, 3)), np.zeros(n, np.int32)
+    lib().hc_imu_time_offset_se3(int(which), C.c_double(t0), C.c_double(dt), len(k8), int(compat), C.c_double(time_offset), C.c_double(max_time_offset),
+                                 int(locked), _p(k8), _p(pairs), n, _p(t), _p(w), _p(out), _p(st))
+    return out, st
+
+
+def imu_time_offset_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, w=None, time_offset=0.0, max_time_offset=0.1, locked=True):
+    v4, q4, pairs, _ = split_prepass(vecs3, quats)
+    t = _f(t)
+    n = len(t)
+    w = np.ones(n) if w is None else _f(w)
+    out, st = np.zeros((n, 3)), np.zeros(n, np.int32)
+    lib().hc_imu_time_offset_split(int(which), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4),
+                                   C.c_double(time_offset), C.c_double(max_time_offset), int(locked), _p(v4), _p(q4), _p(pairs), n, _p(t), _p(w), _p(out), _p(st))
+    return out, st
+
+
+def static_rs_sensor_se3(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    k8, pairs = prepass(knots7)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    out, st = np.zeros((n, 16)), np.zeros(n, np.int32)
+    lib().hc_static_rs_sensor_se3(C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset),
+                                  C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows), _p(k8), _p(pairs), n,
+                                  _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc), _p(out), _p(st))
     return out, st

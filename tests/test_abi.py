@@ -46,11 +46,17 @@ def test_no_cpu_fallback():
     assert e.value.code == _lib.ECUDA
 
 
-def test_unlocked_sensor_is_refused_not_ignored():
+def test_structure_unlocked_time_offset_matches_oracle():
+    """gyroscope_measurement.h:83-91: with the time offset unlocked the span is t -+ max_time_offset => more knot blocks."""
+    knots = fx.smooth_se3_knots(80, 0.05)
+    t = np.random.default_rng(1).uniform(0.2, 3.6, 200)
     p = _lib.Problem(-1)
-    p.set_se3_spline(0.1, 0.0, 20)
-    with pytest.raises(NotImplementedError):
-        p.add_gyroscope(_lib.make_sensor(time_offset_locked=False), [0.5], [[0, 0, 0]])
+    p.set_se3_spline(0.05, 0.0, 80)
+    g = p.add_gyroscope(_lib.make_sensor(time_offset_locked=False, max_time_offset=0.1), t, np.zeros((200, 3)))
+    ids, nids = p.get_structure(g, cap=12)
+    o = kto.imu_residuals(kto.Traj(kto.SE3, 0.05, 0.0, knots), kto.Sensor(d_locked=False, max_time_offset=0.1), 0, t, np.zeros((200, 3)), jac_mode=0, cap=12)
+    assert (ids == o["ids_a"]).all()
+    assert nids.min() >= 8
 
 
 def test_structure_imu_matches_oracle():

@@ -300,3 +300,64 @@ def test_split_non_unit_quaternion_is_a_runtime_error():
     p.add_gyroscope(_lib.make_sensor(), c["t"][:64], c["y"][:64])
     with pytest.raises(RuntimeError):
         p.evaluate((c["vecs"], q))
+
+
+# ---- unlocked sensor parameters --------------------------------------------------------------------
+def test_unlocked_sensors_se3_match_oracle():
+    """Time offset / camera relative pose unlocked: wider spans (structure), same knot blocks, plus the sensor-block columns.
+
+    Reference quirk reproduced (static_rscamera_measurement.h:153-157): with the camera's time offset unlocked the FIRST span is
+    shifted earlier and the SECOND later by max_time_offset (instead of both being widened), so an evaluation time can fall
+    outside every segment and the reference throws from inside Evaluate.  Rows for which the oracle throws are dropped here;
+    test_out_of_range_is_an_error_not_garbage covers the error path."""
+    dt, n_knots = 0.1, 200
+    knots = syn.smooth_se3_knots(n_knots, dt)
+    rng = np.random.default_rng(8)
+    t = rng.uniform(0.3, (n_knots - 3) * dt - 0.4, 3000)
+    y = rng.uniform(-1, 1, (3000, 3))
+    c = syn.make_static_rs(knots, dt, 300, obs_per_landmark=8, seed=8, noise_px=1.0)
+    keep = (np.minimum(c["ref_t0"], c["obs_t0"]) > 0.3) & (np.maximum(c["ref_t0"], c["obs_t0"]) < (n_knots - 3) * dt - 0.4)
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    traj = kto.Traj(kto.SE3, dt, 0.0, knots)
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], q_ct=q_ct, p_ct=p_ct, time_offset=-0.002, max_time_offset=0.004, q_locked=False,
+                      p_locked=False, d_locked=False)
+    o_all = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=0, cap=32,
+                                    raise_on_error=False)
+    keep &= o_all["status"] == 0
+    assert 0.5 * len(keep) < keep.sum() < len(keep)          # the quirk bites some rows, not most
+    for a in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "weight", "huber_c"):
+        c[a] = c[a][keep]
+    p = _lib.Problem(0)
+    p.set_se3_spline(dt, 0.0, n_knots)
+    imu = _lib.make_sensor(time_offset=0.003, max_time_offset=0.05, time_offset_locked=False)
+    gg = p.add_gyroscope(imu, t, y)
+    ga = p.add_accelerometer(imu, t, y)
+    p.set_group_bias(ga, [0.01, -0.02, 0.03])
+    cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], q_ct=q_ct, p_ct=p_ct, time_offset=-0.002, max_time_offset=0.004,
+                           q_locked=False, p_locked=False, time_offset_locked=False)
+    gc = p.add_static_rs(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
+    outs = p.evaluate(knots, c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_SENSOR_JACOBIANS)
+    for g, which, bias in ((gg, 0, None), (ga, 1, [0.01, -0.02, 0.03])):
+        osen = kto.Sensor(time_offset=0.003, max_time_offset=0.05, d_locked=False, abias=bias, gbias=None if bias is None else [0, 0, 0])
+        o = kto.imu_residuals(traj, osen, which, t, y, jac_mode=2, cap=16)
+        out = outs[g]
+        assert (out["i0"] == o["i0_a"]).all()
+        ids, nids = p.get_structure(g, cap=16)
+        assert (ids == o["ids_a"]).all() and nids.min() > 4
+        assert parity.rel_err(out["r"], o["r"]) < parity.TOL
+        pos = np.array([list(ids[i]).index(out["i0"][i]) for i in range(len(ids))])
+        Jo = np.stack([o["Ja"][i, pos[i]:pos[i] + 4] for i in range(len(ids))])
+        assert parity.rel_err(out["J"], Jo) < parity.TOL
+        assert parity.rel_err(out["Js"], o["Js"][:, 21:24]) < parity.TOL
+        if bias is not None:
+            assert np.allclose(o["Js"][:, 24:33].reshape(-1, 3, 3), -np.eye(3), atol=1e-15)       # d r / d abias = -weight I
+    o = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=2, cap=32)
+    out = outs[gc]
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_b"] == o["i0_obs_a"]).all()
+    ids, _ = p.get_structure(gc, cap=32)
+    assert (ids == o["ids_a"]).all()
+    Js = p.expand_static_rs(gc, ids, out["J"], out["i0"], out["i0_b"])
+    assert np.abs(out["r"] - o["r"]).max() < parity.TOL * 1e3
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL
+    for a, b in ((0, 8), (8, 14), (14, 16)):
+        assert parity.rel_err(out["Js"][:, a:b], o["Js"][:, a:b]) < parity.TOL
