@@ -198,11 +198,12 @@ class TrajectoryEstimator:
                 g = p.add_static_rs(sensor._c_camera(), np.array([m.observation.uv for m in ms]), [m.observation.view.t0 for m in ms],
                                     np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
                                     lm, [m.weight for m in ms], [m.huber_c for m in ms])
-                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64)))
+                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor))
             else:
                 fn = p.add_gyroscope if kind is GyroscopeMeasurement else p.add_accelerometer
                 g = fn(sensor._c_sensor(), [m.t for m in ms], np.array([m._x for m in ms]), [m.weight for m in ms])
-                self._groups.append(dict(g=g, kind="gyro" if kind is GyroscopeMeasurement else "accel", rows=rows))
+                self._groups.append(dict(g=g, kind="gyro" if kind is GyroscopeMeasurement else "accel", rows=rows, sensor=sensor,
+                                         weight=np.array([m.weight for m in ms])))
         self._problem = p
 
     def _point(self):
@@ -211,11 +212,41 @@ class TrajectoryEstimator:
         rho = np.array([L.inverse_depth for L in self._landmarks]) if self._landmarks else None
         return knots, rho
 
+    @staticmethod
+    def _sensor_free(sensor):
+        """Names of the sensor's unlocked parameter blocks, in the reference's block order (sensors.h:139-161, constant_bias_imu.h:106-118)."""
+        free = []
+        cam = hasattr(sensor, "camera_matrix")
+        if cam and not sensor.relative_orientation_locked:
+            free.append("q")                 # an IMU's relative pose is not applied by the reference (TODO.md:6): zero columns, left out
+        if cam and not sensor.relative_position_locked:
+            free.append("p")
+        if not sensor.time_offset_locked:
+            free.append("d")
+        if not getattr(sensor, "accelerometer_bias_locked", True):
+            free.append("ab")
+        if not getattr(sensor, "gyroscope_bias_locked", True):
+            free.append("gb")
+        return free
+
+    def _push_sensors(self):
+        """The sensor parameters are part of the evaluation point (ktk_set_group_sensor / ktk_set_group_bias)."""
+        for grp in self._groups:
+            sn = grp["sensor"]
+            if self._sensor_free(sn):
+                self._problem.set_group_sensor(grp["g"], sn._c_sensor())
+            bias = getattr(sn, "gyroscope_bias" if grp["kind"] == "gyro" else "accelerometer_bias", None) if grp["kind"] != "cam" else None
+            if bias is not None:
+                self._problem.set_group_bias(grp["g"], bias)
+
     def evaluate(self, jacobians=True, robust=True):
         """One batched residual (+ Jacobian) evaluation at the current state; list of per-group outputs (C ABI layouts)."""
         self._build()
+        self._push_sensors()
         knots, rho = self._point()
         flags = _lib.EVAL_RESIDUALS | (_lib.EVAL_JACOBIANS if jacobians else 0) | (_lib.EVAL_ROBUST if robust else 0)
+        if jacobians and any(self._sensor_free(g["sensor"]) for g in self._groups):
+            flags |= _lib.EVAL_SENSOR_JACOBIANS
         return self._problem.evaluate(knots, rho, flags)
 
     # ---- local (tangent) sparse Jacobian ----------------------------------------------------------------------------------
@@ -233,7 +264,20 @@ class TrajectoryEstimator:
         free_lm = np.array([not L.locked for L in self._landmarks], bool) if self._landmarks else np.zeros(0, bool)
         self._lm_col = np.full(len(self._landmarks), -1, np.int64)
         self._lm_col[free_lm] = off + np.arange(free_lm.sum())
-        return layout, off + int(free_lm.sum())
+        off += int(free_lm.sum())
+        # unlocked sensor parameter blocks, one set of columns per distinct sensor object
+        width = {"q": 3, "p": 3, "d": 1, "ab": 3, "gb": 3}
+        self._sensor_cols = {}
+        for grp in getattr(self, "_groups", []):
+            sn = grp["sensor"]
+            if id(sn) in self._sensor_cols:
+                continue
+            cols = {}
+            for name in self._sensor_free(sn):
+                cols[name] = off
+                off += width[name]
+            self._sensor_cols[id(sn)] = (sn, cols)
+        return layout, off
 
     def _sparse_system(self, outs):
         """r (stacked) and J in local coordinates as scipy CSR, from the packed device rows."""
@@ -290,6 +334,22 @@ class TrajectoryEstimator:
                 else:
                     add_blocks(o["J"][:, :36].reshape(n, 4, 3, 3), o["i0"], 3, "r3", 3)
                     add_blocks(o["J"][:, 36:].reshape(n, 4, 3, 4), o["i0_c"], 4, "so3", 3)
+            # sensor-block columns (KTK_EVAL_SENSOR_JACOBIANS)
+            sn, scols = self._sensor_cols.get(id(grp["sensor"]), (None, {}))
+            rr = row0 + nres * np.arange(n)[:, None] + np.arange(nres)[None, :]           # (n, nres) global residual rows
+            if "d" in scols:
+                Jd = o["Js"][:, 14:16] if grp["kind"] == "cam" else o["Js"][:, 0:3]
+                rows_i.append(rr.reshape(-1)); cols_i.append(np.full(rr.size, scols["d"])); vals.append(Jd.reshape(-1))
+            if grp["kind"] == "cam" and ("q" in scols or "p" in scols):
+                if "q" in scols:
+                    Pq = _quat_plus_jacobian(sn._q_ct[None, :])[0]                         # (4, 3)
+                    Jq = o["Js"][:, 0:8].reshape(n, 2, 4) @ Pq
+                    rows_i.append(np.repeat(rr.reshape(-1), 3)); cols_i.append(np.tile(scols["q"] + np.arange(3), rr.size)); vals.append(Jq.reshape(-1))
+                if "p" in scols:
+                    rows_i.append(np.repeat(rr.reshape(-1), 3)); cols_i.append(np.tile(scols["p"] + np.arange(3), rr.size)); vals.append(o["Js"][:, 8:14].reshape(-1))
+            bname = {"gyro": "gb", "accel": "ab"}.get(grp["kind"])
+            if bname in scols:                                                                # d r / d bias = -weight I
+                rows_i.append(rr.reshape(-1)); cols_i.append(np.tile(scols[bname] + np.arange(3), n)); vals.append(np.repeat(-grp["weight"], 3))
             rs.append(o["r"].reshape(-1))
             row0 += nres * n
         r = np.concatenate(rs) if rs else np.zeros(0)
@@ -317,11 +377,24 @@ class TrajectoryEstimator:
         for L, c in zip(self._landmarks, self._lm_col):
             if c >= 0:
                 L.inverse_depth = max(rho_lower, L.inverse_depth + delta[c])      # lower bound 0, static_rscamera_measurement.h:178-181
+        for sn, cols in self._sensor_cols.values():
+            if "q" in cols:
+                sn._q_ct = _quat_plus(sn._q_ct[None, :], delta[cols["q"]:cols["q"] + 3][None, :])[0]
+            if "p" in cols:
+                sn._p_ct = sn._p_ct + delta[cols["p"]:cols["p"] + 3]
+            if "d" in cols:      # bounds +-max_time_offset (sensors.h:159-160)
+                sn.time_offset = float(np.clip(sn.time_offset + delta[cols["d"]], -sn.max_time_offset, sn.max_time_offset))
+            if "ab" in cols:
+                sn.accelerometer_bias = sn.accelerometer_bias + delta[cols["ab"]:cols["ab"] + 3]
+            if "gb" in cols:
+                sn.gyroscope_bias = sn.gyroscope_bias + delta[cols["gb"]:cols["gb"] + 3]
 
     def _snapshot(self):
         tr = self._trajectory
         spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
-        return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks]
+        sens = [(sn, sn._q_ct.copy(), sn._p_ct.copy(), sn.time_offset, getattr(sn, "accelerometer_bias", None), getattr(sn, "gyroscope_bias", None))
+                for sn, _ in getattr(self, "_sensor_cols", {}).values()]
+        return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks], sens
 
     def _restore(self, snap):
         tr = self._trajectory
@@ -330,6 +403,10 @@ class TrajectoryEstimator:
             s.control_points[:] = c
         for L, v in zip(self._landmarks, snap[1]):
             L.inverse_depth = v
+        for sn, q, pp, d, ab, gb in snap[2]:
+            sn._q_ct, sn._p_ct, sn.time_offset = q.copy(), pp.copy(), d
+            if ab is not None:
+                sn.accelerometer_bias, sn.gyroscope_bias = ab.copy(), gb.copy()
 
     @staticmethod
     def _cost(outs, groups, hubers):
@@ -344,6 +421,11 @@ class TrajectoryEstimator:
         multi-GPU aware), or "auto" (device_pcg above 20 000 measurements)."""
         if linear_solver == "auto":
             linear_solver = "device_pcg" if len(self._measurements) > 20000 else "host_cholesky"
+        self._build()
+        if any(self._sensor_free(g["sensor"]) for g in self._groups):
+            if linear_solver == "device_pcg":
+                raise NotImplementedError("unlocked sensor parameters are optimised by the host_cholesky path only")
+            linear_solver = "host_cholesky"
         if linear_solver == "device_pcg":
             return self._solve_device(max_iterations, progress)
         if linear_solver != "host_cholesky":

@@ -30,16 +30,23 @@ class _ImuMeasurement:
         self.imu, self.t, self.weight = imu, float(t), float(weight)
         self._x = np.asarray(x, float).reshape(3).copy()
 
-    def error(self, trajectory):
+    def _bias(self):
+        name = "gyroscope_bias" if self._add == "add_gyroscope" else "accelerometer_bias"
+        return getattr(self.imu, name, None)
+
+    def _residual(self, trajectory, x, weight):
         p, knots = _problem_for(trajectory)
-        getattr(p, self._add)(self.imu._c_sensor(), [self.t], self._x[None, :], [self.weight])
+        g = getattr(p, self._add)(self.imu._c_sensor(), [self.t], np.asarray(x, float).reshape(1, 3), [weight])
+        if self._bias() is not None:
+            p.set_group_bias(g, self._bias())
         return p.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0]
+
+    def error(self, trajectory):
+        return self._residual(trajectory, self._x, self.weight)
 
     def measure(self, trajectory):
         # error = weight (x - measure)   (gyroscope_measurement.h:36-38)
-        p, knots = _problem_for(trajectory)
-        getattr(p, self._add)(self.imu._c_sensor(), [self.t], np.zeros((1, 3)), [1.0])
-        return -p.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0]
+        return -self._residual(trajectory, np.zeros(3), 1.0)
 
 
 class GyroscopeMeasurement(_ImuMeasurement):

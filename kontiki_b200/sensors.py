@@ -45,6 +45,17 @@ class BasicImu(_Sensor):
     """sensors/basic_imu.h:26-33."""
 
 
+class ConstantBiasImu(_Sensor):
+    """sensors/constant_bias_imu.h: BasicImu + constant accelerometer / gyroscope biases (both locked by default, :83-97)."""
+
+    def __init__(self, accelerometer_bias=(0, 0, 0), gyroscope_bias=(0, 0, 0)):
+        super().__init__()
+        self.accelerometer_bias = np.asarray(accelerometer_bias, float).copy()
+        self.gyroscope_bias = np.asarray(gyroscope_bias, float).copy()
+        self.accelerometer_bias_locked = True
+        self.gyroscope_bias_locked = True
+
+
 class PinholeCamera(_Sensor):
     """sensors/pinhole_camera.h; PinholeCamera(rows, cols, readout[, camera_matrix])."""
 

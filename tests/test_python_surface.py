@@ -297,3 +297,37 @@ def test_device_pcg_solve_converges_like_host_cholesky(split):
     assert sh.final_cost < 1e-6 * sh.initial_cost and sd.final_cost < 1e-5 * sd.initial_cost
     assert sd.iterations[1].cost < 1e-3 * sd.initial_cost            # first LM step already takes almost all of the decrease
     assert max(i.linear_solver_iterations for i in sd.iterations) > 0
+
+
+def test_solve_recovers_time_offset_and_gyro_bias():
+    """unlocked IMU time offset (bounded by max_time_offset, sensors.h:159-160) and a ConstantBiasImu
+    gyroscope bias are estimated together with nothing else (trajectory locked), test_estimator.py:78-99 style."""
+    from kontiki_b200.sensors import ConstantBiasImu
+    from kontiki_b200 import synthetic as syn
+    dt, n = 0.1, 60
+    traj = UniformSE3SplineTrajectory(dt, 0.0)
+    traj._cp = syn.smooth_se3_knots(n, dt, noise=0.0)
+    true_imu = ConstantBiasImu(gyroscope_bias=[0.02, -0.01, 0.03])
+    true_imu.time_offset = 0.012
+    true_imu.time_offset_locked, true_imu.max_time_offset = False, 0.05      # a LOCKED non-zero offset may leave the 4-knot segment (SURVEY 8b edge case i)
+    rng = np.random.default_rng(5)
+    times = rng.uniform(traj.min_time + 0.2, traj.max_time - 0.2, 200)
+    ws = [GyroscopeMeasurement(true_imu, t, np.zeros(3)).measure(traj) for t in times[:3]]      # single-row API with bias + offset
+    p, knots = kontiki.measurements._problem_for(traj)
+    g = p.add_gyroscope(true_imu._c_sensor(), times, np.zeros((len(times), 3)))
+    p.set_group_bias(g, true_imu.gyroscope_bias)
+    w_all = -p.evaluate(knots, None, 1)[g]["r"]
+    assert np.allclose(w_all[:3], ws, atol=1e-12)
+    imu = ConstantBiasImu()
+    imu.time_offset_locked = False
+    imu.gyroscope_bias_locked = False
+    imu.max_time_offset = 0.05
+    traj.locked = True
+    est = kontiki.TrajectoryEstimator(traj)
+    for t, w in zip(times, w_all):
+        est.add_measurement(GyroscopeMeasurement(imu, t, w))
+    s = est.solve(max_iterations=20, progress=False)
+    assert s.num_effective_parameters_reduced == 4
+    assert abs(imu.time_offset - 0.012) < 1e-6
+    assert np.allclose(imu.gyroscope_bias, true_imu.gyroscope_bias, atol=1e-7)
+    assert s.final_cost < 1e-12
