@@ -63,9 +63,13 @@ constexpr int kCamRow = 114;                          // packed camera row in gl
 // it, the reference-window half is produced in place and scattered, then the observation-window half re-uses it):
 // 23 KB per warp => 8 warps of rows per SM (register-limited) AND ~40 KB of L1 left for the pair table.  L1 matters:
 // with 4 KB left (8 warps x 28 KB) the kernel took 0.40 ms, with 24 KB (7 x 29 KB) 0.27 ms (profiles/README.md).
+#ifndef KTK_WINDOW
+#define KTK_WINDOW 0
+#endif
+constexpr int kWinCap = KTK_WINDOW;   // pair records of the tile window staged in shared memory; 0 (default) = read through L1: staging measured no gain
 constexpr int kCamHalf = 56, kCamRowStride = KTK_CAM_STRIDE;
 constexpr int kCamStage = 112, kCamSplitStride = 114;  // the split-trajectory kernel still stages the whole row
-constexpr int kCamWarpSmem = 32 * kCamRowStride;      // doubles of shared memory per warp: 32 row buffers
+constexpr int kCamWarpSmem = 32 * kCamRowStride + kWinCap * kPairStride;   // doubles of shared memory per warp: 32 row buffers + pair window
 constexpr int kCamSplitWarpSmem = 32 * kCamSplitStride;
 
 // ---- data movement helpers ---------------------------------------------------------------------------------------
@@ -83,6 +87,8 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Warp-cooperative scatter of the warp's 32 staged rows (STAGE doubles each, STRIDE apart in shared memory) to their
 // rows (GROW doubles apart) in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store
@@ -257,15 +263,40 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const CamIn cur = cam_load(a, tile * 32 + lane);
+  const double ouv[2] = {cur.u, cur.v};
+  const bool live = cur.perm >= 0 && cur.ridx >= 0;
+  const double* pairs = a.pairs;
+  int wmin = 0, wmax = -1;
+#if KTK_WINDOW > 0
+  // Stage the tile's window of the pair table: rows are sorted by first knot, so the 32 rows share 3 + (i0max - i0min)
+  // consecutive 832-B records.  A one-warp CTA meets a cold L1 and the row scatter streams through it, so without this
+  // every sector of the window is fetched from L2 several times per tile (ncu: 18 % L1 hit rate on the loads).
+  {
+    const int ig = live ? knot_floor(static_rs_time(a.cam, cur.obs_t0, cur.v), a.sp.t0, a.sp.dt) : 0;
+    wmin = __reduce_min_sync(0xffffffffu, live ? ig : 0x7fffffff);
+    wmax = __reduce_max_sync(0xffffffffu, live ? ig : (int)0x80000000);
+    const int nrec = wmax - wmin + 3;
+    if (wmin <= wmax && nrec <= kWinCap && wmin >= 0 && wmax + 3 < a.sp.n_knots) {
+      const double2* src = reinterpret_cast<const double2*>(a.pairs + (size_t)(wmin + 1) * kPairStride);
+      double2* dst = reinterpret_cast<double2*>(wbase + 32 * kCamRowStride);
+      for (int c = lane; c < nrec * (kPairStride / 2); c += 32) cp_async16(dst + c, src + c);
+    } else {
+      wmax = wmin - 1;      // nothing staged: every lane reads the global table
+    }
+    cp_async_commit();
+  }
+#endif
   // gather the 32 landmark records of this tile into the row buffers (cooperative 16-B LDGSTS: every instruction moves
   // one contiguous 512-B run), in flight during the observation-pose evaluation below
   warp_gather_records<kRefStride, kCamRowStride, kRefInRow>(wbase, a.recs, cur.ridx, lane);
-  const double ouv[2] = {cur.u, cur.v};
+  cp_async_commit();
   ObsForward f; f.status = kStatusRange; f.io = -1;
-  if (cur.perm >= 0 && cur.ridx >= 0) {
-    static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
-    static_rs_row_pose(a.knots, a.pairs, f);
-  }
+  if (live) static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
+  // a row whose exact first knot (segment arithmetic) lies in the staged window reads its pair records from shared memory
+  if (f.status == 0 && f.io >= wmin && f.io <= wmax) pairs = wbase + 32 * kCamRowStride - (size_t)(wmin + 1) * kPairStride;
+  cp_async_wait_group<1>();      // the window has landed; the record gather may still be in flight
+  __syncwarp();
+  static_rs_row_pose(a.knots, pairs, f);
   cp_async_wait_all();
   __syncwarp();
   ObsAdjoint adj;
@@ -289,7 +320,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, (long long)cur.perm, lane);              // reference-window half
   __syncwarp();
   if (cur.perm >= 0) {
-    if (st == 0) static_rs_row_obs_half(a.knots, a.pairs, f, adj, row);
+    if (st == 0) static_rs_row_obs_half(a.knots, pairs, f, adj, row);
     else for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
   }
   __syncwarp();
