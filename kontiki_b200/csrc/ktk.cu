@@ -94,22 +94,22 @@ template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm vol
 // rows (GROW doubles apart) in global memory: for each row, the 32 lanes move consecutive 16-byte chunks, so every store
 // instruction writes one contiguous run.  dst_row < 0 skips a row (ragged tail / nothing to write).
 template <int STAGE, int STRIDE, int GROW>
-__device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, long long dst_row, int lane) {   // gJ may carry a column offset
+__device__ __forceinline__ void warp_scatter_rows(const double* wbase, double* gJ, int dst_row, int lane) {   // gJ may carry a column offset
   constexpr int kChunks = STAGE / 2;     // 16-byte chunks per row
   static_assert(kChunks <= 64, "at most two passes of 32 lanes");
   const bool full = __all_sync(0xffffffffu, dst_row >= 0);
   if (full) {
 #pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
-      const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
+      const int d = __shfl_sync(0xffffffffu, dst_row, rr);
       const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
-      double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * GROW);
+      double2* dst = reinterpret_cast<double2*>(gJ + (size_t)(unsigned)d * GROW);
       if (kChunks >= 32 || lane < kChunks) dst[lane] = src[lane];
       if (kChunks > 32 && lane < kChunks - 32) dst[32 + lane] = src[32 + lane];
     }
   } else {
     for (int rr = 0; rr < 32; ++rr) {
-      const long long d = __shfl_sync(0xffffffffu, dst_row, rr);
+      const int d = __shfl_sync(0xffffffffu, dst_row, rr);
       if (d < 0) continue;
       const double2* src = reinterpret_cast<const double2*>(wbase + rr * STRIDE);
       double2* dst = reinterpret_cast<double2*>(gJ + (size_t)d * GROW);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
     if (a.i0) a.i0[dst] = i0;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, (long long)cur.perm, lane);
+  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, cur.perm, lane);
 }
 
 struct RefArgs {
@@ -317,14 +317,14 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
     if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, (long long)cur.perm, lane);              // reference-window half
+  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, cur.perm, lane);              // reference-window half
   __syncwarp();
   if (cur.perm >= 0) {
     if (st == 0) static_rs_row_obs_half(a.knots, pairs, f, adj, row);
     else for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J + kCamHalf, (long long)cur.perm, lane);   // observation-window half
+  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J + kCamHalf, cur.perm, lane);   // observation-window half
 }
 
 // =====================================================================================================================
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
     if (a.i0_so3) a.i0_so3[dst] = ib;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, (long long)perm, lane);
+  if (wantJ) warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, perm, lane);
 }
 
 struct RefSplitArgs {
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
     for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, (long long)perm, lane);
+  if (wantJ) warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, perm, lane);
 }
 
 __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,
