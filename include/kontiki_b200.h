@@ -58,8 +58,14 @@ enum {
   KTK_EVAL_JACOBIANS = 2u,
   KTK_EVAL_ROBUST = 4u,   /* apply ceres::HuberLoss(huber_c) + Corrector to static-RS rows, as Ceres does after Evaluate
                              (static_rscamera_measurement.h:195-197) */
-  KTK_EVAL_SENSOR_JACOBIANS = 8u   /* also fill ktk_group_out.Js: the columns of the sensor's own parameter blocks
+  KTK_EVAL_SENSOR_JACOBIANS = 8u,  /* also fill ktk_group_out.Js: the columns of the sensor's own parameter blocks
                              (sensors/sensors.h:135-165), needed when one of them is unlocked */
+  KTK_EVAL_LOCAL = 16u    /* knot blocks in LOCAL (tangent) coordinates, i.e. after the knots' ceres::LocalParameterization:
+                             SE3 knots 6 columns [upsilon; omega] (LocalParameterizationSE3, uniform_se3_spline_trajectory.h:17-49),
+                             SO3 knots 3 (EigenQuaternionParameterization, uniform_so3_spline_trajectory.h:21), R3 knots 3.
+                             Rows shrink: IMU 4x3x6 = 72; static RS 4x2x6 + 4x2x6 + 2 = 98; split: gyro 36, accel 36 + 36,
+                             static RS 24 + 24 + 24 + 24 + 2 = 98 (ktk_group_row_size_local).  The Gauss-Newton product
+                             entry points below expect ambient rows. */
 };
 
 enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2 };
@@ -139,6 +145,7 @@ int32_t ktk_num_groups(const ktk_problem* p);
 int64_t ktk_group_size(const ktk_problem* p, int32_t group);
 int32_t ktk_group_kind(const ktk_problem* p, int32_t group);
 int32_t ktk_group_row_size(const ktk_problem* p, int32_t group);   /* doubles per packed Jacobian row (84 / 114 / 48) */
+int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t group);   /* ... with KTK_EVAL_LOCAL */
 int64_t ktk_num_knot_doubles(const ktk_problem* p);                /* length of the `knots` argument of ktk_evaluate */
 
 /* One batched evaluation at the parameter point (knots[n_knots*7], rho[n_rho]) with HOST buffers: uploads the point,

@@ -10,7 +10,7 @@ import numpy as np
 from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS = 1, 2, 4, 8
+EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL = 1, 2, 4, 8, 16
 GYROSCOPE, ACCELEROMETER, STATIC_RS = 0, 1, 2
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local"]
 
 _lib = None
 
@@ -76,6 +76,7 @@ def lib():
         L.ktk_expand_static_rs.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5
         L.ktk_set_split_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32]
         L.ktk_group_row_size.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_group_row_size_local.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_num_knot_doubles.argtypes = [C.c_void_p]
         L.ktk_num_knot_doubles.restype = C.c_int64
         L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
@@ -218,14 +219,17 @@ class Problem:
         b = _f64(bias).reshape(3)
         check(lib().ktk_set_group_bias(self._h, int(g), _ptr(b)))
 
-    def alloc_outputs(self, jacobians=True, sensor_jacobians=False):
+    def alloc_outputs(self, jacobians=True, sensor_jacobians=False, local=False):
         """Host (numpy) output arrays for every group, in the C ABI's packed layouts."""
         outs = []
         for g in range(self.num_groups):
             n, cam = self.group_size(g), self.group_kind(g) == STATIC_RS
             o = dict(r=np.zeros((n, 2 if cam else 3)), i0=np.full(n, -1, np.int32))
             if jacobians:
-                o["J"] = np.zeros((n, 4, 3, 7)) if (not cam and not self.split) else np.zeros((n, self.group_row_size(g)))
+                if local:
+                    o["J"] = np.zeros((n, lib().ktk_group_row_size_local(self._h, g)))
+                else:
+                    o["J"] = np.zeros((n, 4, 3, 7)) if (not cam and not self.split) else np.zeros((n, self.group_row_size(g)))
             if cam:
                 o["i0_b"] = np.full(n, -1, np.int32)
             if self.split:
@@ -263,7 +267,7 @@ class Problem:
                 raise ValueError(f"knots must have shape ({self.n_knots}, 7)")
         rho = None if rho is None else _f64(rho)
         if outs is None:
-            outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS), bool(flags & EVAL_SENSOR_JACOBIANS))
+            outs = self.alloc_outputs(bool(flags & EVAL_JACOBIANS), bool(flags & EVAL_SENSOR_JACOBIANS), bool(flags & EVAL_LOCAL))
         arr = self._out_array(outs, _ptr)
         check(lib().ktk_evaluate(self._h, _ptr(knots), _ptr(rho), 0 if rho is None else len(rho), int(flags), arr))
         return outs

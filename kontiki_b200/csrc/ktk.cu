@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
   const int tile = warp_tile();
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
   const ImuIn cur = imu_load(a, tile * 32 + lane);
   if (cur.perm >= 0) {
     const double y[3] = {cur.y0 - a.imu.bias[0], cur.y1 - a.imu.bias[1], cur.y2 - a.imu.bias[2]};   // r = w (y - (model + bias))
@@ -194,12 +195,16 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
       r[0] = r[1] = r[2] = nan("");
       for (int c = 0; c < kImuRow; ++c) row[c] = nan("");
     }
+    else if (local) localize_se3_blocks<3>(row, 4, a.knots + (size_t)i0 * kKnotStride);
     const size_t dst = (size_t)cur.perm;
     if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
     if (a.i0) a.i0[dst] = i0;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, cur.perm, lane);
+  if (wantJ) {
+    if (local) warp_scatter_rows<72, kImuRowStride, 72>(wbase, a.J, cur.perm, lane);
+    else warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, cur.perm, lane);
+  }
 }
 
 struct RefArgs {
@@ -262,6 +267,8 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   const int tile = warp_tile();
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
+  const int grow = local ? 98 : kCamRow;        // doubles per row in global memory: [ref half | obs half | d r/d rho (2)]
   const CamIn cur = cam_load(a, tile * 32 + lane);
   const double ouv[2] = {cur.u, cur.v};
   const bool live = cur.perm >= 0 && cur.ridx >= 0;
@@ -309,22 +316,28 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
       atomicMin(a.err, st);
       r[0] = r[1] = jrho[0] = jrho[1] = nan(""); ir = io = -1;
       for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
-    }
+    } else if (local) localize_se3_blocks<2>(row, 4, a.knots + (size_t)ir * kKnotStride);
     const size_t dst = (size_t)cur.perm;
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
     if (a.i0r) a.i0r[dst] = ir;
     if (a.i0o) a.i0o[dst] = io;
-    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
+    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * grow + (grow - 2)) = make_double2(jrho[0], jrho[1]);
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, cur.perm, lane);              // reference-window half
+  if (wantJ) {                                                                                               // reference-window half
+    if (local) warp_scatter_rows<48, kCamRowStride, 98>(wbase, a.J, cur.perm, lane);
+    else warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J, cur.perm, lane);
+  }
   __syncwarp();
   if (cur.perm >= 0) {
-    if (st == 0) static_rs_row_obs_half(a.knots, pairs, f, adj, row);
+    if (st == 0) { static_rs_row_obs_half(a.knots, pairs, f, adj, row); if (local) localize_se3_blocks<2>(row, 4, a.knots + (size_t)f.io * kKnotStride); }
     else for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J + kCamHalf, cur.perm, lane);   // observation-window half
+  if (wantJ) {                                                                                               // observation-window half
+    if (local) warp_scatter_rows<48, kCamRowStride, 98>(wbase, a.J + 48, cur.perm, lane);
+    else warp_scatter_rows<kCamHalf, kCamRowStride, kCamRow>(wbase, a.J + kCamHalf, cur.perm, lane);
+  }
 }
 
 // =====================================================================================================================
@@ -365,6 +378,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
   const int tile = warp_tile();
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
   const int i = tile * 32 + lane;
   int perm = -1;
   if (i < a.n) {
@@ -377,14 +391,17 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan(""); ia = ib = -1;
       for (int c = 0; c < ROW; ++c) row[c] = nan("");
-    }
+    } else if (local) localize_so3_blocks<3>(row + (WHICH == 0 ? 0 : 36), 4, a.quats + (size_t)ib * kQuatStride);
     const size_t dst = (size_t)perm;
     if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
     if (a.i0_r3) a.i0_r3[dst] = ia;
     if (a.i0_so3) a.i0_so3[dst] = ib;
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, perm, lane);
+  if (wantJ) {
+    if (local) warp_scatter_rows<ROW - 12, STRIDE, ROW - 12>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from 3x4 to 3x3
+    else warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, perm, lane);
+  }
 }
 
 struct RefSplitArgs {
@@ -435,6 +452,8 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
   const int tile = warp_tile();
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
+  const int grow = local ? 98 : kCamRow;
   const int i = tile * 32 + lane;
   const int perm = i < a.n ? a.perm[i] : -1;
   const int myridx = i < a.n ? a.ref_idx[i] : -1;
@@ -457,15 +476,23 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
       atomicMin(a.err, st);
       r[0] = r[1] = jrho[0] = jrho[1] = nan(""); idx[0] = idx[1] = idx[2] = idx[3] = -1;
       for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
+    } else if (local) {      // [ref R3 24 | ref SO3 32 | obs R3 24 | obs SO3 32] -> [24 | 24 | 24 | 24]
+      localize_so3_blocks<2>(row + 24, 4, a.quats + (size_t)idx[2] * kQuatStride);
+      for (int c = 0; c < 24; ++c) row[48 + c] = row[56 + c];
+      localize_so3_blocks<2>(row + 80, 4, a.quats + (size_t)idx[3] * kQuatStride);
+      for (int c = 0; c < 24; ++c) row[72 + c] = row[80 + c];
     }
     const size_t dst = (size_t)perm;
-    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * kCamRow + kCamStage) = make_double2(jrho[0], jrho[1]);
+    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * grow + (grow - 2)) = make_double2(jrho[0], jrho[1]);
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
   }
   __syncwarp();
-  if (wantJ) warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, perm, lane);
+  if (wantJ) {
+    if (local) warp_scatter_rows<96, kCamSplitStride, 98>(wbase, a.J, perm, lane);
+    else warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, perm, lane);
+  }
 }
 
 __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,
@@ -832,10 +859,11 @@ int upload_group(ktk_problem* p, Group& g) {
 }
 
 // doubles per packed Jacobian row / per residual of a group (include/kontiki_b200.h "Layouts")
-int row_doubles(const ktk_problem* p, const Group& g) {
-  if (g.kind == KTK_STATIC_RS) return kCamRow;
-  if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? kGyroSplitRow : kAccelSplitRow;
-  return kImuRow;
+int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
+  const bool local = (flags & KTK_EVAL_LOCAL) != 0;
+  if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
+  if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? (local ? 36 : kGyroSplitRow) : (local ? 72 : kAccelSplitRow);
+  return local ? 72 : kImuRow;
 }
 int res_doubles(const Group& g) { return g.kind == KTK_STATIC_RS ? 2 : 3; }
 
@@ -960,6 +988,7 @@ int64_t ktk_group_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 &&
 int32_t ktk_group_kind(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->kind : -1; }
 int64_t ktk_launch_count(const ktk_problem* p) { return p ? p->launches : 0; }
 int32_t ktk_group_row_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? row_doubles(p, *p->groups[g]) : -1; }
+int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? row_doubles(p, *p->groups[g], KTK_EVAL_LOCAL) : -1; }
 int64_t ktk_num_knot_doubles(const ktk_problem* p) {
   if (!p || !p->have_spline) return 0;
   return p->traj == 1 ? (int64_t)3 * p->spl.n_r3 + (int64_t)4 * p->spl.n_so3 : (int64_t)7 * p->sp.n_knots;
@@ -1181,7 +1210,7 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     const size_t n = (size_t)g.n;
     dev[gi] = ktk_group_out{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (o.r) { if ((st = g.o_r.resize(n * res_doubles(g)))) return st; dev[gi].r = g.o_r.p; }
-    if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize(n * row_doubles(p, g)))) return st; dev[gi].J = g.o_J.p; }
+    if (o.J && (flags & KTK_EVAL_JACOBIANS)) { if ((st = g.o_J.resize(n * row_doubles(p, g, flags)))) return st; dev[gi].J = g.o_J.p; }
     if (o.i0) { if ((st = g.o_i0.resize(n))) return st; dev[gi].i0 = g.o_i0.p; }
     if (o.i0_b) { if ((st = g.o_i0b.resize(n))) return st; dev[gi].i0_b = g.o_i0b.p; }
     if (o.i0_c) { if ((st = g.o_i0c.resize(n))) return st; dev[gi].i0_c = g.o_i0c.p; }
@@ -1195,7 +1224,7 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     const size_t n = (size_t)g.n;
     const bool cam = g.kind == KTK_STATIC_RS, split = p->traj == 1;
     if (dev[gi].r) KTK_CUDA(cudaMemcpyAsync(o.r, dev[gi].r, n * res_doubles(g) * sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, n * row_doubles(p, g) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, n * row_doubles(p, g, flags) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0) KTK_CUDA(cudaMemcpyAsync(o.i0, dev[gi].i0, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_b && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_c && split) KTK_CUDA(cudaMemcpyAsync(o.i0_c, dev[gi].i0_c, n * sizeof(int), cudaMemcpyDeviceToHost, s));

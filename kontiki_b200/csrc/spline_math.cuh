@@ -590,6 +590,52 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
   }
 }
 
+// ---- local (tangent) coordinates -----------------------------------------------------------------------------------------
+// Ceres applies the knots' LocalParameterization to the ambient blocks after Evaluate; KTK_EVAL_LOCAL does it in the kernel.
+// SE3 knot (uniform_se3_spline_trajectory.h:17-49): Plus(T, [upsilon; omega]) = T exp(.), so with q = (v, w):
+//   J_local[:, 0:3] = J[:, 4:7] R(q),   J_local[:, 3:6] = J[:, 0:4] * 1/2 [[w I + hat(v)], [-v^T]]
+// Repacks `nblk` consecutive (N x 7) blocks of knots i0.. into (N x 6) blocks in place, front to back.
+template <int N>
+KB_HD void localize_se3_blocks(double* blocks, int nblk, const double* knot0) {
+  for (int k = 0; k < nblk; ++k) {
+    const double* q = knot0 + (size_t)k * kKnotStride;
+    const M3 R = quat_to_rot(q[0], q[1], q[2], q[3]);
+    double in[N * 7];
+#pragma unroll
+    for (int i = 0; i < N * 7; ++i) in[i] = blocks[k * N * 7 + i];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      const double* j = in + 7 * r;
+      double* o = blocks + k * N * 6 + 6 * r;
+      o[0] = j[4] * R.a[0] + j[5] * R.a[3] + j[6] * R.a[6];
+      o[1] = j[4] * R.a[1] + j[5] * R.a[4] + j[6] * R.a[7];
+      o[2] = j[4] * R.a[2] + j[5] * R.a[5] + j[6] * R.a[8];
+      o[3] = 0.5 * (j[0] * q[3] + j[1] * q[2] - j[2] * q[1] - j[3] * q[0]);
+      o[4] = 0.5 * (-j[0] * q[2] + j[1] * q[3] + j[2] * q[0] - j[3] * q[1]);
+      o[5] = 0.5 * (j[0] * q[1] - j[1] * q[0] + j[2] * q[3] - j[3] * q[2]);
+    }
+  }
+}
+// SO3 knot (ceres::EigenQuaternionParameterization, uniform_so3_spline_trajectory.h:21): Plus(q, d) = q_d q, d the half-angle
+// vector:  J_local = J [[w I - hat(v)], [-v^T]].   (N x 4) -> (N x 3) in place.
+template <int N>
+KB_HD void localize_so3_blocks(double* blocks, int nblk, const double* quat0) {
+  for (int k = 0; k < nblk; ++k) {
+    const double* q = quat0 + (size_t)k * 4;
+    double in[N * 4];
+#pragma unroll
+    for (int i = 0; i < N * 4; ++i) in[i] = blocks[k * N * 4 + i];
+#pragma unroll
+    for (int r = 0; r < N; ++r) {
+      const double* j = in + 4 * r;
+      double* o = blocks + k * N * 3 + 3 * r;
+      o[0] = j[0] * q[3] - j[1] * q[2] + j[2] * q[1] - j[3] * q[0];
+      o[1] = j[0] * q[2] + j[1] * q[3] - j[2] * q[0] - j[3] * q[1];
+      o[2] = -j[0] * q[1] + j[1] * q[0] + j[2] * q[3] - j[3] * q[2];
+    }
+  }
+}
+
 // =================================================================================================================
 // Row drivers: everything one measurement does, from its record to its residual / packed Jacobian row.
 // `knots` / `pairs` are indexable by GLOBAL knot index.

@@ -361,3 +361,54 @@ def test_unlocked_sensors_se3_match_oracle():
     assert parity.rel_err(Js, o["Ja"]) < parity.TOL
     for a, b in ((0, 8), (8, 14), (14, 16)):
         assert parity.rel_err(out["Js"][:, a:b], o["Js"][:, a:b]) < parity.TOL
+
+
+# ---- KTK_EVAL_LOCAL: knot blocks after the knots' LocalParameterization ------------------------------------------------------
+def test_local_coordinates_equal_ambient_times_plus_jacobian():
+    """J_local = J_ambient * dPlus/ddelta (LocalParameterizationSE3 uniform_se3_spline_trajectory.h:25-48; EigenQuaternionParameterization
+    for SO3 knots), which is what Ceres forms after Evaluate; the ambient rows are already parity-gated against the oracle."""
+    from kontiki_b200.estimator import _quat_plus_jacobian, _se3_plus_jacobian
+    cfg = syn.make_config("H1", scale=0.004)
+    c = cfg["cam"]
+    p, g = _problem(cfg)
+    amb = p.evaluate(cfg["knots"], c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST)
+    loc = p.evaluate(cfg["knots"], c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST | _lib.EVAL_LOCAL)
+    P = _se3_plus_jacobian(cfg["knots"])
+    for name in ("gyro", "accel"):
+        a, l = amb[g[name]], loc[g[name]]
+        assert np.array_equal(a["r"], l["r"])
+        ref = np.einsum("nkra,nkad->nkrd", a["J"], P[a["i0"][:, None] + np.arange(4)])
+        assert parity.rel_err(l["J"].reshape(-1, 4, 3, 6), ref) < 1e-12
+    a, l = amb[g["cam"]], loc[g["cam"]]
+    n = len(a["r"])
+    assert l["J"].shape == (n, 98)
+    ref_r = np.einsum("nkra,nkad->nkrd", a["J"][:, :56].reshape(n, 4, 2, 7), P[a["i0"][:, None] + np.arange(4)])
+    ref_o = np.einsum("nkra,nkad->nkrd", a["J"][:, 56:112].reshape(n, 4, 2, 7), P[a["i0_b"][:, None] + np.arange(4)])
+    assert parity.rel_err(l["J"][:, :48].reshape(n, 4, 2, 6), ref_r) < 1e-12
+    assert parity.rel_err(l["J"][:, 48:96].reshape(n, 4, 2, 6), ref_o) < 1e-12
+    assert np.array_equal(l["J"][:, 96:98], a["J"][:, 112:114])
+    # split trajectory
+    s = _split_case(scale_imu=500, n_lm=60)
+    cam = s["cam"]
+    p = _lib.Problem(0)
+    p.set_split_spline(s["dt_a"], s["t0_a"], len(s["vecs"]), s["dt_b"], s["t0_b"], len(s["quats"]))
+    imu = _lib.make_sensor()
+    gg = p.add_gyroscope(imu, s["t"], s["y"], s["w"])
+    ga = p.add_accelerometer(imu, s["t"], s["y"], s["w"])
+    gc = p.add_static_rs(_lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"]), cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"],
+                         cam["lm_idx"], cam["weight"], cam["huber_c"])
+    amb = p.evaluate((s["vecs"], s["quats"]), cam["rho"], 3)
+    loc = p.evaluate((s["vecs"], s["quats"]), cam["rho"], 3 | _lib.EVAL_LOCAL)
+    Pq = _quat_plus_jacobian(s["quats"])
+    n = len(s["t"])
+    ref = np.einsum("nkra,nkad->nkrd", amb[gg]["J"].reshape(n, 4, 3, 4), Pq[amb[gg]["i0_c"][:, None] + np.arange(4)])
+    assert loc[gg]["J"].shape == (n, 36) and parity.rel_err(loc[gg]["J"].reshape(n, 4, 3, 3), ref) < 1e-12
+    ref = np.einsum("nkra,nkad->nkrd", amb[ga]["J"][:, 36:].reshape(n, 4, 3, 4), Pq[amb[ga]["i0_c"][:, None] + np.arange(4)])
+    assert np.array_equal(loc[ga]["J"][:, :36], amb[ga]["J"][:, :36]) and parity.rel_err(loc[ga]["J"][:, 36:].reshape(n, 4, 3, 3), ref) < 1e-12
+    a, l = amb[gc], loc[gc]
+    n = len(a["r"])
+    assert np.array_equal(l["J"][:, 0:24], a["J"][:, 0:24]) and np.array_equal(l["J"][:, 48:72], a["J"][:, 56:80]) and np.array_equal(l["J"][:, 96:98], a["J"][:, 112:114])
+    ref = np.einsum("nkra,nkad->nkrd", a["J"][:, 24:56].reshape(n, 4, 2, 4), Pq[a["i0_c"][:, None] + np.arange(4)])
+    assert parity.rel_err(l["J"][:, 24:48].reshape(n, 4, 2, 3), ref) < 1e-12
+    ref = np.einsum("nkra,nkad->nkrd", a["J"][:, 80:112].reshape(n, 4, 2, 4), Pq[a["i0_d"][:, None] + np.arange(4)])
+    assert parity.rel_err(l["J"][:, 72:96].reshape(n, 4, 2, 3), ref) < 1e-12
