@@ -165,6 +165,9 @@ int ktk_synchronize(ktk_problem* p);
  * orientation x,y,z,w (4) | angular velocity in the world frame (3); status[n] per time (KTK_ERANGE where the reference
  * throws std::range_error, rows NaN).  Returns the worst status. */
 int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status);
+/* UniformSE3SplineTrajectory.evaluate(t) (python/src/kontiki/trajectories/py_uniform_se3_spline_trajectory.cc:53-60): out[48 n] =
+ * the 4x4 matrices P | P' | P'' of EvaluateSpline (uniform_se3_spline_trajectory.h:101-194), row-major. */
+int ktk_se3_evaluate_matrices(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status);
 
 /* Number of kernel launches ktk_evaluate_device enqueued since the problem was created. */
 int64_t ktk_launch_count(const ktk_problem* p);

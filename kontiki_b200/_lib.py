@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices"]
 
 _lib = None
 
@@ -87,6 +87,7 @@ def lib():
         L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p]
         L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_graphs.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_se3_evaluate_matrices.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_group_sensor.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Sensor)]
         L.ktk_set_group_bias.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -290,6 +291,13 @@ class Problem:
         out, st = np.zeros((len(t), 16)), np.zeros(len(t), np.int32)
         check(lib().ktk_traj_evaluate(self._h, _ptr(kf), len(t), _ptr(t), _ptr(out), _ptr(st)))
         return dict(position=out[:, 0:3], velocity=out[:, 3:6], acceleration=out[:, 6:9], orientation=out[:, 9:13], angular_velocity=out[:, 13:16])
+
+    def se3_evaluate_matrices(self, knots, t):
+        kf = self._flat_knots(knots)
+        t = _f64(np.atleast_1d(t))
+        out, st = np.zeros((len(t), 3, 4, 4)), np.zeros(len(t), np.int32)
+        check(lib().ktk_se3_evaluate_matrices(self._h, _ptr(kf), len(t), _ptr(t), _ptr(out), _ptr(st)))
+        return out
 
     def evaluate_flat(self, knots_flat, rho, flags, outs):
         """ktk_evaluate on an already flattened float64 knot array (the C ABI's layout); outs as from alloc_outputs()."""

@@ -504,6 +504,15 @@ __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots
   for (int c = 0; c < 16; ++c) out[16 * (size_t)i + c] = st == 0 ? o[c] : nan("");
   status[i] = st;
 }
+__global__ void k_traj_eval_se3_matrices(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,
+                                         double* __restrict__ out, int* __restrict__ status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double o[48];
+  const int st = traj_eval_se3_matrices(sp, knots, pairs, t[i], o);
+  for (int c = 0; c < 48; ++c) out[48 * (size_t)i + c] = st == 0 ? o[c] : nan("");
+  status[i] = st;
+}
 __global__ void k_traj_eval_split(SplitConst sp, const double* __restrict__ vecs, const double* __restrict__ quats, const double* __restrict__ pairs, int n,
                                   const double* __restrict__ t, double* __restrict__ out, int* __restrict__ status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1234,7 +1243,15 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
   return ktk_synchronize(p);
 }
 
+static int traj_evaluate_impl(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status, int width);
 int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status) {
+  return traj_evaluate_impl(p, knots, n, t, out, status, 16);
+}
+int ktk_se3_evaluate_matrices(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status) {
+  if (p && p->traj != 0) return fail(KTK_EINVAL, "not a UniformSE3SplineTrajectory");
+  return traj_evaluate_impl(p, knots, n, t, out, status, 48);
+}
+static int traj_evaluate_impl(ktk_problem* p, const double* knots, int64_t n, const double* t, double* out, int32_t* status, int width) {
   if (!p || !knots || (n > 0 && (!t || !out || !status))) return fail(KTK_EINVAL, "NULL argument");
   if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set before evaluation");
   if (p->device < 0) return fail(KTK_ECUDA, "this problem was created without a device; there is no CPU evaluation path");
@@ -1244,7 +1261,7 @@ int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const doub
   int st;
   const size_t nkd = (size_t)ktk_num_knot_doubles(p);
   DevBuf<double> d_t, d_out; DevBuf<int> d_st;
-  if ((st = p->d_knots7.resize(nkd)) || (st = d_t.resize((size_t)n)) || (st = d_out.resize((size_t)n * 16)) || (st = d_st.resize((size_t)n))) return st;
+  if ((st = p->d_knots7.resize(nkd)) || (st = d_t.resize((size_t)n)) || (st = d_out.resize((size_t)n * width)) || (st = d_st.resize((size_t)n))) return st;
   KTK_CUDA(cudaMemcpyAsync(p->d_knots7.p, knots, nkd * sizeof(double), cudaMemcpyHostToDevice, s));
   KTK_CUDA(cudaMemcpyAsync(d_t.p, t, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
   KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
@@ -1254,7 +1271,8 @@ int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const doub
     if ((st = p->d_knots8.resize((size_t)nk * kKnotStride)) || (st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
     k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p);
     k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
-    k_traj_eval_se3<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
+    if (width == 16) k_traj_eval_se3<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
+    else k_traj_eval_se3_matrices<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
   } else {
     const SplitConst& sp = p->spl;
     const double* d_quats = p->d_knots7.p + (size_t)3 * sp.n_r3;
@@ -1265,7 +1283,7 @@ int ktk_traj_evaluate(ktk_problem* p, const double* knots, int64_t n, const doub
   }
   p->launches += 3;
   KTK_CUDA(cudaGetLastError());
-  KTK_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * 16 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  KTK_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
   KTK_CUDA(cudaMemcpyAsync(status, d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));
   KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
   KTK_CUDA(cudaStreamSynchronize(s));

@@ -44,6 +44,32 @@ KB_HD void se3_body_twist3(const double* p1, const double* p2, const double* p3,
   }
 }
 
+// UniformSE3SplineTrajectory.evaluate(t) of the reference's Python API (py_uniform_se3_spline_trajectory.cc:53-60): the 4x4
+// matrices P, P', P'' of EvaluateSpline with every flag set (uniform_se3_spline_trajectory.h:101-194):
+//   P' = P s^,   P'' = P (s^ s^ + s'^)     with the body twist s = [v; w] and hat([v; w]) = [[hat w, v], [0, 0]].
+// out[48] = P | P' | P'' row-major.
+KB_HD int traj_eval_se3_matrices(const SplineConst& sp, const double* knots, const double* pairs, double t, double* out) {
+  Segment sg; sg.start = 0; sg.n = sp.n_knots;
+  int i0; double u;
+  if (!segment_locate(sg, t, sp.t0, sp.dt, i0, u)) return kStatusRange;
+  const Basis bs = cumulative_basis(u, sp.dt);
+  const double* p1 = pairs + (size_t)(i0 + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  Pose P; pose_forward(knots + (size_t)i0 * kKnotStride, p1, p2, p3, bs, P);
+  Tw s, ds, dds;
+  se3_body_twist3(p1, p2, p3, bs, sp.dt, s, ds, dds);
+  const M3 hw = hat(s.w);
+  const M3 R1 = P.R * hw, R2 = P.R * (hw * hw + hat(ds.w));
+  const V3 t1 = P.R * s.u, t2 = P.R * (cross(s.w, s.u) + ds.u);
+  for (int i = 0; i < 48; ++i) out[i] = 0.0;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) { out[4 * i + j] = P.R.a[3 * i + j]; out[16 + 4 * i + j] = R1.a[3 * i + j]; out[32 + 4 * i + j] = R2.a[3 * i + j]; }
+  }
+  out[3] = P.p.x; out[7] = P.p.y; out[11] = P.p.z; out[15] = 1.0;
+  out[16 + 3] = t1.x; out[16 + 7] = t1.y; out[16 + 11] = t1.z;
+  out[32 + 3] = t2.x; out[32 + 7] = t2.y; out[32 + 11] = t2.z;
+  return 0;
+}
+
 // d r / d time_offset of a gyroscope (which = 0) / accelerometer (which = 1) row on SE3; out[3].
 // Returns a status like imu_row.  compat_zero_dB accelerometer rows are refused (the reference's Jet path differentiates
 // an expression whose dB was never assigned; its time derivative is not the derivative of the intended accelerometer).

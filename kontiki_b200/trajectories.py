@@ -182,6 +182,14 @@ class UniformSE3SplineTrajectory(_Spline):
         p.set_se3_spline(self._dt, self._t0, len(self._cp), self.compat_zero_dB)
         return p.traj_evaluate(self._cp, [float(t)])
 
+    def evaluate(self, t):
+        """(P, P', P'') as 4x4 matrices (py_uniform_se3_spline_trajectory.cc:53-60)."""
+        self._check()
+        p = _lib.Problem(0)
+        p.set_se3_spline(self._dt, self._t0, len(self._cp), False)
+        m = p.se3_evaluate_matrices(self._cp, [float(t)])[0]
+        return m[0], m[1], m[2]
+
 
 class UniformR3SplineTrajectory(_Spline):
     _width = 3

@@ -159,4 +159,10 @@ void hc_static_rs_sensor_se3(double t0, double dt, int n_knots, const double* K,
                                          huber_c ? huber_c[i] : 0.0, out + 16 * i);
 }
 
+
+void hc_se3_matrices(double t0, double dt, int n_knots, const double* knots8, const double* pairs, int n, const double* t, double* out, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  for (int i = 0; i < n; ++i) status[i] = traj_eval_se3_matrices(sp, knots8, pairs, t[i], out + 48 * i);
+}
+
 }  // extern "C"

@@ -181,3 +181,11 @@ def static_rs_sensor_se3(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm
                                   C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows), _p(k8), _p(pairs), n,
                                   _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc), _p(out), _p(st))
     return out, st
+
+
+def se3_matrices(knots7, dt, t0, t):
+    k8, pairs = prepass(knots7)
+    t = _f(np.atleast_1d(t))
+    out, st = np.zeros((len(t), 3, 4, 4)), np.zeros(len(t), np.int32)
+    lib().hc_se3_matrices(C.c_double(t0), C.c_double(dt), len(k8), _p(k8), _p(pairs), len(t), _p(t), _p(out), _p(st))
+    return out, st

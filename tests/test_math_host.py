@@ -152,3 +152,38 @@ def test_camera_sensor_jacobians_match_oracle(robust):
             Js[i, 0:8], Js[i, 8:14], Js[i, 14:16] = J2[:, 0:4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7]
     for a, b in ((0, 8), (8, 14), (14, 16)):
         assert parity.rel_err(out[:, a:b], Js[:, a:b]) < parity.TOL
+
+
+def test_se3_evaluate_matrices_match_oracle():
+    """UniformSE3SplineTrajectory.evaluate(t) -> (P, P', P'') (py_uniform_se3_spline_trajectory.cc:53-60) on the reference's fixture."""
+    t = np.linspace(fx.SE3_T0, fx.SE3_T0 + 3 * fx.SE3_DT - 1e-9, 33)
+    P, Pp, Pb = kto.se3_evaluate_matrices(kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS), t)
+    out, st = hc.se3_matrices(fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t)
+    assert (st == 0).all()
+    for a, b in ((out[:, 0], P), (out[:, 1], Pp), (out[:, 2], Pb)):
+        assert np.abs(a - b).max() <= 1e-12 * max(1.0, np.abs(b).max())
+
+
+def test_traj_point_queries_match_oracle():
+    Pf, V, A, Q, W = 1, 2, 4, 8, 16
+    traj = kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS)
+    t = np.linspace(traj.min_time, traj.max_time - 1e-6, 40)
+    o = kto.traj_evaluate(traj, t, Pf | V | A | Q | W)
+    out, st = hc.traj_eval_se3(fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t)
+    assert (st == 0).all()
+    q = out[:, 9:13] * np.sign((out[:, 9:13] * o["orientation"]).sum(1))[:, None]
+    for a, b in ((out[:, 0:3], o["position"]), (out[:, 3:6], o["velocity"]), (out[:, 6:9], o["acceleration"]), (q, o["orientation"]),
+                 (out[:, 13:16], o["angular_velocity"])):
+        assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())
+    # compat_zero_dB: what the reference's Jet path gives for acceleration(t) alone (flags = EvalAcceleration, dB unassigned)
+    oc = kto.traj_evaluate(kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS, compat_zero_dB=True), t, A)
+    outc, _ = hc.traj_eval_se3(fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t, compat=True)
+    assert np.abs(outc[:, 6:9] - oc["acceleration"]).max() < 1e-12 * np.abs(oc["acceleration"]).max()
+    straj = kto.Traj(kto.SPLIT, fx.R3_DT, fx.R3_T0, fx.R3_KNOTS, fx.SO3_DT, fx.SO3_T0, fx.SO3_KNOTS)
+    t = np.linspace(straj.min_time, straj.max_time - 1e-6, 40)
+    o = kto.traj_evaluate(straj, t, Pf | V | A | Q | W)
+    out, st = hc.traj_eval_split(fx.R3_KNOTS, fx.R3_DT, fx.R3_T0, fx.SO3_KNOTS, fx.SO3_DT, fx.SO3_T0, t)
+    assert (st == 0).all()
+    for a, b in ((out[:, 0:3], o["position"]), (out[:, 3:6], o["velocity"]), (out[:, 6:9], o["acceleration"]), (out[:, 9:13], o["orientation"]),
+                 (out[:, 13:16], o["angular_velocity"])):
+        assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())

@@ -63,6 +63,17 @@ def test_world_frame_round_trip_and_convention():
     assert np.allclose(traj.from_world(traj.to_world(X, t), t), X, atol=1e-12)
 
 
+def test_se3_evaluate_matrices():
+    """py_uniform_se3_spline_trajectory.cc:53-60: P' by central differences of P, velocity = P'[:3, 3]."""
+    traj = se3_fixture()
+    t, h = traj.min_time + 2.0, 1e-6
+    P, Pp, Pb = traj.evaluate(t)
+    assert np.allclose(P[:3, 3], traj.position(t), atol=1e-12) and np.allclose(Pp[:3, 3], traj.velocity(t), atol=1e-12)
+    assert np.allclose(Pb[:3, 3], traj.acceleration(t), atol=1e-12)
+    assert np.allclose(Pp, (traj.evaluate(t + h)[0] - traj.evaluate(t - h)[0]) / (2 * h), atol=1e-6)
+    assert np.allclose(Pb, (traj.evaluate(t + h)[1] - traj.evaluate(t - h)[1]) / (2 * h), atol=1e-6)
+
+
 def test_spline_container_api_and_errors():
     """spline_helpers.h:26-48; std::range_error / std::domain_error -> ValueError (test_spline_trajectories.py:151-155,227-253)."""
     traj = UniformR3SplineTrajectory(0.5, 1.0)
