@@ -40,10 +40,13 @@ def parse():
     ap.add_argument("--workload", default="H1")
     ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--row-order", default="caller", choices=["caller", "device"],
+                    help="row order of the device-resident leg: the caller's insertion order (default, what the drop-in contract documents) or "
+                         "KTK_EVAL_DEVICE_ORDER (rows sorted by first knot, one TMA bulk store per warp tile)")
     return ap.parse_args()
 
 
-def workload_config(name, cfg):
+def workload_config(name, cfg, row_order="caller"):
     from kontiki_b200 import synthetic as syn
     traj = "SplitTrajectory (UniformR3 + UniformSO3)" if cfg.get("split") else "UniformSE3SplineTrajectory"
     return {"workload": f"{name}: {traj} {len(cfg['knots'])} knots dt={cfg['dt']}, "
@@ -53,7 +56,8 @@ def workload_config(name, cfg):
             "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
             "jacobian": "ambient (7 per SE3 knot; 3 + 4 per split knot), Huber corrector applied to camera rows",
             "l2": "per-step working set (outputs + records) >> 126 MB L2; no flush",
-            "sharding": "measurements sharded across ranks, knots replicated, no data-path collective"}
+            "sharding": "measurements sharded across ranks, knots replicated, no data-path collective",
+            "row_order": row_order}
 
 
 # ---- CPU oracle leg (cpu_baseline and --impl reference) ------------------------------------------------------------
@@ -235,8 +239,10 @@ def main():
         d_outs.append(dict(r=r.data_ptr(), J=J.data_ptr(), i0=idx[0].data_ptr(), i0_b=idx[1].data_ptr() if cam else None,
                            i0_c=idx[2].data_ptr() if cfg.get("split") else None, i0_d=idx[3].data_ptr() if (cfg.get("split") and cam) else None))
 
+    dev_flags = flags | (_lib.EVAL_DEVICE_ORDER if a.row_order == "device" else 0)
+
     def step_device():
-        p.evaluate_device(d_knots.data_ptr(), d_rho.data_ptr() if d_rho is not None else 0, 0 if rho is None else len(rho), flags, d_outs)
+        p.evaluate_device(d_knots.data_ptr(), d_rho.data_ptr() if d_rho is not None else 0, 0 if rho is None else len(rho), dev_flags, d_outs)
 
     def barrier():
         if dist is not None:
@@ -335,7 +341,7 @@ def main():
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a.workload, cfg),
+            "config": workload_config(a.workload, cfg, a.row_order),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
             "gpu_launches": int(launches),

@@ -60,6 +60,11 @@ enum {
                              (static_rscamera_measurement.h:195-197) */
   KTK_EVAL_SENSOR_JACOBIANS = 8u,  /* also fill ktk_group_out.Js: the columns of the sensor's own parameter blocks
                              (sensors/sensors.h:135-165), needed when one of them is unlocked */
+  KTK_EVAL_DEVICE_ORDER = 32u,   /* write row k of every output array in DEVICE order (rows sorted by first active knot) instead of the
+                             caller's insertion order; ktk_get_row_order() gives the insertion index of device row k.  The values
+                             are bit-identical to the default, permuted.  This is the fast layout for device-side consumers (the
+                             Gauss-Newton products below take the same flag): a warp's 32 rows are one contiguous block and
+                             leave the SM with one TMA bulk store instead of a scatter. */
   KTK_EVAL_LOCAL = 16u    /* knot blocks in LOCAL (tangent) coordinates, i.e. after the knots' ceres::LocalParameterization:
                              SE3 knots 6 columns [upsilon; omega] (LocalParameterizationSE3, uniform_se3_spline_trajectory.h:17-49),
                              SO3 knots 3 (EigenQuaternionParameterization, uniform_so3_spline_trajectory.h:21), R3 knots 3.
@@ -184,14 +189,19 @@ int64_t ktk_launch_count(const ktk_problem* p);
  * All asynchronous on the problem's stream.  With rows sharded over several GPUs, the sum over ranks of d_y is the
  * full product: one ncclAllReduce of ktk_num_parameters() doubles per product (kontiki_b200/gn.py). */
 int64_t ktk_num_parameters(const ktk_problem* p, int64_t n_rho);
-int ktk_j_apply(ktk_problem* p, const ktk_group_out* d_outs, const double* d_v, double* const* d_u);
-int ktk_jt_apply(ktk_problem* p, const ktk_group_out* d_outs, double* const* d_u, double* d_y);
-int ktk_jtj_diagonal(ktk_problem* p, const ktk_group_out* d_outs, double* d_y);
+int ktk_j_apply(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, const double* d_v, double* const* d_u);
+int ktk_jt_apply(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, double* const* d_u, double* d_y);
+int ktk_jtj_diagonal(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, double* d_y);
 /* diag(P^T J^T J P) in LOCAL (tangent) coordinates, laid out [6 per SE3 knot | rho] or [3 per R3 knot | 3 per SO3 knot |
  * rho]: d_Pa = d Plus/d delta of every SE3 knot (n x 7 x 6, row-major; LocalParameterizationSE3,
  * uniform_se3_spline_trajectory.h:25-48), d_Pb = the same for SO3 knots (n_so3 x 4 x 3; ceres::EigenQuaternionParameterization,
  * uniform_so3_spline_trajectory.h:21); NULL where the trajectory has no such spline. */
-int ktk_jtj_diagonal_local(ktk_problem* p, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y);
+int ktk_jtj_diagonal_local(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y);
+/* (flags: 0, or KTK_EVAL_DEVICE_ORDER if the rows were written with it.) */
+
+/* order[k] = insertion index (0-based, within the group) of the k-th row in device order.  Fixed once the group has been
+ * uploaded (first evaluation, or this call); changes only if the spline grid or the sensor's time offset is changed. */
+int ktk_get_row_order(ktk_problem* p, int32_t group, int32_t* order);
 
 /* Kernel timing for bench.py's roofline: while on, every kernel launch of a measurement group is bracketed by CUDA
  * events on the problem's stream; ktk_read_profile synchronises, returns the summed device time (ms) and the number

@@ -10,7 +10,7 @@ import numpy as np
 from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
-EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL = 1, 2, 4, 8, 16
+EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL, EVAL_DEVICE_ORDER = 1, 2, 4, 8, 16, 32
 GYROSCOPE, ACCELEROMETER, STATIC_RS = 0, 1, 2
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -32,7 +32,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order"]
 
 _lib = None
 
@@ -82,10 +82,11 @@ def lib():
         L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
         L.ktk_num_parameters.argtypes = [C.c_void_p, C.c_int64]
         L.ktk_num_parameters.restype = C.c_int64
-        L.ktk_j_apply.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.POINTER(C.c_void_p)]
-        L.ktk_jt_apply.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.POINTER(C.c_void_p), C.c_void_p]
-        L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p]
-        L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_j_apply.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(GroupOut), C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ktk_jt_apply.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(GroupOut), C.POINTER(C.c_void_p), C.c_void_p]
+        L.ktk_jtj_diagonal.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(GroupOut), C.c_void_p]
+        L.ktk_get_row_order.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.ktk_jtj_diagonal_local.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(GroupOut), C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_graphs.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_se3_evaluate_matrices.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_group_sensor.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Sensor)]
@@ -331,17 +332,22 @@ class Problem:
             arr[i] = None if not q else int(q)
         return arr
 
-    def j_apply(self, d_outs, d_v, d_u):
-        check(lib().ktk_j_apply(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_v)), self._ptr_array(d_u)))
+    def j_apply(self, d_outs, d_v, d_u, flags=0):
+        check(lib().ktk_j_apply(self._h, int(flags), self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_v)), self._ptr_array(d_u)))
 
-    def jt_apply(self, d_outs, d_u, d_y):
-        check(lib().ktk_jt_apply(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), self._ptr_array(d_u), C.c_void_p(int(d_y))))
+    def jt_apply(self, d_outs, d_u, d_y, flags=0):
+        check(lib().ktk_jt_apply(self._h, int(flags), self._out_array(d_outs, lambda q: None if q is None else int(q)), self._ptr_array(d_u), C.c_void_p(int(d_y))))
 
-    def jtj_diagonal(self, d_outs, d_y):
-        check(lib().ktk_jtj_diagonal(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_y))))
+    def jtj_diagonal(self, d_outs, d_y, flags=0):
+        check(lib().ktk_jtj_diagonal(self._h, int(flags), self._out_array(d_outs, lambda q: None if q is None else int(q)), C.c_void_p(int(d_y))))
 
-    def jtj_diagonal_local(self, d_outs, d_Pa, d_Pb, d_y):
-        check(lib().ktk_jtj_diagonal_local(self._h, self._out_array(d_outs, lambda q: None if q is None else int(q)), None if not d_Pa else C.c_void_p(int(d_Pa)),
+    def get_row_order(self, g):
+        order = np.zeros(self.group_size(g), np.int32)
+        check(lib().ktk_get_row_order(self._h, int(g), _ptr(order)))
+        return order
+
+    def jtj_diagonal_local(self, d_outs, d_Pa, d_Pb, d_y, flags=0):
+        check(lib().ktk_jtj_diagonal_local(self._h, int(flags), self._out_array(d_outs, lambda q: None if q is None else int(q)), None if not d_Pa else C.c_void_p(int(d_Pa)),
                                            None if not d_Pb else C.c_void_p(int(d_Pb)), C.c_void_p(int(d_y))))
 
     def synchronize(self):

@@ -170,7 +170,10 @@ struct ImuArgs {
 struct ImuIn { double t, y0, y1, y2, w; int perm; };
 __device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
   ImuIn in; in.perm = -1; in.t = 0; in.y0 = in.y1 = in.y2 = 0; in.w = 0;
-  if (i < a.n) { in.t = a.t[i]; in.y0 = a.y[3 * (size_t)i]; in.y1 = a.y[3 * (size_t)i + 1]; in.y2 = a.y[3 * (size_t)i + 2]; in.w = a.w[i]; in.perm = a.perm[i]; }
+  if (i < a.n) {
+    in.t = a.t[i]; in.y0 = a.y[3 * (size_t)i]; in.y1 = a.y[3 * (size_t)i + 1]; in.y2 = a.y[3 * (size_t)i + 2]; in.w = a.w[i];
+    in.perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];      // destination row: device order or the caller's insertion order
+  }
   return in;
 }
 
@@ -254,7 +257,8 @@ __device__ __forceinline__ CamIn cam_load(const CamArgs& a, int i) {
   CamIn in; in.perm = -1; in.ridx = -1; in.u = in.v = in.obs_t0 = in.ref_t0 = in.w = in.huber = 0;
   if (i < a.n) {
     in.u = a.obs_uv[2 * (size_t)i]; in.v = a.obs_uv[2 * (size_t)i + 1]; in.obs_t0 = a.obs_t0[i]; in.ref_t0 = a.ref_t0[i]; in.w = a.w[i];
-    in.huber = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0; in.ridx = a.ref_idx[i]; in.perm = a.perm[i];
+    in.huber = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0; in.ridx = a.ref_idx[i];
+    in.perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
   }
   return in;
 }
@@ -340,6 +344,55 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   }
 }
 
+// Device-order variant (KTK_EVAL_DEVICE_ORDER, ambient rows): row k of the output is the k-th row in DEVICE order (sorted by
+// first knot; ktk_get_row_order gives the insertion index).  A warp's 32 rows are then one contiguous 32 x 912 B block of the
+// output: the rows are staged whole and leave with ONE TMA bulk store issued by lane 0 -- no scatter loop, no per-row address
+// arithmetic, and the residual / index stores are coalesced.
+constexpr int kCamDevStride = 114, kRefInRowDev = 22;      // record at 22..113: block k read at 30 + 21 k, written at 14 k
+__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_dev(const CamArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kCamDevStride;
+  double* row = wbase + lane * kCamDevStride;
+  const int tile = warp_tile();
+  if (tile * 32 >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const int i = tile * 32 + lane;
+  const CamIn cur = cam_load(a, i);
+  const double ouv[2] = {cur.u, cur.v};
+  warp_gather_records<kRefStride, kCamDevStride, kRefInRowDev>(wbase, a.recs, cur.ridx, lane);
+  ObsForward f; f.status = kStatusRange; f.io = -1;
+  if (cur.perm >= 0 && cur.ridx >= 0) {
+    static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
+    static_rs_row_pose(a.knots, a.pairs, f);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  if (cur.perm >= 0) {
+    double r[2], jrho[2];
+    int ir = -1, io = -1;
+    ObsAdjoint adj;
+    const int st = static_rs_row_ref_half(a.cam, f, row + kRefInRowDev, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io, adj);
+    if (st == 0) {
+      static_rs_row_obs_half(a.knots, a.pairs, f, adj, row + kCamHalf);
+      row[112] = jrho[0]; row[113] = jrho[1];
+    } else {
+      atomicMin(a.err, st);
+      r[0] = r[1] = nan(""); ir = io = -1;
+      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+    }
+    if (a.r) { a.r[2 * (size_t)i] = r[0]; a.r[2 * (size_t)i + 1] = r[1]; }
+    if (a.i0r) a.i0r[i] = ir;
+    if (a.i0o) a.i0o[i] = io;
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (wantJ && lane == 0) {
+    bulk_store(a.J + (size_t)tile * 32 * kCamRow, wbase, (unsigned)(min(32, a.n - tile * 32) * kCamRow * 8));
+    bulk_store_wait_read();
+  }
+}
+
 // =====================================================================================================================
 // Split trajectory (R3 + SO3) kernels: same tiling and data movement as above, rows of 48 / 84 / 114 doubles.
 // =====================================================================================================================
@@ -382,7 +435,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
   const int i = tile * 32 + lane;
   int perm = -1;
   if (i < a.n) {
-    perm = a.perm[i];
+    perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
     const double y[3] = {a.y[3 * (size_t)i] - a.imu.bias[0], a.y[3 * (size_t)i + 1] - a.imu.bias[1], a.y[3 * (size_t)i + 2] - a.imu.bias[2]};
     double r[3];
     int ia = -1, ib = -1;
@@ -455,7 +508,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
   const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
   const int grow = local ? 98 : kCamRow;
   const int i = tile * 32 + lane;
-  const int perm = i < a.n ? a.perm[i] : -1;
+  const int perm = i < a.n ? ((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]) : -1;
   const int myridx = i < a.n ? a.ref_idx[i] : -1;
   warp_gather_records<kRefSplitStride, kCamSplitStride, kRefSplitInRow>(wbase, a.recs, myridx, lane);
   double ouv[2] = {0.0, 0.0};
@@ -654,7 +707,7 @@ __global__ void k_jt_apply(const ApplyArgs a) {
 struct ImuSensorArgs {
   int traj, which; SplineConst sp; SplitConst spl; ImuConst imu;
   const double* knots; const double* pairs; const double* vecs; const double* quats; const double* so3pairs;
-  const double* t; const double* w; const int* perm; int n; double* Js; int* err;
+  const double* t; const double* w; const int* perm; int n; double* Js; int* err; int device_order;
 };
 __global__ void k_imu_sensor(const ImuSensorArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -663,7 +716,7 @@ __global__ void k_imu_sensor(const ImuSensorArgs a) {
   const int st = a.traj == 0 ? imu_time_offset_jac_se3(a.which, a.sp, a.imu, a.knots, a.pairs, a.t[i], a.w[i], o)
                              : imu_time_offset_jac_split(a.which, a.spl, a.imu, a.vecs, a.quats, a.so3pairs, a.t[i], a.w[i], o);
   if (st != 0) { atomicMin(a.err, st); o[0] = o[1] = o[2] = nan(""); }
-  double* dst = a.Js + 3 * (size_t)a.perm[i];
+  double* dst = a.Js + 3 * (size_t)(a.device_order ? i : a.perm[i]);
   dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
 }
 struct CamSensorArgs {
@@ -680,7 +733,7 @@ __global__ void k_static_rs_sensor(const CamSensorArgs a) {
   const int st = static_rs_sensor_jac_se3(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i],
                                           (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, o);
   if (st != 0) { atomicMin(a.err, st); for (int c = 0; c < 16; ++c) o[c] = nan(""); }
-  double* dst = a.Js + 16 * (size_t)a.perm[i];
+  double* dst = a.Js + 16 * (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
   for (int c = 0; c < 16; ++c) dst[c] = o[c];
 }
 
@@ -917,6 +970,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
+  cudaFuncSetAttribute(k_static_rs_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamSplitWarpSmem * 8);
@@ -1022,6 +1076,7 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
     a.traj = p->traj; a.which = g.kind == KTK_GYROSCOPE ? 0 : 1; a.sp = p->sp; a.spl = p->spl; fill_sensor_consts(g.sensor, a.imu);
     a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.vecs = p->d_vecs4.p; a.quats = d_quats; a.so3pairs = p->d_so3pairs.p;
     a.t = g.d_t.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.Js = o.Js; a.err = p->d_err.p;
+    a.device_order = (flags & KTK_EVAL_DEVICE_ORDER) ? 1 : 0;
     k_imu_sensor<<<blocks, 128, 0, s>>>(a);
   }
   p->launches += 1;
@@ -1166,7 +1221,8 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
-      k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
+      if ((flags & KTK_EVAL_DEVICE_ORDER) && !(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
+      else k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {
       ImuArgs a;
       a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
@@ -1315,7 +1371,7 @@ static RowWindows row_windows(const ktk_problem* p, const Group& g) {
 int64_t ktk_num_parameters(const ktk_problem* p, int64_t n_rho) { return p ? ktk_num_knot_doubles(p) + n_rho : 0; }
 
 // mode 0: u = J v ; mode 1: y += J^T u ; mode 2: y += diag(J^T J) ; mode 3: y_local += diag(P^T J^T J P)
-static int apply_products(ktk_problem* p, int mode, const ktk_group_out* d_outs, const double* d_v, double* const* d_u, double* d_y,
+static int apply_products(ktk_problem* p, int mode, uint32_t flags, const ktk_group_out* d_outs, const double* d_v, double* const* d_u, double* d_y,
                           const double* d_Pa = nullptr, const double* d_Pb = nullptr) {
   if (!p || !d_outs || (mode == 0 && (!d_v || !d_u)) || (mode == 1 && (!d_u || !d_y)) || (mode >= 2 && !d_y)) return fail(KTK_EINVAL, "NULL argument");
   if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
@@ -1330,9 +1386,15 @@ static int apply_products(ktk_problem* p, int mode, const ktk_group_out* d_outs,
     a.w = row_windows(p, g); a.n = (int)g.n; a.J = o.J;
     a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d;
     for (int w = 0; w < a.w.nwin; ++w) if (!a.idx[a.w.slot[w]]) return fail(KTK_EINVAL, "the group's index arrays are missing");
-    if (g.kind == KTK_STATIC_RS) {
-      if (g.d_lm_caller.n != (size_t)g.n) { int st = g.d_lm_caller.upload(g.lm, s); if (st) return st; KTK_CUDA(cudaStreamSynchronize(s)); }
-      a.lm = g.d_lm_caller.p;
+    if (g.kind == KTK_STATIC_RS) {        // landmark index of every row, in the order the rows were written
+      if (flags & KTK_EVAL_DEVICE_ORDER) {
+        if (g.perm.size() != (size_t)g.n) return fail(KTK_EINVAL, "device-order rows need an evaluation first");
+        if (g.d_lm_sorted.n != (size_t)g.n) { int st = g.d_lm_sorted.upload(gather(g.lm, g.perm, 1), s); if (st) return st; KTK_CUDA(cudaStreamSynchronize(s)); }
+        a.lm = g.d_lm_sorted.p;
+      } else {
+        if (g.d_lm_caller.n != (size_t)g.n) { int st = g.d_lm_caller.upload(g.lm, s); if (st) return st; KTK_CUDA(cudaStreamSynchronize(s)); }
+        a.lm = g.d_lm_caller.p;
+      }
     }
     a.v = d_v; a.u = d_u ? d_u[gi] : nullptr; a.y = d_y; a.mode = mode == 2 ? 1 : 0;
     if ((mode == 0 || mode == 1) && !a.u) return fail(KTK_EINVAL, "u is NULL for a non-empty group");
@@ -1355,11 +1417,24 @@ static int apply_products(ktk_problem* p, int mode, const ktk_group_out* d_outs,
   KTK_CUDA(cudaGetLastError());
   return KTK_OK;
 }
-int ktk_j_apply(ktk_problem* p, const ktk_group_out* d_outs, const double* d_v, double* const* d_u) { return apply_products(p, 0, d_outs, d_v, d_u, nullptr); }
-int ktk_jt_apply(ktk_problem* p, const ktk_group_out* d_outs, double* const* d_u, double* d_y) { return apply_products(p, 1, d_outs, nullptr, d_u, d_y); }
-int ktk_jtj_diagonal(ktk_problem* p, const ktk_group_out* d_outs, double* d_y) { return apply_products(p, 2, d_outs, nullptr, nullptr, d_y); }
-int ktk_jtj_diagonal_local(ktk_problem* p, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y) {
-  return apply_products(p, 3, d_outs, nullptr, nullptr, d_y, d_Pa, d_Pb);
+int ktk_j_apply(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, const double* d_v, double* const* d_u) { return apply_products(p, 0, flags, d_outs, d_v, d_u, nullptr); }
+int ktk_jt_apply(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, double* const* d_u, double* d_y) { return apply_products(p, 1, flags, d_outs, nullptr, d_u, d_y); }
+int ktk_jtj_diagonal(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, double* d_y) { return apply_products(p, 2, flags, d_outs, nullptr, nullptr, d_y); }
+int ktk_jtj_diagonal_local(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y) {
+  return apply_products(p, 3, flags, d_outs, nullptr, nullptr, d_y, d_Pa, d_Pb);
+}
+
+int ktk_get_row_order(ktk_problem* p, int32_t group, int32_t* order) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !order) return fail(KTK_EINVAL, "bad argument");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set first");
+  Group& g = *p->groups[group];
+  if (g.perm.size() != (size_t)g.n || !g.uploaded) {          // the device order is fixed when the group is uploaded
+    if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
+    KTK_CUDA(cudaSetDevice(p->device));
+    int st = upload_group(p, g); if (st) return st;
+  }
+  for (int64_t k = 0; k < g.n; ++k) order[k] = g.perm[k];
+  return KTK_OK;
 }
 
 int ktk_set_profiling(ktk_problem* p, int32_t on) { if (!p) return fail(KTK_EINVAL, "problem is NULL"); p->profiling = on != 0; return KTK_OK; }

@@ -30,7 +30,7 @@ class DeviceNormalEquations:
     def __init__(self, problem, split, n_a, n_b, n_rho, device, robust=True):
         self.p, self.split, self.n_a, self.n_b, self.n_rho = problem, split, n_a, n_b, n_rho
         self.dev = torch.device("cuda", device)
-        self.flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+        self.flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_DEVICE_ORDER | (_lib.EVAL_ROBUST if robust else 0)   # rows stay on the device: device order
         self.n_amb = problem.num_parameters(n_rho)
         self.n_loc = (3 * n_a + 3 * n_b if split else 6 * n_a) + n_rho
         self.outs, self._keep, self.u = [], [], []
@@ -92,20 +92,20 @@ class DeviceNormalEquations:
     def gradient(self):
         """g = P^T J^T r (local coordinates), summed over ranks."""
         y = torch.zeros(self.n_amb, dtype=torch.float64, device=self.dev)
-        self.p.jt_apply(self.outs, [k[0].data_ptr() for k in self._keep], y.data_ptr())
+        self.p.jt_apply(self.outs, [k[0].data_ptr() for k in self._keep], y.data_ptr(), _lib.EVAL_DEVICE_ORDER)
         return self._to_local(self._reduce(y)) * self.free
 
     def hessian_apply(self, v):
         """(P^T J^T J P) v."""
         va = self._to_ambient(v * self.free).contiguous()
-        self.p.j_apply(self.outs, va.data_ptr(), [u.data_ptr() for u in self.u])
+        self.p.j_apply(self.outs, va.data_ptr(), [u.data_ptr() for u in self.u], _lib.EVAL_DEVICE_ORDER)
         y = torch.zeros(self.n_amb, dtype=torch.float64, device=self.dev)
-        self.p.jt_apply(self.outs, [u.data_ptr() for u in self.u], y.data_ptr())
+        self.p.jt_apply(self.outs, [u.data_ptr() for u in self.u], y.data_ptr(), _lib.EVAL_DEVICE_ORDER)
         return self._to_local(self._reduce(y)) * self.free
 
     def hessian_diagonal(self):
         y = torch.zeros(self.n_loc, dtype=torch.float64, device=self.dev)
-        self.p.jtj_diagonal_local(self.outs, 0 if self.P_a is None else self.P_a.data_ptr(), 0 if self.P_b is None else self.P_b.data_ptr(), y.data_ptr())
+        self.p.jtj_diagonal_local(self.outs, 0 if self.P_a is None else self.P_a.data_ptr(), 0 if self.P_b is None else self.P_b.data_ptr(), y.data_ptr(), _lib.EVAL_DEVICE_ORDER)
         return self._reduce(y) * self.free
 
 

@@ -412,3 +412,20 @@ def test_local_coordinates_equal_ambient_times_plus_jacobian():
     assert parity.rel_err(l["J"][:, 24:48].reshape(n, 4, 2, 3), ref) < 1e-12
     ref = np.einsum("nkra,nkad->nkrd", a["J"][:, 80:112].reshape(n, 4, 2, 4), Pq[a["i0_d"][:, None] + np.arange(4)])
     assert parity.rel_err(l["J"][:, 72:96].reshape(n, 4, 2, 3), ref) < 1e-12
+
+
+def test_device_order_is_a_bit_exact_permutation():
+    """KTK_EVAL_DEVICE_ORDER: same values, rows in device order; ktk_get_row_order maps device row k to its insertion index."""
+    cfg = syn.make_config("H1", scale=0.01)
+    c = cfg["cam"]
+    p, g = _problem(cfg)
+    base = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST
+    a = p.evaluate(cfg["knots"], c["rho"], base)
+    d = p.evaluate(cfg["knots"], c["rho"], base | _lib.EVAL_DEVICE_ORDER)
+    for name in ("gyro", "accel", "cam"):
+        order = p.get_row_order(g[name])
+        assert sorted(order.tolist()) == list(range(len(order)))
+        for key in a[g[name]]:
+            assert np.array_equal(d[g[name]][key], a[g[name]][key][order]), (name, key)
+        i0 = d[g[name]]["i0_b" if name == "cam" else "i0"]
+        assert (np.diff(i0) >= 0).all()            # device order = sorted by first active knot (of the observation for camera rows)
