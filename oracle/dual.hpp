@@ -60,6 +60,7 @@ inline double ksqrt(double x) { return std::sqrt(x); }
 inline double ksin(double x) { return std::sin(x); }
 inline double kcos(double x) { return std::cos(x); }
 inline double katan(double x) { return std::atan(x); }
+inline double ktan(double x) { return std::tan(x); }
 inline double katan2(double y, double x) { return std::atan2(y, x); }
 inline double kexp(double x) { return std::exp(x); }
 inline double kabs(double x) { return std::fabs(x); }
@@ -70,6 +71,7 @@ template <int N> inline Dual<N> scale_(const Dual<N>& x, double fa, double d) {
 template <int N> inline Dual<N> ksqrt(const Dual<N>& x) { const double s = std::sqrt(x.a); return scale_(x, s, 1.0 / (2.0 * s)); }
 template <int N> inline Dual<N> ksin(const Dual<N>& x) { return scale_(x, std::sin(x.a), std::cos(x.a)); }
 template <int N> inline Dual<N> kcos(const Dual<N>& x) { return scale_(x, std::cos(x.a), -std::sin(x.a)); }
+template <int N> inline Dual<N> ktan(const Dual<N>& x) { const double t = std::tan(x.a); return scale_(x, t, 1.0 + t * t); }   // ceres/jet.h tan
 template <int N> inline Dual<N> katan(const Dual<N>& x) { return scale_(x, std::atan(x.a), 1.0 / (1.0 + x.a * x.a)); }
 template <int N> inline Dual<N> kexp(const Dual<N>& x) { const double e = std::exp(x.a); return scale_(x, e, e); }
 template <int N> inline Dual<N> kabs(const Dual<N>& x) { return x.a < 0.0 ? -x : x; }

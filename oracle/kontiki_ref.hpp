@@ -344,19 +344,73 @@ template <class T> Vec3<T> imu_accelerometer(const SensorView<T>& imu, const Tra
   return imu.has_bias ? a + imu.accelerometer_bias() : a;
 }
 
-// sensors/camera.h:24-28 + sensors/pinhole_camera.h:20-26
-struct CameraMeta { double readout; size_t rows, cols; double K[3][3]; };
+// sensors/camera.h:24-28 + sensors/pinhole_camera.h:20-26 (+ sensors/atan_camera.h:20-52: wc, gamma)
+enum CameraModel { kPinhole = 0, kAtan = 1 };
+struct CameraMeta { double readout; size_t rows, cols; double K[3][3]; int model = kPinhole; double wc[2] = {0, 0}; double gamma = 0; };
 
-// sensors/pinhole_camera.h:47-51 (non-derive branch) via sensors/camera.h:59-63
-template <class T> void pinhole_project(const CameraMeta& cm, const Vec3<T>& X, T y[2]) {
+template <class T> Mat3<T> camera_matrix(const CameraMeta& cm) {
   Mat3<T> K; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) K.m[i][j] = T(cm.K[i][j]);
+  return K; }
+
+// sensors/pinhole_camera.h:47-60 (EvaluateProjection; dy only when derive) via sensors/camera.h:59-63
+template <class T> void pinhole_project(const CameraMeta& cm, const Vec3<T>& X, const Vec3<T>& dX, bool derive, T y[2], T dy[2]) {
+  Mat3<T> K = camera_matrix<T>(cm);
   Vec3<T> p = K * X;
   y[0] = p.x / p.z; y[1] = p.y / p.z;
+  if (derive) {
+    const T z_eps = T(1e-32);
+    Vec3<T> dp = K * dX;
+    T denominator = (p.z * p.z) + z_eps;
+    dy[0] = ((dp.x * p.z) - (p.x * dp.z)) / denominator;
+    dy[1] = ((dp.y * p.z) - (p.y * dp.z)) / denominator;
+  }
 }
 // sensors/pinhole_camera.h:63-67 (3x3 inverse recomputed per call, on T)
 template <class T> Vec3<T> pinhole_unproject(const CameraMeta& cm, const T y[2]) {
-  Mat3<T> K; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) K.m[i][j] = T(cm.K[i][j]);
-  return inverse3(K) * Vec3<T>{y[0], y[1], T(1.0)};
+  return inverse3(camera_matrix<T>(cm)) * Vec3<T>{y[0], y[1], T(1.0)};
+}
+// sensors/atan_camera.h:54-91
+template <class T> void atan_project(const CameraMeta& cm, const Vec3<T>& X, const Vec3<T>& dX, bool derive, T y[2], T dy[2]) {
+  const T eps = T(1e-32);
+  const T gamma = T(cm.gamma), wc0 = T(cm.wc[0]), wc1 = T(cm.wc[1]);
+  T A0 = X.x / (X.z + eps), A1 = X.y / (X.z + eps);
+  T L0 = A0 - wc0, L1 = A1 - wc1;
+  T r = ksqrt((L0 * L0 + L1 * L1) + eps);
+  T f = katan(r * gamma) / gamma;
+  T g0 = L0 / r, g1 = L1 / r;
+  Mat3<T> K = camera_matrix<T>(cm);
+  Vec3<T> Y{wc0 + f * g0, wc1 + f * g1, T(1.0)};
+  Vec3<T> yk = K * Y;            // "Normalization not needed since Y(2) == 1" (:71-73)
+  y[0] = yk.x; y[1] = yk.y;
+  if (derive) {
+    T dx = (dX.x * X.z - X.x * dX.z) / (X.z * X.z + eps);
+    T dyy = (dX.y * X.z - X.y * dX.z) / (X.z * X.z + eps);
+    T common = (g0 * dx + g1 * dyy);
+    T df = common / (T(1.0) + kpow(gamma, 2.0) * r * r);
+    T dgu = (dx * r - L0 * common) / (r * r);
+    T du = f * dgu + df * g0;
+    T dgv = (dyy * r - L1 * common) / (r * r);
+    T dv = f * dgv + df * g1;
+    Vec3<T> d = K * Vec3<T>{du, dv, T(0.0)};
+    dy[0] = d.x; dy[1] = d.y;
+  }
+}
+// sensors/atan_camera.h:92-103
+template <class T> Vec3<T> atan_unproject(const CameraMeta& cm, const T y[2]) {
+  const T eps = T(1e-32);
+  const T gamma = T(cm.gamma), wc0 = T(cm.wc[0]), wc1 = T(cm.wc[1]);
+  Vec3<T> phn = inverse3(camera_matrix<T>(cm)) * Vec3<T>{y[0], y[1], T(1.0)};
+  T L0 = phn.x - wc0, L1 = phn.y - wc1;
+  T r = ksqrt((L0 * L0 + L1 * L1) + eps);
+  T f = ktan(r * gamma) / gamma;
+  return {wc0 + f * L0 / r, wc1 + f * L1 / r, T(1.0)};
+}
+// CameraView::Project / EvaluateProjection / Unproject dispatch (sensors/camera.h:59-63)
+template <class T> void camera_project(const CameraMeta& cm, const Vec3<T>& X, const Vec3<T>& dX, bool derive, T y[2], T dy[2]) {
+  if (cm.model == kAtan) atan_project(cm, X, dX, derive, y, dy); else pinhole_project(cm, X, dX, derive, y, dy);
+}
+template <class T> Vec3<T> camera_unproject(const CameraMeta& cm, const T y[2]) {
+  return cm.model == kAtan ? atan_unproject(cm, y) : pinhole_unproject(cm, y);
 }
 
 // measurements/gyroscope_measurement.h:36-38
@@ -386,12 +440,72 @@ template <class T> void reproject_static(const CameraMeta& cm, const double ref_
   const Vec3<T> p_ct = camera.relative_position();
   const Quat<T> q_ct = camera.relative_orientation();
   T y[2] = {T(ref_uv[0]), T(ref_uv[1])};
-  Vec3<T> yh = pinhole_unproject(cm, y);
+  Vec3<T> yh = camera_unproject(cm, y);
   Vec3<T> X_ref = qrot(qconj(q_ct), yh - inverse_depth * p_ct);
   Vec3<T> X = qrot(eval_ref->orientation, X_ref) + eval_ref->position * inverse_depth;
   Vec3<T> X_obs = qrot(qconj(eval_obs->orientation), X - inverse_depth * eval_obs->position);
   Vec3<T> X_camera = qrot(q_ct, X_obs) + p_ct * inverse_depth;
-  pinhole_project(cm, X_camera, y_out);
+  const Vec3<T> zero{T(0.0), T(0.0), T(0.0)}; T unused[2];
+  camera_project(cm, X_camera, zero, false, y_out, unused);   // CameraView::Project, sensors/camera.h:59-63
+}
+
+// math/quaternion_math.h:96-115
+template <class T> Quat<T> embed_vector(const Vec3<T>& v) { return {v.x, v.y, v.z, T(0.0)}; }
+template <class T> Quat<T> dq_from_angular_velocity(const Vec3<T>& w, const Quat<T>& q) {
+  Quat<T> p = qmul(embed_vector(w), q);
+  return {T(0.5) * p.x, T(0.5) * p.y, T(0.5) * p.z, T(0.5) * p.w}; }
+template <class T> Vec3<T> vector_sandwich(const Quat<T>& qa, const Vec3<T>& x, const Quat<T>& qb) {
+  Quat<T> r = qmul(qmul(qa, embed_vector(x)), qb);
+  return {r.x, r.y, r.z}; }
+
+// measurements/newton_rscamera_measurement.h:23-120.  As in reproject_static, traj_ref / traj_obs are the same view in
+// the reference.  Comparisons on T look at the scalar part (ceres::Jet), so the iteration count follows the values.
+template <class T> void reproject_newton(const CameraMeta& cm, const double ref_uv[2], double ref_t0, const double obs_uv[2], double obs_t0,
+                                         T inverse_depth, const TrajectoryView<T>& traj_ref, const TrajectoryView<T>& traj_obs,
+                                         const SensorView<T>& camera, T y_out[2], int max_iterations = 5) {
+  T time_offset = camera.time_offset();
+  T row_delta = T(cm.readout) / T(double(cm.rows));
+  T t0_obs = T(obs_t0) + time_offset;
+  T t_ref = T(ref_t0) + time_offset + T(ref_uv[1]) * row_delta;
+  T t_obs = t0_obs + T(obs_uv[1]) * row_delta;
+  int flags = EvalPosition | EvalVelocity | EvalOrientation | EvalAngularVelocity;
+  const Vec3<T> p_ct = camera.relative_position();
+  const Quat<T> q_ct = camera.relative_orientation();
+  auto eval_ref = traj_ref.Evaluate(t_ref, flags);
+  T y[2] = {T(ref_uv[0]), T(ref_uv[1])};
+  Vec3<T> yh = camera_unproject(cm, y);
+  Vec3<T> X_ref = qrot(qconj(q_ct), yh - inverse_depth * p_ct);
+  Vec3<T> X = qrot(eval_ref->orientation, X_ref) + eval_ref->position * inverse_depth;
+  const T max_time_delta = T(0.5) * T(cm.readout) / T(double(cm.rows));
+  const T max_time_delta_squared = kpow(max_time_delta, 2.0);
+  T min_bound = t0_obs;
+  T max_bound = t0_obs + T(cm.readout);
+  for (int iter = 0; iter < max_iterations; ++iter) {
+    auto eval_obs = traj_obs.Evaluate(t_obs, flags);
+    Vec3<T> p = eval_obs->position;
+    Vec3<T> dp = eval_obs->velocity;
+    Quat<T> q = eval_obs->orientation;
+    Quat<T> dq = dq_from_angular_velocity(eval_obs->angular_velocity, q);
+    Quat<T> dq_inv = qconj(dq);
+    Quat<T> q_inv = qconj(q);
+    Vec3<T> s = X - inverse_depth * p;
+    Vec3<T> ds = (-inverse_depth) * dp;
+    Vec3<T> X_obs = qrot(qconj(q), s);
+    Vec3<T> X_obs_cam = qrot(q_ct, X_obs) + inverse_depth * p_ct;
+    Vec3<T> dX_obs = vector_sandwich(dq_inv, s, q) + vector_sandwich(q_inv, ds, q) + vector_sandwich(q_inv, s, dq);
+    Vec3<T> dX_obs_cam = qrot(q_ct, dX_obs) + inverse_depth * p_ct;   // sic (:92)
+    T dy[2];
+    camera_project(cm, X_obs_cam, dX_obs_cam, true, y_out, dy);
+    T v = y_out[1];
+    T dv = dy[1];
+    T f = v - (T(double(cm.rows)) * (t_obs - t0_obs) / T(cm.readout));
+    T df = dv - (T(double(cm.rows)) / T(cm.readout));
+    T dt = f / df;
+    t_obs -= dt;
+    if ((dt * dt) < max_time_delta_squared) break;
+    if (t_obs < min_bound) t_obs = min_bound;
+    else if (t_obs > max_bound) t_obs = max_bound;
+  }
 }
 
 // ---- structure rule (trajectories/spline_base.h:361-404) -------------------------------------------------

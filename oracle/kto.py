@@ -38,7 +38,8 @@ class _Sensor(C.Structure):
 
 
 class _Camera(C.Structure):
-    _fields_ = [("readout", C.c_double), ("rows", C.c_int), ("cols", C.c_int), ("K", C.c_double * 9)]
+    _fields_ = [("readout", C.c_double), ("rows", C.c_int), ("cols", C.c_int), ("K", C.c_double * 9), ("model", C.c_int), ("method", C.c_int),
+                ("wc", C.c_double * 2), ("gamma", C.c_double)]
 
 
 _lib = None
@@ -128,15 +129,22 @@ class Sensor:
 
 
 class Camera(Sensor):
-    def __init__(self, rows, cols, readout, K=None, **kw):
+    def __init__(self, rows, cols, readout, K=None, wc=None, gamma=None, method="static", **kw):
+        """PinholeCamera, or AtanCamera when wc / gamma are given; method "static" | "newton" picks the measurement class."""
         super().__init__(**kw)
         self.rows, self.cols, self.readout = rows, cols, readout
         self.K = np.eye(3) if K is None else np.asarray(K, float)
+        self.wc, self.gamma, self.method = wc, gamma, method
 
     def cmeta(self):
         m = _Camera()
         m.readout, m.rows, m.cols = self.readout, self.rows, self.cols
         m.K[:] = list(self.K.reshape(-1))
+        m.model = 0 if self.gamma is None else 1
+        m.method = {"static": 0, "newton": 1}[self.method]
+        if self.gamma is not None:
+            m.wc[:] = [float(self.wc[0]), float(self.wc[1])]
+            m.gamma = float(self.gamma)
         return m
 
 
@@ -259,3 +267,19 @@ def spline_structure(dt, t0, spans, cap=64):
 
 def num_threads():
     return lib().kto_num_threads()
+
+
+def camera_project(cam, X, dX=None):
+    """CameraView::EvaluateProjection(X, dX, derive=True): returns (y, dy)."""
+    X = _f64(X); dX = np.zeros(3) if dX is None else _f64(dX)
+    y, dy = np.zeros(2), np.zeros(2)
+    cm = cam.cmeta()
+    lib().kto_camera_project(C.byref(cm), _p(X), _p(dX), _p(y), _p(dy))
+    return y, dy
+
+
+def camera_unproject(cam, y):
+    y = _f64(y); X = np.zeros(3)
+    cm = cam.cmeta()
+    lib().kto_camera_unproject(C.byref(cm), _p(y), _p(X))
+    return X

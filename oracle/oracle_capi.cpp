@@ -41,7 +41,8 @@ typedef struct {
   int abias_locked, gbias_locked;
 } kto_sensor;
 
-typedef struct { double readout; int rows, cols; double K[9]; } kto_camera;
+// model: 0 PinholeCamera, 1 AtanCamera (wc, gamma);  method: 0 StaticRsCameraMeasurement, 1 NewtonRsCameraMeasurement
+typedef struct { double readout; int rows, cols; double K[9]; int model, method; double wc[2]; double gamma; } kto_camera;
 
 enum { KTO_OK = 0, KTO_RANGE_ERROR = -1, KTO_RUNTIME_ERROR = -2, KTO_CAPACITY = -3 };
 
@@ -131,8 +132,8 @@ struct ImuFunctor {   // measurements/gyroscope_measurement.h:54-72 / accelerome
   }
 };
 
-struct StaticRsFunctor {   // measurements/static_rscamera_measurement.h:108-127
-  const Block* blk; CameraMeta cm; double weight; const double *ref_uv, *obs_uv; double ref_t0, obs_t0;
+struct StaticRsFunctor {   // measurements/static_rscamera_measurement.h:108-127 / newton_rscamera_measurement.h:183-199
+  const Block* blk; CameraMeta cm; double weight; const double *ref_uv, *obs_uv; double ref_t0, obs_t0; int method;
   template <class T> bool operator()(T const* const* params, T* residual) const {
     size_t offset = 0;
     const TrajectoryView<T> trajectory(blk->meta, &params[offset]);
@@ -141,7 +142,8 @@ struct StaticRsFunctor {   // measurements/static_rscamera_measurement.h:108-127
     offset += 3;
     T inverse_depth = params[offset][0];
     T y_hat[2];
-    reproject_static<T>(cm, ref_uv, ref_t0, obs_uv, obs_t0, inverse_depth, trajectory, trajectory, camera, y_hat);
+    if (method == 1) reproject_newton<T>(cm, ref_uv, ref_t0, obs_uv, obs_t0, inverse_depth, trajectory, trajectory, camera, y_hat);
+    else reproject_static<T>(cm, ref_uv, ref_t0, obs_uv, obs_t0, inverse_depth, trajectory, trajectory, camera, y_hat);
     residual[0] = T(weight) * (T(obs_uv[0]) - y_hat[0]);   // :89-94
     residual[1] = T(weight) * (T(obs_uv[1]) - y_hat[1]);
     return true;
@@ -306,6 +308,8 @@ int kto_static_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto
   TrajData td(*tr);
   CameraMeta cm; cm.readout = cmeta->readout; cm.rows = cmeta->rows; cm.cols = cmeta->cols;
   for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) cm.K[a][c] = cmeta->K[3 * a + c];
+  cm.model = cmeta->model; cm.wc[0] = cmeta->wc[0]; cm.wc[1] = cmeta->wc[1]; cm.gamma = cmeta->gamma;
+  const int method = cmeta->method;
   std::vector<Block> blocks(n);
   std::vector<int> st(n, KTO_OK);
   std::string first_err;
@@ -334,13 +338,14 @@ int kto_static_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto
   for (int i = 0; i < n; ++i) {
     if (st[i] != KTO_OK) continue;
     const Block& b = blocks[i];
-    StaticRsFunctor f{&b, cm, weight ? weight[i] : 1.0, ref_uv + 2 * i, obs_uv + 2 * i, ref_t0[i], obs_t0[i]};
+    StaticRsFunctor f{&b, cm, weight ? weight[i] : 1.0, ref_uv + 2 * i, obs_uv + 2 * i, ref_t0[i], obs_t0[i], method};
     std::vector<std::vector<double>> jac;
     st[i] = guarded([&] { evaluate_block(f, b, 2, jac_mode, r + 2 * i, jac); });
     if (st[i] != KTO_OK) continue;
     const double row_delta = cm.readout / double(cm.rows);
     const double t_ref = ref_t0[i] + cam->time_offset + ref_uv[2 * i + 1] * row_delta;
-    const double t_obs = obs_t0[i] + cam->time_offset + obs_uv[2 * i + 1] * row_delta;
+    // NewtonRs evaluates at several row times inside [t0_obs, t0_obs + readout]: report the window of the lower bound
+    const double t_obs = obs_t0[i] + cam->time_offset + (method == 1 ? 0.0 : obs_uv[2 * i + 1] * row_delta);
     if (i0_ref_a) i0_ref_a[i] = td.has_a() ? locate_knot(b.meta.a, b.ids_a, t_ref) : -1;
     if (i0_obs_a) i0_obs_a[i] = td.has_a() ? locate_knot(b.meta.a, b.ids_a, t_obs) : -1;
     if (i0_ref_b) i0_ref_b[i] = td.has_b() ? locate_knot(b.meta.b, b.ids_b, t_ref) : -1;
@@ -365,6 +370,24 @@ int kto_static_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto
   for (int i = 0; i < n; ++i) { if (status) status[i] = st[i]; if (st[i] != KTO_OK) worst = st[i]; }
   if (worst != KTO_OK && !first_err.empty()) g_last_error = first_err;
   return worst;
+}
+
+static CameraMeta camera_meta_of(const kto_camera* cmeta) {
+  CameraMeta cm; cm.readout = cmeta->readout; cm.rows = cmeta->rows; cm.cols = cmeta->cols;
+  for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) cm.K[a][c] = cmeta->K[3 * a + c];
+  cm.model = cmeta->model; cm.wc[0] = cmeta->wc[0]; cm.wc[1] = cmeta->wc[1]; cm.gamma = cmeta->gamma;
+  return cm;
+}
+// CameraView::EvaluateProjection(X, dX, true) / Unproject on doubles (sensors/pinhole_camera.h:47-67, atan_camera.h:54-103):
+// what python/tests/test_cameras.py:32-75 exercises.
+void kto_camera_project(const kto_camera* cmeta, const double* X, const double* dX, double* y, double* dy) {
+  const CameraMeta cm = camera_meta_of(cmeta);
+  camera_project<double>(cm, Vec3<double>{X[0], X[1], X[2]}, Vec3<double>{dX[0], dX[1], dX[2]}, true, y, dy);
+}
+void kto_camera_unproject(const kto_camera* cmeta, const double* y, double* X) {
+  const CameraMeta cm = camera_meta_of(cmeta);
+  const Vec3<double> v = camera_unproject<double>(cm, y);
+  X[0] = v.x; X[1] = v.y; X[2] = v.z;
 }
 
 // ceres::HuberLoss(a) + ceres::internal::Corrector (un-vendored Ceres 1.x), applied by Ceres

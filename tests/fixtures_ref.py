@@ -105,3 +105,11 @@ def smooth_se3_knots(n, dt, seed=1001, noise=1e-3):
         if np.dot(q[i - 1], q[i]) < 0:
             q[i] = -q[i]
     return np.concatenate([q, p], 1)
+
+
+# fixtures/camera_fixtures.py:12-16 (AtanCamera fixture)
+ATAN_K = np.array([[853.12703455, 0., 988.06311256],
+                   [0., 873.54956631, 525.71056312],
+                   [0., 0., 1.]])
+ATAN_WC = np.array([0.0029110778971412417, 0.0004189670467132041])
+ATAN_GAMMA = 0.8894355177968156

@@ -281,8 +281,7 @@ def _rs_project(traj, cam, X_world, t0):
         X_cam = R_ct @ X_traj + cam.p_ct
         if X_cam[2] <= 0:
             raise ValueError("Behind camera")
-        p = cam.K @ X_cam
-        return p[:2] / p[2]
+        return kto.camera_project(cam, X_cam)[0]
 
     def rootfunc(t):
         u, v = project(t)
@@ -296,7 +295,6 @@ def make_sfm(traj, cam, rng, nviews=8, nlm=12):
     fps = 30
     t1 = traj.min_time + 1e-2
     view_t0 = t1 + np.arange(nviews) / fps
-    Kinv = np.linalg.inv(cam.K)
     R_ct = fx.rot_xyzw(cam.q_ct)
     ref_uv, ref_t0, rho, obs = [], [], [], []
     tries = 0
@@ -305,7 +303,7 @@ def make_sfm(traj, cam, rng, nviews=8, nlm=12):
         i = rng.integers(0, nviews - 1)
         y0 = np.array([rng.uniform(0, cam.cols), rng.uniform(0, cam.rows)])
         z0 = rng.uniform(0.5, 100)
-        X_cam = z0 * (Kinv @ np.array([y0[0], y0[1], 1.0]))
+        X_cam = z0 * kto.camera_unproject(cam, y0)
         X_traj = R_ct.T @ (X_cam - cam.p_ct)
         t = view_t0[i] + y0[1] * cam.readout / cam.rows
         ev = kto.traj_evaluate(traj, [t], P | Q)
@@ -326,6 +324,59 @@ def make_sfm(traj, cam, rng, nviews=8, nlm=12):
     lm_idx = obs[:, 0].astype(np.int32)
     return dict(lm_idx=lm_idx, obs_t0=obs[:, 1].copy(), obs_uv=obs[:, 2:4].copy(), ref_uv=np.array(ref_uv)[lm_idx], ref_t0=np.array(ref_t0)[lm_idx],
                 rho=np.array(rho))
+
+
+ATAN = dict(K=fx.ATAN_K, wc=fx.ATAN_WC, gamma=fx.ATAN_GAMMA)          # fixtures/camera_fixtures.py:12-16
+PINHOLE = dict(K=np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+
+
+def make_camera(model, method="static", **kw):
+    return kto.Camera(fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT, method=method, **(ATAN if model == "atan" else PINHOLE), **kw)
+
+
+def _sfm_case(name, model, method, seed=11, **kw):
+    rng = np.random.default_rng(seed)
+    k = fx.smooth_se3_knots(40, 0.1)
+    traj = kto.Traj(kto.SE3, 0.1, 0.0, k) if name == "se3" else kto.Traj(kto.SPLIT, 0.1, 0.0, k[:, 4:7].copy(), 0.1, 0.0, k[:, 0:4].copy())
+    cam = make_camera(model, method, q_ct=fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), p_ct=np.array([0.05, -0.02, 0.1]))
+    return traj, cam, make_sfm(traj, cam, rng, **kw)
+
+
+# --- test_measurements.py:16-32 over projection_types x camera fixture (Pinhole, Atan) -------------------------
+@pytest.mark.parametrize("name", ["se3", "split"])
+@pytest.mark.parametrize("model", ["pinhole", "atan"])
+@pytest.mark.parametrize("method", ["static", "newton"])
+def test_rscamera_measurements(name, model, method):
+    traj, cam, s = _sfm_case(name, model, method)
+    assert len(s["lm_idx"]) >= 10
+    res = kto.static_rs_residuals(traj, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], jac_mode=0)
+    assert_almost_equal(res["r"], 0 * res["r"])       # np.testing.assert_almost_equal(yhat, obs.uv)  (decimal=7)
+
+
+# --- test_measurements.py:34-54: Newton lands within half a row of the noise-free row ---------------------------
+@pytest.mark.parametrize("model", ["pinhole", "atan"])
+def test_newton_rscamera_measurements_with_noise(model):
+    traj, cam, s = _sfm_case("se3", model, "newton", seed=12)
+    noisy = s["obs_uv"] + np.random.default_rng(5).normal(0, 2.0, size=s["obs_uv"].shape)
+    res = kto.static_rs_residuals(traj, cam, noisy, s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], jac_mode=0)
+    yhat = noisy - res["r"]
+    assert np.abs(yhat[:, 1] - s["obs_uv"][:, 1]).max() <= 0.5
+
+
+# --- test_cameras.py:32-37 project(unproject(y) * scale) == y;  :40-66 dy against numerical differentiation ---------
+@pytest.mark.parametrize("model", ["pinhole", "atan"])
+def test_camera_project_unproject_and_derivative(model):
+    cam = make_camera(model)
+    rng = np.random.default_rng(8)
+    for _ in range(50):
+        y = np.array([rng.uniform(0, cam.cols), rng.uniform(0, cam.rows)])
+        X = kto.camera_unproject(cam, y) * rng.uniform(0.01, 10)
+        assert_almost_equal(kto.camera_project(cam, X)[0], y)
+        X = kto.camera_unproject(cam, y) * rng.uniform(3, 10)
+        dX = X + rng.normal(size=3)
+        _, dy = kto.camera_project(cam, X, dX)
+        Jn = _numdiff(lambda x: kto.camera_project(cam, x)[0], X, h=1e-3)
+        assert_almost_equal(Jn @ dX, dy, decimal=3)
 
 
 @pytest.mark.parametrize("name", ["se3", "split"])
@@ -418,6 +469,34 @@ def test_camera_jacobian_vs_numdiff_se3():
         return kto.static_rs_residuals(traj, cam, *args, r, jac_mode=0)["r"][0]
     Jr = _numdiff(frho, s["rho"])[:, s["lm_idx"][0]]
     assert_allclose(res["Jrho"][0], Jr, atol=1e-5 * max(1, np.abs(Jr).max()))
+
+
+@pytest.mark.parametrize("model", ["pinhole", "atan"])
+@pytest.mark.parametrize("method", ["static", "newton"])
+def test_camera_jacobian_vs_numdiff_models(model, method):
+    """Atan / Newton variants of the check above (self-consistency of the multipass autodiff)."""
+    traj, cam, s = _sfm_case("se3", model, method, seed=2, nlm=3)
+    knots = traj.knots_a.copy()
+    rng = np.random.default_rng(4)
+    s["obs_uv"] = s["obs_uv"] + rng.normal(0, 0.5, size=s["obs_uv"].shape)
+    for row in range(min(3, len(s["lm_idx"]))):
+        sel = slice(row, row + 1)
+        args = [s[k][sel] for k in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx")]
+        res = kto.static_rs_residuals(traj, cam, *args, s["rho"], jac_mode=2)
+        ids = res["ids_a"][0]
+        ids = ids[ids >= 0]
+
+        def f(kn):
+            kk = knots.copy(); kk[ids] = kn
+            return kto.static_rs_residuals(kto.Traj(kto.SE3, 0.1, 0.0, kk), cam, *args, s["rho"], jac_mode=0)["r"][0]
+        Jn = _numdiff(f, knots[ids], h=1e-7)
+        Ja = np.concatenate([res["Ja"][0, k] for k in range(len(ids))], axis=1)
+        assert_allclose(Ja, Jn, atol=2e-5 * np.abs(Ja).max())
+
+        def frho(r):
+            return kto.static_rs_residuals(traj, cam, *args, r, jac_mode=0)["r"][0]
+        Jr = _numdiff(frho, s["rho"], h=1e-7)[:, s["lm_idx"][row]]
+        assert_allclose(res["Jrho"][0], Jr, atol=1e-4 * max(1, np.abs(Jr).max()))
 
 
 def test_huber_corrector_matches_definition():
