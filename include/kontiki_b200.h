@@ -31,6 +31,11 @@
  *   gyro row  : J[4 SO3 knots][3][4] (48);          the R3 blocks of the residual are structurally present but zero
  *   accel row : J[4 R3 knots][3][3] (36) | [4 SO3 knots][3][4] (48)
  *   static RS : J[ref R3 4x(2x3)] (24) | [ref SO3 4x(2x4)] (32) | [obs R3] (24) | [obs SO3] (32) | [d r/d rho] (2)
+ *   Newton-RS row      : r[2];  J[58 + 14 W] = [ref window: 4 x (2 x 7)] [obs SPAN: W x (2 x 7)] [d r / d rho (2)].  The Newton iteration
+ *                        on the row time (newton_rscamera_measurement.h:62-117) evaluates the spline at several times inside
+ *                        [t0_obs, t0_obs + readout], so the row carries every knot of the residual's observation span
+ *                        {t0_obs - 1e-3, t0_obs + readout + 1e-3} (:210-236): i0_obs = first knot of that span, W = knots of the
+ *                        widest span in the group = (ktk_group_row_size - 58) / 14; blocks past a row's own span are zero.
  * Rows are returned in the caller's order of insertion, whatever order the device processes them in.
  */
 #ifndef KONTIKI_B200_H_
@@ -73,7 +78,8 @@ enum {
                              entry points below expect ambient rows. */
 };
 
-enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2 };
+enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3 };
+enum { KTK_CAMERA_PINHOLE = 0, KTK_CAMERA_ATAN = 1 };
 
 /* sensors/sensors.h:91-109: relative pose + time offset; *_locked as the reference's lock flags (default locked). */
 typedef struct {
@@ -84,13 +90,19 @@ typedef struct {
   int32_t q_locked, p_locked, time_offset_locked;
 } ktk_sensor;
 
-/* sensors/camera.h:24-28 + sensors/pinhole_camera.h:25 */
+/* sensors/camera.h:24-28 + sensors/pinhole_camera.h:25 (PinholeCamera) / sensors/atan_camera.h:20-22 (AtanCamera: the same
+ * camera matrix plus the distortion centre wc and parameter gamma of the FOV/arctangent model, atan_camera.h:54-103). */
 typedef struct {
   ktk_sensor base;
   int32_t rows, cols;
   double readout;
   double K[9];               /* row-major 3x3 */
-} ktk_pinhole_camera;
+  int32_t model;             /* KTK_CAMERA_PINHOLE / KTK_CAMERA_ATAN */
+  int32_t reserved;
+  double wc[2];              /* AtanCamera only */
+  double gamma;              /* AtanCamera only, != 0 */
+} ktk_camera;
+typedef ktk_camera ktk_pinhole_camera;   /* model = KTK_CAMERA_PINHOLE */
 
 /* Per measurement group output pointers (any may be NULL).  Host pointers for ktk_evaluate, device pointers for
  * ktk_evaluate_device.  Sizes for n rows: r n*3 (IMU) / n*2 (camera); J n*84 / n*114; i0 n; i0_b n (camera: obs). */
@@ -137,7 +149,13 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
  *   static_rscamera_measurement.h:68-69). */
 int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
 int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
-int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
+int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
+                      const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
+/* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static
+ * measurement.  The row time is found by the reference's 5-step Newton iteration (:62-117) and the Jacobian is the
+ * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  UniformSE3SplineTrajectory with locked
+ * camera parameters only (KTK_EUNSUPPORTED otherwise); KTK_EVAL_LOCAL / KTK_EVAL_SENSOR_JACOBIANS are not built for it. */
+int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 
 /* The sensor parameters are part of the evaluation point when they are unlocked: update them between evaluations.
@@ -149,7 +167,7 @@ int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias);
 int32_t ktk_num_groups(const ktk_problem* p);
 int64_t ktk_group_size(const ktk_problem* p, int32_t group);
 int32_t ktk_group_kind(const ktk_problem* p, int32_t group);
-int32_t ktk_group_row_size(const ktk_problem* p, int32_t group);   /* doubles per packed Jacobian row (84 / 114 / 48) */
+int32_t ktk_group_row_size(const ktk_problem* p, int32_t group);   /* doubles per packed Jacobian row (84 / 114 / 48; Newton-RS 58 + 14 W) */
 int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t group);   /* ... with KTK_EVAL_LOCAL */
 int64_t ktk_num_knot_doubles(const ktk_problem* p);                /* length of the `knots` argument of ktk_evaluate */
 
@@ -221,8 +239,8 @@ int ktk_get_structure(const ktk_problem* p, int32_t group, int32_t cap, int32_t*
  * blocks are all R3 knots, then all SO3 knots, split_trajectory.h:117-123). */
 int ktk_get_structure_so3(const ktk_problem* p, int32_t group, int32_t cap, int32_t* knot_ids, int32_t* n_ids);
 
-/* Packed static-RS rows -> the reference's structural blocks: out[n][cap][2][7] for the knot ids of ktk_get_structure
- * (zero for knots in the segment that are not active).  Host-side helper for Ceres-style consumers. */
+/* Packed static-RS / Newton-RS rows -> the reference's structural blocks: out[n][cap][2][7] for the knot ids of
+ * ktk_get_structure (zero for knots in the segment that are not active).  Host-side helper for Ceres-style consumers. */
 int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const int32_t* knot_ids, const double* J_packed,
                          const int32_t* i0_ref, const int32_t* i0_obs, double* out);
 

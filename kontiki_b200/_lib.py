@@ -11,7 +11,8 @@ from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL, EVAL_DEVICE_ORDER = 1, 2, 4, 8, 16, 32
-GYROSCOPE, ACCELEROMETER, STATIC_RS = 0, 1, 2
+GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS = 0, 1, 2, 3
+CAMERA_PINHOLE, CAMERA_ATAN = 0, 1
 IMU_ROW, CAM_ROW = 84, 114
 
 
@@ -20,8 +21,12 @@ class Sensor(C.Structure):
                 ("q_locked", C.c_int32), ("p_locked", C.c_int32), ("time_offset_locked", C.c_int32)]
 
 
-class PinholeCamera(C.Structure):
-    _fields_ = [("base", Sensor), ("rows", C.c_int32), ("cols", C.c_int32), ("readout", C.c_double), ("K", C.c_double * 9)]
+class Camera(C.Structure):
+    _fields_ = [("base", Sensor), ("rows", C.c_int32), ("cols", C.c_int32), ("readout", C.c_double), ("K", C.c_double * 9),
+                ("model", C.c_int32), ("reserved", C.c_int32), ("wc", C.c_double * 2), ("gamma", C.c_double)]
+
+
+PinholeCamera = Camera
 
 
 class GroupOut(C.Structure):
@@ -32,7 +37,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs"]
 
 _lib = None
 
@@ -64,7 +69,8 @@ def lib():
         L.ktk_set_se3_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32]
         L.ktk_add_gyroscope.argtypes = [C.c_void_p, C.POINTER(Sensor), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_add_accelerometer.argtypes = L.ktk_add_gyroscope.argtypes
-        L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(PinholeCamera), C.c_int64] + [C.c_void_p] * 7
+        L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [C.c_void_p] * 7
+        L.ktk_add_newton_rs.argtypes = L.ktk_add_static_rs.argtypes
         L.ktk_num_groups.argtypes = [C.c_void_p]
         L.ktk_group_size.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_group_kind.argtypes = [C.c_void_p, C.c_int32]
@@ -129,11 +135,16 @@ def make_sensor(q_ct=(0, 0, 0, 1), p_ct=(0, 0, 0), time_offset=0.0, max_time_off
     return s
 
 
-def make_camera(rows, cols, readout, K, **sensor_kw):
-    c = PinholeCamera()
+def make_camera(rows, cols, readout, K, wc=None, gamma=None, **sensor_kw):
+    """PinholeCamera; AtanCamera when the distortion centre wc and gamma are given (sensors/atan_camera.h)."""
+    c = Camera()
     c.base = make_sensor(**sensor_kw)
     c.rows, c.cols, c.readout = int(rows), int(cols), float(readout)
     c.K[:] = [float(x) for x in np.asarray(K, float).reshape(-1)]
+    if gamma is not None:
+        c.model = CAMERA_ATAN
+        c.wc[:] = [float(wc[0]), float(wc[1])]
+        c.gamma = float(gamma)
     return c
 
 
@@ -188,7 +199,10 @@ class Problem:
     def add_accelerometer(self, sensor, t, y, weight=None):
         return self._add_imu(lib().ktk_add_accelerometer, sensor, t, y, weight)
 
-    def add_static_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
+    def add_newton_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
+        return self.add_static_rs(camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight, huber_c, _fn=lib().ktk_add_newton_rs)
+
+    def add_static_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None, _fn=None):
         obs_uv, ref_uv = _f64(obs_uv).reshape(-1, 2), _f64(ref_uv).reshape(-1, 2)
         obs_t0, ref_t0 = _f64(obs_t0), _f64(ref_t0)
         lm = np.ascontiguousarray(lm_idx, np.int32)
@@ -197,8 +211,8 @@ class Problem:
             raise ValueError("static-RS arrays differ in length")
         w = None if weight is None else _f64(weight)
         h = None if huber_c is None else _f64(huber_c)
-        return check(lib().ktk_add_static_rs(self._h, C.byref(camera), n, _ptr(obs_uv), _ptr(obs_t0), _ptr(ref_uv), _ptr(ref_t0), _ptr(lm),
-                                             _ptr(w), _ptr(h)))
+        return check((_fn or lib().ktk_add_static_rs)(self._h, C.byref(camera), n, _ptr(obs_uv), _ptr(obs_t0), _ptr(ref_uv), _ptr(ref_t0), _ptr(lm),
+                                                      _ptr(w), _ptr(h)))
 
     @property
     def num_groups(self):
@@ -225,7 +239,7 @@ class Problem:
         """Host (numpy) output arrays for every group, in the C ABI's packed layouts."""
         outs = []
         for g in range(self.num_groups):
-            n, cam = self.group_size(g), self.group_kind(g) == STATIC_RS
+            n, cam = self.group_size(g), self.group_kind(g) in (STATIC_RS, NEWTON_RS)
             o = dict(r=np.zeros((n, 2 if cam else 3)), i0=np.full(n, -1, np.int32))
             if jacobians:
                 if local:
@@ -368,7 +382,7 @@ class Problem:
     def expand_static_rs(self, g, ids, J, i0_ref, i0_obs):
         n, cap = ids.shape
         out = np.zeros((n, cap, 2, 7))
-        J = _f64(J).reshape(n, CAM_ROW)
+        J = _f64(J).reshape(n, self.group_row_size(g))
         check(lib().ktk_expand_static_rs(self._h, g, cap, _ptr(np.ascontiguousarray(ids, np.int32)), _ptr(J), _ptr(np.ascontiguousarray(i0_ref, np.int32)),
                                          _ptr(np.ascontiguousarray(i0_obs, np.int32)), _ptr(out)))
         return out

@@ -1,4 +1,5 @@
-// kontiki_b200 -- one-direction forward-mode dual number used ONLY by the knot-pair prepass (K0).
+// kontiki_b200 -- one-direction forward-mode dual number used by the knot-pair prepass (K0) and by the Newton
+// rolling-shutter rows (newton_math.cuh), whose derivative IS the forward-mode derivative of an iteration.
 //
 // The knot-pair log map  omega = log(P_{i-1}^-1 * P_i)  is a function of two *ambient* SE3 knots
 // (7 doubles each, quaternion not constrained to unit norm while differentiating).  The reference
@@ -44,5 +45,9 @@ KB_HD D1 t_sqrt(D1 x) { const double s = sqrt(x.a); return D1(s, x.d / (2.0 * s)
 KB_HD D1 t_sin(D1 x) { return D1(sin(x.a), cos(x.a) * x.d); }
 KB_HD D1 t_cos(D1 x) { return D1(cos(x.a), -sin(x.a) * x.d); }
 KB_HD D1 t_atan(D1 x) { return D1(atan(x.a), x.d / (1.0 + x.a * x.a)); }
+KB_HD double t_tan(double x) { return tan(x); }
+KB_HD D1 t_tan(D1 x) { const double t = tan(x.a); return D1(t, (1.0 + t * t) * x.d); }
+KB_HD double deriv(double) { return 0.0; }
+KB_HD double deriv(D1 x) { return x.d; }
 
 }  // namespace kb

@@ -24,6 +24,7 @@
 
 #include "../../include/kontiki_b200.h"
 #include "sensor_jac.cuh"
+#include "newton_math.cuh"
 
 using namespace kb;
 
@@ -31,6 +32,7 @@ namespace {
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NEWTON_RS; }
 #define KTK_CUDA(call)                                                                                   \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -587,6 +589,7 @@ __global__ void k_traj_eval_split(SplitConst sp, const double* __restrict__ vecs
 struct RowWindows {            // where the blocks of a packed row live in the parameter vector
   int nwin;                    // number of 4-knot windows
   int j_off[4], width[4], col_off[4], slot[4];     // offset in the row, knot width, first column of that spline, index array
+  int nk[4];                                        // knots per window: 4, except the observation span of a Newton-RS row
   int nres, row_len, rho_off_in_row;                // residuals per row, doubles per row, offset of d r/d rho (-1: none)
   long long rho_col0;                               // first column of rho
 };
@@ -605,7 +608,7 @@ __global__ void k_j_apply(const ApplyArgs a) {
     const int wd = a.w.width[w];
     const double* vv = a.v + a.w.col_off[w] + (size_t)wd * a.idx[a.w.slot[w]][i];
     const double* Jw = Jr + a.w.j_off[w];
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < a.w.nk[w]; ++k)
       for (int r = 0; r < a.w.nres; ++r) {
         double s = 0.0;
         for (int c = 0; c < wd; ++c) s += Jw[(k * a.w.nres + r) * wd + c] * vv[k * wd + c];
@@ -686,7 +689,7 @@ __global__ void k_jt_apply(const ApplyArgs a) {
     const int wd = a.w.width[w];
     double* yy = a.y + a.w.col_off[w] + (size_t)wd * a.idx[a.w.slot[w]][i];
     const double* Jw = Jr + a.w.j_off[w];
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < a.w.nk[w]; ++k)
       for (int c = 0; c < wd; ++c) {
         double s = 0.0;
         for (int r = 0; r < a.w.nres; ++r) { const double j = Jw[(k * a.w.nres + r) * wd + c]; s += a.mode == 0 ? j * ur[r] : j * j; }
@@ -737,6 +740,58 @@ __global__ void k_static_rs_sensor(const CamSensorArgs a) {
   for (int c = 0; c < 16; ++c) dst[c] = o[c];
 }
 
+// =====================================================================================================================
+// NewtonRsCameraMeasurement rows (newton_rscamera_measurement.h): the reference's Jacobian is the forward-mode derivative
+// through the Newton iteration on the row time, so one thread runs ONE direction of ONE row on a dual number
+// (newton_math.cuh); 29 + 7 W directions per row, no staging -- thread (row, dir) owns two doubles of the packed row.
+// The landmark side comes from the same k_landmark_ref records as the static measurement.
+// =====================================================================================================================
+struct NewtonArgs {
+  SplineConst sp; CameraConst cam;
+  const double* knots; const double* pairs; const double* recs;
+  const double* obs_uv; const double* obs_t0; const double* ref_t0; const int* ref_idx; const double* w; const double* huber;
+  const int* perm;
+  int n, W; uint32_t flags;
+  double* r; double* J; int* i0r; int* i0o; int* err;
+};
+__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a) {
+  const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / ndir), dir = (int)(tid % ndir);
+  if (i >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  if (!wantJ && dir != 0) return;
+  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+  const double obs_t0 = a.obs_t0[i];
+  const int ridx = a.ref_idx[i];
+  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+  int st = kStatusRange;
+  double r[2] = {nan(""), nan("")}, j[2] = {nan(""), nan("")};
+  int ir = -1;
+  if (ridx >= 0) {
+    const double* rec = a.recs + (size_t)ridx * kRefStride;
+    ir = (int)rec[7];
+    if (ir >= 0) {
+      NewtonRow o;
+      st = newton_rs_direction(a.sp, a.cam, a.knots, a.pairs, rec, ouv, obs_t0, a.ref_t0[i], kbase, a.W, wantJ ? dir : -1, o);
+      if (st == 0) newton_rs_finish(o, ouv, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, j);
+    }
+  }
+  if (st != 0) { atomicMin(a.err, st); ir = -1; }
+  if (dir == 0) {
+    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+    if (a.i0r) a.i0r[dst] = ir;
+    if (a.i0o) a.i0o[dst] = st == 0 ? kbase : -1;
+  }
+  if (wantJ) {
+    int stride;
+    const int off = newton_dir_offset(dir, a.W, stride);
+    double* Jr = a.J + dst * row_len;
+    Jr[off] = j[0]; Jr[off + stride] = j[1];
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -747,7 +802,8 @@ template <class T> struct DevBuf {
 
 struct Group {
   int kind = 0; int64_t n = 0;
-  ktk_sensor sensor{}; ktk_pinhole_camera cam{};
+  ktk_sensor sensor{}; ktk_camera cam{};
+  int newton_W = 0;               // Newton-RS groups: knots of the widest observation span (0 = not computed for the current spline)
   // caller-order host copies (structure queries) and sorted device copies
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
@@ -797,7 +853,7 @@ void fill_sensor_consts(const ktk_sensor& s, ImuConst& c) {
   c.bias[0] = c.bias[1] = c.bias[2] = 0.0;
 }
 
-void fill_camera_consts(const ktk_pinhole_camera& cm, CameraConst& c) {
+void fill_camera_consts(const ktk_camera& cm, CameraConst& c) {
   for (int i = 0; i < 9; ++i) c.K[i] = cm.K[i];
   // Eigen fixed-size 3x3 inverse = cofactors / determinant (pinhole_camera.h:63-67 inverts K per call)
   const double* a = cm.K; double k[9];
@@ -810,6 +866,7 @@ void fill_camera_consts(const ktk_pinhole_camera& cm, CameraConst& c) {
   for (int i = 0; i < 3; ++i) c.p_ct[i] = cm.base.p_ct[i];
   c.time_offset = cm.base.time_offset; c.max_time_offset = cm.base.max_time_offset; c.time_offset_locked = cm.base.time_offset_locked;
   c.readout = cm.readout; c.row_delta = cm.readout / (double)cm.rows;
+  c.rows = cm.rows; c.model = cm.model; c.wc[0] = cm.wc[0]; c.wc[1] = cm.wc[1]; c.gamma = cm.gamma;
 }
 
 int check_sensor(const ktk_sensor* s) {
@@ -838,7 +895,7 @@ int upload_group(ktk_problem* p, Group& g) {
   // the spline whose first active knot orders the rows: SE3, or the SO3 part of a split trajectory
   const double kt0 = split ? p->spl.t0_so3 : p->sp.t0, kdt = split ? p->spl.dt_so3 : p->sp.dt;
   std::vector<int> key((size_t)g.n);
-  if (g.kind == KTK_STATIC_RS) {
+  if (is_camera(g.kind)) {
     const double row_delta = g.cam.readout / (double)g.cam.rows;
     for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.obs_t0[i] + g.cam.base.time_offset + g.obs_uv[2 * i + 1] * row_delta, kt0, kdt);
   } else {
@@ -849,7 +906,7 @@ int upload_group(ktk_problem* p, Group& g) {
   cudaStream_t s = p->stream;
   if ((st = g.d_perm.upload(g.perm, s))) return st;
   if ((st = g.d_w.upload(gather(g.w, g.perm, 1), s))) return st;
-  if (g.kind == KTK_STATIC_RS) {
+  if (is_camera(g.kind)) {
     // Landmark-reference table.  The reference evaluation of a residual happens in the segment (of that residual's two
     // spans) that holds t_ref; its origin is what fixes (i0_ref, u_ref) bit-exactly.  Observations of one landmark
     // share it whenever the reference view is the earlier one; otherwise they get their own record.
@@ -921,13 +978,23 @@ int upload_group(ktk_problem* p, Group& g) {
 }
 
 // doubles per packed Jacobian row / per residual of a group (include/kontiki_b200.h "Layouts")
+// Newton-RS groups: knots of the widest observation span {t0_obs - 1e-3, t0_obs + readout + 1e-3} on the current spline
+int newton_window(const ktk_problem* p, const Group& g) {
+  if (g.newton_W > 0) return g.newton_W;
+  CameraConst cc; fill_camera_consts(g.cam, cc);
+  int W = 4;
+  for (int64_t i = 0; i < g.n; ++i) W = std::max(W, newton_obs_window_size(p->sp, cc, g.obs_t0[i]));
+  const_cast<Group&>(g).newton_W = W;
+  return W;
+}
 int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
+  if (g.kind == KTK_NEWTON_RS) return 58 + 14 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
   if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? (local ? 36 : kGyroSplitRow) : (local ? 72 : kAccelSplitRow);
   return local ? 72 : kImuRow;
 }
-int res_doubles(const Group& g) { return g.kind == KTK_STATIC_RS ? 2 : 3; }
+int res_doubles(const Group& g) { return is_camera(g.kind) ? 2 : 3; }
 
 int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
@@ -991,7 +1058,7 @@ int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, in
   if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
   p->traj = 0; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) g->uploaded = false;   // the sort key depends on (t0, dt)
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; }   // the sort key depends on (t0, dt)
   return KTK_OK;
 }
 
@@ -1001,22 +1068,26 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
   if (n_r3 < 4 || n_so3 < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->spl = SplitConst{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   p->traj = 1; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) g->uploaded = false;
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; }
   return KTK_OK;
 }
 
 int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_GYROSCOPE, imu, n, t, y, w); }
 int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_ACCELEROMETER, imu, n, t, y, w); }
 
-int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
-                      const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
+static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
+                            const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
   if (!cam) return fail(KTK_EINVAL, "camera is NULL");
   int st = check_sensor(&cam->base); if (st) return st;
   if (cam->rows <= 0 || cam->cols <= 0) return fail(KTK_EINVAL, "camera rows/cols must be positive");
+  if (cam->model != KTK_CAMERA_PINHOLE && cam->model != KTK_CAMERA_ATAN) return fail(KTK_EINVAL, "unknown camera model");
+  if (cam->model == KTK_CAMERA_ATAN && !(cam->gamma != 0.0)) return fail(KTK_EINVAL, "AtanCamera needs gamma != 0");
+  if (kind == KTK_NEWTON_RS && (!cam->base.q_locked || !cam->base.p_locked || !cam->base.time_offset_locked))
+    return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement with unlocked camera parameters is not built");
   if (n < 0 || (n > 0 && (!obs_uv || !obs_t0 || !ref_uv || !ref_t0 || !lm_idx))) return fail(KTK_EINVAL, "bad measurement arrays");
   if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
-  Group* g = new Group; g->kind = KTK_STATIC_RS; g->n = n; g->cam = *cam; g->sensor = cam->base;
+  Group* g = new Group; g->kind = kind; g->n = n; g->cam = *cam; g->sensor = cam->base;
   g->obs_uv.assign(obs_uv, obs_uv + 2 * n); g->obs_t0.assign(obs_t0, obs_t0 + n);
   g->ref_uv.assign(ref_uv, ref_uv + 2 * n); g->ref_t0.assign(ref_t0, ref_t0 + n);
   g->lm.assign(lm_idx, lm_idx + n);
@@ -1026,6 +1097,14 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_pinhole_camera* cam, int64_t n, 
   drop_graph(p);
   p->groups.push_back(g);
   return (int)p->groups.size() - 1;
+}
+int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
+                      const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
+  return add_camera_group(p, KTK_STATIC_RS, cam, n, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, w, huber_c);
+}
+int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
+                      const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
+  return add_camera_group(p, KTK_NEWTON_RS, cam, n, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, w, huber_c);
 }
 
 int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor) {
@@ -1040,7 +1119,7 @@ int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor
 int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !bias) return fail(KTK_EINVAL, "bad argument");
   Group& g = *p->groups[group];
-  if (g.kind == KTK_STATIC_RS) return fail(KTK_EINVAL, "a camera has no bias");
+  if (is_camera(g.kind)) return fail(KTK_EINVAL, "a camera has no bias");
   for (int c = 0; c < 3; ++c) g.bias[c] = bias[c];
   drop_graph(p);
   return KTK_OK;
@@ -1062,6 +1141,7 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   if (!(flags & KTK_EVAL_SENSOR_JACOBIANS) || !o.Js || g.n == 0) return KTK_OK;
   cudaStream_t s = p->stream;
   const int blocks = (int)((g.n + 127) / 128);
+  if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRsCameraMeasurement are not built");
   if (g.kind == KTK_STATIC_RS) {
     if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
     if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
@@ -1099,6 +1179,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     Group& g = *p->groups[gi];
     if (g.n == 0) continue;
     const ktk_group_out& o = outs[gi];
+    if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement on a split trajectory is not built");
     const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
     const int blocks = (int)((g.n + tpb - 1) / tpb);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1145,7 +1226,8 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
   int st;
   for (auto g : p->groups) {
     if ((st = upload_group(p, *g))) return st;
-    if (g->kind == KTK_STATIC_RS) {
+    if (g->kind == KTK_NEWTON_RS && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRsCameraMeasurement are not built");
+    if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
     }
@@ -1208,7 +1290,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     const int blocks = (int)((g.n + tpb - 1) / tpb);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
-    if (g.kind == KTK_STATIC_RS) {
+    if (is_camera(g.kind)) {
       RefArgs ra;
       ra.sp = p->sp; fill_camera_consts(g.cam, ra.cam);
       ra.knots = p->d_knots8.p; ra.pairs = p->d_pairs.p; ra.rho = d_rho;
@@ -1221,7 +1303,15 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
-      if ((flags & KTK_EVAL_DEVICE_ORDER) && !(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
+      if (g.kind == KTK_NEWTON_RS) {
+        NewtonArgs na;
+        na.sp = a.sp; na.cam = a.cam; na.knots = a.knots; na.pairs = a.pairs; na.recs = a.recs;
+        na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
+        na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
+        const long long threads = (long long)g.n * (29 + 7 * na.W);
+        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
+      }
+      else if ((flags & KTK_EVAL_DEVICE_ORDER) && !(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
       else k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {
       ImuArgs a;
@@ -1280,14 +1370,14 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     if (o.i0_b) { if ((st = g.o_i0b.resize(n))) return st; dev[gi].i0_b = g.o_i0b.p; }
     if (o.i0_c) { if ((st = g.o_i0c.resize(n))) return st; dev[gi].i0_c = g.o_i0c.p; }
     if (o.i0_d) { if ((st = g.o_i0d.resize(n))) return st; dev[gi].i0_d = g.o_i0d.p; }
-    if (o.Js && (flags & KTK_EVAL_SENSOR_JACOBIANS)) { if ((st = g.o_Js.resize(n * (g.kind == KTK_STATIC_RS ? 16 : 3)))) return st; dev[gi].Js = g.o_Js.p; }
+    if (o.Js && (flags & KTK_EVAL_SENSOR_JACOBIANS)) { if ((st = g.o_Js.resize(n * (is_camera(g.kind) ? 16 : 3)))) return st; dev[gi].Js = g.o_Js.p; }
   }
   if ((st = ktk_evaluate_device(p, p->d_knots7.p, (rho && n_rho > 0) ? p->d_rho.p : nullptr, n_rho, flags, dev.data()))) return st;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
     Group& g = *p->groups[gi];
     const ktk_group_out& o = outs[gi];
     const size_t n = (size_t)g.n;
-    const bool cam = g.kind == KTK_STATIC_RS, split = p->traj == 1;
+    const bool cam = is_camera(g.kind), split = p->traj == 1;
     if (dev[gi].r) KTK_CUDA(cudaMemcpyAsync(o.r, dev[gi].r, n * res_doubles(g) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dev[gi].J) KTK_CUDA(cudaMemcpyAsync(o.J, dev[gi].J, n * row_doubles(p, g, flags) * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0) KTK_CUDA(cudaMemcpyAsync(o.i0, dev[gi].i0, n * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -1356,11 +1446,12 @@ static RowWindows row_windows(const ktk_problem* p, const Group& g) {
   const int colB = split ? 3 * n_a : 0;
   w.rho_col0 = split ? (long long)3 * n_a + (long long)4 * n_b : (long long)7 * n_a;
   w.rho_off_in_row = -1;
-  w.nres = g.kind == KTK_STATIC_RS ? 2 : 3;
+  w.nres = is_camera(g.kind) ? 2 : 3;
   w.row_len = row_doubles(p, g);
-  auto set = [&](int i, int off, int width, int col, int slot) { w.j_off[i] = off; w.width[i] = width; w.col_off[i] = col; w.slot[i] = slot; };
+  auto set = [&](int i, int off, int width, int col, int slot) { w.j_off[i] = off; w.width[i] = width; w.col_off[i] = col; w.slot[i] = slot; w.nk[i] = 4; };
   if (!split) {
-    if (g.kind == KTK_STATIC_RS) { w.nwin = 2; set(0, 0, 7, 0, 0); set(1, 56, 7, 0, 1); w.rho_off_in_row = 112; }
+    if (g.kind == KTK_NEWTON_RS) { w.nwin = 2; set(0, 0, 7, 0, 0); set(1, 56, 7, 0, 1); w.nk[1] = newton_window(p, g); w.rho_off_in_row = 56 + 14 * w.nk[1]; }
+    else if (g.kind == KTK_STATIC_RS) { w.nwin = 2; set(0, 0, 7, 0, 0); set(1, 56, 7, 0, 1); w.rho_off_in_row = 112; }
     else { w.nwin = 1; set(0, 0, 7, 0, 0); }
   } else if (g.kind == KTK_STATIC_RS) {
     w.nwin = 4; set(0, 0, 3, 0, 0); set(1, 24, 4, colB, 2); set(2, 56, 3, 0, 1); set(3, 80, 4, colB, 3); w.rho_off_in_row = 112;
@@ -1386,7 +1477,8 @@ static int apply_products(ktk_problem* p, int mode, uint32_t flags, const ktk_gr
     a.w = row_windows(p, g); a.n = (int)g.n; a.J = o.J;
     a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d;
     for (int w = 0; w < a.w.nwin; ++w) if (!a.idx[a.w.slot[w]]) return fail(KTK_EINVAL, "the group's index arrays are missing");
-    if (g.kind == KTK_STATIC_RS) {        // landmark index of every row, in the order the rows were written
+    if (mode == 3 && g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "ktk_jtj_diagonal_local over NewtonRsCameraMeasurement rows is not built");
+    if (is_camera(g.kind)) {        // landmark index of every row, in the order the rows were written
       if (flags & KTK_EVAL_DEVICE_ORDER) {
         if (g.perm.size() != (size_t)g.n) return fail(KTK_EINVAL, "device-order rows need an evaluation first");
         if (g.d_lm_sorted.n != (size_t)g.n) { int st = g.d_lm_sorted.upload(gather(g.lm, g.perm, 1), s); if (st) return st; KTK_CUDA(cudaStreamSynchronize(s)); }
@@ -1464,7 +1556,7 @@ static int group_segments(const ktk_problem* p, const Group& g, int64_t i, int w
   const double dt = !split ? p->sp.dt : (which == 0 ? p->spl.dt_r3 : p->spl.dt_so3);
   const double tmin = split ? split_min_time(p->spl) : p->sp.t0;
   const double tmax = split ? split_max_time(p->spl) : spline_max_time(p->sp);
-  if (g.kind == KTK_STATIC_RS) {
+  if (is_camera(g.kind)) {
     double t1, t2;
     if (g.ref_t0[i] <= g.obs_t0[i]) { t1 = g.ref_t0[i]; t2 = g.obs_t0[i]; } else { t1 = g.obs_t0[i]; t2 = g.ref_t0[i]; }
     if (!g.sensor.time_offset_locked) { t1 -= g.sensor.max_time_offset; t2 += g.sensor.max_time_offset; }
@@ -1512,18 +1604,24 @@ int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const
                          const int32_t* i0o, double* out) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !knot_ids || !Jp || !i0r || !i0o || !out) return fail(KTK_EINVAL, "bad argument");
   const Group& g = *p->groups[group];
-  if (g.kind != KTK_STATIC_RS) return fail(KTK_EINVAL, "not a static-RS group");
+  if (!is_camera(g.kind)) return fail(KTK_EINVAL, "not a camera group");
   if (p->traj != 0) return fail(KTK_EINVAL, "ktk_expand_static_rs is for the SE3 layout");
+  const int W = g.kind == KTK_NEWTON_RS ? newton_window(p, g) : 4, row_len = 58 + 14 * W;
   std::memset(out, 0, sizeof(double) * (size_t)g.n * cap * 14);
   for (int64_t i = 0; i < g.n; ++i) {
     const int32_t* ids = knot_ids + (size_t)i * cap;
     for (int w = 0; w < 2; ++w) {
       const int base = w == 0 ? i0r[i] : i0o[i];
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < (w == 0 ? 4 : W); ++k) {
+        const double* src = Jp + (size_t)i * row_len + w * 56 + k * 14;
         int pos = -1;
         for (int c = 0; c < cap && ids[c] >= 0; ++c) if (ids[c] == base + k) { pos = c; break; }
-        if (pos < 0) return fail(KTK_EINVAL, "active knot not in the structural block list");
-        const double* src = Jp + (size_t)i * kCamRow + w * 56 + k * 14;
+        if (pos < 0) {       // a Newton-RS row carries the widest span of its group: blocks past this row's own span are zero
+          bool zero = true;
+          for (int c = 0; c < 14; ++c) zero = zero && src[c] == 0.0;
+          if (zero && g.kind == KTK_NEWTON_RS) continue;
+          return fail(KTK_EINVAL, "active knot not in the structural block list");
+        }
         double* dst = out + ((size_t)i * cap + pos) * 14;
         for (int c = 0; c < 14; ++c) dst[c] += src[c];
       }

@@ -1,0 +1,311 @@
+// kontiki_b200 -- NewtonRsCameraMeasurement (measurements/newton_rscamera_measurement.h:23-120) on the SE3 spline.
+//
+// The reference's Jacobian of this measurement is the forward-mode (ceres::Jet) derivative THROUGH the Newton iteration on
+// the row time: t_{k+1} = t_k - f_k / df_k carries a dual part, and df_k comes from hand-written first-derivative formulas
+// (:76-96) whose own dual part needs second-order quantities of the spline.  There is no closed form worth having, so
+// this path differentiates exactly as the reference does -- one forward-mode direction per thread (dualnum.cuh D1) --
+// but on the hoisted structure of the rest of the library:
+//   * the knot-pair logs omega_j and their 6x14 ambient Jacobians D_j come from the K0 prepass (no log in the loop):
+//     direction "component c of knot k" seeds  d omega_p = Da_p[:, c] (k = p-1) / Db_p[:, c] (k = p)  and knot i0 itself;
+//   * the reference side X(t_ref) is evaluated once per landmark (k_landmark_ref record) and enters as a seed
+//     dX = dX/dknot[:, c]  (reference-window directions) or dX/drho.
+// Operation order follows uniform_se3_spline_trajectory.h:101-194 where it decides which derivative a non-unit knot
+// quaternion sees: the raw knot enters through P0.matrix() (:178-190) and the first translation
+// step q0 * a1 (Sophus SE3::operator*=), every composed rotation is re-normalised.
+#pragma once
+#include "spline_math.cuh"
+
+namespace kb {
+
+template <class T> struct TV3 { T x, y, z; };
+template <class T> struct TQ { T x, y, z, w; };
+template <class T> struct TM3 { T a[9]; };
+
+template <class T> KB_HD TV3<T> tv3(T x, T y, T z) { TV3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <class T> KB_HD TV3<T> operator+(const TV3<T>& a, const TV3<T>& b) { return tv3<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <class T> KB_HD TV3<T> operator-(const TV3<T>& a, const TV3<T>& b) { return tv3<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <class T> KB_HD TV3<T> operator*(const T& s, const TV3<T>& a) { return tv3<T>(s * a.x, s * a.y, s * a.z); }
+template <class T> KB_HD T tdot(const TV3<T>& a, const TV3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <class T> KB_HD TV3<T> tcross(const TV3<T>& a, const TV3<T>& b) { return tv3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+template <class T> KB_HD TM3<T> operator*(const TM3<T>& A, const TM3<T>& B) {
+  TM3<T> r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.a[3 * i + j] = A.a[3 * i] * B.a[j] + A.a[3 * i + 1] * B.a[3 + j] + A.a[3 * i + 2] * B.a[6 + j];
+  return r; }
+template <class T> KB_HD TM3<T> operator+(const TM3<T>& A, const TM3<T>& B) { TM3<T> r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.a[i] = A.a[i] + B.a[i]; return r; }
+template <class T> KB_HD TV3<T> operator*(const TM3<T>& A, const TV3<T>& v) {
+  return tv3<T>(A.a[0] * v.x + A.a[1] * v.y + A.a[2] * v.z, A.a[3] * v.x + A.a[4] * v.y + A.a[5] * v.z, A.a[6] * v.x + A.a[7] * v.y + A.a[8] * v.z); }
+// A * B^T
+template <class T> KB_HD TM3<T> tmul_nt(const TM3<T>& A, const TM3<T>& B) {
+  TM3<T> r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) r.a[3 * i + j] = A.a[3 * i] * B.a[3 * j] + A.a[3 * i + 1] * B.a[3 * j + 1] + A.a[3 * i + 2] * B.a[3 * j + 2];
+  return r; }
+// s * A * hat(v): every row of A crossed with v
+template <class T> KB_HD TM3<T> tmul_hat(const T& s, const TM3<T>& A, const TV3<T>& v) {
+  TM3<T> r;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const T ax = A.a[3 * i], ay = A.a[3 * i + 1], az = A.a[3 * i + 2];
+    r.a[3 * i] = s * (ay * v.z - az * v.y); r.a[3 * i + 1] = s * (az * v.x - ax * v.z); r.a[3 * i + 2] = s * (ax * v.y - ay * v.x); }
+  return r; }
+
+// ---- Eigen::Quaternion semantics (x, y, z, w) -------------------------------------------------------------------------------
+template <class T> KB_HD TQ<T> tqmul(const TQ<T>& a, const TQ<T>& b) {          // Hamilton product, no renormalisation
+  TQ<T> r;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  return r; }
+template <class T> KB_HD TQ<T> tqconj(const TQ<T>& q) { TQ<T> r; r.x = -q.x; r.y = -q.y; r.z = -q.z; r.w = q.w; return r; }
+template <class T> KB_HD TQ<T> tqnormalized(const TQ<T>& q) {
+  const T inv = T(1.0) / t_sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  TQ<T> r; r.x = q.x * inv; r.y = q.y * inv; r.z = q.z * inv; r.w = q.w * inv; return r; }
+// Eigen's q * v: v + w (2 u x v) + u x (2 u x v) -- a polynomial in q, not scale invariant
+template <class T> KB_HD TV3<T> tqrot(const TQ<T>& q, const TV3<T>& v) {
+  const TV3<T> u = tv3<T>(q.x, q.y, q.z);
+  TV3<T> uv = tcross(u, v); uv = uv + uv;
+  return v + q.w * uv + tcross(u, uv); }
+template <class T> KB_HD TM3<T> tqmat(const TQ<T>& q) {                        // Eigen toRotationMatrix (same polynomial)
+  const T tx = T(2.0) * q.x, ty = T(2.0) * q.y, tz = T(2.0) * q.z;
+  const T twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x, tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  TM3<T> r;
+  r.a[0] = T(1.0) - (tyy + tzz); r.a[1] = txy - twz; r.a[2] = txz + twy;
+  r.a[3] = txy + twz; r.a[4] = T(1.0) - (txx + tzz); r.a[5] = tyz - twx;
+  r.a[6] = txz - twy; r.a[7] = tyz + twx; r.a[8] = T(1.0) - (txx + tyy);
+  return r; }
+
+// A_j = exp(B omega): rotation quaternion, its matrix E, translation a = V (B upsilon).  Coefficients as entire functions of
+// x = theta^2 (series below 1e-2: the closed forms cancel), so that B -> 0 needs no special case.
+template <class T> struct TExp { TQ<T> q; TM3<T> E; TV3<T> a; };
+template <class T> KB_HD TExp<T> se3_exp_t(const T* om, const T& B) {
+  const TV3<T> th = tv3<T>(B * om[3], B * om[4], B * om[5]), up = tv3<T>(B * om[0], B * om[1], B * om[2]);
+  const T x = tdot(th, th);
+  T sh, ch, cb, cc;        // sin(theta/2)/theta, cos(theta/2), (1 - cos theta)/theta^2, (theta - sin theta)/theta^3
+  if (value(x) < KB_SMALL_X) {
+    const T h = T(0.25) * x;
+    sh = T(0.5) * (T(1.0) + h * (T(-1.0 / 6.0) + h * (T(1.0 / 120.0) + h * (T(-1.0 / 5040.0) + h * T(1.0 / 362880.0)))));
+    ch = T(1.0) + h * (T(-0.5) + h * (T(1.0 / 24.0) + h * (T(-1.0 / 720.0) + h * (T(1.0 / 40320.0) + h * T(-1.0 / 3628800.0)))));
+    cb = T(0.5) + x * (T(-1.0 / 24.0) + x * (T(1.0 / 720.0) + x * (T(-1.0 / 40320.0) + x * (T(1.0 / 3628800.0) + x * T(-1.0 / 479001600.0)))));
+    cc = T(1.0 / 6.0) + x * (T(-1.0 / 120.0) + x * (T(1.0 / 5040.0) + x * (T(-1.0 / 362880.0) + x * (T(1.0 / 39916800.0) + x * T(-1.0 / 6227020800.0)))));
+  } else {
+    const T theta = t_sqrt(x), half = T(0.5) * theta;
+    sh = t_sin(half) / theta; ch = t_cos(half);
+    cb = (T(1.0) - t_cos(theta)) / x; cc = (theta - t_sin(theta)) / (x * theta);
+  }
+  TExp<T> e;
+  e.q.x = sh * th.x; e.q.y = sh * th.y; e.q.z = sh * th.z; e.q.w = ch;
+  e.E = tqmat(e.q);
+  // a = V up,  V = I + cb hat(th) + cc hat(th)^2
+  const TV3<T> c1 = tcross(th, up), c2 = tcross(th, c1);
+  e.a = up + cb * c1 + cc * c2;
+  return e;
+}
+
+// position, velocity, orientation, world angular velocity of the cumulative spline at basis (B, dB):
+// uniform_se3_spline_trajectory.h:81-99 (outputs) and :101-194 (P, P').
+template <class T> struct TEval { TV3<T> p, v, w; TQ<T> q; };
+template <class T> KB_HD TEval<T> se3_eval_t(const T* k0, const T* om1, const T* om2, const T* om3, const T* B, const T* dB) {
+  const T* om[3] = {om1, om2, om3};
+  TExp<T> e[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) e[j] = se3_exp_t<T>(om[j], B[j]);
+  TEval<T> r;
+  // P = P0 A1 A2 A3 with Sophus' operator*= : t += so3 * a (the raw knot for j = 1), so3 = normalised product
+  TQ<T> q; q.x = k0[0]; q.y = k0[1]; q.z = k0[2]; q.w = k0[3];
+  const TQ<T> q0 = q;
+  TV3<T> t = tv3<T>(k0[4], k0[5], k0[6]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { t = t + tqrot(q, e[j].a); q = tqnormalized(tqmul(q, e[j].q)); }
+  r.p = t; r.q = q;
+  // P' = P0.matrix() (A1' A2 A3 + A1 A2' A3 + A1 A2 A3'),  A_j' = A_j hat(omega_j) dB_j = dB_j [[E_j hat(phi_j), E_j upsilon_j], [0, 0]]
+  TM3<T> Ed[3]; TV3<T> ad[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    Ed[j] = tmul_hat(dB[j], e[j].E, tv3<T>(om[j][3], om[j][4], om[j][5]));
+    ad[j] = dB[j] * (e[j].E * tv3<T>(om[j][0], om[j][1], om[j][2]));
+  }
+  const TM3<T> E23 = e[1].E * e[2].E, E12 = e[0].E * e[1].E;
+  const TV3<T> c2 = e[1].E * e[2].a + e[1].a;                                  // translation of A2 A3
+  const TM3<T> MR = Ed[0] * E23 + e[0].E * (Ed[1] * e[2].E) + E12 * Ed[2];
+  const TV3<T> Mt = (Ed[0] * c2 + ad[0]) + e[0].E * (Ed[1] * e[2].a + ad[1]) + E12 * ad[2];
+  const TM3<T> R0 = tqmat(q0);                                                 // raw knot: P0.matrix()
+  r.v = R0 * Mt;
+  const TM3<T> W = tmul_nt(R0 * MR, tqmat(q));                                 // P'[0:3,0:3] * R(P)^T  (:93-96)
+  r.w = tv3<T>(T(0.5) * (W.a[7] - W.a[5]), T(0.5) * (W.a[2] - W.a[6]), T(0.5) * (W.a[3] - W.a[1]));
+  return r;
+}
+
+// CameraView::EvaluateProjection(X, dX, derive = true): y and the hand-written dy (pinhole_camera.h:47-61, atan_camera.h:54-90)
+template <class T> KB_HD void camera_project_t(const CameraConst& cam, const TV3<T>& X, const TV3<T>& dX, T* y, T* dy) {
+  const double* K = cam.K;
+  if (cam.model == 0) {
+    const TV3<T> p = tv3<T>(T(K[0]) * X.x + T(K[1]) * X.y + T(K[2]) * X.z, T(K[3]) * X.x + T(K[4]) * X.y + T(K[5]) * X.z, T(K[6]) * X.x + T(K[7]) * X.y + T(K[8]) * X.z);
+    const TV3<T> dp = tv3<T>(T(K[0]) * dX.x + T(K[1]) * dX.y + T(K[2]) * dX.z, T(K[3]) * dX.x + T(K[4]) * dX.y + T(K[5]) * dX.z, T(K[6]) * dX.x + T(K[7]) * dX.y + T(K[8]) * dX.z);
+    y[0] = p.x / p.z; y[1] = p.y / p.z;
+    const T z2 = p.z * p.z + T(1e-32);
+    dy[0] = (dp.x * p.z - p.x * dp.z) / z2;
+    dy[1] = (dp.y * p.z - p.y * dp.z) / z2;
+    return;
+  }
+  const T eps = T(1e-32), gamma = T(cam.gamma), wc0 = T(cam.wc[0]), wc1 = T(cam.wc[1]);
+  const T A0 = X.x / (X.z + eps), A1 = X.y / (X.z + eps);
+  const T L0 = A0 - wc0, L1 = A1 - wc1;
+  const T r = t_sqrt((L0 * L0 + L1 * L1) + eps);
+  const T f = t_atan(r * gamma) / gamma;
+  const T g0 = L0 / r, g1 = L1 / r;
+  const T Y0 = wc0 + f * g0, Y1 = wc1 + f * g1;
+  y[0] = T(K[0]) * Y0 + T(K[1]) * Y1 + T(K[2]);
+  y[1] = T(K[3]) * Y0 + T(K[4]) * Y1 + T(K[5]);
+  const T dx = (dX.x * X.z - X.x * dX.z) / (X.z * X.z + eps);
+  const T dyy = (dX.y * X.z - X.y * dX.z) / (X.z * X.z + eps);
+  const T common = g0 * dx + g1 * dyy;
+  const T df = common / (T(1.0) + gamma * gamma * r * r);
+  const T dgu = (dx * r - L0 * common) / (r * r);
+  const T du = f * dgu + df * g0;
+  const T dgv = (dyy * r - L1 * common) / (r * r);
+  const T dv = f * dgv + df * g1;
+  dy[0] = T(K[0]) * du + T(K[1]) * dv;
+  dy[1] = T(K[3]) * du + T(K[4]) * dv;
+}
+
+// One direction of a Newton-RS row.  `dir` selects the seed (see the packed layout in include/kontiki_b200.h):
+//   [0, 28)            reference-window knot dir/7, component dir%7   -> dX = column of the landmark record's dX/dknots
+//   [28, 28 + 7 W)     observation-window knot kbase + (dir-28)/7, component (dir-28)%7
+//   28 + 7 W           rho
+//   anything else      values only
+// Returns 0 or kStatusRange; y = projection y_out (2), dy = its derivative along the seed.
+struct NewtonRow { double y[2], dy[2]; int iterations; };
+KB_HD int newton_rs_direction(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                              const double* obs_uv, double obs_t0, double ref_t0, int kbase, int W, int dir, NewtonRow& out) {
+  typedef D1 T;
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const int rho_dir = 28 + 7 * W;
+  // seeds of the reference side (record: X(3) | dX/drho(3) | rho | i0_ref | dX/dknots [4][3][7])
+  TV3<T> X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
+  T rho = T(rec[6]);
+  if (dir >= 0 && dir < 28) { const double* d = rec + kRefDOff + 21 * (dir / 7) + dir % 7; X.x.d = d[0]; X.y.d = d[7]; X.z.d = d[14]; }
+  else if (dir == rho_dir) { X.x.d = rec[3]; X.y.d = rec[4]; X.z.d = rec[5]; rho.d = 1.0; }
+  const int ok = (dir >= 28 && dir < rho_dir) ? kbase + (dir - 28) / 7 : -1;      // observation-window knot of this direction
+  const int oc = (dir - 28) % 7;
+  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
+  const TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  // newton_rscamera_measurement.h:37-58
+  const double rows = (double)cam.rows;
+  const double t0_obs = add_rn(obs_t0, cam.time_offset);
+  T t_obs = T(static_rs_time(cam, obs_t0, obs_uv[1]));                      // not FMA-contracted: it fixes the first knot index
+  const double max_dt = 0.5 * cam.readout / rows, max_dt2 = max_dt * max_dt;
+  const double min_bound = t0_obs, max_bound = add_rn(t0_obs, cam.readout);
+  T y[2] = {T(0.0), T(0.0)};
+  out.iterations = 0;
+  for (int iter = 0; iter < 5; ++iter) {
+    // trajectory.Evaluate(t_obs): SplineView::Evaluate + CalculateIndexAndInterpolationAmount (floor drops the derivative)
+    int i0; double u0;
+    if (locate_in_segments(nseg, s0, s1, t_obs.a, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+    if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;               // outside the observation span's knots
+    const T u = T(u0, t_obs.d / sp.dt);
+    const T u2 = u * u, u3 = u2 * u;
+    const double di = 1.0 / sp.dt;
+    T B[3], dB[3];
+    B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
+    B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
+    B[2] = u3 * T(1.0 / 6.0);
+    dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
+    dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
+    dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
+    T k0[7], om[3][6];
+    const double* kn = knots + (size_t)i0 * kKnotStride;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) k0[c] = T(kn[c], (ok == i0 && oc == c) ? 1.0 : 0.0);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int p = i0 + 1 + j;                                              // pair (knot p-1, knot p)
+      const double* pr = pairs + (size_t)p * kPairStride;
+      const double* D = ok == p - 1 ? pr + kPairDOff : (ok == p ? pr + kPairDOff + kPairSide : nullptr);
+#pragma unroll
+      for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m], D ? D[m * 8 + oc] : 0.0);
+    }
+    const TEval<T> ev = se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
+    // :66-96
+    TQ<T> wq; wq.x = ev.w.x; wq.y = ev.w.y; wq.z = ev.w.z; wq.w = T(0.0);
+    TQ<T> dq = tqmul(wq, ev.q); dq.x = T(0.5) * dq.x; dq.y = T(0.5) * dq.y; dq.z = T(0.5) * dq.z; dq.w = T(0.5) * dq.w;
+    const TQ<T> dq_inv = tqconj(dq), q_inv = tqconj(ev.q);
+    const TV3<T> s = X - rho * ev.p;
+    const TV3<T> ds = (T(0.0) - rho) * ev.v;
+    const TV3<T> X_obs = tqrot(q_inv, s);
+    const TV3<T> X_cam = tqrot(qct, X_obs) + rho * pct;
+    TQ<T> sq; sq.x = s.x; sq.y = s.y; sq.z = s.z; sq.w = T(0.0);
+    TQ<T> dsq; dsq.x = ds.x; dsq.y = ds.y; dsq.z = ds.z; dsq.w = T(0.0);
+    const TQ<T> a1 = tqmul(tqmul(dq_inv, sq), ev.q), a2 = tqmul(tqmul(q_inv, dsq), ev.q), a3 = tqmul(tqmul(q_inv, sq), dq);
+    const TV3<T> dX_obs = tv3<T>(a1.x + a2.x + a3.x, a1.y + a2.y + a3.y, a1.z + a2.z + a3.z);
+    const TV3<T> dX_cam = tqrot(qct, dX_obs) + rho * pct;                    // sic (:92)
+    T dy[2];
+    camera_project_t<T>(cam, X_cam, dX_cam, y, dy);
+    // :101-117
+    const T f = y[1] - (T(rows) * (t_obs - T(t0_obs)) / T(cam.readout));
+    const T df = dy[1] - T(rows / cam.readout);
+    const T dt = f / df;
+    t_obs = t_obs - dt;
+    out.iterations = iter + 1;
+    if (dt.a * dt.a < max_dt2) break;
+    if (t_obs.a < min_bound) t_obs = T(min_bound);
+    else if (t_obs.a > max_bound) t_obs = T(max_bound);
+  }
+  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+  return 0;
+}
+
+// Knots of the observation span {t0_obs - 1e-3, t0_obs + readout + 1e-3} of the residual (newton_rscamera_measurement.h:210-236,
+// spline_base.h:371-377), time offset locked: first knot and count.  Every row time the iteration visits lies inside.
+KB_HD int newton_obs_window_base(const SplineConst& sp, const CameraConst& cam, double obs_t0) { return knot_floor(sub_rn(obs_t0, 1e-3), sp.t0, sp.dt); }
+KB_HD int newton_obs_window_size(const SplineConst& sp, const CameraConst& cam, double obs_t0) {
+  return knot_floor(add_rn(add_rn(obs_t0, cam.readout), 1e-3), sp.t0, sp.dt) + 4 - newton_obs_window_base(sp, cam, obs_t0); }
+
+// Where direction `dir` lands in the packed row [ref 4x(2x7) | obs W x(2x7) | rho 2] (residual row 0; row 1 is +7, rho +1)
+KB_HD int newton_dir_offset(int dir, int W, int& stride) {
+  stride = 7;
+  if (dir < 28) return 14 * (dir / 7) + dir % 7;
+  if (dir < 28 + 7 * W) { const int d = dir - 28; return 56 + 14 * (d / 7) + d % 7; }
+  stride = 1;
+  return 56 + 14 * W;
+}
+// r = weight (uv_obs - y) (:150-155), column j = -weight dy, then ceres::HuberLoss + Corrector as Ceres applies them after Evaluate
+KB_HD void newton_rs_finish(const NewtonRow& o, const double* obs_uv, double weight, double huber_c, double* r, double* j) {
+  const double r0 = weight * (obs_uv[0] - o.y[0]), r1 = weight * (obs_uv[1] - o.y[1]);
+  double j0 = -weight * o.dy[0], j1 = -weight * o.dy[1], rs = 1.0;
+  if (huber_c > 0.0) {
+    const HuberScale h = huber_scale(huber_c, r0 * r0 + r1 * r1);
+    const double rj = r0 * j0 + r1 * j1;
+    j0 = h.sqrt_rho1 * (j0 - h.alpha_sq_norm * r0 * rj); j1 = h.sqrt_rho1 * (j1 - h.alpha_sq_norm * r1 * rj);
+    rs = h.residual_scaling;
+  }
+  r[0] = rs * r0; r[1] = rs * r1; j[0] = j0; j[1] = j1;
+}
+// A whole row, direction after direction (host check; the kernel runs one direction per thread).
+KB_HD int newton_rs_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                        const double* obs_uv, double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c,
+                        double* r, double* J, int* iterations) {
+  const int ndir = 29 + 7 * W;
+  for (int dir = 0; dir < ndir; ++dir) {
+    NewtonRow o;
+    const int st = newton_rs_direction(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, dir, o);
+    if (st != 0) return st;
+    double j[2]; int stride;
+    newton_rs_finish(o, obs_uv, weight, huber_c, r, j);
+    const int off = newton_dir_offset(dir, W, stride);
+    J[off] = j[0]; J[off + stride] = j[1];
+    *iterations = o.iterations;
+  }
+  return 0;
+}
+
+}  // namespace kb

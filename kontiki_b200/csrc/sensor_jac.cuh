@@ -156,15 +156,15 @@ KB_HD int static_rs_sensor_jac_se3(const SplineConst& sp, const CameraConst& cam
   se3_body_twist3(o1, o1 + kPairStride, o1 + 2 * kPairStride, bo, sp.dt, so, t1, t2);
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  const M3 Km = load_m3(cam.K);
-  const V3 yv = load_m3(cam.Kinv) * v3(ref_uv[0], ref_uv[1], 1.0) - rho * pct;
+  const V3 yv = camera_unproject(cam, ref_uv[0], ref_uv[1]) - rho * pct;
   const V3 Xref = mul_t(Rct, yv);
   const V3 X = Pr.R * Xref + rho * Pr.p;
   const V3 Xw = X - rho * Po.p;
   const V3 Xobs = mul_t(Po.R, Xw);
   const V3 RX = Rct * Xobs;
-  const V3 pr = Km * (RX + rho * pct);
-  const double iz = 1.0 / pr.z, y0 = pr.x * iz, y1 = pr.y * iz;
+  double y0, y1;
+  Mr<2> Jp0, Gc;
+  camera_project_jac(cam, RX + rho * pct, y0, y1, Jp0);
   const double r0 = weight * (obs_uv[0] - y0), rr1 = weight * (obs_uv[1] - y1);
   double c00 = 1.0, c01 = 0.0, c10 = 0.0, c11 = 1.0;
   if (huber_c > 0.0) {
@@ -172,9 +172,6 @@ KB_HD int static_rs_sensor_jac_se3(const SplineConst& sp, const CameraConst& cam
     c00 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * r0 * r0); c01 = -h.sqrt_rho1 * h.alpha_sq_norm * r0 * rr1;
     c10 = c01; c11 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * rr1 * rr1);
   }
-  Mr<2> Jp0, Gc;
-  Jp0.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); Jp0.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); Jp0.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
-  Jp0.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); Jp0.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); Jp0.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
   for (int c = 0; c < 3; ++c) { Gc.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Gc.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
   const Mr<2> Go = rmul(Gc, Rct), GX = rmul_nt(Go, Po.R), GXR = rmul(GX, Pr.R);
   // time offset: both evaluation times move with d

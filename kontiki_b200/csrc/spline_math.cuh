@@ -501,10 +501,56 @@ struct CameraConst {
   double time_offset, row_delta;   // row_delta = readout / rows (static_rscamera_measurement.h:30)
   double readout, max_time_offset;
   int time_offset_locked;
+  int rows;                 // image rows (camera.h:24-28)
+  int model;                // 0 PinholeCamera (pinhole_camera.h), 1 AtanCamera (atan_camera.h)
+  double wc[2], gamma;      // AtanCamera distortion centre and parameter (atan_camera.h:20-22)
 };
 KB_HD M3 load_m3(const double* a) { M3 m;
 #pragma unroll
   for (int i = 0; i < 9; ++i) m.a[i] = a[i]; return m; }
+
+// CameraView::Unproject: pinhole K^-1 [u v 1] (pinhole_camera.h:63-67); atan additionally undoes the distortion
+// L = phn.xy - wc, r = sqrt(|L|^2 + eps), f = tan(r gamma) / gamma, Y = [wc + f L / r, 1] (atan_camera.h:92-103).
+KB_HD V3 camera_unproject(const CameraConst& cam, double u, double v) {
+  const V3 ph = load_m3(cam.Kinv) * v3(u, v, 1.0);
+  if (cam.model == 0) return ph;
+  const double L0 = ph.x - cam.wc[0], L1 = ph.y - cam.wc[1];
+  const double r = sqrt((L0 * L0 + L1 * L1) + 1e-32);
+  const double f = tan(r * cam.gamma) / cam.gamma;
+  return v3(cam.wc[0] + f * L0 / r, cam.wc[1] + f * L1 / r, 1.0);
+}
+// CameraView::Project (sensors/camera.h:59-63) and its 2 x 3 Jacobian d y / d X.
+//   pinhole (pinhole_camera.h:47-51): p = K X, y = p.xy / p.z
+//   atan (atan_camera.h:54-75): A = X.xy / (X.z + eps), L = A - wc, r = sqrt(|L|^2 + eps), f = atan(r gamma) / gamma,
+//     g = L / r, Y = [wc + f g, 1], y = (K Y).xy;   dY/dA = f' g g^T + (f / r)(I - g g^T), f' = 1 / (1 + gamma^2 r^2)
+KB_HD void camera_project_jac(const CameraConst& cam, V3 X, double& y0, double& y1, Mr<2>& J) {
+  const M3 Km = load_m3(cam.K);
+  if (cam.model == 0) {
+    const V3 pr = Km * X;
+    const double iz = 1.0 / pr.z;
+    y0 = pr.x * iz; y1 = pr.y * iz;
+    J.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); J.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); J.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
+    J.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); J.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); J.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
+    return;
+  }
+  const double eps = 1e-32;
+  const double iz = 1.0 / (X.z + eps);
+  const double A0 = X.x * iz, A1 = X.y * iz;
+  const double L0 = A0 - cam.wc[0], L1 = A1 - cam.wc[1];
+  const double r = sqrt((L0 * L0 + L1 * L1) + eps), ir = 1.0 / r;
+  const double f = atan(r * cam.gamma) / cam.gamma;
+  const double g0 = L0 * ir, g1 = L1 * ir;
+  const double Y0 = cam.wc[0] + f * g0, Y1 = cam.wc[1] + f * g1;
+  y0 = Km.a[0] * Y0 + Km.a[1] * Y1 + Km.a[2];
+  y1 = Km.a[3] * Y0 + Km.a[4] * Y1 + Km.a[5];
+  const double fr = f * ir, dd = 1.0 / (1.0 + cam.gamma * cam.gamma * r * r) - fr;
+  const double m00 = fr + dd * g0 * g0, m01 = dd * g0 * g1, m11 = fr + dd * g1 * g1;
+  // dA/dX = iz [I2 | -A]
+  const double d0[3] = {iz * m00, iz * m01, -iz * (m00 * A0 + m01 * A1)};
+  const double d1[3] = {iz * m01, iz * m11, -iz * (m01 * A0 + m11 * A1)};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { J.a[c] = Km.a[0] * d0[c] + Km.a[1] * d1[c]; J.a[3 + c] = Km.a[3] * d0[c] + Km.a[4] * d1[c]; }
+}
 
 // Reference side, ONCE PER LANDMARK REFERENCE (hoisted: the reference re-evaluates it for every observation).
 // All observations of a landmark share the reference observation (landmark.h:19-54), hence
@@ -519,7 +565,7 @@ KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const doub
   pose_forward(k0, p1, p2, p3, bs, P);
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  const V3 yh = load_m3(cam.Kinv) * v3(ref_uv[0], ref_uv[1], 1.0);
+  const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
   const V3 Xref = mul_t(Rct, yh - rho * pct);
   const V3 X = P.R * Xref + rho * P.p;
   const V3 dXr = P.p - P.R * mul_t(Rct, pct);
@@ -545,12 +591,11 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
   const double rho = ref[6];
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  const M3 Km = load_m3(cam.K);
   const V3 Xobs = mul_t(P.R, X - rho * P.p);                 // static_rscamera_measurement.h:49
   const V3 Xc = Rct * Xobs + rho * pct;                      // :52
-  const V3 pr = Km * Xc;                                     // pinhole_camera.h:47-51
-  const double iz = 1.0 / pr.z;
-  const double y0 = pr.x * iz, y1 = pr.y * iz;
+  double y0, y1;
+  Mr<2> Jp0;                                                 // d y / d Xc
+  camera_project_jac(cam, Xc, y0, y1, Jp0);                  // pinhole_camera.h:47-51 / atan_camera.h:54-75
   double r0 = weight * (obs_uv[0] - y0), r1 = weight * (obs_uv[1] - y1);
   // ceres::HuberLoss + Corrector folded into the row scale: J <- sqrt(rho') (J - alpha/|r|^2 r r^T J), r <- r * scaling
   // (2x2 matrix C applied to the two rows; identity when the loss is off or in its quadratic region)
@@ -563,9 +608,6 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
   }
   r[0] = rs * r0; r[1] = rs * r1;
   // d r / d Xc = -weight * C * d y / d Xc   (2 x 3)
-  Mr<2> Jp0;
-  Jp0.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); Jp0.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); Jp0.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
-  Jp0.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); Jp0.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); Jp0.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
   Mr<2> Jp;
 #pragma unroll
   for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }

@@ -219,7 +219,7 @@ KB_HD void landmark_ref_split(const CameraConst& cam, const double* c0, const Ba
   const V3 p = r3_combine(c0, br.Bp);
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  const V3 yh = load_m3(cam.Kinv) * v3(ref_uv[0], ref_uv[1], 1.0);
+  const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
   const V3 Xref = mul_t(Rct, yh - rho * pct);
   const V3 RX = R * Xref;
   const V3 X = RX + rho * p;
@@ -247,13 +247,12 @@ KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const B
   const V3 p = r3_combine(c0, br.Bp);
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
-  const M3 Km = load_m3(cam.K);
   const V3 Xw = X - rho * p;
   const V3 Xobs = mul_t(R, Xw);
   const V3 Xc = Rct * Xobs + rho * pct;
-  const V3 pr = Km * Xc;
-  const double iz = 1.0 / pr.z;
-  const double y0 = pr.x * iz, y1 = pr.y * iz;
+  double y0, y1;
+  Mr<2> Jp0;
+  camera_project_jac(cam, Xc, y0, y1, Jp0);
   double r0 = weight * (obs_uv[0] - y0), r1 = weight * (obs_uv[1] - y1);
   double c00 = 1.0, c01 = 0.0, c10 = 0.0, c11 = 1.0, rs = 1.0;
   if (huber_c > 0.0) {
@@ -263,9 +262,6 @@ KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const B
     rs = h.residual_scaling;
   }
   r[0] = rs * r0; r[1] = rs * r1;
-  Mr<2> Jp0;
-  Jp0.a[0] = iz * (Km.a[0] - y0 * Km.a[6]); Jp0.a[1] = iz * (Km.a[1] - y0 * Km.a[7]); Jp0.a[2] = iz * (Km.a[2] - y0 * Km.a[8]);
-  Jp0.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); Jp0.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); Jp0.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
   Mr<2> Jp;
 #pragma unroll
   for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }

@@ -14,7 +14,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import _lib
-from .measurements import AccelerometerMeasurement, GyroscopeMeasurement, StaticRsCameraMeasurement, _problem_for
+from .measurements import AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, StaticRsCameraMeasurement, _problem_for
 from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
 
 
@@ -182,12 +182,12 @@ class TrajectoryEstimator:
         groups, self._landmarks, lm_index = {}, [], {}
         for i, m in enumerate(self._measurements):
             kind = type(m)
-            sensor = m.camera if kind is StaticRsCameraMeasurement else m.imu
+            sensor = m.camera if issubclass(kind, StaticRsCameraMeasurement) else m.imu
             groups.setdefault((kind, id(sensor)), (sensor, []))[1].append(i)
         self._groups = []
         for (kind, _), (sensor, rows) in groups.items():
             ms = [self._measurements[i] for i in rows]
-            if kind is StaticRsCameraMeasurement:
+            if issubclass(kind, StaticRsCameraMeasurement):
                 lm = []
                 for m in ms:
                     L = m.observation.landmark
@@ -195,10 +195,10 @@ class TrajectoryEstimator:
                         lm_index[id(L)] = len(self._landmarks)
                         self._landmarks.append(L)
                     lm.append(lm_index[id(L)])
-                g = p.add_static_rs(sensor._c_camera(), np.array([m.observation.uv for m in ms]), [m.observation.view.t0 for m in ms],
+                g = getattr(p, kind._add)(sensor._c_camera(), np.array([m.observation.uv for m in ms]), [m.observation.view.t0 for m in ms],
                                     np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
                                     lm, [m.weight for m in ms], [m.huber_c for m in ms])
-                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor))
+                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor, newton=kind is NewtonRsCameraMeasurement))
             else:
                 fn = p.add_gyroscope if kind is GyroscopeMeasurement else p.add_accelerometer
                 g = fn(sensor._c_sensor(), [m.t for m in ms], np.array([m._x for m in ms]), [m.weight for m in ms])
@@ -287,7 +287,7 @@ class TrajectoryEstimator:
         row0 = 0
 
         def add_blocks(Jb, first_knot, width_amb, name, nres):
-            """Jb: (n, 4, nres, width_amb) ambient blocks at knots first_knot + k."""
+            """Jb: (n, nk, nres, width_amb) ambient blocks at knots first_knot + k (nk = 4; the observation span of a Newton-RS row)."""
             off, dof, spl = layout[name]
             if spl.locked:
                 return
@@ -299,8 +299,8 @@ class TrajectoryEstimator:
                 P = _quat_plus_jacobian(cp)
             else:
                 P = None
-            for k in range(4):
-                kn = first_knot + k
+            for k in range(Jb.shape[1]):
+                kn = np.minimum(first_knot + k, len(spl) - 1)      # blocks past a Newton-RS row's own span are zero
                 Jl = Jb[:, k] if P is None else np.einsum("nra,nad->nrd", Jb[:, k], P[kn])
                 r_idx = (row0 + nres * np.arange(n)[:, None, None] + np.arange(nres)[None, :, None]) + np.zeros((1, 1, dof), np.int64)
                 c_idx = (off + dof * kn)[:, None, None] + np.arange(dof)[None, None, :] + np.zeros((1, nres, 1), np.int64)
@@ -311,10 +311,11 @@ class TrajectoryEstimator:
             o = outs[grp["g"]]
             n = len(o["r"])
             if grp["kind"] == "cam":
-                J = o["J"].reshape(n, 114)
+                J = o["J"].reshape(n, -1)
+                nrow = J.shape[1]                                  # 114; Newton-RS 58 + 14 W
                 if not split:
                     add_blocks(J[:, :56].reshape(n, 4, 2, 7), o["i0"], 7, "se3", 2)
-                    add_blocks(J[:, 56:112].reshape(n, 4, 2, 7), o["i0_b"], 7, "se3", 2)
+                    add_blocks(J[:, 56:nrow - 2].reshape(n, -1, 2, 7), o["i0_b"], 7, "se3", 2)
                 else:
                     add_blocks(J[:, 0:24].reshape(n, 4, 2, 3), o["i0"], 3, "r3", 2)
                     add_blocks(J[:, 24:56].reshape(n, 4, 2, 4), o["i0_c"], 4, "so3", 2)
@@ -323,7 +324,7 @@ class TrajectoryEstimator:
                 col = self._lm_col[grp["lm"]]
                 free = col >= 0
                 r_idx = (row0 + 2 * np.arange(n)[:, None] + np.arange(2)[None, :])[free]
-                rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(col[free], 2)); vals.append(J[free, 112:114].reshape(-1))
+                rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(col[free], 2)); vals.append(J[free, nrow - 2:nrow].reshape(-1))
                 nres = 2
             else:
                 nres = 3
@@ -419,9 +420,14 @@ class TrajectoryEstimator:
         linear_solver: "host_cholesky" (rows copied to the host, sparse Cholesky with scipy -- the reference's split: Ceres
         does its linear algebra on the host too), "device_pcg" (rows stay on the GPU, matrix-free PCG, kontiki_b200/gn.py;
         multi-GPU aware), or "auto" (device_pcg above 20 000 measurements)."""
-        if linear_solver == "auto":
+        auto = linear_solver == "auto"
+        if auto:
             linear_solver = "device_pcg" if len(self._measurements) > 20000 else "host_cholesky"
         self._build()
+        if any(g.get("newton") for g in self._groups):
+            if linear_solver == "device_pcg" and not auto:
+                raise NotImplementedError("NewtonRsCameraMeasurement rows are solved by the host_cholesky path only")
+            linear_solver = "host_cholesky"
         if any(self._sensor_free(g["sensor"]) for g in self._groups):
             if linear_solver == "device_pcg":
                 raise NotImplementedError("unlocked sensor parameters are optimised by the host_cholesky path only")

@@ -64,6 +64,8 @@ class AccelerometerMeasurement(_ImuMeasurement):
 class StaticRsCameraMeasurement:
     """StaticRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (static_rscamera_measurement.h:62-69)"""
 
+    _add = "add_static_rs"
+
     def __init__(self, camera, observation, huber_c=5.0, weight=1.0):
         self.camera, self.observation, self.huber_c, self.weight = camera, observation, float(huber_c), float(weight)
 
@@ -75,7 +77,7 @@ class StaticRsCameraMeasurement:
     def _residual(self, trajectory, weight):
         p, knots = _problem_for(trajectory)
         r = self._row()
-        p.add_static_rs(self.camera._c_camera(), r["obs_uv"], r["obs_t0"], r["ref_uv"], r["ref_t0"], [0], [weight])
+        getattr(p, self._add)(self.camera._c_camera(), r["obs_uv"], r["obs_t0"], r["ref_uv"], r["ref_t0"], [0], [weight])
         return p.evaluate(knots, np.array([r["rho"]]), _lib.EVAL_RESIDUALS)[0]["r"][0]      # no loss: error() is the raw residual
 
     def error(self, trajectory):
@@ -86,3 +88,9 @@ class StaticRsCameraMeasurement:
         return self.observation.uv - self._residual(trajectory, 1.0)
 
     measure = project
+
+
+class NewtonRsCameraMeasurement(StaticRsCameraMeasurement):
+    """NewtonRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (newton_rscamera_measurement.h:127-141): the row
+    time of the projection is found by a 5-step Newton iteration instead of being read off the observed row."""
+    _add = "add_newton_rs"

@@ -1,6 +1,5 @@
 """Sensor classes with the reference's Python surface (python/src/kontiki/sensors/sensors_helper.h:12-35, camera_help.h:25-49,
-py_pinhole_camera.cc, py_basic_imu.cc).  Only what the built path needs is implemented: BasicImu and PinholeCamera with
-locked relative pose / time offset (sensors/sensors.h:91-109 defaults)."""
+py_pinhole_camera.cc, py_atan_camera.cc, py_basic_imu.cc): BasicImu, ConstantBiasImu, PinholeCamera, AtanCamera."""
 import numpy as np
 
 from . import _lib
@@ -75,3 +74,37 @@ class PinholeCamera(_Sensor):
         return _lib.make_camera(self.rows, self.cols, self.readout, self.camera_matrix, q_ct=self._q_ct, p_ct=self._p_ct, time_offset=self.time_offset,
                                 max_time_offset=self.max_time_offset, q_locked=self.relative_orientation_locked,
                                 p_locked=self.relative_position_locked, time_offset_locked=self.time_offset_locked)
+
+
+class AtanCamera(PinholeCamera):
+    """sensors/atan_camera.h; AtanCamera(rows, cols, readout, camera_matrix, wc, gamma) (py_atan_camera.cc:23-27): pinhole camera
+    matrix plus the FOV / arctangent distortion model with centre wc and parameter gamma."""
+
+    def __init__(self, rows, cols, readout, camera_matrix=None, wc=(0.0, 0.0), gamma=1.0):
+        super().__init__(rows, cols, readout, camera_matrix)
+        self.wc = np.asarray(wc, float).reshape(2).copy()
+        self.gamma = float(gamma)
+
+    def project(self, X):                                    # atan_camera.h:54-75
+        X = np.asarray(X, float)
+        eps = 1e-32
+        L = X[:2] / (X[2] + eps) - self.wc
+        r = np.sqrt(L @ L + eps)
+        f = np.arctan(r * self.gamma) / self.gamma
+        Y = np.array([*(self.wc + f * L / r), 1.0])
+        return (self.camera_matrix @ Y)[:2]
+
+    def unproject(self, y):                                  # atan_camera.h:92-103
+        eps = 1e-32
+        phn = np.linalg.inv(self.camera_matrix) @ np.array([y[0], y[1], 1.0])
+        L = phn[:2] - self.wc
+        r = np.sqrt(L @ L + eps)
+        f = np.tan(r * self.gamma) / self.gamma
+        return np.array([*(self.wc + f * L / r), 1.0])
+
+    def _c_camera(self):
+        c = super()._c_camera()
+        c.model = _lib.CAMERA_ATAN
+        c.wc[:] = [float(self.wc[0]), float(self.wc[1])]
+        c.gamma = self.gamma
+        return c

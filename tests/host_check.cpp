@@ -5,10 +5,17 @@
 #include <vector>
 
 #include "../kontiki_b200/csrc/sensor_jac.cuh"
+#include "../kontiki_b200/csrc/newton_math.cuh"
 
 using namespace kb;
 
+// camera model of the following hc_* camera calls (0 pinhole, 1 atan): set by hc_set_camera_model
+static int g_model = 0; static double g_wc[2] = {0.0, 0.0}, g_gamma = 0.0;
+static void finish_cam(CameraConst& cam, int rows) { cam.rows = rows; cam.model = g_model; cam.wc[0] = g_wc[0]; cam.wc[1] = g_wc[1]; cam.gamma = g_gamma; }
+
 extern "C" {
+
+void hc_set_camera_model(int model, double wc0, double wc1, double gamma) { g_model = model; g_wc[0] = wc0; g_wc[1] = wc1; g_gamma = gamma; }
 
 // knots7: n x 7 (reference layout) -> padded records + pair records (what ktk_evaluate's pack + K0 do on the device)
 void hc_prepass(const double* knots7, int n, double* knots8, double* pairs) {
@@ -40,6 +47,7 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
   for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
   for (int i = 0; i < n; ++i) {
     i0_ref[i] = -1; i0_obs[i] = -1;
     double* row = J + (size_t)114 * i;
@@ -62,6 +70,45 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     status[i] = static_rs_row_ref_half(cam, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, i0_ref + i, i0_obs + i, adj);
     if (status[i] == 0) static_rs_row_obs_half(knots8, pairs, f, adj, row + 56);
   }
+}
+
+// NewtonRsCameraMeasurement rows: what k_landmark_ref + k_newton_rs do, one (row, direction) at a time.
+// J: n x (58 + 14 W) packed [ref 4x(2x7) | obs W x(2x7) | rho 2]; kbase = first knot of the observation span.
+void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
+                  double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
+                  const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
+                  const int* lm_idx, const double* rho, const double* w, const double* huber_c, int W, double* r, double* J, int* i0_ref,
+                  int* kbase_out, int* iterations, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
+  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  const int row_len = 58 + 14 * W;
+  for (int i = 0; i < n; ++i) {
+    i0_ref[i] = -1; kbase_out[i] = -1; iterations[i] = 0;
+    double rec[kRefStride];
+    Segment s0, s1;
+    const int nseg = static_rs_segments(sp, cam, ref_t0[i], obs_t0[i], s0, s1);
+    int ir; double ur;
+    const int which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, static_rs_time(cam, ref_t0[i], ref_uv[2 * i + 1]), sp.t0, sp.dt, ir, ur);
+    if (which < 0) { status[i] = kStatusRange; continue; }
+    const Segment& sr = which == 0 ? s0 : s1;
+    status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
+    if (status[i] != 0) continue;
+    const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
+    status[i] = newton_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
+                              r + 2 * i, J + (size_t)row_len * i, iterations + i);
+    i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
+  }
+}
+int hc_newton_window(double t0, double dt, double readout, double obs_t0) {
+  SplineConst sp{t0, dt, 1 << 30, 0};
+  CameraConst cam; cam.readout = readout; cam.time_offset_locked = 1; cam.max_time_offset = 0.0;
+  return newton_obs_window_size(sp, cam, obs_t0);
 }
 
 
@@ -97,6 +144,7 @@ void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
   for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
   for (int i = 0; i < n; ++i) {
     for (int c = 0; c < 4; ++c) idx[4 * i + c] = -1;
     double* row = J + (size_t)114 * i;
@@ -154,6 +202,7 @@ void hc_static_rs_sensor_se3(double t0, double dt, int n_knots, const double* K,
   for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
   for (int i = 0; i < n; ++i)
     status[i] = static_rs_sensor_jac_se3(sp, cam, knots8, pairs, obs_uv + 2 * i, obs_t0[i], ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], w[i],
                                          huber_c ? huber_c[i] : 0.0, out + 16 * i);

@@ -19,7 +19,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "split_math.cuh", "sensor_jac.cuh", "lie_math.cuh", "dualnum.cuh")]
+        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("spline_math.cuh", "split_math.cuh", "sensor_jac.cuh", "lie_math.cuh", "dualnum.cuh", "newton_math.cuh")]
         if not os.path.exists(_OUT) or any(os.path.getmtime(d) > os.path.getmtime(_OUT) for d in deps):
             os.makedirs(os.path.dirname(_OUT), exist_ok=True)
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++", _SRC, "-o", _OUT])
@@ -66,8 +66,45 @@ def kinv_cofactor(K):
     return c / det
 
 
+def _set_camera_model(cam):
+    """PinholeCamera unless the oracle-style camera carries AtanCamera parameters (wc, gamma)."""
+    lib().hc_set_camera_model.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    if getattr(cam, "gamma", None) is None:
+        lib().hc_set_camera_model(0, 0.0, 0.0, 0.0)
+    else:
+        lib().hc_set_camera_model(1, float(cam.wc[0]), float(cam.wc[1]), float(cam.gamma))
+
+
+def newton_window(t0, dt, readout, obs_t0):
+    lib().hc_newton_window.argtypes = [C.c_double] * 4
+    return max(int(lib().hc_newton_window(t0, dt, readout, float(t))) for t in np.atleast_1d(obs_t0))
+
+
+def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    """NewtonRsCameraMeasurement rows in the packed layout [ref 4x(2x7) | obs W x(2x7) | rho 2]; W = widest observation span."""
+    _set_camera_model(cam)
+    k8, pairs = prepass(knots7)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    W = newton_window(t0, dt, cam.readout, obs_t0)
+    r, J = np.zeros((n, 2)), np.zeros((n, 58 + 14 * W))
+    ir, kb, it, st = (np.zeros(n, np.int32) for _ in range(4))
+    lib().hc_newton_rs(C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset),
+                       C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows), _p(k8), _p(pairs), n,
+                       _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc), int(W), _p(r), _p(J), _p(ir), _p(kb),
+                       _p(it), _p(st))
+    return dict(r=r, J=J, i0_ref=ir, i0_obs=kb, W=W, iterations=it, status=st)
+
+
 def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
     """cam: oracle.kto.Camera-like (K, q_ct, p_ct, time_offset, max_time_offset, d_locked, readout, rows)."""
+    _set_camera_model(cam)
     k8, pairs = prepass(knots7)
     obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
     obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
@@ -108,6 +145,7 @@ def imu_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, y, w=None, t
 
 
 def static_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    _set_camera_model(cam)
     v4, q4, pairs, st0 = split_prepass(vecs3, quats)
     obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
     obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
@@ -167,6 +205,7 @@ def imu_time_offset_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, 
 
 
 def static_rs_sensor_se3(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    _set_camera_model(cam)
     k8, pairs = prepass(knots7)
     obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
     obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)

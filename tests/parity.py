@@ -23,14 +23,20 @@ def oracle_imu(traj, which, t, y, w=None, imu=None):
     return dict(r=res["r"], J=res["Ja"][:, :4], i0=res["i0_a"])
 
 
-def scatter_cam(Jp, i0_ref, i0_obs, ids):
-    """Packed camera row [ref 4x(2x7) | obs 4x(2x7) | rho 2] -> the reference's structural blocks (n, cap, 2, 7) for `ids`."""
+def scatter_cam(Jp, i0_ref, i0_obs, ids, W=4):
+    """Packed camera row [ref 4x(2x7) | obs W x(2x7) | rho 2] -> the reference's structural blocks (n, cap, 2, 7) for `ids`.
+    W = 4 for static-RS rows; Newton-RS rows carry the whole observation span (blocks outside `ids` must be zero)."""
     n, cap = ids.shape
     out = np.zeros((n, cap, 2, 7))
-    Jp = np.asarray(Jp).reshape(n, 114)
+    row = 58 + 14 * W
+    Jp = np.asarray(Jp).reshape(n, row)
     for i in range(n):
         pos = {int(k): j for j, k in enumerate(ids[i]) if k >= 0}
-        for base, off in ((i0_ref[i], 0), (i0_obs[i], 56)):
-            for k in range(4):
-                out[i, pos[int(base) + k]] += Jp[i, off + 14 * k: off + 14 * (k + 1)].reshape(2, 7)
-    return out, Jp[:, 112:114]
+        for base, off, nk in ((i0_ref[i], 0, 4), (i0_obs[i], 56, W)):
+            for k in range(nk):
+                blk = Jp[i, off + 14 * k: off + 14 * (k + 1)].reshape(2, 7)
+                if int(base) + k in pos:
+                    out[i, pos[int(base) + k]] += blk
+                else:
+                    assert not blk.any(), "non-zero block outside the residual's structural knots"
+    return out, Jp[:, row - 2:row]

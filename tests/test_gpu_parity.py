@@ -429,3 +429,86 @@ def test_device_order_is_a_bit_exact_permutation():
             assert np.array_equal(d[g[name]][key], a[g[name]][key][order]), (name, key)
         i0 = d[g[name]]["i0_b" if name == "cam" else "i0"]
         assert (np.diff(i0) >= 0).all()            # device order = sorted by first active knot (of the observation for camera rows)
+
+
+# ---- AtanCamera and NewtonRsCameraMeasurement ---------------------------------------------------------
+def _camera_group(cfg, method, atan, p=None):
+    c = cfg["cam"]
+    kw = dict(wc=(0.02, -0.01), gamma=0.9) if atan else {}
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    if p is None:
+        p = _lib.Problem(0)
+        p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+    cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], q_ct=q_ct, p_ct=p_ct, **kw)
+    add = p.add_newton_rs if method == "newton" else p.add_static_rs
+    g = add(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method=method, q_ct=q_ct, p_ct=p_ct, **kw)
+    return p, g, ocam
+
+
+@pytest.mark.parametrize("method,atan,robust", [("static", True, False), ("static", True, True), ("newton", False, False), ("newton", True, True)])
+def test_newton_and_atan_rows_match_oracle(method, atan, robust):
+    cfg = syn.make_config("C3", scale=0.004)                      # 2000 rows on 5k knots (dt 0.02: Newton spans cover 5-6 knots)
+    c = cfg["cam"]
+    rng = np.random.default_rng(33)
+    out = rng.random(len(c["lm_idx"])) < 0.2
+    c["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    c["obs_uv"] += rng.normal(0, 1.0, c["obs_uv"].shape)          # > half a row: the Newton iteration takes more than one step
+    c["weight"] = rng.uniform(0.5, 2, len(c["lm_idx"]))
+    p, g, ocam = _camera_group(cfg, method, atan)
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    out = p.evaluate(cfg["knots"], c["rho"], flags)[g]
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    o = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=2, cap=24)
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_b"] == o["i0_obs_a"]).all()            # bit-exact indexing
+    row = p.group_row_size(g)
+    assert out["J"].shape[1] == row and (row == 114 if method == "static" else (row - 58) % 14 == 0 and row >= 114)
+    ids, nids = p.get_structure(g, cap=24)
+    assert (ids == o["ids_a"]).all()
+    Js = p.expand_static_rs(g, ids, out["J"], out["i0"], out["i0_b"])
+    Jrho = out["J"][:, row - 2:row]
+    if not robust:
+        assert np.abs(out["r"] - o["r"]).max() < parity.TOL * 1e3
+        assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+    else:
+        for i in range(0, len(c["lm_idx"]), 7):
+            m = int(nids[i])
+            Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+            _, r2, J2 = kto.huber_correct(c["huber_c"][i], o["r"][i], Jfull)
+            Jmine = np.concatenate([Js[i, k] for k in range(m)] + [Jrho[i].reshape(2, 1)], axis=1)
+            assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+            assert np.abs(out["r"][i] - r2).max() <= parity.TOL * 1e3
+    # device order is the same rows, permuted, bit for bit
+    dev = p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_DEVICE_ORDER)[g]
+    order = p.get_row_order(g)
+    assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order]) and np.array_equal(dev["i0_b"], out["i0_b"][order])
+
+
+def test_newton_rows_without_noise_equal_static_rows_and_unsupported_modes():
+    """Exact observations: the first Newton step is below half a row, so every row is the static row inside a wider span."""
+    cfg = syn.make_config("C3", scale=0.002)
+    c = cfg["cam"]
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    # regenerate exact (noise-free, converged) observations with the oracle's Newton projection
+    cam0 = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method="newton")
+    o = kto.static_rs_residuals(traj, cam0, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], jac_mode=0, cap=24)
+    c["obs_uv"] = c["obs_uv"] - o["r"]                            # uv - r = projection
+    c["q_ct"], c["p_ct"] = (0, 0, 0, 1), (0, 0, 0)
+    p = _lib.Problem(0)
+    p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+    cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"])
+    gs = p.add_static_rs(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"])
+    gn = p.add_newton_rs(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"])
+    outs = p.evaluate(cfg["knots"], c["rho"])
+    s, n = outs[gs], outs[gn]
+    assert np.abs(n["r"] - s["r"]).max() < 1e-6 and np.abs(s["r"]).max() < 0.5
+    k = s["i0_b"] - n["i0_b"]
+    assert (k >= 0).all() and (k + 4 <= (n["J"].shape[1] - 58) // 14).all()
+    for i in range(0, len(k), 5):
+        a, b = n["J"][i, 56 + 14 * k[i]:56 + 14 * (k[i] + 4)], s["J"][i, 56:112]
+        assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
+    with pytest.raises(NotImplementedError):
+        p.evaluate(cfg["knots"], c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_LOCAL)
+    with pytest.raises(NotImplementedError):
+        p.add_newton_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], time_offset_locked=False), c["obs_uv"], c["obs_t0"], c["ref_uv"],
+                        c["ref_t0"], c["lm_idx"])

@@ -187,3 +187,78 @@ def test_traj_point_queries_match_oracle():
     for a, b in ((out[:, 0:3], o["position"]), (out[:, 3:6], o["velocity"]), (out[:, 6:9], o["acceleration"]), (out[:, 9:13], o["orientation"]),
                  (out[:, 13:16], o["angular_velocity"])):
         assert np.abs(a - b).max() < 1e-12 * max(1.0, np.abs(b).max())
+
+
+# ---- AtanCamera and NewtonRsCameraMeasurement ---------------------------------------------------------
+def _camera_case_model(dt, seed, atan, method):
+    knots, s, _ = _camera_case(dt, seed)
+    kw = dict(wc=(0.02, -0.01), gamma=0.9) if atan else {}
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], method=method, q_ct=fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])),
+                     p_ct=np.array([0.05, -0.02, 0.1]), **kw)
+    return knots, s, cam
+
+
+@pytest.mark.parametrize("dt", [0.02, 0.1])
+def test_static_rs_atan_camera_rows_match_oracle(dt):
+    """AtanCamera (sensors/atan_camera.h:54-103) under the static measurement: analytic projection Jacobian vs the oracle's autodiff."""
+    knots, s, cam = _camera_case_model(dt, 5, True, "static")
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    h = hc.static_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
+    assert (h["status"] == 0).all()
+    assert (h["i0_ref"] == o["i0_ref_a"]).all() and (h["i0_obs"] == o["i0_obs_a"]).all()
+    assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+    Js, Jrho = parity.scatter_cam(h["J"], h["i0_ref"], h["i0_obs"], o["ids_a"])
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+
+
+@pytest.mark.parametrize("dt", [0.02, 0.1])
+@pytest.mark.parametrize("atan", [False, True])
+def test_newton_rs_rows_match_oracle(dt, atan):
+    """NewtonRsCameraMeasurement (newton_rscamera_measurement.h:23-120): residual and the derivative THROUGH the iteration."""
+    knots, s, cam = _camera_case_model(dt, 5, atan, "newton")
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    h = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
+    assert (h["status"] == 0).all()
+    assert (h["i0_ref"] == o["i0_ref_a"]).all() and (h["i0_obs"] == o["i0_obs_a"]).all()       # bit-exact: i0_obs = first knot of the span
+    assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+    Js, Jrho = parity.scatter_cam(h["J"], h["i0_ref"], h["i0_obs"], o["ids_a"], h["W"])
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+    it = np.bincount(h["iterations"], minlength=6)
+    assert it[1] > 0 and it[2:].sum() > 0          # rows that stop after one step AND rows that iterate
+
+
+def test_newton_rs_one_step_rows_equal_static_rows():
+    """A row whose first Newton step is below half a row time returns the projection at the observed row: the static-RS row."""
+    dt = 0.05
+    knots, s, cam = _camera_case_model(dt, 11, False, "newton")
+    args = (knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
+    hn, hs = hc.newton_rs(*args), hc.static_rs(*args)
+    one = hn["iterations"] == 1
+    assert one.sum() > 5
+    assert np.abs(hn["r"][one] - hs["r"][one]).max() < 1e-9
+    Jn = hn["J"][one]
+    W = hn["W"]
+    off = (hs["i0_obs"][one] - hn["i0_obs"][one])          # position of the static row's 4-knot window inside the span
+    for a, (jn, js, k) in enumerate(zip(Jn, hs["J"][one], off)):
+        assert np.abs(jn[:56] - js[:56]).max() <= 1e-9 * np.abs(js[:56]).max()
+        assert np.abs(jn[56 + 14 * k:56 + 14 * (k + 4)] - js[56:112]).max() <= 1e-9 * np.abs(js[56:112]).max()
+        assert np.abs(jn[-2:] - js[112:114]).max() <= 1e-9 * np.abs(js[112:114]).max()
+
+
+def test_newton_rs_huber_corrector_matches_oracle():
+    dt = 0.05
+    knots, s, cam = _camera_case_model(dt, 9, False, "newton")
+    n = len(s["lm_idx"])
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    h = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], huber_c=np.full(n, 5.0))
+    for i in range(n):
+        m = int((o["ids_a"][i] >= 0).sum())
+        Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+        _, r2, J2 = kto.huber_correct(5.0, o["r"][i], Jfull)
+        Js, Jr = parity.scatter_cam(h["J"][i:i + 1], h["i0_ref"][i:i + 1], h["i0_obs"][i:i + 1], o["ids_a"][i:i + 1], h["W"])
+        Jmine = np.concatenate([Js[0, k] for k in range(m)] + [Jr[0].reshape(2, 1)], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(h["r"][i] - r2).max() <= parity.TOL * 1e3

@@ -6,8 +6,8 @@ import pytest
 import fixtures_ref as fx
 import kontiki_b200 as kontiki
 from kontiki_b200 import sfm
-from kontiki_b200.measurements import AccelerometerMeasurement, GyroscopeMeasurement, StaticRsCameraMeasurement
-from kontiki_b200.sensors import BasicImu, PinholeCamera
+from kontiki_b200.measurements import AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, StaticRsCameraMeasurement
+from kontiki_b200.sensors import AtanCamera, BasicImu, PinholeCamera
 from kontiki_b200.trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory
 
 pytestmark = pytest.mark.gpu
@@ -342,3 +342,85 @@ def test_solve_recovers_time_offset_and_gyro_bias():
     assert abs(imu.time_offset - 0.012) < 1e-6
     assert np.allclose(imu.gyroscope_bias, true_imu.gyroscope_bias, atol=1e-7)
     assert s.final_cost < 1e-12
+
+
+# ---- AtanCamera / NewtonRsCameraMeasurement (python/tests/test_cameras.py:32-104, test_measurements.py:16-56) ------------------------
+ATAN_K = np.array([[853.12703455, 0., 988.06311256], [0., 873.54956631, 525.71056312], [0., 0., 1.]])     # fixtures/camera_fixtures.py:12-16
+ATAN_WC, ATAN_GAMMA = np.array([0.0029110778971412417, 0.0004189670467132041]), 0.8894355177968156
+
+
+def test_atan_camera_surface_and_project_unproject():
+    cam1 = AtanCamera(1080, 1920, 0.026, ATAN_K, ATAN_WC, ATAN_GAMMA)
+    cam2 = AtanCamera(1080, 1920, 0.026)                     # test_cameras.py:93-108: both constructors give the same camera
+    cam2.camera_matrix, cam2.wc, cam2.gamma = ATAN_K, ATAN_WC, ATAN_GAMMA
+    rng = np.random.default_rng(0)
+    for cam in (cam1, cam2):
+        for _ in range(20):                                  # test_cameras.py:32-44
+            y = np.array([rng.uniform(0, cam.cols), rng.uniform(0, cam.rows)])
+            X = cam.unproject(y) * rng.uniform(0.5, 20)
+            assert np.allclose(cam.project(X), y, atol=1e-8)
+    # the device projection is the same function: a landmark seen by an un-moving camera re-projects onto its reference pixel
+    traj = smooth_se3()
+    traj._cp[:] = traj._cp[0]
+    L = sfm.Landmark()
+    v0, v1 = sfm.View(0, 1.0), sfm.View(1, 2.0)
+    uv = np.array([700.0, 300.0])
+    L.reference = v0.create_observation(L, uv)
+    obs = v1.create_observation(L, uv)
+    L.inverse_depth = 0.2
+    for cls in (StaticRsCameraMeasurement, NewtonRsCameraMeasurement):
+        assert np.allclose(cls(cam1, obs).project(traj), uv, atol=1e-8)
+
+
+def test_newton_rscamera_measurements_with_noise():
+    """test_measurements.py:34-56: with 2 px of observation noise the Newton projection lands within half a row of the true row."""
+    traj = smooth_se3()
+    for cam in (PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]])), AtanCamera(1080, 1920, 0.026, ATAN_K, ATAN_WC, ATAN_GAMMA)):
+        lms = _small_sfm(traj, PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]])))
+        if isinstance(cam, AtanCamera):                      # make the structure consistent with this camera: re-project it once, noise-free
+            for L in lms:
+                for obs in L.observations:
+                    if not obs.is_reference:
+                        obs.uv = NewtonRsCameraMeasurement(cam, obs).project(traj)
+                        obs.uv = NewtonRsCameraMeasurement(cam, obs).project(traj)
+        rng = np.random.default_rng(4)
+        n = 0
+        for L in lms:
+            for obs in L.observations:
+                if obs.is_reference:
+                    continue
+                uv_org = obs.uv.copy()
+                m0 = NewtonRsCameraMeasurement(cam, obs)
+                assert m0.camera is cam and m0.observation is obs
+                obs.uv = uv_org + rng.normal(0, 2.0, 2)
+                yhat = NewtonRsCameraMeasurement(cam, obs).project(traj)
+                assert abs(yhat[1] - uv_org[1]) <= 0.5
+                obs.uv = uv_org
+                n += 1
+        assert n == 40
+
+
+def test_estimator_solve_newton_measurements_reduce_cost():
+    traj = smooth_se3(n=40, dt=0.1)
+    cam = PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    lms = _small_sfm(traj, cam, n_lm=30, n_views=6, seed=5)
+    rng = np.random.default_rng(2)
+    for L in lms:
+        L.inverse_depth *= 1.0 + 0.1 * rng.normal()
+    est = kontiki.TrajectoryEstimator(traj)
+    for L in lms:
+        for obs in L.observations:
+            if not obs.is_reference:
+                est.add_measurement(NewtonRsCameraMeasurement(cam, obs))
+    traj.locked = True
+    summary = est.solve(max_iterations=20, progress=False)
+    assert summary.final_cost < 0.05 * summary.initial_cost
+    # ... and with the trajectory free the sparse system accepts the wide observation spans
+    traj.locked = False
+    est2 = kontiki.TrajectoryEstimator(traj)
+    for L in lms:
+        for obs in L.observations:
+            if not obs.is_reference:
+                est2.add_measurement(NewtonRsCameraMeasurement(cam, obs))
+    s2 = est2.solve(max_iterations=5, progress=False)
+    assert s2.final_cost <= s2.initial_cost
