@@ -40,18 +40,25 @@ def parse():
     ap.add_argument("--workload", default="H1")
     ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--camera-method", default="static", choices=["static", "newton"],
+                    help="StaticRsCameraMeasurement (the BASELINE.json workloads) or NewtonRsCameraMeasurement rows (SURVEY.md 8f-3) for the camera group")
+    ap.add_argument("--camera-model", default="pinhole", choices=["pinhole", "atan"], help="PinholeCamera (BASELINE.json) or AtanCamera")
     ap.add_argument("--row-order", default="caller", choices=["caller", "device"],
                     help="row order of the device-resident leg: the caller's insertion order (default, what the drop-in contract documents) or "
                          "KTK_EVAL_DEVICE_ORDER (rows sorted by first knot, one TMA bulk store per warp tile)")
     return ap.parse_args()
 
 
-def workload_config(name, cfg, row_order="caller"):
+ATAN = dict(wc=(0.0029110778971412417, 0.0004189670467132041), gamma=0.8894355177968156)      # python/tests/fixtures/camera_fixtures.py:15-16
+
+
+def workload_config(name, cfg, row_order="caller", method="static", model="pinhole"):
     from kontiki_b200 import synthetic as syn
     traj = "SplitTrajectory (UniformR3 + UniformSO3)" if cfg.get("split") else "UniformSE3SplineTrajectory"
     return {"workload": f"{name}: {traj} {len(cfg['knots'])} knots dt={cfg['dt']}, "
                         f"{len(cfg['gyro']['t']) if cfg['gyro'] else 0} gyro + {len(cfg['accel']['t']) if cfg['accel'] else 0} accel (BasicImu) + "
-                        f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} StaticRsCamera (Pinhole, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
+                        f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} {'NewtonRsCamera' if method == 'newton' else 'StaticRsCamera'} "
+                        f"({'Atan' if model == 'atan' else 'Pinhole'}, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
             "measurements_per_step_per_gpu": syn.num_measurements(cfg),
             "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
             "jacobian": "ambient (7 per SE3 knot; 3 + 4 per split knot), Huber corrector applied to camera rows",
@@ -78,6 +85,9 @@ def oracle_sample(cfg, frac, seed=0):
     return out
 
 
+CAMERA = {"method": "static", "model": "pinhole"}      # set from the command line in main()
+
+
 def oracle_step(cfg, sample):
     """One residual+Jacobian evaluation of the sample with the CPU oracle; returns (rows, seconds inside Evaluate)."""
     from oracle import kto
@@ -94,7 +104,7 @@ def oracle_step(cfg, sample):
             rows += len(m["t"]); secs += res["eval_seconds"]
     if "cam" in sample:
         c = sample["cam"]
-        ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"])
+        ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method=CAMERA["method"], **(ATAN if CAMERA["model"] == "atan" else {}))
         res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24,
                                       nthreads=NTHREADS)
         rows += len(c["lm_idx"]); secs += res["eval_seconds"]
@@ -162,6 +172,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from kontiki_b200 import synthetic as syn
+    CAMERA.update(method=a.camera_method, model=a.camera_model)
 
     if a.impl == "reference":
         if rank != 0:
@@ -170,7 +181,7 @@ def main():
         base, rows, secs = cpu_baseline(cfg, a.cpu_sample, steps=a.steps, warmup=1 if a.warmup > 0 else 0, budget_s=90.0)
         line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": 1e3 * secs / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": workload_config(a.workload, cfg), "cpu_baseline": base,
+                "data": "synthetic", "config": workload_config(a.workload, cfg, "caller", a.camera_method, a.camera_model), "cpu_baseline": base,
                 "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "restated reference on host cores: the reference needs Ceres 1.x + Sophus + Eigen, none installable here (oracle/README.md)"}
         print(json.dumps(line))
@@ -221,8 +232,9 @@ def main():
     if cfg["cam"]:
         c = cfg["cam"]
         rho = c["rho"]
-        groups["cam"] = p.add_static_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"]), c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"],
-                                        c["lm_idx"], c["weight"], c["huber_c"])
+        add = p.add_newton_rs if a.camera_method == "newton" else p.add_static_rs
+        groups["cam"] = add(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], **(ATAN if a.camera_model == "atan" else {})), c["obs_uv"], c["obs_t0"],
+                            c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
     flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST
 
     # ---- device-resident leg -------------------------------------------------------------------------------------
@@ -231,7 +243,7 @@ def main():
     d_rho = torch.from_numpy(rho).to(dev) if rho is not None else None
     d_outs, keep = [], []
     for g in range(p.num_groups):
-        n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
+        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
         r = torch.empty((n, 2 if cam else 3), dtype=torch.float64, device=dev)
         J = torch.empty((n, p.group_row_size(g)), dtype=torch.float64, device=dev)
         idx = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
@@ -287,7 +299,7 @@ def main():
     h_rho = torch.from_numpy(rho).pin_memory() if rho is not None else None
     h_outs, d2h = [], 0
     for g in range(p.num_groups):
-        n, cam = p.group_size(g), p.group_kind(g) == _lib.STATIC_RS
+        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
         o = dict(r=torch.empty((n, 2 if cam else 3), dtype=torch.float64).pin_memory(),
                  J=torch.empty((n, p.group_row_size(g)), dtype=torch.float64).pin_memory(),
                  i0=torch.empty(n, dtype=torch.int32).pin_memory())
@@ -332,6 +344,8 @@ def main():
     dom_ms, dom_n = prof[dom]
     dom_rows = p.group_size(groups[dom])
     per_row = ({"cam": 1020, "accel": 744, "gyro": 452} if cfg.get("split") else {"cam": 1012, "accel": 740, "gyro": 740})[dom]
+    if dom == "cam" and a.camera_method == "newton":      # in 76 + r 16 + packed row (58 + 14 W doubles) + i0_ref, i0_obs
+        per_row = 76 + 16 + 8 * p.group_row_size(groups["cam"]) + 8
     dom_bytes = dom_rows * per_row
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_ms > 0 else None
     traffic = None
@@ -341,12 +355,12 @@ def main():
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a.workload, cfg, a.row_order),
+            "config": workload_config(a.workload, cfg, a.row_order, a.camera_method, a.camera_model),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": {"cam": "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"cam": "k_newton_rs" if a.camera_method == "newton" else "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
@@ -355,7 +369,7 @@ def main():
                          # the ncu instruction mix (profiles/README.md: 1568 DFMA + 611 DMUL + 236 DADD per static-RS row on SE3), peak =
                          # the dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
                          "fp64": ({"flop_per_row": 3983, "achieved_tflops": dom_rows * 3983 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
-                                   "frac": dom_rows * 3983 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0) else None)}}
+                                   "frac": dom_rows * 3983 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
     if not a.no_cpu_baseline and world == 1:
         base, _, _ = cpu_baseline(cfg, a.cpu_sample)
         line["cpu_baseline"] = base

@@ -78,7 +78,7 @@ enum {
                              entry points below expect ambient rows. */
 };
 
-enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3 };
+enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3, KTK_POSITION = 4 };
 enum { KTK_CAMERA_PINHOLE = 0, KTK_CAMERA_ATAN = 1 };
 
 /* sensors/sensors.h:91-109: relative pose + time offset; *_locked as the reference's lock flags (default locked). */
@@ -149,6 +149,10 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
  *   static_rscamera_measurement.h:68-69). */
 int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
 int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* weight);
+/* PositionMeasurement::AddToEstimator (measurements/position_measurement.h:58-79): r = weight (position[i] - trajectory.Position(t[i])),
+ * 3 residuals, no sensor, no loss (the reference has no weight: pass NULL).  Rows as the IMU rows: SE3 J[4][3][7]; split trajectory
+ * J[4 R3 knots][3][3] (36; the SO3 blocks of the residual are structurally present but zero), i0 = R3 knot, i0_c = SO3 segment start. */
+int ktk_add_position(ktk_problem* p, int64_t n, const double* t, const double* position, const double* weight);
 int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static

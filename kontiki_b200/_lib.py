@@ -11,7 +11,7 @@ from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL, EVAL_DEVICE_ORDER = 1, 2, 4, 8, 16, 32
-GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS = 0, 1, 2, 3
+GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS, POSITION = 0, 1, 2, 3, 4
 CAMERA_PINHOLE, CAMERA_ATAN = 0, 1
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -37,7 +37,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position"]
 
 _lib = None
 
@@ -69,6 +69,7 @@ def lib():
         L.ktk_set_se3_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_int32]
         L.ktk_add_gyroscope.argtypes = [C.c_void_p, C.POINTER(Sensor), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_add_accelerometer.argtypes = L.ktk_add_gyroscope.argtypes
+        L.ktk_add_position.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [C.c_void_p] * 7
         L.ktk_add_newton_rs.argtypes = L.ktk_add_static_rs.argtypes
         L.ktk_num_groups.argtypes = [C.c_void_p]
@@ -198,6 +199,13 @@ class Problem:
 
     def add_accelerometer(self, sensor, t, y, weight=None):
         return self._add_imu(lib().ktk_add_accelerometer, sensor, t, y, weight)
+
+    def add_position(self, t, position, weight=None):
+        t, y = _f64(t), _f64(position).reshape(-1, 3)
+        if len(t) != len(y):
+            raise ValueError("t and position differ in length")
+        w = None if weight is None else _f64(weight)
+        return check(lib().ktk_add_position(self._h, len(t), _ptr(t), _ptr(y), _ptr(w)))
 
     def add_newton_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
         return self.add_static_rs(camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight, huber_c, _fn=lib().ktk_add_newton_rs)

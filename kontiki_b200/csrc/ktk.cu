@@ -33,6 +33,7 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NEWTON_RS; }
+inline int imu_which(int kind) { return kind == KTK_GYROSCOPE ? 0 : (kind == KTK_ACCELEROMETER ? 1 : 2); }
 #define KTK_CUDA(call)                                                                                   \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_dev(con
 // =====================================================================================================================
 constexpr int kGyroSplitRow = 48, kGyroSplitStride = 50;
 constexpr int kAccelSplitRow = 84, kAccelSplitStride = 86;
+constexpr int kPosSplitRow = 36, kPosSplitStride = 38;       // PositionMeasurement on a split trajectory: [4 R3 knots][3][3]
 
 __global__ void k_pack_vecs(const double* __restrict__ v3, int n, double* __restrict__ v4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,8 +426,8 @@ struct ImuSplitArgs {
 };
 template <int WHICH>
 __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
-  constexpr int ROW = WHICH == 0 ? kGyroSplitRow : kAccelSplitRow;
-  constexpr int STRIDE = WHICH == 0 ? kGyroSplitStride : kAccelSplitStride;
+  constexpr int ROW = WHICH == 0 ? kGyroSplitRow : (WHICH == 1 ? kAccelSplitRow : kPosSplitRow);
+  constexpr int STRIDE = WHICH == 0 ? kGyroSplitStride : (WHICH == 1 ? kAccelSplitStride : kPosSplitStride);
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * STRIDE;
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan(""); ia = ib = -1;
       for (int c = 0; c < ROW; ++c) row[c] = nan("");
-    } else if (local) localize_so3_blocks<3>(row + (WHICH == 0 ? 0 : 36), 4, a.quats + (size_t)ib * kQuatStride);
+    } else if (local && WHICH != 2) localize_so3_blocks<3>(row + (WHICH == 0 ? 0 : 36), 4, a.quats + (size_t)ib * kQuatStride);
     const size_t dst = (size_t)perm;
     if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
     if (a.i0_r3) a.i0_r3[dst] = ia;
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
   }
   __syncwarp();
   if (wantJ) {
-    if (local) warp_scatter_rows<ROW - 12, STRIDE, ROW - 12>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from 3x4 to 3x3
+    if (local && WHICH != 2) warp_scatter_rows<ROW - 12, STRIDE, ROW - 12>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from 3x4 to 3x3
     else warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, perm, lane);
   }
 }
@@ -991,6 +993,7 @@ int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
   if (g.kind == KTK_NEWTON_RS) return 58 + 14 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
+  if (p->traj == 1 && g.kind == KTK_POSITION) return kPosSplitRow;
   if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? (local ? 36 : kGyroSplitRow) : (local ? 72 : kAccelSplitRow);
   return local ? 72 : kImuRow;
 }
@@ -1035,6 +1038,8 @@ int ktk_problem_create(int device, ktk_problem** out) {
   // opt in to the shared-memory carve-out the row staging needs
   cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kPosSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_static_rs_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
@@ -1074,6 +1079,11 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
 
 int ktk_add_gyroscope(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_GYROSCOPE, imu, n, t, y, w); }
 int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) { return add_imu(p, KTK_ACCELEROMETER, imu, n, t, y, w); }
+int ktk_add_position(ktk_problem* p, int64_t n, const double* t, const double* position, const double* w) {
+  ktk_sensor none{};           // PositionMeasurement has no sensor: identity pose, zero locked time offset
+  none.q_ct[3] = 1.0; none.max_time_offset = 0.0; none.q_locked = none.p_locked = none.time_offset_locked = 1;
+  return add_imu(p, KTK_POSITION, &none, n, t, position, w);
+}
 
 static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
                             const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
@@ -1119,7 +1129,7 @@ int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor
 int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !bias) return fail(KTK_EINVAL, "bad argument");
   Group& g = *p->groups[group];
-  if (is_camera(g.kind)) return fail(KTK_EINVAL, "a camera has no bias");
+  if (is_camera(g.kind) || g.kind == KTK_POSITION) return fail(KTK_EINVAL, "only IMU groups have a bias");
   for (int c = 0; c < 3; ++c) g.bias[c] = bias[c];
   drop_graph(p);
   return KTK_OK;
@@ -1141,6 +1151,7 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   if (!(flags & KTK_EVAL_SENSOR_JACOBIANS) || !o.Js || g.n == 0) return KTK_OK;
   cudaStream_t s = p->stream;
   const int blocks = (int)((g.n + 127) / 128);
+  if (g.kind == KTK_POSITION) return KTK_OK;           // no sensor
   if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRsCameraMeasurement are not built");
   if (g.kind == KTK_STATIC_RS) {
     if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
@@ -1206,6 +1217,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
       a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0_r3 = o.i0; a.i0_so3 = o.i0_c; a.err = p->d_err.p;
       if (g.kind == KTK_GYROSCOPE) k_imu_split<0><<<blocks, kThreads, kThreads * kGyroSplitStride * 8, s>>>(a);
+      else if (g.kind == KTK_POSITION) k_imu_split<2><<<blocks, kThreads, kThreads * kPosSplitStride * 8, s>>>(a);
       else k_imu_split<1><<<blocks, kThreads, kThreads * kAccelSplitStride * 8, s>>>(a);
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
@@ -1321,6 +1333,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
       if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
+      else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
       else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
@@ -1456,6 +1469,7 @@ static RowWindows row_windows(const ktk_problem* p, const Group& g) {
   } else if (g.kind == KTK_STATIC_RS) {
     w.nwin = 4; set(0, 0, 3, 0, 0); set(1, 24, 4, colB, 2); set(2, 56, 3, 0, 1); set(3, 80, 4, colB, 3); w.rho_off_in_row = 112;
   } else if (g.kind == KTK_GYROSCOPE) { w.nwin = 1; set(0, 0, 4, colB, 2); }
+  else if (g.kind == KTK_POSITION) { w.nwin = 1; set(0, 0, 3, 0, 0); }
   else { w.nwin = 2; set(0, 0, 3, 0, 0); set(1, 36, 4, colB, 2); }
   return w;
 }

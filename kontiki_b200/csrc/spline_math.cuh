@@ -691,7 +691,16 @@ KB_HD double spline_max_time(const SplineConst& sp) { return add_rn(sp.t0, mul_r
 
 struct ImuConst { double time_offset, max_time_offset; int time_offset_locked; double bias[3]; };   // bias: ConstantBiasImu (constant_bias_imu.h:52-61), 0 for BasicImu
 
-// gyroscope (which = 0) / accelerometer (which = 1); gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
+// PositionMeasurement on SE3 (measurements/position_measurement.h:24-31): r = weight (p_meas - position(t)); J: [4 knots][3][7]
+KB_HD void position_se3(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, double weight,
+                        const double* y, double* r, double* J) {
+  Pose P;
+  pose_forward(knot0, p1, p2, p3, bs, P);
+  r[0] = weight * (y[0] - P.p.x); r[1] = weight * (y[1] - P.p.y); r[2] = weight * (y[2] - P.p.z);
+  pose_backward<3>(knot0, p1, p2, p3, bs, m3_identity(), P.R, m3_zero(), -weight, J);
+}
+
+// gyroscope (which = 0) / accelerometer (which = 1) / position (which = 2); gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
 KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const double* knots, const double* pairs,
                   double t, const double* y, double weight, double* r, double* J, int* i0_out) {
   double ta = t, tb = t;
@@ -704,6 +713,7 @@ KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const d
   const double* k0 = knots + (size_t)i0 * kKnotStride;
   const double* p1 = pairs + (size_t)(i0 + 1) * kPairStride;
   if (which == 0) gyro_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);
+  else if (which == 2) position_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);
   else {
     if (sp.compat_zero_dB) { bs.dB[0] = 0.0; bs.dB[1] = 0.0; bs.dB[2] = 0.0; }
     accel_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);

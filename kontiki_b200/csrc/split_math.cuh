@@ -304,7 +304,7 @@ KB_HD double split_max_time(const SplitConst& sp) {                             
   return a < b ? a : b;
 }
 
-// which: 0 gyroscope (J 48 doubles, i0 = SO3), 1 accelerometer (J 84 doubles; i0_r3, i0_so3)
+// which: 0 gyroscope (J 48 doubles, i0 = SO3), 1 accelerometer (J 84 doubles; i0_r3, i0_so3), 2 position (J [4 R3 knots][3][3] = 36)
 KB_HD int imu_row_split(int which, const SplitConst& sp, const ImuConst& imu, const double* vecs, const double* quats, const double* pairs,
                         double t, const double* y, double weight, double* r, double* J, int* i0_r3, int* i0_so3) {
   double ta = t, tb = t;
@@ -312,6 +312,21 @@ KB_HD int imu_row_split(int which, const SplitConst& sp, const ImuConst& imu, co
   if (sp.n_r3 < 4 || sp.n_so3 < 4 || !(ta >= split_min_time(sp)) || !(tb < split_max_time(sp))) return kStatusRange;
   const double te = add_rn(t, imu.time_offset);
   Segment seg; int ib; double ub;
+  if (which == 2) {      // position_measurement.h: only the R3 spline is evaluated; the SO3 segment is structure only
+    int ia; double ua;
+    segments_one_span(ta, tb, sp.t0_so3, sp.dt_so3, seg);
+    *i0_so3 = seg.start;
+    segments_one_span(ta, tb, sp.t0_r3, sp.dt_r3, seg);
+    if (!segment_locate(seg, te, sp.t0_r3, sp.dt_r3, ia, ua)) return kStatusRange;
+    *i0_r3 = ia;
+    const BasisR3 br = r3_basis(ua, sp.dt_r3);
+    const V3 pos = r3_combine(vecs + (size_t)ia * kVecStride, br.Bp);
+    r[0] = weight * (y[0] - pos.x); r[1] = weight * (y[1] - pos.y); r[2] = weight * (y[2] - pos.z);
+    for (int k = 0; k < 4; ++k)
+      for (int a = 0; a < 3; ++a)
+        for (int c = 0; c < 3; ++c) J[9 * k + 3 * a + c] = a == c ? -weight * br.Bp[k] : 0.0;
+    return 0;
+  }
   segments_one_span(ta, tb, sp.t0_so3, sp.dt_so3, seg);
   if (!segment_locate(seg, te, sp.t0_so3, sp.dt_so3, ib, ub)) return kStatusRange;
   const Basis bs = cumulative_basis(ub, sp.dt_so3);

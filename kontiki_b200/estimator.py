@@ -14,7 +14,8 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import _lib
-from .measurements import AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, StaticRsCameraMeasurement, _problem_for
+from .measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, PositionMeasurement,
+                           StaticRsCameraMeasurement, _problem_for)
 from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
 
 
@@ -134,6 +135,14 @@ def _quat_plus(q, d):
     return out / np.linalg.norm(out, axis=1, keepdims=True)
 
 
+class _NoSensor:
+    """PositionMeasurement has no sensor: nothing to unlock."""
+    relative_orientation_locked = relative_position_locked = time_offset_locked = True
+
+
+_NO_SENSOR = _NoSensor()
+
+
 class TrajectoryEstimator:
     """TrajectoryEstimator(trajectory) -- same surface as the reference; `device` selects the GPU."""
 
@@ -148,7 +157,7 @@ class TrajectoryEstimator:
     trajectory = property(lambda self: self._trajectory)
 
     def add_measurement(self, m):
-        if not isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement, StaticRsCameraMeasurement)):
+        if not isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement, StaticRsCameraMeasurement, PositionMeasurement)):
             raise TypeError(f"unsupported measurement type {type(m).__name__}")
         # AddToEstimator checks the time span when the measurement is added (trajectory_estimator.h:97-122)
         tr = self._trajectory
@@ -182,7 +191,7 @@ class TrajectoryEstimator:
         groups, self._landmarks, lm_index = {}, [], {}
         for i, m in enumerate(self._measurements):
             kind = type(m)
-            sensor = m.camera if issubclass(kind, StaticRsCameraMeasurement) else m.imu
+            sensor = m.camera if issubclass(kind, StaticRsCameraMeasurement) else (_NO_SENSOR if kind is PositionMeasurement else m.imu)
             groups.setdefault((kind, id(sensor)), (sensor, []))[1].append(i)
         self._groups = []
         for (kind, _), (sensor, rows) in groups.items():
@@ -199,6 +208,9 @@ class TrajectoryEstimator:
                                     np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
                                     lm, [m.weight for m in ms], [m.huber_c for m in ms])
                 self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor, newton=kind is NewtonRsCameraMeasurement))
+            elif kind is PositionMeasurement:
+                g = p.add_position([m.t for m in ms], np.array([m.p for m in ms]))
+                self._groups.append(dict(g=g, kind="pos", rows=rows, sensor=sensor, weight=np.ones(len(ms))))
             else:
                 fn = p.add_gyroscope if kind is GyroscopeMeasurement else p.add_accelerometer
                 g = fn(sensor._c_sensor(), [m.t for m in ms], np.array([m._x for m in ms]), [m.weight for m in ms])
@@ -235,7 +247,7 @@ class TrajectoryEstimator:
             sn = grp["sensor"]
             if self._sensor_free(sn):
                 self._problem.set_group_sensor(grp["g"], sn._c_sensor())
-            bias = getattr(sn, "gyroscope_bias" if grp["kind"] == "gyro" else "accelerometer_bias", None) if grp["kind"] != "cam" else None
+            bias = getattr(sn, "gyroscope_bias" if grp["kind"] == "gyro" else "accelerometer_bias", None) if grp["kind"] in ("gyro", "accel") else None
             if bias is not None:
                 self._problem.set_group_bias(grp["g"], bias)
 
@@ -270,7 +282,7 @@ class TrajectoryEstimator:
         self._sensor_cols = {}
         for grp in getattr(self, "_groups", []):
             sn = grp["sensor"]
-            if id(sn) in self._sensor_cols:
+            if id(sn) in self._sensor_cols or sn is _NO_SENSOR:
                 continue
             cols = {}
             for name in self._sensor_free(sn):
@@ -332,6 +344,8 @@ class TrajectoryEstimator:
                     add_blocks(o["J"].reshape(n, 4, 3, 7), o["i0"], 7, "se3", 3)
                 elif grp["kind"] == "gyro":
                     add_blocks(o["J"].reshape(n, 4, 3, 4), o["i0_c"], 4, "so3", 3)
+                elif grp["kind"] == "pos":
+                    add_blocks(o["J"].reshape(n, 4, 3, 3), o["i0"], 3, "r3", 3)
                 else:
                     add_blocks(o["J"][:, :36].reshape(n, 4, 3, 3), o["i0"], 3, "r3", 3)
                     add_blocks(o["J"][:, 36:].reshape(n, 4, 3, 4), o["i0_c"], 4, "so3", 3)
@@ -442,7 +456,7 @@ class TrajectoryEstimator:
         layout, ncols = self._columns()
         tr = self._trajectory
         n_knot_params = (7 * len(tr)) if isinstance(tr, UniformSE3SplineTrajectory) else (3 * len(tr.R3_spline) + 4 * len(tr.SO3_spline))
-        n_sensors = len(self._groups)        # one sensor per group: q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
+        n_sensors = sum(g["kind"] != "pos" for g in self._groups)        # one sensor per group (none for PositionMeasurement): q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
         s.num_parameters = n_knot_params + len(self._landmarks) + 8 * n_sensors
         s.num_parameter_blocks = n_knot_params // (7 if isinstance(tr, UniformSE3SplineTrajectory) else 1) + len(self._landmarks) + 3 * n_sensors
         s.num_parameters_reduced = ncols + self._ambient_free(layout)      # ambient sizes of the non-constant blocks
@@ -561,7 +575,7 @@ class TrajectoryEstimator:
         ne.free = torch.from_numpy(free).to(ne.dev)
         n_free = int(free.sum())
         layout, ncols = self._columns()
-        s.num_parameters = ne.n_amb + 8 * len(self._groups)
+        s.num_parameters = ne.n_amb + 8 * sum(g["kind"] != "pos" for g in self._groups)
         s.num_parameters_reduced = ncols + self._ambient_free(layout)
         s.num_effective_parameters_reduced = n_free
         s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)

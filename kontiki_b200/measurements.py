@@ -61,6 +61,25 @@ class AccelerometerMeasurement(_ImuMeasurement):
     a = property(lambda self: self._x.copy())
 
 
+class PositionMeasurement:
+    """PositionMeasurement(t, p)  (measurements/position_measurement.h:17-31, py_position_measurement.cc): error = p - position(t)."""
+
+    def __init__(self, t, p):
+        self.t = float(t)
+        self.p = np.asarray(p, float).reshape(3).copy()
+
+    def _residual(self, trajectory, p):
+        prob, knots = _problem_for(trajectory)
+        prob.add_position([self.t], np.asarray(p, float).reshape(1, 3))
+        return prob.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0]
+
+    def error(self, trajectory):
+        return self._residual(trajectory, self.p)
+
+    def measure(self, trajectory):
+        return -self._residual(trajectory, np.zeros(3))
+
+
 class StaticRsCameraMeasurement:
     """StaticRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (static_rscamera_measurement.h:62-69)"""
 

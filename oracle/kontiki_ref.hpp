@@ -418,6 +418,12 @@ template <class T> void gyro_error(double weight, const double w[3], double t, c
   Vec3<T> m = imu_gyroscope(imu, traj, T(t));
   r[0] = T(weight) * (T(w[0]) - m.x); r[1] = T(weight) * (T(w[1]) - m.y); r[2] = T(weight) * (T(w[2]) - m.z);
 }
+// measurements/position_measurement.h:24-31: Error = p - trajectory.Position(t) (no sensor, no weight in the reference; the
+// weight argument is the oracle's own generalisation and is 1 for the reference's measurement)
+template <class T> void position_error(double weight, const double p[3], double t, const TrajectoryView<T>& traj, T r[3]) {
+  auto result = traj.Evaluate(T(t), EvalPosition);
+  r[0] = T(weight) * (T(p[0]) - result->position.x); r[1] = T(weight) * (T(p[1]) - result->position.y); r[2] = T(weight) * (T(p[2]) - result->position.z);
+}
 // measurements/accelerometer_measurement.h:37-39
 template <class T> void accel_error(double weight, const double a[3], double t, const SensorView<T>& imu, const TrajectoryView<T>& traj, T r[3]) {
   Vec3<T> m = imu_accelerometer(imu, traj, T(t));

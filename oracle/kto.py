@@ -184,7 +184,7 @@ def se3_evaluate_matrices(traj, t, raise_on_error=True):
 
 
 def imu_residuals(traj, imu, which, t, y, weight=None, jac_mode=2, nthreads=0, cap=None, raise_on_error=True):
-    """which: 0 gyro / 1 accel.  Returns dict(r, ids_a, Ja, ids_b, Jb, Js, i0_a, i0_b, status, eval_seconds)."""
+    """which: 0 gyro / 1 accel / 2 position (PositionMeasurement; `imu` is inert).  Returns dict(r, ids_a, Ja, ids_b, Jb, Js, i0_a, i0_b, status, eval_seconds)."""
     t, y = _f64(t), _f64(y).reshape(-1, 3)
     n = len(t)
     weight = np.ones(n) if weight is None else _f64(weight)

@@ -127,6 +127,7 @@ struct ImuFunctor {   // measurements/gyroscope_measurement.h:54-72 / accelerome
     offset += blk->meta.NumParameters();
     SensorView<T> imu; imu.params = &params[offset]; imu.has_bias = has_bias;
     if (which == 0) gyro_error<T>(weight, y, t, imu, trajectory, residual);
+    else if (which == 2) position_error<T>(weight, y, t, trajectory, residual);      // PositionMeasurement: the sensor blocks are inert
     else accel_error<T>(weight, y, t, imu, trajectory, residual);
     return true;
   }
@@ -232,7 +233,7 @@ int kto_se3_evaluate_matrices(const kto_traj* tr, int n, const double* t, double
   return worst;
 }
 
-// Gyroscope (which=0) / accelerometer (which=1) residual blocks.
+// Gyroscope (which=0) / accelerometer (which=1) / PositionMeasurement (which=2, position_measurement.h) residual blocks.
 //   r[3n]; cap_a / cap_b = capacity (knots per measurement) of ids_a/Ja and ids_b/Jb;
 //   ids_a[n*cap_a] (-1 padded), Ja[n*cap_a*3*size_a] row-major 3 x size blocks; same for b (SO3, size 4);
 //   Js[n*42]: q_ct 3x4 | p_ct 3x3 | d 3x1 | abias 3x3 | gbias 3x3 ; i0_a/i0_b: global index of the first ACTIVE knot.

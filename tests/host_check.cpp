@@ -125,7 +125,7 @@ void hc_imu_split(int which, double t0_r3, double dt_r3, int n_r3, double t0_so3
                   const double* y, const double* w, double* r, double* J, int* i0_r3, int* i0_so3, int* status) {
   SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
-  const int row = which == 0 ? 48 : 84;
+  const int row = which == 0 ? 48 : (which == 1 ? 84 : 36);
   for (int i = 0; i < n; ++i) {
     i0_r3[i] = -1; i0_so3[i] = -1;
     status[i] = imu_row_split(which, sp, imu, vecs4, quats, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)row * i, i0_r3 + i, i0_so3 + i);

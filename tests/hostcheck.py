@@ -137,7 +137,7 @@ def imu_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, y, w=None, t
     n = len(t)
     w = np.ones(n) if w is None else _f(w)
     r = np.zeros((n, 3))
-    J = np.zeros((n, 48)) if which == 0 else np.zeros((n, 84))
+    J = np.zeros((n, {0: 48, 1: 84, 2: 36}[which]))
     ia, ib, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
     lib().hc_imu_split(int(which), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), C.c_double(time_offset),
                        C.c_double(max_time_offset), int(locked), _p(v4), _p(q4), _p(pairs), n, _p(t), _p(y), _p(w), _p(r), _p(J), _p(ia), _p(ib), _p(st))

@@ -512,3 +512,41 @@ def test_newton_rows_without_noise_equal_static_rows_and_unsupported_modes():
     with pytest.raises(NotImplementedError):
         p.add_newton_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], time_offset_locked=False), c["obs_uv"], c["obs_t0"], c["ref_uv"],
                         c["ref_t0"], c["lm_idx"])
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_position_rows_match_oracle(split):
+    """PositionMeasurement (measurements/position_measurement.h) through the C ABI, SE3 and split trajectories; ragged tile."""
+    rng = np.random.default_rng(12)
+    n = 1000 + 17
+    p = _lib.Problem(0)
+    if not split:
+        knots = syn.smooth_se3_knots(300, 0.05)
+        traj = kto.Traj(kto.SE3, 0.05, 0.0, knots)
+        p.set_se3_spline(0.05, 0.0, len(knots))
+        tmax = 0.05 * (len(knots) - 3)
+    else:
+        k = syn.smooth_se3_knots(300, 0.05)
+        vecs, quats = k[:, 4:7].copy(), syn.smooth_se3_knots(380, 0.04)[:, :4].copy()
+        traj = kto.Traj(kto.SPLIT, 0.05, 0.0, vecs, 0.04, 0.01, quats)
+        p.set_split_spline(0.05, 0.0, len(vecs), 0.04, 0.01, len(quats))
+        knots = (vecs, quats)
+        tmax = min(0.05 * (len(vecs) - 3), 0.01 + 0.04 * (len(quats) - 3))
+    t, y, w = rng.uniform(0.02, tmax - 1e-6, n), rng.uniform(-5, 5, (n, 3)), rng.uniform(0.5, 2, n)
+    g = p.add_position(t, y, w)
+    assert p.group_kind(g) == _lib.POSITION and p.group_row_size(g) == (36 if split else 84)
+    out = p.evaluate(knots)[g]
+    o = kto.imu_residuals(traj, kto.Sensor(), 2, t, y, w, jac_mode=2)
+    assert (out["i0"] == o["i0_a"]).all()
+    assert parity.rel_err(out["r"], o["r"]) < parity.TOL
+    sa = 3 if split else 7
+    assert parity.rel_err(out["J"].reshape(n, 4, 3, sa), o["Ja"][:, :4]) < parity.TOL
+    if split:
+        assert (out["i0_c"] == o["ids_b"][:, 0]).all() and not o["Jb"].any()
+    ids, nids = p.get_structure(g, cap=8)
+    assert (ids[:, :4] == o["ids_a"][:, :4]).all() and (nids == 4).all()
+    with pytest.raises(ValueError):
+        p2 = _lib.Problem(0)
+        p2.set_se3_spline(0.05, 0.0, 300)
+        p2.add_position([tmax + 1.0], np.zeros((1, 3)))
+        p2.evaluate(syn.smooth_se3_knots(300, 0.05))

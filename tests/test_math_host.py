@@ -262,3 +262,20 @@ def test_newton_rs_huber_corrector_matches_oracle():
         Jmine = np.concatenate([Js[0, k] for k in range(m)] + [Jr[0].reshape(2, 1)], axis=1)
         assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
         assert np.abs(h["r"][i] - r2).max() <= parity.TOL * 1e3
+
+
+def test_position_rows_match_oracle():
+    """PositionMeasurement (position_measurement.h:24-31) on SE3: r = p - position(t), Jacobian through the cumulative spline."""
+    knots = fx.smooth_se3_knots(60, 0.1)
+    rng = np.random.default_rng(8)
+    t, y, w = rng.uniform(0.0, 5.69, 200), rng.uniform(-5, 5, (200, 3)), rng.uniform(0.5, 2, 200)
+    o = parity.oracle_imu(kto.Traj(kto.SE3, 0.1, 0.0, knots), 2, t, y, w)
+    h = hc.imu(2, knots, 0.1, 0.0, t, y, w)
+    assert (h["status"] == 0).all() and (h["i0"] == o["i0"]).all()
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(h["J"], o["J"]) < parity.TOL
+    # ... and on the reference's own SE3 fixture (large relative rotations between knots)
+    t = np.linspace(fx.SE3_T0, fx.SE3_T0 + 3 * fx.SE3_DT - 1e-9, 40)
+    o = parity.oracle_imu(kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS), 2, t, np.zeros((40, 3)))
+    h = hc.imu(2, fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t, np.zeros((40, 3)))
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL and parity.rel_err(h["J"], o["J"]) < parity.TOL

@@ -83,3 +83,17 @@ def test_split_non_unit_quaternion_flags_runtime_error():
     q[10] *= 1.001
     _, _, _, st = hc.split_prepass(vecs, q)
     assert st == -2        # std::runtime_error in the reference (quaternion_math.h:19-23)
+
+
+def test_split_position_rows_match_oracle():
+    """PositionMeasurement (position_measurement.h:24-31) on the split trajectory: only the R3 spline is evaluated."""
+    vecs, quats, traj, _ = _traj()
+    rng = np.random.default_rng(5)
+    t, y, w = rng.uniform(0.02, 7.2, 200), rng.uniform(-5, 5, (200, 3)), rng.uniform(0.5, 2, 200)
+    o = kto.imu_residuals(traj, kto.Sensor(), 2, t, y, w, jac_mode=2)
+    h = hc.imu_split(2, vecs, 0.05, 0.0, quats, 0.04, 0.01, t, y, w)
+    assert (h["status"] == 0).all()
+    assert (h["i0_r3"] == o["i0_a"]).all() and (h["i0_so3"] == o["ids_b"][:, 0]).all()
+    assert parity.rel_err(h["r"], o["r"]) < parity.TOL
+    assert parity.rel_err(h["J"].reshape(-1, 4, 3, 3), o["Ja"][:, :4]) < parity.TOL
+    assert not o["Jb"].any()                                  # the SO3 blocks are structurally present but zero

@@ -6,7 +6,8 @@ import pytest
 import fixtures_ref as fx
 import kontiki_b200 as kontiki
 from kontiki_b200 import sfm
-from kontiki_b200.measurements import AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, StaticRsCameraMeasurement
+from kontiki_b200.measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, PositionMeasurement,
+                                       StaticRsCameraMeasurement)
 from kontiki_b200.sensors import AtanCamera, BasicImu, PinholeCamera
 from kontiki_b200.trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory
 
@@ -424,3 +425,27 @@ def test_estimator_solve_newton_measurements_reduce_cost():
                 est2.add_measurement(NewtonRsCameraMeasurement(cam, obs))
     s2 = est2.solve(max_iterations=5, progress=False)
     assert s2.final_cost <= s2.initial_cost
+
+
+@pytest.mark.parametrize("make", [smooth_se3, split_fixture])
+def test_position_measurement_and_solve(make):
+    """test_measurements.py (position): measure == trajectory.position; test_estimator.py:41-45: solve with PositionMeasurements."""
+    traj = make()
+    ts = np.linspace(traj.min_time + 1e-3, traj.max_time - 1e-3, 80)
+    truth = [traj.position(t) for t in ts]
+    m = PositionMeasurement(ts[3], truth[3] + 1.0)
+    assert np.allclose(m.measure(traj), truth[3], atol=1e-12) and np.allclose(m.error(traj), 1.0, atol=1e-12)
+    assert m.t == ts[3] and np.allclose(m.p, truth[3] + 1.0)
+    # perturb the positions, then fit them back
+    rng = np.random.default_rng(0)
+    spl = traj if isinstance(traj, UniformSE3SplineTrajectory) else traj.R3_spline
+    cols = slice(4, 7) if isinstance(traj, UniformSE3SplineTrajectory) else slice(0, 3)
+    spl.control_points[:, cols] += rng.normal(0, 0.05, spl.control_points[:, cols].shape)
+    est = kontiki.TrajectoryEstimator(traj)
+    for t, p in zip(ts, truth):
+        est.add_measurement(PositionMeasurement(t, p))
+    s = est.solve(max_iterations=25, progress=False)
+    assert s.final_cost < 1e-6 * s.initial_cost
+    assert max(np.abs(traj.position(t) - p).max() for t, p in zip(ts, truth)) < 1e-4
+    with pytest.raises(ValueError):
+        est.add_measurement(PositionMeasurement(traj.max_time + 1.0, np.zeros(3)))
