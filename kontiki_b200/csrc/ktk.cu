@@ -33,7 +33,6 @@ namespace {
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NEWTON_RS; }
-inline int imu_which(int kind) { return kind == KTK_GYROSCOPE ? 0 : (kind == KTK_ACCELEROMETER ? 1 : 2); }
 #define KTK_CUDA(call)                                                                                   \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -1190,7 +1189,6 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     Group& g = *p->groups[gi];
     if (g.n == 0) continue;
     const ktk_group_out& o = outs[gi];
-    if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement on a split trajectory is not built");
     const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
     const int blocks = (int)((g.n + tpb - 1) / tpb);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1239,6 +1237,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
   for (auto g : p->groups) {
     if ((st = upload_group(p, *g))) return st;
     if (g->kind == KTK_NEWTON_RS && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRsCameraMeasurement are not built");
+    if (g->kind == KTK_NEWTON_RS && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement on a split trajectory is not built");
     if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
