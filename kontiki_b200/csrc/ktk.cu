@@ -251,14 +251,15 @@ struct CamArgs {
   const double* knots; const double* pairs; const double* recs;
   const double* obs_uv; const double* obs_t0; const double* ref_t0; const int* ref_idx; const double* w; const double* huber;
   const int* perm;
+  const int* io; const double* uo;     // first knot / interpolation amount of the observation evaluation, located once at upload time
   int n; uint32_t flags;
   double* r; double* J; int* i0r; int* i0o; int* err;
 };
-struct CamIn { double u, v, obs_t0, ref_t0, w, huber; int ridx, perm; };
+struct CamIn { double u, v, uo, w, huber; int io, ridx, perm; };
 __device__ __forceinline__ CamIn cam_load(const CamArgs& a, int i) {
-  CamIn in; in.perm = -1; in.ridx = -1; in.u = in.v = in.obs_t0 = in.ref_t0 = in.w = in.huber = 0;
+  CamIn in; in.perm = -1; in.ridx = -1; in.io = -1; in.u = in.v = in.uo = in.w = in.huber = 0;
   if (i < a.n) {
-    in.u = a.obs_uv[2 * (size_t)i]; in.v = a.obs_uv[2 * (size_t)i + 1]; in.obs_t0 = a.obs_t0[i]; in.ref_t0 = a.ref_t0[i]; in.w = a.w[i];
+    in.u = a.obs_uv[2 * (size_t)i]; in.v = a.obs_uv[2 * (size_t)i + 1]; in.io = a.io[i]; in.uo = a.uo[i]; in.w = a.w[i];
     in.huber = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0; in.ridx = a.ref_idx[i];
     in.perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
   }
@@ -285,7 +286,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   // consecutive 832-B records.  A one-warp CTA meets a cold L1 and the row scatter streams through it, so without this
   // every sector of the window is fetched from L2 several times per tile (ncu: 18 % L1 hit rate on the loads).
   {
-    const int ig = live ? knot_floor(static_rs_time(a.cam, cur.obs_t0, cur.v), a.sp.t0, a.sp.dt) : 0;
+    const int ig = live ? cur.io : 0;
     wmin = __reduce_min_sync(0xffffffffu, live ? ig : 0x7fffffff);
     wmax = __reduce_max_sync(0xffffffffu, live ? ig : (int)0x80000000);
     const int nrec = wmax - wmin + 3;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   warp_gather_records<kRefStride, kCamRowStride, kRefInRow>(wbase, a.recs, cur.ridx, lane);
   cp_async_commit();
   ObsForward f; f.status = kStatusRange; f.io = -1;
-  if (live) static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
+  if (live && cur.io >= 0) { f.status = 0; f.io = cur.io; f.bo = cumulative_basis(cur.uo, a.sp.dt); }
   // a row whose exact first knot (segment arithmetic) lies in the staged window reads its pair records from shared memory
   if (f.status == 0 && f.io >= wmin && f.io <= wmax) pairs = wbase + 32 * kCamRowStride - (size_t)(wmin + 1) * kPairStride;
   cp_async_wait_group<1>();      // the window has landed; the record gather may still be in flight
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_dev(con
   const double ouv[2] = {cur.u, cur.v};
   warp_gather_records<kRefStride, kCamDevStride, kRefInRowDev>(wbase, a.recs, cur.ridx, lane);
   ObsForward f; f.status = kStatusRange; f.io = -1;
-  if (cur.perm >= 0 && cur.ridx >= 0) {
-    static_rs_row_locate(a.sp, a.cam, ouv, cur.obs_t0, cur.ref_t0, f);
+  if (cur.perm >= 0 && cur.ridx >= 0 && cur.io >= 0) {
+    f.status = 0; f.io = cur.io; f.bo = cumulative_basis(cur.uo, a.sp.dt);
     static_rs_row_pose(a.knots, a.pairs, f);
   }
   cp_async_wait_all();
@@ -383,14 +384,21 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_dev(con
       r[0] = r[1] = nan(""); ir = io = -1;
       for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
     }
-    if (a.r) { a.r[2 * (size_t)i] = r[0]; a.r[2 * (size_t)i + 1] = r[1]; }
-    if (a.i0r) a.i0r[i] = ir;
-    if (a.i0o) a.i0o[i] = io;
+    const size_t dst = (size_t)cur.perm;                 // == i in device order
+    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+    if (a.i0r) a.i0r[dst] = ir;
+    if (a.i0o) a.i0o[dst] = io;
   }
   fence_async_smem();
   __syncwarp();
-  if (wantJ && lane == 0) {
-    bulk_store(a.J + (size_t)tile * 32 * kCamRow, wbase, (unsigned)(min(32, a.n - tile * 32) * kCamRow * 8));
+  if (!wantJ) return;
+  if (a.flags & KTK_EVAL_DEVICE_ORDER) {
+    if (lane == 0) {
+      bulk_store(a.J + (size_t)tile * 32 * kCamRow, wbase, (unsigned)(min(32, a.n - tile * 32) * kCamRow * 8));
+      bulk_store_wait_read();
+    }
+  } else if (cur.perm >= 0) {                            // caller order: one 912-B bulk store per row, to the row's insertion index
+    bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
     bulk_store_wait_read();
   }
 }
@@ -809,7 +817,8 @@ struct Group {
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
   DevBuf<double> d_t, d_y, d_w, d_obs_uv, d_obs_t0, d_ref_t0, d_huber;
-  DevBuf<int> d_perm, d_ref_idx, d_lm_caller, d_lm_sorted;
+  DevBuf<int> d_perm, d_ref_idx, d_lm_caller, d_lm_sorted, d_io;
+  DevBuf<double> d_uo;
   DevBuf<double> d_ref_uv_sorted;
   double bias[3] = {0.0, 0.0, 0.0};
   DevBuf<double> o_Js;
@@ -863,8 +872,7 @@ void fill_camera_consts(const ktk_camera& cm, CameraConst& c) {
   k[6] = a[3] * a[7] - a[4] * a[6]; k[7] = a[1] * a[6] - a[0] * a[7]; k[8] = a[0] * a[4] - a[1] * a[3];
   const double det = a[0] * k[0] + a[1] * k[3] + a[2] * k[6];
   for (int i = 0; i < 9; ++i) c.Kinv[i] = k[i] / det;
-  for (int i = 0; i < 4; ++i) c.q_ct[i] = cm.base.q_ct[i];
-  for (int i = 0; i < 3; ++i) c.p_ct[i] = cm.base.p_ct[i];
+  camera_set_pose(c, cm.base.q_ct, cm.base.p_ct);
   c.time_offset = cm.base.time_offset; c.max_time_offset = cm.base.max_time_offset; c.time_offset_locked = cm.base.time_offset_locked;
   c.readout = cm.readout; c.row_delta = cm.readout / (double)cm.rows;
   c.rows = cm.rows; c.model = cm.model; c.wc[0] = cm.wc[0]; c.wc[1] = cm.wc[1]; c.gamma = cm.gamma;
@@ -965,6 +973,12 @@ int upload_group(ktk_problem* p, Group& g) {
     if ((st = g.d_obs_t0.upload(gather(g.obs_t0, g.perm, 1), s))) return st;
     if ((st = g.d_ref_t0.upload(gather(g.ref_t0, g.perm, 1), s))) return st;
     if ((st = g.d_huber.upload(gather(g.huber, g.perm, 1), s))) return st;
+    if (!split) {      // observation-side lookup, independent of the evaluation point: once per row, here
+      std::vector<int> io((size_t)g.n); std::vector<double> uo((size_t)g.n);
+      for (int64_t i = 0; i < g.n; ++i) static_rs_row_locate_u(p->sp, cc, &g.obs_uv[2 * i], g.obs_t0[i], g.ref_t0[i], io[i], uo[i]);
+      if ((st = g.d_io.upload(gather(io, g.perm, 1), s))) return st;
+      if ((st = g.d_uo.upload(gather(uo, g.perm, 1), s))) return st;
+    }
     if (!g.sensor.q_locked || !g.sensor.p_locked || !g.sensor.time_offset_locked) {     // inputs of the sensor-Jacobian kernel
       if ((st = g.d_ref_uv_sorted.upload(gather(g.ref_uv, g.perm, 2), s))) return st;
       if ((st = g.d_lm_sorted.upload(gather(g.lm, g.perm, 1), s))) return st;
@@ -1312,7 +1326,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.sp = p->sp; a.cam = ra.cam;
       a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.recs = g.d_recs.p;
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
-      a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+      a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
       if (g.kind == KTK_NEWTON_RS) {
         NewtonArgs na;
@@ -1322,6 +1336,9 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
       }
+#ifndef KTK_CALLER_SCATTER
+      else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
+#endif
       else if ((flags & KTK_EVAL_DEVICE_ORDER) && !(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
       else k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {

@@ -228,7 +228,8 @@ template <int N> KB_HD G6<N> mul_Jr6(const G6<N>& g, const ExpPart& e, double B)
 template <int N> KB_HD G6<N> gadd(const G6<N>& a, const G6<N>& b) { G6<N> r; r.U = radd(a.U, b.U); r.W = radd(a.W, b.W); return r; }
 template <int N> KB_HD G6<N> gscale(double s, const G6<N>& a) { G6<N> r; r.U = rscale(s, a.U); r.W = rscale(s, a.W); return r; }
 
-// J_block(N x 7) (+)= scale * [G.U | G.W](N x 6) * D,   D = one side (6 x 8 padded) of a pair record, 16-B aligned
+// J_block(N x 7) (+)= scale * [G.U | G.W](N x 6) * D,   D = one side (6 x 8 padded) of a pair record, 16-B aligned.
+// The rotation part of log(Pa^-1 Pb) does not depend on the translations: rows 3..5 of D are zero in columns 4..6 and are skipped.
 template <int N, bool ACC>
 KB_HD void contract_pair(double* J, const G6<N>& g, const double* D, double scale) {
 #pragma unroll
@@ -239,7 +240,7 @@ KB_HD void contract_pair(double* J, const G6<N>& g, const double* D, double scal
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
 #pragma unroll
-    for (int m = 0; m < 6; ++m) {
+    for (int m = 0; m < (h == 0 ? 6 : 3); ++m) {       // d phi / d t == 0: the translation columns only see the upsilon rows
       const Dbl2* d2 = reinterpret_cast<const Dbl2*>(D + m * 8 + 4 * h);
       const Dbl2 v0 = d2[0], v1 = d2[1];
       const double d[4] = {v0.x, v0.y, v1.x, v1.y};
@@ -498,6 +499,7 @@ KB_HD HuberScale huber_scale(double a, double s) {
 struct CameraConst {
   double K[9], Kinv[9];     // pinhole_camera.h:25 (meta, not optimised); Kinv by cofactors once instead of per call (:63-67)
   double q_ct[4], p_ct[3];  // sensors.h:36-57 relative pose (x,y,z,w)
+  double Rct[9];            // R(q_ct) (Eigen toRotationMatrix), once per group instead of once per row; camera_set_pose() fills it
   double time_offset, row_delta;   // row_delta = readout / rows (static_rscamera_measurement.h:30)
   double readout, max_time_offset;
   int time_offset_locked;
@@ -508,6 +510,12 @@ struct CameraConst {
 KB_HD M3 load_m3(const double* a) { M3 m;
 #pragma unroll
   for (int i = 0; i < 9; ++i) m.a[i] = a[i]; return m; }
+KB_HD void camera_set_pose(CameraConst& c, const double* q_ct, const double* p_ct) {
+  for (int i = 0; i < 4; ++i) c.q_ct[i] = q_ct[i];
+  for (int i = 0; i < 3; ++i) c.p_ct[i] = p_ct[i];
+  const M3 R = quat_to_rot(q_ct[0], q_ct[1], q_ct[2], q_ct[3]);
+  for (int i = 0; i < 9; ++i) c.Rct[i] = R.a[i];
+}
 
 // CameraView::Unproject: pinhole K^-1 [u v 1] (pinhole_camera.h:63-67); atan additionally undoes the distortion
 // L = phn.xy - wc, r = sqrt(|L|^2 + eps), f = tan(r gamma) / gamma, Y = [wc + f L / r, 1] (atan_camera.h:92-103).
@@ -563,7 +571,11 @@ KB_HD void landmark_ref_se3(const CameraConst& cam, const double* k0, const doub
                             const double* ref_uv, double rho, int i0, double* rec) {
   Pose P;
   pose_forward(k0, p1, p2, p3, bs, P);
+#ifdef KTK_RCT_INLINE
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+#else
+  const M3 Rct = load_m3(cam.Rct);
+#endif
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
   const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
   const V3 Xref = mul_t(Rct, yh - rho * pct);
@@ -589,7 +601,11 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
   *i0_ref = (int)ref[7];
   const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
   const double rho = ref[6];
+#ifdef KTK_RCT_INLINE
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+#else
+  const M3 Rct = load_m3(cam.Rct);
+#endif
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
   const V3 Xobs = mul_t(P.R, X - rho * P.p);                 // static_rscamera_measurement.h:49
   const V3 Xc = Rct * Xobs + rho * pct;                      // :52
@@ -773,6 +789,16 @@ KB_HD void static_rs_row_locate(const SplineConst& sp, const CameraConst& cam, c
   if (nseg == 0 || locate_in_segments(nseg, s0, s1, static_rs_time(cam, obs_t0, obs_uv[1]), sp.t0, sp.dt, f.io, uo) < 0) { f.status = kStatusRange; f.io = -1; return; }
   f.status = 0;
   f.bo = cumulative_basis(uo, sp.dt);
+}
+// The same lookup for the host: first knot and interpolation amount of the observation evaluation.  Neither depends on the
+// evaluation point (knots, rho), so upload_group() runs it ONCE per row and the kernels read (io, u) instead of redoing the two
+// spans, the segment rule and their six fp64 divisions in every evaluation.  Returns false where the reference throws.
+KB_HD bool static_rs_row_locate_u(const SplineConst& sp, const CameraConst& cam, const double* obs_uv, double obs_t0, double ref_t0, int& io, double& uo) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  io = -1; uo = 0.0;
+  if (nseg == 0 || locate_in_segments(nseg, s0, s1, static_rs_time(cam, obs_t0, obs_uv[1]), sp.t0, sp.dt, io, uo) < 0) { io = -1; return false; }
+  return true;
 }
 KB_HD void static_rs_row_pose(const double* knots, const double* pairs, ObsForward& f) {
   if (f.status != 0) return;

@@ -217,7 +217,7 @@ KB_HD void landmark_ref_split(const CameraConst& cam, const double* c0, const Ba
                               const Basis& bs, int i0_so3, const double* ref_uv, double rho, double* rec) {
   const M3 R = so3_forward(q0, p1, bs);
   const V3 p = r3_combine(c0, br.Bp);
-  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+  const M3 Rct = load_m3(cam.Rct);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
   const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
   const V3 Xref = mul_t(Rct, yh - rho * pct);
@@ -245,7 +245,7 @@ KB_HD void static_rs_obs_split(const CameraConst& cam, const double* c0, const B
   const double rho = ref[6];
   const double rbp[4] = {ref[kRefSplitBp], ref[kRefSplitBp + 1], ref[kRefSplitBp + 2], ref[kRefSplitBp + 3]};
   const V3 p = r3_combine(c0, br.Bp);
-  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+  const M3 Rct = load_m3(cam.Rct);
   const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
   const V3 Xw = X - rho * p;
   const V3 Xobs = mul_t(R, Xw);

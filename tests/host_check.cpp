@@ -43,8 +43,7 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
   SplineConst sp{t0, dt, n_knots, 0};
   CameraConst cam;
   for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
-  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
-  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  camera_set_pose(cam, q_ct, p_ct);
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
   finish_cam(cam, rows);
@@ -82,8 +81,7 @@ void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const doub
   SplineConst sp{t0, dt, n_knots, 0};
   CameraConst cam;
   for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
-  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
-  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  camera_set_pose(cam, q_ct, p_ct);
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
   finish_cam(cam, rows);
@@ -140,8 +138,7 @@ void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
   SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   CameraConst cam;
   for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
-  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
-  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  camera_set_pose(cam, q_ct, p_ct);
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
   finish_cam(cam, rows);
@@ -198,8 +195,7 @@ void hc_static_rs_sensor_se3(double t0, double dt, int n_knots, const double* K,
   SplineConst sp{t0, dt, n_knots, 0};
   CameraConst cam;
   for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
-  for (int i = 0; i < 4; ++i) cam.q_ct[i] = q_ct[i];
-  for (int i = 0; i < 3; ++i) cam.p_ct[i] = p_ct[i];
+  camera_set_pose(cam, q_ct, p_ct);
   cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
   cam.time_offset_locked = locked;
   finish_cam(cam, rows);
