@@ -365,11 +365,12 @@ def main():
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
                          "kernel_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in prof.items()},
-                         # secondary, compute side (north_star: "fp64-pipe utilisation against chip peak"): fp64 instructions per row from
-                         # the ncu instruction mix (profiles/README.md: 1568 DFMA + 611 DMUL + 236 DADD per static-RS row on SE3), peak =
-                         # the dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
-                         "fp64": ({"flop_per_row": 3983, "achieved_tflops": dom_rows * 3983 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
-                                   "frac": dom_rows * 3983 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
+                         # secondary, compute side (north_star: "fp64-pipe utilisation against chip peak"): fp64 instructions per row from the
+                         # ncu instruction mix (profiles/r1h_ncu_summary.csv / README.md: k_static_rs 1410 DFMA + 594 DMUL + 206 DADD per row, plus
+                         # k_landmark_ref 1565 + 548 + 249 per landmark record, 0.1 records per row on H1: 3620 + 393 flop), peak = the
+                         # dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
+                         "fp64": ({"flop_per_row": 4013, "achieved_tflops": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
+                                   "frac": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
     if not a.no_cpu_baseline and world == 1:
         base, _, _ = cpu_baseline(cfg, a.cpu_sample)
         line["cpu_baseline"] = base

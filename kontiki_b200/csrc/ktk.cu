@@ -6,10 +6,14 @@
 //   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
 //   k_landmark_ref   reference side of the static-RS rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
 //   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); the warp gathers its 32
-//                    landmark records into the row buffers with LDGSTS copies that overlap the observation-pose math
+//                    landmark records into the row buffers with LDGSTS copies that overlap the observation-pose math, every
+//                    thread builds its whole 912-B row in shared memory and the row leaves with ONE TMA bulk store to the
+//                    caller's row index (one store per 32-row tile with KTK_EVAL_DEVICE_ORDER)
+//   k_static_rs_local  the same rows in tangent coordinates (KTK_EVAL_LOCAL), staged in two halves and scattered cooperatively
+//   k_newton_rs      NewtonRsCameraMeasurement rows, one forward-mode direction per thread (newton_math.cuh)
 // Measurement records are sorted once (first evaluation) by their first active knot so that a warp touches one or two
-// knot windows; each thread builds its Jacobian row in shared memory, then the warp writes the 32 rows cooperatively
-// (16-byte chunks, one contiguous 672-B / 912-B run per row) at the CALLER's row indices, so rows come out in insertion
+// knot windows; IMU threads build their Jacobian row in shared memory, then the warp writes the 32 rows cooperatively
+// (16-byte chunks, one contiguous 672-B run per row) at the CALLER's row indices, so rows come out in insertion
 // order at full sector efficiency without a second pass.
 #include <cuda_runtime.h>
 
@@ -266,7 +270,8 @@ __device__ __forceinline__ CamIn cam_load(const CamArgs& a, int i) {
   return in;
 }
 
-__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const CamArgs a) {
+// KTK_EVAL_LOCAL rows (2 x 6 blocks, 98 doubles): staged in two halves through one 92-double buffer, cooperative scatter.
+__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_local(const CamArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * kCamWarpSmem;
@@ -347,12 +352,14 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   }
 }
 
-// Device-order variant (KTK_EVAL_DEVICE_ORDER, ambient rows): row k of the output is the k-th row in DEVICE order (sorted by
-// first knot; ktk_get_row_order gives the insertion index).  A warp's 32 rows are then one contiguous 32 x 912 B block of the
-// output: the rows are staged whole and leave with ONE TMA bulk store issued by lane 0 -- no scatter loop, no per-row address
-// arithmetic, and the residual / index stores are coalesced.
+// The static-RS kernel for ambient rows.  Every thread builds its whole 114-double row in shared memory (the landmark record is
+// gathered at offset 22 so that the in-place rewrite of the reference-window blocks never overtakes its reads) and the row leaves
+// with ONE TMA bulk store (cp.async.bulk.global.shared::cta, 912 B) to the caller's row index: no scatter loop, no second
+// staging pass.  With KTK_EVAL_DEVICE_ORDER row k of the output is the k-th row in DEVICE order (sorted by first knot;
+// ktk_get_row_order gives the insertion index): the warp's 32 rows are one contiguous 29-KB block and lane 0 issues a single
+// bulk store for the tile.
 constexpr int kCamDevStride = 114, kRefInRowDev = 22;      // record at 22..113: block k read at 30 + 21 k, written at 14 k
-__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_dev(const CamArgs a) {
+__global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const CamArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kCamDevStride;
@@ -1053,9 +1060,9 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kPosSplitStride * 8);
-  cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
+  cudaFuncSetAttribute(k_static_rs_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
-  cudaFuncSetAttribute(k_static_rs_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
+  cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamSplitWarpSmem * 8);
@@ -1336,11 +1343,8 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
       }
-#ifndef KTK_CALLER_SCATTER
-      else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
-#endif
-      else if ((flags & KTK_EVAL_DEVICE_ORDER) && !(flags & KTK_EVAL_LOCAL)) k_static_rs_dev<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
-      else k_static_rs<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
+      else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
+      else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {
       ImuArgs a;
       a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
