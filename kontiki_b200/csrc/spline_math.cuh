@@ -716,7 +716,33 @@ KB_HD void position_se3(const double* knot0, const double* p1, const double* p2,
   pose_backward<3>(knot0, p1, p2, p3, bs, m3_identity(), P.R, m3_zero(), -weight, J);
 }
 
-// gyroscope (which = 0) / accelerometer (which = 1) / position (which = 2); gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
+// OrientationMeasurement (measurements/orientation_measurement.h:27-31): ONE residual, Eigen 3.3's q.angularDistance(q_hat) =
+// 2 atan2(|vec(d)|, |d.w|), d = q conj(q_hat): the rotation angle theta in [0, pi] of E = R(q) R_hat^T, evaluated as
+// atan2(|s|, c) with s = vee(E - E^T)/2 = sin(theta) n, c = (tr E - 1)/2.  A body-frame perturbation R_hat <- R_hat Exp(d) turns E into
+// E Exp(-R_hat d), and d theta = n . eps for E Exp(eps) (n is an eigenvector of Jr^-1 with eigenvalue 1), so G_theta = -(R_hat^T n)^T.
+// theta = 0 or pi has no derivative (the reference's Jets give 0/0 there as well).  Returns theta, fills G_theta (1 x 3).
+KB_HD double orientation_angle(const double* q_meas /* x y z w */, const M3& Rhat, Mr<1>& Gth) {
+  const double inv = 1.0 / sqrt(q_meas[0] * q_meas[0] + q_meas[1] * q_meas[1] + q_meas[2] * q_meas[2] + q_meas[3] * q_meas[3]);
+  const M3 E = mul_nt(quat_to_rot(q_meas[0] * inv, q_meas[1] * inv, q_meas[2] * inv, q_meas[3] * inv), Rhat);
+  const V3 sv = v3(0.5 * (E.a[7] - E.a[5]), 0.5 * (E.a[2] - E.a[6]), 0.5 * (E.a[3] - E.a[1]));
+  const double sn = sqrt(dot(sv, sv)), c = 0.5 * (trace(E) - 1.0);
+  const V3 n = (1.0 / sn) * sv;
+  const V3 g = mul_t(Rhat, n);
+  Gth.a[0] = -g.x; Gth.a[1] = -g.y; Gth.a[2] = -g.z;
+  return atan2(sn, c);
+}
+KB_HD void orientation_se3(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, const double* q_meas,
+                           double* r, double* J /* [4 knots][1][7] */) {
+  Pose P;
+  pose_forward(knot0, p1, p2, p3, bs, P);
+  Mr<1> Gth, zero;
+  zero.a[0] = zero.a[1] = zero.a[2] = 0.0;
+  r[0] = orientation_angle(q_meas, P.R, Gth);
+  pose_backward<1>(knot0, p1, p2, p3, bs, zero, zero, Gth, 1.0, J);
+}
+
+// gyroscope (which = 0) / accelerometer (which = 1) / position (which = 2) / orientation (which = 3: y = q (x,y,z,w), r[1], J [4][1][7]);
+// gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
 KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const double* knots, const double* pairs,
                   double t, const double* y, double weight, double* r, double* J, int* i0_out) {
   double ta = t, tb = t;
@@ -730,6 +756,7 @@ KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const d
   const double* p1 = pairs + (size_t)(i0 + 1) * kPairStride;
   if (which == 0) gyro_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);
   else if (which == 2) position_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);
+  else if (which == 3) orientation_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, y, r, J);
   else {
     if (sp.compat_zero_dB) { bs.dB[0] = 0.0; bs.dB[1] = 0.0; bs.dB[2] = 0.0; }
     accel_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);

@@ -304,7 +304,8 @@ KB_HD double split_max_time(const SplitConst& sp) {                             
   return a < b ? a : b;
 }
 
-// which: 0 gyroscope (J 48 doubles, i0 = SO3), 1 accelerometer (J 84 doubles; i0_r3, i0_so3), 2 position (J [4 R3 knots][3][3] = 36)
+// which: 0 gyroscope (J 48 doubles, i0 = SO3), 1 accelerometer (J 84 doubles; i0_r3, i0_so3), 2 position (J [4 R3 knots][3][3] = 36),
+// 3 orientation (y = q (x,y,z,w), ONE residual, J [4 SO3 knots][1][4] = 16)
 KB_HD int imu_row_split(int which, const SplitConst& sp, const ImuConst& imu, const double* vecs, const double* quats, const double* pairs,
                         double t, const double* y, double weight, double* r, double* J, int* i0_r3, int* i0_so3) {
   double ta = t, tb = t;
@@ -333,6 +334,16 @@ KB_HD int imu_row_split(int which, const SplitConst& sp, const ImuConst& imu, co
   const double* q0 = quats + (size_t)ib * kQuatStride;
   const double* p1 = pairs + (size_t)(ib + 1) * kSo3PairStride;
   *i0_so3 = ib;
+  if (which == 3) {      // orientation_measurement.h: only the SO3 spline is evaluated (J [4 SO3 knots][1][4]); angularDistance is scale invariant
+    segments_one_span(ta, tb, sp.t0_r3, sp.dt_r3, seg);
+    *i0_r3 = seg.start;
+    const M3 R = so3_forward(q0, p1, bs);
+    Mr<1> Gth;
+    r[0] = orientation_angle(y, R, Gth);
+    const double grad[1] = {0.0};
+    so3_backward<1>(q0, p1, bs, Gth, grad, 1.0, J);
+    return 0;
+  }
   if (which == 0) {
     // the R3 segment is part of the residual's structure (split_trajectory.h:117-123) and must exist, but is not evaluated
     segments_one_span(ta, tb, sp.t0_r3, sp.dt_r3, seg);

@@ -424,6 +424,16 @@ template <class T> void position_error(double weight, const double p[3], double 
   auto result = traj.Evaluate(T(t), EvalPosition);
   r[0] = T(weight) * (T(p[0]) - result->position.x); r[1] = T(weight) * (T(p[1]) - result->position.y); r[2] = T(weight) * (T(p[2]) - result->position.z);
 }
+// measurements/orientation_measurement.h:27-31: Error = q.angularDistance(trajectory.Orientation(t)), ONE residual, with Eigen 3.3's
+// QuaternionBase::angularDistance:  d = (*this) * other.conjugate();  return 2 * atan2(d.vec().norm(), abs(d.w()))
+// (Eigen/src/Geometry/Quaternion.h; the CI image's libeigen3-dev is 3.3.4, .circleci/Dockerfile:1,15).  q_meas is (x, y, z, w) here.
+template <class T> void orientation_error(const double q_meas[4], double t, const TrajectoryView<T>& traj, T r[1]) {
+  auto result = traj.Evaluate(T(t), EvalOrientation);
+  const Quat<T> q{T(q_meas[0]), T(q_meas[1]), T(q_meas[2]), T(q_meas[3])};
+  const Quat<T> d = qmul(q, qconj(result->orientation));
+  const T n = ksqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+  r[0] = T(2.0) * katan2(n, kabs(d.w));
+}
 // measurements/accelerometer_measurement.h:37-39
 template <class T> void accel_error(double weight, const double a[3], double t, const SensorView<T>& imu, const TrajectoryView<T>& traj, T r[3]) {
   Vec3<T> m = imu_accelerometer(imu, traj, T(t));

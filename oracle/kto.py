@@ -184,19 +184,21 @@ def se3_evaluate_matrices(traj, t, raise_on_error=True):
 
 
 def imu_residuals(traj, imu, which, t, y, weight=None, jac_mode=2, nthreads=0, cap=None, raise_on_error=True):
-    """which: 0 gyro / 1 accel / 2 position (PositionMeasurement; `imu` is inert).  Returns dict(r, ids_a, Ja, ids_b, Jb, Js, i0_a, i0_b, status, eval_seconds)."""
-    t, y = _f64(t), _f64(y).reshape(-1, 3)
+    """which: 0 gyro / 1 accel / 2 position (PositionMeasurement; `imu` is inert) / 3 orientation (OrientationMeasurement: y = q (x,y,z,w),
+    ONE residual per row).  Returns dict(r, ids_a, Ja, ids_b, Jb, Js, i0_a, i0_b, status, eval_seconds)."""
+    nres = 1 if which == 3 else 3
+    t, y = _f64(t), _f64(y).reshape(-1, 4 if which == 3 else 3)
     n = len(t)
     weight = np.ones(n) if weight is None else _f64(weight)
     if cap is None:
         cap = 4 if imu.d_locked else 4 + int(np.ceil(2 * imu.max_time_offset / min(traj.dt_a, traj.dt_b))) + 2
     has_a, has_b = traj.kind != SO3, traj.kind in (SPLIT, SO3)
     sa = traj.size_a
-    r = np.zeros((n, 3))
+    r = np.zeros((n, nres))
     ids_a = np.full((n, cap), -1, np.int32) if has_a else None
-    Ja = np.zeros((n, cap, 3, sa)) if (has_a and jac_mode) else None
+    Ja = np.zeros((n, cap, nres, sa)) if (has_a and jac_mode) else None
     ids_b = np.full((n, cap), -1, np.int32) if has_b else None
-    Jb = np.zeros((n, cap, 3, 4)) if (has_b and jac_mode) else None
+    Jb = np.zeros((n, cap, nres, 4)) if (has_b and jac_mode) else None
     Js = np.zeros((n, 42)) if jac_mode else None
     i0_a, i0_b, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
     secs = C.c_double(0)

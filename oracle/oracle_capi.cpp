@@ -128,6 +128,7 @@ struct ImuFunctor {   // measurements/gyroscope_measurement.h:54-72 / accelerome
     SensorView<T> imu; imu.params = &params[offset]; imu.has_bias = has_bias;
     if (which == 0) gyro_error<T>(weight, y, t, imu, trajectory, residual);
     else if (which == 2) position_error<T>(weight, y, t, trajectory, residual);      // PositionMeasurement: the sensor blocks are inert
+    else if (which == 3) orientation_error<T>(y, t, trajectory, residual);           // OrientationMeasurement: y = q (x,y,z,w), 1 residual
     else accel_error<T>(weight, y, t, imu, trajectory, residual);
     return true;
   }
@@ -233,7 +234,8 @@ int kto_se3_evaluate_matrices(const kto_traj* tr, int n, const double* t, double
   return worst;
 }
 
-// Gyroscope (which=0) / accelerometer (which=1) / PositionMeasurement (which=2, position_measurement.h) residual blocks.
+// Gyroscope (which=0) / accelerometer (which=1) / PositionMeasurement (which=2, position_measurement.h) / OrientationMeasurement
+// (which=3, orientation_measurement.h: y has 4 doubles per row (x,y,z,w), ONE residual per row: r[n], blocks 1 x size) residual blocks.
 //   r[3n]; cap_a / cap_b = capacity (knots per measurement) of ids_a/Ja and ids_b/Jb;
 //   ids_a[n*cap_a] (-1 padded), Ja[n*cap_a*3*size_a] row-major 3 x size blocks; same for b (SO3, size 4);
 //   Js[n*42]: q_ct 3x4 | p_ct 3x3 | d 3x1 | abias 3x3 | gbias 3x3 ; i0_a/i0_b: global index of the first ACTIVE knot.
@@ -258,6 +260,7 @@ int kto_imu_residuals(const kto_traj* tr, const kto_sensor* imu, int which, int 
     if (st[i] != KTO_OK && first_err.empty()) first_err = g_last_error;
   }
   const int sa = td.has_a() ? td.size_a() : 0;
+  const int nres = which == 3 ? 1 : 3, ny = which == 3 ? 4 : 3;
 #ifdef _OPENMP
   if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
@@ -266,9 +269,9 @@ int kto_imu_residuals(const kto_traj* tr, const kto_sensor* imu, int which, int 
   for (int i = 0; i < n; ++i) {
     if (st[i] != KTO_OK) continue;
     const Block& b = blocks[i];
-    ImuFunctor f{&b, which, t[i], weight ? weight[i] : 1.0, y + 3 * i, imu->has_bias != 0};
+    ImuFunctor f{&b, which, t[i], weight ? weight[i] : 1.0, y + ny * i, imu->has_bias != 0};
     std::vector<std::vector<double>> jac;
-    st[i] = guarded([&] { evaluate_block(f, b, 3, jac_mode, r + 3 * i, jac); });
+    st[i] = guarded([&] { evaluate_block(f, b, nres, jac_mode, r + nres * i, jac); });
     if (st[i] != KTO_OK) continue;
     const double te = t[i] + imu->time_offset;
     if (i0_a) i0_a[i] = td.has_a() ? locate_knot(b.meta.a, b.ids_a, te) : -1;
@@ -277,13 +280,13 @@ int kto_imu_residuals(const kto_traj* tr, const kto_sensor* imu, int which, int 
     if (ids_b) for (int k = 0; k < cap_b; ++k) ids_b[size_t(i) * cap_b + k] = k < int(b.ids_b.size()) ? b.ids_b[k] : -1;
     if (jac_mode == 0) continue;
     size_t pb = 0;
-    if (Ja) { std::memset(Ja + size_t(i) * cap_a * 3 * sa, 0, sizeof(double) * cap_a * 3 * sa);
-      for (size_t k = 0; k < b.ids_a.size(); ++k) copy_block(jac[pb + k], Ja + (size_t(i) * cap_a + k) * 3 * sa, 3 * sa); }
+    if (Ja) { std::memset(Ja + size_t(i) * cap_a * nres * sa, 0, sizeof(double) * cap_a * nres * sa);
+      for (size_t k = 0; k < b.ids_a.size(); ++k) copy_block(jac[pb + k], Ja + (size_t(i) * cap_a + k) * nres * sa, nres * sa); }
     pb += b.ids_a.size();
-    if (Jb) { std::memset(Jb + size_t(i) * cap_b * 12, 0, sizeof(double) * cap_b * 12);
-      for (size_t k = 0; k < b.ids_b.size(); ++k) copy_block(jac[pb + k], Jb + (size_t(i) * cap_b + k) * 12, 12); }
+    if (Jb) { std::memset(Jb + size_t(i) * cap_b * nres * 4, 0, sizeof(double) * cap_b * nres * 4);
+      for (size_t k = 0; k < b.ids_b.size(); ++k) copy_block(jac[pb + k], Jb + (size_t(i) * cap_b + k) * nres * 4, nres * 4); }
     pb += b.ids_b.size();
-    if (Js) {
+    if (Js && nres == 3) {
       double* d = Js + size_t(i) * 42; std::memset(d, 0, 42 * sizeof(double));
       copy_block(jac[pb], d, 12); copy_block(jac[pb + 1], d + 12, 9); copy_block(jac[pb + 2], d + 21, 3);
       if (imu->has_bias) { copy_block(jac[pb + 3], d + 24, 9); copy_block(jac[pb + 4], d + 33, 9); }

@@ -29,9 +29,10 @@ void hc_imu(int which, double t0, double dt, int n_knots, int compat, double tim
             int* i0, int* status) {
   SplineConst sp{t0, dt, n_knots, compat};
   ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
+  const int ny = which == 3 ? 4 : 3, nres = which == 3 ? 1 : 3, row = which == 3 ? 28 : 84;      // orientation rows: q (4), one residual, [4][1][7]
   for (int i = 0; i < n; ++i) {
     i0[i] = -1;
-    status[i] = imu_row(which, sp, imu, knots8, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)84 * i, i0 + i);
+    status[i] = imu_row(which, sp, imu, knots8, pairs, t[i], y + ny * i, w[i], r + nres * i, J + (size_t)row * i, i0 + i);
   }
 }
 
@@ -123,10 +124,11 @@ void hc_imu_split(int which, double t0_r3, double dt_r3, int n_r3, double t0_so3
                   const double* y, const double* w, double* r, double* J, int* i0_r3, int* i0_so3, int* status) {
   SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   ImuConst imu{time_offset, max_time_offset, locked, {0.0, 0.0, 0.0}};
-  const int row = which == 0 ? 48 : (which == 1 ? 84 : 36);
+  const int row = which == 0 ? 48 : (which == 1 ? 84 : (which == 2 ? 36 : 16));
+  const int ny = which == 3 ? 4 : 3, nres = which == 3 ? 1 : 3;
   for (int i = 0; i < n; ++i) {
     i0_r3[i] = -1; i0_so3[i] = -1;
-    status[i] = imu_row_split(which, sp, imu, vecs4, quats, pairs, t[i], y + 3 * i, w[i], r + 3 * i, J + (size_t)row * i, i0_r3 + i, i0_so3 + i);
+    status[i] = imu_row_split(which, sp, imu, vecs4, quats, pairs, t[i], y + ny * i, w[i], r + nres * i, J + (size_t)row * i, i0_r3 + i, i0_so3 + i);
   }
 }
 

@@ -45,10 +45,10 @@ def prepass(knots7):
 
 def imu(which, knots7, dt, t0, t, y, w=None, compat=False, time_offset=0.0, max_time_offset=0.1, locked=True):
     k8, pairs = prepass(knots7)
-    t, y = _f(t), _f(y).reshape(-1, 3)
+    t, y = _f(t), _f(y).reshape(-1, 4 if which == 3 else 3)
     n = len(t)
     w = np.ones(n) if w is None else _f(w)
-    r, J = np.zeros((n, 3)), np.zeros((n, 4, 3, 7))
+    r, J = (np.zeros((n, 1)), np.zeros((n, 4, 1, 7))) if which == 3 else (np.zeros((n, 3)), np.zeros((n, 4, 3, 7)))
     i0, st = np.zeros(n, np.int32), np.zeros(n, np.int32)
     lib().hc_imu(int(which), C.c_double(t0), C.c_double(dt), len(k8), int(compat), C.c_double(time_offset), C.c_double(max_time_offset),
                  int(locked), _p(k8), _p(pairs), n, _p(t), _p(y), _p(w), _p(r), _p(J), _p(i0), _p(st))
@@ -133,11 +133,11 @@ def split_prepass(vecs3, quats):
 
 def imu_split(which, vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, t, y, w=None, time_offset=0.0, max_time_offset=0.1, locked=True):
     v4, q4, pairs, st0 = split_prepass(vecs3, quats)
-    t, y = _f(t), _f(y).reshape(-1, 3)
+    t, y = _f(t), _f(y).reshape(-1, 4 if which == 3 else 3)
     n = len(t)
     w = np.ones(n) if w is None else _f(w)
-    r = np.zeros((n, 3))
-    J = np.zeros((n, {0: 48, 1: 84, 2: 36}[which]))
+    r = np.zeros((n, 1 if which == 3 else 3))
+    J = np.zeros((n, {0: 48, 1: 84, 2: 36, 3: 16}[which]))
     ia, ib, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
     lib().hc_imu_split(int(which), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), C.c_double(time_offset),
                        C.c_double(max_time_offset), int(locked), _p(v4), _p(q4), _p(pairs), n, _p(t), _p(y), _p(w), _p(r), _p(J), _p(ia), _p(ib), _p(st))

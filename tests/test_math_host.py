@@ -279,3 +279,31 @@ def test_position_rows_match_oracle():
     o = parity.oracle_imu(kto.Traj(kto.SE3, fx.SE3_DT, fx.SE3_T0, fx.SE3_KNOTS), 2, t, np.zeros((40, 3)))
     h = hc.imu(2, fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0, t, np.zeros((40, 3)))
     assert parity.rel_err(h["r"], o["r"]) < parity.TOL and parity.rel_err(h["J"], o["J"]) < parity.TOL
+
+
+def _orientation_case(knots, dt, t0, n, seed):
+    """Measured orientations = the trajectory's own, rotated by a random 0.05 .. 2.5 rad (both hemispheres of the quaternion)."""
+    rng = np.random.default_rng(seed)
+    t = rng.uniform(t0 + 1e-3, t0 + (len(knots) - 3) * dt - 1e-3, n)
+    q = kto.traj_evaluate(kto.Traj(kto.SE3, dt, t0, knots), t, 0xff)["orientation"]
+    ang = rng.uniform(0.05, 2.5, n)
+    ax = rng.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1)[:, None]
+    dq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1)
+    x1, y1, z1, w1 = q.T; x2, y2, z2, w2 = dq.T
+    qm = np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+                   w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2], axis=1)
+    qm[::2] *= -1.0                     # q and -q are the same rotation: angularDistance uses |d.w|
+    qm[::3] *= 1.7                      # ... and is scale invariant
+    return t, qm, ang
+
+
+def test_orientation_rows_match_oracle():
+    """OrientationMeasurement (orientation_measurement.h:27-31): one residual = angular distance, analytic Jacobian vs the oracle's autodiff."""
+    knots = fx.smooth_se3_knots(60, 0.1)
+    t, qm, ang = _orientation_case(knots, 0.1, 0.0, 200, 3)
+    o = kto.imu_residuals(kto.Traj(kto.SE3, 0.1, 0.0, knots), kto.Sensor(), 3, t, qm, jac_mode=2)
+    assert np.abs(o["r"][:, 0] - ang).max() < 1e-9          # the oracle returns the angle the case was built with
+    h = hc.imu(3, knots, 0.1, 0.0, t, qm)
+    assert (h["status"] == 0).all() and (h["i0"] == o["i0_a"]).all()
+    assert np.abs(h["r"] - o["r"]).max() < parity.TOL
+    assert parity.rel_err(h["J"], o["Ja"][:, :4]) < parity.TOL

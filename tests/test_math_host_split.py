@@ -97,3 +97,24 @@ def test_split_position_rows_match_oracle():
     assert parity.rel_err(h["r"], o["r"]) < parity.TOL
     assert parity.rel_err(h["J"].reshape(-1, 4, 3, 3), o["Ja"][:, :4]) < parity.TOL
     assert not o["Jb"].any()                                  # the SO3 blocks are structurally present but zero
+
+
+def test_split_orientation_rows_match_oracle():
+    """OrientationMeasurement on the split trajectory: only the SO3 spline is evaluated, one residual, J [4 SO3 knots][1][4]."""
+    vecs, quats, traj, _ = _traj()
+    rng = np.random.default_rng(6)
+    t = rng.uniform(0.02, 7.2, 150)
+    q = kto.traj_evaluate(traj, t, 0xff)["orientation"]
+    ang = rng.uniform(0.05, 2.5, len(t))
+    ax = rng.normal(size=(len(t), 3)); ax /= np.linalg.norm(ax, axis=1)[:, None]
+    dq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1)
+    x1, y1, z1, w1 = q.T; x2, y2, z2, w2 = dq.T
+    qm = np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+                   w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2], axis=1)
+    qm[::2] *= -1.0
+    o = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm, jac_mode=2)
+    h = hc.imu_split(3, vecs, 0.05, 0.0, quats, 0.04, 0.01, t, qm)
+    assert (h["status"] == 0).all() and (h["i0_so3"] == o["i0_b"]).all() and (h["i0_r3"] == o["ids_a"][:, 0]).all()
+    assert np.abs(o["r"][:, 0] - ang).max() < 1e-9 and np.abs(h["r"] - o["r"]).max() < parity.TOL
+    assert parity.rel_err(h["J"].reshape(-1, 4, 1, 4), o["Jb"][:, :4]) < parity.TOL
+    assert not o["Ja"].any()
