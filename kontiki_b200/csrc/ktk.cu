@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -173,9 +174,18 @@ struct ImuArgs {
   int n; uint32_t flags;
   double* r; double* J; int* i0; int* err;
 };
-struct ImuIn { double t, y0, y1, y2, w; int perm; };
+struct ImuIn { double t, y0, y1, y2, y3, w; int perm; };
+__device__ __forceinline__ ImuIn imu_load_q(const ImuArgs& a, int i) {      // OrientationMeasurement: y = q, 4 doubles per row
+  ImuIn in; in.perm = -1; in.t = 0; in.y0 = in.y1 = in.y2 = in.y3 = 0; in.w = 0;
+  if (i < a.n) {
+    const double2 q0 = reinterpret_cast<const double2*>(a.y)[2 * (size_t)i], q1 = reinterpret_cast<const double2*>(a.y)[2 * (size_t)i + 1];
+    in.t = a.t[i]; in.y0 = q0.x; in.y1 = q0.y; in.y2 = q1.x; in.y3 = q1.y; in.w = a.w[i];
+    in.perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
+  }
+  return in;
+}
 __device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
-  ImuIn in; in.perm = -1; in.t = 0; in.y0 = in.y1 = in.y2 = 0; in.w = 0;
+  ImuIn in; in.perm = -1; in.t = 0; in.y0 = in.y1 = in.y2 = in.y3 = 0; in.w = 0;
   if (i < a.n) {
     in.t = a.t[i]; in.y0 = a.y[3 * (size_t)i]; in.y1 = a.y[3 * (size_t)i + 1]; in.y2 = a.y[3 * (size_t)i + 2]; in.w = a.w[i];
     in.perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];      // destination row: device order or the caller's insertion order
@@ -183,8 +193,11 @@ __device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
   return in;
 }
 
+// WHICH: 0 gyroscope, 1 accelerometer, 2 PositionMeasurement (3 residuals, y[3], rows [4][3][7]); 3 OrientationMeasurement (ONE residual,
+// y = q (x,y,z,w), rows [4][1][7])
 template <int WHICH>
 __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACCEL_MINB) k_imu(const ImuArgs a) {
+  constexpr int NR = WHICH == 3 ? 1 : 3, ROW = NR * 28, LROW = NR * 24;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kImuRowStride;
@@ -193,26 +206,31 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
-  const ImuIn cur = imu_load(a, tile * 32 + lane);
+  const int i = tile * 32 + lane;
+  const ImuIn cur = WHICH == 3 ? imu_load_q(a, i) : imu_load(a, i);
   if (cur.perm >= 0) {
-    const double y[3] = {cur.y0 - a.imu.bias[0], cur.y1 - a.imu.bias[1], cur.y2 - a.imu.bias[2]};   // r = w (y - (model + bias))
+    double y[4] = {cur.y0, cur.y1, cur.y2, cur.y3};
+    if (WHICH != 3) { y[0] -= a.imu.bias[0]; y[1] -= a.imu.bias[1]; y[2] -= a.imu.bias[2]; }   // r = w (y - (model + bias))
     double r[3];
     int i0 = -1;
     const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, cur.t, y, cur.w, r, row, &i0);
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan("");
-      for (int c = 0; c < kImuRow; ++c) row[c] = nan("");
+      for (int c = 0; c < ROW; ++c) row[c] = nan("");
     }
-    else if (local) localize_se3_blocks<3>(row, 4, a.knots + (size_t)i0 * kKnotStride);
+    else if (local) localize_se3_blocks<NR>(row, 4, a.knots + (size_t)i0 * kKnotStride);
     const size_t dst = (size_t)cur.perm;
-    if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+    if (a.r) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) a.r[NR * dst + c] = r[c];
+    }
     if (a.i0) a.i0[dst] = i0;
   }
   __syncwarp();
   if (wantJ) {
-    if (local) warp_scatter_rows<72, kImuRowStride, 72>(wbase, a.J, cur.perm, lane);
-    else warp_scatter_rows<kImuRow, kImuRowStride, kImuRow>(wbase, a.J, cur.perm, lane);
+    if (local) warp_scatter_rows<LROW, kImuRowStride, LROW>(wbase, a.J, cur.perm, lane);
+    else warp_scatter_rows<ROW, kImuRowStride, ROW>(wbase, a.J, cur.perm, lane);
   }
 }
 
@@ -410,12 +428,122 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   }
 }
 
+// The static-RS kernel with FOUR lanes per row (spline_math.cuh "static-RS row split over FOUR lanes"): a warp is a tile of 8 rows, lane
+// 4 q + j works on row q; j = 1..3 owns level j of the cumulative product (exp part, Jr6, contraction with both sides of pair record j),
+// j = 0 owns knot i0; every lane produces one reference-window block.  The dependent chain per thread is ~3.5x shorter than one thread
+// per row and the live state fits in fewer registers, so more warps are resident.  Shared memory per warp: 8 contiguous 114-double rows
+// (the landmark record lands at offset 22 of its row, is read into registers, and the row is rebuilt over it) + 36 doubles per row of
+// (E_j, a_j) exchange.  Rows leave exactly like k_static_rs: one TMA bulk store per row (caller order) or per tile (device order).
+#ifndef KTK_CAM_QUAD_DEFAULT
+#define KTK_CAM_QUAD_DEFAULT 0
+#endif
+#ifndef KTK_QUAD_MINB
+#define KTK_QUAD_MINB 12
+#endif
+#ifndef KTK_QUAD_WARPS
+#define KTK_QUAD_WARPS 1
+#endif
+constexpr int kQuadRows = 8, kQuadThreads = 32 * KTK_QUAD_WARPS;
+constexpr int kQuadWarpSmem = kQuadRows * kCamRow + kQuadRows * 3 * kQuadEx;      // doubles per warp
+__global__ void __launch_bounds__(kQuadThreads, KTK_QUAD_MINB) k_static_rs_quad(const CamArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, j = lane & 3, q = lane >> 2;
+  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kQuadWarpSmem;
+  double* row = wbase + q * kCamRow;
+  double* ex = wbase + kQuadRows * kCamRow + q * 3 * kQuadEx;
+  const int tile = warp_tile();
+  if (tile * kQuadRows >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const CamIn cur = cam_load(a, tile * kQuadRows + q);
+  const double ouv[2] = {cur.u, cur.v};
+  // gather the tile's 8 landmark records (46 16-byte chunks each) into the row buffers, in flight during the forward chain
+  {
+    constexpr int kChunks = kRefStride / 2;
+#pragma unroll
+    for (int rr = 0; rr < kQuadRows; ++rr) {
+      const int ri = __shfl_sync(0xffffffffu, cur.ridx, 4 * rr);
+      if (ri < 0) continue;
+      const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ri * kRefStride);
+      double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRow + kRefInRowDev);
+      cp_async16(dst + lane, src + lane);
+      if (lane < kChunks - 32) cp_async16(dst + 32 + lane, src + 32 + lane);
+    }
+  }
+  const bool live = cur.perm >= 0 && cur.ridx >= 0 && cur.io >= 0;
+  const int jj = j < 1 ? 1 : j;
+  const double* knot0 = a.knots + (size_t)(live ? cur.io : 0) * kKnotStride;
+  const double* pj = a.pairs + (size_t)((live ? cur.io : 0) + jj) * kPairStride;
+  ExpPart e;
+  double B = 0.0;
+  if (live) {
+    B = quad_basis(cumulative_basis(cur.uo, a.sp.dt), jj);
+    double scratch[kQuadEx];
+    quad_level_exp(pj, B, e, j >= 1 ? ex + (j - 1) * kQuadEx : scratch);
+  }
+  __syncwarp();
+  Pose P; QuadTail qt; V3 a1;
+  if (live) quad_chain(knot0, ex, j, P, qt, a1);
+  cp_async_wait_all();
+  __syncwarp();
+  int st = live ? 0 : kStatusRange;
+  double r[2] = {0.0, 0.0}, jrho[2] = {0.0, 0.0}, out14[14];
+  int ir = -1;
+  ObsAdjoint adj;
+  if (st == 0) {
+    const double* rec = row + kRefInRowDev;
+    Mr<2> GX;
+    static_rs_project(a.cam, P, rec, ouv, cur.w, cur.huber, r, jrho, &ir, adj, GX);
+    if (ir < 0) st = kStatusRange;                 // the landmark record itself was out of range
+    double blk[21];
+#pragma unroll
+    for (int c = 0; c < 21; ++c) blk[c] = rec[kRefDOff + 21 * j + c];
+    static_rs_ref_block(GX, blk, out14);
+  }
+  __syncwarp();                                    // every lane has read what it needs of the record: the row is rebuilt over it
+  G6<2> g;
+  if (st == 0) {
+#pragma unroll
+    for (int c = 0; c < 14; ++c) row[14 * j + c] = out14[c];
+    if (j >= 1) { g = quad_level_adjoint(adj, qt, e, B); contract_pair_dyn<2>(row + kCamHalf + 14 * (j - 1), g, pj + kPairDOff, false); }
+    else { row[112] = jrho[0]; row[113] = jrho[1]; }
+  }
+  __syncwarp();
+  if (cur.perm >= 0) {
+    if (st == 0) {
+      if (j >= 1) contract_pair_dyn<2>(row + kCamHalf + 14 * j, g, pj + kPairDOff + kPairSide, j < 3);
+      else quad_direct(knot0, adj, qt, a1, row + kCamHalf);
+    } else {
+      for (int c = j; c < kCamRow; c += 4) row[c] = nan("");
+    }
+    if (j == 0) {
+      if (st != 0) { atomicMin(a.err, st); r[0] = r[1] = nan(""); ir = -1; }
+      const size_t dst = (size_t)cur.perm;
+      if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+      if (a.i0r) a.i0r[dst] = ir;
+      if (a.i0o) a.i0o[dst] = st == 0 ? cur.io : -1;
+    }
+  }
+  fence_async_smem();
+  __syncwarp();
+  if (!wantJ) return;
+  if (a.flags & KTK_EVAL_DEVICE_ORDER) {
+    if (lane == 0) {
+      bulk_store(a.J + (size_t)tile * kQuadRows * kCamRow, wbase, (unsigned)(min(kQuadRows, a.n - tile * kQuadRows) * kCamRow * 8));
+      bulk_store_wait_read();
+    }
+  } else if (j == 0 && cur.perm >= 0) {
+    bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
+    bulk_store_wait_read();
+  }
+}
+
 // =====================================================================================================================
 // Split trajectory (R3 + SO3) kernels: same tiling and data movement as above, rows of 48 / 84 / 114 doubles.
 // =====================================================================================================================
 constexpr int kGyroSplitRow = 48, kGyroSplitStride = 50;
 constexpr int kAccelSplitRow = 84, kAccelSplitStride = 86;
 constexpr int kPosSplitRow = 36, kPosSplitStride = 38;       // PositionMeasurement on a split trajectory: [4 R3 knots][3][3]
+constexpr int kOriSplitRow = 16, kOriSplitStride = 18;       // OrientationMeasurement on a split trajectory: [4 SO3 knots][1][4]
 
 __global__ void k_pack_vecs(const double* __restrict__ v3, int n, double* __restrict__ v4) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,8 +568,9 @@ struct ImuSplitArgs {
 };
 template <int WHICH>
 __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
-  constexpr int ROW = WHICH == 0 ? kGyroSplitRow : (WHICH == 1 ? kAccelSplitRow : kPosSplitRow);
-  constexpr int STRIDE = WHICH == 0 ? kGyroSplitStride : (WHICH == 1 ? kAccelSplitStride : kPosSplitStride);
+  constexpr int ROW = WHICH == 0 ? kGyroSplitRow : (WHICH == 1 ? kAccelSplitRow : (WHICH == 2 ? kPosSplitRow : kOriSplitRow));
+  constexpr int STRIDE = WHICH == 0 ? kGyroSplitStride : (WHICH == 1 ? kAccelSplitStride : (WHICH == 2 ? kPosSplitStride : kOriSplitStride));
+  constexpr int NR = WHICH == 3 ? 1 : 3, NY = WHICH == 3 ? 4 : 3;
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * STRIDE;
@@ -454,7 +583,10 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
   int perm = -1;
   if (i < a.n) {
     perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
-    const double y[3] = {a.y[3 * (size_t)i] - a.imu.bias[0], a.y[3 * (size_t)i + 1] - a.imu.bias[1], a.y[3 * (size_t)i + 2] - a.imu.bias[2]};
+    double y[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < NY; ++c) y[c] = a.y[NY * (size_t)i + c];
+    if (WHICH != 3) { y[0] -= a.imu.bias[0]; y[1] -= a.imu.bias[1]; y[2] -= a.imu.bias[2]; }
     double r[3];
     int ia = -1, ib = -1;
     const int st = imu_row_split(WHICH, a.sp, a.imu, a.vecs, a.quats, a.pairs, a.t[i], y, a.w[i], r, row, &ia, &ib);
@@ -462,15 +594,18 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan(""); ia = ib = -1;
       for (int c = 0; c < ROW; ++c) row[c] = nan("");
-    } else if (local && WHICH != 2) localize_so3_blocks<3>(row + (WHICH == 0 ? 0 : 36), 4, a.quats + (size_t)ib * kQuatStride);
+    } else if (local && WHICH != 2) localize_so3_blocks<NR>(row + (WHICH == 1 ? 36 : 0), 4, a.quats + (size_t)ib * kQuatStride);
     const size_t dst = (size_t)perm;
-    if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+    if (a.r) {
+#pragma unroll
+      for (int c = 0; c < NR; ++c) a.r[NR * dst + c] = r[c];
+    }
     if (a.i0_r3) a.i0_r3[dst] = ia;
     if (a.i0_so3) a.i0_so3[dst] = ib;
   }
   __syncwarp();
   if (wantJ) {
-    if (local && WHICH != 2) warp_scatter_rows<ROW - 12, STRIDE, ROW - 12>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from 3x4 to 3x3
+    if (local && WHICH != 2) warp_scatter_rows<ROW - 4 * NR, STRIDE, ROW - 4 * NR>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from NR x 4 to NR x 3
     else warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, perm, lane);
   }
 }
@@ -818,6 +953,7 @@ template <class T> struct DevBuf {
 
 struct Group {
   int kind = 0; int64_t n = 0;
+  int ny = 3;                     // doubles of y per row: 3 (gyroscope / accelerometer / position), 4 (orientation: q)
   ktk_sensor sensor{}; ktk_camera cam{};
   int newton_W = 0;               // Newton-RS groups: knots of the widest observation span (0 = not computed for the current spline)
   // caller-order host copies (structure queries) and sorted device copies
@@ -857,6 +993,7 @@ struct ktk_problem {
   int64_t launches = 0;
   bool profiling = false;
   bool graphs_enabled = true;
+  bool cam_quad = false;          // static-RS rows through k_static_rs_quad (four lanes per row) instead of k_static_rs
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<uint64_t> graph_key;
   int64_t graph_launches = 0;
@@ -992,7 +1129,7 @@ int upload_group(ktk_problem* p, Group& g) {
     }
   } else {
     if ((st = g.d_t.upload(gather(g.t, g.perm, 1), s))) return st;
-    if ((st = g.d_y.upload(gather(g.y, g.perm, 3), s))) return st;
+    if ((st = g.d_y.upload(gather(g.y, g.perm, g.ny), s))) return st;
   }
   KTK_CUDA(cudaStreamSynchronize(s));   // the gathered host vectors are temporaries
   g.uploaded = true;
@@ -1014,10 +1151,11 @@ int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   if (g.kind == KTK_NEWTON_RS) return 58 + 14 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
   if (p->traj == 1 && g.kind == KTK_POSITION) return kPosSplitRow;
+  if (g.kind == KTK_ORIENTATION) return p->traj == 1 ? (local ? 12 : kOriSplitRow) : (local ? 24 : 28);
   if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? (local ? 36 : kGyroSplitRow) : (local ? 72 : kAccelSplitRow);
   return local ? 72 : kImuRow;
 }
-int res_doubles(const Group& g) { return is_camera(g.kind) ? 2 : 3; }
+int res_doubles(const Group& g) { return is_camera(g.kind) ? 2 : (g.kind == KTK_ORIENTATION ? 1 : 3); }
 
 int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
@@ -1025,7 +1163,8 @@ int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const do
   if (n < 0 || (n > 0 && (!t || !y))) return fail(KTK_EINVAL, "bad measurement arrays");
   if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
   Group* g = new Group; g->kind = kind; g->n = n; g->sensor = *imu;
-  g->t.assign(t, t + n); g->y.assign(y, y + 3 * n);
+  g->ny = kind == KTK_ORIENTATION ? 4 : 3;
+  g->t.assign(t, t + n); g->y.assign(y, y + g->ny * n);
   if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
   p->groups.push_back(g);
   if (p->graph_exec) { cudaGraphExecDestroy(p->graph_exec); p->graph_exec = nullptr; }
@@ -1059,10 +1198,14 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu_split<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kOriSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kPosSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
+  cudaFuncSetAttribute(k_static_rs_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (kQuadThreads / 32) * kQuadWarpSmem * 8);
+  { const char* v = getenv("KTK_CAM_QUAD"); p->cam_quad = v ? atoi(v) != 0 : KTK_CAM_QUAD_DEFAULT; }
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamSplitWarpSmem * 8);
@@ -1103,6 +1246,11 @@ int ktk_add_position(ktk_problem* p, int64_t n, const double* t, const double* p
   ktk_sensor none{};           // PositionMeasurement has no sensor: identity pose, zero locked time offset
   none.q_ct[3] = 1.0; none.max_time_offset = 0.0; none.q_locked = none.p_locked = none.time_offset_locked = 1;
   return add_imu(p, KTK_POSITION, &none, n, t, position, w);
+}
+int ktk_add_orientation(ktk_problem* p, int64_t n, const double* t, const double* q) {
+  ktk_sensor none{};           // OrientationMeasurement has no sensor and no weight (orientation_measurement.h:20-31)
+  none.q_ct[3] = 1.0; none.max_time_offset = 0.0; none.q_locked = none.p_locked = none.time_offset_locked = 1;
+  return add_imu(p, KTK_ORIENTATION, &none, n, t, q, nullptr);
 }
 
 static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
@@ -1149,7 +1297,7 @@ int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor
 int ktk_set_group_bias(ktk_problem* p, int32_t group, const double* bias) {
   if (!p || group < 0 || group >= (int)p->groups.size() || !bias) return fail(KTK_EINVAL, "bad argument");
   Group& g = *p->groups[group];
-  if (is_camera(g.kind) || g.kind == KTK_POSITION) return fail(KTK_EINVAL, "only IMU groups have a bias");
+  if (is_camera(g.kind) || g.kind == KTK_POSITION || g.kind == KTK_ORIENTATION) return fail(KTK_EINVAL, "only IMU groups have a bias");
   for (int c = 0; c < 3; ++c) g.bias[c] = bias[c];
   drop_graph(p);
   return KTK_OK;
@@ -1171,7 +1319,7 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   if (!(flags & KTK_EVAL_SENSOR_JACOBIANS) || !o.Js || g.n == 0) return KTK_OK;
   cudaStream_t s = p->stream;
   const int blocks = (int)((g.n + 127) / 128);
-  if (g.kind == KTK_POSITION) return KTK_OK;           // no sensor
+  if (g.kind == KTK_POSITION || g.kind == KTK_ORIENTATION) return KTK_OK;           // no sensor
   if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRsCameraMeasurement are not built");
   if (g.kind == KTK_STATIC_RS) {
     if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
@@ -1237,6 +1385,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
       a.r = o.r; a.J = o.J; a.i0_r3 = o.i0; a.i0_so3 = o.i0_c; a.err = p->d_err.p;
       if (g.kind == KTK_GYROSCOPE) k_imu_split<0><<<blocks, kThreads, kThreads * kGyroSplitStride * 8, s>>>(a);
       else if (g.kind == KTK_POSITION) k_imu_split<2><<<blocks, kThreads, kThreads * kPosSplitStride * 8, s>>>(a);
+      else if (g.kind == KTK_ORIENTATION) k_imu_split<3><<<blocks, kThreads, kThreads * kOriSplitStride * 8, s>>>(a);
       else k_imu_split<1><<<blocks, kThreads, kThreads * kAccelSplitStride * 8, s>>>(a);
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
@@ -1343,6 +1492,10 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
       }
+      else if (!(flags & KTK_EVAL_LOCAL) && p->cam_quad) {
+        const int rows_per_cta = kQuadRows * (kQuadThreads / 32);
+        k_static_rs_quad<<<(int)((g.n + rows_per_cta - 1) / rows_per_cta), kQuadThreads, (kQuadThreads / 32) * kQuadWarpSmem * 8, s>>>(a);
+      }
       else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
       else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     } else {
@@ -1354,6 +1507,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
       if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
       else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
+      else if (g.kind == KTK_ORIENTATION) k_imu<3><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
       else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
     }
     if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
@@ -1479,7 +1633,7 @@ static RowWindows row_windows(const ktk_problem* p, const Group& g) {
   const int colB = split ? 3 * n_a : 0;
   w.rho_col0 = split ? (long long)3 * n_a + (long long)4 * n_b : (long long)7 * n_a;
   w.rho_off_in_row = -1;
-  w.nres = is_camera(g.kind) ? 2 : 3;
+  w.nres = res_doubles(g);
   w.row_len = row_doubles(p, g);
   auto set = [&](int i, int off, int width, int col, int slot) { w.j_off[i] = off; w.width[i] = width; w.col_off[i] = col; w.slot[i] = slot; w.nk[i] = 4; };
   if (!split) {
@@ -1488,7 +1642,7 @@ static RowWindows row_windows(const ktk_problem* p, const Group& g) {
     else { w.nwin = 1; set(0, 0, 7, 0, 0); }
   } else if (g.kind == KTK_STATIC_RS) {
     w.nwin = 4; set(0, 0, 3, 0, 0); set(1, 24, 4, colB, 2); set(2, 56, 3, 0, 1); set(3, 80, 4, colB, 3); w.rho_off_in_row = 112;
-  } else if (g.kind == KTK_GYROSCOPE) { w.nwin = 1; set(0, 0, 4, colB, 2); }
+  } else if (g.kind == KTK_GYROSCOPE || g.kind == KTK_ORIENTATION) { w.nwin = 1; set(0, 0, 4, colB, 2); }
   else if (g.kind == KTK_POSITION) { w.nwin = 1; set(0, 0, 3, 0, 0); }
   else { w.nwin = 2; set(0, 0, 3, 0, 0); set(1, 36, 4, colB, 2); }
   return w;

@@ -595,12 +595,13 @@ constexpr int kRefInRow = 0;       // the record fills the row buffer: block k i
 //  overlap the record gather with it)
 // The adjoints of the observation pose that the second half needs (18 doubles carried across the first scatter).
 struct ObsAdjoint { Mr<2> Gp, GpR, Gth; };
-// First half: projection, residual, reference-window blocks Jref[56] (may alias `ref`, see kRefInRow) and d r / d rho.
-KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c,
-                                  double* r, double* Jref, double* Jrho, int* i0_ref, ObsAdjoint& adj) {
-  *i0_ref = (int)ref[7];
-  const V3 X = v3(ref[0], ref[1], ref[2]), dXr = v3(ref[3], ref[4], ref[5]);
-  const double rho = ref[6];
+// Projection part of the first half: projection, residual (Huber-corrected), d r / d rho, the adjoints of the observation pose and
+// GX = d r / d X.  `hdr` = the first 8 doubles of the landmark record (X, dX/drho, rho, i0_ref).
+KB_HD void static_rs_project(const CameraConst& cam, const Pose& P, const double* hdr, const double* obs_uv, double weight, double huber_c,
+                             double* r, double* Jrho, int* i0_ref, ObsAdjoint& adj, Mr<2>& GX) {
+  *i0_ref = (int)hdr[7];
+  const V3 X = v3(hdr[0], hdr[1], hdr[2]), dXr = v3(hdr[3], hdr[4], hdr[5]);
+  const double rho = hdr[6];
 #ifdef KTK_RCT_INLINE
   const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
 #else
@@ -628,12 +629,25 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
 #pragma unroll
   for (int c = 0; c < 3; ++c) { Jp.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Jp.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
   const Mr<2> Go = rmul(Jp, Rct);               // d r / d Xobs
-  const Mr<2> GX = rmul_nt(Go, P.R);            // d r / d X
+  GX = rmul_nt(Go, P.R);                        // d r / d X
   // inverse depth: dXc/drho = R_ct R_o^T (dX/drho - p_o) + p_ct
   const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
   Jrho[0] = Jp.a[0] * dXc.x + Jp.a[1] * dXc.y + Jp.a[2] * dXc.z; Jrho[1] = Jp.a[3] * dXc.x + Jp.a[4] * dXc.y + Jp.a[5] * dXc.z;
   // observation pose: Xobs = R_o^T (X - rho p_o):  d/dp_o = -rho GX,  d/dtheta_o = Go hat(Xobs)
   adj.Gp = rscale(-rho, GX); adj.GpR = rscale(-rho, Go); adj.Gth = rmul_hat(Go, Xobs);
+}
+// One reference-window block: GX (2x3) * dX/dknot_k (3x7) -> out (2x7).  `blk` is in registers, so `out` may alias the record.
+KB_HD void static_rs_ref_block(const Mr<2>& GX, const double* blk, double* out) {
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+    for (int c = 0; c < 7; ++c) out[7 * rr + c] = GX.a[3 * rr] * blk[c] + GX.a[3 * rr + 1] * blk[7 + c] + GX.a[3 * rr + 2] * blk[14 + c];
+}
+// First half: projection, residual, reference-window blocks Jref[56] (may alias `ref`, see kRefInRow) and d r / d rho.
+KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const double* ref, const double* obs_uv, double weight, double huber_c,
+                                  double* r, double* Jref, double* Jrho, int* i0_ref, ObsAdjoint& adj) {
+  Mr<2> GX;
+  static_rs_project(cam, P, ref, obs_uv, weight, huber_c, r, Jrho, i0_ref, adj, GX);
   // reference-window blocks: GX (2x3) * dX/dknot_k (3x7), in place (see kRefInRow)
   const double* dXk = ref + kRefDOff;
 #pragma unroll
@@ -641,10 +655,7 @@ KB_HD void static_rs_obs_ref_half(const CameraConst& cam, const Pose& P, const d
     double blk[21];
 #pragma unroll
     for (int i = 0; i < 21; ++i) blk[i] = dXk[21 * k + i];
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-      for (int c = 0; c < 7; ++c) Jref[14 * k + 7 * rr + c] = GX.a[3 * rr] * blk[c] + GX.a[3 * rr + 1] * blk[7 + c] + GX.a[3 * rr + 2] * blk[14 + c];
+    static_rs_ref_block(GX, blk, Jref + 14 * k);
   }
 }
 
@@ -846,6 +857,89 @@ KB_HD int static_rs_row_ref_half(const CameraConst& cam, const ObsForward& f, co
 KB_HD void static_rs_row_obs_half(const double* knots, const double* pairs, const ObsForward& f, const ObsAdjoint& adj, double* Jobs) {
   const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
   pose_backward<2>(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, adj.Gp, adj.GpR, adj.Gth, 1.0, Jobs);
+}
+
+// ---- static-RS row split over FOUR lanes (k_static_rs_quad) ----------------------------------------------------------------
+// One thread per row runs ~3600 dependent-ish fp64 instructions with 255 registers; the kernel is bound by that chain (profiles/README.md).
+// The observation side factors by LEVEL of the cumulative product P = P0 A1 A2 A3, A_j = exp(B_j w_j): lane j = 1..3 of a row's quad
+// owns level j (its exp part, its Jr6 and the contraction with the two sides of pair record j), lane 0 owns knot i0 itself; the
+// reference-window half is one knot block per lane.  What the lanes exchange is (E_j, a_j), 12 doubles per level, through shared memory;
+// projection and adjoints (a few hundred instructions) are recomputed by all four lanes.  The pieces below are the per-lane steps; the
+// kernel (and tests/host_check.cpp, which runs the four lanes one after the other) only orders them.
+constexpr int kQuadEx = 12;          // E (9, row-major) | a (3)
+struct QuadTail { M3 T; V3 c; };     // T_j = E_{j+1} .. E_3 and c_{j+1} of pose_backward: what level j sees of the levels after it
+KB_HD double quad_basis(const Basis& bo, int jj) { return jj == 1 ? bo.B[0] : (jj == 2 ? bo.B[1] : bo.B[2]); }
+// step 1, lane j (jj = max(j, 1)): the level's exp part; ex = this level's 12-double slot
+KB_HD void quad_level_exp(const double* pj, double B, ExpPart& e, double* ex) {
+  exp_part(pj, B, true, true, e);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) ex[i] = e.E.a[i];
+  ex[9] = e.a.x; ex[10] = e.a.y; ex[11] = e.a.z;
+}
+// step 2, every lane: the forward chain of pose_forward from the three exchanged levels, and this lane's tail
+KB_HD void quad_chain(const double* knot0, const double* ex /* [3][12], levels 1..3 */, int j, Pose& P, QuadTail& q, V3& a1) {
+  const M3 E1 = load_m3(ex), E2 = load_m3(ex + kQuadEx), E3 = load_m3(ex + 2 * kQuadEx);
+  a1 = v3(ex[9], ex[10], ex[11]);
+  const V3 a2 = v3(ex[kQuadEx + 9], ex[kQuadEx + 10], ex[kQuadEx + 11]), a3 = v3(ex[2 * kQuadEx + 9], ex[2 * kQuadEx + 10], ex[2 * kQuadEx + 11]);
+  const V3 c2 = a2 + E2 * a3; const M3 T1 = E2 * E3;
+  const V3 c1 = a1 + E1 * c2; const M3 T0 = E1 * T1;
+  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
+  P.R = R0 * T0;
+  P.p = v3(knot0[4], knot0[5], knot0[6]) + R0 * c1;
+  if (j == 3) { q.T = m3_identity(); q.c = v3(0, 0, 0); }
+  else if (j == 2) { q.T = E3; q.c = a3; }
+  else if (j == 1) { q.T = T1; q.c = c2; }
+  else { q.T = T0; q.c = c1; }
+}
+// step 3, lanes 1..3: the level's 2 x 6 adjoint (pose_backward with the tail (T, c)); level 3 sees T = I, c = 0, which is exact
+KB_HD G6<2> quad_level_adjoint(const ObsAdjoint& adj, const QuadTail& q, const ExpPart& e, double B) {
+  G6<2> t;
+  t.U = rmul_nt(adj.GpR, q.T); t.W = rsub(rmul_nt(adj.Gth, q.T), rmul_hat(t.U, q.c));
+  return mul_Jr6(t, e, B);
+}
+// contract_pair with the accumulate switch at run time (level 3 writes block 3, levels 1 and 2 add to blocks written by the level above)
+template <int N>
+KB_HD void contract_pair_dyn(double* J, const G6<N>& g, const double* D, bool acc) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    double s[N][4];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[r][c] = 0.0;
+#pragma unroll
+    for (int m = 0; m < (h == 0 ? 6 : 3); ++m) {
+      const Dbl2* d2 = reinterpret_cast<const Dbl2*>(D + m * 8 + 4 * h);
+      const Dbl2 v0 = d2[0], v1 = d2[1];
+      const double d[4] = {v0.x, v0.y, v1.x, v1.y};
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        const double gm = m < 3 ? g.U.a[3 * r + m] : g.W.a[3 * r + m - 3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[r][c] += gm * d[c];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int c = 0; c < (h == 0 ? 4 : 3); ++c) {
+        const double v = 1.0 * s[r][c];
+        J[r * 7 + 4 * h + c] = acc ? J[r * 7 + 4 * h + c] + v : v;
+      }
+  }
+}
+// step 4, lane 0: knot i0 itself, added to block 0 after level 1 wrote its first side there (the tail of pose_backward)
+KB_HD void quad_direct(const double* knot0, const ObsAdjoint& adj, const QuadTail& q, V3 a1, double* J0) {
+  const Mr<2> GpR0 = rmul_nt(adj.GpR, q.T);
+  const Mr<2> Gth0 = rsub(rmul_nt(adj.Gth, q.T), rmul_hat(GpR0, q.c));
+  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
+  const V3 dps = 2.0 * (R0 * a1 - a1);
+  double grad[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) grad[r] = dot(rrow(adj.Gp, r), dps);
+  add_q0_block<2>(J0, Gth0, grad, knot0, 1.0);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) { J0[r * 7 + 4] += 1.0 * adj.Gp.a[3 * r]; J0[r * 7 + 5] += 1.0 * adj.Gp.a[3 * r + 1]; J0[r * 7 + 6] += 1.0 * adj.Gp.a[3 * r + 2]; }
 }
 
 }  // namespace kb
