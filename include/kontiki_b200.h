@@ -78,7 +78,7 @@ enum {
                              entry points below expect ambient rows. */
 };
 
-enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3, KTK_POSITION = 4 };
+enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3, KTK_POSITION = 4, KTK_ORIENTATION = 5 };
 enum { KTK_CAMERA_PINHOLE = 0, KTK_CAMERA_ATAN = 1 };
 
 /* sensors/sensors.h:91-109: relative pose + time offset; *_locked as the reference's lock flags (default locked). */
@@ -105,7 +105,8 @@ typedef struct {
 typedef ktk_camera ktk_pinhole_camera;   /* model = KTK_CAMERA_PINHOLE */
 
 /* Per measurement group output pointers (any may be NULL).  Host pointers for ktk_evaluate, device pointers for
- * ktk_evaluate_device.  Sizes for n rows: r n*3 (IMU) / n*2 (camera); J n*84 / n*114; i0 n; i0_b n (camera: obs). */
+ * ktk_evaluate_device.  Sizes for n rows: r n*3 (IMU, position) / n*2 (camera) / n (orientation); J n*84 / n*114 / n*28
+ * (ktk_group_row_size); i0 n; i0_b n (camera: obs). */
 typedef struct {
   double* r;
   double* J;
@@ -153,6 +154,13 @@ int ktk_add_accelerometer(ktk_problem* p, const ktk_sensor* imu, int64_t n, cons
  * 3 residuals, no sensor, no loss (the reference has no weight: pass NULL).  Rows as the IMU rows: SE3 J[4][3][7]; split trajectory
  * J[4 R3 knots][3][3] (36; the SO3 blocks of the residual are structurally present but zero), i0 = R3 knot, i0_c = SO3 segment start. */
 int ktk_add_position(ktk_problem* p, int64_t n, const double* t, const double* position, const double* weight);
+/* OrientationMeasurement::AddToEstimator (measurements/orientation_measurement.h:57-79): ONE residual per row,
+ * r = q.angularDistance(trajectory.Orientation(t)) (:27-31; Eigen 3.3: 2 atan2(|vec(d)|, |d.w|), d = q conj(q_hat)), no sensor, no weight,
+ * no loss.  q[4n] is (x, y, z, w) per row like every quaternion of this interface (the reference's constructor takes (w, x, y, z),
+ * orientation_measurement.h:21-22); it need not be normalised.  Outputs: r[n]; SE3 rows J[4][1][7] (28; KTK_EVAL_LOCAL 24), i0; split
+ * trajectory rows J[4 SO3 knots][1][4] (16; local 12), i0 = R3 segment start (structurally present, identically zero blocks), i0_c = SO3 knot.
+ * The angle has no derivative at 0 and pi (the reference's Jets produce 0/0 there too): such rows come out NaN in J. */
+int ktk_add_orientation(ktk_problem* p, int64_t n, const double* t, const double* q);
 int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static

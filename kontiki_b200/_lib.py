@@ -11,7 +11,7 @@ from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL, EVAL_DEVICE_ORDER = 1, 2, 4, 8, 16, 32
-GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS, POSITION = 0, 1, 2, 3, 4
+GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS, POSITION, ORIENTATION = 0, 1, 2, 3, 4, 5
 CAMERA_PINHOLE, CAMERA_ATAN = 0, 1
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -37,7 +37,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation"]
 
 _lib = None
 
@@ -70,6 +70,7 @@ def lib():
         L.ktk_add_gyroscope.argtypes = [C.c_void_p, C.POINTER(Sensor), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_add_accelerometer.argtypes = L.ktk_add_gyroscope.argtypes
         L.ktk_add_position.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_add_orientation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [C.c_void_p] * 7
         L.ktk_add_newton_rs.argtypes = L.ktk_add_static_rs.argtypes
         L.ktk_num_groups.argtypes = [C.c_void_p]
@@ -207,6 +208,13 @@ class Problem:
         w = None if weight is None else _f64(weight)
         return check(lib().ktk_add_position(self._h, len(t), _ptr(t), _ptr(y), _ptr(w)))
 
+    def add_orientation(self, t, q_xyzw):
+        """OrientationMeasurement rows: q (n, 4) as (x, y, z, w); one residual per row (the angular distance)."""
+        t, q = _f64(t), _f64(q_xyzw).reshape(-1, 4)
+        if len(t) != len(q):
+            raise ValueError("t and q differ in length")
+        return check(lib().ktk_add_orientation(self._h, len(t), _ptr(t), _ptr(q)))
+
     def add_newton_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
         return self.add_static_rs(camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight, huber_c, _fn=lib().ktk_add_newton_rs)
 
@@ -248,12 +256,13 @@ class Problem:
         outs = []
         for g in range(self.num_groups):
             n, cam = self.group_size(g), self.group_kind(g) in (STATIC_RS, NEWTON_RS)
-            o = dict(r=np.zeros((n, 2 if cam else 3)), i0=np.full(n, -1, np.int32))
+            nres = 2 if cam else (1 if self.group_kind(g) == ORIENTATION else 3)
+            o = dict(r=np.zeros((n, nres)), i0=np.full(n, -1, np.int32))
             if jacobians:
                 if local:
                     o["J"] = np.zeros((n, lib().ktk_group_row_size_local(self._h, g)))
                 else:
-                    o["J"] = np.zeros((n, 4, 3, 7)) if (not cam and not self.split) else np.zeros((n, self.group_row_size(g)))
+                    o["J"] = np.zeros((n, 4, nres, 7)) if (not cam and not self.split) else np.zeros((n, self.group_row_size(g)))
             if cam:
                 o["i0_b"] = np.full(n, -1, np.int32)
             if self.split:

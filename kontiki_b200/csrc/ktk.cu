@@ -275,6 +275,7 @@ struct CamArgs {
   const int* perm;
   const int* io; const double* uo;     // first knot / interpolation amount of the observation evaluation, located once at upload time
   int n; uint32_t flags;
+  int ahead;                           // k_static_rs: tiles resident on the chip (0 = no input prefetch)
   double* r; double* J; int* i0r; int* i0o; int* err;
 };
 struct CamIn { double u, v, uo, w, huber; int io, ridx, perm; };
@@ -377,6 +378,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_local(c
 // ktk_get_row_order gives the insertion index): the warp's 32 rows are one contiguous 29-KB block and lane 0 issues a single
 // bulk store for the tile.
 constexpr int kCamDevStride = 114, kRefInRowDev = 22;      // record at 22..113: block k read at 30 + 21 k, written at 14 k
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const CamArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -386,6 +388,20 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const int i = tile * 32 + lane;
+  // A one-shot CTA meets its row inputs cold (one exposed DRAM round trip, 10 % of the stall samples): pull the inputs of the tile
+  // `ahead` tiles further on -- about what is resident on the chip, i.e. a CTA that starts when this one ends -- into L2 now.
+  if (a.ahead > 0) {
+    const long long i2 = 32ll * ((long long)tile + a.ahead);
+    if (i2 + 32 <= a.n) {
+      if (lane < 4) prefetch_l2(a.obs_uv + 2 * i2 + 16 * lane);       // 512 B of (u, v)
+      else if (lane < 6) prefetch_l2(a.uo + i2 + 16 * (lane - 4));    // 256 B each below
+      else if (lane < 8) prefetch_l2(a.w + i2 + 16 * (lane - 6));
+      else if (lane < 10) prefetch_l2(a.huber + i2 + 16 * (lane - 8));
+      else if (lane == 10) prefetch_l2(a.io + i2);                     // 128 B each
+      else if (lane == 11) prefetch_l2(a.ref_idx + i2);
+      else if (lane == 12) prefetch_l2(a.perm + i2);
+    }
+  }
   const CamIn cur = cam_load(a, i);
   const double ouv[2] = {cur.u, cur.v};
   warp_gather_records<kRefStride, kCamDevStride, kRefInRowDev>(wbase, a.recs, cur.ridx, lane);
@@ -423,115 +439,6 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
       bulk_store_wait_read();
     }
   } else if (cur.perm >= 0) {                            // caller order: one 912-B bulk store per row, to the row's insertion index
-    bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
-    bulk_store_wait_read();
-  }
-}
-
-// The static-RS kernel with FOUR lanes per row (spline_math.cuh "static-RS row split over FOUR lanes"): a warp is a tile of 8 rows, lane
-// 4 q + j works on row q; j = 1..3 owns level j of the cumulative product (exp part, Jr6, contraction with both sides of pair record j),
-// j = 0 owns knot i0; every lane produces one reference-window block.  The dependent chain per thread is ~3.5x shorter than one thread
-// per row and the live state fits in fewer registers, so more warps are resident.  Shared memory per warp: 8 contiguous 114-double rows
-// (the landmark record lands at offset 22 of its row, is read into registers, and the row is rebuilt over it) + 36 doubles per row of
-// (E_j, a_j) exchange.  Rows leave exactly like k_static_rs: one TMA bulk store per row (caller order) or per tile (device order).
-#ifndef KTK_CAM_QUAD_DEFAULT
-#define KTK_CAM_QUAD_DEFAULT 0
-#endif
-#ifndef KTK_QUAD_MINB
-#define KTK_QUAD_MINB 12
-#endif
-#ifndef KTK_QUAD_WARPS
-#define KTK_QUAD_WARPS 1
-#endif
-constexpr int kQuadRows = 8, kQuadThreads = 32 * KTK_QUAD_WARPS;
-constexpr int kQuadWarpSmem = kQuadRows * kCamRow + kQuadRows * 3 * kQuadEx;      // doubles per warp
-__global__ void __launch_bounds__(kQuadThreads, KTK_QUAD_MINB) k_static_rs_quad(const CamArgs a) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31, j = lane & 3, q = lane >> 2;
-  double* wbase = smem + (size_t)(threadIdx.x >> 5) * kQuadWarpSmem;
-  double* row = wbase + q * kCamRow;
-  double* ex = wbase + kQuadRows * kCamRow + q * 3 * kQuadEx;
-  const int tile = warp_tile();
-  if (tile * kQuadRows >= a.n) return;
-  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
-  const CamIn cur = cam_load(a, tile * kQuadRows + q);
-  const double ouv[2] = {cur.u, cur.v};
-  // gather the tile's 8 landmark records (46 16-byte chunks each) into the row buffers, in flight during the forward chain
-  {
-    constexpr int kChunks = kRefStride / 2;
-#pragma unroll
-    for (int rr = 0; rr < kQuadRows; ++rr) {
-      const int ri = __shfl_sync(0xffffffffu, cur.ridx, 4 * rr);
-      if (ri < 0) continue;
-      const double2* src = reinterpret_cast<const double2*>(a.recs + (size_t)ri * kRefStride);
-      double2* dst = reinterpret_cast<double2*>(wbase + rr * kCamRow + kRefInRowDev);
-      cp_async16(dst + lane, src + lane);
-      if (lane < kChunks - 32) cp_async16(dst + 32 + lane, src + 32 + lane);
-    }
-  }
-  const bool live = cur.perm >= 0 && cur.ridx >= 0 && cur.io >= 0;
-  const int jj = j < 1 ? 1 : j;
-  const double* knot0 = a.knots + (size_t)(live ? cur.io : 0) * kKnotStride;
-  const double* pj = a.pairs + (size_t)((live ? cur.io : 0) + jj) * kPairStride;
-  ExpPart e;
-  double B = 0.0;
-  if (live) {
-    B = quad_basis(cumulative_basis(cur.uo, a.sp.dt), jj);
-    double scratch[kQuadEx];
-    quad_level_exp(pj, B, e, j >= 1 ? ex + (j - 1) * kQuadEx : scratch);
-  }
-  __syncwarp();
-  Pose P; QuadTail qt; V3 a1;
-  if (live) quad_chain(knot0, ex, j, P, qt, a1);
-  cp_async_wait_all();
-  __syncwarp();
-  int st = live ? 0 : kStatusRange;
-  double r[2] = {0.0, 0.0}, jrho[2] = {0.0, 0.0}, out14[14];
-  int ir = -1;
-  ObsAdjoint adj;
-  if (st == 0) {
-    const double* rec = row + kRefInRowDev;
-    Mr<2> GX;
-    static_rs_project(a.cam, P, rec, ouv, cur.w, cur.huber, r, jrho, &ir, adj, GX);
-    if (ir < 0) st = kStatusRange;                 // the landmark record itself was out of range
-    double blk[21];
-#pragma unroll
-    for (int c = 0; c < 21; ++c) blk[c] = rec[kRefDOff + 21 * j + c];
-    static_rs_ref_block(GX, blk, out14);
-  }
-  __syncwarp();                                    // every lane has read what it needs of the record: the row is rebuilt over it
-  G6<2> g;
-  if (st == 0) {
-#pragma unroll
-    for (int c = 0; c < 14; ++c) row[14 * j + c] = out14[c];
-    if (j >= 1) { g = quad_level_adjoint(adj, qt, e, B); contract_pair_dyn<2>(row + kCamHalf + 14 * (j - 1), g, pj + kPairDOff, false); }
-    else { row[112] = jrho[0]; row[113] = jrho[1]; }
-  }
-  __syncwarp();
-  if (cur.perm >= 0) {
-    if (st == 0) {
-      if (j >= 1) contract_pair_dyn<2>(row + kCamHalf + 14 * j, g, pj + kPairDOff + kPairSide, j < 3);
-      else quad_direct(knot0, adj, qt, a1, row + kCamHalf);
-    } else {
-      for (int c = j; c < kCamRow; c += 4) row[c] = nan("");
-    }
-    if (j == 0) {
-      if (st != 0) { atomicMin(a.err, st); r[0] = r[1] = nan(""); ir = -1; }
-      const size_t dst = (size_t)cur.perm;
-      if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
-      if (a.i0r) a.i0r[dst] = ir;
-      if (a.i0o) a.i0o[dst] = st == 0 ? cur.io : -1;
-    }
-  }
-  fence_async_smem();
-  __syncwarp();
-  if (!wantJ) return;
-  if (a.flags & KTK_EVAL_DEVICE_ORDER) {
-    if (lane == 0) {
-      bulk_store(a.J + (size_t)tile * kQuadRows * kCamRow, wbase, (unsigned)(min(kQuadRows, a.n - tile * kQuadRows) * kCamRow * 8));
-      bulk_store_wait_read();
-    }
-  } else if (j == 0 && cur.perm >= 0) {
     bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
     bulk_store_wait_read();
   }
@@ -993,7 +900,7 @@ struct ktk_problem {
   int64_t launches = 0;
   bool profiling = false;
   bool graphs_enabled = true;
-  bool cam_quad = false;          // static-RS rows through k_static_rs_quad (four lanes per row) instead of k_static_rs
+  int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<uint64_t> graph_key;
   int64_t graph_launches = 0;
@@ -1204,8 +1111,12 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_static_rs_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
-  cudaFuncSetAttribute(k_static_rs_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (kQuadThreads / 32) * kQuadWarpSmem * 8);
-  { const char* v = getenv("KTK_CAM_QUAD"); p->cam_quad = v ? atoi(v) != 0 : KTK_CAM_QUAD_DEFAULT; }
+  {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
+      p->cam_resident_tiles = per_sm * (kCamThreads / 32) * prop.multiProcessorCount;
+    if (const char* v = getenv("KTK_CAM_AHEAD")) p->cam_resident_tiles = atoi(v);      // A/B switch (0 = off)
+  }
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_split, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamSplitWarpSmem * 8);
@@ -1482,7 +1393,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.sp = p->sp; a.cam = ra.cam;
       a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.recs = g.d_recs.p;
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
-      a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags;
+      a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->cam_resident_tiles;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
       if (g.kind == KTK_NEWTON_RS) {
         NewtonArgs na;
@@ -1491,10 +1402,6 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
-      }
-      else if (!(flags & KTK_EVAL_LOCAL) && p->cam_quad) {
-        const int rows_per_cta = kQuadRows * (kQuadThreads / 32);
-        k_static_rs_quad<<<(int)((g.n + rows_per_cta - 1) / rows_per_cta), kQuadThreads, (kQuadThreads / 32) * kQuadWarpSmem * 8, s>>>(a);
       }
       else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
       else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);

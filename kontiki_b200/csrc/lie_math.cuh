@@ -143,6 +143,24 @@ KB_HD M3 quat_to_rot(double x, double y, double z, double w) {
 // Each is an entire function of x; the closed forms cancel catastrophically for small phi, so a Taylor series is used
 // below a per-group threshold chosen so that BOTH branches are good to <1e-13 relative (series truncation below it,
 // cancellation above it): x < 1e-2 for sa/cb/cc (6 terms), x < 0.5 for c2/c3 (7 terms).
+// Taylor coefficients of the five functions below (x^0 .. x^5 of sa, cb, cc; x^0 .. x^6 of c2, c3).  On the device they live in the
+// constant bank so that the Horner DFMAs read them as c[bank][offset] operands: as literals every coefficient costs two UMOV / IMAD.MOV
+// issue slots (64-bit immediates do not exist), ~300 per camera row in a kernel that is bound by issue slots and dependent latency.
+#define KB_TAYLOR_COEFS                                                                                                        \
+  1.0, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0,                                               \
+  0.5, -1.0 / 24.0, 1.0 / 720.0, -1.0 / 40320.0, 1.0 / 3628800.0, -1.0 / 479001600.0,                                           \
+  1.0 / 6.0, -1.0 / 120.0, 1.0 / 5040.0, -1.0 / 362880.0, 1.0 / 39916800.0, -1.0 / 6227020800.0,                                \
+  1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0, 1.0 / 20922789888000.0,   \
+  1.0 / 120.0, -1.0 / 2520.0, 1.0 / 120960.0, -1.0 / 9979200.0, 1.0 / 1245404160.0, -1.0 / 217945728000.0, 1.0 / 50812489728000.0
+#if defined(__CUDACC__)
+__constant__ double kTaylorDev[32] = {KB_TAYLOR_COEFS};
+#endif
+static const double kTaylorHost[32] = {KB_TAYLOR_COEFS};
+#if defined(__CUDA_ARCH__)
+#define KB_TC(i) kTaylorDev[i]
+#else
+#define KB_TC(i) kTaylorHost[i]
+#endif
 struct AngleCoefs { double sa, cb, cc, c2, c3; };
 #define KB_SMALL_X 1.0e-2
 #define KB_SMALL_XQ 0.5
@@ -158,9 +176,9 @@ KB_HD AngleCoefs angle_coefs(double x, bool need_q) {
 #endif
   }
   if (x < KB_SMALL_X) {
-    c.sa = 1.0 + x * (-1.0 / 6.0 + x * (1.0 / 120.0 + x * (-1.0 / 5040.0 + x * (1.0 / 362880.0 + x * (-1.0 / 39916800.0)))));
-    c.cb = 0.5 + x * (-1.0 / 24.0 + x * (1.0 / 720.0 + x * (-1.0 / 40320.0 + x * (1.0 / 3628800.0 + x * (-1.0 / 479001600.0)))));
-    c.cc = 1.0 / 6.0 + x * (-1.0 / 120.0 + x * (1.0 / 5040.0 + x * (-1.0 / 362880.0 + x * (1.0 / 39916800.0 + x * (-1.0 / 6227020800.0)))));
+    c.sa = KB_TC(0) + x * (KB_TC(1) + x * (KB_TC(2) + x * (KB_TC(3) + x * (KB_TC(4) + x * KB_TC(5)))));
+    c.cb = KB_TC(6) + x * (KB_TC(7) + x * (KB_TC(8) + x * (KB_TC(9) + x * (KB_TC(10) + x * KB_TC(11)))));
+    c.cc = KB_TC(12) + x * (KB_TC(13) + x * (KB_TC(14) + x * (KB_TC(15) + x * (KB_TC(16) + x * KB_TC(17)))));
   } else {
     const double ix = 1.0 / x;
     c.sa = s / phi;
@@ -170,10 +188,8 @@ KB_HD AngleCoefs angle_coefs(double x, bool need_q) {
   c.c2 = 0.0; c.c3 = 0.0;
   if (need_q) {
     if (x < KB_SMALL_XQ) {
-      c.c2 = 1.0 / 24.0 + x * (-1.0 / 720.0 + x * (1.0 / 40320.0 + x * (-1.0 / 3628800.0 + x * (1.0 / 479001600.0 +
-             x * (-1.0 / 87178291200.0 + x * (1.0 / 20922789888000.0))))));
-      c.c3 = 1.0 / 120.0 + x * (-1.0 / 2520.0 + x * (1.0 / 120960.0 + x * (-1.0 / 9979200.0 + x * (1.0 / 1245404160.0 +
-             x * (-1.0 / 217945728000.0 + x * (1.0 / 50812489728000.0))))));
+      c.c2 = KB_TC(18) + x * (KB_TC(19) + x * (KB_TC(20) + x * (KB_TC(21) + x * (KB_TC(22) + x * (KB_TC(23) + x * KB_TC(24))))));
+      c.c3 = KB_TC(25) + x * (KB_TC(26) + x * (KB_TC(27) + x * (KB_TC(28) + x * (KB_TC(29) + x * (KB_TC(30) + x * KB_TC(31))))));
     } else {
       const double ix = 1.0 / x;
       c.c2 = (x + 2.0 * co - 2.0) * 0.5 * ix * ix;

@@ -859,87 +859,4 @@ KB_HD void static_rs_row_obs_half(const double* knots, const double* pairs, cons
   pose_backward<2>(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, adj.Gp, adj.GpR, adj.Gth, 1.0, Jobs);
 }
 
-// ---- static-RS row split over FOUR lanes (k_static_rs_quad) ----------------------------------------------------------------
-// One thread per row runs ~3600 dependent-ish fp64 instructions with 255 registers; the kernel is bound by that chain (profiles/README.md).
-// The observation side factors by LEVEL of the cumulative product P = P0 A1 A2 A3, A_j = exp(B_j w_j): lane j = 1..3 of a row's quad
-// owns level j (its exp part, its Jr6 and the contraction with the two sides of pair record j), lane 0 owns knot i0 itself; the
-// reference-window half is one knot block per lane.  What the lanes exchange is (E_j, a_j), 12 doubles per level, through shared memory;
-// projection and adjoints (a few hundred instructions) are recomputed by all four lanes.  The pieces below are the per-lane steps; the
-// kernel (and tests/host_check.cpp, which runs the four lanes one after the other) only orders them.
-constexpr int kQuadEx = 12;          // E (9, row-major) | a (3)
-struct QuadTail { M3 T; V3 c; };     // T_j = E_{j+1} .. E_3 and c_{j+1} of pose_backward: what level j sees of the levels after it
-KB_HD double quad_basis(const Basis& bo, int jj) { return jj == 1 ? bo.B[0] : (jj == 2 ? bo.B[1] : bo.B[2]); }
-// step 1, lane j (jj = max(j, 1)): the level's exp part; ex = this level's 12-double slot
-KB_HD void quad_level_exp(const double* pj, double B, ExpPart& e, double* ex) {
-  exp_part(pj, B, true, true, e);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) ex[i] = e.E.a[i];
-  ex[9] = e.a.x; ex[10] = e.a.y; ex[11] = e.a.z;
-}
-// step 2, every lane: the forward chain of pose_forward from the three exchanged levels, and this lane's tail
-KB_HD void quad_chain(const double* knot0, const double* ex /* [3][12], levels 1..3 */, int j, Pose& P, QuadTail& q, V3& a1) {
-  const M3 E1 = load_m3(ex), E2 = load_m3(ex + kQuadEx), E3 = load_m3(ex + 2 * kQuadEx);
-  a1 = v3(ex[9], ex[10], ex[11]);
-  const V3 a2 = v3(ex[kQuadEx + 9], ex[kQuadEx + 10], ex[kQuadEx + 11]), a3 = v3(ex[2 * kQuadEx + 9], ex[2 * kQuadEx + 10], ex[2 * kQuadEx + 11]);
-  const V3 c2 = a2 + E2 * a3; const M3 T1 = E2 * E3;
-  const V3 c1 = a1 + E1 * c2; const M3 T0 = E1 * T1;
-  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
-  P.R = R0 * T0;
-  P.p = v3(knot0[4], knot0[5], knot0[6]) + R0 * c1;
-  if (j == 3) { q.T = m3_identity(); q.c = v3(0, 0, 0); }
-  else if (j == 2) { q.T = E3; q.c = a3; }
-  else if (j == 1) { q.T = T1; q.c = c2; }
-  else { q.T = T0; q.c = c1; }
-}
-// step 3, lanes 1..3: the level's 2 x 6 adjoint (pose_backward with the tail (T, c)); level 3 sees T = I, c = 0, which is exact
-KB_HD G6<2> quad_level_adjoint(const ObsAdjoint& adj, const QuadTail& q, const ExpPart& e, double B) {
-  G6<2> t;
-  t.U = rmul_nt(adj.GpR, q.T); t.W = rsub(rmul_nt(adj.Gth, q.T), rmul_hat(t.U, q.c));
-  return mul_Jr6(t, e, B);
-}
-// contract_pair with the accumulate switch at run time (level 3 writes block 3, levels 1 and 2 add to blocks written by the level above)
-template <int N>
-KB_HD void contract_pair_dyn(double* J, const G6<N>& g, const double* D, bool acc) {
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    double s[N][4];
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) s[r][c] = 0.0;
-#pragma unroll
-    for (int m = 0; m < (h == 0 ? 6 : 3); ++m) {
-      const Dbl2* d2 = reinterpret_cast<const Dbl2*>(D + m * 8 + 4 * h);
-      const Dbl2 v0 = d2[0], v1 = d2[1];
-      const double d[4] = {v0.x, v0.y, v1.x, v1.y};
-#pragma unroll
-      for (int r = 0; r < N; ++r) {
-        const double gm = m < 3 ? g.U.a[3 * r + m] : g.W.a[3 * r + m - 3];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) s[r][c] += gm * d[c];
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < N; ++r)
-#pragma unroll
-      for (int c = 0; c < (h == 0 ? 4 : 3); ++c) {
-        const double v = 1.0 * s[r][c];
-        J[r * 7 + 4 * h + c] = acc ? J[r * 7 + 4 * h + c] + v : v;
-      }
-  }
-}
-// step 4, lane 0: knot i0 itself, added to block 0 after level 1 wrote its first side there (the tail of pose_backward)
-KB_HD void quad_direct(const double* knot0, const ObsAdjoint& adj, const QuadTail& q, V3 a1, double* J0) {
-  const Mr<2> GpR0 = rmul_nt(adj.GpR, q.T);
-  const Mr<2> Gth0 = rsub(rmul_nt(adj.Gth, q.T), rmul_hat(GpR0, q.c));
-  const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
-  const V3 dps = 2.0 * (R0 * a1 - a1);
-  double grad[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) grad[r] = dot(rrow(adj.Gp, r), dps);
-  add_q0_block<2>(J0, Gth0, grad, knot0, 1.0);
-#pragma unroll
-  for (int r = 0; r < 2; ++r) { J0[r * 7 + 4] += 1.0 * adj.Gp.a[3 * r]; J0[r * 7 + 5] += 1.0 * adj.Gp.a[3 * r + 1]; J0[r * 7 + 6] += 1.0 * adj.Gp.a[3 * r + 2]; }
-}
-
 }  // namespace kb

@@ -14,9 +14,9 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import _lib
-from .measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, PositionMeasurement,
+from .measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
                            StaticRsCameraMeasurement, _problem_for)
-from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
+from .trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory, evaluable
 
 
 class CallbackReturnType(enum.Enum):       # py_ceres.cc:61-66
@@ -147,7 +147,8 @@ class TrajectoryEstimator:
     """TrajectoryEstimator(trajectory) -- same surface as the reference; `device` selects the GPU."""
 
     def __init__(self, trajectory, device=0):
-        if not isinstance(trajectory, (UniformSE3SplineTrajectory, SplitTrajectory)):
+        # trajectory_estimator.h / py_trajectory_estimator.cc declare the estimator for all four trajectory classes
+        if not isinstance(trajectory, (UniformSE3SplineTrajectory, SplitTrajectory, UniformR3SplineTrajectory, UniformSO3SplineTrajectory)):
             raise TypeError(f"No TrajectoryEstimator declared for {type(trajectory)}")
         self._trajectory, self._device = trajectory, device
         self._measurements = []
@@ -155,12 +156,14 @@ class TrajectoryEstimator:
         self._problem = None
 
     trajectory = property(lambda self: self._trajectory)
+    # what the CUDA path evaluates: the trajectory itself, or a lone R3 / SO3 spline with its constant, locked companion (trajectories.evaluable)
+    _tr = property(lambda self: evaluable(self._trajectory))
 
     def add_measurement(self, m):
-        if not isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement, StaticRsCameraMeasurement, PositionMeasurement)):
+        if not isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement, StaticRsCameraMeasurement, PositionMeasurement, OrientationMeasurement)):
             raise TypeError(f"unsupported measurement type {type(m).__name__}")
         # AddToEstimator checks the time span when the measurement is added (trajectory_estimator.h:97-122)
-        tr = self._trajectory
+        tr = self._tr
         if isinstance(m, StaticRsCameraMeasurement):
             ref = m.observation.landmark.reference
             t1, t2 = sorted([ref.view.t0, m.observation.view.t0])
@@ -180,10 +183,10 @@ class TrajectoryEstimator:
     def _build(self):
         if self._problem is not None:
             return
-        p, _ = _problem_for(self._trajectory)
+        p, _ = _problem_for(self._tr)
         p.close()
         p = _lib.Problem(self._device)
-        tr = self._trajectory
+        tr = self._tr
         if isinstance(tr, UniformSE3SplineTrajectory):
             p.set_se3_spline(tr.dt, tr.t0, len(tr), tr.compat_zero_dB)
         else:
@@ -191,7 +194,7 @@ class TrajectoryEstimator:
         groups, self._landmarks, lm_index = {}, [], {}
         for i, m in enumerate(self._measurements):
             kind = type(m)
-            sensor = m.camera if issubclass(kind, StaticRsCameraMeasurement) else (_NO_SENSOR if kind is PositionMeasurement else m.imu)
+            sensor = m.camera if issubclass(kind, StaticRsCameraMeasurement) else (_NO_SENSOR if kind in (PositionMeasurement, OrientationMeasurement) else m.imu)
             groups.setdefault((kind, id(sensor)), (sensor, []))[1].append(i)
         self._groups = []
         for (kind, _), (sensor, rows) in groups.items():
@@ -211,6 +214,9 @@ class TrajectoryEstimator:
             elif kind is PositionMeasurement:
                 g = p.add_position([m.t for m in ms], np.array([m.p for m in ms]))
                 self._groups.append(dict(g=g, kind="pos", rows=rows, sensor=sensor, weight=np.ones(len(ms))))
+            elif kind is OrientationMeasurement:
+                g = p.add_orientation([m.t for m in ms], np.array([m._q_xyzw for m in ms]))
+                self._groups.append(dict(g=g, kind="ori", rows=rows, sensor=sensor, weight=np.ones(len(ms))))
             else:
                 fn = p.add_gyroscope if kind is GyroscopeMeasurement else p.add_accelerometer
                 g = fn(sensor._c_sensor(), [m.t for m in ms], np.array([m._x for m in ms]), [m.weight for m in ms])
@@ -219,7 +225,7 @@ class TrajectoryEstimator:
         self._problem = p
 
     def _point(self):
-        tr = self._trajectory
+        tr = self._tr
         knots = tr.control_points if isinstance(tr, UniformSE3SplineTrajectory) else (tr.R3_spline.control_points, tr.SO3_spline.control_points)
         rho = np.array([L.inverse_depth for L in self._landmarks]) if self._landmarks else None
         return knots, rho
@@ -263,7 +269,7 @@ class TrajectoryEstimator:
 
     # ---- local (tangent) sparse Jacobian ----------------------------------------------------------------------------------
     def _columns(self):
-        tr = self._trajectory
+        tr = self._tr
         if isinstance(tr, UniformSE3SplineTrajectory):
             blocks = [("se3", tr, 6)]
         else:
@@ -294,7 +300,7 @@ class TrajectoryEstimator:
     def _sparse_system(self, outs):
         """r (stacked) and J in local coordinates as scipy CSR, from the packed device rows."""
         layout, ncols = self._columns()
-        tr = self._trajectory
+        tr = self._tr
         rs, rows_i, cols_i, vals = [], [], [], []
         row0 = 0
 
@@ -338,6 +344,12 @@ class TrajectoryEstimator:
                 r_idx = (row0 + 2 * np.arange(n)[:, None] + np.arange(2)[None, :])[free]
                 rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(col[free], 2)); vals.append(J[free, nrow - 2:nrow].reshape(-1))
                 nres = 2
+            elif grp["kind"] == "ori":
+                nres = 1
+                if not split:
+                    add_blocks(o["J"].reshape(n, 4, 1, 7), o["i0"], 7, "se3", 1)
+                else:
+                    add_blocks(o["J"].reshape(n, 4, 1, 4), o["i0_c"], 4, "so3", 1)
             else:
                 nres = 3
                 if not split:
@@ -405,14 +417,14 @@ class TrajectoryEstimator:
                 sn.gyroscope_bias = sn.gyroscope_bias + delta[cols["gb"]:cols["gb"] + 3]
 
     def _snapshot(self):
-        tr = self._trajectory
+        tr = self._tr
         spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
         sens = [(sn, sn._q_ct.copy(), sn._p_ct.copy(), sn.time_offset, getattr(sn, "accelerometer_bias", None), getattr(sn, "gyroscope_bias", None))
                 for sn, _ in getattr(self, "_sensor_cols", {}).values()]
         return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks], sens
 
     def _restore(self, snap):
-        tr = self._trajectory
+        tr = self._tr
         spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
         for s, c in zip(spl, snap[0]):
             s.control_points[:] = c
@@ -454,11 +466,13 @@ class TrajectoryEstimator:
         s = Summary()
         self._build()
         layout, ncols = self._columns()
-        tr = self._trajectory
-        n_knot_params = (7 * len(tr)) if isinstance(tr, UniformSE3SplineTrajectory) else (3 * len(tr.R3_spline) + 4 * len(tr.SO3_spline))
-        n_sensors = sum(g["kind"] != "pos" for g in self._groups)        # one sensor per group (none for PositionMeasurement): q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
+        tr = self._tr
+        real = lambda spl: 0 if getattr(spl, "_companion", False) else len(spl)       # the companion of a lone spline has no parameter blocks
+        n_knot_params = (7 * len(tr)) if isinstance(tr, UniformSE3SplineTrajectory) else (3 * real(tr.R3_spline) + 4 * real(tr.SO3_spline))
+        n_sensors = sum(g["kind"] not in ("pos", "ori") for g in self._groups)        # one sensor per group (none for PositionMeasurement): q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
         s.num_parameters = n_knot_params + len(self._landmarks) + 8 * n_sensors
-        s.num_parameter_blocks = n_knot_params // (7 if isinstance(tr, UniformSE3SplineTrajectory) else 1) + len(self._landmarks) + 3 * n_sensors
+        n_knot_blocks = len(tr) if isinstance(tr, UniformSE3SplineTrajectory) else real(tr.R3_spline) + real(tr.SO3_spline)
+        s.num_parameter_blocks = n_knot_blocks + len(self._landmarks) + 3 * n_sensors
         s.num_parameters_reduced = ncols + self._ambient_free(layout)      # ambient sizes of the non-constant blocks
         s.num_effective_parameters_reduced = ncols
         s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)
@@ -559,7 +573,7 @@ class TrajectoryEstimator:
         t_start = time.perf_counter()
         s = Summary()
         self._build()
-        tr = self._trajectory
+        tr = self._tr
         split = isinstance(tr, SplitTrajectory)
         spl_a = tr.R3_spline if split else tr
         spl_b = tr.SO3_spline if split else None
@@ -575,11 +589,12 @@ class TrajectoryEstimator:
         ne.free = torch.from_numpy(free).to(ne.dev)
         n_free = int(free.sum())
         layout, ncols = self._columns()
-        s.num_parameters = ne.n_amb + 8 * sum(g["kind"] != "pos" for g in self._groups)
+        n_companion = sum(spl._width * len(spl) for spl in (spl_a, spl_b) if spl is not None and getattr(spl, "_companion", False))
+        s.num_parameters = ne.n_amb - n_companion + 8 * sum(g["kind"] not in ("pos", "ori") for g in self._groups)
         s.num_parameters_reduced = ncols + self._ambient_free(layout)
         s.num_effective_parameters_reduced = n_free
         s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)
-        s.num_residuals = s.num_residuals_reduced = sum(self._problem.group_size(g["g"]) * (2 if g["kind"] == "cam" else 3) for g in self._groups)
+        s.num_residuals = s.num_residuals_reduced = sum(self._problem.group_size(g["g"]) * {"cam": 2, "ori": 1}.get(g["kind"], 3) for g in self._groups)
 
         def load_point():
             if split:

@@ -36,7 +36,7 @@ class DeviceNormalEquations:
         self.outs, self._keep, self.u = [], [], []
         for g in range(problem.num_groups):
             n, cam = problem.group_size(g), problem.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
-            r = torch.zeros((n, 2 if cam else 3), dtype=torch.float64, device=self.dev)
+            r = torch.zeros((n, 2 if cam else (1 if problem.group_kind(g) == _lib.ORIENTATION else 3)), dtype=torch.float64, device=self.dev)
             J = torch.zeros((n, problem.group_row_size(g)), dtype=torch.float64, device=self.dev)
             idx = [torch.zeros(n, dtype=torch.int32, device=self.dev) for _ in range(4)]
             self._keep.append((r, J, idx))

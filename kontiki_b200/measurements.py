@@ -4,11 +4,12 @@ project evaluate ONE row through the CUDA library; the batched path is Trajector
 import numpy as np
 
 from . import _lib
-from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory
+from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory, evaluable
 
 
 def _problem_for(traj):
     """A ktk problem bound to `traj` and the knots argument for it."""
+    traj = evaluable(traj)
     p = _lib.Problem(0)
     if isinstance(traj, UniformSE3SplineTrajectory):
         traj._check()
@@ -78,6 +79,28 @@ class PositionMeasurement:
 
     def measure(self, trajectory):
         return -self._residual(trajectory, np.zeros(3))
+
+
+class OrientationMeasurement:
+    """OrientationMeasurement(t, q)  (measurements/orientation_measurement.h:17-31, py_orientation_measurement.cc): q = (w, x, y, z) as the
+    reference's Eigen::Quaterniond(qvec(0..3)) constructor reads it; error = q.angularDistance(orientation(t)), a scalar."""
+
+    def __init__(self, t, q):
+        self.t = float(t)
+        self.q = np.asarray(q, float).reshape(4).copy()
+
+    @property
+    def _q_xyzw(self):
+        return np.array([self.q[1], self.q[2], self.q[3], self.q[0]])
+
+    def error(self, trajectory):
+        prob, knots = _problem_for(trajectory)
+        prob.add_orientation([self.t], self._q_xyzw[None, :])
+        return float(prob.evaluate(knots, None, _lib.EVAL_RESIDUALS)[0]["r"][0, 0])
+
+    def measure(self, trajectory):
+        """trajectory.Orientation(t) as (w, x, y, z) (orientation_measurement.h:24-26)."""
+        return trajectory.orientation(self.t)
 
 
 class StaticRsCameraMeasurement:

@@ -281,3 +281,44 @@ class SplitTrajectory(_Trajectory):
         p = _lib.Problem(0)
         p.set_split_spline(r.dt, r.t0, len(r), s.dt, s.t0, len(s))
         return p.traj_evaluate((r.control_points, s.control_points), [float(t)])
+
+
+class _LoneSplineView(SplitTrajectory):
+    """How a lone UniformR3SplineTrajectory / UniformSO3SplineTrajectory is evaluated: the reference's R3 view returns the identity
+    orientation and zero angular velocity (uniform_r3_spline_trajectory.h:61-65), its SO3 view zero position / velocity / acceleration
+    (uniform_so3_spline_trajectory.h:50-54) -- i.e. a split trajectory whose other half is a CONSTANT, LOCKED companion spline on the
+    same knot grid.  The companion has no parameter blocks in the reference; it is never optimised nor counted here."""
+
+    def __init__(self, spline):
+        self.lone = spline
+        self._sync()
+
+    def _sync(self):
+        sp = self.lone
+        n = max(len(sp), 4)
+        if isinstance(sp, UniformR3SplineTrajectory):
+            comp = UniformSO3SplineTrajectory(sp.dt, sp.t0)
+            comp._cp = np.tile(np.array([0.0, 0.0, 0.0, 1.0]), (n, 1))
+            self.R3_spline, self.SO3_spline = sp, comp
+        else:
+            comp = UniformR3SplineTrajectory(sp.dt, sp.t0)
+            comp._cp = np.zeros((n, 3))
+            self.R3_spline, self.SO3_spline = comp, sp
+        comp._locked, comp._companion = True, True
+        self.companion = comp
+
+    def refreshed(self):
+        if len(self.companion) != max(len(self.lone), 4) or self.companion.dt != self.lone.dt or self.companion.t0 != self.lone.t0:
+            self._sync()
+        return self
+
+
+def evaluable(traj):
+    """The trajectory the CUDA path evaluates: SE3 and split trajectories as they are, a lone R3 / SO3 spline through _LoneSplineView."""
+    if isinstance(traj, (UniformR3SplineTrajectory, UniformSO3SplineTrajectory)):
+        v = getattr(traj, "_lone_view", None)
+        if v is None:
+            v = traj._lone_view = _LoneSplineView(traj)
+        return v.refreshed()
+    return traj
+

@@ -7,6 +7,7 @@ product a second, file-based target.  Inputs are the reference's own fixtures (p
 plus one seeded smooth trajectory.
 
     python tests/golden/make_golden.py          # rewrites oracle_v1.npz; commit the result
+    python tests/golden/make_golden.py v2       # rewrites oracle_v2.npz (OrientationMeasurement rows)
 """
 import os
 import sys
@@ -69,8 +70,43 @@ def build():
     return out
 
 
+def build_v2():
+    """oracle_v2.npz: OrientationMeasurement rows (added after v1 was frozen; v1 is not regenerated)."""
+    out = {}
+    rng = np.random.default_rng(20261018)
+
+    def rotated(q):
+        n = len(q)
+        ang = rng.uniform(0.05, 2.5, n)
+        ax = rng.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1)[:, None]
+        dq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1)
+        x1, y1, z1, w1 = q.T; x2, y2, z2, w2 = dq.T
+        qm = np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+                       w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2], axis=1)
+        qm[::2] *= -1.0
+        return qm, ang
+
+    for name, knots, dt, t0 in (("fix", fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0), ("smooth", syn.smooth_se3_knots(40, 0.1), 0.1, 0.0)):
+        n = 24
+        traj = kto.Traj(kto.SE3, dt, t0, knots)
+        t = np.sort(rng.uniform(t0 + 1e-6, t0 + (len(knots) - 3) * dt - 1e-6, n))
+        qm, ang = rotated(kto.traj_evaluate(traj, t, 0xff)["orientation"])
+        o = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm, jac_mode=2)
+        out[f"se3_{name}_knots"], out[f"se3_{name}_meta"] = np.asarray(knots, float), np.array([dt, t0])
+        out[f"se3_{name}_t"], out[f"se3_{name}_q"], out[f"se3_{name}_angle"] = t, qm, ang
+        out[f"se3_{name}_ori_r"], out[f"se3_{name}_ori_J"], out[f"se3_{name}_ori_i0"] = o["r"], o["Ja"][:, :4], o["i0_a"]
+    t = np.linspace(max(fx.R3_T0, fx.SO3_T0) + 1e-6, min(fx.R3_T0 + (len(fx.R3_KNOTS) - 3) * fx.R3_DT, fx.SO3_T0 + (len(fx.SO3_KNOTS) - 3) * fx.SO3_DT) - 1e-6, 16)
+    traj = kto.Traj(kto.SPLIT, fx.R3_DT, fx.R3_T0, fx.R3_KNOTS, fx.SO3_DT, fx.SO3_T0, fx.SO3_KNOTS)
+    qm, ang = rotated(kto.traj_evaluate(traj, t, 0xff)["orientation"])
+    o = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm, jac_mode=2)
+    out["split_t"], out["split_q"], out["split_angle"] = t, qm, ang
+    out["split_ori_r"], out["split_ori_Jb"], out["split_ori_i0a"], out["split_ori_i0b"] = o["r"], o["Jb"][:, :4], o["ids_a"][:, 0], o["i0_b"]
+    return out
+
+
 if __name__ == "__main__":
-    data = build()
-    path = os.path.join(HERE, "oracle_v1.npz")
+    which = sys.argv[1] if len(sys.argv) > 1 else "v1"
+    data = build_v2() if which == "v2" else build()
+    path = os.path.join(HERE, f"oracle_{which}.npz")
     np.savez_compressed(path, **data)
     print(path, f"{os.path.getsize(path) / 1024:.0f} KiB, {len(data)} arrays")

@@ -36,48 +36,6 @@ void hc_imu(int which, double t0, double dt, int n_knots, int compat, double tim
   }
 }
 
-// k_static_rs_quad on the host: the four lanes of a row's quad run one after the other, step by step, with the kernel's
-// synchronisation points between the steps (record at offset 22 of the 114-double row buffer, as in the kernel).
-static int g_quad = 0;
-void hc_set_quad(int on) { g_quad = on; }
-static int quad_row(const CameraConst& cam, const double* knots8, const double* pairs, const ObsForward& f, const double* rec_in, const double* obs_uv,
-                    double weight, double huber_c, double* r_out, double* row, int* i0_ref, int* i0_obs) {
-  if (f.status != 0) return f.status;
-  double rec[92];
-  for (int c = 0; c < 92; ++c) rec[c] = rec_in[c];           // rec_in aliases the row (kRefInRow == 0 in this harness)
-  const double* knot0 = knots8 + (size_t)f.io * kKnotStride;
-  double ex[36];
-  ExpPart e[4]; double B[4]; const double* pj[4];
-  for (int j = 0; j < 4; ++j) {                               // step 1
-    const int jj = j < 1 ? 1 : j;
-    pj[j] = pairs + (size_t)(f.io + jj) * kPairStride; B[j] = quad_basis(f.bo, jj);
-    double tmp[12];
-    quad_level_exp(pj[j], B[j], e[j], j >= 1 ? ex + (j - 1) * kQuadEx : tmp);
-  }
-  Pose P[4]; QuadTail q[4]; V3 a1[4];
-  for (int j = 0; j < 4; ++j) quad_chain(knot0, ex, j, P[j], q[j], a1[j]);      // step 2
-  ObsAdjoint adj[4]; Mr<2> GX[4]; double out14[4][14], r[4][2], jrho[4][2]; int ir[4];
-  for (int j = 0; j < 4; ++j) {                               // projection (redundant per lane) + this lane's reference block, in registers
-    static_rs_project(cam, P[j], rec, obs_uv, weight, huber_c, r[j], jrho[j], &ir[j], adj[j], GX[j]);
-    double blk[21];
-    for (int c = 0; c < 21; ++c) blk[c] = rec[kRefDOff + 21 * j + c];
-    static_rs_ref_block(GX[j], blk, out14[j]);
-  }
-  if (ir[0] < 0) return kStatusRange;
-  G6<2> g[4];
-  for (int j = 0; j < 4; ++j) {                               // after the first __syncwarp
-    for (int c = 0; c < 14; ++c) row[14 * j + c] = out14[j][c];
-    if (j >= 1) { g[j] = quad_level_adjoint(adj[j], q[j], e[j], B[j]); contract_pair_dyn<2>(row + 56 + 14 * (j - 1), g[j], pj[j] + kPairDOff, false); }
-    else { row[112] = jrho[0][0]; row[113] = jrho[0][1]; }
-  }
-  for (int j = 0; j < 4; ++j) {                               // after the second __syncwarp
-    if (j >= 1) contract_pair_dyn<2>(row + 56 + 14 * j, g[j], pj[j] + kPairDOff + kPairSide, j < 3);
-    else quad_direct(knot0, adj[0], q[0], a1[0], row + 56);
-  }
-  r_out[0] = r[0][0]; r_out[1] = r[0][1]; *i0_ref = ir[0]; *i0_obs = f.io;
-  return 0;
-}
-
 void hc_static_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
                   double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
                   const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
@@ -107,7 +65,6 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
     // K_obs: the observation row
     ObsForward f;
     static_rs_row_locate(sp, cam, obs_uv + 2 * i, obs_t0[i], ref_t0[i], f);
-    if (g_quad) { status[i] = quad_row(cam, knots8, pairs, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, i0_ref + i, i0_obs + i); continue; }
     static_rs_row_pose(knots8, pairs, f);
     ObsAdjoint adj;
     status[i] = static_rs_row_ref_half(cam, f, rec, obs_uv + 2 * i, w[i], huber_c ? huber_c[i] : 0.0, r + 2 * i, row, row + 112, i0_ref + i, i0_obs + i, adj);

@@ -102,11 +102,9 @@ def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
     return dict(r=r, J=J, i0_ref=ir, i0_obs=kb, W=W, iterations=it, status=st)
 
 
-def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None, quad=False):
-    """cam: oracle.kto.Camera-like (K, q_ct, p_ct, time_offset, max_time_offset, d_locked, readout, rows).
-    quad=True runs the observation side as k_static_rs_quad does: four lanes per row, step by step."""
+def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    """cam: oracle.kto.Camera-like (K, q_ct, p_ct, time_offset, max_time_offset, d_locked, readout, rows)."""
     _set_camera_model(cam)
-    lib().hc_set_quad(int(quad))
     k8, pairs = prepass(knots7)
     obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
     obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)

@@ -103,3 +103,54 @@ def test_cuda_path_matches_golden():
         Js = p.expand_static_rs(g, ids, o["J"], o["i0"], o["i0_b"])
         assert np.abs(o["r"] - G[tag + "_r"]).max() < parity.TOL * 1e3
         assert parity.rel_err(Js, G[tag + "_Ja"]) < parity.TOL and parity.rel_err(o["J"][:, -2:], G[tag + "_Jrho"]) < parity.TOL
+
+
+# ---- oracle_v2.npz: OrientationMeasurement rows (tests/golden/make_golden.py v2) ---------------------------------------------------------
+G2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_v2.npz"))
+
+
+def _split_traj():
+    import fixtures_ref as fx
+    return fx, kto.Traj(kto.SPLIT, fx.R3_DT, fx.R3_T0, fx.R3_KNOTS, fx.SO3_DT, fx.SO3_T0, fx.SO3_KNOTS)
+
+
+def test_oracle_reproduces_the_golden_orientation_vectors():
+    for name in ("fix", "smooth"):
+        dt, t0 = G2[f"se3_{name}_meta"]
+        o = kto.imu_residuals(kto.Traj(kto.SE3, dt, t0, G2[f"se3_{name}_knots"]), kto.Sensor(), 3, G2[f"se3_{name}_t"], G2[f"se3_{name}_q"], jac_mode=2)
+        assert _same(o["r"], G2[f"se3_{name}_ori_r"]) and _same(o["Ja"][:, :4], G2[f"se3_{name}_ori_J"]) and np.array_equal(o["i0_a"], G2[f"se3_{name}_ori_i0"])
+        assert np.abs(o["r"][:, 0] - G2[f"se3_{name}_angle"]).max() < 1e-9        # the residual IS the angle the vectors were rotated by
+    fx, traj = _split_traj()
+    o = kto.imu_residuals(traj, kto.Sensor(), 3, G2["split_t"], G2["split_q"], jac_mode=2)
+    assert _same(o["r"], G2["split_ori_r"]) and _same(o["Jb"][:, :4], G2["split_ori_Jb"]) and np.array_equal(o["i0_b"], G2["split_ori_i0b"])
+
+
+def test_host_math_matches_golden_orientation():
+    for name in ("fix", "smooth"):
+        dt, t0 = G2[f"se3_{name}_meta"]
+        h = hc.imu(3, G2[f"se3_{name}_knots"], dt, t0, G2[f"se3_{name}_t"], G2[f"se3_{name}_q"])
+        assert (h["i0"] == G2[f"se3_{name}_ori_i0"]).all()
+        assert np.abs(h["r"] - G2[f"se3_{name}_ori_r"]).max() < parity.TOL and parity.rel_err(h["J"], G2[f"se3_{name}_ori_J"]) < parity.TOL
+    fx, _ = _split_traj()
+    h = hc.imu_split(3, fx.R3_KNOTS, fx.R3_DT, fx.R3_T0, fx.SO3_KNOTS, fx.SO3_DT, fx.SO3_T0, G2["split_t"], G2["split_q"])
+    assert (h["i0_so3"] == G2["split_ori_i0b"]).all() and (h["i0_r3"] == G2["split_ori_i0a"]).all()
+    assert np.abs(h["r"] - G2["split_ori_r"]).max() < parity.TOL and parity.rel_err(h["J"].reshape(-1, 4, 1, 4), G2["split_ori_Jb"]) < parity.TOL
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_golden_orientation():
+    for name in ("fix", "smooth"):
+        dt, t0 = G2[f"se3_{name}_meta"]
+        p = _lib.Problem(0)
+        p.set_se3_spline(dt, t0, len(G2[f"se3_{name}_knots"]))
+        g = p.add_orientation(G2[f"se3_{name}_t"], G2[f"se3_{name}_q"])
+        o = p.evaluate(G2[f"se3_{name}_knots"])[g]
+        assert (o["i0"] == G2[f"se3_{name}_ori_i0"]).all()
+        assert np.abs(o["r"] - G2[f"se3_{name}_ori_r"]).max() < parity.TOL and parity.rel_err(o["J"].reshape(-1, 4, 1, 7), G2[f"se3_{name}_ori_J"]) < parity.TOL
+    fx, _ = _split_traj()
+    p = _lib.Problem(0)
+    p.set_split_spline(fx.R3_DT, fx.R3_T0, len(fx.R3_KNOTS), fx.SO3_DT, fx.SO3_T0, len(fx.SO3_KNOTS))
+    g = p.add_orientation(G2["split_t"], G2["split_q"])
+    o = p.evaluate((np.asarray(fx.R3_KNOTS, float), np.asarray(fx.SO3_KNOTS, float)))[g]
+    assert (o["i0_c"] == G2["split_ori_i0b"]).all() and (o["i0"] == G2["split_ori_i0a"]).all()
+    assert np.abs(o["r"] - G2["split_ori_r"]).max() < parity.TOL and parity.rel_err(o["J"].reshape(-1, 4, 1, 4), G2["split_ori_Jb"]) < parity.TOL

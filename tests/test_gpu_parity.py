@@ -550,3 +550,73 @@ def test_position_rows_match_oracle(split):
         p2.set_se3_spline(0.05, 0.0, 300)
         p2.add_position([tmax + 1.0], np.zeros((1, 3)))
         p2.evaluate(syn.smooth_se3_knots(300, 0.05))
+
+
+def _rotated_orientations(q_xyzw, rng):
+    """q * dq with dq a rotation by 0.05 .. 2.5 rad about a random axis; every second sign-flipped, every third rescaled."""
+    n = len(q_xyzw)
+    ang = rng.uniform(0.05, 2.5, n)
+    ax = rng.normal(size=(n, 3)); ax /= np.linalg.norm(ax, axis=1)[:, None]
+    dq = np.concatenate([ax * np.sin(ang / 2)[:, None], np.cos(ang / 2)[:, None]], axis=1)
+    x1, y1, z1, w1 = q_xyzw.T; x2, y2, z2, w2 = dq.T
+    qm = np.stack([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+                   w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2], axis=1)
+    qm[::2] *= -1.0
+    qm[::3] *= 1.7
+    return qm, ang
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("local", [False, True])
+def test_orientation_rows_match_oracle(split, local):
+    """OrientationMeasurement (measurements/orientation_measurement.h:27-31, :57-79) through the C ABI: ONE residual per row (Eigen's
+    angularDistance), rows [4][1][7] on SE3 and [4 SO3 knots][1][4] on a split trajectory; ragged tile; tangent rows = ambient rows x Plus."""
+    rng = np.random.default_rng(21)
+    n = 700 + 13
+    p = _lib.Problem(0)
+    if not split:
+        knots = syn.smooth_se3_knots(300, 0.05)
+        traj = kto.Traj(kto.SE3, 0.05, 0.0, knots)
+        p.set_se3_spline(0.05, 0.0, len(knots))
+        tmax = 0.05 * (len(knots) - 3)
+    else:
+        k = syn.smooth_se3_knots(300, 0.05)
+        vecs, quats = k[:, 4:7].copy(), syn.smooth_se3_knots(380, 0.04)[:, :4].copy()
+        traj = kto.Traj(kto.SPLIT, 0.05, 0.0, vecs, 0.04, 0.01, quats)
+        p.set_split_spline(0.05, 0.0, len(vecs), 0.04, 0.01, len(quats))
+        knots = (vecs, quats)
+        tmax = min(0.05 * (len(vecs) - 3), 0.01 + 0.04 * (len(quats) - 3))
+    t = rng.uniform(0.02, tmax - 1e-6, n)
+    qm, ang = _rotated_orientations(kto.traj_evaluate(traj, t, 0xff)["orientation"], rng)
+    g = p.add_orientation(t, qm)
+    assert p.group_kind(g) == _lib.ORIENTATION and p.group_row_size(g) == (16 if split else 28)
+    o = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm, jac_mode=2)
+    assert np.abs(o["r"][:, 0] - ang).max() < 1e-9
+    sa = 4 if split else 7
+    Jo = (o["Jb"] if split else o["Ja"])[:, :4]                        # (n, 4, 1, sa)
+    if not local:
+        out = p.evaluate(knots)[g]
+        assert out["r"].shape == (n, 1) and np.abs(out["r"] - o["r"]).max() < parity.TOL
+        assert parity.rel_err(out["J"].reshape(n, 4, 1, sa), Jo) < parity.TOL
+    else:
+        out = p.evaluate(knots, None, _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_LOCAL)[g]
+        from kontiki_b200.estimator import _quat_plus_jacobian, _se3_plus_jacobian
+        i0 = o["i0_b"] if split else o["i0_a"]
+        P = _quat_plus_jacobian(quats) if split else _se3_plus_jacobian(knots)
+        want = np.stack([np.einsum("nra,nad->nrd", Jo[:, k], P[i0 + k]) for k in range(4)], axis=1)
+        assert np.abs(out["r"] - o["r"]).max() < parity.TOL
+        assert parity.rel_err(out["J"].reshape(n, 4, 1, -1), want) < parity.TOL
+    if split:
+        assert (out["i0_c"] == o["i0_b"]).all() and (out["i0"] == o["ids_a"][:, 0]).all() and not o["Ja"].any()
+        ids, nids = p.get_structure(g, cap=8)
+        assert (ids[:, :4] == o["ids_a"][:, :4]).all() and (nids == 4).all()
+    else:
+        assert (out["i0"] == o["i0_a"]).all()
+        ids, nids = p.get_structure(g, cap=8)
+        assert (ids[:, :4] == o["ids_a"][:, :4]).all() and (nids == 4).all()
+    with pytest.raises(ValueError):
+        p2 = _lib.Problem(0)
+        p2.set_se3_spline(0.05, 0.0, 300)
+        p2.add_orientation([tmax + 1.0], np.array([[0.0, 0.0, 0.0, 1.0]]))
+        p2.evaluate(syn.smooth_se3_knots(300, 0.05))
+

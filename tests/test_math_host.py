@@ -307,17 +307,3 @@ def test_orientation_rows_match_oracle():
     assert (h["status"] == 0).all() and (h["i0"] == o["i0_a"]).all()
     assert np.abs(h["r"] - o["r"]).max() < parity.TOL
     assert parity.rel_err(h["J"], o["Ja"][:, :4]) < parity.TOL
-
-
-@pytest.mark.parametrize("atan", [False, True])
-def test_static_rs_quad_lane_rows_equal_thread_per_row(atan):
-    """k_static_rs_quad's per-lane steps (four lanes per row: one level of the cumulative product each, one reference block each), run on
-    the host in the kernel's order, give the rows of the one-thread-per-row path: same operations, same order per output => bit for bit."""
-    dt = 0.02
-    knots, s, cam = _camera_case_model(dt, 5, atan, "static")
-    c = np.full(len(s["lm_idx"]), 5.0); c[::3] = 0.0
-    args = (knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
-    a, b = hc.static_rs(*args, huber_c=c), hc.static_rs(*args, huber_c=c, quad=True)
-    assert (a["status"] == 0).all() and (b["status"] == 0).all() and len(a["r"]) > 50
-    assert (a["i0_ref"] == b["i0_ref"]).all() and (a["i0_obs"] == b["i0_obs"]).all()
-    assert np.array_equal(a["r"], b["r"]) and np.array_equal(a["J"], b["J"])

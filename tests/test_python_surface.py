@@ -6,7 +6,7 @@ import pytest
 import fixtures_ref as fx
 import kontiki_b200 as kontiki
 from kontiki_b200 import sfm
-from kontiki_b200.measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, PositionMeasurement,
+from kontiki_b200.measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
                                        StaticRsCameraMeasurement)
 from kontiki_b200.sensors import AtanCamera, BasicImu, PinholeCamera
 from kontiki_b200.trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory
@@ -449,3 +449,89 @@ def test_position_measurement_and_solve(make):
     assert max(np.abs(traj.position(t) - p).max() for t, p in zip(ts, truth)) < 1e-4
     with pytest.raises(ValueError):
         est.add_measurement(PositionMeasurement(traj.max_time + 1.0, np.zeros(3)))
+
+
+def _rotate_wxyz(q_wxyz, angle, axis=(1.0, 0.0, 0.0)):
+    """q * Exp(angle * axis), quaternions (w, x, y, z)."""
+    ax = np.asarray(axis, float) / np.linalg.norm(axis)
+    w1, x1, y1, z1 = q_wxyz
+    w2, (x2, y2, z2) = np.cos(angle / 2), np.sin(angle / 2) * ax
+    return np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                     w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2])
+
+
+def lone_so3_fixture():
+    traj = UniformSO3SplineTrajectory(fx.SO3_DT, fx.SO3_T0)
+    for q in fx.SO3_KNOTS:
+        traj.append_knot(fx.xyzw_to_wxyz(q))
+    return traj
+
+
+def lone_r3_fixture():
+    traj = UniformR3SplineTrajectory(fx.R3_DT, fx.R3_T0)
+    for cp in fx.R3_KNOTS:
+        traj.append_knot(cp)
+    return traj
+
+
+@pytest.mark.parametrize("make", [smooth_se3, split_fixture, lone_so3_fixture])
+def test_orientation_measurement_and_solve(make):
+    """OrientationMeasurement(t, q) with q = (w, x, y, z) (orientation_measurement.h:21-31): measure == trajectory.orientation, error ==
+    the angular distance; an estimator with OrientationMeasurements pulls perturbed rotations back (the reference registers the class for
+    every trajectory type, trajectory_estimator.h / py_trajectory_estimator.cc, but has no test of its own for it)."""
+    traj = make()
+    ts = np.linspace(traj.min_time + 1e-3, traj.max_time - 1e-3, 90)
+    truth = [traj.orientation(t) for t in ts]                         # (w, x, y, z)
+    m = OrientationMeasurement(ts[5], truth[5])
+    assert m.t == ts[5] and np.allclose(m.measure(traj), truth[5], atol=1e-12)
+    # rotate the measured orientation by 0.3 rad: the error is that angle, whatever the sign or the scale of q
+    for scale in (1.0, -1.0, 2.5):
+        assert abs(OrientationMeasurement(ts[5], scale * _rotate_wxyz(truth[5], 0.3)).error(traj) - 0.3) < 1e-12
+    # perturb the rotations, then fit them back
+    rng = np.random.default_rng(1)
+    spl = traj if isinstance(traj, (UniformSE3SplineTrajectory, UniformSO3SplineTrajectory)) else traj.SO3_spline
+    q = spl.control_points[:, :4] + rng.normal(0, 0.01, (len(spl), 4))
+    spl.control_points[:, :4] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    est = kontiki.TrajectoryEstimator(traj)
+    assert est.trajectory is traj
+    for t, qt in zip(ts, truth):
+        est.add_measurement(OrientationMeasurement(t, qt))
+    before = max(OrientationMeasurement(t, qt).error(traj) for t, qt in zip(ts[::9], truth[::9]))
+    s = est.solve(max_iterations=30, progress=False)
+    after = max(OrientationMeasurement(t, qt).error(traj) for t, qt in zip(ts[::9], truth[::9]))
+    assert s.final_cost < 1e-3 * s.initial_cost and after < 0.1 * before
+    assert s.num_residuals == len(ts)
+    with pytest.raises(ValueError):
+        est.add_measurement(OrientationMeasurement(traj.max_time + 1.0, np.array([1.0, 0.0, 0.0, 0.0])))
+
+
+def test_lone_spline_estimators():
+    """conftest.py:27-29 + test_estimator.py:12-15, 41-45: the estimator exists for every trajectory class.  A lone R3 spline evaluates the
+    identity orientation, a lone SO3 spline zero position (uniform_r3_spline_trajectory.h:61-65, uniform_so3_spline_trajectory.h:50-54):
+    measurements on them equal the same measurements on a split trajectory with a constant other half."""
+    from kontiki_b200.sensors import BasicImu
+    r3, so3, split = lone_r3_fixture(), lone_so3_fixture(), split_fixture()
+    assert kontiki.TrajectoryEstimator(r3).trajectory is r3 and kontiki.TrajectoryEstimator(so3).trajectory is so3
+    imu = BasicImu()
+    t = 0.5 * (split.min_time + split.max_time)
+    # gyroscope on the lone SO3 spline == gyroscope on the split trajectory (only the SO3 half is evaluated)
+    g = GyroscopeMeasurement(imu, t, np.array([0.1, -0.2, 0.3]))
+    assert np.allclose(g.error(so3), g.error(split), atol=1e-13) and np.allclose(g.measure(so3), g.measure(split), atol=1e-13)
+    # accelerometer on the lone R3 spline: identity orientation => a_world + g
+    a = AccelerometerMeasurement(imu, t, np.zeros(3))
+    assert np.allclose(a.measure(r3), r3.acceleration(t) + np.array([0.0, 0.0, -9.80665]), atol=1e-12)
+    # position fit on the lone R3 spline
+    ts = np.linspace(r3.min_time + 1e-3, r3.max_time - 1e-3, 60)
+    truth = [r3.position(x) for x in ts]
+    r3.control_points[:] += np.random.default_rng(3).normal(0, 0.05, r3.control_points.shape)
+    est = kontiki.TrajectoryEstimator(r3)
+    for x, p in zip(ts, truth):
+        est.add_measurement(PositionMeasurement(x, p))
+    s = est.solve(max_iterations=20, progress=False)
+    assert s.final_cost < 1e-6 * s.initial_cost and s.num_parameters == 3 * len(r3) and s.num_parameters_reduced == 3 * len(r3)
+    assert max(np.abs(r3.position(x) - p).max() for x, p in zip(ts, truth)) < 1e-4
+    # a locked lone spline has nothing to optimise (test_estimator.py:54-76)
+    r3.locked = True
+    est2 = kontiki.TrajectoryEstimator(r3)
+    est2.add_measurement(PositionMeasurement(ts[3], truth[3]))
+    assert est2.solve(progress=False).num_parameters_reduced == 0
