@@ -164,38 +164,41 @@ static const double kTaylorHost[32] = {KB_TAYLOR_COEFS};
 struct AngleCoefs { double sa, cb, cc, c2, c3; };
 #define KB_SMALL_X 1.0e-2
 #define KB_SMALL_XQ 0.5
+// Large-angle branch (closed forms), out of line on the device: spline increments B_j omega_j are small, so the Taylor branch is the
+// hot one and is kept straight-line; inlining sincos and three divisions into every exp_part costs branch-merge moves and code size.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void angle_coefs_large(double x, bool need_q, AngleCoefs& c) {
+  const double phi = sqrt(x);
+  double s, co;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &s, &co);
+#else
+  s = sin(phi); co = cos(phi);
+#endif
+  const double ix = 1.0 / x;
+  c.sa = s / phi;
+  c.cb = (1.0 - co) * ix;
+  c.cc = (phi - s) * ix / phi;
+  if (need_q && !(x < KB_SMALL_XQ)) {
+    c.c2 = (x + 2.0 * co - 2.0) * 0.5 * ix * ix;
+    c.c3 = (2.0 * phi - 3.0 * s + phi * co) * 0.5 * ix * ix / phi;
+  }
+}
 KB_HD AngleCoefs angle_coefs(double x, bool need_q) {
   AngleCoefs c;
-  double phi = 0.0, s = 0.0, co = 1.0;
-  if (x >= KB_SMALL_X) {
-    phi = sqrt(x);
-#if defined(__CUDA_ARCH__)
-    sincos(phi, &s, &co);
-#else
-    s = sin(phi); co = cos(phi);
-#endif
-  }
-  if (x < KB_SMALL_X) {
-    c.sa = KB_TC(0) + x * (KB_TC(1) + x * (KB_TC(2) + x * (KB_TC(3) + x * (KB_TC(4) + x * KB_TC(5)))));
-    c.cb = KB_TC(6) + x * (KB_TC(7) + x * (KB_TC(8) + x * (KB_TC(9) + x * (KB_TC(10) + x * KB_TC(11)))));
-    c.cc = KB_TC(12) + x * (KB_TC(13) + x * (KB_TC(14) + x * (KB_TC(15) + x * (KB_TC(16) + x * KB_TC(17)))));
-  } else {
-    const double ix = 1.0 / x;
-    c.sa = s / phi;
-    c.cb = (1.0 - co) * ix;
-    c.cc = (phi - s) * ix / phi;
-  }
+  c.sa = KB_TC(0) + x * (KB_TC(1) + x * (KB_TC(2) + x * (KB_TC(3) + x * (KB_TC(4) + x * KB_TC(5)))));
+  c.cb = KB_TC(6) + x * (KB_TC(7) + x * (KB_TC(8) + x * (KB_TC(9) + x * (KB_TC(10) + x * KB_TC(11)))));
+  c.cc = KB_TC(12) + x * (KB_TC(13) + x * (KB_TC(14) + x * (KB_TC(15) + x * (KB_TC(16) + x * KB_TC(17)))));
   c.c2 = 0.0; c.c3 = 0.0;
   if (need_q) {
-    if (x < KB_SMALL_XQ) {
-      c.c2 = KB_TC(18) + x * (KB_TC(19) + x * (KB_TC(20) + x * (KB_TC(21) + x * (KB_TC(22) + x * (KB_TC(23) + x * KB_TC(24))))));
-      c.c3 = KB_TC(25) + x * (KB_TC(26) + x * (KB_TC(27) + x * (KB_TC(28) + x * (KB_TC(29) + x * (KB_TC(30) + x * KB_TC(31))))));
-    } else {
-      const double ix = 1.0 / x;
-      c.c2 = (x + 2.0 * co - 2.0) * 0.5 * ix * ix;
-      c.c3 = (2.0 * phi - 3.0 * s + phi * co) * 0.5 * ix * ix / phi;
-    }
+    c.c2 = KB_TC(18) + x * (KB_TC(19) + x * (KB_TC(20) + x * (KB_TC(21) + x * (KB_TC(22) + x * (KB_TC(23) + x * KB_TC(24))))));
+    c.c3 = KB_TC(25) + x * (KB_TC(26) + x * (KB_TC(27) + x * (KB_TC(28) + x * (KB_TC(29) + x * (KB_TC(30) + x * KB_TC(31))))));
   }
+  if (!(x < KB_SMALL_X)) angle_coefs_large(x, need_q, c);
   return c; }
 
 // Q block of the SE(3) left Jacobian J_l([rho; phi]) = [[Jl(phi), Ql],[0, Jl(phi)]] (Barfoot 2017, eq. 7.86),
