@@ -484,14 +484,29 @@ KB_HD void pose_backward(const double* knot0, const double* p1, const double* p2
 
 // ceres::HuberLoss(a) + ceres::internal::Corrector (un-vendored Ceres 1.x): scale factors for one
 // residual block with squared norm s.  Ceres applies them to r and J after Evaluate.
+// Cold branches (rarely taken, heavy in libm calls) are kept OUT of the straight-line code of the row kernels: inlining them costs
+// instruction-cache footprint and branch-merge moves in kernels that are bound by issue slots (profiles/README.md, r1i).
+#if defined(__CUDACC__)
+#define KB_COLD __host__ __device__ __noinline__
+#else
+#define KB_COLD inline
+#endif
 struct HuberScale { double sqrt_rho1, residual_scaling, alpha_sq_norm, rho0; };
-KB_HD HuberScale huber_scale(double a, double s) {
-  HuberScale h; const double b = a * a; double rho1, rho2;
-  if (s > b) { const double rr = sqrt(s); h.rho0 = 2.0 * a * rr - b; rho1 = fmax(2.2250738585072014e-308, a / rr); rho2 = -rho1 / (2.0 * s); }
-  else { h.rho0 = s; rho1 = 1.0; rho2 = 0.0; }
+// The linear region (|r| > a) is out of line on the device (KB_COLD): two square roots and three divisions with their slow-path
+// subroutines do not belong in the straight-line code of every row; in the quadratic region rho' = 1, rho'' = 0 and every factor is
+// exactly 1 or 0.
+KB_COLD void huber_scale_linear_region(double a, double s, HuberScale& h) {
+  const double b = a * a;
+  const double rr = sqrt(s);
+  h.rho0 = 2.0 * a * rr - b;
+  const double rho1 = fmax(2.2250738585072014e-308, a / rr), rho2 = -rho1 / (2.0 * s);
   h.sqrt_rho1 = sqrt(rho1);
   if (s == 0.0 || rho2 <= 0.0) { h.residual_scaling = h.sqrt_rho1; h.alpha_sq_norm = 0.0; }
   else { const double Dd = 1.0 + 2.0 * s * rho2 / rho1; const double alpha = 1.0 - sqrt(Dd); h.residual_scaling = h.sqrt_rho1 / (1.0 - alpha); h.alpha_sq_norm = alpha / s; }
+}
+KB_HD HuberScale huber_scale(double a, double s) {
+  HuberScale h; h.rho0 = s; h.sqrt_rho1 = 1.0; h.residual_scaling = 1.0; h.alpha_sq_norm = 0.0;
+  if (s > a * a) huber_scale_linear_region(a, s, h);
   return h;
 }
 
@@ -519,21 +534,47 @@ KB_HD void camera_set_pose(CameraConst& c, const double* q_ct, const double* p_c
 
 // CameraView::Unproject: pinhole K^-1 [u v 1] (pinhole_camera.h:63-67); atan additionally undoes the distortion
 // L = phn.xy - wc, r = sqrt(|L|^2 + eps), f = tan(r gamma) / gamma, Y = [wc + f L / r, 1] (atan_camera.h:92-103).
+// The AtanCamera branches are KB_COLD with scalar arguments (a struct by reference would pin the camera constants to local memory).
+KB_COLD void camera_unproject_atan(double wc0, double wc1, double gamma, double px, double py, double* out) {
+  const double L0 = px - wc0, L1 = py - wc1;
+  const double r = sqrt((L0 * L0 + L1 * L1) + 1e-32);
+  const double f = tan(r * gamma) / gamma;
+  out[0] = wc0 + f * L0 / r; out[1] = wc1 + f * L1 / r;
+}
 KB_HD V3 camera_unproject(const CameraConst& cam, double u, double v) {
   const V3 ph = load_m3(cam.Kinv) * v3(u, v, 1.0);
   if (cam.model == 0) return ph;
-  const double L0 = ph.x - cam.wc[0], L1 = ph.y - cam.wc[1];
-  const double r = sqrt((L0 * L0 + L1 * L1) + 1e-32);
-  const double f = tan(r * cam.gamma) / cam.gamma;
-  return v3(cam.wc[0] + f * L0 / r, cam.wc[1] + f * L1 / r, 1.0);
+  double o[2];
+  camera_unproject_atan(cam.wc[0], cam.wc[1], cam.gamma, ph.x, ph.y, o);
+  return v3(o[0], o[1], 1.0);
 }
 // CameraView::Project (sensors/camera.h:59-63) and its 2 x 3 Jacobian d y / d X.
 //   pinhole (pinhole_camera.h:47-51): p = K X, y = p.xy / p.z
 //   atan (atan_camera.h:54-75): A = X.xy / (X.z + eps), L = A - wc, r = sqrt(|L|^2 + eps), f = atan(r gamma) / gamma,
 //     g = L / r, Y = [wc + f g, 1], y = (K Y).xy;   dY/dA = f' g g^T + (f / r)(I - g g^T), f' = 1 / (1 + gamma^2 r^2)
+// out: y0 y1 | J (2 x 3 row-major)
+KB_COLD void camera_project_jac_atan(double k0, double k1, double k2, double k3, double k4, double k5, double wc0, double wc1, double gamma,
+                                     double Xx, double Xy, double Xz, double* out) {
+  const double eps = 1e-32;
+  const double iz = 1.0 / (Xz + eps);
+  const double A0 = Xx * iz, A1 = Xy * iz;
+  const double L0 = A0 - wc0, L1 = A1 - wc1;
+  const double r = sqrt((L0 * L0 + L1 * L1) + eps), ir = 1.0 / r;
+  const double f = atan(r * gamma) / gamma;
+  const double g0 = L0 * ir, g1 = L1 * ir;
+  const double Y0 = wc0 + f * g0, Y1 = wc1 + f * g1;
+  out[0] = k0 * Y0 + k1 * Y1 + k2;
+  out[1] = k3 * Y0 + k4 * Y1 + k5;
+  const double fr = f * ir, dd = 1.0 / (1.0 + gamma * gamma * r * r) - fr;
+  const double m00 = fr + dd * g0 * g0, m01 = dd * g0 * g1, m11 = fr + dd * g1 * g1;
+  // dA/dX = iz [I2 | -A]
+  const double d0[3] = {iz * m00, iz * m01, -iz * (m00 * A0 + m01 * A1)};
+  const double d1[3] = {iz * m01, iz * m11, -iz * (m01 * A0 + m11 * A1)};
+  for (int c = 0; c < 3; ++c) { out[2 + c] = k0 * d0[c] + k1 * d1[c]; out[5 + c] = k3 * d0[c] + k4 * d1[c]; }
+}
 KB_HD void camera_project_jac(const CameraConst& cam, V3 X, double& y0, double& y1, Mr<2>& J) {
-  const M3 Km = load_m3(cam.K);
   if (cam.model == 0) {
+    const M3 Km = load_m3(cam.K);
     const V3 pr = Km * X;
     const double iz = 1.0 / pr.z;
     y0 = pr.x * iz; y1 = pr.y * iz;
@@ -541,23 +582,11 @@ KB_HD void camera_project_jac(const CameraConst& cam, V3 X, double& y0, double& 
     J.a[3] = iz * (Km.a[3] - y1 * Km.a[6]); J.a[4] = iz * (Km.a[4] - y1 * Km.a[7]); J.a[5] = iz * (Km.a[5] - y1 * Km.a[8]);
     return;
   }
-  const double eps = 1e-32;
-  const double iz = 1.0 / (X.z + eps);
-  const double A0 = X.x * iz, A1 = X.y * iz;
-  const double L0 = A0 - cam.wc[0], L1 = A1 - cam.wc[1];
-  const double r = sqrt((L0 * L0 + L1 * L1) + eps), ir = 1.0 / r;
-  const double f = atan(r * cam.gamma) / cam.gamma;
-  const double g0 = L0 * ir, g1 = L1 * ir;
-  const double Y0 = cam.wc[0] + f * g0, Y1 = cam.wc[1] + f * g1;
-  y0 = Km.a[0] * Y0 + Km.a[1] * Y1 + Km.a[2];
-  y1 = Km.a[3] * Y0 + Km.a[4] * Y1 + Km.a[5];
-  const double fr = f * ir, dd = 1.0 / (1.0 + cam.gamma * cam.gamma * r * r) - fr;
-  const double m00 = fr + dd * g0 * g0, m01 = dd * g0 * g1, m11 = fr + dd * g1 * g1;
-  // dA/dX = iz [I2 | -A]
-  const double d0[3] = {iz * m00, iz * m01, -iz * (m00 * A0 + m01 * A1)};
-  const double d1[3] = {iz * m01, iz * m11, -iz * (m01 * A0 + m11 * A1)};
+  double o[8];
+  camera_project_jac_atan(cam.K[0], cam.K[1], cam.K[2], cam.K[3], cam.K[4], cam.K[5], cam.wc[0], cam.wc[1], cam.gamma, X.x, X.y, X.z, o);
+  y0 = o[0]; y1 = o[1];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) { J.a[c] = Km.a[0] * d0[c] + Km.a[1] * d1[c]; J.a[3 + c] = Km.a[3] * d0[c] + Km.a[4] * d1[c]; }
+  for (int c = 0; c < 6; ++c) J.a[c] = o[2 + c];
 }
 
 // Reference side, ONCE PER LANDMARK REFERENCE (hoisted: the reference re-evaluates it for every observation).
