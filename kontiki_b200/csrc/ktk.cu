@@ -44,6 +44,8 @@ inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NE
     if (e_ != cudaSuccess) return fail(KTK_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
   } while (0)
 
+// error paths fill a row with NaN: keep that loop rolled, it never runs in a healthy evaluation
+#define KTK_COLD_LOOP _Pragma("unroll 1")
 #ifndef KTK_THREADS
 #define KTK_THREADS 32
 #endif
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan("");
-      for (int c = 0; c < ROW; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < ROW; ++c) row[c] = nan("");
     }
     else if (local) localize_se3_blocks<NR>(row, 4, a.knots + (size_t)i0 * kKnotStride);
     const size_t dst = (size_t)cur.perm;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
     const int st = landmark_ref_row(a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.seg_start[i], a.seg_n[i], a.rho[a.lm[i]], row);
     if (st != 0) {
       atomicMin(a.err, st);
-      for (int c = 0; c < kRefStride; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < kRefStride; ++c) row[c] = nan("");
       row[7] = -1.0;
     }
   }
@@ -346,7 +348,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_local(c
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = jrho[0] = jrho[1] = nan(""); ir = io = -1;
-      for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < kCamHalf; ++c) row[c] = nan("");
     } else if (local) localize_se3_blocks<2>(row, 4, a.knots + (size_t)ir * kKnotStride);
     const size_t dst = (size_t)cur.perm;
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
     } else {
       atomicMin(a.err, st);
       r[0] = r[1] = nan(""); ir = io = -1;
-      for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
     }
     const size_t dst = (size_t)cur.perm;                 // == i in device order
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan(""); ia = ib = -1;
-      for (int c = 0; c < ROW; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < ROW; ++c) row[c] = nan("");
     } else if (local && WHICH != 2) localize_so3_blocks<NR>(row + (WHICH == 1 ? 36 : 0), 4, a.quats + (size_t)ib * kQuatStride);
     const size_t dst = (size_t)perm;
     if (a.r) {
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(kThreads) k_landmark_ref_split(const RefSplitA
                                           a.rho[a.lm[i]], row);
     if (st != 0) {
       atomicMin(a.err, st);
-      for (int c = 0; c < kRefSplitStride; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < kRefSplitStride; ++c) row[c] = nan("");
       row[7] = -1.0; row[8] = -1.0;
     }
   }
@@ -588,7 +590,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = jrho[0] = jrho[1] = nan(""); idx[0] = idx[1] = idx[2] = idx[3] = -1;
-      for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
+      KTK_COLD_LOOP for (int c = 0; c < kCamStage; ++c) row[c] = nan("");
     } else if (local) {      // [ref R3 24 | ref SO3 32 | obs R3 24 | obs SO3 32] -> [24 | 24 | 24 | 24]
       localize_so3_blocks<2>(row + 24, 4, a.quats + (size_t)idx[2] * kQuatStride);
       for (int c = 0; c < 24; ++c) row[48 + c] = row[56 + c];
