@@ -78,7 +78,7 @@ enum {
                              entry points below expect ambient rows. */
 };
 
-enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3, KTK_POSITION = 4, KTK_ORIENTATION = 5 };
+enum { KTK_GYROSCOPE = 0, KTK_ACCELEROMETER = 1, KTK_STATIC_RS = 2, KTK_NEWTON_RS = 3, KTK_POSITION = 4, KTK_ORIENTATION = 5, KTK_LIFTING_RS = 6 };
 enum { KTK_CAMERA_PINHOLE = 0, KTK_CAMERA_ATAN = 1 };
 
 /* sensors/sensors.h:91-109: relative pose + time offset; *_locked as the reference's lock flags (default locked). */
@@ -169,6 +169,16 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
  * camera parameters only (KTK_EUNSUPPORTED otherwise); KTK_EVAL_LOCAL / KTK_EVAL_SENSOR_JACOBIANS are not built for it. */
 int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
+/* LiftingRsCameraMeasurement::AddToEstimator (measurements/lifting_rscamera_measurement.h:151-229), same arrays as the static measurement.
+ * The observation is evaluated at the LIFTED time t0_obs + time_offset + vt * readout (:34), vt in [0, 1] a parameter block of the
+ * measurement (initially obs_uv.y / rows, :68); 3 residuals weight * [uv - y ; rows * (vt - vt_orig)] (:105-116) under the Huber loss.
+ * ktk_set_group_vt feeds the current row times (caller order) like ktk_set_group_sensor feeds sensor parameters.  Packed row
+ * [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles (ktk_group_row_size), W and i0_b as for the Newton
+ * rows (whole observation span); r is 3 per row.  UniformSE3SplineTrajectory with locked camera parameters only; no KTK_EVAL_LOCAL,
+ * no matrix-free products (KTK_EUNSUPPORTED). */
+int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
+                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
+int ktk_set_group_vt(ktk_problem* p, int32_t group, const double* vt);
 
 /* The sensor parameters are part of the evaluation point when they are unlocked: update them between evaluations.
  * (Changing the time offset re-sorts the group on the next evaluation.)  ktk_set_group_bias: accelerometer / gyroscope bias of

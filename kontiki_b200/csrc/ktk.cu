@@ -37,7 +37,8 @@ namespace {
 
 thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
-inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NEWTON_RS; }
+inline bool is_camera(int kind) { return kind == KTK_STATIC_RS || kind == KTK_NEWTON_RS || kind == KTK_LIFTING_RS; }
+inline bool is_span_camera(int kind) { return kind == KTK_NEWTON_RS || kind == KTK_LIFTING_RS; }      // rows carry the whole observation span
 #define KTK_CUDA(call)                                                                                   \
   do {                                                                                                   \
     cudaError_t e_ = (call);                                                                             \
@@ -852,6 +853,46 @@ __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a) {
   }
 }
 
+// LiftingRsCameraMeasurement rows (newton_math.cuh "LiftingRsCameraMeasurement"): the Newton kernel's shape -- one forward-mode direction
+// per thread on the hoisted structure -- without the iteration; vt[i] is the current value of row i's own parameter block.
+// Packed row [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)], 3 residuals.
+__global__ void __launch_bounds__(128) k_lifting_rs(const NewtonArgs a, const double* __restrict__ vt) {
+  const int ndir = 30 + 7 * a.W, row_len = 90 + 21 * a.W;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / ndir), dir = (int)(tid % ndir);
+  if (i >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  if (!wantJ && dir != 0) return;
+  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+  const double obs_t0 = a.obs_t0[i], v = vt[i];
+  const int ridx = a.ref_idx[i];
+  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+  int st = kStatusRange;
+  double r[3] = {nan(""), nan(""), nan("")}, j[3] = {nan(""), nan(""), nan("")};
+  int ir = -1;
+  if (ridx >= 0) {
+    const double* rec = a.recs + (size_t)ridx * kRefStride;
+    ir = (int)rec[7];
+    if (ir >= 0) {
+      LiftingRow o;
+      st = lifting_rs_direction(a.sp, a.cam, a.knots, a.pairs, rec, obs_t0, a.ref_t0[i], v, kbase, a.W, wantJ ? dir : -1, o);
+      if (st == 0) lifting_rs_finish(o, a.cam, ouv, v, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, j);
+    }
+  }
+  if (st != 0) { atomicMin(a.err, st); ir = -1; }
+  if (dir == 0) {
+    if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
+    if (a.i0r) a.i0r[dst] = ir;
+    if (a.i0o) a.i0o[dst] = st == 0 ? kbase : -1;
+  }
+  if (wantJ) {
+    const int off = lifting_dir_offset(dir, a.W), stride = dir < 28 + 7 * a.W ? 7 : 1;
+    double* Jr = a.J + dst * row_len;
+    Jr[off] = j[0]; Jr[off + stride] = j[1]; Jr[off + 2 * stride] = j[2];
+  }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
   T* p = nullptr; size_t n = 0;
@@ -873,6 +914,7 @@ struct Group {
   DevBuf<double> d_uo;
   DevBuf<double> d_ref_uv_sorted;
   double bias[3] = {0.0, 0.0, 0.0};
+  std::vector<double> vt; DevBuf<double> d_vt; bool vt_dirty = true;      // LiftingRs: current frame-normalised row times, caller order (ktk_set_group_vt)
   DevBuf<double> o_Js;
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
@@ -1058,13 +1100,14 @@ int newton_window(const ktk_problem* p, const Group& g) {
 int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
   if (g.kind == KTK_NEWTON_RS) return 58 + 14 * newton_window(p, g);
+  if (g.kind == KTK_LIFTING_RS) return 90 + 21 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
   if (p->traj == 1 && g.kind == KTK_POSITION) return kPosSplitRow;
   if (g.kind == KTK_ORIENTATION) return p->traj == 1 ? (local ? 12 : kOriSplitRow) : (local ? 24 : 28);
   if (p->traj == 1) return g.kind == KTK_GYROSCOPE ? (local ? 36 : kGyroSplitRow) : (local ? 72 : kAccelSplitRow);
   return local ? 72 : kImuRow;
 }
-int res_doubles(const Group& g) { return is_camera(g.kind) ? 2 : (g.kind == KTK_ORIENTATION ? 1 : 3); }
+int res_doubles(const Group& g) { return g.kind == KTK_LIFTING_RS ? 3 : (is_camera(g.kind) ? 2 : (g.kind == KTK_ORIENTATION ? 1 : 3)); }
 
 int add_imu(ktk_problem* p, int kind, const ktk_sensor* imu, int64_t n, const double* t, const double* y, const double* w) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
@@ -1139,7 +1182,7 @@ int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, in
   if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
   p->traj = 0; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; }   // the sort key depends on (t0, dt)
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->vt_dirty = true; }   // the sort key depends on (t0, dt)
   return KTK_OK;
 }
 
@@ -1149,7 +1192,7 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
   if (n_r3 < 4 || n_so3 < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->spl = SplitConst{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   p->traj = 1; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; }
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->vt_dirty = true; }
   return KTK_OK;
 }
 
@@ -1174,8 +1217,8 @@ static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int
   if (cam->rows <= 0 || cam->cols <= 0) return fail(KTK_EINVAL, "camera rows/cols must be positive");
   if (cam->model != KTK_CAMERA_PINHOLE && cam->model != KTK_CAMERA_ATAN) return fail(KTK_EINVAL, "unknown camera model");
   if (cam->model == KTK_CAMERA_ATAN && !(cam->gamma != 0.0)) return fail(KTK_EINVAL, "AtanCamera needs gamma != 0");
-  if (kind == KTK_NEWTON_RS && (!cam->base.q_locked || !cam->base.p_locked || !cam->base.time_offset_locked))
-    return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement with unlocked camera parameters is not built");
+  if (is_span_camera(kind) && (!cam->base.q_locked || !cam->base.p_locked || !cam->base.time_offset_locked))
+    return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements with unlocked camera parameters are not built");
   if (n < 0 || (n > 0 && (!obs_uv || !obs_t0 || !ref_uv || !ref_t0 || !lm_idx))) return fail(KTK_EINVAL, "bad measurement arrays");
   if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
   Group* g = new Group; g->kind = kind; g->n = n; g->cam = *cam; g->sensor = cam->base;
@@ -1185,6 +1228,7 @@ static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int
   for (int l : g->lm) { g->lm_max = std::max(g->lm_max, l); g->lm_min = std::min(g->lm_min, l); }
   if (w) g->w.assign(w, w + n); else g->w.assign((size_t)n, 1.0);
   if (huber_c) g->huber.assign(huber_c, huber_c + n); else g->huber.assign((size_t)n, 5.0);
+  if (kind == KTK_LIFTING_RS) { g->vt.resize((size_t)n); for (int64_t i = 0; i < n; ++i) g->vt[i] = obs_uv[2 * i + 1] / (double)cam->rows; }   // vt_orig, lifting_rscamera_measurement.h:68
   drop_graph(p);
   p->groups.push_back(g);
   return (int)p->groups.size() - 1;
@@ -1197,13 +1241,26 @@ int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
                       const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
   return add_camera_group(p, KTK_NEWTON_RS, cam, n, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, w, huber_c);
 }
+int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0, const double* ref_uv,
+                       const double* ref_t0, const int32_t* lm_idx, const double* w, const double* huber_c) {
+  return add_camera_group(p, KTK_LIFTING_RS, cam, n, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, w, huber_c);
+}
+int ktk_set_group_vt(ktk_problem* p, int32_t group, const double* vt) {
+  if (!p || group < 0 || group >= (int)p->groups.size() || !vt) return fail(KTK_EINVAL, "bad argument");
+  Group& g = *p->groups[group];
+  if (g.kind != KTK_LIFTING_RS) return fail(KTK_EINVAL, "only LiftingRs groups have a row-time parameter");
+  g.vt.assign(vt, vt + g.n);
+  g.vt_dirty = true;
+  drop_graph(p);
+  return KTK_OK;
+}
 
 int ktk_set_group_sensor(ktk_problem* p, int32_t group, const ktk_sensor* sensor) {
   if (!p || group < 0 || group >= (int)p->groups.size()) return fail(KTK_EINVAL, "bad group");
   int st = check_sensor(sensor); if (st) return st;
   Group& g = *p->groups[group];
   g.sensor = *sensor; g.cam.base = *sensor;
-  g.uploaded = false;            // the row order and the landmark-reference table depend on the time offset
+  g.uploaded = false; g.vt_dirty = true;            // the row order and the landmark-reference table depend on the time offset
   drop_graph(p);
   return KTK_OK;
 }
@@ -1233,7 +1290,7 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   cudaStream_t s = p->stream;
   const int blocks = (int)((g.n + 127) / 128);
   if (g.kind == KTK_POSITION || g.kind == KTK_ORIENTATION) return KTK_OK;           // no sensor
-  if (g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRsCameraMeasurement are not built");
+  if (is_span_camera(g.kind)) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRs / LiftingRs camera measurements are not built");
   if (g.kind == KTK_STATIC_RS) {
     if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
     if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
@@ -1319,8 +1376,15 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
   int st;
   for (auto g : p->groups) {
     if ((st = upload_group(p, *g))) return st;
-    if (g->kind == KTK_NEWTON_RS && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRsCameraMeasurement are not built");
-    if (g->kind == KTK_NEWTON_RS && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRsCameraMeasurement on a split trajectory is not built");
+    if (g->kind == KTK_LIFTING_RS && (g->vt_dirty || g->d_vt.n != (size_t)g->n)) {      // the row times are part of the evaluation point (device order); outside any capture
+      std::vector<double> sorted((size_t)g->n);
+      for (int64_t k = 0; k < g->n; ++k) sorted[k] = g->vt[(size_t)g->perm[k]];
+      if ((st = g->d_vt.upload(sorted, s))) return st;
+      KTK_CUDA(cudaStreamSynchronize(s));
+      g->vt_dirty = false;
+    }
+    if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs camera measurements are not built");
+    if (is_span_camera(g->kind) && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
@@ -1397,13 +1461,18 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->cam_resident_tiles;
       a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
-      if (g.kind == KTK_NEWTON_RS) {
+      if (is_span_camera(g.kind)) {
         NewtonArgs na;
         na.sp = a.sp; na.cam = a.cam; na.knots = a.knots; na.pairs = a.pairs; na.recs = a.recs;
         na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
         na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
+        if (g.kind == KTK_LIFTING_RS) {
+          const long long threads = (long long)g.n * (30 + 7 * na.W);
+          k_lifting_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_vt.p);
+        } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
+        }
       }
       else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
       else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
@@ -1575,6 +1644,7 @@ static int apply_products(ktk_problem* p, int mode, uint32_t flags, const ktk_gr
     a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d;
     for (int w = 0; w < a.w.nwin; ++w) if (!a.idx[a.w.slot[w]]) return fail(KTK_EINVAL, "the group's index arrays are missing");
     if (mode == 3 && g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "ktk_jtj_diagonal_local over NewtonRsCameraMeasurement rows is not built");
+    if (g.kind == KTK_LIFTING_RS) return fail(KTK_EUNSUPPORTED, "the matrix-free products do not cover LiftingRs rows (their row-time blocks are per measurement)");
     if (is_camera(g.kind)) {        // landmark index of every row, in the order the rows were written
       if (flags & KTK_EVAL_DEVICE_ORDER) {
         if (g.perm.size() != (size_t)g.n) return fail(KTK_EINVAL, "device-order rows need an evaluation first");
@@ -1703,24 +1773,25 @@ int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const
   const Group& g = *p->groups[group];
   if (!is_camera(g.kind)) return fail(KTK_EINVAL, "not a camera group");
   if (p->traj != 0) return fail(KTK_EINVAL, "ktk_expand_static_rs is for the SE3 layout");
-  const int W = g.kind == KTK_NEWTON_RS ? newton_window(p, g) : 4, row_len = 58 + 14 * W;
-  std::memset(out, 0, sizeof(double) * (size_t)g.n * cap * 14);
+  const int W = is_span_camera(g.kind) ? newton_window(p, g) : 4, row_len = row_doubles(p, g);
+  const int bs = 7 * res_doubles(g);      // doubles per knot block: 2 x 7, LiftingRs 3 x 7
+  std::memset(out, 0, sizeof(double) * (size_t)g.n * cap * bs);
   for (int64_t i = 0; i < g.n; ++i) {
     const int32_t* ids = knot_ids + (size_t)i * cap;
     for (int w = 0; w < 2; ++w) {
       const int base = w == 0 ? i0r[i] : i0o[i];
       for (int k = 0; k < (w == 0 ? 4 : W); ++k) {
-        const double* src = Jp + (size_t)i * row_len + w * 56 + k * 14;
+        const double* src = Jp + (size_t)i * row_len + w * 4 * bs + k * bs;
         int pos = -1;
         for (int c = 0; c < cap && ids[c] >= 0; ++c) if (ids[c] == base + k) { pos = c; break; }
         if (pos < 0) {       // a Newton-RS row carries the widest span of its group: blocks past this row's own span are zero
           bool zero = true;
-          for (int c = 0; c < 14; ++c) zero = zero && src[c] == 0.0;
-          if (zero && g.kind == KTK_NEWTON_RS) continue;
+          for (int c = 0; c < bs; ++c) zero = zero && src[c] == 0.0;
+          if (zero && is_span_camera(g.kind)) continue;
           return fail(KTK_EINVAL, "active knot not in the structural block list");
         }
-        double* dst = out + ((size_t)i * cap + pos) * 14;
-        for (int c = 0; c < 14; ++c) dst[c] += src[c];
+        double* dst = out + ((size_t)i * cap + pos) * bs;
+        for (int c = 0; c < bs; ++c) dst[c] += src[c];
       }
     }
   }

@@ -308,4 +308,100 @@ KB_HD int newton_rs_row(const SplineConst& sp, const CameraConst& cam, const dou
   return 0;
 }
 
+// ---- LiftingRsCameraMeasurement (measurements/lifting_rscamera_measurement.h:21-56, :98-118) ---------------------------------------------
+// The static projection with the observation evaluated at the LIFTED time t_obs = t0_obs + time_offset + vt * readout, vt in [0, 1] a
+// parameter block of the measurement; 3 residuals weight * [uv - y ; rows (vt - vt_orig)].  Same forward-mode machinery as the Newton
+// rows (one direction per thread, hoisted pair logs and landmark record), no iteration.  Directions:
+//   [0, 28) reference-window knots | [28, 28 + 7 W) observation-span knots | 28 + 7 W: vt | 29 + 7 W: rho | anything else: values only
+// Packed row (include/kontiki_b200.h): [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles.
+struct LiftingRow { double y[2], dy[2], dvt; };
+KB_HD int lifting_rs_direction(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                               double obs_t0, double ref_t0, double vt, int kbase, int W, int dir, LiftingRow& out) {
+  typedef D1 T;
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const int vt_dir = 28 + 7 * W, rho_dir = vt_dir + 1;
+  TV3<T> X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
+  T rho = T(rec[6]);
+  if (dir >= 0 && dir < 28) { const double* d = rec + kRefDOff + 21 * (dir / 7) + dir % 7; X.x.d = d[0]; X.y.d = d[7]; X.z.d = d[14]; }
+  else if (dir == rho_dir) { X.x.d = rec[3]; X.y.d = rec[4]; X.z.d = rec[5]; rho.d = 1.0; }
+  const int ok = (dir >= 28 && dir < vt_dir) ? kbase + (dir - 28) / 7 : -1;
+  const int oc = (dir - 28) % 7;
+  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
+  const TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  // t_obs = t0_obs + time_offset + vt * readout (:34), left to right, never FMA-contracted: it fixes the first knot index
+  const T t_obs = T(add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(vt, cam.readout)), dir == vt_dir ? cam.readout : 0.0);
+  out.dvt = dir == vt_dir ? 1.0 : 0.0;
+  int i0; double u0;
+  if (locate_in_segments(nseg, s0, s1, t_obs.a, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+  if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;
+  const T u = T(u0, t_obs.d / sp.dt);
+  const T u2 = u * u, u3 = u2 * u;
+  const double di = 1.0 / sp.dt;
+  T B[3], dB[3];
+  B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
+  B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
+  B[2] = u3 * T(1.0 / 6.0);
+  dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
+  dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
+  dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
+  T k0[7], om[3][6];
+  const double* kn = knots + (size_t)i0 * kKnotStride;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) k0[c] = T(kn[c], (ok == i0 && oc == c) ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int p = i0 + 1 + j;
+    const double* pr = pairs + (size_t)p * kPairStride;
+    const double* D = ok == p - 1 ? pr + kPairDOff : (ok == p ? pr + kPairDOff + kPairSide : nullptr);
+#pragma unroll
+    for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m], D ? D[m * 8 + oc] : 0.0);
+  }
+  const TEval<T> ev = se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
+  // :43-54
+  const TV3<T> X_obs = tqrot(tqconj(ev.q), X - rho * ev.p);
+  const TV3<T> X_cam = tqrot(qct, X_obs) + rho * pct;
+  T y[2], dy[2];
+  camera_project_t<T>(cam, X_cam, tv3<T>(T(0.0), T(0.0), T(0.0)), y, dy);
+  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+  return 0;
+}
+KB_HD int lifting_dir_offset(int dir, int W) {                 // residual row 0 of the direction's column; rows 1, 2 are +7 (+1 for vt / rho)
+  if (dir < 28) return 21 * (dir / 7) + dir % 7;
+  if (dir < 28 + 7 * W) { const int d = dir - 28; return 84 + 21 * (d / 7) + d % 7; }
+  return 84 + 21 * W + 3 * (dir - 28 - 7 * W);
+}
+// r = weight [uv - y ; rows (vt - vt_orig)] (:105-116), column j = weight [-dy ; rows dvt], then ceres::HuberLoss + Corrector (3 residuals)
+KB_HD void lifting_rs_finish(const LiftingRow& o, const CameraConst& cam, const double* obs_uv, double vt, double weight, double huber_c,
+                             double* r, double* j) {
+  const double rows = (double)cam.rows;
+  const double r0 = weight * (obs_uv[0] - o.y[0]), r1 = weight * (obs_uv[1] - o.y[1]), r2 = weight * (rows * (vt - obs_uv[1] / rows));
+  double j0 = -weight * o.dy[0], j1 = -weight * o.dy[1], j2 = weight * (rows * o.dvt), rs = 1.0;
+  if (huber_c > 0.0) {
+    const HuberScale h = huber_scale(huber_c, r0 * r0 + r1 * r1 + r2 * r2);
+    const double rj = r0 * j0 + r1 * j1 + r2 * j2;
+    j0 = h.sqrt_rho1 * (j0 - h.alpha_sq_norm * r0 * rj); j1 = h.sqrt_rho1 * (j1 - h.alpha_sq_norm * r1 * rj); j2 = h.sqrt_rho1 * (j2 - h.alpha_sq_norm * r2 * rj);
+    rs = h.residual_scaling;
+  }
+  r[0] = rs * r0; r[1] = rs * r1; r[2] = rs * r2; j[0] = j0; j[1] = j1; j[2] = j2;
+}
+// A whole row, direction after direction (host check; the kernel runs one direction per thread).
+KB_HD int lifting_rs_row(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                         const double* obs_uv, double obs_t0, double ref_t0, double vt, int kbase, int W, double weight, double huber_c,
+                         double* r, double* J) {
+  const int ndir = 30 + 7 * W;
+  for (int dir = 0; dir < ndir; ++dir) {
+    LiftingRow o;
+    const int st = lifting_rs_direction(sp, cam, knots, pairs, rec, obs_t0, ref_t0, vt, kbase, W, dir, o);
+    if (st != 0) return st;
+    double j[3];
+    lifting_rs_finish(o, cam, obs_uv, vt, weight, huber_c, r, j);
+    const int off = lifting_dir_offset(dir, W);
+    const int stride = dir < 28 + 7 * W ? 7 : 1;
+    J[off] = j[0]; J[off + stride] = j[1]; J[off + 2 * stride] = j[2];
+  }
+  return 0;
+}
+
 }  // namespace kb

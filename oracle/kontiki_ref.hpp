@@ -465,6 +465,29 @@ template <class T> void reproject_static(const CameraMeta& cm, const double ref_
   camera_project(cm, X_camera, zero, false, y_out, unused);   // CameraView::Project, sensors/camera.h:59-63
 }
 
+// measurements/lifting_rscamera_measurement.h:21-56: reproject_static with the observation evaluated at the LIFTED time
+// t_obs = t0_obs + time_offset + vt * readout, vt in [0, 1] a parameter of the measurement (frame-normalised row time).
+template <class T> void reproject_lifting(const CameraMeta& cm, const double ref_uv[2], double ref_t0, double obs_t0, T vt, T inverse_depth,
+                                          const TrajectoryView<T>& trajectory, const SensorView<T>& camera, T y_out[2]) {
+  T time_offset = camera.time_offset();
+  T row_delta = T(cm.readout) / T(double(cm.rows));
+  T t_ref = T(ref_t0) + time_offset + T(ref_uv[1]) * row_delta;
+  T t_obs = T(obs_t0) + time_offset + vt * T(cm.readout);
+  int flags = EvalPosition | EvalOrientation;
+  auto eval_ref = trajectory.Evaluate(t_ref, flags);
+  auto eval_obs = trajectory.Evaluate(t_obs, flags);
+  const Vec3<T> p_ct = camera.relative_position();
+  const Quat<T> q_ct = camera.relative_orientation();
+  T y[2] = {T(ref_uv[0]), T(ref_uv[1])};
+  Vec3<T> yh = camera_unproject(cm, y);
+  Vec3<T> X_ref = qrot(qconj(q_ct), yh - inverse_depth * p_ct);
+  Vec3<T> X = qrot(eval_ref->orientation, X_ref) + eval_ref->position * inverse_depth;
+  Vec3<T> X_obs = qrot(qconj(eval_obs->orientation), X - inverse_depth * eval_obs->position);
+  Vec3<T> X_camera = qrot(q_ct, X_obs) + p_ct * inverse_depth;
+  const Vec3<T> zero{T(0.0), T(0.0), T(0.0)}; T unused[2];
+  camera_project(cm, X_camera, zero, false, y_out, unused);
+}
+
 // math/quaternion_math.h:96-115
 template <class T> Quat<T> embed_vector(const Vec3<T>& v) { return {v.x, v.y, v.z, T(0.0)}; }
 template <class T> Quat<T> dq_from_angular_velocity(const Vec3<T>& w, const Quat<T>& q) {

@@ -241,6 +241,41 @@ def static_rs_residuals(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
                 status=st, eval_seconds=secs.value)
 
 
+def lifting_rs_residuals(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, vt=None, weight=None, jac_mode=2, nthreads=0, cap=None,
+                         raise_on_error=True):
+    """LiftingRsCameraMeasurement rows (lifting_rscamera_measurement.h): 3 residuals; vt = current frame-normalised row times (default: the
+    initial value obs_uv.y / rows, :68).  Returns dict(r (n,3), ids_a, Ja (n,cap,3,size), ids_b, Jb, Jvt (n,3), Jrho (n,3), i0_*...)."""
+    obs_uv, ref_uv = _f64(obs_uv).reshape(-1, 2), _f64(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f64(obs_t0), _f64(ref_t0), _f64(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    vt = obs_uv[:, 1] / float(cam.rows) if vt is None else _f64(vt)
+    vt = np.ascontiguousarray(vt, np.float64)
+    weight = np.ones(n) if weight is None else _f64(weight)
+    if cap is None:
+        span = cam.readout + 2e-3 + (0 if cam.d_locked else 2 * cam.max_time_offset)
+        cap = 2 * (4 + int(np.ceil(span / min(traj.dt_a, traj.dt_b))) + 1)
+    has_a, has_b = traj.kind != SO3, traj.kind in (SPLIT, SO3)
+    sa = traj.size_a
+    r = np.zeros((n, 3))
+    ids_a = np.full((n, cap), -1, np.int32) if has_a else None
+    Ja = np.zeros((n, cap, 3, sa)) if (has_a and jac_mode) else None
+    ids_b = np.full((n, cap), -1, np.int32) if has_b else None
+    Jb = np.zeros((n, cap, 3, 4)) if (has_b and jac_mode) else None
+    Jvt = np.zeros((n, 3)) if jac_mode else None
+    Jrho = np.zeros((n, 3)) if jac_mode else None
+    i0 = [np.zeros(n, np.int32) for _ in range(4)]
+    st = np.zeros(n, np.int32)
+    secs = C.c_double(0)
+    tc, sc, cm = traj.c(), cam.c(), cam.cmeta()
+    code = lib().kto_lifting_rs_residuals(C.byref(tc), C.byref(sc), C.byref(cm), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx),
+                                          _p(rho), _p(vt), _p(weight), int(jac_mode), int(nthreads), _p(r), cap, _p(ids_a), _p(Ja), cap,
+                                          _p(ids_b), _p(Jb), _p(Jvt), _p(Jrho), _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i0[3]), _p(st), C.byref(secs))
+    _check(code, raise_on_error)
+    return dict(r=r, ids_a=ids_a, Ja=Ja, ids_b=ids_b, Jb=Jb, Jvt=Jvt, Jrho=Jrho, vt=vt, i0_ref_a=i0[0], i0_obs_a=i0[1], i0_ref_b=i0[2], i0_obs_b=i0[3],
+                status=st, eval_seconds=secs.value)
+
+
 def huber_correct(a, r, J=None):
     """ceres::HuberLoss(a) + Corrector on one residual block; returns (rho, r_corrected, J_corrected)."""
     r = _f64(r).copy()

@@ -152,6 +152,26 @@ struct StaticRsFunctor {   // measurements/static_rscamera_measurement.h:108-127
   }
 };
 
+struct LiftingRsFunctor {   // measurements/lifting_rscamera_measurement.h:105-149: blocks [trajectory | camera (3) | vt | rho], 3 residuals
+  const Block* blk; CameraMeta cm; double weight; const double *ref_uv, *obs_uv; double ref_t0, obs_t0, vt_orig;
+  template <class T> bool operator()(T const* const* params, T* residual) const {
+    size_t offset = 0;
+    const TrajectoryView<T> trajectory(blk->meta, &params[offset]);
+    offset += blk->meta.NumParameters();
+    SensorView<T> camera; camera.params = &params[offset]; camera.has_bias = false;
+    offset += 3;
+    T vt = params[offset][0];
+    offset += 1;
+    T inverse_depth = params[offset][0];
+    T y_hat[2];
+    reproject_lifting<T>(cm, ref_uv, ref_t0, obs_t0, vt, inverse_depth, trajectory, camera, y_hat);
+    residual[0] = T(weight) * (T(obs_uv[0]) - y_hat[0]);                       // :105-110 projection error (pixels)
+    residual[1] = T(weight) * (T(obs_uv[1]) - y_hat[1]);
+    residual[2] = T(weight) * (T(double(cm.rows)) * (vt - T(vt_orig)));        // :112-113 timing error (pixels)
+    return true;
+  }
+};
+
 // SplineView::Evaluate segment choice + CalculateIndexAndInterpolationAmount -> GLOBAL index of the first
 // active knot (spline_base.h:188-202, 148-152); returns -1 if no segment holds t.
 int locate_knot(const SplineMeta& meta, const std::vector<int>& ids, double t) {
@@ -367,6 +387,77 @@ int kto_static_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto
     if (Js) { double* d = Js + size_t(i) * 16; std::memset(d, 0, 16 * sizeof(double));
       copy_block(jac[pb], d, 8); copy_block(jac[pb + 1], d + 8, 6); copy_block(jac[pb + 2], d + 14, 2); }
     if (Jrho) copy_block(jac[pb + 3], Jrho + 2 * size_t(i), 2);
+  }
+  auto toc = std::chrono::steady_clock::now();
+  if (eval_seconds) *eval_seconds = std::chrono::duration<double>(toc - tic).count();
+  int worst = KTO_OK;
+  for (int i = 0; i < n; ++i) { if (status) status[i] = st[i]; if (st[i] != KTO_OK) worst = st[i]; }
+  if (worst != KTO_OK && !first_err.empty()) g_last_error = first_err;
+  return worst;
+}
+
+// LiftingRsCameraMeasurement residual blocks (lifting_rscamera_measurement.h:151-229).  vt[n]: the current value of each measurement's
+// frame-normalised row time (its own parameter block, bounds [0, 1]); vt_orig = obs_uv.y / rows (:68).
+//   r[3n]; ids_a/Ja (3 x size_a blocks), ids_b/Jb (3 x 4), Jvt[3n], Jrho[3n]; i0_* as kto_static_rs_residuals (observation at the lifted time).
+int kto_lifting_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto_camera* cmeta, int n, const double* obs_uv,
+                             const double* obs_t0, const double* ref_uv, const double* ref_t0, const int* lm_idx, const double* rho,
+                             const double* vt, const double* weight, int jac_mode, int nthreads, double* r, int cap_a, int* ids_a,
+                             double* Ja, int cap_b, int* ids_b, double* Jb, double* Jvt, double* Jrho, int* i0_ref_a, int* i0_obs_a,
+                             int* i0_ref_b, int* i0_obs_b, int* status, double* eval_seconds) {
+  TrajData td(*tr);
+  CameraMeta cm; cm.readout = cmeta->readout; cm.rows = cmeta->rows; cm.cols = cmeta->cols;
+  for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) cm.K[a][c] = cmeta->K[3 * a + c];
+  cm.model = cmeta->model; cm.wc[0] = cmeta->wc[0]; cm.wc[1] = cmeta->wc[1]; cm.gamma = cmeta->gamma;
+  std::vector<Block> blocks(n);
+  std::vector<int> st(n, KTO_OK);
+  std::string first_err;
+  for (int i = 0; i < n; ++i) {
+    st[i] = guarded([&] {
+      double t1, t2;                                                                     // :162-177
+      if (ref_t0[i] <= obs_t0[i]) { t1 = ref_t0[i]; t2 = obs_t0[i]; } else { t1 = obs_t0[i]; t2 = ref_t0[i]; }
+      if (!cam->d_locked) { t1 -= cam->max_time_offset; t2 += cam->max_time_offset; }
+      const double margin = 1e-3;
+      add_trajectory(td, {{t1 - margin, t1 + cm.readout + margin}, {t2 - margin, t2 + cm.readout + margin}}, blocks[i]);
+      add_sensor(*cam, blocks[i]);
+      blocks[i].params.push_back(vt + i); blocks[i].sizes.push_back(1); blocks[i].constant.push_back(0);              // :200-205
+      blocks[i].params.push_back(rho + lm_idx[i]); blocks[i].sizes.push_back(1); blocks[i].constant.push_back(0);     // :209-215
+      if (int(blocks[i].ids_a.size()) > cap_a && ids_a) throw std::length_error("cap_a too small");
+      if (int(blocks[i].ids_b.size()) > cap_b && ids_b) throw std::length_error("cap_b too small");
+    });
+    if (st[i] != KTO_OK && first_err.empty()) first_err = g_last_error;
+  }
+  const int sa = td.has_a() ? td.size_a() : 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  auto tic = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int i = 0; i < n; ++i) {
+    if (st[i] != KTO_OK) continue;
+    const Block& b = blocks[i];
+    LiftingRsFunctor f{&b, cm, weight ? weight[i] : 1.0, ref_uv + 2 * i, obs_uv + 2 * i, ref_t0[i], obs_t0[i], obs_uv[2 * i + 1] / double(cm.rows)};
+    std::vector<std::vector<double>> jac;
+    st[i] = guarded([&] { evaluate_block(f, b, 3, jac_mode, r + 3 * i, jac); });
+    if (st[i] != KTO_OK) continue;
+    const double row_delta = cm.readout / double(cm.rows);
+    const double t_ref = ref_t0[i] + cam->time_offset + ref_uv[2 * i + 1] * row_delta;
+    const double t_obs = obs_t0[i] + cam->time_offset + vt[i] * cm.readout;
+    if (i0_ref_a) i0_ref_a[i] = td.has_a() ? locate_knot(b.meta.a, b.ids_a, t_ref) : -1;
+    if (i0_obs_a) i0_obs_a[i] = td.has_a() ? locate_knot(b.meta.a, b.ids_a, t_obs) : -1;
+    if (i0_ref_b) i0_ref_b[i] = td.has_b() ? locate_knot(b.meta.b, b.ids_b, t_ref) : -1;
+    if (i0_obs_b) i0_obs_b[i] = td.has_b() ? locate_knot(b.meta.b, b.ids_b, t_obs) : -1;
+    if (ids_a) for (int k = 0; k < cap_a; ++k) ids_a[size_t(i) * cap_a + k] = k < int(b.ids_a.size()) ? b.ids_a[k] : -1;
+    if (ids_b) for (int k = 0; k < cap_b; ++k) ids_b[size_t(i) * cap_b + k] = k < int(b.ids_b.size()) ? b.ids_b[k] : -1;
+    if (jac_mode == 0) continue;
+    size_t pb = 0;
+    if (Ja) { std::memset(Ja + size_t(i) * cap_a * 3 * sa, 0, sizeof(double) * cap_a * 3 * sa);
+      for (size_t k = 0; k < b.ids_a.size(); ++k) copy_block(jac[pb + k], Ja + (size_t(i) * cap_a + k) * 3 * sa, 3 * sa); }
+    pb += b.ids_a.size();
+    if (Jb) { std::memset(Jb + size_t(i) * cap_b * 12, 0, sizeof(double) * cap_b * 12);
+      for (size_t k = 0; k < b.ids_b.size(); ++k) copy_block(jac[pb + k], Jb + (size_t(i) * cap_b + k) * 12, 12); }
+    pb += b.ids_b.size();
+    if (Jvt) copy_block(jac[pb + 3], Jvt + 3 * size_t(i), 3);
+    if (Jrho) copy_block(jac[pb + 4], Jrho + 3 * size_t(i), 3);
   }
   auto toc = std::chrono::steady_clock::now();
   if (eval_seconds) *eval_seconds = std::chrono::duration<double>(toc - tic).count();

@@ -104,6 +104,37 @@ void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const doub
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }
 }
+// LiftingRsCameraMeasurement rows: what k_landmark_ref + k_lifting_rs do.  J: n x (90 + 21 W) packed [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3].
+void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
+                   double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
+                   const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
+                   const int* lm_idx, const double* rho, const double* vt, const double* w, const double* huber_c, int W, double* r, double* J,
+                   int* i0_ref, int* kbase_out, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  camera_set_pose(cam, q_ct, p_ct);
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  const int row_len = 90 + 21 * W;
+  for (int i = 0; i < n; ++i) {
+    i0_ref[i] = -1; kbase_out[i] = -1;
+    double rec[kRefStride];
+    Segment s0, s1;
+    const int nseg = static_rs_segments(sp, cam, ref_t0[i], obs_t0[i], s0, s1);
+    int ir; double ur;
+    const int which = nseg == 0 ? -1 : locate_in_segments(nseg, s0, s1, static_rs_time(cam, ref_t0[i], ref_uv[2 * i + 1]), sp.t0, sp.dt, ir, ur);
+    if (which < 0) { status[i] = kStatusRange; continue; }
+    const Segment& sr = which == 0 ? s0 : s1;
+    status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
+    if (status[i] != 0) continue;
+    const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
+    status[i] = lifting_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
+                               r + 3 * i, J + (size_t)row_len * i);
+    i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
+  }
+}
 int hc_newton_window(double t0, double dt, double readout, double obs_t0) {
   SplineConst sp{t0, dt, 1 << 30, 0};
   CameraConst cam; cam.readout = readout; cam.time_offset_locked = 1; cam.max_time_offset = 0.0;

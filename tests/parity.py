@@ -40,3 +40,22 @@ def scatter_cam(Jp, i0_ref, i0_obs, ids, W=4):
                 else:
                     assert not blk.any(), "non-zero block outside the residual's structural knots"
     return out, Jp[:, row - 2:row]
+
+
+def scatter_lifting(Jp, i0_ref, i0_obs, ids, W):
+    """Packed lifting row [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3] -> (structural blocks (n, cap, 3, 7), Jvt (n, 3), Jrho (n, 3))."""
+    n, cap = ids.shape
+    out = np.zeros((n, cap, 3, 7))
+    row = 90 + 21 * W
+    Jp = np.asarray(Jp).reshape(n, row)
+    for i in range(n):
+        pos = {int(k): j for j, k in enumerate(ids[i]) if k >= 0}
+        for base, off, nk in ((i0_ref[i], 0, 4), (i0_obs[i], 84, W)):
+            for k in range(nk):
+                blk = Jp[i, off + 21 * k: off + 21 * (k + 1)].reshape(3, 7)
+                if int(base) + k in pos:
+                    out[i, pos[int(base) + k]] += blk
+                else:
+                    assert not blk.any(), "non-zero block outside the residual's structural knots"
+    return out, Jp[:, row - 6:row - 3], Jp[:, row - 3:row]
+

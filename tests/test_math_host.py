@@ -307,3 +307,37 @@ def test_orientation_rows_match_oracle():
     assert (h["status"] == 0).all() and (h["i0"] == o["i0_a"]).all()
     assert np.abs(h["r"] - o["r"]).max() < parity.TOL
     assert parity.rel_err(h["J"], o["Ja"][:, :4]) < parity.TOL
+
+
+@pytest.mark.parametrize("atan,robust", [(False, False), (True, True)])
+def test_lifting_rs_rows_match_oracle(atan, robust):
+    """LiftingRsCameraMeasurement (lifting_rscamera_measurement.h:21-56, :98-149): 3 residuals, the observation evaluated at the lifted time
+    t0 + vt readout with vt its own parameter block; forward-mode columns on the hoisted structure vs the oracle's autodiff, at the initial
+    vt (= v / rows, where rows 0..1 are the static rows and row 2 is zero) and at displaced vt (all three rows alive)."""
+    dt = 0.05
+    knots, s, cam = _camera_case_model(dt, 11, atan, "static")
+    n = len(s["lm_idx"])
+    rng = np.random.default_rng(4)
+    args = (s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"])
+    for vt in (None, np.clip(s["obs_uv"][:, 1] / s["rows"] + rng.uniform(-0.2, 0.2, n), 0.0, 1.0)):
+        o = kto.lifting_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, *args, vt=vt, weight=s["weight"], jac_mode=2, cap=24)
+        c = np.full(n, 2.0) if robust else None
+        h = hc.lifting_rs(knots, dt, 0.0, cam, *args, vt=vt, w=s["weight"], huber_c=c)
+        assert (h["status"] == 0).all() and (h["i0_ref"] == o["i0_ref_a"]).all()
+        Js, Jvt, Jrho = parity.scatter_lifting(h["J"], h["i0_ref"], h["i0_obs"], o["ids_a"], h["W"])
+        if not robust:
+            assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+            assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jvt, o["Jvt"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+            if vt is None:
+                assert not h["r"][:, 2].any() and np.allclose(h["J"][:, -6:-3], o["Jvt"])
+        else:
+            n_out = 0
+            for i in range(n):
+                m = int((o["ids_a"][i] >= 0).sum())
+                Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jvt"][i].reshape(3, 1), o["Jrho"][i].reshape(3, 1)], axis=1)
+                _, r2, J2 = kto.huber_correct(2.0, o["r"][i], Jfull)
+                Jmine = np.concatenate([Js[i, k] for k in range(m)] + [Jvt[i].reshape(3, 1), Jrho[i].reshape(3, 1)], axis=1)
+                assert np.abs(h["r"][i] - r2).max() < parity.TOL * 1e3 and parity.rel_err(Jmine[None], J2[None]) < parity.TOL
+                n_out += float(np.dot(o["r"][i], o["r"][i])) > 4.0
+            assert n_out > 0
+
