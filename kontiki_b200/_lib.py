@@ -11,7 +11,7 @@ from . import build as _build
 
 OK, ERANGE, ERUNTIME, EINVAL, ECUDA, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 EVAL_RESIDUALS, EVAL_JACOBIANS, EVAL_ROBUST, EVAL_SENSOR_JACOBIANS, EVAL_LOCAL, EVAL_DEVICE_ORDER = 1, 2, 4, 8, 16, 32
-GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS, POSITION, ORIENTATION = 0, 1, 2, 3, 4, 5
+GYROSCOPE, ACCELEROMETER, STATIC_RS, NEWTON_RS, POSITION, ORIENTATION, LIFTING_RS = 0, 1, 2, 3, 4, 5, 6
 CAMERA_PINHOLE, CAMERA_ATAN = 0, 1
 IMU_ROW, CAM_ROW = 84, 114
 
@@ -37,7 +37,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation", "ktk_add_lifting_rs", "ktk_set_group_vt"]
 
 _lib = None
 
@@ -73,6 +73,8 @@ def lib():
         L.ktk_add_orientation.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.ktk_add_static_rs.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int64] + [C.c_void_p] * 7
         L.ktk_add_newton_rs.argtypes = L.ktk_add_static_rs.argtypes
+        L.ktk_add_lifting_rs.argtypes = L.ktk_add_static_rs.argtypes
+        L.ktk_set_group_vt.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.ktk_num_groups.argtypes = [C.c_void_p]
         L.ktk_group_size.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_group_kind.argtypes = [C.c_void_p, C.c_int32]
@@ -218,6 +220,16 @@ class Problem:
     def add_newton_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
         return self.add_static_rs(camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight, huber_c, _fn=lib().ktk_add_newton_rs)
 
+    def add_lifting_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None):
+        """LiftingRsCameraMeasurement rows (3 residuals; the row times start at obs_uv.y / rows, set_group_vt moves them)."""
+        return self.add_static_rs(camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight, huber_c, _fn=lib().ktk_add_lifting_rs)
+
+    def set_group_vt(self, g, vt):
+        vt = _f64(vt).reshape(-1)
+        if len(vt) != self.group_size(g):
+            raise ValueError("vt must have one entry per measurement of the group")
+        check(lib().ktk_set_group_vt(self._h, int(g), _ptr(vt)))
+
     def add_static_rs(self, camera, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, weight=None, huber_c=None, _fn=None):
         obs_uv, ref_uv = _f64(obs_uv).reshape(-1, 2), _f64(ref_uv).reshape(-1, 2)
         obs_t0, ref_t0 = _f64(obs_t0), _f64(ref_t0)
@@ -255,8 +267,8 @@ class Problem:
         """Host (numpy) output arrays for every group, in the C ABI's packed layouts."""
         outs = []
         for g in range(self.num_groups):
-            n, cam = self.group_size(g), self.group_kind(g) in (STATIC_RS, NEWTON_RS)
-            nres = 2 if cam else (1 if self.group_kind(g) == ORIENTATION else 3)
+            n, cam = self.group_size(g), self.group_kind(g) in (STATIC_RS, NEWTON_RS, LIFTING_RS)
+            nres = {STATIC_RS: 2, NEWTON_RS: 2, ORIENTATION: 1}.get(self.group_kind(g), 3)
             o = dict(r=np.zeros((n, nres)), i0=np.full(n, -1, np.int32))
             if jacobians:
                 if local:
@@ -398,7 +410,7 @@ class Problem:
 
     def expand_static_rs(self, g, ids, J, i0_ref, i0_obs):
         n, cap = ids.shape
-        out = np.zeros((n, cap, 2, 7))
+        out = np.zeros((n, cap, 3 if self.group_kind(g) == LIFTING_RS else 2, 7))
         J = _f64(J).reshape(n, self.group_row_size(g))
         check(lib().ktk_expand_static_rs(self._h, g, cap, _ptr(np.ascontiguousarray(ids, np.int32)), _ptr(J), _ptr(np.ascontiguousarray(i0_ref, np.int32)),
                                          _ptr(np.ascontiguousarray(i0_obs, np.int32)), _ptr(out)))

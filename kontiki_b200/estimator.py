@@ -14,7 +14,7 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 from . import _lib
-from .measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
+from .measurements import (AccelerometerMeasurement, GyroscopeMeasurement, LiftingRsCameraMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
                            StaticRsCameraMeasurement, _problem_for)
 from .trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory, evaluable
 
@@ -210,7 +210,8 @@ class TrajectoryEstimator:
                 g = getattr(p, kind._add)(sensor._c_camera(), np.array([m.observation.uv for m in ms]), [m.observation.view.t0 for m in ms],
                                     np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
                                     lm, [m.weight for m in ms], [m.huber_c for m in ms])
-                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor, newton=kind is NewtonRsCameraMeasurement))
+                self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor, newton=kind is NewtonRsCameraMeasurement,
+                                         lifting=kind is LiftingRsCameraMeasurement, ms=ms))
             elif kind is PositionMeasurement:
                 g = p.add_position([m.t for m in ms], np.array([m.p for m in ms]))
                 self._groups.append(dict(g=g, kind="pos", rows=rows, sensor=sensor, weight=np.ones(len(ms))))
@@ -250,6 +251,8 @@ class TrajectoryEstimator:
     def _push_sensors(self):
         """The sensor parameters are part of the evaluation point (ktk_set_group_sensor / ktk_set_group_bias)."""
         for grp in self._groups:
+            if grp.get("lifting"):                       # the row times are parameter blocks of the measurements (ktk_set_group_vt)
+                self._problem.set_group_vt(grp["g"], [m.vt for m in grp["ms"]])
             sn = grp["sensor"]
             if self._sensor_free(sn):
                 self._problem.set_group_sensor(grp["g"], sn._c_sensor())
@@ -283,6 +286,11 @@ class TrajectoryEstimator:
         self._lm_col = np.full(len(self._landmarks), -1, np.int64)
         self._lm_col[free_lm] = off + np.arange(free_lm.sum())
         off += int(free_lm.sum())
+        # LiftingRs row times: one column per measurement (lifting_rscamera_measurement.h:200-205)
+        for grp in getattr(self, "_groups", []):
+            if grp.get("lifting"):
+                grp["vt_col0"] = off
+                off += len(grp["ms"])
         # unlocked sensor parameter blocks, one set of columns per distinct sensor object
         width = {"q": 3, "p": 3, "d": 1, "ab": 3, "gb": 3}
         self._sensor_cols = {}
@@ -328,7 +336,18 @@ class TrajectoryEstimator:
         for grp in self._groups:
             o = outs[grp["g"]]
             n = len(o["r"])
-            if grp["kind"] == "cam":
+            if grp["kind"] == "cam" and grp.get("lifting"):
+                J = o["J"].reshape(n, -1)
+                nrow = J.shape[1]                                  # 90 + 21 W: [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3]
+                add_blocks(J[:, :84].reshape(n, 4, 3, 7), o["i0"], 7, "se3", 3)
+                add_blocks(J[:, 84:nrow - 6].reshape(n, -1, 3, 7), o["i0_b"], 7, "se3", 3)
+                r_idx = row0 + 3 * np.arange(n)[:, None] + np.arange(3)[None, :]
+                rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(grp["vt_col0"] + np.arange(n), 3)); vals.append(J[:, nrow - 6:nrow - 3].reshape(-1))
+                col = self._lm_col[grp["lm"]]
+                free = col >= 0
+                rows_i.append(r_idx[free].reshape(-1)); cols_i.append(np.repeat(col[free], 3)); vals.append(J[free, nrow - 3:nrow].reshape(-1))
+                nres = 3
+            elif grp["kind"] == "cam":
                 J = o["J"].reshape(n, -1)
                 nrow = J.shape[1]                                  # 114; Newton-RS 58 + 14 W
                 if not split:
@@ -404,6 +423,10 @@ class TrajectoryEstimator:
         for L, c in zip(self._landmarks, self._lm_col):
             if c >= 0:
                 L.inverse_depth = max(rho_lower, L.inverse_depth + delta[c])      # lower bound 0, static_rscamera_measurement.h:178-181
+        for grp in self._groups:
+            if grp.get("lifting"):                                                # bounds [0, 1], lifting_rscamera_measurement.h:202-204
+                for m, dv in zip(grp["ms"], delta[grp["vt_col0"]:grp["vt_col0"] + len(grp["ms"])]):
+                    m.vt = float(np.clip(m.vt + dv, 0.0, 1.0))
         for sn, cols in self._sensor_cols.values():
             if "q" in cols:
                 sn._q_ct = _quat_plus(sn._q_ct[None, :], delta[cols["q"]:cols["q"] + 3][None, :])[0]
@@ -421,7 +444,8 @@ class TrajectoryEstimator:
         spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
         sens = [(sn, sn._q_ct.copy(), sn._p_ct.copy(), sn.time_offset, getattr(sn, "accelerometer_bias", None), getattr(sn, "gyroscope_bias", None))
                 for sn, _ in getattr(self, "_sensor_cols", {}).values()]
-        return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks], sens
+        vts = [[m.vt for m in g["ms"]] for g in self._groups if g.get("lifting")]
+        return [s.control_points.copy() for s in spl], [L.inverse_depth for L in self._landmarks], sens, vts
 
     def _restore(self, snap):
         tr = self._tr
@@ -434,6 +458,9 @@ class TrajectoryEstimator:
             sn._q_ct, sn._p_ct, sn.time_offset = q.copy(), pp.copy(), d
             if ab is not None:
                 sn.accelerometer_bias, sn.gyroscope_bias = ab.copy(), gb.copy()
+        for g, vt in zip([g for g in self._groups if g.get("lifting")], snap[3]):
+            for m, v in zip(g["ms"], vt):
+                m.vt = v
 
     @staticmethod
     def _cost(outs, groups, hubers):
@@ -450,9 +477,9 @@ class TrajectoryEstimator:
         if auto:
             linear_solver = "device_pcg" if len(self._measurements) > 20000 else "host_cholesky"
         self._build()
-        if any(g.get("newton") for g in self._groups):
+        if any(g.get("newton") or g.get("lifting") for g in self._groups):
             if linear_solver == "device_pcg" and not auto:
-                raise NotImplementedError("NewtonRsCameraMeasurement rows are solved by the host_cholesky path only")
+                raise NotImplementedError("NewtonRs / LiftingRs camera rows are solved by the host_cholesky path only")
             linear_solver = "host_cholesky"
         if any(self._sensor_free(g["sensor"]) for g in self._groups):
             if linear_solver == "device_pcg":
@@ -470,9 +497,10 @@ class TrajectoryEstimator:
         real = lambda spl: 0 if getattr(spl, "_companion", False) else len(spl)       # the companion of a lone spline has no parameter blocks
         n_knot_params = (7 * len(tr)) if isinstance(tr, UniformSE3SplineTrajectory) else (3 * real(tr.R3_spline) + 4 * real(tr.SO3_spline))
         n_sensors = sum(g["kind"] not in ("pos", "ori") for g in self._groups)        # one sensor per group (none for PositionMeasurement): q_ct(4) p_ct(3) time_offset(1), constant (sensors.h:135-165)
-        s.num_parameters = n_knot_params + len(self._landmarks) + 8 * n_sensors
+        n_vt = sum(len(g["ms"]) for g in self._groups if g.get("lifting"))
+        s.num_parameters = n_knot_params + len(self._landmarks) + 8 * n_sensors + n_vt
         n_knot_blocks = len(tr) if isinstance(tr, UniformSE3SplineTrajectory) else real(tr.R3_spline) + real(tr.SO3_spline)
-        s.num_parameter_blocks = n_knot_blocks + len(self._landmarks) + 3 * n_sensors
+        s.num_parameter_blocks = n_knot_blocks + len(self._landmarks) + 3 * n_sensors + n_vt
         s.num_parameters_reduced = ncols + self._ambient_free(layout)      # ambient sizes of the non-constant blocks
         s.num_effective_parameters_reduced = ncols
         s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)

@@ -136,3 +136,28 @@ class NewtonRsCameraMeasurement(StaticRsCameraMeasurement):
     """NewtonRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (newton_rscamera_measurement.h:127-141): the row
     time of the projection is found by a 5-step Newton iteration instead of being read off the observed row."""
     _add = "add_newton_rs"
+
+
+class LiftingRsCameraMeasurement(StaticRsCameraMeasurement):
+    """LiftingRsCameraMeasurement(camera, observation[, huber_c=5[, weight=1]])  (lifting_rscamera_measurement.h:60-79): the row time of the
+    observation is a parameter of the measurement, `vt` in [0, 1] (frame-normalised, initially observation.v / rows); error is the
+    3-vector weight * [uv - project ; rows * (vt - vt_orig)] (:98-118)."""
+    _add = "add_lifting_rs"
+
+    def __init__(self, camera, observation, huber_c=5.0, weight=1.0):
+        super().__init__(camera, observation, huber_c, weight)
+        self.vt_orig = float(observation.uv[1]) / float(camera.rows)
+        self.vt = self.vt_orig
+
+    def _residual(self, trajectory, weight):
+        p, knots = _problem_for(trajectory)
+        r = self._row()
+        g = p.add_lifting_rs(self.camera._c_camera(), r["obs_uv"], r["obs_t0"], r["ref_uv"], r["ref_t0"], [0], [weight])
+        p.set_group_vt(g, [self.vt])
+        return p.evaluate(knots, np.array([r["rho"]]), _lib.EVAL_RESIDUALS)[0]["r"][0]      # 3 residuals, no loss
+
+    def project(self, trajectory):
+        return self.observation.uv - self._residual(trajectory, 1.0)[:2]
+
+    measure = project
+

@@ -440,9 +440,9 @@ def _camera_group(cfg, method, atan, p=None):
         p = _lib.Problem(0)
         p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
     cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], q_ct=q_ct, p_ct=p_ct, **kw)
-    add = p.add_newton_rs if method == "newton" else p.add_static_rs
+    add = {"newton": p.add_newton_rs, "lifting": p.add_lifting_rs}.get(method, p.add_static_rs)
     g = add(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
-    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method=method, q_ct=q_ct, p_ct=p_ct, **kw)
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method="static" if method == "lifting" else method, q_ct=q_ct, p_ct=p_ct, **kw)
     return p, g, ocam
 
 
@@ -619,4 +619,55 @@ def test_orientation_rows_match_oracle(split, local):
         p2.set_se3_spline(0.05, 0.0, 300)
         p2.add_orientation([tmax + 1.0], np.array([[0.0, 0.0, 0.0, 1.0]]))
         p2.evaluate(syn.smooth_se3_knots(300, 0.05))
+
+
+@pytest.mark.parametrize("atan,robust", [(False, False), (True, True)])
+def test_lifting_rows_match_oracle(atan, robust):
+    """LiftingRsCameraMeasurement (lifting_rscamera_measurement.h) through the C ABI: 3 residuals, rows [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3];
+    at the initial row times (where rows 0..1 are the static residuals and row 2 is zero) and after ktk_set_group_vt has moved them."""
+    cfg = syn.make_config("C3", scale=0.004)
+    c = cfg["cam"]
+    rng = np.random.default_rng(35)
+    n = len(c["lm_idx"])
+    out_l = rng.random(n) < 0.2
+    c["obs_uv"][out_l] += rng.normal(0, 40, (out_l.sum(), 2))
+    c["weight"] = rng.uniform(0.5, 2, n)
+    p, g, ocam = _camera_group(cfg, "lifting", atan)
+    assert p.group_kind(g) == _lib.LIFTING_RS
+    row = p.group_row_size(g)
+    W = (row - 90) // 21
+    assert (row - 90) % 21 == 0 and W >= 4
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    vt0 = c["obs_uv"][:, 1] / c["rows"]
+    for vt in (None, np.clip(vt0 + rng.uniform(-0.3, 0.3, n), 0.0, 1.0)):
+        if vt is not None:
+            p.set_group_vt(g, vt)
+        out = p.evaluate(cfg["knots"], c["rho"], flags)[g]
+        o = kto.lifting_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], vt=vt, weight=c["weight"], jac_mode=2, cap=24)
+        assert out["r"].shape == (n, 3) and out["J"].shape[1] == row
+        assert (out["i0"] == o["i0_ref_a"]).all()                                               # bit-exact indexing (reference window)
+        ids, nids = p.get_structure(g, cap=24)
+        assert (ids == o["ids_a"]).all()
+        assert ((o["i0_obs_a"] >= out["i0_b"]) & (o["i0_obs_a"] + 4 <= out["i0_b"] + W)).all()     # the active window lies inside the row's span
+        Js = p.expand_static_rs(g, ids, out["J"], out["i0"], out["i0_b"])                        # (n, cap, 3, 7)
+        Jvt, Jrho = out["J"][:, row - 6:row - 3], out["J"][:, row - 3:row]
+        if not robust:
+            assert np.abs(out["r"] - o["r"]).max() < parity.TOL * 1e3
+            assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jvt, o["Jvt"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+            if vt is None:
+                assert not out["r"][:, 2].any()
+        else:
+            for i in range(0, n, 7):
+                m = int(nids[i])
+                Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jvt"][i].reshape(3, 1), o["Jrho"][i].reshape(3, 1)], axis=1)
+                _, r2, J2 = kto.huber_correct(c["huber_c"][i], o["r"][i], Jfull)
+                Jmine = np.concatenate([Js[i, k] for k in range(m)] + [Jvt[i].reshape(3, 1), Jrho[i].reshape(3, 1)], axis=1)
+                assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+                assert np.abs(out["r"][i] - r2).max() <= parity.TOL * 1e3
+        dev = p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_DEVICE_ORDER)[g]
+        order = p.get_row_order(g)
+        assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order])
+    with pytest.raises(NotImplementedError):
+        p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_LOCAL)
 

@@ -6,7 +6,7 @@ import pytest
 import fixtures_ref as fx
 import kontiki_b200 as kontiki
 from kontiki_b200 import sfm
-from kontiki_b200.measurements import (AccelerometerMeasurement, GyroscopeMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
+from kontiki_b200.measurements import (AccelerometerMeasurement, GyroscopeMeasurement, LiftingRsCameraMeasurement, NewtonRsCameraMeasurement, OrientationMeasurement, PositionMeasurement,
                                        StaticRsCameraMeasurement)
 from kontiki_b200.sensors import AtanCamera, BasicImu, PinholeCamera
 from kontiki_b200.trajectories import SplitTrajectory, UniformR3SplineTrajectory, UniformSE3SplineTrajectory, UniformSO3SplineTrajectory
@@ -538,3 +538,36 @@ def test_lone_spline_estimators():
     est2 = kontiki.TrajectoryEstimator(r3)
     est2.add_measurement(PositionMeasurement(ts[3], truth[3]))
     assert est2.solve(progress=False).num_parameters_reduced == 0
+
+
+def test_lifting_rscamera_measurement_and_solve():
+    """conftest.py:151-166 puts LiftingRsCameraMeasurement next to the static and Newton classes in every camera test: project at the initial
+    row time equals the static projection, error is the 3-vector [uv - y ; rows (vt - vt_orig)], and an estimator over lifting measurements
+    (trajectory locked: landmarks and row times free) reduces the cost, the row times staying inside [0, 1]."""
+    traj = smooth_se3(n=40, dt=0.1)
+    cam = PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    lms = _small_sfm(traj, cam, n_lm=30, n_views=6, seed=5)
+    obs = next(o for L in lms for o in L.observations if not o.is_reference)
+    ms, ml = StaticRsCameraMeasurement(cam, obs), LiftingRsCameraMeasurement(cam, obs)
+    assert ml.camera is cam and ml.observation is obs and ml.vt == obs.uv[1] / cam.rows
+    assert np.allclose(ml.project(traj), ms.project(traj), atol=1e-9) and np.allclose(ml.measure(traj), ms.measure(traj), atol=1e-9)
+    e = ml.error(traj)
+    assert e.shape == (3,) and np.allclose(e[:2], ms.error(traj), atol=1e-9) and e[2] == 0.0
+    ml.vt = min(1.0, ml.vt + 0.01)
+    assert abs(ml.error(traj)[2] - cam.rows * (ml.vt - ml.vt_orig)) < 1e-9
+    rng = np.random.default_rng(2)
+    for L in lms:
+        L.inverse_depth *= 1.0 + 0.1 * rng.normal()
+    est = kontiki.TrajectoryEstimator(traj)
+    meas = []
+    for L in lms:
+        for o in L.observations:
+            if not o.is_reference:
+                meas.append(LiftingRsCameraMeasurement(cam, o))
+                est.add_measurement(meas[-1])
+    traj.locked = True
+    summary = est.solve(max_iterations=20, progress=False)
+    assert summary.final_cost < 0.05 * summary.initial_cost
+    assert summary.num_residuals == 3 * len(meas) and all(0.0 <= m.vt <= 1.0 for m in meas)
+    assert summary.num_parameters_reduced == len(lms) + len(meas)
+
