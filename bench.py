@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--workload", default="H1")
     ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--camera-method", default="static", choices=["static", "newton"],
+    ap.add_argument("--camera-method", default="static", choices=["static", "newton", "lifting"],
                     help="StaticRsCameraMeasurement (the BASELINE.json workloads) or NewtonRsCameraMeasurement rows (SURVEY.md 8f-3) for the camera group")
     ap.add_argument("--camera-model", default="pinhole", choices=["pinhole", "atan"], help="PinholeCamera (BASELINE.json) or AtanCamera")
     ap.add_argument("--row-order", default="caller", choices=["caller", "device"],
@@ -57,7 +57,7 @@ def workload_config(name, cfg, row_order="caller", method="static", model="pinho
     traj = "SplitTrajectory (UniformR3 + UniformSO3)" if cfg.get("split") else "UniformSE3SplineTrajectory"
     return {"workload": f"{name}: {traj} {len(cfg['knots'])} knots dt={cfg['dt']}, "
                         f"{len(cfg['gyro']['t']) if cfg['gyro'] else 0} gyro + {len(cfg['accel']['t']) if cfg['accel'] else 0} accel (BasicImu) + "
-                        f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} {'NewtonRsCamera' if method == 'newton' else 'StaticRsCamera'} "
+                        f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} {dict(newton='NewtonRsCamera', lifting='LiftingRsCamera').get(method, 'StaticRsCamera')} "
                         f"({'Atan' if model == 'atan' else 'Pinhole'}, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
             "measurements_per_step_per_gpu": syn.num_measurements(cfg),
             "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
@@ -104,9 +104,14 @@ def oracle_step(cfg, sample):
             rows += len(m["t"]); secs += res["eval_seconds"]
     if "cam" in sample:
         c = sample["cam"]
-        ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method=CAMERA["method"], **(ATAN if CAMERA["model"] == "atan" else {}))
-        res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24,
-                                      nthreads=NTHREADS)
+        ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method="static" if CAMERA["method"] == "lifting" else CAMERA["method"],
+                          **(ATAN if CAMERA["model"] == "atan" else {}))
+        if CAMERA["method"] == "lifting":
+            res = kto.lifting_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], weight=c["weight"], jac_mode=1,
+                                           cap=24, nthreads=NTHREADS)
+        else:
+            res = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=1, cap=24,
+                                          nthreads=NTHREADS)
         rows += len(c["lm_idx"]); secs += res["eval_seconds"]
     return rows, secs
 
@@ -232,7 +237,7 @@ def main():
     if cfg["cam"]:
         c = cfg["cam"]
         rho = c["rho"]
-        add = p.add_newton_rs if a.camera_method == "newton" else p.add_static_rs
+        add = {"newton": p.add_newton_rs, "lifting": p.add_lifting_rs}.get(a.camera_method, p.add_static_rs)
         groups["cam"] = add(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], **(ATAN if a.camera_model == "atan" else {})), c["obs_uv"], c["obs_t0"],
                             c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
     flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST
@@ -243,8 +248,8 @@ def main():
     d_rho = torch.from_numpy(rho).to(dev) if rho is not None else None
     d_outs, keep = [], []
     for g in range(p.num_groups):
-        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
-        r = torch.empty((n, 2 if cam else 3), dtype=torch.float64, device=dev)
+        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS, _lib.LIFTING_RS)
+        r = torch.empty((n, 2 if p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS) else 3), dtype=torch.float64, device=dev)
         J = torch.empty((n, p.group_row_size(g)), dtype=torch.float64, device=dev)
         idx = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(4)]
         keep.append((r, J, idx))
@@ -299,8 +304,8 @@ def main():
     h_rho = torch.from_numpy(rho).pin_memory() if rho is not None else None
     h_outs, d2h = [], 0
     for g in range(p.num_groups):
-        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
-        o = dict(r=torch.empty((n, 2 if cam else 3), dtype=torch.float64).pin_memory(),
+        n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS, _lib.LIFTING_RS)
+        o = dict(r=torch.empty((n, 2 if p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS) else 3), dtype=torch.float64).pin_memory(),
                  J=torch.empty((n, p.group_row_size(g)), dtype=torch.float64).pin_memory(),
                  i0=torch.empty(n, dtype=torch.int32).pin_memory())
         if cam:
@@ -346,11 +351,13 @@ def main():
     per_row = ({"cam": 1020, "accel": 744, "gyro": 452} if cfg.get("split") else {"cam": 1012, "accel": 740, "gyro": 740})[dom]
     if dom == "cam" and a.camera_method == "newton":      # in 76 + r 16 + packed row (58 + 14 W doubles) + i0_ref, i0_obs
         per_row = 76 + 16 + 8 * p.group_row_size(groups["cam"]) + 8
+    if dom == "cam" and a.camera_method == "lifting":     # in 76 + vt 8 + r 24 + packed row (90 + 21 W doubles) + i0_ref, i0_obs
+        per_row = 76 + 8 + 24 + 8 * p.group_row_size(groups["cam"]) + 8
     dom_bytes = dom_rows * per_row
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_ms > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get({"cam": "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom])
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get({"cam": "k_static_rs" if a.camera_method == "static" else "-", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom])
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
@@ -360,7 +367,7 @@ def main():
                     "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
-            "roofline": {"bound": "hbm", "kernel": {"cam": "k_newton_rs" if a.camera_method == "newton" else "k_static_rs", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_newton_rs", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
