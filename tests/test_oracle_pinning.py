@@ -345,11 +345,16 @@ def _sfm_case(name, model, method, seed=11, **kw):
 # --- test_measurements.py:16-32 over projection_types x camera fixture (Pinhole, Atan) -------------------------
 @pytest.mark.parametrize("name", ["se3", "split"])
 @pytest.mark.parametrize("model", ["pinhole", "atan"])
-@pytest.mark.parametrize("method", ["static", "newton"])
+@pytest.mark.parametrize("method", ["static", "newton", "lifting"])
 def test_rscamera_measurements(name, model, method):
-    traj, cam, s = _sfm_case(name, model, method)
+    traj, cam, s = _sfm_case(name, model, "static" if method == "lifting" else method)
     assert len(s["lm_idx"]) >= 10
-    res = kto.static_rs_residuals(traj, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], jac_mode=0)
+    if method == "lifting":       # LiftingRsCameraMeasurement.project at its initial row time vt = v / rows (lifting_rscamera_measurement.h:68, :90-96)
+        res = kto.lifting_rs_residuals(traj, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], jac_mode=0)
+        assert res["r"].shape[1] == 3 and not res["r"][:, 2].any()
+        res["r"] = res["r"][:, :2]
+    else:
+        res = kto.static_rs_residuals(traj, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], jac_mode=0)
     assert_almost_equal(res["r"], 0 * res["r"])       # np.testing.assert_almost_equal(yhat, obs.uv)  (decimal=7)
 
 
@@ -469,6 +474,33 @@ def test_camera_jacobian_vs_numdiff_se3():
         return kto.static_rs_residuals(traj, cam, *args, r, jac_mode=0)["r"][0]
     Jr = _numdiff(frho, s["rho"])[:, s["lm_idx"][0]]
     assert_allclose(res["Jrho"][0], Jr, atol=1e-5 * max(1, np.abs(Jr).max()))
+
+
+@pytest.mark.parametrize("name", ["se3", "split"])
+def test_lifting_jacobian_vs_numdiff(name):
+    """LiftingRsCameraMeasurement: the multipass autodiff of the restated residual (3 rows; blocks [knots | camera | vt | rho]) against central
+    differences of its double path, at a displaced row time."""
+    traj, cam, s = _sfm_case(name, "pinhole", "static", seed=2, nlm=3)
+    sel = slice(0, 1)
+    args = [s[k][sel] for k in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx")]
+    vt = np.array([s["obs_uv"][0, 1] / cam.rows + 0.05])
+    res = kto.lifting_rs_residuals(traj, cam, *args, s["rho"], vt=vt, jac_mode=2)
+    assert abs(res["r"][0, 2] - cam.rows * 0.05) < 1e-9
+    Jv = _numdiff(lambda v: kto.lifting_rs_residuals(traj, cam, *args, s["rho"], vt=v, jac_mode=0)["r"][0], vt)[:, 0]
+    assert_allclose(res["Jvt"][0], Jv, atol=2e-6 * np.abs(Jv).max())
+    Jr = _numdiff(lambda r: kto.lifting_rs_residuals(traj, cam, *args, r, vt=vt, jac_mode=0)["r"][0], s["rho"])[:, s["lm_idx"][0]]
+    assert_allclose(res["Jrho"][0], Jr, atol=1e-5 * max(1, np.abs(Jr).max()))
+    if name == "se3":
+        knots = traj.knots_a.copy()
+        ids = res["ids_a"][0]; ids = ids[ids >= 0]
+
+        def f(kn):
+            kk = knots.copy(); kk[ids] = kn
+            return kto.lifting_rs_residuals(kto.Traj(kto.SE3, 0.1, 0.0, kk), cam, *args, s["rho"], vt=vt, jac_mode=0)["r"][0]
+        Jn = _numdiff(f, knots[ids])
+        Ja = np.concatenate([res["Ja"][0, k] for k in range(len(ids))], axis=1)
+        assert_allclose(Ja, Jn, atol=2e-6 * np.abs(Ja).max())
+        assert not Ja[2].any()                       # the timing residual does not see the trajectory
 
 
 @pytest.mark.parametrize("model", ["pinhole", "atan"])
