@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_ANALYTIC_PATH = os.path.join(_HERE, "libanalytic_cpu.so")      # the optimised CPU variant of SURVEY.md 8(d), analytic_cpu.cpp
 
 SE3, SPLIT, R3, SO3 = 0, 1, 2, 3
 EvalPosition, EvalVelocity, EvalAcceleration, EvalOrientation, EvalAngularVelocity = 1, 2, 4, 8, 16
@@ -20,8 +21,11 @@ OK, RANGE_ERROR, RUNTIME_ERROR = 0, -1, -2
 def build(force=False):
     """Compile the oracle with the committed Makefile (g++ only, no dependencies)."""
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "kontiki_ref.hpp", "lie.hpp", "dual.hpp", "Makefile")]
-    if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CXX": "g++"})
+    csrc = os.path.join(os.path.dirname(_HERE), "kontiki_b200", "csrc")
+    srcs2 = [os.path.join(_HERE, "analytic_cpu.cpp"), os.path.join(_HERE, "Makefile")] + [os.path.join(csrc, f) for f in ("spline_math.cuh", "lie_math.cuh", "dualnum.cuh")]
+    stale = lambda lib, deps: not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in deps)
+    if force or stale(_LIB_PATH, srcs) or stale(_ANALYTIC_PATH, srcs2):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []), env={**os.environ, "CXX": "g++"})
     return _LIB_PATH
 
 
@@ -320,3 +324,45 @@ def camera_unproject(cam, y):
     cm = cam.cmeta()
     lib().kto_camera_unproject(C.byref(cm), _p(y), _p(X))
     return X
+
+
+_alib = None
+
+
+def analytic_se3_evaluate(dt, t0, knots, gyro=None, accel=None, cam=None, nthreads=0):
+    """The OPTIMISED CPU variant (oracle/analytic_cpu.cpp): the product's closed-form mathematics compiled for the host and
+    looped over the rows with OpenMP.  gyro / accel: dicts t, y, weight; cam: dict K, readout, rows, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx,
+    rho, weight, huber_c (None = no loss), optional wc / gamma (AtanCamera).  Returns dict(seconds, bad, gyro=(r, J), accel=(r, J), cam=(r, J))."""
+    global _alib
+    if _alib is None:
+        build()
+        _alib = C.CDLL(_ANALYTIC_PATH)
+        _alib.kta_se3_evaluate.restype = C.c_double
+    knots = _f64(knots)
+    out, keep = {}, []
+
+    def imu_args(m):
+        if m is None:
+            return [0, None, None, None], (None, None)
+        t, y = _f64(m["t"]), _f64(m["y"]).reshape(-1, 3)
+        w = np.ones(len(t)) if m.get("weight") is None else _f64(m["weight"])
+        keep.extend([t, y, w])
+        return [len(t), _p(t), _p(y), _p(w)], (np.zeros((len(t), 3)), np.zeros((len(t), 84)))
+    ga, (gr, gJ) = imu_args(gyro)
+    aa, (ar, aJ) = imu_args(accel)
+    if cam is None:
+        ca, cr, cJ = [0, None, C.c_double(0.0), 0, 0, None, C.c_double(0.0)] + [None] * 8, None, None
+    else:
+        n = len(cam["obs_t0"])
+        arrs = [_f64(cam["obs_uv"]).reshape(-1, 2), _f64(cam["obs_t0"]), _f64(cam["ref_uv"]).reshape(-1, 2), _f64(cam["ref_t0"]),
+                np.ascontiguousarray(cam["lm_idx"], np.int32), _f64(cam["rho"]), np.ones(n) if cam.get("weight") is None else _f64(cam["weight"]),
+                None if cam.get("huber_c") is None else _f64(cam["huber_c"])]
+        K, wc = _f64(cam["K"]).reshape(-1), _f64(cam.get("wc", (0.0, 0.0)))
+        keep.extend(arrs + [K, wc])
+        ca = [n, _p(K), C.c_double(cam["readout"]), int(cam["rows"]), 0 if cam.get("gamma") is None else 1, _p(wc), C.c_double(cam.get("gamma") or 0.0)] + [_p(a) for a in arrs]
+        cr, cJ = np.zeros((n, 2)), np.zeros((n, 114))
+    bad = np.zeros(1, np.int32)
+    secs = _alib.kta_se3_evaluate(C.c_double(t0), C.c_double(dt), len(knots), _p(knots), *ga, *aa, *ca, int(nthreads),
+                                  _p(gr), _p(gJ), _p(ar), _p(aJ), _p(cr), _p(cJ), _p(bad))
+    return dict(seconds=float(secs), bad=int(bad[0]), gyro=(gr, gJ), accel=(ar, aJ), cam=(cr, cJ))
+

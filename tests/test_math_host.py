@@ -341,3 +341,25 @@ def test_lifting_rs_rows_match_oracle(atan, robust):
                 n_out += float(np.dot(o["r"][i], o["r"][i])) > 4.0
             assert n_out > 0
 
+
+def test_optimised_cpu_variant_matches_oracle():
+    """oracle/analytic_cpu.cpp -- the OPTIMISED CPU baseline bench.py reports next to the restated reference: the product's
+    closed-form math on the host with OpenMP.  It is only a baseline if it computes the same rows: gyro / accel / static-RS vs the oracle."""
+    from kontiki_b200 import synthetic as syn
+    cfg = syn.make_config("H1", scale=0.002)
+    c = cfg["cam"]
+    camd = {k: c[k] for k in ("K", "readout", "rows", "obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "rho", "weight")}
+    res = kto.analytic_se3_evaluate(cfg["dt"], cfg["t0"], cfg["knots"], gyro=cfg["gyro"], accel=cfg["accel"], cam=camd, nthreads=2)
+    assert res["bad"] == 0 and res["seconds"] > 0
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    for which, key in ((0, "gyro"), (1, "accel")):
+        m = cfg[key]
+        o = kto.imu_residuals(traj, kto.Sensor(), which, m["t"], m["y"], m["weight"], jac_mode=2)
+        assert parity.rel_err(res[key][0], o["r"]) < parity.TOL and parity.rel_err(res[key][1].reshape(-1, 4, 3, 7), o["Ja"][:, :4]) < parity.TOL
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"])
+    o = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=2, cap=24)
+    r, J = res["cam"]
+    assert np.abs(r - o["r"]).max() < parity.TOL * 1e3
+    Js, Jrho = parity.scatter_cam(J, o["i0_ref_a"], o["i0_obs_a"], o["ids_a"])
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+
