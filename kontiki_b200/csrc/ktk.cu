@@ -1,8 +1,8 @@
 // kontiki_b200 -- CUDA kernels (sm_100a) and the C ABI of include/kontiki_b200.h.
 //
 // Kernels per evaluation point:
-//   k_pack_knots     n_knots x 7 (reference layout) -> 64-B knot records
-//   k_pair_prepass   K0: omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian, one thread per (pair, direction)
+//   k_pair_prepass   K0: n_knots x 7 (reference layout) -> 64-B knot records; omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian,
+//                    one thread per (pair, direction)
 //   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
 //   k_landmark_ref   reference side of the static-RS rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
 //   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); the warp gathers its 32
@@ -152,18 +152,20 @@ __device__ __forceinline__ void warp_gather_records(double* wbase, const double*
   }
 }
 
-__global__ void k_pack_knots(const double* __restrict__ k7, int n, double* __restrict__ k8) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * kKnotStride) return;
-  const int k = i / kKnotStride, c = i % kKnotStride;
-  k8[i] = c < 7 ? k7[(size_t)k * 7 + c] : 0.0;
-}
-
-__global__ void k_pair_prepass(const double* __restrict__ knots, int n_knots, double* __restrict__ pairs) {
+// K0, fused with the knot packing: reads the caller's n x 7 knots, writes the 64-B knot records (thread dir == 14 of pair p packs knot p,
+// pair 1 also knot 0) and the pair records.  One launch instead of two: the step is a chain of short kernels and each link costs ~3 us.
+__global__ void k_pair_prepass(const double* __restrict__ k7, int n_knots, double* __restrict__ k8, double* __restrict__ pairs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int p = 1 + i / 15, dir = i % 15;
   if (p >= n_knots) return;
-  pair_prepass_item(knots, p, dir, pairs);
+  pair_prepass_item<7>(k7, p, dir, pairs);
+  if (dir == 14) {
+    for (int q = (p == 1 ? 0 : p); q <= p; ++q) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) k8[(size_t)q * kKnotStride + c] = k7[(size_t)q * 7 + c];
+      k8[(size_t)q * kKnotStride + 7] = 0.0;
+    }
+  }
 }
 
 // One warp = one tile of 32 consecutive sorted rows; CTAs are small (1-2 warps) and one-shot: the hardware CTA scheduler
@@ -1437,9 +1439,8 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
   cudaStream_t s = p->stream;
   const int nk = p->sp.n_knots;
   KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
-  k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(d_knots, nk, p->d_knots8.p);
-  k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
-  p->launches += 2;
+  k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(d_knots, nk, p->d_knots8.p, p->d_pairs.p);
+  p->launches += 1;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
     Group& g = *p->groups[gi];
     if (g.n == 0) continue;
@@ -1580,8 +1581,7 @@ static int traj_evaluate_impl(ktk_problem* p, const double* knots, int64_t n, co
   if (p->traj == 0) {
     const int nk = p->sp.n_knots;
     if ((st = p->d_knots8.resize((size_t)nk * kKnotStride)) || (st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
-    k_pack_knots<<<(nk * kKnotStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p);
-    k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots8.p, nk, p->d_pairs.p);
+    k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p, p->d_pairs.p);
     if (width == 16) k_traj_eval_se3<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
     else k_traj_eval_se3_matrices<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
   } else {
@@ -1592,7 +1592,7 @@ static int traj_evaluate_impl(ktk_problem* p, const double* knots, int64_t n, co
     k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
     k_traj_eval_split<<<blocks, 128, 0, s>>>(sp, p->d_vecs4.p, d_quats, p->d_so3pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
   }
-  p->launches += 3;
+  p->launches += p->traj == 0 ? 2 : 3;
   KTK_CUDA(cudaGetLastError());
   KTK_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
   KTK_CUDA(cudaMemcpyAsync(status, d_st.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -170,9 +170,11 @@ template <class T> KB_HD void pair_log(const T* a, const T* b, T* om) {
 
 // One (pair, direction) work item of K0.  dir in [0,14): derivative with respect to ambient scalar `dir` of
 // [knot p-1 (7), knot p (7)]; dir == 14: values only.  knots: kKnotStride records; out: pair record `p`.
+// KSTRIDE: doubles between knots in `knots` (kKnotStride records, or 7 for the caller's n x 7 array: the fused pack + prepass kernel).
+template <int KSTRIDE = kKnotStride>
 KB_HD void pair_prepass_item(const double* knots, int p, int dir, double* pairs) {
-  const double* ka = knots + (size_t)(p - 1) * kKnotStride;
-  const double* kb_ = knots + (size_t)p * kKnotStride;
+  const double* ka = knots + (size_t)(p - 1) * KSTRIDE;
+  const double* kb_ = knots + (size_t)p * KSTRIDE;
   double* rec = pairs + (size_t)p * kPairStride;
   if (dir >= 14) {
     double om[6];
