@@ -1378,7 +1378,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
   int st;
   for (auto g : p->groups) {
     if ((st = upload_group(p, *g))) return st;
-    if (g->kind == KTK_LIFTING_RS && (g->vt_dirty || g->d_vt.n != (size_t)g->n)) {      // the row times are part of the evaluation point (device order); outside any capture
+    if (g->kind == KTK_LIFTING_RS && g->n > 0 && (g->vt_dirty || g->d_vt.n != (size_t)g->n)) {      // the row times are part of the evaluation point (device order); outside any capture
       std::vector<double> sorted((size_t)g->n);
       for (int64_t k = 0; k < g->n; ++k) sorted[k] = g->vt[(size_t)g->perm[k]];
       if ((st = g->d_vt.upload(sorted, s))) return st;

@@ -71,7 +71,7 @@ def build():
 
 
 def build_v2():
-    """oracle_v2.npz: OrientationMeasurement rows (added after v1 was frozen; v1 is not regenerated)."""
+    """oracle_v2.npz: OrientationMeasurement and LiftingRsCameraMeasurement rows (added after v1 was frozen; v1 is not regenerated)."""
     out = {}
     rng = np.random.default_rng(20261018)
 
@@ -101,6 +101,17 @@ def build_v2():
     o = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm, jac_mode=2)
     out["split_t"], out["split_q"], out["split_angle"] = t, qm, ang
     out["split_ori_r"], out["split_ori_Jb"], out["split_ori_i0a"], out["split_ori_i0b"] = o["r"], o["Jb"][:, :4], o["ids_a"][:, 0], o["i0_b"]
+    # --- LiftingRsCameraMeasurement rows on the camera case of v1 (same structure, relative pose set), at displaced row times
+    dt = 0.05
+    knots = syn.smooth_se3_knots(80, dt)
+    s = syn.make_static_rs(knots, dt, 8, obs_per_landmark=4, seed=77, noise_px=1.0)
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], q_ct=q_ct, p_ct=p_ct)
+    vt = np.clip(np.asarray(s["obs_uv"])[:, 1] / s["rows"] + rng.uniform(-0.2, 0.2, len(s["lm_idx"])), 0.0, 1.0)
+    o = kto.lifting_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], vt=vt,
+                                 jac_mode=2, cap=16)
+    out["lift_vt"] = vt
+    out["lift_r"], out["lift_ids"], out["lift_Ja"], out["lift_Jvt"], out["lift_Jrho"], out["lift_i0_ref"] = o["r"], o["ids_a"], o["Ja"], o["Jvt"], o["Jrho"], o["i0_ref_a"]
     return out
 
 

@@ -154,3 +154,42 @@ def test_cuda_path_matches_golden_orientation():
     o = p.evaluate((np.asarray(fx.R3_KNOTS, float), np.asarray(fx.SO3_KNOTS, float)))[g]
     assert (o["i0_c"] == G2["split_ori_i0b"]).all() and (o["i0"] == G2["split_ori_i0a"]).all()
     assert np.abs(o["r"] - G2["split_ori_r"]).max() < parity.TOL and parity.rel_err(o["J"].reshape(-1, 4, 1, 4), G2["split_ori_Jb"]) < parity.TOL
+
+
+# ---- oracle_v2.npz: LiftingRsCameraMeasurement rows on the v1 camera case (structure arrays from oracle_v1.npz) ------------------------------
+def _lifting_args():
+    return (G["cam_obs_uv"], G["cam_obs_t0"], G["cam_ref_uv"], G["cam_ref_t0"], G["cam_lm_idx"], G["cam_rho"])
+
+
+def test_oracle_reproduces_the_golden_lifting_vectors():
+    cam = _oracle_cam("static", "pinhole")
+    o = kto.lifting_rs_residuals(kto.Traj(kto.SE3, float(G["cam_dt"][0]), 0.0, G["cam_knots"]), cam, *_lifting_args(), vt=G2["lift_vt"], jac_mode=2, cap=16)
+    assert _same(o["r"], G2["lift_r"]) and _same(o["Ja"], G2["lift_Ja"]) and _same(o["Jvt"], G2["lift_Jvt"]) and _same(o["Jrho"], G2["lift_Jrho"])
+    assert np.array_equal(o["ids_a"], G2["lift_ids"]) and np.array_equal(o["i0_ref_a"], G2["lift_i0_ref"])
+
+
+def test_host_math_matches_golden_lifting():
+    cam = _oracle_cam("static", "pinhole")
+    h = hc.lifting_rs(G["cam_knots"], float(G["cam_dt"][0]), 0.0, cam, *_lifting_args(), vt=G2["lift_vt"])
+    assert (h["status"] == 0).all() and (h["i0_ref"] == G2["lift_i0_ref"]).all()
+    Js, Jvt, Jrho = parity.scatter_lifting(h["J"], h["i0_ref"], h["i0_obs"], G2["lift_ids"], h["W"])
+    assert np.abs(h["r"] - G2["lift_r"]).max() < parity.TOL * 1e3
+    assert parity.rel_err(Js, G2["lift_Ja"]) < parity.TOL and parity.rel_err(Jvt, G2["lift_Jvt"]) < parity.TOL and parity.rel_err(Jrho, G2["lift_Jrho"]) < parity.TOL
+
+
+@pytest.mark.gpu
+def test_cuda_path_matches_golden_lifting():
+    rows, cols, readout = G["cam_meta"]
+    p = _lib.Problem(0)
+    p.set_se3_spline(float(G["cam_dt"][0]), 0.0, len(G["cam_knots"]))
+    cam = _lib.make_camera(int(rows), int(cols), float(readout), G["cam_K"], q_ct=G["cam_q_ct"], p_ct=G["cam_p_ct"])
+    g = p.add_lifting_rs(cam, *_lifting_args()[:5])
+    p.set_group_vt(g, G2["lift_vt"])
+    o = p.evaluate(G["cam_knots"], G["cam_rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS)[g]
+    assert (o["i0"] == G2["lift_i0_ref"]).all()
+    ids, _ = p.get_structure(g, cap=16)
+    assert (ids == G2["lift_ids"]).all()
+    Js = p.expand_static_rs(g, ids, o["J"], o["i0"], o["i0_b"])
+    assert np.abs(o["r"] - G2["lift_r"]).max() < parity.TOL * 1e3
+    assert parity.rel_err(Js, G2["lift_Ja"]) < parity.TOL and parity.rel_err(o["J"][:, -6:-3], G2["lift_Jvt"]) < parity.TOL
+    assert parity.rel_err(o["J"][:, -3:], G2["lift_Jrho"]) < parity.TOL

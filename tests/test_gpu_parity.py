@@ -132,6 +132,16 @@ def test_empty_and_ragged_groups():
     assert outs[g0]["r"].shape == (0, 3)
     o = parity.oracle_imu(kto.Traj(kto.SE3, cfg["dt"], 0.0, cfg["knots"]), 0, cfg["gyro"]["t"], cfg["gyro"]["y"])
     _check_imu(outs[g1], o)
+    # empty groups of every other kind sit in the same problem without disturbing it
+    cam = _lib.make_camera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    e = np.zeros(0)
+    g2 = p.add_orientation(e, np.zeros((0, 4)))
+    g3 = p.add_position(e, np.zeros((0, 3)))
+    g4 = p.add_lifting_rs(cam, np.zeros((0, 2)), e, np.zeros((0, 2)), e, np.zeros(0, np.int32))
+    g5 = p.add_newton_rs(cam, np.zeros((0, 2)), e, np.zeros((0, 2)), e, np.zeros(0, np.int32))
+    outs = p.evaluate(cfg["knots"], np.zeros(1))
+    assert outs[g2]["r"].shape == (0, 1) and outs[g3]["r"].shape == (0, 3) and outs[g4]["r"].shape == (0, 3) and outs[g5]["r"].shape == (0, 2)
+    _check_imu(outs[g1], o)
 
 
 def test_full_size_properties_h1():
