@@ -1435,63 +1435,77 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
   return st;
 }
 
+// One kernel after the other: running the short kernels (IMU-like rows, landmark records) as parallel branches of the graph was measured
+// twice and lost both times (profiles/r1g_kernel_experiments.md): co-resident CTAs of different kernels share the instruction cache.
 static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs) {
   cudaStream_t s = p->stream;
   const int nk = p->sp.n_knots;
   KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
   k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(d_knots, nk, p->d_knots8.p, p->d_pairs.p);
   p->launches += 1;
-  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
-    Group& g = *p->groups[gi];
-    if (g.n == 0) continue;
-    const ktk_group_out& o = outs[gi];
-    const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
-    const int blocks = (int)((g.n + tpb - 1) / tpb);
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
+  // the kernels of one group: "short" = IMU-like rows or the landmark records of a camera group (about one wave each on H1);
+  // "rows" = the camera rows, which need their landmark records
+  auto launch_short = [&](Group& g, const ktk_group_out& o, cudaStream_t ss) {
     if (is_camera(g.kind)) {
       RefArgs ra;
       ra.sp = p->sp; fill_camera_consts(g.cam, ra.cam);
       ra.knots = p->d_knots8.p; ra.pairs = p->d_pairs.p; ra.rho = d_rho;
       ra.ref_uv = g.d_rr_uv.p; ra.ref_t0 = g.d_rr_t0.p; ra.seg_start = g.d_rr_start.p; ra.seg_n = g.d_rr_n.p; ra.lm = g.d_rr_lm.p;
       ra.n = (int)g.n_ref; ra.recs = g.d_recs.p; ra.err = p->d_err.p;
-      if (g.n_ref > 0) { k_landmark_ref<<<(int)((g.n_ref + kThreads - 1) / kThreads), kThreads, kThreads * kRefStride * 8, s>>>(ra); p->launches += 1; }
-      CamArgs a;
-      a.sp = p->sp; a.cam = ra.cam;
-      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.recs = g.d_recs.p;
-      a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
-      a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->cam_resident_tiles;
-      a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
-      if (is_span_camera(g.kind)) {
-        NewtonArgs na;
-        na.sp = a.sp; na.cam = a.cam; na.knots = a.knots; na.pairs = a.pairs; na.recs = a.recs;
-        na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
-        na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
-        if (g.kind == KTK_LIFTING_RS) {
-          const long long threads = (long long)g.n * (30 + 7 * na.W);
-          k_lifting_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_vt.p);
-        } else {
+      if (g.n_ref > 0) { k_landmark_ref<<<(int)((g.n_ref + kThreads - 1) / kThreads), kThreads, kThreads * kRefStride * 8, ss>>>(ra); p->launches += 1; }
+      return;
+    }
+    const int blocks = (int)((g.n + kThreads - 1) / kThreads);
+    ImuArgs a;
+    a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
+    for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
+    a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
+    a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+    a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
+    if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
+    else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
+    else if (g.kind == KTK_ORIENTATION) k_imu<3><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
+    else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
+    p->launches += 1;
+  };
+  auto launch_rows = [&](Group& g, const ktk_group_out& o) {
+    if (!is_camera(g.kind)) return;
+    const int blocks = (int)((g.n + kCamThreads - 1) / kCamThreads);
+    CamArgs a;
+    a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
+    a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.recs = g.d_recs.p;
+    a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
+    a.perm = g.d_perm.p; a.io = g.d_io.p; a.uo = g.d_uo.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->cam_resident_tiles;
+    a.r = o.r; a.J = o.J; a.i0r = o.i0; a.i0o = o.i0_b; a.err = p->d_err.p;
+    if (is_span_camera(g.kind)) {
+      NewtonArgs na;
+      na.sp = a.sp; na.cam = a.cam; na.knots = a.knots; na.pairs = a.pairs; na.recs = a.recs;
+      na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
+      na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
+      if (g.kind == KTK_LIFTING_RS) {
+        const long long threads = (long long)g.n * (30 + 7 * na.W);
+        k_lifting_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_vt.p);
+      } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
-        }
       }
-      else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
-      else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
-    } else {
-      ImuArgs a;
-      a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
-      for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
-      a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
-      a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
-      a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
-      if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
-      else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
-      else if (g.kind == KTK_ORIENTATION) k_imu<3><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
-      else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, s>>>(a);
     }
-    if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
+    else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);
+    else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     p->launches += 1;
-    { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, nullptr); if (sj) return sj; }
+  };
+  {
+    for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+      Group& g = *p->groups[gi];
+      if (g.n == 0) continue;
+      const ktk_group_out& o = outs[gi];
+      cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+      if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
+      launch_short(g, o, s);
+      launch_rows(g, o);
+      if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
+      { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, nullptr); if (sj) return sj; }
+    }
   }
   KTK_CUDA(cudaGetLastError());
   KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
