@@ -174,7 +174,8 @@ int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
  * measurement (initially obs_uv.y / rows, :68); 3 residuals weight * [uv - y ; rows * (vt - vt_orig)] (:105-116) under the Huber loss.
  * ktk_set_group_vt feeds the current row times (caller order) like ktk_set_group_sensor feeds sensor parameters.  Packed row
  * [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles (ktk_group_row_size), W and i0_b as for the Newton
- * rows (whole observation span); r is 3 per row.  UniformSE3SplineTrajectory with locked camera parameters only; no KTK_EVAL_LOCAL,
+ * rows (whole observation span; the four active knot blocks sit at their place inside it, the others are zero); r is 3 per row.
+ * UniformSE3SplineTrajectory with locked camera parameters only; no KTK_EVAL_LOCAL,
  * no matrix-free products (KTK_EUNSUPPORTED). */
 int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                        const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);

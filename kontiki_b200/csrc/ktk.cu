@@ -855,43 +855,58 @@ __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a) {
   }
 }
 
-// LiftingRsCameraMeasurement rows (newton_math.cuh "LiftingRsCameraMeasurement"): the Newton kernel's shape -- one forward-mode direction
-// per thread on the hoisted structure -- without the iteration; vt[i] is the current value of row i's own parameter block.
-// Packed row [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)], 3 residuals.
-__global__ void __launch_bounds__(128) k_lifting_rs(const NewtonArgs a, const double* __restrict__ vt) {
-  const int ndir = 30 + 7 * a.W, row_len = 90 + 21 * a.W;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(tid / ndir), dir = (int)(tid % ndir);
-  if (i >= a.n) return;
+// LiftingRsCameraMeasurement rows in closed form (newton_math.cuh "LiftingRs rows in CLOSED FORM"): one thread per row like the static kernel,
+// three residual rows through the same reverse sweep; vt[i] is the current value of row i's own parameter block.  A thread stages
+// [Jref 84 | Jobs 84 | vt 3 | rho 3] in shared memory; the warp then writes the 32 packed rows [ref 4 x (3x7) | obs W x (3x7) | vt 3 | rho 3]
+// cooperatively (8-byte stores, consecutive lanes on consecutive doubles), the active window at its place inside the W-knot span and zeros elsewhere.
+constexpr int kLiftStage = 176;      // 174 staged doubles per row, padded to a 16-byte multiple
+__global__ void __launch_bounds__(32) k_lifting_rs(const NewtonArgs a, const double* __restrict__ vt) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* row = smem + lane * kLiftStage;
+  const int i = blockIdx.x * 32 + lane;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
-  if (!wantJ && dir != 0) return;
-  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
-  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
-  const double obs_t0 = a.obs_t0[i], v = vt[i];
-  const int ridx = a.ref_idx[i];
-  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
-  int st = kStatusRange;
-  double r[3] = {nan(""), nan(""), nan("")}, j[3] = {nan(""), nan(""), nan("")};
-  int ir = -1;
-  if (ridx >= 0) {
-    const double* rec = a.recs + (size_t)ridx * kRefStride;
-    ir = (int)rec[7];
-    if (ir >= 0) {
-      LiftingRow o;
-      st = lifting_rs_direction(a.sp, a.cam, a.knots, a.pairs, rec, obs_t0, a.ref_t0[i], v, kbase, a.W, wantJ ? dir : -1, o);
-      if (st == 0) lifting_rs_finish(o, a.cam, ouv, v, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, j);
+  const int row_len = 90 + 21 * a.W;
+  int perm = -1, rel = 0;
+  if (i < a.n) {
+    perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
+    const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+    const double obs_t0 = a.obs_t0[i];
+    const int ridx = a.ref_idx[i];
+    const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+    int st = kStatusRange, ir = -1, io = -1;
+    double r[3] = {nan(""), nan(""), nan("")};
+    if (ridx >= 0) {
+      st = lifting_rs_row_analytic(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)ridx * kRefStride, ouv, obs_t0, a.ref_t0[i], vt[i], a.w[i],
+                                   (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, row, row + 84, row + 168, row + 171, &ir, &io);
+      if (st == 0 && (io < kbase || io + 4 > kbase + a.W)) st = kStatusRange;
     }
-  }
-  if (st != 0) { atomicMin(a.err, st); ir = -1; }
-  if (dir == 0) {
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = r[2] = nan(""); ir = -1;
+      KTK_COLD_LOOP for (int c = 0; c < 174; ++c) row[c] = nan("");
+      io = kbase;
+    }
+    rel = io - kbase;
+    const size_t dst = (size_t)perm;
     if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
     if (a.i0r) a.i0r[dst] = ir;
     if (a.i0o) a.i0o[dst] = st == 0 ? kbase : -1;
   }
-  if (wantJ) {
-    const int off = lifting_dir_offset(dir, a.W), stride = dir < 28 + 7 * a.W ? 7 : 1;
-    double* Jr = a.J + dst * row_len;
-    Jr[off] = j[0]; Jr[off + stride] = j[1]; Jr[off + 2 * stride] = j[2];
+  __syncwarp();
+  if (!wantJ) return;
+  for (int rr = 0; rr < 32; ++rr) {
+    const int d = __shfl_sync(0xffffffffu, perm, rr), sh = __shfl_sync(0xffffffffu, rel, rr);
+    if (d < 0) continue;
+    const double* src = smem + rr * kLiftStage;
+    double* dst = a.J + (size_t)d * row_len;
+    for (int c = lane; c < row_len; c += 32) {
+      double v;
+      if (c < 84) v = src[c];
+      else if (c < 84 + 21 * a.W) { const int b = (c - 84) / 21 - sh; v = (b >= 0 && b < 4) ? src[84 + 21 * b + (c - 84) % 21] : 0.0; }
+      else v = src[168 + (c - 84 - 21 * a.W)];
+      dst[c] = v;
+    }
   }
 }
 
@@ -1157,6 +1172,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_imu_split<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kPosSplitStride * 8);
   cudaFuncSetAttribute(k_static_rs_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
+  cudaFuncSetAttribute(k_lifting_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kLiftStage * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
     int per_sm = 0;
@@ -1483,8 +1499,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
       na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
       if (g.kind == KTK_LIFTING_RS) {
-        const long long threads = (long long)g.n * (30 + 7 * na.W);
-        k_lifting_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_vt.p);
+        k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
       } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);

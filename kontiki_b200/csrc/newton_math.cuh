@@ -14,6 +14,7 @@
 // step q0 * a1 (Sophus SE3::operator*=), every composed rotation is re-normalised.
 #pragma once
 #include "spline_math.cuh"
+#include "split_math.cuh"      // se3_body_twist (analytic lifting rows)
 
 namespace kb {
 
@@ -311,7 +312,8 @@ KB_HD int newton_rs_row(const SplineConst& sp, const CameraConst& cam, const dou
 // ---- LiftingRsCameraMeasurement (measurements/lifting_rscamera_measurement.h:21-56, :98-118) ---------------------------------------------
 // The static projection with the observation evaluated at the LIFTED time t_obs = t0_obs + time_offset + vt * readout, vt in [0, 1] a
 // parameter block of the measurement; 3 residuals weight * [uv - y ; rows (vt - vt_orig)].  Same forward-mode machinery as the Newton
-// rows (one direction per thread, hoisted pair logs and landmark record), no iteration.  Directions:
+// rows (one direction at a time, hoisted pair logs and landmark record), no iteration.  The product kernel runs the CLOSED FORM further down
+// (lifting_rs_row_analytic); this forward-mode version is the independent cross-check of the host-compiled test harness.  Directions:
 //   [0, 28) reference-window knots | [28, 28 + 7 W) observation-span knots | 28 + 7 W: vt | 29 + 7 W: rho | anything else: values only
 // Packed row (include/kontiki_b200.h): [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles.
 struct LiftingRow { double y[2], dy[2], dvt; };
@@ -401,6 +403,96 @@ KB_HD int lifting_rs_row(const SplineConst& sp, const CameraConst& cam, const do
     const int stride = dir < 28 + 7 * W ? 7 : 1;
     J[off] = j[0]; J[off + stride] = j[1]; J[off + 2 * stride] = j[2];
   }
+  return 0;
+}
+
+// ---- LiftingRs rows in CLOSED FORM (one thread per row, the static kernel's machinery with three residual rows) ------------------------------
+// Everything but the d/d vt column is the static row evaluated at the lifted time: with the corrector C (3 x 3, identity without the loss)
+//   d r / d Xc = C [:, 0:2] (-weight) d y / d Xc          (3 x 3; the timing residual does not see the point)
+// runs through the same reference-window product and the same reverse sweep (pose_backward<3>).  The row-time column uses the body twist
+// (v_b, w_b) of the spline at t_obs:  d Xobs / d t = -w_b x Xobs - rho v_b   (Xobs = R^T (X - rho p)),  so
+//   d r / d vt = (d r / d Xc) R_ct (d Xobs / d t) readout + C [:, 2] weight rows.
+// Outputs: r (3), Jref [4][3][7] (84), Jobs [4][3][7] (84: the ACTIVE window, first knot *i0_obs), Jvt (3), Jrho (3).
+KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                  const double* obs_uv, double obs_t0, double ref_t0, double vt, double weight, double huber_c,
+                                  double* r, double* Jref, double* Jobs, double* Jvt, double* Jrho, int* i0_ref, int* i0_obs) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const double t_obs = add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(vt, cam.readout));
+  int io; double uo;
+  if (locate_in_segments(nseg, s0, s1, t_obs, sp.t0, sp.dt, io, uo) < 0) return kStatusRange;
+  if (io < 0 || io + 3 >= sp.n_knots) return kStatusRange;
+  *i0_ref = (int)rec[7]; *i0_obs = io;
+  if (*i0_ref < 0) return kStatusRange;
+  const Basis bs = cumulative_basis(uo, sp.dt);
+  const double* k0 = knots + (size_t)io * kKnotStride;
+  const double* p1 = pairs + (size_t)(io + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  Pose P;
+  pose_forward(k0, p1, p2, p3, bs, P);
+  V3 vb, wb, dvb;
+  se3_body_twist(p1, p2, p3, bs, vb, wb, dvb);
+  const V3 X = v3(rec[0], rec[1], rec[2]), dXr = v3(rec[3], rec[4], rec[5]);
+  const double rho = rec[6];
+  const M3 Rct = load_m3(cam.Rct);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  const V3 Xobs = mul_t(P.R, X - rho * P.p);
+  const V3 Xc = Rct * Xobs + rho * pct;
+  double y0, y1;
+  Mr<2> Jp0;
+  camera_project_jac(cam, Xc, y0, y1, Jp0);
+  const double rows = (double)cam.rows;
+  const double r0 = weight * (obs_uv[0] - y0), r1 = weight * (obs_uv[1] - y1), r2 = weight * (rows * (vt - obs_uv[1] / rows));
+  double C[9] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0}, rs = 1.0;
+  if (huber_c > 0.0) {
+    const HuberScale h = huber_scale(huber_c, r0 * r0 + r1 * r1 + r2 * r2);
+    const double rr[3] = {r0, r1, r2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) C[3 * i + j] = h.sqrt_rho1 * ((i == j ? 1.0 : 0.0) - h.alpha_sq_norm * rr[i] * rr[j]);
+    rs = h.residual_scaling;
+  }
+  r[0] = rs * r0; r[1] = rs * r1; r[2] = rs * r2;
+  Mr<3> Jp;                                       // d r / d Xc, corrected
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Jp.a[3 * i + c] = -weight * (C[3 * i] * Jp0.a[c] + C[3 * i + 1] * Jp0.a[3 + c]);
+  const Mr<3> Go = rmul(Jp, Rct);                 // d r / d Xobs
+  const Mr<3> GX = rmul_nt(Go, P.R);              // d r / d X
+  const V3 dXc = Rct * mul_t(P.R, dXr - P.p) + pct;
+  const V3 dXobs_dt = (-1.0) * cross(wb, Xobs) - rho * vb;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Jrho[i] = Jp.a[3 * i] * dXc.x + Jp.a[3 * i + 1] * dXc.y + Jp.a[3 * i + 2] * dXc.z;
+    Jvt[i] = cam.readout * (Go.a[3 * i] * dXobs_dt.x + Go.a[3 * i + 1] * dXobs_dt.y + Go.a[3 * i + 2] * dXobs_dt.z) + C[3 * i + 2] * (weight * rows);
+  }
+  // reference-window blocks: GX (3x3) * dX/dknot_k (3x7)
+  const double* dXk = rec + kRefDOff;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int c = 0; c < 7; ++c)
+        Jref[21 * k + 7 * i + c] = GX.a[3 * i] * dXk[21 * k + c] + GX.a[3 * i + 1] * dXk[21 * k + 7 + c] + GX.a[3 * i + 2] * dXk[21 * k + 14 + c];
+  pose_backward<3>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, Jobs);
+  return 0;
+}
+// ... packed into the C ABI's row [ref 4 x (3x7) | obs W x (3x7) | vt 3 | rho 3] (the blocks of the span outside the active window are zero)
+KB_HD int lifting_rs_row_packed(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                const double* obs_uv, double obs_t0, double ref_t0, double vt, int kbase, int W, double weight, double huber_c,
+                                double* r, double* J) {
+  double Jref[84], Jobs[84], Jvt[3], Jrho[3];
+  int ir, io;
+  const int st = lifting_rs_row_analytic(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, vt, weight, huber_c, r, Jref, Jobs, Jvt, Jrho, &ir, &io);
+  if (st != 0) return st;
+  if (io < kbase || io + 4 > kbase + W) return kStatusRange;
+  for (int c = 0; c < 84; ++c) J[c] = Jref[c];
+  for (int c = 0; c < 21 * W; ++c) J[84 + c] = 0.0;
+  for (int c = 0; c < 84; ++c) J[84 + 21 * (io - kbase) + c] = Jobs[c];
+  for (int c = 0; c < 3; ++c) { J[84 + 21 * W + c] = Jvt[c]; J[87 + 21 * W + c] = Jrho[c]; }
   return 0;
 }
 

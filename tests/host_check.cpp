@@ -104,6 +104,8 @@ void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const doub
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }
 }
+static int g_lifting_analytic = 0;      // 0: forward-mode directions (k_lifting_rs_fwd), 1: closed form (k_lifting_rs)
+void hc_set_lifting_analytic(int on) { g_lifting_analytic = on; }
 // LiftingRsCameraMeasurement rows: what k_landmark_ref + k_lifting_rs do.  J: n x (90 + 21 W) packed [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3].
 void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
                    double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8,
@@ -130,8 +132,12 @@ void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const dou
     status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
     if (status[i] != 0) continue;
     const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
-    status[i] = lifting_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
-                               r + 3 * i, J + (size_t)row_len * i);
+    if (g_lifting_analytic)
+      status[i] = lifting_rs_row_packed(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
+                                        r + 3 * i, J + (size_t)row_len * i);
+    else
+      status[i] = lifting_rs_row(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
+                                 r + 3 * i, J + (size_t)row_len * i);
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }
 }

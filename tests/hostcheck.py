@@ -102,9 +102,11 @@ def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
     return dict(r=r, J=J, i0_ref=ir, i0_obs=kb, W=W, iterations=it, status=st)
 
 
-def lifting_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, vt=None, w=None, huber_c=None):
-    """LiftingRsCameraMeasurement rows; J (n, 90 + 21 W) packed [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3], kbase = first knot of the span."""
+def lifting_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, vt=None, w=None, huber_c=None, analytic=True):
+    """LiftingRsCameraMeasurement rows; J (n, 90 + 21 W) packed [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3], kbase = first knot of the span.
+    analytic=True: the closed-form rows (what k_lifting_rs runs); False: the forward-mode directions (k_lifting_rs_fwd)."""
     _set_camera_model(cam)
+    lib().hc_set_lifting_analytic(int(analytic))
     k8, pairs = prepass(knots7)
     obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
     obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)

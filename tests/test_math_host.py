@@ -323,6 +323,9 @@ def test_lifting_rs_rows_match_oracle(atan, robust):
         o = kto.lifting_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, *args, vt=vt, weight=s["weight"], jac_mode=2, cap=24)
         c = np.full(n, 2.0) if robust else None
         h = hc.lifting_rs(knots, dt, 0.0, cam, *args, vt=vt, w=s["weight"], huber_c=c)
+        hf = hc.lifting_rs(knots, dt, 0.0, cam, *args, vt=vt, w=s["weight"], huber_c=c, analytic=False)
+        # the closed-form rows and the forward-mode rows are the same rows
+        assert (hf["status"] == 0).all() and np.abs(hf["r"] - h["r"]).max() < parity.TOL * 1e3 and parity.rel_err(hf["J"][:, None], h["J"][:, None]) < parity.TOL
         assert (h["status"] == 0).all() and (h["i0_ref"] == o["i0_ref_a"]).all()
         Js, Jvt, Jrho = parity.scatter_lifting(h["J"], h["i0_ref"], h["i0_obs"], o["ids_a"], h["W"])
         if not robust:
