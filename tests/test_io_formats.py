@@ -88,7 +88,7 @@ def test_two_objects_in_one_container(tmp_path):
     root = io._NpzGroup(store, "")
     io.save_structure(root, landmarks)
     io.save_trajectory(root, _trajectories()[3])
-    _, lm2, _ = io.load_structure(root)
+    views2, lm2, _ = io.load_structure(root)      # the views own the observations (as in the reference): keep them
     _same_structure(landmarks, lm2)
     assert isinstance(io.load_trajectory(root), SplitTrajectory)
 

@@ -119,6 +119,9 @@ def test_imu_measurements(make):
         assert np.allclose(e1, g.w - g.measure(traj), atol=1e-12)
 
 
+_KEEP_VIEWS = []
+
+
 def _small_sfm(traj, camera, n_lm=8, n_views=6, seed=3):
     from kontiki_b200 import synthetic as syn
     s = syn.make_static_rs(traj.control_points, traj.dt, n_lm, obs_per_landmark=n_views - 1, t0=traj.t0, seed=seed, noise_px=0.0, rows=camera.rows,
@@ -135,6 +138,7 @@ def _small_sfm(traj, camera, n_lm=8, n_views=6, seed=3):
             v = views.setdefault(s["obs_t0"][i], sfm.View(len(views), s["obs_t0"][i]))
             v.create_observation(L, s["obs_uv"][i])
         landmarks.append(L)
+    _KEEP_VIEWS.append(views)            # a View owns its observations (view.h:30-33): dropping the views would empty the landmarks
     return landmarks
 
 
