@@ -40,11 +40,24 @@ class _Sensor:
                                 self.relative_position_locked, self.time_offset_locked)
 
 
-class BasicImu(_Sensor):
+class _Imu(_Sensor):
+    """python/src/kontiki/sensors/imu_helper.h: every IMU exposes accelerometer(trajectory, t) / gyroscope(trajectory, t) -- the model value that
+    the measurement classes compare against (sensors/imu.h:32-45), evaluated by the CUDA path like measurement.measure()."""
+
+    def gyroscope(self, trajectory, t):
+        from .measurements import GyroscopeMeasurement
+        return GyroscopeMeasurement(self, t, np.zeros(3)).measure(trajectory)
+
+    def accelerometer(self, trajectory, t):
+        from .measurements import AccelerometerMeasurement
+        return AccelerometerMeasurement(self, t, np.zeros(3)).measure(trajectory)
+
+
+class BasicImu(_Imu):
     """sensors/basic_imu.h:26-33."""
 
 
-class ConstantBiasImu(_Sensor):
+class ConstantBiasImu(_Imu):
     """sensors/constant_bias_imu.h: BasicImu + constant accelerometer / gyroscope biases (both locked by default, :83-97)."""
 
     def __init__(self, accelerometer_bias=(0, 0, 0), gyroscope_bias=(0, 0, 0)):
