@@ -165,3 +165,21 @@ def test_sensor_defaults_and_relative_pose():                      # sensors.h:9
         X = np.array([0.5, -1.0, 2.0])
         np.testing.assert_allclose(s.from_trajectory(X), [1.5, 3.0, 1.0], atol=1e-15)
         np.testing.assert_allclose(s.to_trajectory(s.from_trajectory(X)), X, atol=1e-15)
+
+
+def test_camera_project_unproject_match_the_oracle():             # test_cameras.py:32-37 on the Python classes, and against the restated reference
+    from oracle import kto
+    import fixtures_ref as fx
+    rng = np.random.default_rng(5)
+    K = np.array([[900.0, 0, 960], [0, 900, 540], [0, 0, 1]])
+    cams = [(PinholeCamera(fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT, K), kto.Camera(fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT, K=K)),
+            (AtanCamera(fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT, fx.ATAN_K, fx.ATAN_WC, fx.ATAN_GAMMA),
+             kto.Camera(fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT, K=fx.ATAN_K, wc=fx.ATAN_WC, gamma=fx.ATAN_GAMMA))]
+    for cam, ocam in cams:
+        assert (cam.rows, cam.cols, cam.readout) == (fx.IMAGE_ROWS, fx.IMAGE_COLS, fx.CAMERA_READOUT)
+        for _ in range(25):
+            y = np.array([rng.uniform(0, cam.cols), rng.uniform(0, cam.rows)])
+            X = cam.unproject(y) * rng.uniform(0.01, 10)
+            np.testing.assert_almost_equal(cam.project(X), y)
+            np.testing.assert_allclose(cam.unproject(y), kto.camera_unproject(ocam, y), rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(cam.project(X), kto.camera_project(ocam, X)[0], rtol=1e-12, atol=1e-9)
