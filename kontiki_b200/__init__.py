@@ -8,5 +8,5 @@ from ._lib import Problem, KontikiError  # noqa: F401
 
 __version__ = "0.1.0"
 
-from . import io, measurements, sensors, sfm, trajectories  # noqa: F401,E402
+from . import io, measurements, sensors, sfm, trajectories, utils  # noqa: F401,E402
 from .estimator import CallbackReturnType, IterationSummary, Summary, TerminationType, TrajectoryEstimator  # noqa: F401,E402

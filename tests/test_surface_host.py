@@ -183,3 +183,21 @@ def test_camera_project_unproject_match_the_oracle():             # test_cameras
             np.testing.assert_almost_equal(cam.project(X), y)
             np.testing.assert_allclose(cam.unproject(y), kto.camera_unproject(ocam, y), rtol=1e-12, atol=1e-12)
             np.testing.assert_allclose(cam.project(X), kto.camera_project(ocam, X)[0], rtol=1e-12, atol=1e-9)
+
+
+def test_safe_time_helpers():                                      # python/kontiki/utils.py, used throughout the reference's tests
+    from kontiki_b200.utils import safe_time, safe_time_span
+    traj, _, _ = _random_spline(UniformR3SplineTrajectory, np.random.default_rng(7))
+    t1, t2 = traj.valid_time
+    assert t1 < safe_time(traj) < t2
+    a, b = safe_time_span(traj, 0.5 * (t2 - t1))
+    assert a >= t1 and b <= t2 and abs((b - a) - 0.5 * (t2 - t1)) < 1e-12
+    with pytest.raises(ValueError):
+        safe_time_span(traj, 2.0 * (t2 - t1))
+    assert safe_time_span(traj, 2.0 * (t2 - t1), allow_shorter=True) == (t1, t2)
+
+    class Unbounded:
+        valid_time = (-np.inf, np.inf)
+    assert np.isfinite(safe_time(Unbounded())) and safe_time_span(Unbounded(), 3.0)[1] - safe_time_span(Unbounded(), 3.0)[0] == 3.0
+    with pytest.raises(ValueError):
+        safe_time(UniformR3SplineTrajectory())                     # empty spline: no valid time
