@@ -477,6 +477,50 @@ def test_camera_jacobian_vs_numdiff_se3():
 
 
 @pytest.mark.parametrize("name", ["se3", "split"])
+def test_orientation_known_answer_and_jacobian_vs_numdiff(name):
+    """OrientationMeasurement (orientation_measurement.h:27-31): the residual is Eigen's angularDistance -- the rotation angle between the
+    measured and the trajectory's orientation, whatever the sign or scale of the measured quaternion -- and the multipass autodiff of the
+    restated residual agrees with central differences of its double path."""
+    k = fx.smooth_se3_knots(40, 0.1)
+    traj = kto.Traj(kto.SE3, 0.1, 0.0, k) if name == "se3" else kto.Traj(kto.SPLIT, 0.1, 0.0, k[:, 4:7].copy(), 0.1, 0.0, k[:, 0:4].copy())
+    t = np.array([1.2345])
+    q = kto.traj_evaluate(traj, t, 0xff)["orientation"][0]                      # x, y, z, w
+    ang = 0.7
+    ax = np.array([0.3, -0.5, 0.8]); ax /= np.linalg.norm(ax)
+    dq = np.array([*(np.sin(ang / 2) * ax), np.cos(ang / 2)])
+    x1, y1, z1, w1 = q; x2, y2, z2, w2 = dq
+    qm = np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2,
+                   w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+    for scale in (1.0, -1.0, 3.0):                                               # q and -q are the same rotation; the distance is scale invariant
+        res = kto.imu_residuals(traj, kto.Sensor(), 3, t, (scale * qm)[None, :], jac_mode=2)
+        assert abs(res["r"][0, 0] - ang) < 1e-12
+    res = kto.imu_residuals(traj, kto.Sensor(), 3, t, qm[None, :], jac_mode=2)
+    if name == "se3":
+        i0 = res["i0_a"][0]
+        knots = k.copy()
+
+        def f(kn):
+            kk = knots.copy(); kk[i0:i0 + 4] = kn
+            return kto.imu_residuals(kto.Traj(kto.SE3, 0.1, 0.0, kk), kto.Sensor(), 3, t, qm[None, :], jac_mode=0)["r"][0]
+        Jn = _numdiff(f, knots[i0:i0 + 4])
+        Ja = np.concatenate([res["Ja"][0, j] for j in range(4)], axis=1)
+        assert_allclose(Ja, Jn, atol=2e-6 * np.abs(Ja).max())
+        assert not Ja[:, [4, 5, 6, 11, 12, 13]].any()                              # the angle does not see the translations
+    else:
+        i0 = res["i0_b"][0]
+        quats = k[:, 0:4].copy()
+
+        def f(qn):
+            qq = quats.copy(); qq[i0:i0 + 4] = qn
+            return kto.imu_residuals(kto.Traj(kto.SPLIT, 0.1, 0.0, k[:, 4:7].copy(), 0.1, 0.0, qq), kto.Sensor(), 3, t, qm[None, :], jac_mode=0)["r"][0]
+        Jn = _numdiff(f, quats[i0:i0 + 4], h=1e-7)
+        Jb = np.concatenate([res["Jb"][0, j] for j in range(4)], axis=1)
+        # logq throws for |q| off the unit sphere by more than 1e-5 (quaternion_math.h:19-23): the step stays far inside
+        assert_allclose(Jb, Jn, atol=2e-5 * np.abs(Jb).max())
+        assert not res["Ja"].any()
+
+
+@pytest.mark.parametrize("name", ["se3", "split"])
 def test_lifting_jacobian_vs_numdiff(name):
     """LiftingRsCameraMeasurement: the multipass autodiff of the restated residual (3 rows; blocks [knots | camera | vt | rho]) against central
     differences of its double path, at a displaced row time."""
