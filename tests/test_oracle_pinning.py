@@ -477,6 +477,36 @@ def test_camera_jacobian_vs_numdiff_se3():
 
 
 @pytest.mark.parametrize("name", ["se3", "split"])
+def test_position_known_answer_and_jacobian_vs_numdiff(name):
+    """PositionMeasurement (position_measurement.h:24-31): r = p - trajectory.Position(t); autodiff vs central differences."""
+    k = fx.smooth_se3_knots(40, 0.1)
+    traj = kto.Traj(kto.SE3, 0.1, 0.0, k) if name == "se3" else kto.Traj(kto.SPLIT, 0.1, 0.0, k[:, 4:7].copy(), 0.1, 0.0, k[:, 0:4].copy())
+    t = np.array([2.3456])
+    pos = kto.traj_evaluate(traj, t, 0xff)["position"][0]
+    y = pos + np.array([0.5, -0.25, 2.0])
+    res = kto.imu_residuals(traj, kto.Sensor(), 2, t, y[None, :], jac_mode=2)
+    assert_allclose(res["r"][0], [0.5, -0.25, 2.0], atol=1e-12)
+    i0 = res["i0_a"][0]
+    if name == "se3":
+        def f(kn):
+            kk = k.copy(); kk[i0:i0 + 4] = kn
+            return kto.imu_residuals(kto.Traj(kto.SE3, 0.1, 0.0, kk), kto.Sensor(), 2, t, y[None, :], jac_mode=0)["r"][0]
+        Jn = _numdiff(f, k[i0:i0 + 4])
+        Ja = np.concatenate([res["Ja"][0, j] for j in range(4)], axis=1)
+        assert_allclose(Ja, Jn, atol=2e-6 * np.abs(Ja).max())
+    else:
+        vecs = k[:, 4:7].copy()
+
+        def f(vn):
+            vv = vecs.copy(); vv[i0:i0 + 4] = vn
+            return kto.imu_residuals(kto.Traj(kto.SPLIT, 0.1, 0.0, vv, 0.1, 0.0, k[:, 0:4].copy()), kto.Sensor(), 2, t, y[None, :], jac_mode=0)["r"][0]
+        Jn = _numdiff(f, vecs[i0:i0 + 4])
+        Ja = np.concatenate([res["Ja"][0, j] for j in range(4)], axis=1)
+        assert_allclose(Ja, Jn, atol=1e-8)                                          # linear in the R3 knots: minus the basis weights
+        assert not res["Jb"].any()
+
+
+@pytest.mark.parametrize("name", ["se3", "split"])
 def test_orientation_known_answer_and_jacobian_vs_numdiff(name):
     """OrientationMeasurement (orientation_measurement.h:27-31): the residual is Eigen's angularDistance -- the rotation angle between the
     measured and the trajectory's orientation, whatever the sign or scale of the measured quaternion -- and the multipass autodiff of the
