@@ -95,3 +95,37 @@ def test_structure_static_rs_matches_oracle(dt):
     assert (ids == o["ids_a"]).all()
     assert (nids == (o["ids_a"] >= 0).sum(1)).all()
     assert len(set(nids.tolist())) > 1        # merged and split segment cases both occur
+
+
+def test_structure_of_the_added_measurement_kinds_matches_oracle():
+    """Host-only handles answer the structure queries of every kind: OrientationMeasurement / PositionMeasurement carry the 4 knots of their
+    segment (orientation_measurement.h:66, position_measurement.h:66), LiftingRs / NewtonRs the two camera spans; row and residual sizes."""
+    dt, n_knots = 0.05, 120
+    knots = syn.smooth_se3_knots(n_knots, dt)
+    traj = kto.Traj(kto.SE3, dt, 0.0, knots)
+    rng = np.random.default_rng(2)
+    t = rng.uniform(0.1, dt * (n_knots - 3) - 0.1, 50)
+    p = _lib.Problem(-1)
+    p.set_se3_spline(dt, 0.0, n_knots)
+    go = p.add_orientation(t, np.tile([0.0, 0.0, 0.0, 1.0], (50, 1)))
+    gp = p.add_position(t, np.zeros((50, 3)))
+    o = kto.imu_residuals(traj, kto.Sensor(), 0, t, np.zeros((50, 3)), jac_mode=0)
+    for g, kind, row in ((go, _lib.ORIENTATION, 28), (gp, _lib.POSITION, 84)):
+        ids, nids = p.get_structure(g, cap=4)
+        assert (ids == o["ids_a"]).all() and (nids == 4).all()
+        assert p.group_kind(g) == kind and p.group_row_size(g) == row
+    cam = syn.make_static_rs(knots, dt, 30, obs_per_landmark=5, seed=9)
+    ccam = _lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"])
+    args = (cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"])
+    gl, gn = p.add_lifting_rs(ccam, *args), p.add_newton_rs(ccam, *args)
+    oc = kto.static_rs_residuals(traj, kto.Camera(cam["rows"], cam["cols"], cam["readout"], K=cam["K"]), *args, cam["rho"], jac_mode=0, cap=24)
+    for g in (gl, gn):
+        ids, _ = p.get_structure(g, cap=24)
+        assert (ids == oc["ids_a"]).all()
+    W = (p.group_row_size(gn) - 58) // 14
+    assert p.group_kind(gl) == _lib.LIFTING_RS and p.group_row_size(gl) == 90 + 21 * W and W >= 4
+    with pytest.raises(_lib.KontikiError) as e:
+        p.evaluate(knots, cam["rho"])
+    assert e.value.code == _lib.ECUDA
+    with pytest.raises(ValueError):
+        p.set_group_vt(gn, np.zeros(len(cam["lm_idx"])))          # only LiftingRs groups have row-time parameters
