@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--workload", default="H1")
     ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel-tuning runs (tools/ab.sh): device-resident leg and per-kernel times only; no e2e leg, no CPU baseline")
     ap.add_argument("--camera-method", default="static", choices=["static", "newton", "lifting"],
                     help="StaticRsCameraMeasurement (the BASELINE.json workloads) or NewtonRsCameraMeasurement rows (SURVEY.md 8f-3) for the camera group")
     ap.add_argument("--camera-model", default="pinhole", choices=["pinhole", "atan"], help="PinholeCamera (BASELINE.json) or AtanCamera")
@@ -316,7 +317,7 @@ def main():
         p.synchronize()
         prof = {name: p.read_profile(g) for name, g in groups.items()}
         p.set_profiling(False)
-        t_end = time.time() + 1.0                                 # keep the GPU under load long enough for a few clock samples
+        t_end = time.time() + (0.3 if a.quick else 1.0)                                 # keep the GPU under load long enough for a few clock samples
         while time.time() < t_end:
             step_device()
             torch.cuda.synchronize()
@@ -330,7 +331,7 @@ def main():
     h_knots = torch.from_numpy(knots_flat.copy()).pin_memory()
     h_rho = torch.from_numpy(rho).pin_memory() if rho is not None else None
     h_outs, d2h = [], 0
-    for g in range(p.num_groups):
+    for g in range(0 if a.quick else p.num_groups):
         n, cam = p.group_size(g), p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS, _lib.LIFTING_RS)
         o = dict(r=torch.empty((n, 2 if p.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS) else 3), dtype=torch.float64).pin_memory(),
                  J=torch.empty((n, p.group_row_size(g)), dtype=torch.float64).pin_memory(),
@@ -345,11 +346,11 @@ def main():
         h_outs.append({k: v.numpy() for k, v in o.items()})
         keep.append(o)
     h2d = h_knots.numel() * 8 + (h_rho.numel() * 8 if h_rho is not None else 0)
-    e2e_steps = max(3, min(a.steps, 10))
+    e2e_steps = 0 if a.quick else max(3, min(a.steps, 10))
     def step_host():
         p.evaluate_flat(h_knots.numpy(), None if h_rho is None else h_rho.numpy(), flags, h_outs)
 
-    for _ in range(2):
+    for _ in range(0 if a.quick else 2):
         step_host()
     barrier()
     t0 = time.perf_counter()
@@ -405,7 +406,7 @@ def main():
                          # dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
                          "fp64": ({"flop_per_row": 4013, "achieved_tflops": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
                                    "frac": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
-    if not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline and not a.quick and world == 1:
         base, _, _ = cpu_baseline(cfg, a.cpu_sample)
         line["cpu_baseline"] = base
     sys.stdout.flush()

@@ -407,7 +407,13 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
       else if (lane == 12) prefetch_l2(a.perm + i2);
     }
   }
-  const CamIn cur = cam_load(a, i);
+  CamIn cur = cam_load(a, i);
+#ifdef KTK_ABL_FIXED_IO      // timing ablations only (tools/ablate.sh): wrong results on purpose
+  if (cur.io >= 0) cur.io = 100;
+#endif
+#ifdef KTK_ABL_NOGATHER
+  if (cur.ridx >= 0) cur.ridx = 0;
+#endif
   const double ouv[2] = {cur.u, cur.v};
   warp_gather_records<kRefStride, kCamDevStride, kRefInRowDev>(wbase, a.recs, cur.ridx, lane);
   ObsForward f; f.status = kStatusRange; f.io = -1;
@@ -422,8 +428,15 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
     int ir = -1, io = -1;
     ObsAdjoint adj;
     const int st = static_rs_row_ref_half(a.cam, f, row + kRefInRowDev, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io, adj);
+#ifdef KTK_ST_EARLY      // experiment: the finished reference-window half leaves while the observation-window half is computed
+    if (st == 0 && wantJ && !(a.flags & KTK_EVAL_DEVICE_ORDER)) { fence_async_smem(); bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamHalf * 8)); }
+#endif
     if (st == 0) {
+#ifndef KTK_ABL_NOBACK
       static_rs_row_obs_half(a.knots, a.pairs, f, adj, row + kCamHalf);
+#else
+      for (int c = 0; c < 18; ++c) row[kCamHalf + c] = adj.Gp.a[c % 6] + adj.GpR.a[c % 6] * adj.Gth.a[c % 6];
+#endif
       row[112] = jrho[0]; row[113] = jrho[1];
     } else {
       atomicMin(a.err, st);
@@ -438,15 +451,35 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
   fence_async_smem();
   __syncwarp();
   if (!wantJ) return;
+#ifdef KTK_ABL_NOSTORE
+  if (cur.u != -12345.678) return;
+#endif
   if (a.flags & KTK_EVAL_DEVICE_ORDER) {
     if (lane == 0) {
       bulk_store(a.J + (size_t)tile * 32 * kCamRow, wbase, (unsigned)(min(32, a.n - tile * 32) * kCamRow * 8));
       bulk_store_wait_read();
     }
-  } else if (cur.perm >= 0) {                            // caller order: one 912-B bulk store per row, to the row's insertion index
-    bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
+  }
+#if defined(KTK_ST_STG)        // experiment: cooperative 16-byte stores instead of TMA
+  else { warp_scatter_rows<kCamRow, kCamDevStride, kCamRow>(wbase, a.J, cur.perm, lane); }
+#elif defined(KTK_ST_EARLY)
+  else if (cur.perm >= 0) {
+    if (row[0] == row[0]) bulk_store(a.J + (size_t)cur.perm * kCamRow + kCamHalf, row + kCamHalf, (unsigned)((kCamRow - kCamHalf) * 8));
+    else bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));      // NaN row (error path): nothing was sent early
     bulk_store_wait_read();
   }
+#else
+  else if (cur.perm >= 0) {                            // caller order: one 912-B bulk store per row, to the row's insertion index
+#ifdef KTK_ST_L2DST
+    bulk_store(a.J + (size_t)(cur.perm & 32767) * kCamRow, row, (unsigned)(kCamRow * 8));
+#else
+    bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
+#endif
+#ifndef KTK_ST_NOWAIT
+    bulk_store_wait_read();
+#endif
+  }
+#endif
 }
 
 // =====================================================================================================================

@@ -166,12 +166,15 @@ struct AngleCoefs { double sa, cb, cc, c2, c3; };
 #define KB_SMALL_XQ 0.5
 // Large-angle branch (closed forms), out of line on the device: spline increments B_j omega_j are small, so the Taylor branch is the
 // hot one and is kept straight-line; inlining sincos and three divisions into every exp_part costs branch-merge moves and code size.
+// The cold function returns ONE coefficient in registers (which: 0 sa, 1 cb, 2 cc, 3 c2, 4 c3): a struct passed by reference lives on
+// the stack, and ptxas stored it there BEFORE the never-taken branch -- 60 STL per 32-row tile, 120 MB of local-memory write traffic per
+// H1 evaluation on the SM -> L2 path (ncu l1tex__t_sectors_pipe_lsu_mem_local_op_st, profiles/README.md r2a).
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
 inline
 #endif
-void angle_coefs_large(double x, bool need_q, AngleCoefs& c) {
+double angle_coef_large(double x, int which) {
   const double phi = sqrt(x);
   double s, co;
 #if defined(__CUDA_ARCH__)
@@ -180,13 +183,11 @@ void angle_coefs_large(double x, bool need_q, AngleCoefs& c) {
   s = sin(phi); co = cos(phi);
 #endif
   const double ix = 1.0 / x;
-  c.sa = s / phi;
-  c.cb = (1.0 - co) * ix;
-  c.cc = (phi - s) * ix / phi;
-  if (need_q && !(x < KB_SMALL_XQ)) {
-    c.c2 = (x + 2.0 * co - 2.0) * 0.5 * ix * ix;
-    c.c3 = (2.0 * phi - 3.0 * s + phi * co) * 0.5 * ix * ix / phi;
-  }
+  if (which == 0) return s / phi;
+  if (which == 1) return (1.0 - co) * ix;
+  if (which == 2) return (phi - s) * ix / phi;
+  if (which == 3) return (x + 2.0 * co - 2.0) * 0.5 * ix * ix;
+  return (2.0 * phi - 3.0 * s + phi * co) * 0.5 * ix * ix / phi;
 }
 KB_HD AngleCoefs angle_coefs(double x, bool need_q) {
   AngleCoefs c;
@@ -198,7 +199,10 @@ KB_HD AngleCoefs angle_coefs(double x, bool need_q) {
     c.c2 = KB_TC(18) + x * (KB_TC(19) + x * (KB_TC(20) + x * (KB_TC(21) + x * (KB_TC(22) + x * (KB_TC(23) + x * KB_TC(24))))));
     c.c3 = KB_TC(25) + x * (KB_TC(26) + x * (KB_TC(27) + x * (KB_TC(28) + x * (KB_TC(29) + x * (KB_TC(30) + x * KB_TC(31))))));
   }
-  if (!(x < KB_SMALL_X)) angle_coefs_large(x, need_q, c);
+  if (!(x < KB_SMALL_X)) {
+    c.sa = angle_coef_large(x, 0); c.cb = angle_coef_large(x, 1); c.cc = angle_coef_large(x, 2);
+    if (need_q && !(x < KB_SMALL_XQ)) { c.c2 = angle_coef_large(x, 3); c.c3 = angle_coef_large(x, 4); }
+  }
   return c; }
 
 // Q block of the SE(3) left Jacobian J_l([rho; phi]) = [[Jl(phi), Ql],[0, Jl(phi)]] (Barfoot 2017, eq. 7.86),

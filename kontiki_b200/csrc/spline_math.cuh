@@ -497,18 +497,24 @@ struct HuberScale { double sqrt_rho1, residual_scaling, alpha_sq_norm, rho0; };
 // The linear region (|r| > a) is out of line on the device (KB_COLD): two square roots and three divisions with their slow-path
 // subroutines do not belong in the straight-line code of every row; in the quadratic region rho' = 1, rho'' = 0 and every factor is
 // exactly 1 or 0.
-KB_COLD void huber_scale_linear_region(double a, double s, HuberScale& h) {
+// One factor per call, returned in registers (which: 0 sqrt_rho1, 1 residual_scaling, 2 alpha_sq_norm, 3 rho0): see angle_coef_large.
+KB_COLD double huber_linear_region(double a, double s, int which) {
   const double b = a * a;
   const double rr = sqrt(s);
-  h.rho0 = 2.0 * a * rr - b;
+  if (which == 3) return 2.0 * a * rr - b;
   const double rho1 = fmax(2.2250738585072014e-308, a / rr), rho2 = -rho1 / (2.0 * s);
-  h.sqrt_rho1 = sqrt(rho1);
-  if (s == 0.0 || rho2 <= 0.0) { h.residual_scaling = h.sqrt_rho1; h.alpha_sq_norm = 0.0; }
-  else { const double Dd = 1.0 + 2.0 * s * rho2 / rho1; const double alpha = 1.0 - sqrt(Dd); h.residual_scaling = h.sqrt_rho1 / (1.0 - alpha); h.alpha_sq_norm = alpha / s; }
+  const double sqrt_rho1 = sqrt(rho1);
+  if (which == 0) return sqrt_rho1;
+  if (s == 0.0 || rho2 <= 0.0) return which == 1 ? sqrt_rho1 : 0.0;
+  const double Dd = 1.0 + 2.0 * s * rho2 / rho1; const double alpha = 1.0 - sqrt(Dd);
+  return which == 1 ? sqrt_rho1 / (1.0 - alpha) : alpha / s;
 }
 KB_HD HuberScale huber_scale(double a, double s) {
   HuberScale h; h.rho0 = s; h.sqrt_rho1 = 1.0; h.residual_scaling = 1.0; h.alpha_sq_norm = 0.0;
-  if (s > a * a) huber_scale_linear_region(a, s, h);
+  if (s > a * a) {
+    h.sqrt_rho1 = huber_linear_region(a, s, 0); h.residual_scaling = huber_linear_region(a, s, 1);
+    h.alpha_sq_norm = huber_linear_region(a, s, 2); h.rho0 = huber_linear_region(a, s, 3);
+  }
   return h;
 }
 

@@ -1,0 +1,207 @@
+"""The oracle (oracle/*.hpp, dual-number autodiff in doubles) against an INDEPENDENT 60-digit transcription of the reference
+(tests/mp_reference.py: mpmath, written from the reference headers + Sophus' published formulas, Jacobians by central differences,
+SE3 poses additionally by 4x4 expm / logm).  Inputs: the reference's own fixture knots (python/tests/conftest.py:32-45, :52-67, :83-105,
+restated in tests/fixtures_ref.py) and random non-degenerate trajectories.  Values AND Jacobians, SE3 + SO3 + R3 (split),
+gyroscope / accelerometer / static-RS camera.  CPU only."""
+import mpmath as mp
+import numpy as np
+import pytest
+
+import fixtures_ref as fx
+import mp_reference as mr
+from oracle import kto
+
+VAL_TOL = 5e-13      # values: double rounding of the oracle against a 60-digit number
+JAC_TOL = 2e-11      # Jacobians: relative to the largest entry of the block row (north_star gate is 1e-9)
+
+
+def f(x):
+    return np.array([[float(v) for v in row] for row in x]) if isinstance(x[0], (list, tuple)) else np.array([float(v) for v in x])
+
+
+def rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def random_se3_knots(n, seed, step=0.35):
+    """Random walk on SE3 with relative rotations up to ~step rad and unit-scale translations: far from every small-angle / pi branch."""
+    rng = np.random.default_rng(seed)
+    q, p, out = np.array([0.1, -0.2, 0.3, 0.9]), np.zeros(3), []
+    q /= np.linalg.norm(q)
+    for _ in range(n):
+        out.append(np.concatenate([q, p]))
+        q = fx.qmul_xyzw(q, fx.so3_exp_xyzw(rng.normal(0, step, 3)))
+        q /= np.linalg.norm(q)
+        p = p + rng.normal(0, 1.0, 3)
+    return np.array(out)
+
+
+SE3_CASES = {"fixture": (fx.SE3_KNOTS, fx.SE3_DT, fx.SE3_T0), "random": (random_se3_knots(9, 7), 0.37, -0.4)}
+
+
+def times_in(knots, dt, t0, k, seed):
+    rng = np.random.default_rng(seed)
+    return t0 + rng.uniform(0.02, len(knots) - 3.02, k) * dt
+
+
+@pytest.mark.parametrize("case", list(SE3_CASES))
+def test_se3_values_three_routes(case):
+    knots, dt, t0 = SE3_CASES[case]
+    traj = kto.Traj(kto.SE3, dt, t0, knots)
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    ts = times_in(knots, dt, t0, 6, 1)
+    o = kto.traj_evaluate(traj, ts, kto.EvalPosition | kto.EvalVelocity | kto.EvalAcceleration | kto.EvalOrientation | kto.EvalAngularVelocity)
+    for k, t in enumerate(ts):
+        e = mt.evaluate(mp.mpf(float(t)), acc=True)
+        assert rel(o["position"][k], f(e["position"])) < VAL_TOL
+        assert rel(o["velocity"][k], f(e["velocity"])) < VAL_TOL
+        assert rel(o["acceleration"][k], f(e["acceleration"])) < VAL_TOL
+        assert rel(o["angular_velocity"][k], f(e["angular_velocity"])) < VAL_TOL
+        assert rel(o["orientation"][k], f(e["orientation"])) < VAL_TOL
+        # second independent route: 4x4 matrix exponential / logarithm, no closed forms at all
+        P = mr.se3_pose_expm(mt.knots, mt.t0, mt.dt, mp.mpf(float(t)))
+        Pm = np.array([[float(P[i, j]) for j in range(4)] for i in range(4)])
+        assert rel(o["position"][k], Pm[:3, 3]) < VAL_TOL
+        assert rel(fx.rot_xyzw(o["orientation"][k]), Pm[:3, :3]) < VAL_TOL
+        # velocity / acceleration are the time derivatives of that pose (what the reference's xfail-ed test wanted to check)
+        h = mp.mpf("1e-20")
+        Pp = mr.se3_pose_expm(mt.knots, mt.t0, mt.dt, mp.mpf(float(t)) + h)
+        Pn = mr.se3_pose_expm(mt.knots, mt.t0, mt.dt, mp.mpf(float(t)) - h)
+        vel = [float((Pp[i, 3] - Pn[i, 3]) / (2 * h)) for i in range(3)]
+        acc = [float((Pp[i, 3] - 2 * P[i, 3] + Pn[i, 3]) / (h * h)) for i in range(3)]
+        assert rel(o["velocity"][k], vel) < VAL_TOL
+        assert rel(o["acceleration"][k], acc) < 1e-10
+
+
+@pytest.mark.parametrize("which", [0, 1])
+@pytest.mark.parametrize("case", list(SE3_CASES))
+def test_se3_imu_residual_and_jacobian(case, which):
+    knots, dt, t0 = SE3_CASES[case]
+    rng = np.random.default_rng(11 + which)
+    ts = times_in(knots, dt, t0, 3, 2 + which)
+    y = rng.uniform(-1, 1, (len(ts), 3))
+    w = rng.uniform(0.5, 2.0, len(ts))
+    for compat in ([False, True] if which == 1 else [False]):
+        o = kto.imu_residuals(kto.Traj(kto.SE3, dt, t0, knots, compat_zero_dB=compat), kto.Sensor(), which, ts, y, w, jac_mode=2)
+        mt = mr.Trajectory("se3", dt, t0, knots=knots, compat_zero_dB=compat)
+        for k, t in enumerate(ts):
+            fun = lambda: mr.imu_residual(mt, which, float(t), y[k], float(w[k]))
+            assert rel(o["r"][k], f(fun())) < VAL_TOL * 10
+            i0 = int(o["i0_a"][k])
+            assert i0 == mt.evaluate(mp.mpf(float(t)))["i0"]
+            J = np.array(mr.jacobian(fun, [(mt.knots, i0 + b, c) for b in range(4) for c in range(7)])).reshape(3, 4, 7).transpose(1, 0, 2)
+            assert (o["ids_a"][k, :4] == i0 + np.arange(4)).all()
+            assert rel(o["Ja"][k, :4], J) < JAC_TOL, (case, which, compat, k)
+            # a knot outside the window does not enter
+            other = [(mt.knots, b, 0) for b in range(len(knots)) if b < i0 or b > i0 + 3][:1]
+            if other:
+                assert np.abs(np.array(mr.jacobian(fun, other))).max() == 0.0
+
+
+def camera_case(knots, dt, t0, seed, q_ct=(0, 0, 0, 1), p_ct=(0, 0, 0), time_offset=0.0):
+    """A few reference / observation pairs whose projections land near the image (rho and uv from a forward simulation in doubles)."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[900., 0, 960], [0, 900., 540], [0, 0, 1]])
+    cam = dict(K=K, rows=1080, readout=0.026, q_ct=q_ct, p_ct=p_ct, time_offset=time_offset)
+    lo, hi = t0 + 0.3 * dt, t0 + (len(knots) - 3.3) * dt - 0.03
+    n = 3
+    ref_t0 = rng.uniform(lo, hi, n)
+    obs_t0 = np.clip(ref_t0 + rng.uniform(-0.8, 0.8, n) * dt, lo, hi)
+    ref_uv = rng.uniform([100, 100], [1800, 1000], (n, 2))
+    obs_uv = rng.uniform([100, 100], [1800, 1000], (n, 2))
+    rho = rng.uniform(0.05, 0.6, n)
+    return cam, obs_uv, obs_t0, ref_uv, ref_t0, rho
+
+
+@pytest.mark.parametrize("relpose", [False, True])
+@pytest.mark.parametrize("case", list(SE3_CASES))
+def test_se3_static_rs_residual_and_jacobian(case, relpose):
+    knots, dt, t0 = SE3_CASES[case]
+    kw = dict(q_ct=tuple(np.array([0.1, -0.05, 0.2, 0.97]) / np.linalg.norm([0.1, -0.05, 0.2, 0.97])), p_ct=(0.05, -0.02, 0.1), time_offset=0.004) if relpose else {}
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = camera_case(knots, dt, t0, 5, **kw)
+    n = len(rho)
+    ocam = kto.Camera(cam["rows"], 1920, cam["readout"], K=cam["K"], **({} if not relpose else dict(q_ct=kw["q_ct"], p_ct=kw["p_ct"], time_offset=kw["time_offset"])))
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, t0, knots), ocam, obs_uv, obs_t0, ref_uv, ref_t0, np.arange(n, dtype=np.int32), rho, jac_mode=2, cap=24)
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    for k in range(n):
+        box = [[mp.mpf(float(rho[k]))]]
+        fun = lambda: mr.static_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])[0]
+        r, ir, io = mr.static_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])
+        assert rel(o["r"][k], f(r)) < 1e-12                                   # |r| ~ 1e3 px: 1e-12 relative = 1e-9 px
+        assert (int(o["i0_ref_a"][k]), int(o["i0_obs_a"][k])) == (ir, io)
+        ids = [int(v) for v in o["ids_a"][k] if v >= 0]
+        J = np.array(mr.jacobian(fun, [(mt.knots, b, c) for b in ids for c in range(7)])).reshape(2, len(ids), 7).transpose(1, 0, 2)
+        assert rel(o["Ja"][k, :len(ids)], J) < JAC_TOL, (case, relpose, k)
+        assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(2)) < JAC_TOL
+        # every knot the residual depends on is in the structural list
+        rest = [(mt.knots, b, c) for b in range(len(knots)) if b not in ids for c in (0, 5)]
+        if rest:
+            assert np.abs(np.array(mr.jacobian(fun, rest))).max() == 0.0
+
+
+def split_fixture():
+    """conftest.py:107-113: the split fixture is the R3 and the SO3 fixture side by side."""
+    return fx.R3_KNOTS, fx.R3_DT, fx.R3_T0, fx.SO3_KNOTS, fx.SO3_DT, fx.SO3_T0
+
+
+def test_split_values_and_so3_known_answer():
+    r3, dta, t0a, so3, dtb, t0b = split_fixture()
+    for t in (2.0, 3.3, 4.9):
+        e = mr.so3_spline([mr.mpv(k) for k in so3], mp.mpf(t0b), mp.mpf(dtb), mp.mpf(t))
+        # conftest.py:52-81 + test_general.py:52-62: constant 10 deg/s about (1,0,1)/sqrt2
+        assert rel(f(e["angular_velocity"]), fx.SO3_RATE * fx.SO3_AXIS) < 1e-5      # the knots sample the motion; the cumulative spline of a one-parameter subgroup reproduces it
+        o = kto.traj_evaluate(kto.Traj(kto.SO3, knots_b=so3, dt_b=dtb, t0_b=t0b), [t], kto.EvalOrientation | kto.EvalAngularVelocity)
+        assert rel(o["orientation"][0], f(e["orientation"])) < VAL_TOL and rel(o["angular_velocity"][0], f(e["angular_velocity"])) < VAL_TOL
+        a = mr.r3_spline([mr.mpv(k) for k in r3], mp.mpf(t0a), mp.mpf(dta), mp.mpf(t + 1.5))
+        o = kto.traj_evaluate(kto.Traj(kto.R3, dta, t0a, r3), [t + 1.5], kto.EvalPosition | kto.EvalVelocity | kto.EvalAcceleration)
+        for key in ("position", "velocity", "acceleration"):
+            assert rel(o[key][0], f(a[key])) < VAL_TOL
+
+
+def random_split(n, seed):
+    se3 = random_se3_knots(n, seed, step=0.3)
+    return se3[:, 4:].copy(), se3[:, :4].copy()
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_split_imu_residual_and_jacobian(which):
+    r3, so3 = random_split(9, 21)
+    dt, t0 = 0.41, 0.3
+    traj = kto.Traj(kto.SPLIT, dt, t0, r3, dt, t0, so3)
+    mt = mr.Trajectory("split", dt, t0, r3=r3, so3=so3)
+    rng = np.random.default_rng(3)
+    ts = t0 + rng.uniform(0.1, 5.9, 3) * dt
+    y, w = rng.uniform(-1, 1, (3, 3)), rng.uniform(0.5, 2, 3)
+    o = kto.imu_residuals(traj, kto.Sensor(), which, ts, y, w, jac_mode=2)
+    for k, t in enumerate(ts):
+        fun = lambda: mr.imu_residual(mt, which, float(t), y[k], float(w[k]))
+        assert rel(o["r"][k], f(fun())) < VAL_TOL * 10
+        ia, ib = int(o["i0_a"][k]), int(o["i0_b"][k])
+        Jb = np.array(mr.jacobian(fun, [(mt.so3, ib + b, c) for b in range(4) for c in range(4)])).reshape(3, 4, 4).transpose(1, 0, 2)
+        assert rel(o["Jb"][k, :4], Jb) < JAC_TOL
+        Ja = np.array(mr.jacobian(fun, [(mt.r3, ia + b, c) for b in range(4) for c in range(3)])).reshape(3, 4, 3).transpose(1, 0, 2)
+        if which == 0:
+            assert np.abs(Ja).max() == 0.0 and np.abs(o["Ja"][k]).max() == 0.0      # R3 blocks structurally present, identically zero
+        else:
+            assert rel(o["Ja"][k, :4], Ja) < JAC_TOL
+
+
+def test_split_static_rs_residual_and_jacobian():
+    r3, so3 = random_split(10, 33)
+    dt, t0 = 0.23, -0.1
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = camera_case(r3, dt, t0, 8)
+    n = len(rho)
+    ocam = kto.Camera(cam["rows"], 1920, cam["readout"], K=cam["K"])
+    o = kto.static_rs_residuals(kto.Traj(kto.SPLIT, dt, t0, r3, dt, t0, so3), ocam, obs_uv, obs_t0, ref_uv, ref_t0, np.arange(n, dtype=np.int32), rho, jac_mode=2, cap=24)
+    mt = mr.Trajectory("split", dt, t0, r3=r3, so3=so3)
+    for k in range(n):
+        box = [[mp.mpf(float(rho[k]))]]
+        fun = lambda: mr.static_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])[0]
+        assert rel(o["r"][k], f(fun())) < 1e-12
+        ida = [int(v) for v in o["ids_a"][k] if v >= 0]
+        idb = [int(v) for v in o["ids_b"][k] if v >= 0]
+        Ja = np.array(mr.jacobian(fun, [(mt.r3, b, c) for b in ida for c in range(3)])).reshape(2, len(ida), 3).transpose(1, 0, 2)
+        Jb = np.array(mr.jacobian(fun, [(mt.so3, b, c) for b in idb for c in range(4)])).reshape(2, len(idb), 4).transpose(1, 0, 2)
+        assert rel(o["Ja"][k, :len(ida)], Ja) < JAC_TOL and rel(o["Jb"][k, :len(idb)], Jb) < JAC_TOL
+        assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(2)) < JAC_TOL
