@@ -4,6 +4,9 @@ import numpy as np
 from oracle import kto
 
 TOL = 1e-9   # BASELINE.json north_star: "within 1e-9 relative on fp64 residuals/Jacobians"
+# Camera residuals r = weight (uv - y_hat) are differences of pixel coordinates of size ~1e3, so the comparison is ABSOLUTE in pixels:
+# 1e-9 px = 5e-13 of the pixel scale (gate what is achieved, ~1e-10 px; round 1 gated 1e-6 px).
+CAM_R_TOL = 1e-9
 
 
 def rel_err(a, b):

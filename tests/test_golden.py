@@ -61,7 +61,7 @@ def test_host_math_matches_golden_camera(method, model):
     h = fn(G["cam_knots"], float(G["cam_dt"][0]), 0.0, cam, G["cam_obs_uv"], G["cam_obs_t0"], G["cam_ref_uv"], G["cam_ref_t0"], G["cam_lm_idx"], G["cam_rho"])
     tag = f"cam_{method}_{model}"
     assert (h["status"] == 0).all() and (h["i0_ref"] == G[tag + "_i0_ref"]).all() and (h["i0_obs"] == G[tag + "_i0_obs"]).all()
-    assert np.abs(h["r"] - G[tag + "_r"]).max() < parity.TOL * 1e3
+    assert np.abs(h["r"] - G[tag + "_r"]).max() < parity.CAM_R_TOL
     Js, Jrho = parity.scatter_cam(h["J"], h["i0_ref"], h["i0_obs"], G[tag + "_ids"], h.get("W", 4))
     assert parity.rel_err(Js, G[tag + "_Ja"]) < parity.TOL and parity.rel_err(Jrho, G[tag + "_Jrho"]) < parity.TOL
 
@@ -101,7 +101,7 @@ def test_cuda_path_matches_golden():
         ids, _ = p.get_structure(g, cap=16)
         assert (ids == G[tag + "_ids"]).all()
         Js = p.expand_static_rs(g, ids, o["J"], o["i0"], o["i0_b"])
-        assert np.abs(o["r"] - G[tag + "_r"]).max() < parity.TOL * 1e3
+        assert np.abs(o["r"] - G[tag + "_r"]).max() < parity.CAM_R_TOL
         assert parity.rel_err(Js, G[tag + "_Ja"]) < parity.TOL and parity.rel_err(o["J"][:, -2:], G[tag + "_Jrho"]) < parity.TOL
 
 
@@ -173,7 +173,7 @@ def test_host_math_matches_golden_lifting():
     h = hc.lifting_rs(G["cam_knots"], float(G["cam_dt"][0]), 0.0, cam, *_lifting_args(), vt=G2["lift_vt"])
     assert (h["status"] == 0).all() and (h["i0_ref"] == G2["lift_i0_ref"]).all()
     Js, Jvt, Jrho = parity.scatter_lifting(h["J"], h["i0_ref"], h["i0_obs"], G2["lift_ids"], h["W"])
-    assert np.abs(h["r"] - G2["lift_r"]).max() < parity.TOL * 1e3
+    assert np.abs(h["r"] - G2["lift_r"]).max() < parity.CAM_R_TOL
     assert parity.rel_err(Js, G2["lift_Ja"]) < parity.TOL and parity.rel_err(Jvt, G2["lift_Jvt"]) < parity.TOL and parity.rel_err(Jrho, G2["lift_Jrho"]) < parity.TOL
 
 
@@ -190,6 +190,6 @@ def test_cuda_path_matches_golden_lifting():
     ids, _ = p.get_structure(g, cap=16)
     assert (ids == G2["lift_ids"]).all()
     Js = p.expand_static_rs(g, ids, o["J"], o["i0"], o["i0_b"])
-    assert np.abs(o["r"] - G2["lift_r"]).max() < parity.TOL * 1e3
+    assert np.abs(o["r"] - G2["lift_r"]).max() < parity.CAM_R_TOL
     assert parity.rel_err(Js, G2["lift_Ja"]) < parity.TOL and parity.rel_err(o["J"][:, -6:-3], G2["lift_Jvt"]) < parity.TOL
     assert parity.rel_err(o["J"][:, -3:], G2["lift_Jrho"]) < parity.TOL

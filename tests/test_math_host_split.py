@@ -61,7 +61,7 @@ def test_split_camera_rows_match_oracle():
     idx = h["idx"]
     assert (idx[:, 0] == o["i0_ref_a"]).all() and (idx[:, 1] == o["i0_obs_a"]).all()
     assert (idx[:, 2] == o["i0_ref_b"]).all() and (idx[:, 3] == o["i0_obs_b"]).all()
-    assert np.abs(h["r"] - o["r"]).max() < parity.TOL * 1e3
+    assert np.abs(h["r"] - o["r"]).max() < parity.CAM_R_TOL
     Ja, Jb = np.zeros_like(o["Ja"]), np.zeros_like(o["Jb"])
     for i in range(n):
         pa = {int(kk): j for j, kk in enumerate(o["ids_a"][i]) if kk >= 0}
