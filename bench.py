@@ -162,6 +162,41 @@ def optimised_cpu(cfg, sample, repeats=3):
                     "compiled for the host, OpenMP over rows; landmark side per measurement; best of %d passes over the same sample" % repeats}
 
 
+
+# ---- parity gate (SURVEY.md 8d "Parity gate run with every benchmark"): the oracle as the CHECKER, after the timed region ------
+def parity_gate(cfg, p, groups, keep, rho, flags, device_order, n_sample=2048, seed=7):
+    """Samples n_sample rows per group from the DEVICE-RESIDENT outputs of the benchmark's last step and compares them with the CPU oracle
+    (oracle/gate.py): indices bit-exact, residuals / Jacobians relative to the row's largest entry (camera residuals: absolute, in pixels)."""
+    import torch
+    from oracle import gate
+    from kontiki_b200 import _lib
+    out = {"rows_checked": 0, "idx_exact": True, "max_rel_r": 0.0, "max_rel_J": 0.0, "max_abs_r_cam_px": 0.0, "tol": gate.TOL, "rows_per_group": n_sample,
+           "checker": "oracle/ (restated reference, dual-number autodiff; pinned by the 60-digit transcription tests/mp_reference.py)"}
+    rng = np.random.default_rng(seed)
+    for name, g in groups.items():
+        if name == "cam" and CAMERA["method"] != "static":
+            out["camera"] = "not gated here (NewtonRs / LiftingRs rows: tests/test_gpu_parity.py)"
+            continue
+        r_t, J_t, idx_t = keep[g]
+        n = p.group_size(g)
+        sel = np.sort(rng.permutation(n)[:min(n, n_sample)])
+        pos = sel
+        if device_order:
+            inv = np.empty(n, np.int64)
+            inv[p.get_row_order(g)] = np.arange(n)
+            pos = inv[sel]
+        tpos = torch.from_numpy(np.ascontiguousarray(pos)).to(r_t.device)
+        res = gate.check_rows(cfg, name, sel, r_t.index_select(0, tpos).cpu().numpy(), J_t.index_select(0, tpos).cpu().numpy(),
+                              [t.index_select(0, tpos).cpu().numpy() for t in idx_t], rho, robust=bool(flags & _lib.EVAL_ROBUST),
+                              atan=ATAN if CAMERA["model"] == "atan" else None, nthreads=NTHREADS)
+        out["idx_exact"] &= res["idx_exact"]
+        for k_out, k_in in (("max_rel_r", "rel_r"), ("max_rel_J", "rel_J"), ("max_abs_r_cam_px", "abs_r_cam_px")):
+            out[k_out] = max(out[k_out], res[k_in])
+        out["rows_checked"] += len(sel)
+    out["pass"] = bool(out["idx_exact"] and out["max_rel_r"] <= gate.TOL and out["max_rel_J"] <= gate.TOL and out["max_abs_r_cam_px"] <= gate.CAM_R_TOL)
+    return out
+
+
 # ---- clocks --------------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -406,6 +441,8 @@ def main():
                          # dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
                          "fp64": ({"flop_per_row": 4013, "achieved_tflops": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
                                    "frac": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
+    if not a.quick:      # rank 0 checks its own shard (every rank's shard has the same construction)
+        line["parity"] = parity_gate(cfg, p, groups, keep, rho, dev_flags, a.row_order == "device")
     if not a.no_cpu_baseline and not a.quick and world == 1:
         base, _, _ = cpu_baseline(cfg, a.cpu_sample)
         line["cpu_baseline"] = base

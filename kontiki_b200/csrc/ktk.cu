@@ -1056,6 +1056,7 @@ int upload_group(ktk_problem* p, Group& g) {
     for (int64_t i = 0; i < g.n; ++i) key[i] = knot_floor(g.t[i] + g.sensor.time_offset, kt0, kdt);
   }
   g.perm = sort_perm(key);
+  g.d_lm_sorted.n = 0; g.d_lm_caller.n = 0;      // per-row landmark indices cached by the Gauss-Newton products: the row order just changed
   int st;
   cudaStream_t s = p->stream;
   if ((st = g.d_perm.upload(g.perm, s))) return st;
@@ -1341,6 +1342,10 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   cudaStream_t s = p->stream;
   const int blocks = (int)((g.n + 127) / 128);
   if (g.kind == KTK_POSITION || g.kind == KTK_ORIENTATION) return KTK_OK;           // no sensor
+  // a group whose sensor blocks are all locked has no sensor columns: the reference hands Ceres NULL Jacobians for constant blocks
+  // (sensors.h:147-164).  The flag is per evaluation, not per group: an unlocked IMU next to a locked camera is the ordinary case.
+  if (g.sensor.q_locked && g.sensor.p_locked && g.sensor.time_offset_locked) return KTK_OK;
+  if (!is_camera(g.kind) && g.sensor.time_offset_locked) return KTK_OK;              // an IMU's relative pose is not applied (TODO.md:6): only the time offset has columns
   if (is_span_camera(g.kind)) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRs / LiftingRs camera measurements are not built");
   if (g.kind == KTK_STATIC_RS) {
     if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");

@@ -154,6 +154,7 @@ class TrajectoryEstimator:
         self._measurements = []
         self._callbacks = []
         self._problem = None
+        self._built_for = None
 
     trajectory = property(lambda self: self._trajectory)
     # what the CUDA path evaluates: the trajectory itself, or a lone R3 / SO3 spline with its constant, locked companion (trajectories.evaluable)
@@ -167,9 +168,15 @@ class TrajectoryEstimator:
         if isinstance(m, StaticRsCameraMeasurement):
             ref = m.observation.landmark.reference
             t1, t2 = sorted([ref.view.t0, m.observation.view.t0])
+            if not m.camera.time_offset_locked:      # static_rscamera_measurement.h:153-157: the first span moves earlier, the second later
+                t1, t2 = t1 - m.camera.max_time_offset, t2 + m.camera.max_time_offset
             spans = [(t1 - 1e-3, t1 + m.camera.readout + 1e-3), (t2 - 1e-3, t2 + m.camera.readout + 1e-3)]
         else:
-            spans = [(m.t, m.t)]
+            sensor = getattr(m, "imu", None)
+            if sensor is not None and not sensor.time_offset_locked:      # gyroscope_measurement.h:88-91
+                spans = [(m.t - sensor.max_time_offset, m.t + sensor.max_time_offset)]
+            else:
+                spans = [(m.t, m.t)]
         for a, b in spans:
             if a < tr.min_time or b >= tr.max_time:
                 raise ValueError("Time span out of range for trajectory")
@@ -180,9 +187,18 @@ class TrajectoryEstimator:
         self._callbacks.append((callback, bool(update_state)))
 
     # ---- flattening ------------------------------------------------------------------------
+    def _traj_key(self):
+        tr = self._tr
+        spl = [tr] if isinstance(tr, UniformSE3SplineTrajectory) else [tr.R3_spline, tr.SO3_spline]
+        return tuple((s.dt, s.t0, len(s)) for s in spl)
+
     def _build(self):
-        if self._problem is not None:
+        if self._problem is not None and self._built_for == self._traj_key():
             return
+        if self._problem is not None:      # knots were appended (or the spline re-gridded) since the problem was flattened
+            self._problem.close()
+            self._problem = None
+        self._built_for = self._traj_key()
         p, _ = _problem_for(self._tr)
         p.close()
         p = _lib.Problem(self._device)
@@ -211,7 +227,7 @@ class TrajectoryEstimator:
                                     np.array([m.observation.landmark.reference.uv for m in ms]), [m.observation.landmark.reference.view.t0 for m in ms],
                                     lm, [m.weight for m in ms], [m.huber_c for m in ms])
                 self._groups.append(dict(g=g, kind="cam", rows=rows, lm=np.array(lm, np.int64), sensor=sensor, newton=kind is NewtonRsCameraMeasurement,
-                                         lifting=kind is LiftingRsCameraMeasurement, ms=ms))
+                                         lifting=kind is LiftingRsCameraMeasurement, ms=ms, huber=np.array([m.huber_c for m in ms], float)))
             elif kind is PositionMeasurement:
                 g = p.add_position([m.t for m in ms], np.array([m.p for m in ms]))
                 self._groups.append(dict(g=g, kind="pos", rows=rows, sensor=sensor, weight=np.ones(len(ms))))
@@ -463,9 +479,18 @@ class TrajectoryEstimator:
                 m.vt = v
 
     @staticmethod
-    def _cost(outs, groups, hubers):
-        """1/2 sum rho(|r|^2); with the corrector applied |r_corrected|^2 == rho(s) for Huber."""
-        return 0.5 * sum(float((outs[g["g"]]["r"] ** 2).sum()) for g in groups)
+    def _cost(outs, groups, robust=True):
+        """Ceres' cost 1/2 sum rho(s), s = |r|^2 per residual block.  The kernels return the CORRECTED residual r_c = sqrt(rho'(s)) r
+        (ceres::internal::Corrector; alpha = 0 for HuberLoss since rho'' <= 0), so |r_c|^2 = a sqrt(s) in the linear region and
+        rho(s) = 2 a sqrt(s) - a^2 = 2 |r_c|^2 - a^2 there (s > a^2  <=>  |r_c|^2 > a^2); rho(s) = s = |r_c|^2 in the quadratic region."""
+        total = 0.0
+        for g in groups:
+            s = (outs[g["g"]]["r"] ** 2).sum(1)
+            if robust and g["kind"] == "cam":
+                a2 = g["huber"] ** 2
+                s = np.where(s > a2, 2.0 * s - a2, s)
+            total += float(s.sum())
+        return 0.5 * total
 
     def solve(self, max_iterations=50, progress=True, num_threads=-1, linear_solver="auto"):
         """Levenberg-Marquardt on the GPU-evaluated residuals/Jacobians; returns a Summary (py_ceres.cc:15-58 fields).
@@ -507,7 +532,7 @@ class TrajectoryEstimator:
         t0 = time.perf_counter()
         outs = self.evaluate(jacobians=True)
         s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
-        cost = self._cost(outs, self._groups, None)
+        cost = self._cost(outs, self._groups)
         s.initial_cost = cost
         s.num_residuals = s.num_residuals_reduced = sum(outs[g["g"]]["r"].size for g in self._groups)
         radius, nu = 1e4, 2.0                               # Ceres defaults: initial_trust_region_radius 1e4
@@ -547,7 +572,7 @@ class TrajectoryEstimator:
             t0 = time.perf_counter()
             try:
                 outs_new = self.evaluate(jacobians=True)
-                cost_new = self._cost(outs_new, self._groups, None)
+                cost_new = self._cost(outs_new, self._groups)
             except ValueError:
                 cost_new, outs_new = np.inf, None
             s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
@@ -607,6 +632,9 @@ class TrajectoryEstimator:
         spl_b = tr.SO3_spline if split else None
         n_a, n_b, n_rho = len(spl_a), (len(spl_b) if split else 0), len(self._landmarks)
         ne = gn.DeviceNormalEquations(self._problem, split, n_a, n_b, n_rho, self._device)
+        for grp in self._groups:
+            if grp["kind"] == "cam":
+                ne.set_huber(grp["g"], grp["huber"])
         free = np.ones(ne.n_loc)
         da = 3 if split else 6
         if spl_a.locked:

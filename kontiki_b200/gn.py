@@ -45,6 +45,12 @@ class DeviceNormalEquations:
         self.problem_stream = torch.cuda.current_stream(self.dev)
         problem.set_stream(self.problem_stream.cuda_stream)
         self.free = torch.ones(self.n_loc, dtype=torch.float64, device=self.dev)      # 0 for constant (locked) parameters
+        self._huber_sq = {}
+
+    def set_huber(self, group, huber_c):
+        """Huber constants of a camera group (caller order), for the cost 1/2 sum rho(s); rows live in device order."""
+        order = self.p.get_row_order(group)
+        self._huber_sq[group] = torch.from_numpy(np.asarray(huber_c, np.float64)[order] ** 2).to(self.dev)
 
     # ---- parameter point ------------------------------------------------------------------------------------------------
     def set_point(self, knots_flat, rho, P_a, P_b):
@@ -58,7 +64,14 @@ class DeviceNormalEquations:
         """One batched residual + Jacobian evaluation; returns the cost 1/2 sum |r|^2 summed over ranks."""
         self.p.evaluate_device(self.knots.data_ptr(), self.rho.data_ptr() if self.n_rho else 0, self.n_rho, self.flags, self.outs)
         self.p.synchronize()
-        cost = sum((k[0] ** 2).sum() for k in self._keep) * 0.5 if self._keep else torch.zeros((), dtype=torch.float64, device=self.dev)
+        # Ceres' cost is 1/2 sum rho(s); the rows carry the corrected residual, |r_c|^2 = a sqrt(s) in Huber's linear region (estimator._cost)
+        cost = torch.zeros((), dtype=torch.float64, device=self.dev)
+        for g, k in enumerate(self._keep):
+            s = (k[0] ** 2).sum(1)
+            a2 = self._huber_sq.get(g)
+            if a2 is not None and (self.flags & _lib.EVAL_ROBUST):
+                s = torch.where(s > a2, 2.0 * s - a2, s)
+            cost = cost + 0.5 * s.sum()
         cost = cost.reshape(1).clone()
         d = _dist()
         if d is not None:

@@ -10,7 +10,8 @@ from .trajectories import SplitTrajectory, UniformSE3SplineTrajectory, evaluable
 def _problem_for(traj):
     """A ktk problem bound to `traj` and the knots argument for it."""
     traj = evaluable(traj)
-    p = _lib.Problem(0)
+    from . import trajectories as _tj
+    p = _lib.Problem(_tj.DEFAULT_DEVICE)
     if isinstance(traj, UniformSE3SplineTrajectory):
         traj._check()
         p.set_se3_spline(traj.dt, traj.t0, len(traj), traj.compat_zero_dB)

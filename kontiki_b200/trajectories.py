@@ -5,6 +5,15 @@ import numpy as np
 
 from . import _lib
 
+DEFAULT_DEVICE = 0           # CUDA device of the point queries below (estimators take their own `device`); see set_default_device()
+
+
+def set_default_device(device):
+    """Selects the GPU that trajectory / measurement point queries (position(t), m.error(traj), ...) run on."""
+    global DEFAULT_DEVICE
+    DEFAULT_DEVICE = int(device)
+
+
 _EPS_SOPHUS = 1e-10          # Sophus::Constants<double>::epsilon(), py_uniform_se3_spline_trajectory.cc:24-38
 _EPS_UNIT = 1e-5             # math/quaternion_math.h:11
 
@@ -38,11 +47,29 @@ def _quat_xyzw_to_rot(q):
 
 
 class _Trajectory:
-    """trajectory_helper.h:12-34."""
+    """trajectory_helper.h:12-34.  Every accessor also takes an ARRAY of times (one batched ktk_traj_evaluate; the reference's
+    accessors are scalar, so a scalar t returns exactly what the reference returns)."""
     _locked = False
 
     def _query(self, t):
         raise NotImplementedError
+
+    def _cached_problem(self, key, setup):
+        """One ktk problem per (trajectory shape, device), re-used by the point queries: creating a problem costs cudaMalloc + pinned
+        allocations, far more than the query."""
+        key = (DEFAULT_DEVICE,) + tuple(key)
+        cur = getattr(self, "_qp", None)
+        if cur is None or cur[0] != key:
+            if cur is not None:
+                cur[1].close()
+            p = _lib.Problem(DEFAULT_DEVICE)
+            setup(p)
+            self._qp = cur = (key, p)
+        return cur[1]
+
+    def evaluate_many(self, t):
+        """dict(position, velocity, acceleration, orientation (x,y,z,w), angular_velocity) at an array of times, one batched call."""
+        return self._query(np.atleast_1d(np.asarray(t, float)))
 
     def position(self, t):
         return self._query(t)["position"][0].copy()
@@ -178,15 +205,15 @@ class UniformSE3SplineTrajectory(_Spline):
 
     def _query(self, t):
         self._check()
-        p = _lib.Problem(0)
-        p.set_se3_spline(self._dt, self._t0, len(self._cp), self.compat_zero_dB)
-        return p.traj_evaluate(self._cp, [float(t)])
+        n, c = len(self._cp), self.compat_zero_dB
+        p = self._cached_problem(("se3", self._dt, self._t0, n, c), lambda q: q.set_se3_spline(self._dt, self._t0, n, c))
+        return p.traj_evaluate(self._cp, np.atleast_1d(np.asarray(t, float)))
 
     def evaluate(self, t):
         """(P, P', P'') as 4x4 matrices (py_uniform_se3_spline_trajectory.cc:53-60)."""
         self._check()
-        p = _lib.Problem(0)
-        p.set_se3_spline(self._dt, self._t0, len(self._cp), False)
+        n = len(self._cp)
+        p = self._cached_problem(("se3", self._dt, self._t0, n, False), lambda q: q.set_se3_spline(self._dt, self._t0, n, False))
         m = p.se3_evaluate_matrices(self._cp, [float(t)])[0]
         return m[0], m[1], m[2]
 
@@ -209,9 +236,8 @@ class UniformR3SplineTrajectory(_Spline):
         self._check()
         n = len(self._cp)
         ident = np.tile(np.array([0.0, 0, 0, 1]), (n, 1))           # uniform_r3_spline_trajectory.h:94-97: identity orientation
-        p = _lib.Problem(0)
-        p.set_split_spline(self._dt, self._t0, n, self._dt, self._t0, n)
-        return p.traj_evaluate((self._cp, ident), [float(t)])
+        p = self._cached_problem(("r3", self._dt, self._t0, n), lambda q: q.set_split_spline(self._dt, self._t0, n, self._dt, self._t0, n))
+        return p.traj_evaluate((self._cp, ident), np.atleast_1d(np.asarray(t, float)))
 
 
 class UniformSO3SplineTrajectory(_Spline):
@@ -235,9 +261,8 @@ class UniformSO3SplineTrajectory(_Spline):
     def _query(self, t):
         self._check()
         n = len(self._cp)
-        p = _lib.Problem(0)
-        p.set_split_spline(self._dt, self._t0, n, self._dt, self._t0, n)
-        return p.traj_evaluate((np.zeros((n, 3)), self._cp), [float(t)])     # uniform_so3_spline_trajectory.h:52-58: zero position
+        p = self._cached_problem(("so3", self._dt, self._t0, n), lambda q: q.set_split_spline(self._dt, self._t0, n, self._dt, self._t0, n))
+        return p.traj_evaluate((np.zeros((n, 3)), self._cp), np.atleast_1d(np.asarray(t, float)))     # uniform_so3_spline_trajectory.h:52-58: zero position
 
 
 class SplitTrajectory(_Trajectory):
@@ -275,12 +300,13 @@ class SplitTrajectory(_Trajectory):
     def _query(self, t):
         self.R3_spline._check()
         self.SO3_spline._check()
-        if not (self.min_time <= t < self.max_time):
+        t = np.atleast_1d(np.asarray(t, float))
+        if not ((self.min_time <= t) & (t < self.max_time)).all():
             raise ValueError(f"t={t} is out of range for the trajectory")
         r, s = self.R3_spline, self.SO3_spline
-        p = _lib.Problem(0)
-        p.set_split_spline(r.dt, r.t0, len(r), s.dt, s.t0, len(s))
-        return p.traj_evaluate((r.control_points, s.control_points), [float(t)])
+        key = ("split", r.dt, r.t0, len(r), s.dt, s.t0, len(s))
+        p = self._cached_problem(key, lambda q: q.set_split_spline(r.dt, r.t0, len(r), s.dt, s.t0, len(s)))
+        return p.traj_evaluate((r.control_points, s.control_points), t)
 
 
 class _LoneSplineView(SplitTrajectory):

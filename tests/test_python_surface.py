@@ -575,3 +575,88 @@ def test_lifting_rscamera_measurement_and_solve():
     assert summary.num_residuals == 3 * len(meas) and all(0.0 <= m.vt <= 1.0 for m in meas)
     assert summary.num_parameters_reduced == len(lms) + len(meas)
 
+
+
+# ---- round-2 fixes -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver", ["host_cholesky", "device_pcg"])
+def test_cost_is_half_sum_of_rho_with_outliers(solver):
+    """Ceres reports 1/2 sum rho(s), not 1/2 sum |r_corrected|^2: with gross outliers the two differ by up to a factor 2 per block."""
+    from oracle import kto
+    traj = smooth_se3(n=40, dt=0.1)
+    cam = PinholeCamera(1080, 1920, 0.026, np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]]))
+    lms = _small_sfm(traj, cam, n_lm=20, n_views=6, seed=9)
+    rng = np.random.default_rng(4)
+    est = kontiki.TrajectoryEstimator(traj)
+    ms = []
+    for L in lms:
+        for obs in L.observations:
+            if not obs.is_reference:
+                if rng.random() < 0.3:
+                    obs.uv = obs.uv + rng.normal(0, 30, 2)            # far outside the quadratic region of HuberLoss(5)
+                ms.append(StaticRsCameraMeasurement(cam, obs))
+                est.add_measurement(ms[-1])
+    s = est.solve(max_iterations=0, progress=False, linear_solver=solver)
+    expect, linear = 0.0, 0
+    for m in ms:
+        e = m.error(traj)                                             # uncorrected weight (uv - y_hat)
+        rho, _, _ = kto.huber_correct(m.huber_c, e)
+        expect += 0.5 * rho
+        linear += float(e @ e) > m.huber_c ** 2
+    assert linear > 10
+    assert abs(s.initial_cost - expect) < 1e-9 * expect
+
+
+@pytest.mark.parametrize("split", [False, True])
+def test_unlocked_bias_imu_next_to_a_locked_camera(split):
+    """The ordinary visual-inertial calibration case: IMU biases / time offset estimated, camera parameters locked (round 1 raised here)."""
+    from kontiki_b200.sensors import ConstantBiasImu
+    start, ms, lms = _vi_problem(split)
+    imu = ConstantBiasImu()
+    imu.gyroscope_bias_locked = imu.accelerometer_bias_locked = False
+    imu.time_offset_locked, imu.max_time_offset = False, 0.02
+    est = kontiki.TrajectoryEstimator(start)
+    lo, hi = start.min_time + 0.05, start.max_time - 0.05
+    n_imu = 0
+    for m in ms:
+        if isinstance(m, (GyroscopeMeasurement, AccelerometerMeasurement)):
+            if lo < m.t < hi:
+                est.add_measurement(type(m)(imu, m.t, m._x + (0.01 if isinstance(m, GyroscopeMeasurement) else -0.02)))
+                n_imu += 1
+        else:
+            est.add_measurement(m)
+    s = est.solve(max_iterations=15, progress=False)
+    assert n_imu > 100 and s.final_cost < 0.05 * s.initial_cost
+    assert np.allclose(imu.gyroscope_bias, 0.01, atol=2e-3) and np.allclose(imu.accelerometer_bias, -0.02, atol=2e-2)
+
+
+def test_appending_knots_between_solves_rebuilds_the_problem():
+    traj = smooth_se3(n=30)
+    imu = BasicImu()
+    est = kontiki.TrajectoryEstimator(traj)
+    for t in np.linspace(traj.min_time, traj.max_time - 1e-3, 40):
+        est.add_measurement(GyroscopeMeasurement(imu, t, np.array([0.3, 0.1, -0.2])))
+    s1 = est.solve(max_iterations=3, progress=False)
+    traj.extend_to(traj.max_time + 1.0, traj[len(traj) - 1])
+    s2 = est.solve(max_iterations=3, progress=False)
+    assert s2.num_parameters == s1.num_parameters + 7 * (len(traj) - 30) and np.isfinite(s2.final_cost)
+
+
+def test_vectorised_point_queries_match_scalar_ones():
+    for traj in (se3_fixture(), split_fixture()):
+        ts = np.linspace(traj.min_time + 0.01, traj.max_time - 0.01, 9)
+        many = traj.evaluate_many(ts)
+        for k, t in enumerate(ts):
+            assert np.array_equal(many["position"][k], traj.position(t)) and np.array_equal(many["angular_velocity"][k], traj.angular_velocity(t))
+
+
+def test_add_measurement_checks_the_widened_span_of_an_unlocked_time_offset():
+    """gyroscope_measurement.h:88-91: with the time offset unlocked the span checked is t +- max_time_offset."""
+    traj = smooth_se3(n=30)
+    imu = BasicImu()
+    imu.time_offset_locked, imu.max_time_offset = False, 0.05
+    est = kontiki.TrajectoryEstimator(traj)
+    est.add_measurement(GyroscopeMeasurement(imu, traj.min_time + 0.06, np.zeros(3)))
+    with pytest.raises(ValueError):
+        est.add_measurement(GyroscopeMeasurement(imu, traj.min_time + 0.01, np.zeros(3)))
+    with pytest.raises(ValueError):
+        est.add_measurement(GyroscopeMeasurement(imu, traj.max_time - 0.01, np.zeros(3)))
