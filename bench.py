@@ -34,12 +34,16 @@ UNIT = "measurements/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="H1")
     ap.add_argument("--cpu-sample", type=float, default=None, help="fraction of the workload the CPU baseline evaluates per step (default: sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): every rank evaluates its own full-size set of measurements, no data-path collective.  "
+                         "strong (BASELINE.json configs[3]/[4]): ONE problem, rows sharded over the ranks by kontiki_b200/sharding.py, knots and inverse depths "
+                         "replicated; a step = evaluation + J^T r + one (J^T J) v with the NCCL all-reduce of the parameter-sized vector")
     ap.add_argument("--quick", action="store_true", help="kernel-tuning runs (tools/ab.sh): device-resident leg and per-kernel times only; no e2e leg, no CPU baseline")
     ap.add_argument("--camera-method", default="static", choices=["static", "newton", "lifting"],
                     help="StaticRsCameraMeasurement (the BASELINE.json workloads) or NewtonRsCameraMeasurement rows (SURVEY.md 8f-3) for the camera group")
@@ -53,18 +57,20 @@ def parse():
 ATAN = dict(wc=(0.0029110778971412417, 0.0004189670467132041), gamma=0.8894355177968156)      # python/tests/fixtures/camera_fixtures.py:15-16
 
 
-def workload_config(name, cfg, row_order="caller", method="static", model="pinhole"):
+def workload_config(name, cfg, row_order="caller", method="static", model="pinhole", strong=False, world=1):
     from kontiki_b200 import synthetic as syn
     traj = "SplitTrajectory (UniformR3 + UniformSO3)" if cfg.get("split") else "UniformSE3SplineTrajectory"
     return {"workload": f"{name}: {traj} {len(cfg['knots'])} knots dt={cfg['dt']}, "
                         f"{len(cfg['gyro']['t']) if cfg['gyro'] else 0} gyro + {len(cfg['accel']['t']) if cfg['accel'] else 0} accel (BasicImu) + "
                         f"{len(cfg['cam']['lm_idx']) if cfg['cam'] else 0} {dict(newton='NewtonRsCamera', lifting='LiftingRsCamera').get(method, 'StaticRsCamera')} "
                         f"({'Atan' if model == 'atan' else 'Pinhole'}, {len(cfg['cam']['rho']) if cfg['cam'] else 0} landmarks)",
-            "measurements_per_step_per_gpu": syn.num_measurements(cfg),
-            "algorithmic_bytes_per_step_per_gpu": syn.algorithmic_bytes(cfg),
+            ("measurements_per_step_total" if strong else "measurements_per_step_per_gpu"): syn.num_measurements(cfg),
+            ("algorithmic_bytes_per_step_total" if strong else "algorithmic_bytes_per_step_per_gpu"): syn.algorithmic_bytes(cfg),
             "jacobian": "ambient (7 per SE3 knot; 3 + 4 per split knot), Huber corrector applied to camera rows",
             "l2": "per-step working set (outputs + records) >> 126 MB L2; no flush",
-            "sharding": "measurements sharded across ranks, knots replicated, no data-path collective",
+            "sharding": ("ONE problem: rows sharded over %d rank(s) (IMU rows by time range, camera rows by landmark), knots / inverse depths replicated; step = evaluation + "
+                         "J^T r + (J^T J) v, one NCCL all-reduce of the parameter vector per product" % world) if strong else
+                        "measurements sharded across ranks, knots replicated, no data-path collective",
             "row_order": row_order}
 
 
@@ -269,7 +275,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cfg = syn.make_config(a.workload)
-    if world > 1:      # every rank owns a different, equally sized shard of measurements (independent seeds), knots replicated
+    strong = a.scaling == "strong"
+    cfg_full = cfg
+    if strong:
+        from kontiki_b200 import sharding
+        cfg = sharding.shard_config(cfg_full, rank, world)      # this rank's rows of the ONE problem
+    if world > 1 and not strong:      # every rank owns a different, equally sized shard of measurements (independent seeds), knots replicated
         n_knots = len(cfg["knots"])
         if cfg["gyro"]:
             cfg["gyro"] = syn.make_imu(len(cfg["gyro"]["t"]), n_knots, cfg["dt"], seed=100 + rank)
@@ -321,7 +332,43 @@ def main():
 
     dev_flags = flags | (_lib.EVAL_DEVICE_ORDER if a.row_order == "device" else 0)
 
+    ne = None
+    if strong:
+        # the Levenberg-Marquardt linearisation on the device over the rows this rank holds (kontiki_b200/gn.py::DeviceSchurSolver, csrc/gn_device.cuh):
+        # landmark blocks, diagonal knot blocks, gradient, reduced right-hand side, and one implicit-Schur product S p.  The exchange between
+        # ranks is the all-reduce (NCCL, fp64 sum) of parameter-sized vectors: [c | g_rho | blocks | gradient] once, the reduced rhs once, S p once.
+        import ctypes as C
+        from kontiki_b200 import gn
+        split = bool(cfg.get("split"))
+        n_a, n_b = (len(cfg["r3"]), len(cfg["so3"])) if split else (len(cfg["knots"]), 0)
+        GN_RADIUS = 1e4
+
+        def make_ne(prob, c_):
+            torch.cuda.set_stream(stream)
+            hub = {g_: c_["cam"]["huber_c"] for g_ in range(prob.num_groups) if prob.group_kind(g_) == _lib.STATIC_RS}
+            e = gn.DeviceSchurSolver(prob, split, n_a, n_b, 0 if rho is None else len(rho), local_rank, hubers=hub)
+            e.set_point(knots_flat, rho)
+            e.evaluate()                  # first evaluation: builds the row lists (ktk_gn_prepare)
+            return e
+        ne = make_ne(p, cfg)
+        d_outs, keep = ne.outs, ne._keep
+        dev_flags = ne.flags
+
+        def gn_linearize(e):
+            e.linearize(GN_RADIUS)
+            e.p.gn_call("pcg_begin", C.c_double(GN_RADIUS), C.c_double(1e-6), C.c_int32(100))
+
+        def gn_product(e):
+            e.p.gn_call("product")
+            e._reduce("q_a", "q_b")
+            e.p.gn_call("pcg_update")
+
     def step_device():
+        if ne is not None:
+            ne.evaluate(cost=False)
+            gn_linearize(ne)
+            gn_product(ne)
+            return
         p.evaluate_device(d_knots.data_ptr(), d_rho.data_ptr() if d_rho is not None else 0, 0 if rho is None else len(rho), dev_flags, d_outs)
 
     def barrier():
@@ -334,33 +381,111 @@ def main():
     p.synchronize()
     barrier()
     l0 = p.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # (1) the timed region: EXACTLY K steps between two events on the launching stream (each evaluation = one CUDA-graph launch), barrier +
+    #     synchronize on both sides.  Nothing else runs on the host meanwhile: the nvidia-smi sampler (a fork per sample, and a driver query that
+    #     every rank issues at once) is started AFTER the second event -- round 1 ran it inside the region.
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    ev[0].record(stream)
+    for k in range(a.steps):
+        step_device()
+        ev[k + 1].record(stream)
+    barrier()
+    launches = p.launch_count - l0
+    ms_total = ev[0].elapsed_time(ev[-1])
+    per_step = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)])
     with ClockSampler(local_rank) as clocks:
-        # (1) the timed region: EXACTLY K steps between two events on the launching stream (each step = one CUDA-graph launch)
-        e0.record(stream)
-        for _ in range(a.steps):
+        # (2) the same steps again, the clocks sampled under this load: >= 200 steps and >= 0.5 s, one event pair per step (median / spread)
+        n_steady = max(200, a.steps)
+        sv = [torch.cuda.Event(enable_timing=True) for _ in range(n_steady + 1)]
+        t_end = time.time() + (0.3 if a.quick else 0.6)
+        sv[0].record(stream)
+        for k in range(n_steady):
             step_device()
-        e1.record(stream)
-        barrier()
-        launches = p.launch_count - l0
-        ms_total = e0.elapsed_time(e1)
-        # (2) the same K steps again with every kernel launch bracketed by CUDA events inside the library (plain stream
-        #     launches, no graph): per-kernel device time for the roofline of the dominant kernel
+            sv[k + 1].record(stream)
+        torch.cuda.synchronize()
+        steady = np.array([sv[k].elapsed_time(sv[k + 1]) for k in range(n_steady)])
+        while ne is None and time.time() < t_end:      # weak mode only: a time-based loop must not contain collectives (ranks would disagree on the count)
+            step_device()
+            torch.cuda.synchronize()
+        # (3) every kernel launch bracketed by CUDA events inside the library (plain stream launches, no graph): per-kernel device time for the
+        #     roofline of the dominant kernel
         p.set_profiling(True)
-        for _ in range(a.steps):
+        for _ in range(min(a.steps, 50)):
             step_device()
         p.synchronize()
         prof = {name: p.read_profile(g) for name, g in groups.items()}
         p.set_profiling(False)
-        t_end = time.time() + (0.3 if a.quick else 1.0)                                 # keep the GPU under load long enough for a few clock samples
-        while time.time() < t_end:
-            step_device()
-            torch.cuda.synchronize()
     ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    rank_ms = [ms.clone() for _ in range(world)]
     if dist is not None:
+        dist.all_gather(rank_ms, ms)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / a.steps
-    value = world * n_meas / (ms_step * 1e-3)
+    n_total = syn.num_measurements(cfg_full) if strong else world * n_meas
+    value = n_total / (ms_step * 1e-3)
+    timing = {"ms_per_step_median": float(np.median(per_step)), "ms_per_step_per_rank": [float(t.item()) / a.steps for t in rank_ms],
+              "steady": {"steps": int(len(steady)), "ms_median": float(np.median(steady)), "ms_p10": float(np.percentile(steady, 10)), "ms_p90": float(np.percentile(steady, 90)),
+                         "window_s": float(steady.sum() * 1e-3)}}
+
+    strong_info = None
+    if strong:
+        # time of the pieces (max over ranks) and of the exchange alone; then the sharded linearisation against the UNSHARDED problem (rank 0)
+        def timed(fn, reps=20):
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            b0.record(stream)
+            for _ in range(reps):
+                fn()
+            b1.record(stream)
+            barrier()
+            t = torch.tensor([b0.elapsed_time(b1) / reps], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        names = ("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b", "q_a", "q_b")
+        parts = {"evaluate": timed(lambda: ne.evaluate(cost=False)), "linearize": timed(lambda: gn_linearize(ne)), "schur_product": timed(lambda: gn_product(ne))}
+        ar = {"linearize": ("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b"), "rhs": ("q_a", "q_b"), "product": ("q_a", "q_b")}
+        ar_bytes = {k_: int(sum(ne.buf(n_).numel() for n_ in v_) * 8) for k_, v_ in ar.items()}
+        ar_ms = {k_: (timed(lambda v_=v_: ne._reduce(*v_), 50) if world > 1 else 0.0) for k_, v_ in ar.items()}
+        strong_info = {"collective": ("ncclAllReduce(sum, fp64) of parameter-sized buffers: landmark blocks + gradient + diagonal knot blocks once per linearisation, "
+                                      "the reduced right-hand side once, S p once per CG iteration") if world > 1 else "none (one rank)",
+                       "allreduce_bytes": ar_bytes, "allreduce_ms": ar_ms, "ms": parts, "rows_this_rank": int(n_meas), "rows_total": int(n_total),
+                       "step": "evaluation + LM linearisation (c, g_rho, B_kk, gradient, reduced rhs, block-Jacobi preconditioner) + one implicit-Schur product and CG update"}
+        ne.evaluate(cost=False)
+        gn_linearize(ne)
+        gn_product(ne)
+        got = {n_: ne.buf(n_).clone() for n_ in ("z_a", "z_b", "b_a", "b_b", "q_a", "q_b", "grho")}
+        cost = ne.evaluate()
+        if rank == 0:
+            saved_dist = gn._dist
+            gn._dist = lambda: None
+            try:
+                p0 = _lib.Problem(local_rank)
+                p0.set_stream(stream.cuda_stream)
+                if split:
+                    p0.set_split_spline(cfg_full["dt"], cfg_full["t0"], n_a, cfg_full["dt"], cfg_full["t0"], n_b)
+                else:
+                    p0.set_se3_spline(cfg_full["dt"], cfg_full["t0"], n_a)
+                for k_, add in (("gyro", p0.add_gyroscope), ("accel", p0.add_accelerometer)):
+                    if cfg_full[k_]:
+                        add(imu, cfg_full[k_]["t"], cfg_full[k_]["y"], cfg_full[k_]["weight"])
+                if cfg_full["cam"]:
+                    c = cfg_full["cam"]
+                    p0.add_static_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"]), c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
+                ne0 = make_ne(p0, cfg_full)
+                cost0 = ne0.evaluate()
+                gn_linearize(ne0)
+                gn_product(ne0)
+                errs = {"rel_err_cost": abs(cost - cost0) / abs(cost0)}
+                for n_ in got:
+                    ref = ne0.buf(n_)
+                    if ref.numel():
+                        errs["rel_err_" + n_] = float((got[n_] - ref).abs().max() / ref.abs().max())
+                errs["ok"] = bool(max(errs.values()) < 1e-10)
+                strong_info["vs_unsharded"] = errs
+                del ne0, p0
+            finally:
+                gn._dist = saved_dist
 
     # ---- end-to-end leg: host buffers through ktk_evaluate ---------------------------------------------------------
     h_knots = torch.from_numpy(knots_flat.copy()).pin_memory()
@@ -395,7 +520,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_meas * e2e_steps / float(e2e_s.item())
+    e2e_value = n_total * e2e_steps / float(e2e_s.item())
 
     if rank != 0:
         if dist is not None:
@@ -424,12 +549,13 @@ def main():
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(a.workload, cfg, a.row_order, a.camera_method, a.camera_model),
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a.workload, cfg_full if strong else cfg, "device" if strong else a.row_order, a.camera_method, a.camera_model, strong, world),
+            "timing": timing,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
             "gpu_launches": int(launches),
-            "clocks": clocks.summary(),
+            "clocks": dict(clocks.summary(), sampled="under the same steps, immediately after the timed region (sampler outside the event pair)"),
             "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_newton_rs", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
@@ -441,10 +567,12 @@ def main():
                          # dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
                          "fp64": ({"flop_per_row": 4013, "achieved_tflops": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
                                    "frac": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
+    if strong_info is not None:
+        line["strong"] = strong_info
     if not a.quick:      # rank 0 checks its own shard (every rank's shard has the same construction)
-        line["parity"] = parity_gate(cfg, p, groups, keep, rho, dev_flags, a.row_order == "device")
-    if not a.no_cpu_baseline and not a.quick and world == 1:
-        base, _, _ = cpu_baseline(cfg, a.cpu_sample)
+        line["parity"] = parity_gate(cfg, p, groups, keep, rho, dev_flags, bool(dev_flags & _lib.EVAL_DEVICE_ORDER))
+    if not a.no_cpu_baseline and not a.quick:      # rank 0's host cores (the other ranks have finished their work by now)
+        base, _, _ = cpu_baseline(cfg_full if strong else cfg, a.cpu_sample)
         line["cpu_baseline"] = base
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -240,6 +240,45 @@ int ktk_jtj_diagonal(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs
 int ktk_jtj_diagonal_local(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, const double* d_Pa, const double* d_Pb, double* d_y);
 /* (flags: 0, or KTK_EVAL_DEVICE_ORDER if the rows were written with it.) */
 
+/* ---- Gauss-Newton / Levenberg-Marquardt step on the device -----------------------------------------------------
+ * What the reference leaves to ceres::Solve with SPARSE_SCHUR (trajectory_estimator.h:38-64), on the rows a ktk_evaluate_device call with
+ * KTK_EVAL_DEVICE_ORDER left in device memory (csrc/gn_device.cuh): the landmark blocks (1x1: rho, static_rscamera_measurement.h:178-184)
+ * are eliminated, the reduced knot system is solved by block-Jacobi preconditioned conjugate gradients with the Schur complement applied
+ * implicitly, Plus() (uniform_se3_spline_trajectory.h:25-48, uniform_so3_spline_trajectory.h:21) and the rho >= 0 bound happen on the device.
+ * Every reduction is a gather in a fixed order (no atomics): results are bit-reproducible.  All calls are asynchronous on the problem's
+ * stream except ktk_gn_prepare and ktk_gn_pcg_status.  Local (tangent) vectors: 6 per SE3 knot; 3 per R3 and 3 per SO3 knot.
+ * With rows sharded over ranks (every landmark's rows on ONE rank, kontiki_b200/sharding.py) the caller all-reduces, between the calls,
+ * the buffers named below (ktk_gn_buffer): that is the only exchange.
+ *   ktk_gn_prepare(flags, d_outs, n_rho, lm_locked, lock_a, lock_b, huber)   after one evaluation into d_outs; static row lists + vectors.
+ *        lm_locked: n_rho bytes or NULL; lock_a / lock_b: SE3 (or R3) / SO3 spline constant; huber[g]: Huber constants of group g in
+ *        caller order (NULL entries / NULL: no loss) for the cost 1/2 sum rho(s).
+ *   ktk_gn_cost                       scal.cost = 1/2 sum rho(s) of this rank's rows
+ *   ktk_gn_linearize_local(knots,rho) tangent bases, "c" = sum J_rho^2, "grho" = J_rho^T r, "blocks_a"/"blocks_b" = diagonal knot blocks
+ *   ktk_gn_gradient_local             "z_a"/"z_b" = P^T J_k^T r
+ *   ktk_gn_linearize_rhs(radius)      damping of c; "q_a"/"q_b" = reduced gradient P^T J_k^T (r - J_rho C^-1 grho)
+ *   ktk_gn_pcg_begin(radius,tol,max)  b = -q, preconditioner (B_kk + D/radius)^-1 with D = clamp(diag B, 1e-6, 1e32) (Ceres' LM scaling)
+ *   ktk_gn_product / ktk_gn_pcg_update   "q_a"/"q_b" = S p of this rank's rows (all-reduce), then one CG update; scalars stay on the device
+ *   ktk_gn_pcg_status                 synchronises: iterations, convergence flag, |r|/|b|
+ *   ktk_gn_finish_local / ktk_gn_finish_mask / ktk_gn_model_local   "drho" (all-reduce after the mask), scal.model_ur / model_uu: the
+ *        model decrease is -(model_ur + model_uu / 2), scal.step2 = |delta_knots|^2
+ *   ktk_gn_retract(knots_in, rho_in, knots_out, rho_out)
+ * scal ("scal" buffer, doubles): [rz, pq, alpha, beta, rnorm2, bnorm2, tol2, (iter, done), (max_iter, pad), model_ur, model_uu, step2, cost]. */
+int ktk_gn_prepare(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, int64_t n_rho, const uint8_t* lm_locked, int32_t lock_a, int32_t lock_b,
+                   const double* const* huber_caller_order);
+int ktk_gn_cost(ktk_problem* p);
+int ktk_gn_linearize_local(ktk_problem* p, const double* d_knots, const double* d_rho);
+int ktk_gn_gradient_local(ktk_problem* p);
+int ktk_gn_linearize_rhs(ktk_problem* p, double radius);
+int ktk_gn_pcg_begin(ktk_problem* p, double radius, double tol, int32_t max_iter);
+int ktk_gn_product(ktk_problem* p);
+int ktk_gn_pcg_update(ktk_problem* p);
+int ktk_gn_pcg_status(ktk_problem* p, int32_t* iterations, int32_t* done, double* rel_residual);
+int ktk_gn_finish_local(ktk_problem* p);
+int ktk_gn_finish_mask(ktk_problem* p);
+int ktk_gn_model_local(ktk_problem* p);
+int ktk_gn_retract(ktk_problem* p, const double* d_knots_in, const double* d_rho_in, double* d_knots_out, double* d_rho_out);
+int64_t ktk_gn_buffer(ktk_problem* p, const char* name, double** ptr);
+
 /* order[k] = insertion index (0-based, within the group) of the k-th row in device order.  Fixed once the group has been
  * uploaded (first evaluation, or this call); changes only if the spline grid or the sensor's time offset is changed. */
 int ktk_get_row_order(ktk_problem* p, int32_t group, int32_t* order);

@@ -37,7 +37,9 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation", "ktk_add_lifting_rs", "ktk_set_group_vt"]
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation", "ktk_add_lifting_rs", "ktk_set_group_vt",
+           "ktk_gn_prepare", "ktk_gn_cost", "ktk_gn_linearize_local", "ktk_gn_gradient_local", "ktk_gn_linearize_rhs", "ktk_gn_pcg_begin", "ktk_gn_product", "ktk_gn_pcg_update",
+           "ktk_gn_pcg_status", "ktk_gn_finish_local", "ktk_gn_finish_mask", "ktk_gn_model_local", "ktk_gn_retract", "ktk_gn_buffer"]
 
 _lib = None
 
@@ -104,6 +106,16 @@ def lib():
         L.ktk_traj_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ktk_set_profiling.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_read_profile.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.ktk_gn_prepare.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(GroupOut), C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+        for name in ("ktk_gn_cost", "ktk_gn_gradient_local", "ktk_gn_product", "ktk_gn_pcg_update", "ktk_gn_finish_local", "ktk_gn_finish_mask", "ktk_gn_model_local"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        L.ktk_gn_linearize_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_gn_linearize_rhs.argtypes = [C.c_void_p, C.c_double]
+        L.ktk_gn_pcg_begin.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32]
+        L.ktk_gn_pcg_status.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.ktk_gn_retract.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ktk_gn_buffer.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.ktk_gn_buffer.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -395,6 +407,34 @@ class Problem:
 
     def synchronize(self):
         check(lib().ktk_synchronize(self._h))
+
+    # ---- Gauss-Newton step on the device (include/kontiki_b200.h "ktk_gn_*"; driven by kontiki_b200/gn.py) ---------------------------
+    def gn_prepare(self, flags, d_outs, n_rho, lm_locked=None, lock_a=False, lock_b=False, hubers=None):
+        arr = self._out_array(d_outs, lambda q: None if q is None else int(q))
+        locked = None if lm_locked is None else np.ascontiguousarray(lm_locked, np.uint8)
+        hub = (C.c_void_p * max(self.num_groups, 1))()
+        keep = []
+        for g in range(self.num_groups):
+            h = None if hubers is None else hubers.get(g)
+            if h is not None:
+                h = np.ascontiguousarray(h, np.float64)
+                keep.append(h)
+                hub[g] = h.ctypes.data
+        check(lib().ktk_gn_prepare(self._h, int(flags), arr, int(n_rho), None if locked is None else locked.ctypes.data, int(bool(lock_a)), int(bool(lock_b)), hub))
+
+    def gn_call(self, name, *args):
+        check(getattr(lib(), "ktk_gn_" + name)(self._h, *args))
+
+    def gn_pcg_status(self):
+        it, done, rel = C.c_int32(0), C.c_int32(0), C.c_double(0)
+        check(lib().ktk_gn_pcg_status(self._h, C.byref(it), C.byref(done), C.byref(rel)))
+        return it.value, bool(done.value), rel.value
+
+    def gn_buffer(self, name):
+        """(device pointer, number of doubles) of one of the solver's buffers."""
+        ptr = C.c_void_p()
+        n = lib().ktk_gn_buffer(self._h, name.encode(), C.byref(ptr))
+        return (ptr.value or 0), int(n)
 
     def get_structure(self, g, cap=16):
         n = self.group_size(g)

@@ -980,7 +980,9 @@ struct Group {
 
 }  // namespace
 
+namespace { struct GnState; void gn_state_free(GnState*); }
 struct ktk_problem {
+  GnState* gn = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool have_spline = false;
@@ -998,7 +1000,7 @@ struct ktk_problem {
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<uint64_t> graph_key;
   int64_t graph_launches = 0;
-  ~ktk_problem() { if (graph_exec) cudaGraphExecDestroy(graph_exec); for (auto g : groups) delete g; if (h_err) cudaFreeHost(h_err); }
+  ~ktk_problem() { gn_state_free(gn); if (graph_exec) cudaGraphExecDestroy(graph_exec); for (auto g : groups) delete g; if (h_err) cudaFreeHost(h_err); }
 };
 
 namespace {
@@ -1863,6 +1865,404 @@ int ktk_expand_static_rs(const ktk_problem* p, int32_t group, int32_t cap, const
     }
   }
   return KTK_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// Gauss-Newton step on the device (gn_device.cuh): host orchestration and C ABI
+// =====================================================================================================================
+#include "gn_device.cuh"
+
+namespace {
+
+struct GnGroupState {
+  int gi = 0, n = 0, nres = 0, row_len = 0, rho_off = -1;
+  RowWindows rw{};
+  const double* J = nullptr; const double* r = nullptr; const int* idx[4] = {nullptr, nullptr, nullptr, nullptr};
+  DevBuf<int> order[4], fk[4], start[4];
+  DevBuf<int> lm_order, lm_start; const int* lm_rows = nullptr;      // landmark of every row (device order)
+  DevBuf<double> u, huber;
+};
+struct GnState {
+  uint32_t flags = 0; int traj = 0;
+  int n[2] = {0, 0}, width[2] = {0, 0}, lw[2] = {0, 0}, kind[2] = {0, 0}; int64_t n_rho = 0; double free_[2] = {1.0, 1.0};
+  std::vector<GnGroupState*> g;
+  DevBuf<double> P[2], va[2], Bd[2], Minv[2], damp[2], x[2], r[2], z[2], p[2], q[2], b[2];
+  DevBuf<double> c, cd, grho, t, s, drho, partial, own;
+  DevBuf<unsigned char> lm_locked; bool have_locked = false;
+  DevBuf<GnScal> scal; GnScal* h_scal = nullptr;
+  GnWinList lists[2];
+  const double* d_knots = nullptr; const double* d_rho = nullptr;
+  ~GnState() { for (auto q : g) delete q; if (h_scal) cudaFreeHost(h_scal); }
+};
+void gn_state_free(GnState* s) { delete s; }
+
+inline int gn_blocks(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+GnVec gn_vec(GnState& S) {
+  GnVec v{};
+  for (int sp = 0; sp < 2; ++sp) {
+    v.n[sp] = S.n[sp]; v.lw[sp] = S.lw[sp]; v.Minv[sp] = S.Minv[sp].p; v.damp[sp] = S.damp[sp].p; v.x[sp] = S.x[sp].p; v.r[sp] = S.r[sp].p;
+    v.z[sp] = S.z[sp].p; v.p[sp] = S.p[sp].p; v.q[sp] = S.q[sp].p; v.b[sp] = S.b[sp].p;
+  }
+  return v;
+}
+
+// rows: u = J_k (P v) for every group, from local vectors vloc[2]
+int gn_rows_apply(ktk_problem* p, GnState& S, double* const vloc[2]) {
+  cudaStream_t s = p->stream;
+  for (int sp = 0; sp < 2; ++sp)
+    if (S.n[sp] > 0) k_gn_to_ambient<<<gn_blocks((int64_t)S.n[sp] * S.width[sp], 256), 256, 0, s>>>(S.P[sp].p, vloc[sp], S.n[sp], S.width[sp], S.lw[sp], S.free_[sp], S.va[sp].p);
+  for (auto gp : S.g) {
+    GnGroupState& G = *gp;
+    GnRowsArgs a{};
+    a.w = G.rw; a.n = G.n; a.J = G.J; for (int k = 0; k < 4; ++k) a.idx[k] = G.idx[k];
+    a.va[0] = S.va[0].p; a.va[1] = S.va[1].p; a.u = G.u.p;
+    k_gn_rows_apply<<<gn_blocks(G.n, 128), 128, 0, s>>>(a);
+  }
+  p->launches += 2 + (int64_t)S.g.size();
+  return KTK_OK;
+}
+// t[l] = sum over all groups of J_rho^T x (x = u of the group, or r if from_r)
+int gn_lm_sums(ktk_problem* p, GnState& S, bool from_r, bool squares, double* out) {
+  cudaStream_t s = p->stream;
+  if (S.n_rho == 0) return KTK_OK;
+  bool first = true;
+  for (auto gp : S.g) {
+    GnGroupState& G = *gp;
+    if (G.rho_off < 0) continue;
+    k_gn_lm_reduce<<<gn_blocks(S.n_rho, 128), 128, 0, s>>>(G.J, G.row_len, G.rho_off, G.nres, squares ? nullptr : (from_r ? G.r : G.u.p), G.lm_order.p, G.lm_start.p,
+                                                          (int)S.n_rho, first ? 0 : 1, out);
+    first = false; p->launches += 1;
+  }
+  if (first) KTK_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * (size_t)S.n_rho, s));
+  return KTK_OK;
+}
+// u (or r -> u) minus J_rho s, every camera group
+void gn_rows_fix(ktk_problem* p, GnState& S, bool from_r) {
+  for (auto gp : S.g) {
+    GnGroupState& G = *gp;
+    if (G.rho_off < 0) { if (from_r) cudaMemcpyAsync(G.u.p, G.r, sizeof(double) * (size_t)G.n * G.nres, cudaMemcpyDeviceToDevice, p->stream); continue; }
+    k_gn_rows_fix<<<gn_blocks(G.n, 256), 256, 0, p->stream>>>(G.J, G.row_len, G.rho_off, G.nres, G.lm_rows, S.s.p, G.n, from_r ? G.r : nullptr, G.u.p);
+    p->launches += 1;
+  }
+}
+void gn_gather(ktk_problem* p, GnState& S, double* const y[2]) {
+  for (int sp = 0; sp < 2; ++sp)
+    if (S.n[sp] > 0) {
+      k_gn_gather<<<gn_blocks((int64_t)S.n[sp] * 32, 128), 128, 0, p->stream>>>(S.lists[sp], S.n[sp], S.width[sp], S.lw[sp], S.P[sp].p, y[sp]);
+      p->launches += 1;
+    }
+}
+void gn_set_x(GnState& S, bool use_r) {      // the gather transposes u (x = G.u) or the residuals
+  for (int sp = 0; sp < 2; ++sp)
+    for (int i = 0; i < S.lists[sp].n; ++i) {
+      GnWinDev& w = S.lists[sp].w[i];
+      for (auto gp : S.g) if (gp->J == w.J) w.x = use_r ? gp->r : gp->u.p;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Builds the static row lists (sorted by first knot per window, sorted by landmark) from the index arrays the LAST evaluation wrote into
+// d_outs (rows in device order), and allocates the solver's vectors.  lm_locked: host array of n_rho bytes (1 = constant landmark) or NULL.
+int ktk_gn_prepare(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, int64_t n_rho, const uint8_t* lm_locked, int32_t lock_a, int32_t lock_b,
+                   const double* const* huber_caller_order) {
+  if (!p || !d_outs) return fail(KTK_EINVAL, "NULL argument");
+  if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
+  if (!(flags & KTK_EVAL_DEVICE_ORDER)) return fail(KTK_EINVAL, "the device Gauss-Newton step works on rows in device order (KTK_EVAL_DEVICE_ORDER)");
+  if (flags & KTK_EVAL_LOCAL) return fail(KTK_EINVAL, "the device Gauss-Newton step takes ambient rows");
+  KTK_CUDA(cudaSetDevice(p->device));
+  cudaStream_t s = p->stream;
+  KTK_CUDA(cudaStreamSynchronize(s));
+  gn_state_free(p->gn); p->gn = nullptr;
+  GnState* S = new GnState;
+  p->gn = S;
+  const bool split = p->traj == 1;
+  S->flags = flags; S->traj = p->traj; S->n_rho = n_rho;
+  S->n[0] = split ? p->spl.n_r3 : p->sp.n_knots; S->width[0] = split ? 3 : 7; S->lw[0] = split ? 3 : 6; S->kind[0] = split ? 1 : 0;
+  S->n[1] = split ? p->spl.n_so3 : 0; S->width[1] = 4; S->lw[1] = 3; S->kind[1] = 2;
+  S->free_[0] = lock_a ? 0.0 : 1.0; S->free_[1] = lock_b ? 0.0 : 1.0;
+  S->lists[0].n = S->lists[1].n = 0;
+  int st;
+  for (size_t gi = 0; gi < p->groups.size(); ++gi) {
+    Group& g = *p->groups[gi];
+    if (g.n == 0) continue;
+    if (is_span_camera(g.kind)) return fail(KTK_EUNSUPPORTED, "the device Gauss-Newton step does not cover NewtonRs / LiftingRs rows (host_cholesky solves them)");
+    const ktk_group_out& o = d_outs[gi];
+    if (!o.J || !o.r) return fail(KTK_EINVAL, "the group has no rows in device memory");
+    GnGroupState* G = new GnGroupState;
+    S->g.push_back(G);
+    G->gi = (int)gi; G->n = (int)g.n; G->rw = row_windows(p, g); G->nres = G->rw.nres; G->row_len = G->rw.row_len; G->rho_off = G->rw.rho_off_in_row;
+    G->J = o.J; G->r = o.r; G->idx[0] = o.i0; G->idx[1] = o.i0_b; G->idx[2] = o.i0_c; G->idx[3] = o.i0_d;
+    if ((st = G->u.resize((size_t)G->n * G->nres))) return st;
+    if (huber_caller_order && huber_caller_order[gi]) {
+      std::vector<double> h((size_t)g.n);
+      for (int64_t k = 0; k < g.n; ++k) h[k] = huber_caller_order[gi][g.perm[k]];
+      if ((st = G->huber.upload(h, s))) return st;
+    }
+    // window lists
+    std::vector<std::vector<int>> first(4);
+    for (int w = 0; w < G->rw.nwin; ++w) {
+      const int slot = G->rw.slot[w];
+      if (!G->idx[slot]) return fail(KTK_EINVAL, "the group's index arrays are missing");
+      if (first[slot].empty()) {
+        first[slot].resize((size_t)g.n);
+        KTK_CUDA(cudaMemcpy(first[slot].data(), G->idx[slot], sizeof(int) * (size_t)g.n, cudaMemcpyDeviceToHost));
+      }
+      const int sp = (split && G->rw.width[w] == 4) ? 1 : 0, nk = S->n[sp];
+      std::vector<int> start((size_t)nk + 1, 0), order((size_t)g.n), fk((size_t)g.n);
+      for (int64_t i = 0; i < g.n; ++i) {
+        const int f = first[slot][i];
+        if (f < 0 || f + 3 >= nk) return fail(KTK_ERANGE, "a row of the last evaluation has no valid knot window (evaluate successfully before ktk_gn_prepare)");
+        start[(size_t)f + 1] += 1;
+      }
+      for (int k = 0; k < nk; ++k) start[(size_t)k + 1] += start[k];
+      std::vector<int> cur(start.begin(), start.end() - 1);
+      for (int64_t i = 0; i < g.n; ++i) { const int f = first[slot][i]; const int j = cur[f]++; order[j] = (int)i; fk[j] = f; }
+      if ((st = G->order[w].upload(order, s)) || (st = G->fk[w].upload(fk, s)) || (st = G->start[w].upload(start, s))) return st;
+      if (S->lists[sp].n >= kGnMaxWin) return fail(KTK_EUNSUPPORTED, "too many measurement groups for the device Gauss-Newton step");
+      GnWinDev& d = S->lists[sp].w[S->lists[sp].n++];
+      d.J = G->J; d.x = G->u.p; d.order = G->order[w].p; d.fk = G->fk[w].p; d.start = G->start[w].p;
+      d.partner_first = nullptr; d.partner_j_off = 0; d.role = 0;
+      d.j_off = G->rw.j_off[w]; d.width = G->rw.width[w]; d.nres = G->nres; d.row_len = G->row_len;
+      if (g.kind == KTK_STATIC_RS) {      // windows come as (reference, observation) pairs on the same spline: w and w + nwin/2
+        const int half = G->rw.nwin / 2, other = w < half ? w + half : w - half;
+        d.role = w < half ? 1 : 2; d.partner_first = G->idx[G->rw.slot[other]]; d.partner_j_off = G->rw.j_off[other];
+      }
+    }
+    if (is_camera(g.kind)) {
+      if (g.lm_min < 0 || g.lm_max >= n_rho) return fail(KTK_EINVAL, "landmark index out of range of rho");
+      if (g.d_lm_sorted.n != (size_t)g.n) { if ((st = g.d_lm_sorted.upload(gather(g.lm, g.perm, 1), s))) return st; }
+      G->lm_rows = g.d_lm_sorted.p;
+      std::vector<int> start((size_t)n_rho + 1, 0), order((size_t)g.n);
+      for (int64_t i = 0; i < g.n; ++i) start[(size_t)g.lm[g.perm[i]] + 1] += 1;
+      for (int64_t l = 0; l < n_rho; ++l) start[(size_t)l + 1] += start[l];
+      std::vector<int> cur(start.begin(), start.end() - 1);
+      for (int64_t i = 0; i < g.n; ++i) order[cur[g.lm[g.perm[i]]]++] = (int)i;
+      if ((st = G->lm_order.upload(order, s)) || (st = G->lm_start.upload(start, s))) return st;
+    }
+  }
+  for (int sp = 0; sp < 2; ++sp) {
+    const size_t nk = (size_t)S->n[sp], lw = (size_t)S->lw[sp], wd = (size_t)S->width[sp];
+    if ((st = S->P[sp].resize(nk * wd * lw)) || (st = S->va[sp].resize(nk * wd)) || (st = S->Bd[sp].resize(nk * lw * lw)) || (st = S->Minv[sp].resize(nk * lw * lw)) ||
+        (st = S->damp[sp].resize(nk * lw)) || (st = S->x[sp].resize(nk * lw)) || (st = S->r[sp].resize(nk * lw)) || (st = S->z[sp].resize(nk * lw)) ||
+        (st = S->p[sp].resize(nk * lw)) || (st = S->q[sp].resize(nk * lw)) || (st = S->b[sp].resize(nk * lw))) return st;
+  }
+  const size_t nr = (size_t)std::max<int64_t>(n_rho, 1);
+  if ((st = S->c.resize(nr)) || (st = S->cd.resize(nr)) || (st = S->grho.resize(nr)) || (st = S->t.resize(nr)) || (st = S->s.resize(nr)) || (st = S->drho.resize(nr)) ||
+      (st = S->own.resize(nr))) return st;
+  int64_t maxrows = 1;
+  for (auto gp : S->g) maxrows = std::max<int64_t>(maxrows, gp->n);
+  if ((st = S->partial.resize((size_t)2 * gn_blocks(maxrows, 256) + 2))) return st;
+  if ((st = S->scal.resize(1))) return st;
+  if (cudaHostAlloc(&S->h_scal, sizeof(GnScal), cudaHostAllocDefault) != cudaSuccess) return fail(KTK_ECUDA, "cudaHostAlloc failed");
+  if (lm_locked && n_rho > 0) {
+    std::vector<unsigned char> l(lm_locked, lm_locked + n_rho);
+    if ((st = S->lm_locked.upload(l, s))) return st;
+    S->have_locked = true;
+  }
+  KTK_CUDA(cudaMemsetAsync(S->scal.p, 0, sizeof(GnScal), s));
+  KTK_CUDA(cudaStreamSynchronize(s));
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+
+#define GN_STATE()                                                                                                            \
+  if (!p || !p->gn) return fail(KTK_EINVAL, "ktk_gn_prepare has not been called");                                            \
+  GnState& S = *p->gn;                                                                                                        \
+  KTK_CUDA(cudaSetDevice(p->device));                                                                                         \
+  cudaStream_t s = p->stream; (void)s
+
+// cost 1/2 sum rho(s) of the rows in device memory -> scal.cost (this rank's rows)
+int ktk_gn_cost(ktk_problem* p) {
+  GN_STATE();
+  bool first = true;
+  for (auto gp : S.g) {
+    GnGroupState& G = *gp;
+    const int nb = gn_blocks(G.n, 256);
+    const bool robust = (S.flags & KTK_EVAL_ROBUST) && G.huber.n == (size_t)G.n;
+    k_gn_cost_rows<<<nb, 256, 0, s>>>(G.r, G.nres, robust ? G.huber.p : nullptr, G.n, S.partial.p);
+    k_gn_sum_partials<<<1, 1024, 0, s>>>(S.partial.p, nb, 1, first ? 0 : 1, &S.scal.p->cost);
+    first = false; p->launches += 2;
+  }
+  if (first) KTK_CUDA(cudaMemsetAsync(&S.scal.p->cost, 0, sizeof(double), s));
+  return KTK_OK;
+}
+
+// Stage 0 (local to this rank's rows): tangent bases P, c_l = sum J_rho^2, g_rho = J_rho^T r, diagonal knot blocks B_kk.
+// Between stages the caller all-reduces c, g_rho and the blocks when the rows are sharded over ranks (ktk_gn_buffer).
+int ktk_gn_linearize_local(ktk_problem* p, const double* d_knots, const double* d_rho) {
+  GN_STATE();
+  if (!d_knots) return fail(KTK_EINVAL, "NULL argument");
+  S.d_knots = d_knots; S.d_rho = d_rho;
+  const double* kb = d_knots + (size_t)S.width[0] * S.n[0];
+  k_gn_plus<<<gn_blocks(S.n[0], 128), 128, 0, s>>>(d_knots, S.n[0], S.kind[0], S.P[0].p);
+  if (S.n[1] > 0) k_gn_plus<<<gn_blocks(S.n[1], 128), 128, 0, s>>>(kb, S.n[1], S.kind[1], S.P[1].p);
+  int st;
+  if ((st = gn_lm_sums(p, S, false, true, S.c.p)) || (st = gn_lm_sums(p, S, true, false, S.grho.p))) return st;
+  if (S.n_rho > 0) KTK_CUDA(cudaMemcpyAsync(S.own.p, S.c.p, sizeof(double) * (size_t)S.n_rho, cudaMemcpyDeviceToDevice, s));      // > 0 where this rank holds rows of the landmark
+  for (int sp = 0; sp < 2; ++sp)
+    if (S.n[sp] > 0) { k_gn_blocks<<<gn_blocks((int64_t)S.n[sp] * 32, 128), 128, 0, s>>>(S.lists[sp], S.n[sp], S.width[sp], S.lw[sp], S.P[sp].p, S.Bd[sp].p); p->launches += 1; }
+  p->launches += 2;
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+// g_k = P^T J_k^T r of this rank's rows (the knot part of the gradient, for the gradient-tolerance test) -> z buffers; g_rho is "grho".
+int ktk_gn_gradient_local(ktk_problem* p) {
+  GN_STATE();
+  gn_set_x(S, true);
+  double* y[2] = {S.z[0].p, S.z[1].p};
+  gn_gather(p, S, y);
+  gn_set_x(S, false);
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+__global__ void k_gn_damp_rho(const double* c, int n, double inv_radius, double* cd) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n) cd[l] = c[l] > 0.0 ? c[l] + fmin(fmax(c[l], 1e-6), 1e32) * inv_radius : 0.0;
+}
+// Stage 1: LM damping of the landmark blocks, s = C^-1 g_rho, reduced gradient y = P^T J_k^T (r - J_rho s) of this rank's rows -> q buffers
+// (all-reduce them before stage 2).
+int ktk_gn_linearize_rhs(ktk_problem* p, double radius) {
+  GN_STATE();
+  if (S.n_rho > 0) {
+    k_gn_damp_rho<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(S.c.p, (int)S.n_rho, 1.0 / radius, S.cd.p);
+    k_gn_lm_scale<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(S.grho.p, S.cd.p, S.have_locked ? S.lm_locked.p : nullptr, (int)S.n_rho, S.s.p);
+  }
+  gn_rows_fix(p, S, true);
+  gn_set_x(S, false);
+  double* y[2] = {S.q[0].p, S.q[1].p};
+  gn_gather(p, S, y);
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+// Stage 2: b = -y, block-Jacobi preconditioner (B_kk + D/radius)^-1, CG state x = 0.
+int ktk_gn_pcg_begin(ktk_problem* p, double radius, double tol, int32_t max_iter) {
+  GN_STATE();
+  for (int sp = 0; sp < 2; ++sp)
+    if (S.n[sp] > 0) {
+      k_gn_negate<<<gn_blocks((int64_t)S.n[sp] * S.lw[sp], 256), 256, 0, s>>>(S.q[sp].p, S.n[sp] * S.lw[sp], S.free_[sp], S.b[sp].p);
+      k_gn_invert_blocks<<<gn_blocks(S.n[sp], 64), 64, 0, s>>>(S.Bd[sp].p, S.n[sp], S.lw[sp], 1.0 / radius, S.free_[sp], S.Minv[sp].p, S.damp[sp].p);
+    }
+  k_gn_pcg_init<<<1, 1024, 0, s>>>(gn_vec(S), S.scal.p, tol, max_iter);
+  p->launches += 5;
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+// q = (S p) of this rank's rows, WITHOUT the damping term (ktk_gn_pcg_update adds D p after the all-reduce): 2 passes over the rows.
+int ktk_gn_product(ktk_problem* p) {
+  GN_STATE();
+  double* pv[2] = {S.p[0].p, S.p[1].p};
+  int st;
+  if ((st = gn_rows_apply(p, S, pv))) return st;
+  if (S.n_rho > 0) {
+    if ((st = gn_lm_sums(p, S, false, false, S.t.p))) return st;
+    k_gn_lm_scale<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(S.t.p, S.cd.p, S.have_locked ? S.lm_locked.p : nullptr, (int)S.n_rho, S.s.p);
+    gn_rows_fix(p, S, false);
+  }
+  gn_set_x(S, false);
+  double* y[2] = {S.q[0].p, S.q[1].p};
+  gn_gather(p, S, y);
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+int ktk_gn_pcg_update(ktk_problem* p) {
+  GN_STATE();
+  k_gn_pcg_update<<<1, 1024, 0, s>>>(gn_vec(S), S.scal.p);
+  p->launches += 1;
+  return KTK_OK;
+}
+// Synchronises and reports the CG state: iterations done, convergence flag, |r| / |b|.
+int ktk_gn_pcg_status(ktk_problem* p, int32_t* iterations, int32_t* done, double* rel_residual) {
+  GN_STATE();
+  KTK_CUDA(cudaMemcpyAsync(S.h_scal, S.scal.p, sizeof(GnScal), cudaMemcpyDeviceToHost, s));
+  KTK_CUDA(cudaStreamSynchronize(s));
+  if (iterations) *iterations = S.h_scal->iter;
+  if (done) *done = S.h_scal->done;
+  if (rel_residual) *rel_residual = S.h_scal->bnorm2 > 0.0 ? sqrt(S.h_scal->rnorm2 / S.h_scal->bnorm2) : 0.0;
+  return KTK_OK;
+}
+// After CG: delta_rho for the landmarks this rank holds (0 elsewhere: all-reduce the buffer "drho" when sharded), u = J delta of this rank's
+// rows, and the partial sums of the model decrease -> scal.model_ur / model_uu (all-reduce the two when sharded), scal.step2 = |delta_k|^2.
+int ktk_gn_finish_local(ktk_problem* p) {
+  GN_STATE();
+  double* xv[2] = {S.x[0].p, S.x[1].p};
+  int st;
+  if ((st = gn_rows_apply(p, S, xv))) return st;
+  if (S.n_rho > 0) {
+    if ((st = gn_lm_sums(p, S, false, false, S.t.p))) return st;
+    k_gn_delta_rho<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(S.grho.p, S.t.p, S.cd.p, S.have_locked ? S.lm_locked.p : nullptr, (int)S.n_rho, S.drho.p);
+  }
+  k_gn_norm2<<<1, 1024, 0, s>>>(S.x[0].p, S.n[0] * S.lw[0], S.x[1].p, S.n[1] * S.lw[1], nullptr, 0, &S.scal.p->step2);
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+__global__ void k_gn_mask_own(const double* own, int n, double* d) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < n && !(own[l] > 0.0)) d[l] = 0.0;
+}
+int ktk_gn_finish_mask(ktk_problem* p) {      // zero the steps of landmarks held by other ranks (before the all-reduce that assembles delta_rho)
+  GN_STATE();
+  if (S.n_rho > 0) k_gn_mask_own<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(S.own.p, (int)S.n_rho, S.drho.p);
+  return KTK_OK;
+}
+// With the complete delta_rho: model decrease sums over this rank's rows.
+int ktk_gn_model_local(ktk_problem* p) {
+  GN_STATE();
+  bool first = true;
+  for (auto gp : S.g) {
+    GnGroupState& G = *gp;
+    const int nb = gn_blocks(G.n, 256);
+    k_gn_model_rows<<<nb, 256, 0, s>>>(G.J, G.row_len, G.rho_off, G.nres, G.lm_rows, S.drho.p, G.r, G.u.p, G.n, S.partial.p);
+    k_gn_sum_partials<<<1, 1024, 0, s>>>(S.partial.p, nb, 2, first ? 0 : 1, &S.scal.p->model_ur);
+    k_gn_sum_partials<<<1, 1024, 0, s>>>(S.partial.p + 1, nb, 2, first ? 0 : 1, &S.scal.p->model_uu);
+    first = false; p->launches += 3;
+  }
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+// Plus on the device: knots_out = Plus(knots_in, delta_k), rho_out = max(0, rho_in + delta_rho) (static_rscamera_measurement.h:180).
+int ktk_gn_retract(ktk_problem* p, const double* d_knots_in, const double* d_rho_in, double* d_knots_out, double* d_rho_out) {
+  GN_STATE();
+  if (!d_knots_in || !d_knots_out) return fail(KTK_EINVAL, "NULL argument");
+  const size_t offb = (size_t)S.width[0] * S.n[0];
+  if (S.traj == 0) k_gn_retract_se3<<<gn_blocks(S.n[0], 128), 128, 0, s>>>(d_knots_in, S.x[0].p, S.n[0], d_knots_out);
+  else {
+    k_gn_retract_add<<<gn_blocks((int64_t)3 * S.n[0], 256), 256, 0, s>>>(d_knots_in, S.x[0].p, 3 * S.n[0], 0.0, 0, d_knots_out);
+    k_gn_retract_so3<<<gn_blocks(S.n[1], 128), 128, 0, s>>>(d_knots_in + offb, S.x[1].p, S.n[1], d_knots_out + offb);
+  }
+  if (S.n_rho > 0 && d_rho_in && d_rho_out) k_gn_retract_add<<<gn_blocks(S.n_rho, 256), 256, 0, s>>>(d_rho_in, S.drho.p, (int)S.n_rho, 0.0, 1, d_rho_out);
+  p->launches += 3;
+  KTK_CUDA(cudaGetLastError());
+  return KTK_OK;
+}
+// Device buffers of the solver, for the all-reduces of a sharded problem and for tests.  Returns the element count (doubles), 0 if unknown.
+int64_t ktk_gn_buffer(ktk_problem* p, const char* name, double** ptr) {
+  if (!p || !p->gn || !name || !ptr) return 0;
+  GnState& S = *p->gn;
+  const std::string n(name);
+  auto kn = [&](int sp, int per) { return (int64_t)S.n[sp] * per; };
+  if (n == "c") { *ptr = S.c.p; return S.n_rho; }
+  if (n == "grho") { *ptr = S.grho.p; return S.n_rho; }
+  if (n == "drho") { *ptr = S.drho.p; return S.n_rho; }
+  if (n == "blocks_a") { *ptr = S.Bd[0].p; return kn(0, S.lw[0] * S.lw[0]); }
+  if (n == "blocks_b") { *ptr = S.Bd[1].p; return kn(1, S.lw[1] * S.lw[1]); }
+  if (n == "q_a") { *ptr = S.q[0].p; return kn(0, S.lw[0]); }
+  if (n == "q_b") { *ptr = S.q[1].p; return kn(1, S.lw[1]); }
+  if (n == "x_a") { *ptr = S.x[0].p; return kn(0, S.lw[0]); }
+  if (n == "x_b") { *ptr = S.x[1].p; return kn(1, S.lw[1]); }
+  if (n == "p_a") { *ptr = S.p[0].p; return kn(0, S.lw[0]); }
+  if (n == "p_b") { *ptr = S.p[1].p; return kn(1, S.lw[1]); }
+  if (n == "z_a") { *ptr = S.z[0].p; return kn(0, S.lw[0]); }
+  if (n == "z_b") { *ptr = S.z[1].p; return kn(1, S.lw[1]); }
+  if (n == "b_a") { *ptr = S.b[0].p; return kn(0, S.lw[0]); }
+  if (n == "b_b") { *ptr = S.b[1].p; return kn(1, S.lw[1]); }
+  if (n == "scal") { *ptr = reinterpret_cast<double*>(S.scal.p); return (int64_t)(sizeof(GnScal) / sizeof(double)); }
+  return 0;
 }
 
 }  // extern "C"

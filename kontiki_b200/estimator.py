@@ -619,9 +619,11 @@ class TrajectoryEstimator:
         s.total_time_in_seconds = s.minimizer_time_in_seconds = time.perf_counter() - t_start
         return s
 
-    # ---- device-side normal equations (kontiki_b200/gn.py) ------------------------------------------------------------------
+    # ---- Levenberg-Marquardt with the whole step on the device (kontiki_b200/gn.py, csrc/gn_device.cuh) ----------------------------------
     def _solve_device(self, max_iterations, progress, pcg_tol=1e-6, pcg_max_iter=300):
-        import torch
+        """What ceres::Solve does with SPARSE_SCHUR (trajectory_estimator.h:38-64), on the GPU: rows stay in device memory, rho is eliminated
+        there (implicit Schur complement), the reduced knot system is solved by block-Jacobi preconditioned CG whose scalars never leave the
+        device, Plus() and the rho >= 0 bound are kernels.  The trust-region bookkeeping below needs three scalars per iteration."""
         from . import gn
         t_start = time.perf_counter()
         s = Summary()
@@ -631,48 +633,33 @@ class TrajectoryEstimator:
         spl_a = tr.R3_spline if split else tr
         spl_b = tr.SO3_spline if split else None
         n_a, n_b, n_rho = len(spl_a), (len(spl_b) if split else 0), len(self._landmarks)
-        ne = gn.DeviceNormalEquations(self._problem, split, n_a, n_b, n_rho, self._device)
-        for grp in self._groups:
-            if grp["kind"] == "cam":
-                ne.set_huber(grp["g"], grp["huber"])
-        free = np.ones(ne.n_loc)
+        lm_locked = np.array([L.locked for L in self._landmarks], np.uint8) if n_rho else None
+        hubers = {grp["g"]: grp["huber"] for grp in self._groups if grp["kind"] == "cam"}
+        sol = gn.DeviceSchurSolver(self._problem, split, n_a, n_b, n_rho, self._device, lm_locked, spl_a.locked, bool(split and spl_b.locked), hubers)
         da = 3 if split else 6
-        if spl_a.locked:
-            free[:da * n_a] = 0
-        if split and spl_b.locked:
-            free[da * n_a:da * n_a + 3 * n_b] = 0
-        free[da * n_a + 3 * n_b:] = [0.0 if L.locked else 1.0 for L in self._landmarks]
-        ne.free = torch.from_numpy(free).to(ne.dev)
-        n_free = int(free.sum())
+        n_free = (0 if spl_a.locked else da * n_a) + (0 if (not split or spl_b.locked) else 3 * n_b) + sum(not L.locked for L in self._landmarks)
         layout, ncols = self._columns()
         n_companion = sum(spl._width * len(spl) for spl in (spl_a, spl_b) if spl is not None and getattr(spl, "_companion", False))
-        s.num_parameters = ne.n_amb - n_companion + 8 * sum(g["kind"] not in ("pos", "ori") for g in self._groups)
+        s.num_parameters = self._problem.num_parameters(n_rho) - n_companion + 8 * sum(g["kind"] not in ("pos", "ori") for g in self._groups)
         s.num_parameters_reduced = ncols + self._ambient_free(layout)
         s.num_effective_parameters_reduced = n_free
         s.num_residual_blocks = s.num_residual_blocks_reduced = len(self._measurements)
         s.num_residuals = s.num_residuals_reduced = sum(self._problem.group_size(g["g"]) * {"cam": 2, "ori": 1}.get(g["kind"], 3) for g in self._groups)
 
-        def load_point():
+        def write_back():
+            kf, rho = sol.point()
             if split:
-                kf = np.concatenate([spl_a.control_points.reshape(-1), spl_b.control_points.reshape(-1)])
-                ne.set_point(kf, np.array([L.inverse_depth for L in self._landmarks]), None, _quat_plus_jacobian(spl_b.control_points))
+                spl_a.control_points[:] = kf[:3 * n_a].reshape(n_a, 3)
+                spl_b.control_points[:] = kf[3 * n_a:].reshape(n_b, 4)
             else:
-                ne.set_point(spl_a.control_points.reshape(-1), np.array([L.inverse_depth for L in self._landmarks]), _se3_plus_jacobian(spl_a.control_points), None)
+                spl_a.control_points[:] = kf.reshape(n_a, 7)
+            for L, v in zip(self._landmarks, rho):
+                L.inverse_depth = float(v)
 
-        def apply(delta):
-            d = delta.cpu().numpy()
-            if not spl_a.locked:
-                blk = d[:da * n_a].reshape(n_a, da)
-                spl_a.control_points[:] = (spl_a.control_points + blk) if split else _se3_plus(spl_a.control_points, blk)
-            if split and not spl_b.locked:
-                spl_b.control_points[:] = _quat_plus(spl_b.control_points, d[da * n_a:da * n_a + 3 * n_b].reshape(n_b, 3))
-            for L, dv in zip(self._landmarks, d[da * n_a + 3 * n_b:]):
-                if not L.locked:
-                    L.inverse_depth = max(0.0, L.inverse_depth + dv)
-
+        kf0 = np.concatenate([spl_a.control_points.reshape(-1), spl_b.control_points.reshape(-1)]) if split else spl_a.control_points.reshape(-1)
+        sol.set_point(kf0, np.array([L.inverse_depth for L in self._landmarks]))
         t0 = time.perf_counter()
-        load_point()
-        cost = ne.evaluate()
+        cost = sol.evaluate()
         s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
         s.initial_cost = cost
         radius, nu, term = 1e4, 2.0, TerminationType.NoConvergence
@@ -683,10 +670,9 @@ class TrajectoryEstimator:
             return s
         for it in range(max_iterations + 1):
             t_it = time.perf_counter()
-            g = ne.gradient()
-            gmax = float(g.abs().max())
+            gmax = float(sol.linearize(radius).item())
             if it == 0:
-                s.iterations.append(IterationSummary(iteration=0, cost=cost, gradient_max_norm=gmax, gradient_norm=float(torch.linalg.vector_norm(g)), trust_region_radius=radius))
+                s.iterations.append(IterationSummary(iteration=0, cost=cost, gradient_max_norm=gmax, trust_region_radius=radius))
                 if progress:
                     print(f"{0:4d}  {cost:12.6e}  {0.0:10.2e}  {gmax:10.2e}  {0.0:9.2e}  {0.0:9.2e}  {radius:9.2e}")
             if gmax < 1e-10:
@@ -695,25 +681,17 @@ class TrajectoryEstimator:
             if it == max_iterations:
                 s.message = "Maximum number of iterations reached"
                 break
-            D = ne.hessian_diagonal()
-            damp = torch.clamp(D, 1e-6, 1e32) / radius * ne.free
-            Minv = ne.free / torch.clamp(D + damp, min=1e-300)
             t_ls = time.perf_counter()
-            delta, n_cg = gn.pcg(lambda v: ne.hessian_apply(v) + damp * v, -g, Minv, tol=pcg_tol, max_iter=pcg_max_iter)
+            n_cg, _ = sol.solve(radius, pcg_tol, pcg_max_iter)
+            model, step_norm = sol.finish()
             s.linear_solver_time_in_seconds += time.perf_counter() - t_ls
-            Hd = ne.hessian_apply(delta)
-            model = -float(torch.dot(delta, g + 0.5 * Hd))
-            snap = self._snapshot()
-            apply(delta)
             t0 = time.perf_counter()
             try:
-                load_point()
-                cost_new = ne.evaluate()
+                cost_new = sol.evaluate(at_new=True)
             except ValueError:
                 cost_new = np.inf
             s.jacobian_evaluation_time_in_seconds += time.perf_counter() - t0
             rho_ratio = (cost - cost_new) / model if model > 0 else -1.0
-            step_norm = float(torch.linalg.vector_norm(delta))
             ok = np.isfinite(cost_new) and rho_ratio > 1e-3
             isum = IterationSummary(iteration=it + 1, cost=cost_new if ok else cost, cost_change=cost - cost_new, step_norm=step_norm, relative_decrease=rho_ratio,
                                     trust_region_radius=radius, step_is_successful=bool(ok), gradient_max_norm=gmax, linear_solver_iterations=n_cg,
@@ -721,13 +699,12 @@ class TrajectoryEstimator:
             if ok:
                 rel = (cost - cost_new) / max(cost, 1e-300)
                 cost = cost_new
+                sol.accept()
                 radius = radius / max(1.0 / 3.0, 1.0 - (2.0 * rho_ratio - 1.0) ** 3)
                 nu = 2.0
                 s.num_successful_steps += 1
             else:
-                self._restore(snap)
-                load_point()
-                ne.evaluate()
+                sol.evaluate()                               # the rows in device memory are the rejected point's: back to the current one
                 radius, nu = radius / nu, 2 * nu
                 s.num_unsuccessful_steps += 1
                 rel = 1.0
@@ -735,7 +712,9 @@ class TrajectoryEstimator:
             if progress:
                 print(f"{it + 1:4d}  {isum.cost:12.6e}  {isum.cost_change:10.2e}  {gmax:10.2e}  {step_norm:9.2e}  {rho_ratio:9.2e}  {radius:9.2e}  {n_cg}")
             stop = None
-            for cb, _ in self._callbacks:
+            for cb, update_state in self._callbacks:
+                if update_state:
+                    write_back()
                 res = cb(isum)
                 if res is not None and res is not CallbackReturnType.Continue:
                     stop = res
@@ -751,6 +730,7 @@ class TrajectoryEstimator:
             if radius < 1e-32:
                 term, s.message = TerminationType.Failure, "Trust region radius collapsed"
                 break
+        write_back()
         s.final_cost, s.termination_type = cost, term
         s.total_time_in_seconds = s.minimizer_time_in_seconds = time.perf_counter() - t_start
         self._problem.set_stream(0)

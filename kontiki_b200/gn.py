@@ -60,9 +60,12 @@ class DeviceNormalEquations:
         self.P_a = None if P_a is None else torch.from_numpy(np.ascontiguousarray(P_a)).to(self.dev)
         self.P_b = None if P_b is None else torch.from_numpy(np.ascontiguousarray(P_b)).to(self.dev)
 
-    def evaluate(self):
-        """One batched residual + Jacobian evaluation; returns the cost 1/2 sum |r|^2 summed over ranks."""
+    def evaluate(self, cost=True):
+        """One batched residual + Jacobian evaluation; returns the cost 1/2 sum rho(s) summed over ranks (cost=False: enqueue only, no
+        host synchronisation)."""
         self.p.evaluate_device(self.knots.data_ptr(), self.rho.data_ptr() if self.n_rho else 0, self.n_rho, self.flags, self.outs)
+        if not cost:
+            return None
         self.p.synchronize()
         # Ceres' cost is 1/2 sum rho(s); the rows carry the corrected residual, |r_c|^2 = a sqrt(s) in Huber's linear region (estimator._cost)
         cost = torch.zeros((), dtype=torch.float64, device=self.dev)
@@ -120,6 +123,143 @@ class DeviceNormalEquations:
         y = torch.zeros(self.n_loc, dtype=torch.float64, device=self.dev)
         self.p.jtj_diagonal_local(self.outs, 0 if self.P_a is None else self.P_a.data_ptr(), 0 if self.P_b is None else self.P_b.data_ptr(), y.data_ptr(), _lib.EVAL_DEVICE_ORDER)
         return self._reduce(y) * self.free
+
+
+class _DevArray:
+    """A raw device pointer as something torch.as_tensor() can wrap without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class DeviceSchurSolver:
+    """Levenberg-Marquardt step on the device (csrc/gn_device.cuh behind the ktk_gn_* calls of the C ABI): rho eliminated (implicit Schur
+    complement), block-Jacobi preconditioned CG on the knots with its scalars in device memory, Plus() on the device, every reduction a
+    fixed-order gather.  This class is the plumbing: it owns the parameter point on the device, enqueues the calls, and -- when
+    torch.distributed is initialised (rows sharded by kontiki_b200/sharding.py: every landmark's rows on ONE rank) -- all-reduces the
+    parameter-sized buffers between them (NCCL over NVLink).  Host round trips: one for the cost, one per `check_every` CG iterations,
+    one for the model decrease."""
+
+    def __init__(self, problem, split, n_a, n_b, n_rho, device, lm_locked=None, lock_a=False, lock_b=False, hubers=None, robust=True):
+        self.p, self.split, self.n_a, self.n_b, self.n_rho = problem, split, n_a, n_b, n_rho
+        self.dev = torch.device("cuda", device)
+        self.flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_DEVICE_ORDER | (_lib.EVAL_ROBUST if robust else 0)
+        self.lm_locked, self.lock_a, self.lock_b, self.hubers = lm_locked, lock_a, lock_b, hubers
+        self.outs, self._keep = [], []
+        for g in range(problem.num_groups):
+            n, cam = problem.group_size(g), problem.group_kind(g) in (_lib.STATIC_RS, _lib.NEWTON_RS)
+            r = torch.zeros((n, 2 if cam else (1 if problem.group_kind(g) == _lib.ORIENTATION else 3)), dtype=torch.float64, device=self.dev)
+            J = torch.zeros((n, problem.group_row_size(g)), dtype=torch.float64, device=self.dev)
+            idx = [torch.zeros(n, dtype=torch.int32, device=self.dev) for _ in range(4)]
+            self._keep.append((r, J, idx))
+            self.outs.append(dict(r=r.data_ptr(), J=J.data_ptr(), i0=idx[0].data_ptr(), i0_b=idx[1].data_ptr(), i0_c=idx[2].data_ptr(), i0_d=idx[3].data_ptr()))
+        self.stream = torch.cuda.current_stream(self.dev)
+        problem.set_stream(self.stream.cuda_stream)
+        self.prepared = False
+        self.knots = self.rho = self.knots_new = self.rho_new = None
+        self._buf = {}
+
+    # ---- point ------------------------------------------------------------------------------------------------------------------
+    def set_point(self, knots_flat, rho):
+        self.knots = torch.from_numpy(np.ascontiguousarray(knots_flat, np.float64)).to(self.dev)
+        self.rho = torch.from_numpy(np.ascontiguousarray(rho if rho is not None else np.zeros(0), np.float64)).to(self.dev)
+        self.knots_new, self.rho_new = torch.empty_like(self.knots), torch.empty_like(self.rho)
+
+    def point(self):
+        """(knots_flat, rho) of the current point as numpy arrays (one device -> host copy)."""
+        return self.knots.cpu().numpy(), self.rho.cpu().numpy()
+
+    def buf(self, name):
+        t = self._buf.get(name)
+        if t is None:
+            ptr, n = self.p.gn_buffer(name)
+            t = self._buf[name] = torch.as_tensor(_DevArray(ptr, n), device=self.dev) if n > 0 and ptr else torch.zeros(0, dtype=torch.float64, device=self.dev)
+        return t
+
+    def _reduce(self, *names):
+        d = _dist()
+        if d is not None:
+            for n in names:
+                t = self.buf(n)
+                if t.numel():
+                    d.all_reduce(t)
+
+    # ---- steps ------------------------------------------------------------------------------------------------------------------
+    def evaluate(self, at_new=False, cost=True):
+        """Residuals + Jacobian rows at the current (or the candidate) point; returns the cost 1/2 sum rho(s) over all ranks
+        (cost=False: enqueue only, no host synchronisation)."""
+        k, r = (self.knots_new, self.rho_new) if at_new else (self.knots, self.rho)
+        self.p.evaluate_device(k.data_ptr(), r.data_ptr() if self.n_rho else 0, self.n_rho, self.flags, self.outs)
+        if not cost and self.prepared:
+            return None
+        if not self.prepared:
+            self.p.synchronize()                      # raises where a measurement left the trajectory
+            self.p.gn_prepare(self.flags, self.outs, self.n_rho, self.lm_locked, self.lock_a, self.lock_b, self.hubers)
+            self.prepared, self._buf = True, {}
+        self.p.gn_call("cost")
+        scal = self.buf("scal")
+        cost = scal[12:13].clone()
+        d = _dist()
+        if d is not None:
+            d.all_reduce(cost)
+        self.p.synchronize()
+        return float(cost.item())
+
+    def linearize(self, radius):
+        """Normal equations at the current point (the rows of the last evaluate() must be the current point's); returns max |gradient|."""
+        import ctypes as C
+        self.p.gn_call("linearize_local", C.c_void_p(self.knots.data_ptr()), C.c_void_p(self.rho.data_ptr()) if self.n_rho else None)
+        self.p.gn_call("gradient_local")
+        self._reduce("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b")
+        gmax = torch.zeros(1, dtype=torch.float64, device=self.dev)
+        for name, locked in (("z_a", self.lock_a), ("z_b", self.lock_b)):
+            t = self.buf(name)
+            if t.numel() and not locked:
+                gmax = torch.maximum(gmax, t.abs().max().reshape(1))
+        g = self.buf("grho")
+        if g.numel():
+            free = torch.ones_like(g) if self.lm_locked is None else torch.from_numpy(1.0 - np.asarray(self.lm_locked, np.float64)).to(self.dev)
+            gmax = torch.maximum(gmax, (g * free).abs().max().reshape(1))
+        self.p.gn_call("linearize_rhs", C.c_double(radius))
+        self._reduce("q_a", "q_b")
+        return gmax
+
+    def solve(self, radius, tol=1e-6, max_iter=300, check_every=8):
+        """CG on the reduced system; returns (iterations, |r|/|b|)."""
+        import ctypes as C
+        self.p.gn_call("pcg_begin", C.c_double(radius), C.c_double(tol), C.c_int32(max_iter))
+        it, done, rel = 0, False, 1.0
+        while not done:
+            for _ in range(check_every):
+                self.p.gn_call("product")
+                self._reduce("q_a", "q_b")
+                self.p.gn_call("pcg_update")
+            it, done, rel = self.p.gn_pcg_status()
+        return it, rel
+
+    def finish(self):
+        """delta_rho, the model decrease -(delta^T g + 1/2 delta^T J^T J delta) and |delta|; retracts into the candidate point."""
+        import ctypes as C
+        self.p.gn_call("finish_local")
+        if _dist() is not None:
+            self.p.gn_call("finish_mask")
+            self._reduce("drho")
+        self.p.gn_call("model_local")
+        scal = self.buf("scal")
+        sums = scal[9:11].clone()
+        d = _dist()
+        if d is not None:
+            d.all_reduce(sums)
+        dr = self.buf("drho")
+        step2 = scal[11:12] + ((dr * dr).sum().reshape(1) if dr.numel() else 0.0)
+        self.p.gn_call("retract", C.c_void_p(self.knots.data_ptr()), C.c_void_p(self.rho.data_ptr()) if self.n_rho else None, C.c_void_p(self.knots_new.data_ptr()),
+                       C.c_void_p(self.rho_new.data_ptr()) if self.n_rho else None)
+        vals = torch.cat([sums, step2]).cpu().numpy()        # the one host round trip of this phase
+        return -(float(vals[0]) + 0.5 * float(vals[1])), float(np.sqrt(vals[2]))
+
+    def accept(self):
+        self.knots, self.knots_new = self.knots_new, self.knots
+        self.rho, self.rho_new = self.rho_new, self.rho
 
 
 def pcg(apply_A, b, Minv, tol=1e-10, max_iter=500):
