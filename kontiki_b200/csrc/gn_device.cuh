@@ -134,77 +134,100 @@ __device__ __forceinline__ double gn_warp_sum(double v) {      // fixed butterfl
   return v;
 }
 
-// y_loc[k] = P_k^T sum_{rows whose window covers knot k} J_block^T x_row : one warp per knot, gather in the fixed order of the sorted row lists.
-__global__ void k_gn_gather(const GnWinList L, int n_knots, int width, int lw, const double* __restrict__ P, double* __restrict__ y) {
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// y_loc[k] = P_k^T sum_{rows whose window covers knot k} J_block^T x_row : kGnWarpsPerKnot warps per knot, gather in the fixed order of the
+// sorted row lists (lane l of warp w takes rows w*32 + l, + 32*kGnWarpsPerKnot, ...), fixed shuffle tree, fixed order over the warps.
+constexpr int kGnWarpsPerKnot = 4;
+template <int W>
+__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_gather(const GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ y) {
+  __shared__ double sh[kGnWarpsPerKnot][8];
+  const int k = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (k >= n_knots) return;
-  double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double acc[W];
+#pragma unroll
+  for (int c = 0; c < W; ++c) acc[c] = 0.0;
   for (int wi = 0; wi < L.n; ++wi) {
     const GnWinDev& w = L.w[wi];
     const int f0 = max(k - 3, 0);
-    for (int j = w.start[f0] + lane; j < w.start[k + 1]; j += 32) {
+    for (int j = w.start[f0] + threadIdx.x; j < w.start[k + 1]; j += 32 * kGnWarpsPerKnot) {
       const int row = w.order[j], b = k - w.fk[j];
-      const double* Jb = w.J + (size_t)row * w.row_len + w.j_off + b * w.nres * w.width;
+      const double* Jb = w.J + (size_t)row * w.row_len + w.j_off + b * w.nres * W;
       const double* xr = w.x + (size_t)row * w.nres;
       for (int r = 0; r < w.nres; ++r) {
         const double xv = xr[r];
 #pragma unroll
-        for (int c = 0; c < 7; ++c) if (c < w.width) acc[c] += Jb[r * w.width + c] * xv;
+        for (int c = 0; c < W; ++c) acc[c] += Jb[r * W + c] * xv;
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 7; ++c) acc[c] = gn_warp_sum(acc[c]);
-  if (lane < lw) {
+  for (int c = 0; c < W; ++c) { acc[c] = gn_warp_sum(acc[c]); if (lane == 0) sh[wid][c] = acc[c]; }
+  __syncthreads();
+  if (threadIdx.x < lw) {
     double s = 0.0;
-    for (int c = 0; c < width; ++c) s += P[((size_t)k * width + c) * lw + lane] * acc[c];
-    y[(size_t)k * lw + lane] = s;
+#pragma unroll
+    for (int c = 0; c < W; ++c) {
+      double a = 0.0;
+#pragma unroll
+      for (int q = 0; q < kGnWarpsPerKnot; ++q) a += sh[q][c];
+      s += P[((size_t)k * W + c) * lw + threadIdx.x] * a;
+    }
+    y[(size_t)k * lw + threadIdx.x] = s;
   }
 }
 
 // B_kk = P_k^T (sum_rows C_k^T C_k) P_k, C_k = the row's column block of knot k.  A camera row whose reference and observation windows both
 // cover knot k has C_k = A + B (ONE parameter block, spline_base.h:391-394): the observation-window pass (role 2) uses A + B, the
 // reference-window pass (role 1) skips such rows.  Output: n_knots x lw x lw (row-major), the exact diagonal block of J^T J in local coordinates.
-__global__ void k_gn_blocks(const GnWinList L, int n_knots, int width, int lw, const double* __restrict__ P, double* __restrict__ Bd) {
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+template <int W>
+__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_blocks(const GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ Bd) {
+  constexpr int NS = W * (W + 1) / 2;
+  __shared__ double sh[kGnWarpsPerKnot][NS];
+  __shared__ double Hs[NS];
+  const int k = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (k >= n_knots) return;
-  double H[28];
+  double H[NS];
 #pragma unroll
-  for (int i = 0; i < 28; ++i) H[i] = 0.0;
+  for (int i = 0; i < NS; ++i) H[i] = 0.0;
   for (int wi = 0; wi < L.n; ++wi) {
     const GnWinDev& w = L.w[wi];
     const int f0 = max(k - 3, 0);
-    for (int j = w.start[f0] + lane; j < w.start[k + 1]; j += 32) {
+    for (int j = w.start[f0] + threadIdx.x; j < w.start[k + 1]; j += 32 * kGnWarpsPerKnot) {
       const int row = w.order[j], b = k - w.fk[j];
-      const double* Jb = w.J + (size_t)row * w.row_len + w.j_off + b * w.nres * w.width;
+      const double* Jb = w.J + (size_t)row * w.row_len + w.j_off + b * w.nres * W;
       int pb = -1;
       if (w.role != 0) { pb = k - w.partner_first[row]; if (pb < 0 || pb > 3) pb = -1; }
       if (w.role == 1 && pb >= 0) continue;
-      const double* Jp = pb >= 0 ? w.J + (size_t)row * w.row_len + w.partner_j_off + pb * w.nres * w.width : nullptr;
+      const double* Jp = pb >= 0 ? w.J + (size_t)row * w.row_len + w.partner_j_off + pb * w.nres * W : nullptr;
       for (int r = 0; r < w.nres; ++r) {
-        double cr[7];
-        for (int c = 0; c < w.width; ++c) cr[c] = Jb[r * w.width + c] + (Jp ? Jp[r * w.width + c] : 0.0);
+        double cr[W];
+#pragma unroll
+        for (int c = 0; c < W; ++c) cr[c] = Jb[r * W + c] + (Jp ? Jp[r * W + c] : 0.0);
         int q = 0;
-        for (int c = 0; c < w.width; ++c)
-          for (int c2 = c; c2 < w.width; ++c2) H[q++] += cr[c] * cr[c2];
+#pragma unroll
+        for (int c = 0; c < W; ++c)
+#pragma unroll
+          for (int c2 = c; c2 < W; ++c2) H[q++] += cr[c] * cr[c2];
       }
     }
   }
-  const int nsym = width * (width + 1) / 2;
-  for (int i = 0; i < nsym; ++i) H[i] = gn_warp_sum(H[i]);
-  // lane (d, e) with d * lw + e < lw*lw: (P^T H P)[d][e]
-  for (int le = lane; le < lw * lw; le += 32) {
-    const int d = le / lw, e = le % lw;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) { H[i] = gn_warp_sum(H[i]); if (lane == 0) sh[wid][i] = H[i]; }
+  __syncthreads();
+  if (threadIdx.x < NS) { double a = 0.0; for (int q = 0; q < kGnWarpsPerKnot; ++q) a += sh[q][threadIdx.x]; Hs[threadIdx.x] = a; }
+  __syncthreads();
+  // thread (d, e): (P^T H P)[d][e]
+  if (threadIdx.x < lw * lw) {
+    const int d = threadIdx.x / lw, e = threadIdx.x % lw;
     double s = 0.0;
     int q = 0;
-    for (int c = 0; c < width; ++c)
-      for (int c2 = c; c2 < width; ++c2) {
-        const double h = H[q++];
-        const double pcd = P[((size_t)k * width + c) * lw + d], pce = P[((size_t)k * width + c) * lw + e];
-        const double p2d = P[((size_t)k * width + c2) * lw + d], p2e = P[((size_t)k * width + c2) * lw + e];
+    for (int c = 0; c < W; ++c)
+      for (int c2 = c; c2 < W; ++c2) {
+        const double h = Hs[q++];
+        const double pcd = P[((size_t)k * W + c) * lw + d], pce = P[((size_t)k * W + c) * lw + e];
+        const double p2d = P[((size_t)k * W + c2) * lw + d], p2e = P[((size_t)k * W + c2) * lw + e];
         s += (c == c2) ? h * pcd * pce : h * (pcd * p2e + p2d * pce);
       }
-    Bd[(size_t)k * lw * lw + le] = s;
+    Bd[(size_t)k * lw * lw + threadIdx.x] = s;
   }
 }
 
@@ -268,47 +291,85 @@ __device__ __forceinline__ void gn_precond(const double* Minv, int lw, const dou
     z[(size_t)k * lw + d] = s;
   }
 }
-// x = 0, r = b, z = M r, p = z, rz = r.z, |b|^2      (ONE CTA of 1024 threads: the vectors have a few 10^4 entries)
-__global__ void __launch_bounds__(1024) k_gn_pcg_init(const GnVec v, GnScal* s, double tol, int max_iter) {
-  __shared__ double sh[33];
+// The CG vector updates run on kGnCtas CTAs; every dot product is two-stage and reproducible: a CTA reduces its (fixed) slice with the fixed
+// tree above into part[slot][cta], and the NEXT kernel of the chain lets every CTA add the kGnCtas partials in index order.
+constexpr int kGnCtas = 64, kGnThreads = 256;
+__device__ __forceinline__ double gn_cta_sum(double v, double* sh) {      // blockDim.x == kGnThreads (8 warps)
+  v = gn_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kGnThreads / 32; ++w) t += sh[w];
+  return t;
+}
+__device__ __forceinline__ double gn_total(const double* part) {
+  double t = 0.0;
+  for (int i = 0; i < kGnCtas; ++i) t += part[i];
+  return t;
+}
+// x = 0, r = b, z = M r, p = z; partials of r.z and |b|^2
+__global__ void __launch_bounds__(kGnThreads) k_gn_pcg_init(const GnVec v, double* __restrict__ part) {
+  __shared__ double sh[8];
   double rz = 0.0, bb = 0.0;
   for (int sp = 0; sp < 2; ++sp)
-    for (int k = threadIdx.x; k < v.n[sp]; k += blockDim.x) {
+    for (int k = blockIdx.x * kGnThreads + threadIdx.x; k < v.n[sp]; k += kGnCtas * kGnThreads) {
       const int lw = v.lw[sp];
       for (int d = 0; d < lw; ++d) { const size_t i = (size_t)k * lw + d; v.x[sp][i] = 0.0; v.r[sp][i] = v.b[sp][i]; }
       gn_precond(v.Minv[sp], lw, v.r[sp], v.z[sp], k);
       for (int d = 0; d < lw; ++d) { const size_t i = (size_t)k * lw + d; v.p[sp][i] = v.z[sp][i]; rz += v.r[sp][i] * v.z[sp][i]; bb += v.b[sp][i] * v.b[sp][i]; }
     }
-  rz = gn_block_sum(rz, sh);
-  bb = gn_block_sum(bb, sh);
-  if (threadIdx.x == 0) { s->rz = rz; s->bnorm2 = bb; s->rnorm2 = bb; s->tol2 = tol * tol; s->iter = 0; s->done = (bb == 0.0) ? 1 : 0; s->max_iter = max_iter; }
+  rz = gn_cta_sum(rz, sh);
+  bb = gn_cta_sum(bb, sh);
+  if (threadIdx.x == 0) { part[blockIdx.x] = rz; part[kGnCtas + blockIdx.x] = bb; }
 }
-// one CG update with q = S p (this kernel adds the damping term D p): alpha, x, r, z, beta, p; sets `done` when |r| <= tol |b|
-__global__ void __launch_bounds__(1024) k_gn_pcg_update(const GnVec v, GnScal* s) {
-  __shared__ double sh[33];
+__global__ void k_gn_pcg_init_scal(const double* __restrict__ part, GnScal* s, double tol, int max_iter) {
+  const double rz = gn_total(part), bb = gn_total(part + kGnCtas);
+  s->rz = rz; s->bnorm2 = bb; s->rnorm2 = bb; s->tol2 = tol * tol; s->iter = 0; s->done = (bb == 0.0) ? 1 : 0; s->max_iter = max_iter;
+}
+// CG update, three kernels: (1) q += D p, partials of p.q; (2) alpha, x, r, z = M r, partials of r.z and r.r; (3) beta, p, scalars.
+__global__ void __launch_bounds__(kGnThreads) k_gn_pcg_a(const GnVec v, const GnScal* __restrict__ s, double* __restrict__ part) {
+  __shared__ double sh[8];
   if (s->done) return;
   double pq = 0.0;
   for (int sp = 0; sp < 2; ++sp)
-    for (int i = threadIdx.x; i < v.n[sp] * v.lw[sp]; i += blockDim.x) { const double q = v.q[sp][i] + v.damp[sp][i] * v.p[sp][i]; v.q[sp][i] = q; pq += v.p[sp][i] * q; }
-  pq = gn_block_sum(pq, sh);
-  const double alpha = s->rz / pq;
+    for (int i = blockIdx.x * kGnThreads + threadIdx.x; i < v.n[sp] * v.lw[sp]; i += kGnCtas * kGnThreads) { const double q = v.q[sp][i] + v.damp[sp][i] * v.p[sp][i]; v.q[sp][i] = q; pq += v.p[sp][i] * q; }
+  pq = gn_cta_sum(pq, sh);
+  if (threadIdx.x == 0) part[blockIdx.x] = pq;
+}
+__global__ void __launch_bounds__(kGnThreads) k_gn_pcg_b(const GnVec v, const GnScal* __restrict__ s, const double* __restrict__ part, double* __restrict__ part2) {
+  __shared__ double sh[8];
+  if (s->done) return;
+  const double alpha = s->rz / gn_total(part);
   double rz = 0.0, rr = 0.0;
   for (int sp = 0; sp < 2; ++sp)
-    for (int k = threadIdx.x; k < v.n[sp]; k += blockDim.x) {
+    for (int k = blockIdx.x * kGnThreads + threadIdx.x; k < v.n[sp]; k += kGnCtas * kGnThreads) {
       const int lw = v.lw[sp];
       for (int d = 0; d < lw; ++d) { const size_t i = (size_t)k * lw + d; v.x[sp][i] += alpha * v.p[sp][i]; v.r[sp][i] -= alpha * v.q[sp][i]; }
       gn_precond(v.Minv[sp], lw, v.r[sp], v.z[sp], k);
       for (int d = 0; d < lw; ++d) { const size_t i = (size_t)k * lw + d; rz += v.r[sp][i] * v.z[sp][i]; rr += v.r[sp][i] * v.r[sp][i]; }
     }
-  rz = gn_block_sum(rz, sh);
-  rr = gn_block_sum(rr, sh);
+  rz = gn_cta_sum(rz, sh);
+  rr = gn_cta_sum(rr, sh);
+  if (threadIdx.x == 0) { part2[blockIdx.x] = rz; part2[kGnCtas + blockIdx.x] = rr; }
+}
+__global__ void __launch_bounds__(kGnThreads) k_gn_pcg_c(const GnVec v, GnScal* s, const double* __restrict__ part, const double* __restrict__ part2, int* __restrict__ ticket) {
+  if (s->done) return;
+  const double rz = gn_total(part2), rr = gn_total(part2 + kGnCtas);
   const double beta = rz / s->rz;
   for (int sp = 0; sp < 2; ++sp)
-    for (int i = threadIdx.x; i < v.n[sp] * v.lw[sp]; i += blockDim.x) v.p[sp][i] = v.z[sp][i] + beta * v.p[sp][i];
+    for (int i = blockIdx.x * kGnThreads + threadIdx.x; i < v.n[sp] * v.lw[sp]; i += kGnCtas * kGnThreads) v.p[sp][i] = v.z[sp][i] + beta * v.p[sp][i];
+  // the LAST CTA to finish publishes the scalars (every CTA has read s->rz / s->done by then)
+  __shared__ int last;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    s->pq = pq; s->alpha = alpha; s->beta = beta; s->rz = rz; s->rnorm2 = rr; s->iter += 1;
+  if (threadIdx.x == 0) { __threadfence(); last = (atomicAdd(ticket, 1) == kGnCtas - 1); }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    const double pq = gn_total(part);
+    s->pq = pq; s->alpha = s->rz / pq; s->beta = beta; s->rz = rz; s->rnorm2 = rr; s->iter += 1;
     if (rr <= s->tol2 * s->bnorm2 || s->iter >= s->max_iter) s->done = 1;
+    *ticket = 0;
   }
 }
 // b = -y (right-hand side of the reduced system from the gathered gradient)

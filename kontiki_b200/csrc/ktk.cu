@@ -1892,6 +1892,7 @@ struct GnState {
   DevBuf<double> c, cd, grho, t, s, drho, partial, own;
   DevBuf<unsigned char> lm_locked; bool have_locked = false;
   DevBuf<GnScal> scal; GnScal* h_scal = nullptr;
+  DevBuf<double> part; DevBuf<int> ticket;      // CG dot-product partials (4 x kGnCtas) and the last-CTA ticket
   GnWinList lists[2];
   const double* d_knots = nullptr; const double* d_rho = nullptr;
   ~GnState() { for (auto q : g) delete q; if (h_scal) cudaFreeHost(h_scal); }
@@ -1951,7 +1952,10 @@ void gn_rows_fix(ktk_problem* p, GnState& S, bool from_r) {
 void gn_gather(ktk_problem* p, GnState& S, double* const y[2]) {
   for (int sp = 0; sp < 2; ++sp)
     if (S.n[sp] > 0) {
-      k_gn_gather<<<gn_blocks((int64_t)S.n[sp] * 32, 128), 128, 0, p->stream>>>(S.lists[sp], S.n[sp], S.width[sp], S.lw[sp], S.P[sp].p, y[sp]);
+      const int th = 32 * kGnWarpsPerKnot;
+      if (S.width[sp] == 7) k_gn_gather<7><<<S.n[sp], th, 0, p->stream>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, y[sp]);
+      else if (S.width[sp] == 4) k_gn_gather<4><<<S.n[sp], th, 0, p->stream>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, y[sp]);
+      else k_gn_gather<3><<<S.n[sp], th, 0, p->stream>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, y[sp]);
       p->launches += 1;
     }
 }
@@ -2058,7 +2062,8 @@ int ktk_gn_prepare(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, 
   int64_t maxrows = 1;
   for (auto gp : S->g) maxrows = std::max<int64_t>(maxrows, gp->n);
   if ((st = S->partial.resize((size_t)2 * gn_blocks(maxrows, 256) + 2))) return st;
-  if ((st = S->scal.resize(1))) return st;
+  if ((st = S->scal.resize(1)) || (st = S->part.resize(4 * kGnCtas)) || (st = S->ticket.resize(1))) return st;
+  KTK_CUDA(cudaMemsetAsync(S->ticket.p, 0, sizeof(int), s));
   if (cudaHostAlloc(&S->h_scal, sizeof(GnScal), cudaHostAllocDefault) != cudaSuccess) return fail(KTK_ECUDA, "cudaHostAlloc failed");
   if (lm_locked && n_rho > 0) {
     std::vector<unsigned char> l(lm_locked, lm_locked + n_rho);
@@ -2106,7 +2111,13 @@ int ktk_gn_linearize_local(ktk_problem* p, const double* d_knots, const double* 
   if ((st = gn_lm_sums(p, S, false, true, S.c.p)) || (st = gn_lm_sums(p, S, true, false, S.grho.p))) return st;
   if (S.n_rho > 0) KTK_CUDA(cudaMemcpyAsync(S.own.p, S.c.p, sizeof(double) * (size_t)S.n_rho, cudaMemcpyDeviceToDevice, s));      // > 0 where this rank holds rows of the landmark
   for (int sp = 0; sp < 2; ++sp)
-    if (S.n[sp] > 0) { k_gn_blocks<<<gn_blocks((int64_t)S.n[sp] * 32, 128), 128, 0, s>>>(S.lists[sp], S.n[sp], S.width[sp], S.lw[sp], S.P[sp].p, S.Bd[sp].p); p->launches += 1; }
+    if (S.n[sp] > 0) {
+      const int th = 32 * kGnWarpsPerKnot;
+      if (S.width[sp] == 7) k_gn_blocks<7><<<S.n[sp], th, 0, s>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, S.Bd[sp].p);
+      else if (S.width[sp] == 4) k_gn_blocks<4><<<S.n[sp], th, 0, s>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, S.Bd[sp].p);
+      else k_gn_blocks<3><<<S.n[sp], th, 0, s>>>(S.lists[sp], S.n[sp], S.lw[sp], S.P[sp].p, S.Bd[sp].p);
+      p->launches += 1;
+    }
   p->launches += 2;
   KTK_CUDA(cudaGetLastError());
   return KTK_OK;
@@ -2148,8 +2159,9 @@ int ktk_gn_pcg_begin(ktk_problem* p, double radius, double tol, int32_t max_iter
       k_gn_negate<<<gn_blocks((int64_t)S.n[sp] * S.lw[sp], 256), 256, 0, s>>>(S.q[sp].p, S.n[sp] * S.lw[sp], S.free_[sp], S.b[sp].p);
       k_gn_invert_blocks<<<gn_blocks(S.n[sp], 64), 64, 0, s>>>(S.Bd[sp].p, S.n[sp], S.lw[sp], 1.0 / radius, S.free_[sp], S.Minv[sp].p, S.damp[sp].p);
     }
-  k_gn_pcg_init<<<1, 1024, 0, s>>>(gn_vec(S), S.scal.p, tol, max_iter);
-  p->launches += 5;
+  k_gn_pcg_init<<<kGnCtas, kGnThreads, 0, s>>>(gn_vec(S), S.part.p);
+  k_gn_pcg_init_scal<<<1, 1, 0, s>>>(S.part.p, S.scal.p, tol, max_iter);
+  p->launches += 6;
   KTK_CUDA(cudaGetLastError());
   return KTK_OK;
 }
@@ -2172,8 +2184,11 @@ int ktk_gn_product(ktk_problem* p) {
 }
 int ktk_gn_pcg_update(ktk_problem* p) {
   GN_STATE();
-  k_gn_pcg_update<<<1, 1024, 0, s>>>(gn_vec(S), S.scal.p);
-  p->launches += 1;
+  const GnVec v = gn_vec(S);
+  k_gn_pcg_a<<<kGnCtas, kGnThreads, 0, s>>>(v, S.scal.p, S.part.p);
+  k_gn_pcg_b<<<kGnCtas, kGnThreads, 0, s>>>(v, S.scal.p, S.part.p, S.part.p + 2 * kGnCtas);
+  k_gn_pcg_c<<<kGnCtas, kGnThreads, 0, s>>>(v, S.scal.p, S.part.p, S.part.p + 2 * kGnCtas, S.ticket.p);
+  p->launches += 3;
   return KTK_OK;
 }
 // Synchronises and reports the CG state: iterations done, convergence flag, |r| / |b|.
