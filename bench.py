@@ -360,7 +360,7 @@ def main():
 
         def gn_product(e):
             e.p.gn_call("product")
-            e._reduce("q_a", "q_b")
+            e._reduce("qq")
             e.p.gn_call("pcg_update")
 
     def step_device():
@@ -444,11 +444,11 @@ def main():
             return float(t.item())
         names = ("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b", "q_a", "q_b")
         parts = {"evaluate": timed(lambda: ne.evaluate(cost=False)), "linearize": timed(lambda: gn_linearize(ne)), "schur_product": timed(lambda: gn_product(ne))}
-        ar = {"linearize": ("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b"), "rhs": ("q_a", "q_b"), "product": ("q_a", "q_b")}
+        ar = {"linearize": ("lin",), "rhs": ("qq",), "product": ("qq",)}
         ar_bytes = {k_: int(sum(ne.buf(n_).numel() for n_ in v_) * 8) for k_, v_ in ar.items()}
         ar_ms = {k_: (timed(lambda v_=v_: ne._reduce(*v_), 50) if world > 1 else 0.0) for k_, v_ in ar.items()}
         strong_info = {"collective": ("ncclAllReduce(sum, fp64) of parameter-sized buffers: landmark blocks + gradient + diagonal knot blocks once per linearisation, "
-                                      "the reduced right-hand side once, S p once per CG iteration") if world > 1 else "none (one rank)",
+                                      "the reduced right-hand side once, S p once per CG iteration; each exchange is ONE collective on a contiguous buffer") if world > 1 else "none (one rank)",
                        "allreduce_bytes": ar_bytes, "allreduce_ms": ar_ms, "ms": parts, "rows_this_rank": int(n_meas), "rows_total": int(n_total),
                        "step": "evaluation + LM linearisation (c, g_rho, B_kk, gradient, reduced rhs, block-Jacobi preconditioner) + one implicit-Schur product and CG update"}
         ne.evaluate(cost=False)

@@ -65,6 +65,8 @@ inline bool is_span_camera(int kind) { return kind == KTK_NEWTON_RS || kind == K
 constexpr int kThreads = KTK_THREADS;            // measurement rows per CTA (one per thread), IMU and landmark kernels
 constexpr int kCamThreads = KTK_CAM_THREADS;     // ... static-RS observation kernel
 constexpr int kImuRow = 84, kImuRowStride = 86;     // doubles; stride keeps rows 16-B aligned and off the same banks
+constexpr int kAccelRowStride = 110;                 // accelerometer rows: + 24 doubles of scratch behind the row (accel_se3<PARK>)
+__host__ __device__ constexpr int imu_stride(int which) { return which == 1 ? kAccelRowStride : kImuRowStride; }
 constexpr int kCamRow = 114;                          // packed camera row in global memory: 112 knot-block doubles + d r/d rho (2)
 #ifndef KTK_CAM_STRIDE
 #define KTK_CAM_STRIDE 92
@@ -154,8 +156,9 @@ __device__ __forceinline__ void warp_gather_records(double* wbase, const double*
 
 // K0, fused with the knot packing: reads the caller's n x 7 knots, writes the 64-B knot records (thread dir == 14 of pair p packs knot p,
 // pair 1 also knot 0) and the pair records.  One launch instead of two: the step is a chain of short kernels and each link costs ~3 us.
-__global__ void k_pair_prepass(const double* __restrict__ k7, int n_knots, double* __restrict__ k8, double* __restrict__ pairs) {
+__global__ void k_pair_prepass(const double* __restrict__ k7, int n_knots, double* __restrict__ k8, double* __restrict__ pairs, int* __restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && err) *err = 0;      // the first kernel of an evaluation clears the status word (every writer runs in a later kernel): no memset node
   const int p = 1 + i / 15, dir = i % 15;
   if (p >= n_knots) return;
   pair_prepass_item<7>(k7, p, dir, pairs);
@@ -201,13 +204,10 @@ __device__ __forceinline__ ImuIn imu_load(const ImuArgs& a, int i) {
 // WHICH: 0 gyroscope, 1 accelerometer, 2 PositionMeasurement (3 residuals, y[3], rows [4][3][7]); 3 OrientationMeasurement (ONE residual,
 // y = q (x,y,z,w), rows [4][1][7])
 template <int WHICH>
-__global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACCEL_MINB) k_imu(const ImuArgs a) {
-  constexpr int NR = WHICH == 3 ? 1 : 3, ROW = NR * 28, LROW = NR * 24;
-  extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void imu_tile(const ImuArgs& a, int tile, double* wbase) {
+  constexpr int NR = WHICH == 3 ? 1 : 3, ROW = NR * 28, LROW = NR * 24, STRIDE = imu_stride(WHICH);
   const int lane = threadIdx.x & 31;
-  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kImuRowStride;
-  double* row = wbase + lane * kImuRowStride;
-  const int tile = warp_tile();
+  double* row = wbase + lane * STRIDE;
   if (tile * 32 >= a.n) return;
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
     if (WHICH != 3) { y[0] -= a.imu.bias[0]; y[1] -= a.imu.bias[1]; y[2] -= a.imu.bias[2]; }   // r = w (y - (model + bias))
     double r[3];
     int i0 = -1;
-    const int st = imu_row(WHICH, a.sp, a.imu, a.knots, a.pairs, cur.t, y, cur.w, r, row, &i0);
+    const int st = imu_row<WHICH == 1>(WHICH, a.sp, a.imu, a.knots, a.pairs, cur.t, y, cur.w, r, row, &i0, row + kImuRowStride);
     if (st != 0) {
       atomicMin(a.err, st);
       r[0] = r[1] = r[2] = nan("");
@@ -234,9 +234,14 @@ __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACC
   }
   __syncwarp();
   if (wantJ) {
-    if (local) warp_scatter_rows<LROW, kImuRowStride, LROW>(wbase, a.J, cur.perm, lane);
-    else warp_scatter_rows<ROW, kImuRowStride, ROW>(wbase, a.J, cur.perm, lane);
+    if (local) warp_scatter_rows<LROW, STRIDE, LROW>(wbase, a.J, cur.perm, lane);
+    else warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, cur.perm, lane);
   }
+}
+template <int WHICH>
+__global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACCEL_MINB) k_imu(const ImuArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  imu_tile<WHICH>(a, warp_tile(), smem + (size_t)(threadIdx.x >> 5) * 32 * imu_stride(WHICH));
 }
 
 struct RefArgs {
@@ -248,12 +253,10 @@ struct RefArgs {
 
 // Landmark-reference records come out in record order: a warp's 32 records are one contiguous 32 x 736 B block,
 // written with a single TMA bulk store issued by lane 0.
-__global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
-  extern __shared__ __align__(16) double smem[];
+__device__ __forceinline__ void landmark_tile(const RefArgs& a, int tile, double* wbase) {
   const int lane = threadIdx.x & 31;
-  double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kRefStride;
   double* row = wbase + lane * kRefStride;
-  const int base = (blockIdx.x * kThreads + threadIdx.x) & ~31;
+  const int base = tile * 32;
   const int i = base + lane;
   if (base >= a.n) return;
   if (i < a.n) {
@@ -271,6 +274,40 @@ __global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
     bulk_store(a.recs + (size_t)base * kRefStride, wbase, (unsigned)(min(32, a.n - base) * kRefStride * 8));
     bulk_store_wait_read();
   }
+}
+__global__ void __launch_bounds__(kThreads) k_landmark_ref(const RefArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  landmark_tile(a, warp_tile(), smem + (size_t)(threadIdx.x >> 5) * 32 * kRefStride);
+}
+
+// The "short" kernels of one evaluation -- every IMU-like group (gyroscope / accelerometer / position / orientation rows) and every camera
+// group's landmark-record table -- in ONE launch: each is about one wave of one-warp CTAs on its own (1.32 waves on H1: two tile latencies
+// where 1.3 would do, three times per evaluation).  Segments are contiguous ranges of blockIdx, so co-resident CTAs mostly run the same
+// code path (running them as concurrent kernels lost to instruction-cache thrash, profiles/r1g_kernel_experiments.md).
+constexpr int kShortMaxImu = 4, kShortMaxRef = 2;
+struct ShortBatch {
+  int n_imu, n_ref;
+  int first[kShortMaxImu + kShortMaxRef + 1];      // first CTA of every segment (IMU segments, then landmark segments), then the total
+  int which[kShortMaxImu];
+  ImuArgs imu[kShortMaxImu];
+  RefArgs ref[kShortMaxRef];
+};
+__global__ void __launch_bounds__(32) k_short_batch(const __grid_constant__ ShortBatch b) {
+  extern __shared__ __align__(16) double smem[];
+  const int cta = blockIdx.x;
+#pragma unroll 1
+  for (int k = 0; k < b.n_imu; ++k)
+    if (cta < b.first[k + 1]) {
+      const int tile = cta - b.first[k];
+      if (b.which[k] == 0) imu_tile<0>(b.imu[k], tile, smem);
+      else if (b.which[k] == 1) imu_tile<1>(b.imu[k], tile, smem);
+      else if (b.which[k] == 2) imu_tile<2>(b.imu[k], tile, smem);
+      else imu_tile<3>(b.imu[k], tile, smem);
+      return;
+    }
+#pragma unroll 1
+  for (int k = 0; k < b.n_ref; ++k)
+    if (cta < b.first[b.n_imu + k + 1]) { landmark_tile(b.ref[k], cta - b.first[b.n_imu + k], smem); return; }
 }
 
 struct CamArgs {
@@ -490,8 +527,9 @@ constexpr int kAccelSplitRow = 84, kAccelSplitStride = 86;
 constexpr int kPosSplitRow = 36, kPosSplitStride = 38;       // PositionMeasurement on a split trajectory: [4 R3 knots][3][3]
 constexpr int kOriSplitRow = 16, kOriSplitStride = 18;       // OrientationMeasurement on a split trajectory: [4 SO3 knots][1][4]
 
-__global__ void k_pack_vecs(const double* __restrict__ v3, int n, double* __restrict__ v4) {
+__global__ void k_pack_vecs(const double* __restrict__ v3, int n, double* __restrict__ v4, int* __restrict__ err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && err) *err = 0;
   if (i >= n * kVecStride) return;
   const int k = i / kVecStride, c = i % kVecStride;
   v4[i] = c < 3 ? v3[(size_t)k * 3 + c] : 0.0;
@@ -997,6 +1035,8 @@ struct ktk_problem {
   bool profiling = false;
   bool graphs_enabled = true;
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
+  int fuse_short = 1;             // 1: all IMU-like groups of an evaluation in one launch (k_short_batch); 2: + the landmark tables (measured slower, r2g); 0: off.  KTK_FUSE_SHORT overrides (A/B)
+  ShortBatch short_batch;
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<uint64_t> graph_key;
   int64_t graph_launches = 0;
@@ -1201,7 +1241,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   if (cudaHostAlloc(&p->h_err, sizeof(int), cudaHostAllocDefault) != cudaSuccess) { delete p; return fail(KTK_ECUDA, "cudaHostAlloc failed"); }
   // opt in to the shared-memory carve-out the row staging needs
   cudaFuncSetAttribute(k_imu<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
-  cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
+  cudaFuncSetAttribute(k_imu<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelRowStride * 8);
   cudaFuncSetAttribute(k_imu<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kImuRowStride * 8);
   cudaFuncSetAttribute(k_imu_split<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kOriSplitStride * 8);
@@ -1210,6 +1250,8 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_lifting_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kLiftStage * 8);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
+  cudaFuncSetAttribute(k_short_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kAccelRowStride * 8);
+  if (const char* v = getenv("KTK_FUSE_SHORT")) p->fuse_short = atoi(v);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
@@ -1378,8 +1420,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
   cudaStream_t s = p->stream;
   const SplitConst& sp = p->spl;
   const double* d_quats = d_knots + (size_t)3 * sp.n_r3;      // 4-double records already
-  KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
-  k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(d_knots, sp.n_r3, p->d_vecs4.p);
+  k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(d_knots, sp.n_r3, p->d_vecs4.p, p->d_err.p);
   k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
   p->launches += 2;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
@@ -1421,8 +1462,7 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, d_quats); if (sj) return sj; }
   }
   KTK_CUDA(cudaGetLastError());
-  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  return KTK_OK;
+  return KTK_OK;      // the status word is fetched by ktk_synchronize
 }
 
 int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_rho, int64_t n_rho, uint32_t flags, const ktk_group_out* outs) {
@@ -1496,8 +1536,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
 static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const double* d_rho, uint32_t flags, const ktk_group_out* outs) {
   cudaStream_t s = p->stream;
   const int nk = p->sp.n_knots;
-  KTK_CUDA(cudaMemsetAsync(p->d_err.p, 0, sizeof(int), s));
-  k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(d_knots, nk, p->d_knots8.p, p->d_pairs.p);
+  k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(d_knots, nk, p->d_knots8.p, p->d_pairs.p, p->d_err.p);
   p->launches += 1;
   // the kernels of one group: "short" = IMU-like rows or the landmark records of a camera group (about one wave each on H1);
   // "rows" = the camera rows, which need their landmark records
@@ -1521,7 +1560,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
     else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
     else if (g.kind == KTK_ORIENTATION) k_imu<3><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
-    else k_imu<1><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
+    else k_imu<1><<<blocks, kThreads, kThreads * kAccelRowStride * 8, ss>>>(a);
     p->launches += 1;
   };
   auto launch_rows = [&](Group& g, const ktk_group_out& o) {
@@ -1549,6 +1588,51 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     else k_static_rs_local<<<blocks, kCamThreads, (kCamThreads / 32) * kCamWarpSmem * 8, s>>>(a);
     p->launches += 1;
   };
+  // All short kernels in one launch (k_short_batch) when they fit its fixed-size argument block and no per-group event timing is wanted;
+  // otherwise group by group as before.
+  bool batched = false;
+  if (!p->profiling && p->fuse_short) {
+    ShortBatch* b = &p->short_batch;
+    b->n_imu = b->n_ref = 0;
+    bool fits = true;
+    int cta = 0;
+    size_t smem = 0;
+    for (int pass = 0; pass < 2 && fits; ++pass)
+      for (size_t gi = 0; gi < p->groups.size() && fits; ++gi) {
+        Group& g = *p->groups[gi];
+        if (g.n == 0) continue;
+        const ktk_group_out& o = outs[gi];
+        if (pass == 0 && !is_camera(g.kind)) {
+          if (b->n_imu == kShortMaxImu) { fits = false; break; }
+          ImuArgs& a = b->imu[b->n_imu];
+          a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
+          for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
+          a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
+          a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+          a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
+          const int which = g.kind == KTK_GYROSCOPE ? 0 : (g.kind == KTK_POSITION ? 2 : (g.kind == KTK_ORIENTATION ? 3 : 1));
+          b->which[b->n_imu] = which; b->first[b->n_imu] = cta; b->n_imu += 1;
+          cta += (int)((g.n + 31) / 32);
+          smem = std::max(smem, (size_t)32 * imu_stride(which) * 8);
+        } else if (pass == 1 && p->fuse_short >= 2 && is_camera(g.kind) && g.n_ref > 0) {
+          if (b->n_ref == kShortMaxRef) { fits = false; break; }
+          RefArgs& ra = b->ref[b->n_ref];
+          ra.sp = p->sp; fill_camera_consts(g.cam, ra.cam);
+          ra.knots = p->d_knots8.p; ra.pairs = p->d_pairs.p; ra.rho = d_rho;
+          ra.ref_uv = g.d_rr_uv.p; ra.ref_t0 = g.d_rr_t0.p; ra.seg_start = g.d_rr_start.p; ra.seg_n = g.d_rr_n.p; ra.lm = g.d_rr_lm.p;
+          ra.n = (int)g.n_ref; ra.recs = g.d_recs.p; ra.err = p->d_err.p;
+          b->first[b->n_imu + b->n_ref] = cta; b->n_ref += 1;
+          cta += (int)((g.n_ref + 31) / 32);
+          smem = std::max(smem, (size_t)32 * kRefStride * 8);
+        }
+      }
+    if (fits && cta > 0 && b->n_imu + b->n_ref > 1) {
+      b->first[b->n_imu + b->n_ref] = cta;
+      k_short_batch<<<cta, 32, smem, s>>>(*b);
+      p->launches += 1;
+      batched = true;
+    }
+  }
   {
     for (size_t gi = 0; gi < p->groups.size(); ++gi) {
       Group& g = *p->groups[gi];
@@ -1556,21 +1640,21 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       const ktk_group_out& o = outs[gi];
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
-      launch_short(g, o, s);
+      if (!batched || (is_camera(g.kind) && p->fuse_short < 2)) launch_short(g, o, s);
       launch_rows(g, o);
       if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
       { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, nullptr); if (sj) return sj; }
     }
   }
   KTK_CUDA(cudaGetLastError());
-  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-  return KTK_OK;
+  return KTK_OK;      // the status word is fetched by ktk_synchronize: an evaluation is kernels only (C1: two graph nodes instead of four)
 }
 
 int ktk_synchronize(ktk_problem* p) {
   if (!p) return fail(KTK_EINVAL, "problem is NULL");
   if (p->device < 0) return fail(KTK_ECUDA, "problem has no device");
   KTK_CUDA(cudaSetDevice(p->device));
+  KTK_CUDA(cudaMemcpyAsync(p->h_err, p->d_err.p, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
   KTK_CUDA(cudaStreamSynchronize(p->stream));
   const int e = *p->h_err;
   if (e == kStatusRange) return fail(KTK_ERANGE, "a measurement time is out of range for the trajectory (its output rows are NaN)");
@@ -1650,14 +1734,14 @@ static int traj_evaluate_impl(ktk_problem* p, const double* knots, int64_t n, co
   if (p->traj == 0) {
     const int nk = p->sp.n_knots;
     if ((st = p->d_knots8.resize((size_t)nk * kKnotStride)) || (st = p->d_pairs.resize((size_t)nk * kPairStride))) return st;
-    k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p, p->d_pairs.p);
+    k_pair_prepass<<<((nk - 1) * 15 + 127) / 128, 128, 0, s>>>(p->d_knots7.p, nk, p->d_knots8.p, p->d_pairs.p, nullptr);
     if (width == 16) k_traj_eval_se3<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
     else k_traj_eval_se3_matrices<<<blocks, 128, 0, s>>>(p->sp, p->d_knots8.p, p->d_pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
   } else {
     const SplitConst& sp = p->spl;
     const double* d_quats = p->d_knots7.p + (size_t)3 * sp.n_r3;
     if ((st = p->d_vecs4.resize((size_t)sp.n_r3 * kVecStride)) || (st = p->d_so3pairs.resize((size_t)sp.n_so3 * kSo3PairStride))) return st;
-    k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, sp.n_r3, p->d_vecs4.p);
+    k_pack_vecs<<<(sp.n_r3 * kVecStride + 255) / 256, 256, 0, s>>>(p->d_knots7.p, sp.n_r3, p->d_vecs4.p, nullptr);
     k_so3_pair_prepass<<<((sp.n_so3 - 1) * 9 + 127) / 128, 128, 0, s>>>(d_quats, sp.n_so3, p->d_so3pairs.p, p->d_err.p);
     k_traj_eval_split<<<blocks, 128, 0, s>>>(sp, p->d_vecs4.p, d_quats, p->d_so3pairs.p, (int)n, d_t.p, d_out.p, d_st.p);
   }
@@ -1888,8 +1972,13 @@ struct GnState {
   uint32_t flags = 0; int traj = 0;
   int n[2] = {0, 0}, width[2] = {0, 0}, lw[2] = {0, 0}, kind[2] = {0, 0}; int64_t n_rho = 0; double free_[2] = {1.0, 1.0};
   std::vector<GnGroupState*> g;
-  DevBuf<double> P[2], va[2], Bd[2], Minv[2], damp[2], x[2], r[2], z[2], p[2], q[2], b[2];
-  DevBuf<double> c, cd, grho, t, s, drho, partial, own;
+  struct View { double* p = nullptr; };      // a slice of one of the two exchange buffers below
+  DevBuf<double> P[2], va[2], Minv[2], damp[2], x[2], r[2], p[2], b[2];
+  DevBuf<double> cd, t, s, drho, partial, own;
+  // what a sharded problem all-reduces lives in two contiguous buffers, so that each exchange is ONE collective:
+  //   lin = [c | grho | blocks_a | blocks_b | z_a | z_b]  (once per linearisation),   qq = [q_a | q_b]  (reduced rhs; S p in every CG iteration)
+  DevBuf<double> lin, qq; int64_t n_lin = 0, n_qq = 0;
+  View c, grho, Bd[2], z[2], q[2];
   DevBuf<unsigned char> lm_locked; bool have_locked = false;
   DevBuf<GnScal> scal; GnScal* h_scal = nullptr;
   DevBuf<double> part; DevBuf<int> ticket;      // CG dot-product partials (4 x kGnCtas) and the last-CTA ticket
@@ -2052,13 +2141,21 @@ int ktk_gn_prepare(ktk_problem* p, uint32_t flags, const ktk_group_out* d_outs, 
   }
   for (int sp = 0; sp < 2; ++sp) {
     const size_t nk = (size_t)S->n[sp], lw = (size_t)S->lw[sp], wd = (size_t)S->width[sp];
-    if ((st = S->P[sp].resize(nk * wd * lw)) || (st = S->va[sp].resize(nk * wd)) || (st = S->Bd[sp].resize(nk * lw * lw)) || (st = S->Minv[sp].resize(nk * lw * lw)) ||
-        (st = S->damp[sp].resize(nk * lw)) || (st = S->x[sp].resize(nk * lw)) || (st = S->r[sp].resize(nk * lw)) || (st = S->z[sp].resize(nk * lw)) ||
-        (st = S->p[sp].resize(nk * lw)) || (st = S->q[sp].resize(nk * lw)) || (st = S->b[sp].resize(nk * lw))) return st;
+    if ((st = S->P[sp].resize(nk * wd * lw)) || (st = S->va[sp].resize(nk * wd)) || (st = S->Minv[sp].resize(nk * lw * lw)) ||
+        (st = S->damp[sp].resize(nk * lw)) || (st = S->x[sp].resize(nk * lw)) || (st = S->r[sp].resize(nk * lw)) ||
+        (st = S->p[sp].resize(nk * lw)) || (st = S->b[sp].resize(nk * lw))) return st;
   }
   const size_t nr = (size_t)std::max<int64_t>(n_rho, 1);
-  if ((st = S->c.resize(nr)) || (st = S->cd.resize(nr)) || (st = S->grho.resize(nr)) || (st = S->t.resize(nr)) || (st = S->s.resize(nr)) || (st = S->drho.resize(nr)) ||
-      (st = S->own.resize(nr))) return st;
+  {
+    const size_t kb[2] = {(size_t)S->n[0] * S->lw[0] * S->lw[0], (size_t)S->n[1] * S->lw[1] * S->lw[1]}, kv[2] = {(size_t)S->n[0] * S->lw[0], (size_t)S->n[1] * S->lw[1]};
+    S->n_lin = (int64_t)(2 * nr + kb[0] + kb[1] + kv[0] + kv[1]); S->n_qq = (int64_t)(kv[0] + kv[1]);
+    if ((st = S->lin.resize((size_t)S->n_lin + 1)) || (st = S->qq.resize((size_t)S->n_qq + 1))) return st;
+    double* q = S->lin.p;
+    S->c.p = q; q += nr; S->grho.p = q; q += nr; S->Bd[0].p = q; q += kb[0]; S->Bd[1].p = q; q += kb[1]; S->z[0].p = q; q += kv[0]; S->z[1].p = q;
+    S->q[0].p = S->qq.p; S->q[1].p = S->qq.p + kv[0];
+    KTK_CUDA(cudaMemsetAsync(S->lin.p, 0, sizeof(double) * (size_t)S->n_lin, s));
+  }
+  if ((st = S->cd.resize(nr)) || (st = S->t.resize(nr)) || (st = S->s.resize(nr)) || (st = S->drho.resize(nr)) || (st = S->own.resize(nr))) return st;
   int64_t maxrows = 1;
   for (auto gp : S->g) maxrows = std::max<int64_t>(maxrows, gp->n);
   if ((st = S->partial.resize((size_t)2 * gn_blocks(maxrows, 256) + 2))) return st;
@@ -2261,6 +2358,8 @@ int64_t ktk_gn_buffer(ktk_problem* p, const char* name, double** ptr) {
   GnState& S = *p->gn;
   const std::string n(name);
   auto kn = [&](int sp, int per) { return (int64_t)S.n[sp] * per; };
+  if (n == "lin") { *ptr = S.lin.p; return S.n_lin; }
+  if (n == "qq") { *ptr = S.qq.p; return S.n_qq; }
   if (n == "c") { *ptr = S.c.p; return S.n_rho; }
   if (n == "grho") { *ptr = S.grho.p; return S.n_rho; }
   if (n == "drho") { *ptr = S.drho.p; return S.n_rho; }

@@ -348,8 +348,13 @@ KB_HD void gyro_se3(const double* knot0, const double* p1, const double* p2, con
 // compat_zero_dB: the reference's Jet path leaves dB == 0 for the accelerometer's flags;
 // passing a Basis with dB = 0 reproduces it (P'' = P0 sum A''_j ... with A'_j = 0).
 // Reverse sweep carries 3x6 adjoints.  J: [4 knots][3][7].
+// PARK: the body twists of the forward pass that the reverse sweep needs again (y_j, z_j: 24 doubles) are parked in `scratch` (the kernels
+// pass spare shared memory behind the row) instead of staying live in registers across the whole sweep; false: a local array (host harness).
+template <bool PARK = false>
 KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs, double weight,
-                     const double* y, double* r, double* J) {
+                     const double* y, double* r, double* J, double* scratch = nullptr) {
+  double local_park[PARK ? 1 : 24];
+  double* park = PARK ? scratch : local_park;
   const V3 u1 = v3(p1[0], p1[1], p1[2]), f1 = v3(p1[3], p1[4], p1[5]);
   const V3 u2 = v3(p2[0], p2[1], p2[2]), f2 = v3(p2[3], p2[4], p2[5]);
   const V3 u3 = v3(p3[0], p3[1], p3[2]), f3 = v3(p3[3], p3[4], p3[5]);
@@ -364,10 +369,18 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
   const V3 d2u = z2u - bs.dB[1] * (cross(f2, y2u) + cross(u2, y2w)) + bs.d2B[1] * u2;
   const V3 d2w = z2w - bs.dB[1] * cross(f2, y2w) + bs.d2B[1] * f2;
   exp_part(p3, bs.B[2], true, false, e);
-  const V3 y3w = mul_t(e.E, s2w), y3u = mul_t(e.E, s2u - cross(e.a, s2w));
-  const V3 z3w = mul_t(e.E, d2w), z3u = mul_t(e.E, d2u - cross(e.a, d2w));
+  {
+    park[0] = y2u.x; park[1] = y2u.y; park[2] = y2u.z; park[3] = y2w.x; park[4] = y2w.y; park[5] = y2w.z;
+    park[6] = z2u.x; park[7] = z2u.y; park[8] = z2u.z; park[9] = z2w.x; park[10] = z2w.y; park[11] = z2w.z;
+  }
+  V3 y3w = mul_t(e.E, s2w), y3u = mul_t(e.E, s2u - cross(e.a, s2w));
+  V3 z3w = mul_t(e.E, d2w), z3u = mul_t(e.E, d2u - cross(e.a, d2w));
   const V3 vb = y3u + bs.dB[2] * u3, wb = y3w + bs.dB[2] * f3;
   const V3 dvb = z3u - bs.dB[2] * (cross(f3, y3u) + cross(u3, y3w)) + bs.d2B[2] * u3;
+  {
+    park[12] = y3u.x; park[13] = y3u.y; park[14] = y3u.z; park[15] = y3w.x; park[16] = y3w.y; park[17] = y3w.z;
+    park[18] = z3u.x; park[19] = z3u.y; park[20] = z3u.z; park[21] = z3w.x; park[22] = z3w.y; park[23] = z3w.z;
+  }
   const V3 fb = cross(wb, vb) + dvb;
   M3 T = E2 * e.E;                                        // E2 E3
   exp_part(p1, bs.B[0], false, false, e);
@@ -382,39 +395,53 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
   const M3 hgb = hat(gb);
   const V3 Tf = T * fb;
   const V3 rad = 2.0 * (fb - mul_t(T, mul_t(R0, Tf)));
-  // reverse: 3x6 adjoints of (s_j, s_j'), from the last factor to the first; T = E_{j+1}..E_3 rebuilt on the way
+  // reverse: 3x6 adjoints of (s_j, s_j'), from the last factor to the first; T = E_{j+1}..E_3 rebuilt on the way.
+  // Register pressure: five 3x6 blocks (gs, gd, gy, gj, t) plus an exp part were live across the Q block and the two contractions of a level
+  // (988 B of spill per thread in round 1).  The adjoints the NEXT level needs are formed as soon as their inputs exist and PARKED in the
+  // part of the output row that is not written yet (J[0..36) during level 3, J[0..18) during level 2 -- the row is built back to front), so
+  // that only gj and t are live across the expensive part.
   G6<3> gs, gd, gj, t;
   gs.U = hat(wb); gs.W = (-1.0) * hat(vb);
   gd.U = m3_identity(); gd.W = m3_zero();
   {
     exp_part(p3, bs.B[2], true, true, e);
+    y3u = v3(park[12], park[13], park[14]); y3w = v3(park[15], park[16], park[17]); z3u = v3(park[18], park[19], park[20]); z3w = v3(park[21], park[22], park[23]);
     const G6<3> gy = gadd(gs, gscale(-bs.dB[2], mul_ad(gd, u3, f3)));
     gj = gadd(gadd(gscale(bs.dB[2], gs), gscale(bs.d2B[2], gd)), gscale(bs.dB[2], mul_ad(gd, y3u, y3w)));
     t = gadd(mul_ad(gy, y3u, y3w), mul_ad(gd, z3u, z3w));
     t.W = t.W + hgb;                 // F3^T F3 = I
+    gs = mul_Adinv(gy, e.E, e.a);
+    gd = mul_Adinv(gd, e.E, e.a);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { J[i] = gs.U.a[i]; J[9 + i] = gs.W.a[i]; J[18 + i] = gd.U.a[i]; J[27 + i] = gd.W.a[i]; }
     gj = gadd(gj, mul_Jr6(t, e, bs.B[2]));
     contract_pair<3, false>(J + 63, gj, p3 + kPairDOff + kPairSide, sc);
     contract_pair<3, false>(J + 42, gj, p3 + kPairDOff, sc);
-    gs = mul_Adinv(gy, e.E, e.a);
-    gd = mul_Adinv(gd, e.E, e.a);
     T = e.E;
   }
   {
     exp_part(p2, bs.B[1], true, true, e);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { gs.U.a[i] = J[i]; gs.W.a[i] = J[9 + i]; gd.U.a[i] = J[18 + i]; gd.W.a[i] = J[27 + i]; }
+    const V3 y2u = v3(park[0], park[1], park[2]), y2w = v3(park[3], park[4], park[5]), z2u = v3(park[6], park[7], park[8]), z2w = v3(park[9], park[10], park[11]);
     const G6<3> gy = gadd(gs, gscale(-bs.dB[1], mul_ad(gd, u2, f2)));
     gj = gadd(gadd(gscale(bs.dB[1], gs), gscale(bs.d2B[1], gd)), gscale(bs.dB[1], mul_ad(gd, y2u, y2w)));
     t = gadd(mul_ad(gy, y2u, y2w), mul_ad(gd, z2u, z2w));
     t.W = t.W + mul_nt(hgb, T);      // F3^T F2 = E3^T
+    {                                // level 1 only needs dB1 gs' + d2B1 gd': form it now, park 18 doubles
+      const G6<3> g1 = gadd(gscale(bs.dB[0], mul_Adinv(gy, e.E, e.a)), gscale(bs.d2B[0], mul_Adinv(gd, e.E, e.a)));
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { J[i] = g1.U.a[i]; J[9 + i] = g1.W.a[i]; }
+    }
     gj = gadd(gj, mul_Jr6(t, e, bs.B[1]));
     contract_pair<3, true>(J + 42, gj, p2 + kPairDOff + kPairSide, sc);
     contract_pair<3, false>(J + 21, gj, p2 + kPairDOff, sc);
-    gs = mul_Adinv(gy, e.E, e.a);
-    gd = mul_Adinv(gd, e.E, e.a);
     T = e.E * T;
   }
   {
     exp_part(p1, bs.B[0], false, false, e);
-    gj = gadd(gscale(bs.dB[0], gs), gscale(bs.d2B[0], gd));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { gj.U.a[i] = J[i]; gj.W.a[i] = J[9 + i]; }
     // rotation of A1 only enters through R^T g:  F3^T F1 = (E2 E3)^T
     gj.W = gj.W + bs.B[0] * mul_nt(mul_nt(hgb, T), e.V);
     contract_pair<3, true>(J + 21, gj, p1 + kPairDOff + kPairSide, sc);
@@ -791,8 +818,9 @@ KB_HD void orientation_se3(const double* knot0, const double* p1, const double* 
 
 // gyroscope (which = 0) / accelerometer (which = 1) / position (which = 2) / orientation (which = 3: y = q (x,y,z,w), r[1], J [4][1][7]);
 // gyroscope_measurement.h:75-105 builds the span, :58-68 evaluates.
+template <bool PARK = false>
 KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const double* knots, const double* pairs,
-                  double t, const double* y, double weight, double* r, double* J, int* i0_out) {
+                  double t, const double* y, double weight, double* r, double* J, int* i0_out, double* scratch = nullptr) {
   double ta = t, tb = t;
   if (!imu.time_offset_locked) { ta = sub_rn(t, imu.max_time_offset); tb = add_rn(t, imu.max_time_offset); }
   if (sp.n_knots < 4 || !(ta >= sp.t0) || !(tb < spline_max_time(sp))) return kStatusRange;
@@ -807,7 +835,7 @@ KB_HD int imu_row(int which, const SplineConst& sp, const ImuConst& imu, const d
   else if (which == 3) orientation_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, y, r, J);
   else {
     if (sp.compat_zero_dB) { bs.dB[0] = 0.0; bs.dB[1] = 0.0; bs.dB[2] = 0.0; }
-    accel_se3(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J);
+    accel_se3<PARK>(k0, p1, p1 + kPairStride, p1 + 2 * kPairStride, bs, weight, y, r, J, scratch);
   }
   *i0_out = i0;
   return 0;

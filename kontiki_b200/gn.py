@@ -210,7 +210,7 @@ class DeviceSchurSolver:
         import ctypes as C
         self.p.gn_call("linearize_local", C.c_void_p(self.knots.data_ptr()), C.c_void_p(self.rho.data_ptr()) if self.n_rho else None)
         self.p.gn_call("gradient_local")
-        self._reduce("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b")
+        self._reduce("lin")               # [c | grho | blocks_a | blocks_b | z_a | z_b] in ONE collective
         gmax = torch.zeros(1, dtype=torch.float64, device=self.dev)
         for name, locked in (("z_a", self.lock_a), ("z_b", self.lock_b)):
             t = self.buf(name)
@@ -221,7 +221,7 @@ class DeviceSchurSolver:
             free = torch.ones_like(g) if self.lm_locked is None else torch.from_numpy(1.0 - np.asarray(self.lm_locked, np.float64)).to(self.dev)
             gmax = torch.maximum(gmax, (g * free).abs().max().reshape(1))
         self.p.gn_call("linearize_rhs", C.c_double(radius))
-        self._reduce("q_a", "q_b")
+        self._reduce("qq")
         return gmax
 
     def solve(self, radius, tol=1e-6, max_iter=300, check_every=8):
@@ -232,7 +232,7 @@ class DeviceSchurSolver:
         while not done:
             for _ in range(check_every):
                 self.p.gn_call("product")
-                self._reduce("q_a", "q_b")
+                self._reduce("qq")                # [q_a | q_b]
                 self.p.gn_call("pcg_update")
             it, done, rel = self.p.gn_pcg_status()
         return it, rel
