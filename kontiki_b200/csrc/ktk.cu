@@ -857,6 +857,7 @@ __global__ void k_imu_sensor(const ImuSensorArgs a) {
   dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
 }
 struct CamSensorArgs {
+  int traj; SplitConst spl; const double* vecs; const double* quats; const double* so3pairs;
   SplineConst sp; CameraConst cam; const double* knots; const double* pairs; const double* rho;
   const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
   const int* perm; int n; uint32_t flags; double* Js; int* err;
@@ -867,8 +868,9 @@ __global__ void k_static_rs_sensor(const CamSensorArgs a) {
   double o[16];
   const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]}, ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
   o[14] = o[15] = 0.0;
-  const int st = static_rs_sensor_jac_se3(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i],
-                                          (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, o);
+  const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
+  const int st = a.traj == 0 ? static_rs_sensor_jac_se3(a.sp, a.cam, a.knots, a.pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i], hub, o)
+                             : static_rs_sensor_jac_split(a.spl, a.cam, a.vecs, a.quats, a.so3pairs, ouv, a.obs_t0[i], ruv, a.ref_t0[i], a.rho[a.lm[i]], a.w[i], hub, o);
   if (st != 0) { atomicMin(a.err, st); for (int c = 0; c < 16; ++c) o[c] = nan(""); }
   double* dst = a.Js + 16 * (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
   for (int c = 0; c < 16; ++c) dst[c] = o[c];
@@ -888,11 +890,88 @@ struct NewtonArgs {
   int n, W; uint32_t flags;
   double* r; double* J; int* i0r; int* i0o; int* err;
 };
-__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a) {
+// Fast path of the Newton-RS rows (round 2).  The Newton iteration on the row time stops after its FIRST evaluation whenever the first step is
+// below half a row (newton_rscamera_measurement.h:111-113) -- with half-pixel noise that is two rows out of three.  y_out is then the
+// projection at the INITIAL row time, which does not depend on any parameter, so the Jet derivative the reference takes through the iteration
+// is exactly the static row's Jacobian (bit for bit: tests/test_gpu_parity.py).  One thread per row runs the iteration once on values only;
+// single-evaluation rows get the closed-form static row (written into the span layout), the others are flagged for the forward-mode kernel.
+constexpr int kNewtonStage = 116;      // [Jref 56 | Jobs 56 | rho 2] + pad
+__global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* __restrict__ slow /* [0] = count, [1 + k] = row of the k-th slow row */) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31;
+  double* row = smem + lane * kNewtonStage;
+  const int i = blockIdx.x * 32 + lane;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  const int row_len = 58 + 14 * a.W;
+  int perm = -1, rel = 0;
+  unsigned char slow_lane = 0;
+  if (i < a.n) {
+    const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+    const double obs_t0 = a.obs_t0[i], ref_t0 = a.ref_t0[i];
+    const int ridx = a.ref_idx[i];
+    const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+    unsigned char is_slow = 1;
+    if (ridx >= 0) {
+      const double* rec = a.recs + (size_t)ridx * kRefStride;
+      NewtonRow o;
+      const int st0 = ((int)rec[7] >= 0) ? newton_rs_direction(a.sp, a.cam, a.knots, a.pairs, rec, ouv, obs_t0, ref_t0, kbase, a.W, -1, o) : kStatusRange;
+      if (st0 == 0 && o.iterations == 1) {
+        ObsForward f; f.status = kStatusRange; f.io = -1;
+        double uo;
+        if (static_rs_row_locate_u(a.sp, a.cam, ouv, obs_t0, ref_t0, f.io, uo) && f.io >= kbase && f.io + 4 <= kbase + a.W) {
+          f.status = 0; f.bo = cumulative_basis(uo, a.sp.dt);
+          static_rs_row_pose(a.knots, a.pairs, f);
+          double r[2], jrho[2];
+          int ir = -1, io = -1;
+          ObsAdjoint adj;
+          for (int c = 0; c < kRefStride; ++c) row[kRefInRowDev + c] = rec[c];      // the record, where the in-place reference half expects it
+          const int st = static_rs_row_ref_half(a.cam, f, row + kRefInRowDev, ouv, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, row, jrho, &ir, &io, adj);
+          if (st == 0) {
+            static_rs_row_obs_half(a.knots, a.pairs, f, adj, row + kCamHalf);
+            row[112] = jrho[0]; row[113] = jrho[1];
+            is_slow = 0;
+            perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
+            rel = io - kbase;
+            const size_t dst = (size_t)perm;
+            if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+            if (a.i0r) a.i0r[dst] = ir;
+            if (a.i0o) a.i0o[dst] = kbase;
+          }
+        }
+      }
+    }
+    slow_lane = is_slow;
+  }
+  {   // compact list of the rows the forward-mode kernel has to do (their order in the list does not matter: rows are independent)
+    const unsigned m = __ballot_sync(0xffffffffu, slow_lane != 0);
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(slow, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (slow_lane) slow[1 + base + __popc(m & ((1u << lane) - 1u))] = i;
+  }
+  if (!wantJ) return;
+  for (int rr = 0; rr < 32; ++rr) {
+    const int d = __shfl_sync(0xffffffffu, perm, rr), sh = __shfl_sync(0xffffffffu, rel, rr);
+    if (d < 0) continue;
+    const double* src = smem + rr * kNewtonStage;
+    double* dst = a.J + (size_t)d * row_len;
+    for (int c = lane; c < row_len; c += 32) {
+      double v;
+      if (c < 56) v = src[c];
+      else if (c < 56 + 14 * a.W) { const int b = (c - 56) / 14 - sh; v = (b >= 0 && b < 4) ? src[56 + 14 * b + (c - 56) % 14] : 0.0; }
+      else v = src[112 + (c - 56 - 14 * a.W)];
+      dst[c] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow) {
   const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int i = (int)(tid / ndir), dir = (int)(tid % ndir);
+  int i = (int)(tid / ndir);
+  const int dir = (int)(tid % ndir);
   if (i >= a.n) return;
+  if (slow) { if (i >= slow[0]) return; i = slow[1 + i]; }      // only the rows the fast path left (compact list)
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   if (!wantJ && dir != 0) return;
   const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
@@ -1004,6 +1083,7 @@ struct Group {
   double bias[3] = {0.0, 0.0, 0.0};
   std::vector<double> vt; DevBuf<double> d_vt; bool vt_dirty = true;      // LiftingRs: current frame-normalised row times, caller order (ktk_set_group_vt)
   DevBuf<double> o_Js;
+  DevBuf<int> d_slow;             // Newton-RS rows that need the forward-mode kernel (more than one Newton evaluation): [count | row indices]
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
   DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
@@ -1035,6 +1115,7 @@ struct ktk_problem {
   bool profiling = false;
   bool graphs_enabled = true;
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
+  bool newton_fast = true;        // KTK_NEWTON_FAST=0: every Newton-RS row through the forward-mode kernel (A/B, cross-check)
   int fuse_short = 1;             // 1: all IMU-like groups of an evaluation in one launch (k_short_batch); 2: + the landmark tables (measured slower, r2g); 0: off.  KTK_FUSE_SHORT overrides (A/B)
   ShortBatch short_batch;
   cudaGraphExec_t graph_exec = nullptr;
@@ -1252,6 +1333,8 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   cudaFuncSetAttribute(k_short_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kAccelRowStride * 8);
   if (const char* v = getenv("KTK_FUSE_SHORT")) p->fuse_short = atoi(v);
+  if (const char* v = getenv("KTK_NEWTON_FAST")) p->newton_fast = atoi(v) != 0;
+  cudaFuncSetAttribute(k_newton_rs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kNewtonStage * 8);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
@@ -1392,9 +1475,9 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   if (!is_camera(g.kind) && g.sensor.time_offset_locked) return KTK_OK;              // an IMU's relative pose is not applied (TODO.md:6): only the time offset has columns
   if (is_span_camera(g.kind)) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRs / LiftingRs camera measurements are not built");
   if (g.kind == KTK_STATIC_RS) {
-    if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "camera sensor-block Jacobians on a split trajectory are not built");
     if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
     CamSensorArgs a;
+    a.traj = p->traj; a.spl = p->spl; a.vecs = p->d_vecs4.p; a.quats = d_quats; a.so3pairs = p->d_so3pairs.p;
     a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
     a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
     a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv_sorted.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm_sorted.p; a.w = g.d_w.p;
@@ -1481,6 +1564,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       KTK_CUDA(cudaStreamSynchronize(s));
       g->vt_dirty = false;
     }
+    if (g->kind == KTK_NEWTON_RS && g->n > 0 && (st = g->d_slow.resize((size_t)g->n + 1))) return st;
     if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs camera measurements are not built");
     if (is_span_camera(g->kind) && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (is_camera(g->kind)) {
@@ -1581,7 +1665,12 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
       } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
-        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na);
+        if (p->newton_fast) {
+          cudaMemsetAsync(g.d_slow.p, 0, sizeof(int), s);
+          k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p);
+          p->launches += 1;
+        }
+        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr);
       }
     }
     else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);

@@ -199,4 +199,76 @@ KB_HD int static_rs_sensor_jac_se3(const SplineConst& sp, const CameraConst& cam
   return 0;
 }
 
+// Pose, body angular velocity and WORLD linear velocity of a split trajectory at located (ia, ua) / (ib, ub):
+// R from the SO3 spline (uniform_so3_spline_trajectory.h:96-104), w_b from its derivative (:108-121, rotation vectors 2 phi), p and p' from
+// the R3 spline (uniform_r3_spline_trajectory.h:62-92).
+KB_HD void split_pose_twist(const SplitConst& sp, const double* vecs, const double* quats, const double* pairs, int ia, double ua, int ib, double ub,
+                            M3& R, V3& p, V3& wb, V3& vw) {
+  const Basis bs = cumulative_basis(ub, sp.dt_so3);
+  const BasisR3 br = r3_basis(ua, sp.dt_r3);
+  const double* q0 = quats + (size_t)ib * kQuatStride;
+  const double* p1 = pairs + (size_t)(ib + 1) * kSo3PairStride; const double* p2 = p1 + kSo3PairStride; const double* p3 = p2 + kSo3PairStride;
+  const V3 f1 = v3(2.0 * p1[0], 2.0 * p1[1], 2.0 * p1[2]), f2 = v3(2.0 * p2[0], 2.0 * p2[1], 2.0 * p2[2]), f3 = v3(2.0 * p3[0], 2.0 * p3[1], 2.0 * p3[2]);
+  ExpPart e2, e3;
+  so3_exp_part(p2, bs.B[1], e2); so3_exp_part(p3, bs.B[2], e3);
+  const V3 s2 = mul_t(e2.E, bs.dB[0] * f1) + bs.dB[1] * f2;
+  wb = mul_t(e3.E, s2) + bs.dB[2] * f3;
+  R = so3_forward(q0, p1, bs);
+  const double* c0 = vecs + (size_t)ia * kVecStride;
+  p = r3_combine(c0, br.Bp); vw = r3_combine(c0, br.Bv);
+}
+
+// Sensor-block Jacobians of a static-RS camera row on a SPLIT trajectory (sensors.h:135-165 blocks, split_trajectory.h:41-58 evaluation):
+// same output layout and the same chain as static_rs_sensor_jac_se3; the pose derivative is (w_b, world velocity) of the two splines.
+KB_HD int static_rs_sensor_jac_split(const SplitConst& sp, const CameraConst& cam, const double* vecs, const double* quats, const double* pairs,
+                                     const double* obs_uv, double obs_t0, const double* ref_uv, double ref_t0, double rho, double weight, double huber_c, double* out) {
+  Segment s0, s1;
+  int ira, irb, ioa, iob; double ura, urb, uoa, uob;
+  const double tr = static_rs_time(cam, ref_t0, ref_uv[1]), to = static_rs_time(cam, obs_t0, obs_uv[1]);
+  int nseg = static_rs_segments_split(sp, cam, ref_t0, obs_t0, sp.t0_r3, sp.dt_r3, s0, s1);
+  if (nseg == 0 || locate_in_segments(nseg, s0, s1, tr, sp.t0_r3, sp.dt_r3, ira, ura) < 0 || locate_in_segments(nseg, s0, s1, to, sp.t0_r3, sp.dt_r3, ioa, uoa) < 0) return kStatusRange;
+  nseg = static_rs_segments_split(sp, cam, ref_t0, obs_t0, sp.t0_so3, sp.dt_so3, s0, s1);
+  if (nseg == 0 || locate_in_segments(nseg, s0, s1, tr, sp.t0_so3, sp.dt_so3, irb, urb) < 0 || locate_in_segments(nseg, s0, s1, to, sp.t0_so3, sp.dt_so3, iob, uob) < 0) return kStatusRange;
+  M3 Rr, Ro; V3 pr, po, wr, wo, vr, vo;
+  split_pose_twist(sp, vecs, quats, pairs, ira, ura, irb, urb, Rr, pr, wr, vr);
+  split_pose_twist(sp, vecs, quats, pairs, ioa, uoa, iob, uob, Ro, po, wo, vo);
+  const M3 Rct = quat_to_rot(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2], cam.q_ct[3]);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  const V3 yv = camera_unproject(cam, ref_uv[0], ref_uv[1]) - rho * pct;
+  const V3 Xref = mul_t(Rct, yv);
+  const V3 X = Rr * Xref + rho * pr;
+  const V3 Xobs = mul_t(Ro, X - rho * po);
+  const V3 RX = Rct * Xobs;
+  double y0, y1;
+  Mr<2> Jp0, Gc;
+  camera_project_jac(cam, RX + rho * pct, y0, y1, Jp0);
+  const double r0 = weight * (obs_uv[0] - y0), rr1 = weight * (obs_uv[1] - y1);
+  double c00 = 1.0, c01 = 0.0, c10 = 0.0, c11 = 1.0;
+  if (huber_c > 0.0) {
+    const HuberScale h = huber_scale(huber_c, r0 * r0 + rr1 * rr1);
+    c00 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * r0 * r0); c01 = -h.sqrt_rho1 * h.alpha_sq_norm * r0 * rr1;
+    c10 = c01; c11 = h.sqrt_rho1 * (1.0 - h.alpha_sq_norm * rr1 * rr1);
+  }
+  for (int c = 0; c < 3; ++c) { Gc.a[c] = -weight * (c00 * Jp0.a[c] + c01 * Jp0.a[3 + c]); Gc.a[3 + c] = -weight * (c10 * Jp0.a[c] + c11 * Jp0.a[3 + c]); }
+  const Mr<2> Go = rmul(Gc, Rct), GX = rmul_nt(Go, Ro), GXR = rmul(GX, Rr);
+  const V3 dXdt = Rr * cross(wr, Xref) + rho * vr;      // d/dt (R_r Xref + rho p_r)
+  const Mr<2> Gth = rmul_hat(Go, Xobs);
+  const Mr<2> Jth = rsub(rmul_hat(GXR, Xref), rmul_hat(Go, Xobs));
+  const V3 radc = 2.0 * (RX - Xobs), radr = 2.0 * (Xref - yv);
+  const V3 v = v3(cam.q_ct[0], cam.q_ct[1], cam.q_ct[2]); const double w = cam.q_ct[3];
+  const Mr<2> GXRRct = rmul_nt(GXR, Rct);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const V3 g = rrow(Jth, r);
+    const V3 tq = 2.0 * (w * g - cross(g, v));
+    const double rad = dot(rrow(Gc, r), radc) + dot(rrow(GXR, r), radr);
+    out[r * 4 + 0] = tq.x + rad * cam.q_ct[0]; out[r * 4 + 1] = tq.y + rad * cam.q_ct[1]; out[r * 4 + 2] = tq.z + rad * cam.q_ct[2];
+    out[r * 4 + 3] = -2.0 * dot(g, v) + rad * cam.q_ct[3];
+    out[8 + r * 3 + 0] = rho * (Gc.a[3 * r] - GXRRct.a[3 * r]); out[8 + r * 3 + 1] = rho * (Gc.a[3 * r + 1] - GXRRct.a[3 * r + 1]);
+    out[8 + r * 3 + 2] = rho * (Gc.a[3 * r + 2] - GXRRct.a[3 * r + 2]);
+    out[14 + r] = dot(rrow(GX, r), dXdt) - rho * dot(rrow(GX, r), vo) + dot(rrow(Gth, r), wo);
+  }
+  return 0;
+}
+
 }  // namespace kb

@@ -243,6 +243,21 @@ void hc_static_rs_sensor_se3(double t0, double dt, int n_knots, const double* K,
                                          huber_c ? huber_c[i] : 0.0, out + 16 * i);
 }
 
+void hc_static_rs_sensor_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, const double* K, const double* Kinv, const double* q_ct,
+                               const double* p_ct, double time_offset, double max_time_offset, int locked, double readout, int rows, const double* vecs4,
+                               const double* quats, const double* pairs, int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0,
+                               const int* lm_idx, const double* rho, const double* w, const double* huber_c, double* out, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  camera_set_pose(cam, q_ct, p_ct);
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  for (int i = 0; i < n; ++i)
+    status[i] = static_rs_sensor_jac_split(sp, cam, vecs4, quats, pairs, obs_uv + 2 * i, obs_t0[i], ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], w[i],
+                                           huber_c ? huber_c[i] : 0.0, out + 16 * i);
+}
 
 void hc_se3_matrices(double t0, double dt, int n_knots, const double* knots8, const double* pairs, int n, const double* t, double* out, int* status) {
   SplineConst sp{t0, dt, n_knots, 0};

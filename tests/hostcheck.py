@@ -248,6 +248,25 @@ def static_rs_sensor_se3(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm
     return out, st
 
 
+def static_rs_sensor_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+    _set_camera_model(cam)
+    v4, q4, pairs, st0 = split_prepass(vecs3, quats)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    out, st = np.zeros((n, 16)), np.zeros(n, np.int32)
+    lib().hc_static_rs_sensor_split(C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(K), _p(Kinv), _p(_f(cam.q_ct)),
+                                    _p(_f(cam.p_ct)), C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout),
+                                    int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(w), _p(hc),
+                                    _p(out), _p(st))
+    return out, st
+
+
 def se3_matrices(knots7, dt, t0, t):
     k8, pairs = prepass(knots7)
     t = _f(np.atleast_1d(t))

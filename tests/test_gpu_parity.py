@@ -373,6 +373,54 @@ def test_unlocked_sensors_se3_match_oracle():
         assert parity.rel_err(out["Js"][:, a:b], o["Js"][:, a:b]) < parity.TOL
 
 
+def test_unlocked_sensors_split_match_oracle():
+    """SURVEY.md 8f-2 on a SPLIT trajectory: unlocked IMU time offset (+ ConstantBiasImu bias) and every camera sensor block."""
+    c0 = _split_case(n_knots=300, dt=0.05, scale_imu=2000, n_lm=200, seed=41)
+    cam = c0["cam"]
+    traj = kto.Traj(kto.SPLIT, c0["dt_a"], c0["t0_a"], c0["vecs"], c0["dt_b"], c0["t0_b"], c0["quats"])
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    hi = (300 - 3) * 0.05
+    t = c0["t"][(c0["t"] > 0.3) & (c0["t"] < hi - 0.4)]
+    y = c0["y"][:len(t)]
+    keep = (np.minimum(cam["ref_t0"], cam["obs_t0"]) > 0.3) & (np.maximum(cam["ref_t0"], cam["obs_t0"]) < hi - 0.4)
+    ocam = kto.Camera(cam["rows"], cam["cols"], cam["readout"], K=cam["K"], q_ct=q_ct, p_ct=p_ct, time_offset=-0.002, max_time_offset=0.004, q_locked=False,
+                      p_locked=False, d_locked=False)
+    o_all = kto.static_rs_residuals(traj, ocam, cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["rho"], cam["weight"], jac_mode=0, cap=32,
+                                    raise_on_error=False)
+    keep &= o_all["status"] == 0
+    assert keep.sum() > 200
+    for a in ("obs_uv", "obs_t0", "ref_uv", "ref_t0", "lm_idx", "weight", "huber_c"):
+        cam[a] = cam[a][keep]
+    p = _lib.Problem(0)
+    p.set_split_spline(c0["dt_a"], c0["t0_a"], len(c0["vecs"]), c0["dt_b"], c0["t0_b"], len(c0["quats"]))
+    imu = _lib.make_sensor(time_offset=0.003, max_time_offset=0.05, time_offset_locked=False)
+    gg = p.add_gyroscope(imu, t, y)
+    ga = p.add_accelerometer(imu, t, y)
+    p.set_group_bias(ga, [0.01, -0.02, 0.03])
+    gc = p.add_static_rs(_lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"], q_ct=q_ct, p_ct=p_ct, time_offset=-0.002, max_time_offset=0.004,
+                                          q_locked=False, p_locked=False, time_offset_locked=False),
+                         cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["weight"], cam["huber_c"])
+    outs = p.evaluate((c0["vecs"], c0["quats"]), cam["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_SENSOR_JACOBIANS)
+    for g, which, bias in ((gg, 0, None), (ga, 1, [0.01, -0.02, 0.03])):
+        osen = kto.Sensor(time_offset=0.003, max_time_offset=0.05, d_locked=False, abias=bias, gbias=None if bias is None else [0, 0, 0])
+        o = kto.imu_residuals(traj, osen, which, t, y, jac_mode=2, cap=16)
+        out = outs[g]
+        assert (out["i0_c"] == o["i0_b"]).all()
+        assert parity.rel_err(out["r"], o["r"]) < parity.TOL
+        assert parity.rel_err(out["Js"], o["Js"][:, 21:24]) < parity.TOL
+        ids_b, nids = p.get_structure_so3(g, cap=16)
+        assert (ids_b == o["ids_b"]).all() and nids.min() > 4
+        pos = np.array([list(ids_b[i]).index(out["i0_c"][i]) for i in range(len(ids_b))])
+        Jo = np.stack([o["Jb"][i, pos[i]:pos[i] + 4] for i in range(len(ids_b))])
+        assert parity.rel_err(out["J"][:, -48:].reshape(-1, 4, 3, 4), Jo) < parity.TOL
+    o = kto.static_rs_residuals(traj, ocam, cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["rho"], cam["weight"], jac_mode=2, cap=32)
+    out = outs[gc]
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_b"] == o["i0_obs_a"]).all() and (out["i0_c"] == o["i0_ref_b"]).all() and (out["i0_d"] == o["i0_obs_b"]).all()
+    assert np.abs(out["r"] - o["r"]).max() < parity.CAM_R_TOL
+    for a, b in ((0, 8), (8, 14), (14, 16)):
+        assert parity.rel_err(out["Js"][:, a:b], o["Js"][:, a:b]) < parity.TOL
+
+
 # ---- KTK_EVAL_LOCAL: knot blocks after the knots' LocalParameterization ------------------------------------------------------
 def test_local_coordinates_equal_ambient_times_plus_jacobian():
     """J_local = J_ambient * dPlus/ddelta (LocalParameterizationSE3 uniform_se3_spline_trajectory.h:25-48; EigenQuaternionParameterization

@@ -154,6 +154,29 @@ def test_camera_sensor_jacobians_match_oracle(robust):
         assert parity.rel_err(out[:, a:b], Js[:, a:b]) < parity.TOL
 
 
+@pytest.mark.parametrize("robust", [False, True])
+def test_camera_sensor_jacobians_split_match_oracle(robust):
+    """SURVEY.md 8f-2 remainder: the camera's q_ct / p_ct / time_offset columns on a SPLIT trajectory (sensors.h:135-165, split_trajectory.h:41-58)."""
+    dt = 0.05
+    knots, s, _ = _camera_case(dt, 7)
+    vecs, quats = knots[:, 4:7].copy(), knots[:, :4].copy()
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], q_ct=fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), p_ct=np.array([0.05, -0.02, 0.1]),
+                     time_offset=0.004)
+    n = len(s["lm_idx"])
+    o = kto.static_rs_residuals(kto.Traj(kto.SPLIT, dt, 0.0, vecs, dt, 0.0, quats), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
+                                s["weight"], jac_mode=2, cap=24)
+    out, st = hc.static_rs_sensor_split(vecs, dt, 0.0, quats, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"],
+                                        huber_c=np.full(n, 5.0) if robust else None)
+    assert (st == 0).all()
+    Js = o["Js"].copy()
+    if robust:
+        for i in range(n):
+            _, _, J2 = kto.huber_correct(5.0, o["r"][i], np.concatenate([Js[i, 0:8].reshape(2, 4), Js[i, 8:14].reshape(2, 3), Js[i, 14:16].reshape(2, 1)], 1))
+            Js[i, 0:8], Js[i, 8:14], Js[i, 14:16] = J2[:, 0:4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7]
+    for a, b in ((0, 8), (8, 14), (14, 16)):
+        assert parity.rel_err(out[:, a:b], Js[:, a:b]) < parity.TOL
+
+
 def test_se3_evaluate_matrices_match_oracle():
     """UniformSE3SplineTrajectory.evaluate(t) -> (P, P', P'') (py_uniform_se3_spline_trajectory.cc:53-60) on the reference's fixture."""
     t = np.linspace(fx.SE3_T0, fx.SE3_T0 + 3 * fx.SE3_DT - 1e-9, 33)
