@@ -421,8 +421,17 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_local(c
 // bulk store for the tile.
 constexpr int kCamDevStride = 114, kRefInRowDev = 22;      // record at 22..113: block k read at 30 + 21 k, written at 14 k
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+#ifdef KTK_PHASE_TIMING      // experimental builds (tools/phase_timing.py): clock64 sums per phase of a tile, lane 0 of every warp
+__device__ unsigned long long g_phase[8];
+#define KTK_PHASE(k) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[k], (unsigned long long)(t_ - tphase)); tphase = t_; } } while (0)
+#else
+#define KTK_PHASE(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const CamArgs a) {
   extern __shared__ __align__(16) double smem[];
+#ifdef KTK_PHASE_TIMING
+  long long tphase = clock64();
+#endif
   const int lane = threadIdx.x & 31;
   double* wbase = smem + (size_t)(threadIdx.x >> 5) * 32 * kCamDevStride;
   double* row = wbase + lane * kCamDevStride;
@@ -445,6 +454,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
     }
   }
   CamIn cur = cam_load(a, i);
+  KTK_PHASE(0);      // prefetch issue + input loads issued
 #ifdef KTK_ABL_FIXED_IO      // timing ablations only (tools/ablate.sh): wrong results on purpose
   if (cur.io >= 0) cur.io = 100;
 #endif
@@ -453,18 +463,22 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
 #endif
   const double ouv[2] = {cur.u, cur.v};
   warp_gather_records<kRefStride, kCamDevStride, kRefInRowDev>(wbase, a.recs, cur.ridx, lane);
+  KTK_PHASE(1);      // waited for the inputs (ridx), gather issued
   ObsForward f; f.status = kStatusRange; f.io = -1;
   if (cur.perm >= 0 && cur.ridx >= 0 && cur.io >= 0) {
     f.status = 0; f.io = cur.io; f.bo = cumulative_basis(cur.uo, a.sp.dt);
     static_rs_row_pose(a.knots, a.pairs, f);
   }
+  KTK_PHASE(2);      // observation pose (forward sweep)
   cp_async_wait_all();
   __syncwarp();
+  KTK_PHASE(3);      // waited for the landmark records
   if (cur.perm >= 0) {
     double r[2], jrho[2];
     int ir = -1, io = -1;
     ObsAdjoint adj;
     const int st = static_rs_row_ref_half(a.cam, f, row + kRefInRowDev, ouv, cur.w, cur.huber, r, row, jrho, &ir, &io, adj);
+    KTK_PHASE(4);    // projection + reference-window half
 #ifdef KTK_ST_EARLY      // experiment: the finished reference-window half leaves while the observation-window half is computed
     if (st == 0 && wantJ && !(a.flags & KTK_EVAL_DEVICE_ORDER)) { fence_async_smem(); bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamHalf * 8)); }
 #endif
@@ -485,6 +499,7 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
     if (a.i0r) a.i0r[dst] = ir;
     if (a.i0o) a.i0o[dst] = io;
   }
+  KTK_PHASE(5);      // observation-window half (reverse sweep) + r / index stores
   fence_async_smem();
   __syncwarp();
   if (!wantJ) return;
@@ -512,9 +527,11 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
 #else
     bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamRow * 8));
 #endif
+    KTK_PHASE(6);    // store issue
 #ifndef KTK_ST_NOWAIT
     bulk_store_wait_read();
 #endif
+    KTK_PHASE(7);    // waited for the TMA engine to read the rows
   }
 #endif
 }
@@ -2469,3 +2486,11 @@ int64_t ktk_gn_buffer(ktk_problem* p, const char* name, double** ptr) {
 }
 
 }  // extern "C"
+#ifdef KTK_PHASE_TIMING
+extern "C" int ktk_debug_read_phases(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_phase, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase, z, sizeof(z)); }
+  return 0;
+}
+#endif
