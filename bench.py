@@ -142,6 +142,9 @@ def cpu_baseline(cfg, frac, steps=1, warmup=1, budget_s=12.0):
     opt = optimised_cpu(cfg, sample)
     if opt:
         base["optimised"] = opt
+        # the driver keeps value / unit / cores / kind / sample: the optimised-CPU figure rides along in `sample` as well
+        base["sample"] += (f"; OPTIMISED CPU variant on the same sample (analytic Jacobians, hoisted knot-pair log, oracle/analytic_cpu.cpp, {opt['cores']} threads): "
+                           f"{opt['value']:.4g} {UNIT}")
     return base, rows, secs
 
 
@@ -442,7 +445,6 @@ def main():
             if dist is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
-        names = ("c", "grho", "blocks_a", "blocks_b", "z_a", "z_b", "q_a", "q_b")
         parts = {"evaluate": timed(lambda: ne.evaluate(cost=False)), "linearize": timed(lambda: gn_linearize(ne)), "schur_product": timed(lambda: gn_product(ne))}
         ar = {"linearize": ("lin",), "rhs": ("qq",), "product": ("qq",)}
         ar_bytes = {k_: int(sum(ne.buf(n_).numel() for n_ in v_) * 8) for k_, v_ in ar.items()}
@@ -543,9 +545,11 @@ def main():
         per_row = 76 + 8 + 24 + 8 * p.group_row_size(groups["cam"]) + 8
     dom_bytes = dom_rows * per_row
     achieved = dom_bytes / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_ms > 0 else None
-    traffic = None
+    traffic, traffic_src = None, None      # NOT measured by this run: dram bytes per launch of the same kernel from the committed ncu --set full capture
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get({"cam": "k_static_rs" if a.camera_method == "static" else "-", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get({"cam": "k_static_rs" if a.camera_method == "static" else "-", "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom])
+        traffic_src = tj.get("_source")
     except Exception:
         pass
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step,
@@ -558,7 +562,7 @@ def main():
             "clocks": dict(clocks.summary(), sampled="under the same steps, immediately after the timed region (sampler outside the event pair)"),
             "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_newton_rs", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
                          "kernel_ms_per_step": {k: v[0] / max(v[1], 1) for k, v in prof.items()},
                          # secondary, compute side (north_star: "fp64-pipe utilisation against chip peak"): fp64 instructions per row from the
@@ -567,6 +571,10 @@ def main():
                          # dependent-DFMA microbenchmark tools/fp64_microbench.cu on this pool's B200 (profiles/r1_fp64_microbench.txt)
                          "fp64": ({"flop_per_row": 4013, "achieved_tflops": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12, "peak_tflops": 32.8,
                                    "frac": dom_rows * 4013 / (dom_ms / max(dom_n, 1) * 1e-3) / 1e12 / 32.8} if (dom == "cam" and not cfg.get("split") and dom_ms > 0 and a.camera_method == "static") else None)}}
+    if line["roofline"].get("fp64"):      # scalars next to the nested object (a parser that keeps only scalars of `roofline` still sees the compute side)
+        line["roofline"]["fp64_frac"] = line["roofline"]["fp64"]["frac"]
+        line["roofline"]["fp64_achieved_tflops"] = line["roofline"]["fp64"]["achieved_tflops"]
+        line["roofline"]["fp64_peak_tflops"] = line["roofline"]["fp64"]["peak_tflops"]
     if strong_info is not None:
         line["strong"] = strong_info
     if not a.quick:      # rank 0 checks its own shard (every rank's shard has the same construction)

@@ -7,7 +7,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libkontiki_b200.so")
 SOURCES = ["ktk.cu"]
-HEADERS = ["spline_math.cuh", "split_math.cuh", "sensor_jac.cuh", "newton_math.cuh", "lie_math.cuh", "dualnum.cuh"]
+HEADERS = ["spline_math.cuh", "split_math.cuh", "sensor_jac.cuh", "newton_math.cuh", "lie_math.cuh", "dualnum.cuh", "gn_device.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
               "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
 

@@ -79,7 +79,7 @@ __global__ void k_gn_to_ambient(const double* __restrict__ P, const double* __re
 struct GnRowsArgs {
   RowWindows w; int n; const double* J; const int* idx[4]; const double* va[2]; double* u; const double* add; double add_scale;
 };
-__global__ void k_gn_rows_apply(const GnRowsArgs a) {
+__global__ void k_gn_rows_apply(const __grid_constant__ GnRowsArgs a) {      // __grid_constant__: the window tables are indexed in the constant bank, not copied to local memory
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   const double* Jr = a.J + (size_t)i * a.w.row_len;
@@ -138,7 +138,7 @@ __device__ __forceinline__ double gn_warp_sum(double v) {      // fixed butterfl
 // sorted row lists (lane l of warp w takes rows w*32 + l, + 32*kGnWarpsPerKnot, ...), fixed shuffle tree, fixed order over the warps.
 constexpr int kGnWarpsPerKnot = 4;
 template <int W>
-__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_gather(const GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ y) {
+__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_gather(const __grid_constant__ GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ y) {
   __shared__ double sh[kGnWarpsPerKnot][8];
   const int k = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (k >= n_knots) return;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_gather(const GnWinL
 // cover knot k has C_k = A + B (ONE parameter block, spline_base.h:391-394): the observation-window pass (role 2) uses A + B, the
 // reference-window pass (role 1) skips such rows.  Output: n_knots x lw x lw (row-major), the exact diagonal block of J^T J in local coordinates.
 template <int W>
-__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_blocks(const GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ Bd) {
+__global__ void __launch_bounds__(32 * kGnWarpsPerKnot) k_gn_blocks(const __grid_constant__ GnWinList L, int n_knots, int lw, const double* __restrict__ P, double* __restrict__ Bd) {
   constexpr int NS = W * (W + 1) / 2;
   __shared__ double sh[kGnWarpsPerKnot][NS];
   __shared__ double Hs[NS];

@@ -171,6 +171,7 @@ __global__ void k_pair_prepass(const double* __restrict__ k7, int n_knots, doubl
   }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 // One warp = one tile of 32 consecutive sorted rows; CTAs are small (1-2 warps) and one-shot: the hardware CTA scheduler
 // balances them better than a persistent loop did (measured: profiles/README.md "experiments").
 __device__ __forceinline__ int warp_tile() { return blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); }
@@ -180,6 +181,7 @@ struct ImuArgs {
   const double* knots; const double* pairs;
   const double* t; const double* y; const double* w; const int* perm;
   int n; uint32_t flags;
+  int ahead;                           // tiles resident on the chip: distance of the L2 prefetch of the row inputs (0 = off)
   double* r; double* J; int* i0; int* err;
 };
 struct ImuIn { double t, y0, y1, y2, y3, w; int perm; };
@@ -212,6 +214,16 @@ __device__ __forceinline__ void imu_tile(const ImuArgs& a, int tile, double* wba
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   const bool local = (a.flags & KTK_EVAL_LOCAL) != 0;
   const int i = tile * 32 + lane;
+  if (a.ahead > 0) {      // same as k_static_rs: a one-shot CTA meets its inputs cold; pull those of the tile that starts when this one ends into L2
+    const long long i2 = 32ll * ((long long)tile + a.ahead);
+    if (i2 + 32 <= a.n) {
+      constexpr int NYP = WHICH == 3 ? 4 : 3;
+      if (lane < 2) prefetch_l2(a.t + i2 + 16 * lane);
+      else if (lane < 4) prefetch_l2(a.w + i2 + 16 * (lane - 2));
+      else if (lane == 4) prefetch_l2(a.perm + i2);
+      else if (lane < 5 + 2 * NYP) prefetch_l2(a.y + NYP * i2 + 16 * (lane - 5));
+    }
+  }
   const ImuIn cur = WHICH == 3 ? imu_load_q(a, i) : imu_load(a, i);
   if (cur.perm >= 0) {
     double y[4] = {cur.y0, cur.y1, cur.y2, cur.y3};
@@ -420,7 +432,6 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_local(c
 // ktk_get_row_order gives the insertion index): the warp's 32 rows are one contiguous 29-KB block and lane 0 issues a single
 // bulk store for the tile.
 constexpr int kCamDevStride = 114, kRefInRowDev = 22;      // record at 22..113: block k read at 30 + 21 k, written at 14 k
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 #ifdef KTK_PHASE_TIMING      // experimental builds (tools/phase_timing.py): clock64 sums per phase of a tile, lane 0 of every warp
 __device__ unsigned long long g_phase[8];
 #define KTK_PHASE(k) do { if (lane == 0) { const long long t_ = clock64(); atomicAdd(&g_phase[k], (unsigned long long)(t_ - tphase)); tphase = t_; } } while (0)
@@ -1132,6 +1143,7 @@ struct ktk_problem {
   bool profiling = false;
   bool graphs_enabled = true;
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
+  int imu_resident_tiles = 0;     // ... of the IMU-row kernels
   bool newton_fast = true;        // KTK_NEWTON_FAST=0: every Newton-RS row through the forward-mode kernel (A/B, cross-check)
   int fuse_short = 1;             // 1: all IMU-like groups of an evaluation in one launch (k_short_batch); 2: + the landmark tables (measured slower, r2g); 0: off.  KTK_FUSE_SHORT overrides (A/B)
   ShortBatch short_batch;
@@ -1357,6 +1369,8 @@ int ktk_problem_create(int device, ktk_problem** out) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
       p->cam_resident_tiles = per_sm * (kCamThreads / 32) * prop.multiProcessorCount;
     if (const char* v = getenv("KTK_CAM_AHEAD")) p->cam_resident_tiles = atoi(v);      // A/B switch (0 = off)
+    p->imu_resident_tiles = 8 * prop.multiProcessorCount;                              // 8 one-warp CTAs per SM (register-limited)
+    if (const char* v = getenv("KTK_IMU_AHEAD")) p->imu_resident_tiles = atoi(v);
   }
   cudaFuncSetAttribute(k_imu_split<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kGyroSplitStride * 8);
   cudaFuncSetAttribute(k_imu_split<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kAccelSplitStride * 8);
@@ -1656,7 +1670,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
     a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
     for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
     a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
-    a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+    a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->imu_resident_tiles;
     a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
     if (g.kind == KTK_GYROSCOPE) k_imu<0><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
     else if (g.kind == KTK_POSITION) k_imu<2><<<blocks, kThreads, kThreads * kImuRowStride * 8, ss>>>(a);
@@ -1714,7 +1728,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
           a.sp = p->sp; fill_sensor_consts(g.sensor, a.imu);
           for (int c = 0; c < 3; ++c) a.imu.bias[c] = g.bias[c];
           a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p;
-          a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
+          a.t = g.d_t.p; a.y = g.d_y.p; a.w = g.d_w.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags; a.ahead = p->imu_resident_tiles;
           a.r = o.r; a.J = o.J; a.i0 = o.i0; a.err = p->d_err.p;
           const int which = g.kind == KTK_GYROSCOPE ? 0 : (g.kind == KTK_POSITION ? 2 : (g.kind == KTK_ORIENTATION ? 3 : 1));
           b->which[b->n_imu] = which; b->first[b->n_imu] = cta; b->n_imu += 1;
