@@ -493,22 +493,25 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs(const C
 #ifdef KTK_ST_EARLY      // experiment: the finished reference-window half leaves while the observation-window half is computed
     if (st == 0 && wantJ && !(a.flags & KTK_EVAL_DEVICE_ORDER)) { fence_async_smem(); bulk_store(a.J + (size_t)cur.perm * kCamRow, row, (unsigned)(kCamHalf * 8)); }
 #endif
+    // Everything the first half produced leaves BEFORE the reverse sweep: d r / d rho (the record under row[112..113] has been consumed), the
+    // residual and the two indices.  Stored after it they were live across the sweep, and two of them were spilled: a reload from local
+    // memory misses the 28 KB of L1 this kernel leaves and is an L2 round trip (ncu, profiles/r2m: ~4 % of the samples on its first use).
+    if (st != 0) {
+      atomicMin(a.err, st);
+      r[0] = r[1] = nan(""); ir = io = -1;
+      KTK_COLD_LOOP for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
+    } else { row[112] = jrho[0]; row[113] = jrho[1]; }
+    const size_t dst = (size_t)cur.perm;                 // == i in device order
+    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+    if (a.i0r) a.i0r[dst] = ir;
+    if (a.i0o) a.i0o[dst] = io;
     if (st == 0) {
 #ifndef KTK_ABL_NOBACK
       static_rs_row_obs_half(a.knots, a.pairs, f, adj, row + kCamHalf);
 #else
       for (int c = 0; c < 18; ++c) row[kCamHalf + c] = adj.Gp.a[c % 6] + adj.GpR.a[c % 6] * adj.Gth.a[c % 6];
 #endif
-      row[112] = jrho[0]; row[113] = jrho[1];
-    } else {
-      atomicMin(a.err, st);
-      r[0] = r[1] = nan(""); ir = io = -1;
-      KTK_COLD_LOOP for (int c = 0; c < kCamRow; ++c) row[c] = nan("");
     }
-    const size_t dst = (size_t)cur.perm;                 // == i in device order
-    if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
-    if (a.i0r) a.i0r[dst] = ir;
-    if (a.i0o) a.i0o[dst] = io;
   }
   KTK_PHASE(5);      // observation-window half (reverse sweep) + r / index stores
   fence_async_smem();

@@ -474,33 +474,53 @@ KB_HD void pose_forward(const double* knot0, const double* p1, const double* p2,
 // for free) and Gth to a body-frame rotation perturbation R <- R Exp(d), writes scale * d(row)/d(knots i0..i0+3)
 // into J ([4][N][7]).  With F_j = R0 E1..E_j = R T_j^T:
 //   eps_j = B_j Jr6(B_j w_j) d(w_j):  d/d(eps_rho_j) = Gp F_j = GpR T_j^T,  d/d(eps_theta_j) = Gth T_j^T - (GpR T_j^T) hat(c_{j+1})
-template <int N>
+// PARK_GP: Gp is not needed until the very end (knot i0's translation columns and its radial term), and N x 3 doubles held across the
+// three levels of the sweep are spilled in the 255-register kernels -- a local-memory reload there is an L2 round trip.  The caller parks
+// Gp in the translation columns of block 0 of J (J[7 r + 4 + c], in shared memory; nothing writes them before the last contraction) and
+// the sweep reads it back where it needs it.
+template <int N, bool PARK_GP = false>
 KB_HD void pose_backward(const double* knot0, const double* p1, const double* p2, const double* p3, const Basis& bs,
-                         const Mr<N>& Gp, const Mr<N>& GpR, const Mr<N>& Gth, double scale, double* J) {
+                         const Mr<N>& Gp_in, const Mr<N>& GpR_in, const Mr<N>& Gth, double scale, double* J) {
+  static_assert(!PARK_GP || N == 2, "parking layout: block 0 of a 2-row Jacobian");
+  // parked (N == 2): Gp at J[4..6], J[11..13];  GpR at J[0..2], J[7..9]
+  auto load_GpR = [&]() -> Mr<N> {
+    if (!PARK_GP) return GpR_in;
+    Mr<N> m;
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) m.a[3 * r + cc] = J[r * 7 + cc];
+    return m;
+  };
   G6<N> g, t;
   ExpPart e;
   exp_part(p3, bs.B[2], true, true, e);
-  t.U = GpR; t.W = Gth;
+  t.U = load_GpR(); t.W = Gth;
   g = mul_Jr6(t, e, bs.B[2]);
   contract_pair<N, false>(J + 3 * N * 7, g, p3 + kPairDOff + kPairSide, scale);
   contract_pair<N, false>(J + 2 * N * 7, g, p3 + kPairDOff, scale);
   M3 T = e.E; V3 c = e.a;
   exp_part(p2, bs.B[1], true, true, e);
-  t.U = rmul_nt(GpR, T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
+  t.U = rmul_nt(load_GpR(), T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
   g = mul_Jr6(t, e, bs.B[1]);
   contract_pair<N, true>(J + 2 * N * 7, g, p2 + kPairDOff + kPairSide, scale);
   contract_pair<N, false>(J + 1 * N * 7, g, p2 + kPairDOff, scale);
   c = e.a + e.E * c; T = e.E * T;
   exp_part(p1, bs.B[0], true, true, e);
-  t.U = rmul_nt(GpR, T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
+  t.U = rmul_nt(load_GpR(), T); t.W = rsub(rmul_nt(Gth, T), rmul_hat(t.U, c));
   g = mul_Jr6(t, e, bs.B[0]);
   contract_pair<N, true>(J + 1 * N * 7, g, p1 + kPairDOff + kPairSide, scale);
-  contract_pair<N, false>(J + 0 * N * 7, g, p1 + kPairDOff, scale);
   c = e.a + e.E * c; T = e.E * T;
   // knot i0 directly: t0 additive; R0 <- R0 Exp(d): dp = -R0 hat(c1) d, dtheta_body = T0^T d;
   // radial: P.t = t0 + q0 * a1 + ... with Eigen's polynomial q*v  =>  dp/ds = 2 (R0 - I) a1
-  const Mr<N> GpR0 = rmul_nt(GpR, T);
+  const Mr<N> GpR0 = rmul_nt(load_GpR(), T);
   const Mr<N> Gth0 = rsub(rmul_nt(Gth, T), rmul_hat(GpR0, c));
+  Mr<N> Gp;
+#pragma unroll
+  for (int r = 0; r < N; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) Gp.a[3 * r + cc] = PARK_GP ? J[r * 7 + 4 + cc] : Gp_in.a[3 * r + cc];
+  contract_pair<N, false>(J + 0 * N * 7, g, p1 + kPairDOff, scale);      // overwrites the parking space
   const M3 R0 = quat_to_rot(knot0[0], knot0[1], knot0[2], knot0[3]);
   const V3 dps = 2.0 * (R0 * e.a - e.a);
   double grad[N];
@@ -921,7 +941,12 @@ KB_HD int static_rs_row_ref_half(const CameraConst& cam, const ObsForward& f, co
 // Part 3: observation-window blocks Jobs[56] from the adjoints.
 KB_HD void static_rs_row_obs_half(const double* knots, const double* pairs, const ObsForward& f, const ObsAdjoint& adj, double* Jobs) {
   const double* po1 = pairs + (size_t)(f.io + 1) * kPairStride;
-  pose_backward<2>(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, adj.Gp, adj.GpR, adj.Gth, 1.0, Jobs);
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    Jobs[r * 7 + 4] = adj.Gp.a[3 * r]; Jobs[r * 7 + 5] = adj.Gp.a[3 * r + 1]; Jobs[r * 7 + 6] = adj.Gp.a[3 * r + 2];
+    Jobs[r * 7 + 0] = adj.GpR.a[3 * r]; Jobs[r * 7 + 1] = adj.GpR.a[3 * r + 1]; Jobs[r * 7 + 2] = adj.GpR.a[3 * r + 2];
+  }
+  pose_backward<2, true>(knots + (size_t)f.io * kKnotStride, po1, po1 + kPairStride, po1 + 2 * kPairStride, f.bo, adj.Gp, adj.GpR, adj.Gth, 1.0, Jobs);
 }
 
 }  // namespace kb
