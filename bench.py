@@ -243,6 +243,27 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host buffers of the end-to-end leg are
+    allocated on the GPU's own NUMA node: with 8 ranks each copying 538 MB per step, buffers on the far socket put every byte on the
+    inter-socket link (round 1: 1.76x end to end on 8 GPUs).  Returns a short description for the JSON line; never fails the run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use or use == allowed:
+            return {"bound": False, "cpus_allowed": len(allowed)}
+        os.sched_setaffinity(0, use)
+        return {"bound": True, "cpus": len(use), "cpus_allowed": len(allowed)}
+    except Exception as e:      # no NVML, no affinity syscall, container cpuset: run unbound
+        return {"bound": False, "why": str(e)[:80]}
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -272,6 +293,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (kontiki_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
+    # before any pinned allocation: the end-to-end leg is a host-memory / PCIe measurement.  One rank keeps every core (its CPU baseline uses them).
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -557,7 +580,7 @@ def main():
             "config": workload_config(a.workload, cfg_full if strong else cfg, "device" if strong else a.row_order, a.camera_method, a.camera_model, strong, world),
             "timing": timing,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)"},
+                    "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)", "numa": numa},
             "gpu_launches": int(launches),
             "clocks": dict(clocks.summary(), sampled="under the same steps, immediately after the timed region (sampler outside the event pair)"),
             "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_newton_rs", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],

@@ -116,8 +116,9 @@ typedef struct {
   int32_t* i0_d;     /*                                 camera i0_obs */
   double* Js;        /* KTK_EVAL_SENSOR_JACOBIANS.  IMU rows: d r / d time_offset (3 per row); the relative pose of an IMU is not
                         applied by the reference (TODO.md:6) so those columns are zero, and d r / d bias = -weight I for a
-                        ConstantBiasImu (constant_bias_imu.h:52-61).  Camera rows (SE3): 16 per row =
-                        d r/d q_ct (2x4) | d r/d p_ct (2x3) | d r/d time_offset (2x1) | pad (2), each block row-major as Ceres'. */
+                        ConstantBiasImu (constant_bias_imu.h:52-61).  Camera rows (static and NewtonRs; SE3 and split): 16 per row =
+                        d r/d q_ct (2x4) | d r/d p_ct (2x3) | d r/d time_offset (2x1), each block row-major as Ceres'; LiftingRs rows:
+                        24 per row = (3x4) | (3x3) | (3x1).  NewtonRs / LiftingRs: relative pose only, the time offset stays locked. */
 } ktk_group_out;
 
 const char* ktk_last_error(void);
@@ -165,8 +166,8 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static
  * measurement.  The row time is found by the reference's 5-step Newton iteration (:62-117) and the Jacobian is the
- * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  UniformSE3SplineTrajectory with locked
- * camera parameters only (KTK_EUNSUPPORTED otherwise); KTK_EVAL_LOCAL / KTK_EVAL_SENSOR_JACOBIANS are not built for it. */
+ * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  UniformSE3SplineTrajectory only; the camera's
+ * relative pose may be unlocked (KTK_EVAL_SENSOR_JACOBIANS), its time offset not (KTK_EUNSUPPORTED); KTK_EVAL_LOCAL is not built for it. */
 int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* LiftingRsCameraMeasurement::AddToEstimator (measurements/lifting_rscamera_measurement.h:151-229), same arrays as the static measurement.
@@ -175,7 +176,7 @@ int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
  * ktk_set_group_vt feeds the current row times (caller order) like ktk_set_group_sensor feeds sensor parameters.  Packed row
  * [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles (ktk_group_row_size), W and i0_b as for the Newton
  * rows (whole observation span; the four active knot blocks sit at their place inside it, the others are zero); r is 3 per row.
- * UniformSE3SplineTrajectory with locked camera parameters only; no KTK_EVAL_LOCAL,
+ * UniformSE3SplineTrajectory only; relative pose of the camera may be unlocked (Js: 24 per row), its time offset not; no KTK_EVAL_LOCAL,
  * no matrix-free products (KTK_EUNSUPPORTED). */
 int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                        const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);

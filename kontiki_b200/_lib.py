@@ -294,7 +294,7 @@ class Problem:
                 if cam:
                     o["i0_d"] = np.full(n, -1, np.int32)
             if sensor_jacobians:
-                o["Js"] = np.zeros((n, 16 if cam else 3))
+                o["Js"] = np.zeros((n, (24 if self.group_kind(g) == LIFTING_RS else 16) if cam else 3))
             outs.append(o)
         return outs
 

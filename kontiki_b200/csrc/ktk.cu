@@ -913,6 +913,30 @@ __global__ void k_static_rs_sensor(const CamSensorArgs a) {
 // (newton_math.cuh); 29 + 7 W directions per row, no staging -- thread (row, dir) owns two doubles of the packed row.
 // The landmark side comes from the same k_landmark_ref records as the static measurement.
 // =====================================================================================================================
+// Sensor-block columns of NewtonRs / LiftingRs rows (newton_math.cuh "sensor-block columns"): one thread per (row, column 0..6) in forward mode.
+// Js per row: [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero)], nres = 2 / 3.  Cold path.
+struct SpanSensorArgs {
+  SplineConst sp; CameraConst cam; const double* knots; const double* pairs; const double* rho;
+  const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
+  const double* vt; const int* perm; int n, W, lifting; uint32_t flags; double* Js; int* err;
+};
+__global__ void k_span_sensor(const SpanSensorArgs a) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / 7), c = (int)(tid % 7);
+  if (i >= a.n) return;
+  const int nres = a.lifting ? 3 : 2;
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]}, ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
+  const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
+  double* dst = a.Js + (size_t)8 * nres * (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+  const int kbase = newton_obs_window_base(a.sp, a.cam, a.obs_t0[i]);
+  const int st = span_sensor_column(a.lifting != 0, a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.rho[a.lm[i]], ouv, a.obs_t0[i],
+                                    a.lifting ? a.vt[i] : 0.0, kbase, a.W, a.w[i], hub, c, dst);
+  if (st != 0) {
+    atomicMin(a.err, st);
+    for (int rr = 0; rr < nres; ++rr) { if (c < 4) dst[4 * rr + c] = nan(""); else dst[4 * nres + 3 * rr + (c - 4)] = nan(""); if (c == 0) dst[7 * nres + rr] = nan(""); }
+  }
+}
+
 struct NewtonArgs {
   SplineConst sp; CameraConst cam;
   const double* knots; const double* pairs; const double* recs;
@@ -1430,8 +1454,8 @@ static int add_camera_group(ktk_problem* p, int kind, const ktk_camera* cam, int
   if (cam->rows <= 0 || cam->cols <= 0) return fail(KTK_EINVAL, "camera rows/cols must be positive");
   if (cam->model != KTK_CAMERA_PINHOLE && cam->model != KTK_CAMERA_ATAN) return fail(KTK_EINVAL, "unknown camera model");
   if (cam->model == KTK_CAMERA_ATAN && !(cam->gamma != 0.0)) return fail(KTK_EINVAL, "AtanCamera needs gamma != 0");
-  if (is_span_camera(kind) && (!cam->base.q_locked || !cam->base.p_locked || !cam->base.time_offset_locked))
-    return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements with unlocked camera parameters are not built");
+  if (is_span_camera(kind) && !cam->base.time_offset_locked)      // (the relative pose may be unlocked: k_span_sensor)
+    return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements with an unlocked time offset are not built");
   if (n < 0 || (n > 0 && (!obs_uv || !obs_t0 || !ref_uv || !ref_t0 || !lm_idx))) return fail(KTK_EINVAL, "bad measurement arrays");
   if (n > 0x7fffffff) return fail(KTK_EINVAL, "more than 2^31-1 measurements in one group");
   Group* g = new Group; g->kind = kind; g->n = n; g->cam = *cam; g->sensor = cam->base;
@@ -1507,7 +1531,21 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   // (sensors.h:147-164).  The flag is per evaluation, not per group: an unlocked IMU next to a locked camera is the ordinary case.
   if (g.sensor.q_locked && g.sensor.p_locked && g.sensor.time_offset_locked) return KTK_OK;
   if (!is_camera(g.kind) && g.sensor.time_offset_locked) return KTK_OK;              // an IMU's relative pose is not applied (TODO.md:6): only the time offset has columns
-  if (is_span_camera(g.kind)) return fail(KTK_EUNSUPPORTED, "sensor-block Jacobians of NewtonRs / LiftingRs camera measurements are not built");
+  if (is_span_camera(g.kind)) {
+    if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
+    if (!g.sensor.time_offset_locked) return fail(KTK_EUNSUPPORTED, "an unlocked time offset under NewtonRs / LiftingRs camera measurements is not built (relative pose: yes)");
+    if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
+    SpanSensorArgs a;
+    a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
+    a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
+    a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv_sorted.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm_sorted.p; a.w = g.d_w.p;
+    a.huber = g.d_huber.p; a.vt = g.d_vt.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.W = newton_window(p, g); a.lifting = g.kind == KTK_LIFTING_RS;
+    a.flags = flags; a.Js = o.Js; a.err = p->d_err.p;
+    const long long threads = (long long)g.n * 7;
+    k_span_sensor<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
+    p->launches += 1;
+    return KTK_OK;
+  }
   if (g.kind == KTK_STATIC_RS) {
     if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
     CamSensorArgs a;
@@ -1812,7 +1850,7 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     if (o.i0_b) { if ((st = g.o_i0b.resize(n))) return st; dev[gi].i0_b = g.o_i0b.p; }
     if (o.i0_c) { if ((st = g.o_i0c.resize(n))) return st; dev[gi].i0_c = g.o_i0c.p; }
     if (o.i0_d) { if ((st = g.o_i0d.resize(n))) return st; dev[gi].i0_d = g.o_i0d.p; }
-    if (o.Js && (flags & KTK_EVAL_SENSOR_JACOBIANS)) { if ((st = g.o_Js.resize(n * (is_camera(g.kind) ? 16 : 3)))) return st; dev[gi].Js = g.o_Js.p; }
+    if (o.Js && (flags & KTK_EVAL_SENSOR_JACOBIANS)) { if ((st = g.o_Js.resize(n * (g.kind == KTK_LIFTING_RS ? 24 : (is_camera(g.kind) ? 16 : 3))))) return st; dev[gi].Js = g.o_Js.p; }
   }
   if ((st = ktk_evaluate_device(p, p->d_knots7.p, (rho && n_rho > 0) ? p->d_rho.p : nullptr, n_rho, flags, dev.data()))) return st;
   for (size_t gi = 0; gi < p->groups.size(); ++gi) {
@@ -1826,7 +1864,7 @@ int ktk_evaluate(ktk_problem* p, const double* knots, const double* rho, int64_t
     if (dev[gi].i0_b && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_b, dev[gi].i0_b, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_c && split) KTK_CUDA(cudaMemcpyAsync(o.i0_c, dev[gi].i0_c, n * sizeof(int), cudaMemcpyDeviceToHost, s));
     if (dev[gi].i0_d && split && cam) KTK_CUDA(cudaMemcpyAsync(o.i0_d, dev[gi].i0_d, n * sizeof(int), cudaMemcpyDeviceToHost, s));
-    if (dev[gi].Js) KTK_CUDA(cudaMemcpyAsync(o.Js, dev[gi].Js, n * (cam ? 16 : 3) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dev[gi].Js) KTK_CUDA(cudaMemcpyAsync(o.Js, dev[gi].Js, n * (g.kind == KTK_LIFTING_RS ? 24 : (cam ? 16 : 3)) * sizeof(double), cudaMemcpyDeviceToHost, s));
   }
   return ktk_synchronize(p);
 }

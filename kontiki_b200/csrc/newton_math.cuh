@@ -406,6 +406,175 @@ KB_HD int lifting_rs_row(const SplineConst& sp, const CameraConst& cam, const do
   return 0;
 }
 
+// ---- sensor-block columns of NewtonRs / LiftingRs rows (KTK_EVAL_SENSOR_JACOBIANS; sensors.h:135-165) ----------------------------------------
+// Direction c of the camera's own parameter blocks: 0..3 relative orientation q_ct (ambient, x y z w), 4..6 relative position p_ct.  Both
+// sides of the row depend on them -- the landmark X(t_ref) = q_r (conj(q_ct) (yh - rho p_ct)) + rho p_r (newton_rscamera_measurement.h:50-53,
+// lifting_rscamera_measurement.h:36-41) and the projection q_ct X_obs + rho p_ct -- so the reference side is evaluated here on the dual number
+// instead of being read from the landmark record.  Eigen's q * v is a polynomial in the RAW q_ct (tqrot), which is what the derivative along a
+// non-unit direction sees.  The time offset of these two measurements stays locked (unlocked: KTK_EUNSUPPORTED; the reference moves both spans).
+template <class T> struct SensorSeed { TQ<T> qct; TV3<T> pct; };
+KB_HD SensorSeed<D1> camera_sensor_seed(const CameraConst& cam, int c) {
+  SensorSeed<D1> s;
+  s.qct.x = D1(cam.q_ct[0], c == 0 ? 1.0 : 0.0); s.qct.y = D1(cam.q_ct[1], c == 1 ? 1.0 : 0.0);
+  s.qct.z = D1(cam.q_ct[2], c == 2 ? 1.0 : 0.0); s.qct.w = D1(cam.q_ct[3], c == 3 ? 1.0 : 0.0);
+  s.pct = tv3<D1>(D1(cam.p_ct[0], c == 4 ? 1.0 : 0.0), D1(cam.p_ct[1], c == 5 ? 1.0 : 0.0), D1(cam.p_ct[2], c == 6 ? 1.0 : 0.0));
+  return s;
+}
+// plain-value spline evaluation at (i0, u0) lifted to T (no knot seeds)
+template <class T> KB_HD TEval<T> se3_eval_plain_t(const SplineConst& sp, const double* knots, const double* pairs, int i0, double u0) {
+  const T u = T(u0);
+  const T u2 = u * u, u3 = u2 * u;
+  const double di = 1.0 / sp.dt;
+  T B[3], dB[3];
+  B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
+  B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
+  B[2] = u3 * T(1.0 / 6.0);
+  dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
+  dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
+  dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
+  T k0[7], om[3][6];
+  const double* kn = knots + (size_t)i0 * kKnotStride;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) k0[c] = T(kn[c]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double* pr = pairs + (size_t)(i0 + 1 + j) * kPairStride;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m]);
+  }
+  return se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
+}
+// X(t_ref) on the dual number: the reference pose in plain doubles, the camera's relative pose seeded
+KB_HD int sensor_ref_point(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, int nseg, const Segment& s0,
+                           const Segment& s1, const double* ref_uv, double ref_t0, double rho, const SensorSeed<D1>& sd, TV3<D1>& X) {
+  typedef D1 T;
+  int i0; double u0;
+  if (locate_in_segments(nseg, s0, s1, static_rs_time(cam, ref_t0, ref_uv[1]), sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+  if (i0 < 0 || i0 + 3 >= sp.n_knots) return kStatusRange;
+  const TEval<T> er = se3_eval_plain_t<T>(sp, knots, pairs, i0, u0);
+  const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
+  const TV3<T> Xref = tqrot(tqconj(sd.qct), tv3<T>(T(yh.x), T(yh.y), T(yh.z)) - T(rho) * sd.pct);
+  X = tqrot(er.q, Xref) + T(rho) * er.p;
+  return 0;
+}
+// NewtonRs: column c of the sensor blocks; same iteration as newton_rs_direction, knots unseeded
+KB_HD int newton_rs_sensor_direction(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref_uv,
+                                     double ref_t0, double rho_v, const double* obs_uv, double obs_t0, int kbase, int W, int c, NewtonRow& out) {
+  typedef D1 T;
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const SensorSeed<T> sd = camera_sensor_seed(cam, c);
+  TV3<T> X;
+  if (sensor_ref_point(sp, cam, knots, pairs, nseg, s0, s1, ref_uv, ref_t0, rho_v, sd, X) != 0) return kStatusRange;
+  const T rho = T(rho_v);
+  const double rows = (double)cam.rows;
+  const double t0_obs = add_rn(obs_t0, cam.time_offset);
+  T t_obs = T(static_rs_time(cam, obs_t0, obs_uv[1]));
+  const double max_dt = 0.5 * cam.readout / rows, max_dt2 = max_dt * max_dt;
+  const double min_bound = t0_obs, max_bound = add_rn(t0_obs, cam.readout);
+  T y[2] = {T(0.0), T(0.0)};
+  out.iterations = 0;
+  for (int iter = 0; iter < 5; ++iter) {
+    int i0; double u0;
+    if (locate_in_segments(nseg, s0, s1, t_obs.a, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+    if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;
+    // the row time carries a derivative from the second iteration on: u = (u0, dt_obs / dt)
+    const T u = T(u0, t_obs.d / sp.dt);
+    const T u2 = u * u, u3 = u2 * u;
+    const double di = 1.0 / sp.dt;
+    T B[3], dB[3];
+    B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
+    B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
+    B[2] = u3 * T(1.0 / 6.0);
+    dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
+    dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
+    dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
+    T k0[7], om[3][6];
+    const double* kn = knots + (size_t)i0 * kKnotStride;
+#pragma unroll
+    for (int cc = 0; cc < 7; ++cc) k0[cc] = T(kn[cc]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double* pr = pairs + (size_t)(i0 + 1 + j) * kPairStride;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m]);
+    }
+    const TEval<T> ev = se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
+    TQ<T> wq; wq.x = ev.w.x; wq.y = ev.w.y; wq.z = ev.w.z; wq.w = T(0.0);
+    TQ<T> dq = tqmul(wq, ev.q); dq.x = T(0.5) * dq.x; dq.y = T(0.5) * dq.y; dq.z = T(0.5) * dq.z; dq.w = T(0.5) * dq.w;
+    const TQ<T> dq_inv = tqconj(dq), q_inv = tqconj(ev.q);
+    const TV3<T> s = X - rho * ev.p;
+    const TV3<T> ds = (T(0.0) - rho) * ev.v;
+    const TV3<T> X_obs = tqrot(q_inv, s);
+    const TV3<T> X_cam = tqrot(sd.qct, X_obs) + rho * sd.pct;
+    TQ<T> sq; sq.x = s.x; sq.y = s.y; sq.z = s.z; sq.w = T(0.0);
+    TQ<T> dsq; dsq.x = ds.x; dsq.y = ds.y; dsq.z = ds.z; dsq.w = T(0.0);
+    const TQ<T> a1 = tqmul(tqmul(dq_inv, sq), ev.q), a2 = tqmul(tqmul(q_inv, dsq), ev.q), a3 = tqmul(tqmul(q_inv, sq), dq);
+    const TV3<T> dX_obs = tv3<T>(a1.x + a2.x + a3.x, a1.y + a2.y + a3.y, a1.z + a2.z + a3.z);
+    const TV3<T> dX_cam = tqrot(sd.qct, dX_obs) + rho * sd.pct;                 // sic (:92)
+    T dy[2];
+    camera_project_t<T>(cam, X_cam, dX_cam, y, dy);
+    const T f = y[1] - (T(rows) * (t_obs - T(t0_obs)) / T(cam.readout));
+    const T df = dy[1] - T(rows / cam.readout);
+    const T dt = f / df;
+    t_obs = t_obs - dt;
+    out.iterations = iter + 1;
+    if (dt.a * dt.a < max_dt2) break;
+    if (t_obs.a < min_bound) t_obs = T(min_bound);
+    else if (t_obs.a > max_bound) t_obs = T(max_bound);
+  }
+  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+  return 0;
+}
+// LiftingRs: column c of the sensor blocks (the third residual does not depend on the camera pose: dvt = 0)
+KB_HD int lifting_rs_sensor_direction(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref_uv,
+                                      double ref_t0, double rho_v, double obs_t0, double vt, int kbase, int W, int c, LiftingRow& out) {
+  typedef D1 T;
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const SensorSeed<T> sd = camera_sensor_seed(cam, c);
+  TV3<T> X;
+  if (sensor_ref_point(sp, cam, knots, pairs, nseg, s0, s1, ref_uv, ref_t0, rho_v, sd, X) != 0) return kStatusRange;
+  const T rho = T(rho_v);
+  const double t_obs = add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(vt, cam.readout));
+  int i0; double u0;
+  if (locate_in_segments(nseg, s0, s1, t_obs, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+  if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;
+  const TEval<T> ev = se3_eval_plain_t<T>(sp, knots, pairs, i0, u0);
+  const TV3<T> X_obs = tqrot(tqconj(ev.q), X - rho * ev.p);
+  const TV3<T> X_cam = tqrot(sd.qct, X_obs) + rho * sd.pct;
+  T y[2], dy[2];
+  camera_project_t<T>(cam, X_cam, tv3<T>(T(0.0), T(0.0), T(0.0)), y, dy);
+  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d; out.dvt = 0.0;
+  return 0;
+}
+
+// Column c (0..6) of a row's sensor blocks, Huber-corrected like its knot columns, into Js_row = [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres)].
+KB_HD int span_sensor_column(bool lifting, const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* ref_uv,
+                             double ref_t0, double rho, const double* obs_uv, double obs_t0, double vt, int kbase, int W, double weight, double huber_c,
+                             int c, double* Js_row) {
+  const int nres = lifting ? 3 : 2;
+  double r[3], j[3];
+  if (lifting) {
+    LiftingRow o;
+    const int st = lifting_rs_sensor_direction(sp, cam, knots, pairs, ref_uv, ref_t0, rho, obs_t0, vt, kbase, W, c, o);
+    if (st != 0) return st;
+    lifting_rs_finish(o, cam, obs_uv, vt, weight, huber_c, r, j);
+  } else {
+    NewtonRow o;
+    const int st = newton_rs_sensor_direction(sp, cam, knots, pairs, ref_uv, ref_t0, rho, obs_uv, obs_t0, kbase, W, c, o);
+    if (st != 0) return st;
+    newton_rs_finish(o, obs_uv, weight, huber_c, r, j);
+  }
+  for (int rr = 0; rr < nres; ++rr) {
+    if (c < 4) Js_row[4 * rr + c] = j[rr]; else Js_row[4 * nres + 3 * rr + (c - 4)] = j[rr];
+    if (c == 0) Js_row[7 * nres + rr] = 0.0;      // time offset: locked for these measurements
+  }
+  return 0;
+}
+
 // ---- LiftingRs rows in CLOSED FORM (one thread per row, the static kernel's machinery with three residual rows) ------------------------------
 // Everything but the d/d vt column is the static row evaluated at the lifted time: with the corrector C (3 x 3, identity without the loss)
 //   d r / d Xc = C [:, 0:2] (-weight) d y / d Xc          (3 x 3; the timing residual does not see the point)

@@ -400,15 +400,15 @@ class TrajectoryEstimator:
             sn, scols = self._sensor_cols.get(id(grp["sensor"]), (None, {}))
             rr = row0 + nres * np.arange(n)[:, None] + np.arange(nres)[None, :]           # (n, nres) global residual rows
             if "d" in scols:
-                Jd = o["Js"][:, 14:16] if grp["kind"] == "cam" else o["Js"][:, 0:3]
+                Jd = o["Js"][:, 7 * nres:8 * nres] if grp["kind"] == "cam" else o["Js"][:, 0:3]
                 rows_i.append(rr.reshape(-1)); cols_i.append(np.full(rr.size, scols["d"])); vals.append(Jd.reshape(-1))
-            if grp["kind"] == "cam" and ("q" in scols or "p" in scols):
+            if grp["kind"] == "cam" and ("q" in scols or "p" in scols):      # Js = [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres)]
                 if "q" in scols:
                     Pq = _quat_plus_jacobian(sn._q_ct[None, :])[0]                         # (4, 3)
-                    Jq = o["Js"][:, 0:8].reshape(n, 2, 4) @ Pq
+                    Jq = o["Js"][:, 0:4 * nres].reshape(n, nres, 4) @ Pq
                     rows_i.append(np.repeat(rr.reshape(-1), 3)); cols_i.append(np.tile(scols["q"] + np.arange(3), rr.size)); vals.append(Jq.reshape(-1))
                 if "p" in scols:
-                    rows_i.append(np.repeat(rr.reshape(-1), 3)); cols_i.append(np.tile(scols["p"] + np.arange(3), rr.size)); vals.append(o["Js"][:, 8:14].reshape(-1))
+                    rows_i.append(np.repeat(rr.reshape(-1), 3)); cols_i.append(np.tile(scols["p"] + np.arange(3), rr.size)); vals.append(o["Js"][:, 4 * nres:7 * nres].reshape(-1))
             bname = {"gyro": "gb", "accel": "ab"}.get(grp["kind"])
             if bname in scols:                                                                # d r / d bias = -weight I
                 rows_i.append(rr.reshape(-1)); cols_i.append(np.tile(scols[bname] + np.arange(3), n)); vals.append(np.repeat(-grp["weight"], 3))

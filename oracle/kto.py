@@ -268,15 +268,16 @@ def lifting_rs_residuals(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho,
     Jb = np.zeros((n, cap, 3, 4)) if (has_b and jac_mode) else None
     Jvt = np.zeros((n, 3)) if jac_mode else None
     Jrho = np.zeros((n, 3)) if jac_mode else None
+    Js = np.zeros((n, 24)) if jac_mode else None      # sensor blocks: q_ct (3x4) | p_ct (3x3) | time offset (3)
     i0 = [np.zeros(n, np.int32) for _ in range(4)]
     st = np.zeros(n, np.int32)
     secs = C.c_double(0)
     tc, sc, cm = traj.c(), cam.c(), cam.cmeta()
     code = lib().kto_lifting_rs_residuals(C.byref(tc), C.byref(sc), C.byref(cm), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx),
                                           _p(rho), _p(vt), _p(weight), int(jac_mode), int(nthreads), _p(r), cap, _p(ids_a), _p(Ja), cap,
-                                          _p(ids_b), _p(Jb), _p(Jvt), _p(Jrho), _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i0[3]), _p(st), C.byref(secs))
+                                          _p(ids_b), _p(Jb), _p(Jvt), _p(Jrho), _p(i0[0]), _p(i0[1]), _p(i0[2]), _p(i0[3]), _p(st), C.byref(secs), _p(Js))
     _check(code, raise_on_error)
-    return dict(r=r, ids_a=ids_a, Ja=Ja, ids_b=ids_b, Jb=Jb, Jvt=Jvt, Jrho=Jrho, vt=vt, i0_ref_a=i0[0], i0_obs_a=i0[1], i0_ref_b=i0[2], i0_obs_b=i0[3],
+    return dict(r=r, ids_a=ids_a, Ja=Ja, ids_b=ids_b, Jb=Jb, Jvt=Jvt, Jrho=Jrho, Js=Js, vt=vt, i0_ref_a=i0[0], i0_obs_a=i0[1], i0_ref_b=i0[2], i0_obs_b=i0[3],
                 status=st, eval_seconds=secs.value)
 
 

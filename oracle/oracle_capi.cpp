@@ -398,12 +398,12 @@ int kto_static_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto
 
 // LiftingRsCameraMeasurement residual blocks (lifting_rscamera_measurement.h:151-229).  vt[n]: the current value of each measurement's
 // frame-normalised row time (its own parameter block, bounds [0, 1]); vt_orig = obs_uv.y / rows (:68).
-//   r[3n]; ids_a/Ja (3 x size_a blocks), ids_b/Jb (3 x 4), Jvt[3n], Jrho[3n]; i0_* as kto_static_rs_residuals (observation at the lifted time).
+//   r[3n]; ids_a/Ja (3 x size_a blocks), ids_b/Jb (3 x 4), Jvt[3n], Jrho[3n], Js[24n] (may be NULL); i0_* as kto_static_rs_residuals (observation at the lifted time).
 int kto_lifting_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kto_camera* cmeta, int n, const double* obs_uv,
                              const double* obs_t0, const double* ref_uv, const double* ref_t0, const int* lm_idx, const double* rho,
                              const double* vt, const double* weight, int jac_mode, int nthreads, double* r, int cap_a, int* ids_a,
                              double* Ja, int cap_b, int* ids_b, double* Jb, double* Jvt, double* Jrho, int* i0_ref_a, int* i0_obs_a,
-                             int* i0_ref_b, int* i0_obs_b, int* status, double* eval_seconds) {
+                             int* i0_ref_b, int* i0_obs_b, int* status, double* eval_seconds, double* Js) {
   TrajData td(*tr);
   CameraMeta cm; cm.readout = cmeta->readout; cm.rows = cmeta->rows; cm.cols = cmeta->cols;
   for (int a = 0; a < 3; ++a) for (int c = 0; c < 3; ++c) cm.K[a][c] = cmeta->K[3 * a + c];
@@ -456,6 +456,9 @@ int kto_lifting_rs_residuals(const kto_traj* tr, const kto_sensor* cam, const kt
     if (Jb) { std::memset(Jb + size_t(i) * cap_b * 12, 0, sizeof(double) * cap_b * 12);
       for (size_t k = 0; k < b.ids_b.size(); ++k) copy_block(jac[pb + k], Jb + (size_t(i) * cap_b + k) * 12, 12); }
     pb += b.ids_b.size();
+    // sensor blocks (sensors.h:135-165): q_ct (3 x 4) | p_ct (3 x 3) | time offset (3 x 1)
+    if (Js) { double* d = Js + size_t(i) * 24; std::memset(d, 0, 24 * sizeof(double));
+      copy_block(jac[pb], d, 12); copy_block(jac[pb + 1], d + 12, 9); copy_block(jac[pb + 2], d + 21, 3); }
     if (Jvt) copy_block(jac[pb + 3], Jvt + 3 * size_t(i), 3);
     if (Jrho) copy_block(jac[pb + 4], Jrho + 3 * size_t(i), 3);
   }

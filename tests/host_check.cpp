@@ -141,6 +141,28 @@ void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const dou
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }
 }
+// Sensor-block columns of NewtonRs (nres = 2, Js n x 16) / LiftingRs (nres = 3, Js n x 24) rows: what k_span_sensor does, one (row, column) at a
+// time.  Layout [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero: locked)], Huber-corrected like the knot columns.
+void hc_span_sensor(int lifting, double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
+                    double time_offset, double max_time_offset, int locked, double readout, int rows, const double* knots8, const double* pairs,
+                    int n, const double* obs_uv, const double* obs_t0, const double* ref_uv, const double* ref_t0, const int* lm_idx,
+                    const double* rho, const double* vt, const double* w, const double* huber_c, int W, double* Js, int* status) {
+  SplineConst sp{t0, dt, n_knots, 0};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  camera_set_pose(cam, q_ct, p_ct);
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  const int nres = lifting ? 3 : 2;
+  for (int i = 0; i < n; ++i) {
+    const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
+    status[i] = 0;
+    for (int c = 0; c < 7 && status[i] == 0; ++c)
+      status[i] = span_sensor_column(lifting != 0, sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], obs_uv + 2 * i, obs_t0[i],
+                                     lifting ? vt[i] : 0.0, kbase, W, w[i], huber_c ? huber_c[i] : 0.0, c, Js + (size_t)8 * nres * i);
+  }
+}
 int hc_newton_window(double t0, double dt, double readout, double obs_t0) {
   SplineConst sp{t0, dt, 1 << 30, 0};
   CameraConst cam; cam.readout = readout; cam.time_offset_locked = 1; cam.max_time_offset = 0.0;

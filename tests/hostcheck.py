@@ -128,6 +128,29 @@ def lifting_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho,
     return dict(r=r, J=J, i0_ref=ir, i0_obs=kb, W=W, status=st, vt=vt)
 
 
+def span_sensor(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, lifting=False, vt=None, w=None, huber_c=None):
+    """Sensor-block columns of NewtonRs (Js (n, 16)) / LiftingRs (Js (n, 24)) rows: [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres)]."""
+    _set_camera_model(cam)
+    k8, pairs = prepass(knots7)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    vt = np.ascontiguousarray(obs_uv[:, 1] / float(cam.rows) if vt is None else _f(vt), np.float64)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    W = newton_window(t0, dt, cam.readout, obs_t0)
+    Js = np.zeros((n, 24 if lifting else 16))
+    st = np.zeros(n, np.int32)
+    lib().hc_span_sensor(int(bool(lifting)), C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)),
+                         C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked), C.c_double(cam.readout), int(cam.rows),
+                         _p(k8), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0), _p(lm_idx), _p(rho), _p(vt), _p(w), _p(hc), int(W),
+                         _p(Js), _p(st))
+    return dict(Js=Js, status=st, W=W)
+
+
 def static_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
     """cam: oracle.kto.Camera-like (K, q_ct, p_ct, time_offset, max_time_offset, d_locked, readout, rows)."""
     _set_camera_model(cam)

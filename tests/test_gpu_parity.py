@@ -729,3 +729,53 @@ def test_lifting_rows_match_oracle(atan, robust):
     with pytest.raises(NotImplementedError):
         p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_LOCAL)
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,atan,robust", [("newton", False, False), ("newton", True, True), ("lifting", False, True), ("lifting", True, False)])
+def test_span_camera_unlocked_relative_pose_matches_oracle(method, atan, robust):
+    """NewtonRs / LiftingRs rows with the camera's relative pose unlocked (sensors.h:135-165): KTK_EVAL_SENSOR_JACOBIANS fills
+    Js = [d r/d q_ct (nres x 4, ambient) | d r/d p_ct (nres x 3) | time offset (zero: it stays locked)] (k_span_sensor, forward mode through both sides of
+    the row) -- against the oracle's autodiff over the sensor blocks; the knot / rho columns are untouched by the flag."""
+    cfg = syn.make_config("C3", scale=0.003)
+    c = cfg["cam"]
+    rng = np.random.default_rng(41)
+    n = len(c["lm_idx"])
+    out_l = rng.random(n) < 0.2
+    c["obs_uv"][out_l] += rng.normal(0, 40, (out_l.sum(), 2))
+    c["obs_uv"] += rng.normal(0, 1.0, c["obs_uv"].shape)
+    c["weight"] = rng.uniform(0.5, 2, n)
+    kw = dict(wc=(0.02, -0.01), gamma=0.9) if atan else {}
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    p = _lib.Problem(0)
+    p.set_se3_spline(cfg["dt"], cfg["t0"], len(cfg["knots"]))
+    cam = _lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], q_ct=q_ct, p_ct=p_ct, q_locked=False, p_locked=False, **kw)
+    add = p.add_newton_rs if method == "newton" else p.add_lifting_rs
+    g = add(cam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["weight"], c["huber_c"])
+    ocam = kto.Camera(c["rows"], c["cols"], c["readout"], K=c["K"], method="newton" if method == "newton" else "static", q_ct=q_ct, p_ct=p_ct,
+                      q_locked=False, p_locked=False, **kw)
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    nres = 2 if method == "newton" else 3
+    vt = None
+    if method == "lifting":
+        vt = np.clip(c["obs_uv"][:, 1] / c["rows"] + rng.uniform(-0.2, 0.2, n), 0.0, 1.0)
+        p.set_group_vt(g, vt)
+        o = kto.lifting_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], vt=vt, weight=c["weight"], jac_mode=2, cap=24)
+    else:
+        o = kto.static_rs_residuals(traj, ocam, c["obs_uv"], c["obs_t0"], c["ref_uv"], c["ref_t0"], c["lm_idx"], c["rho"], c["weight"], jac_mode=2, cap=24)
+    base = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    plain = p.evaluate(cfg["knots"], c["rho"], base)[g]
+    out = p.evaluate(cfg["knots"], c["rho"], base | _lib.EVAL_SENSOR_JACOBIANS)[g]
+    assert np.array_equal(out["J"], plain["J"]) and np.array_equal(out["r"], plain["r"])
+    assert out["Js"].shape == (n, 8 * nres)
+    Jo = o["Js"].copy()
+    if robust:
+        for i in range(n):
+            cols = np.concatenate([Jo[i, :4 * nres].reshape(nres, 4), Jo[i, 4 * nres:7 * nres].reshape(nres, 3), Jo[i, 7 * nres:].reshape(nres, 1)], axis=1)
+            _, _, J2 = kto.huber_correct(c["huber_c"][i], o["r"][i], cols)
+            Jo[i] = np.concatenate([J2[:, :4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7].reshape(-1)])
+    assert np.abs(Jo[:, :7 * nres]).max() > 1.0
+    assert parity.rel_err(out["Js"][:, None, :7 * nres], Jo[:, None, :7 * nres]) < parity.TOL
+    assert not out["Js"][:, 7 * nres:].any()
+    dev = p.evaluate(cfg["knots"], c["rho"], base | _lib.EVAL_SENSOR_JACOBIANS | _lib.EVAL_DEVICE_ORDER)[g]
+    assert np.array_equal(dev["Js"], out["Js"][p.get_row_order(g)])

@@ -389,3 +389,39 @@ def test_optimised_cpu_variant_matches_oracle():
     Js, Jrho = parity.scatter_cam(J, o["i0_ref_a"], o["i0_obs_a"], o["ids_a"])
     assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
 
+
+
+@pytest.mark.parametrize("atan,robust", [(False, False), (True, True)])
+def test_span_camera_sensor_columns_match_oracle(atan, robust):
+    """Unlocked relative pose of the camera (sensors.h:135-165) under NewtonRs / LiftingRs rows: the q_ct (ambient) and p_ct columns, forward mode
+    through BOTH sides of the row (the landmark depends on the camera pose too) vs the oracle's autodiff over the sensor blocks."""
+    dt = 0.05
+    n_checked = 0
+    for method, lifting in (("newton", False), ("static", True)):
+        knots, s, cam = _camera_case_model(dt, 11, atan, method)
+        cam.q_locked = cam.p_locked = False
+        n = len(s["lm_idx"])
+        args = (s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"])
+        traj = kto.Traj(kto.SE3, dt, 0.0, knots)
+        nres = 3 if lifting else 2
+        if lifting:
+            vt = np.clip(s["obs_uv"][:, 1] / s["rows"] + np.random.default_rng(4).uniform(-0.2, 0.2, n), 0.0, 1.0)
+            o = kto.lifting_rs_residuals(traj, cam, *args, vt=vt, weight=s["weight"], jac_mode=2, cap=24)
+        else:
+            vt = None
+            o = kto.static_rs_residuals(traj, cam, *args, s["weight"], jac_mode=2, cap=24)
+        c = np.full(n, 2.0) if robust else None
+        h = hc.span_sensor(knots, dt, 0.0, cam, *args, lifting=lifting, vt=vt, w=s["weight"], huber_c=c)
+        assert (h["status"] == 0).all()
+        Jo = o["Js"]
+        if robust:      # ceres::Corrector on the sensor columns of every row
+            Jo = Jo.copy()
+            for i in range(n):
+                cols = np.concatenate([Jo[i, :4 * nres].reshape(nres, 4), Jo[i, 4 * nres:7 * nres].reshape(nres, 3), Jo[i, 7 * nres:].reshape(nres, 1)], axis=1)
+                _, _, J2 = kto.huber_correct(2.0, o["r"][i], cols)
+                Jo[i] = np.concatenate([J2[:, :4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7].reshape(-1)])
+        assert np.abs(Jo[:, :7 * nres]).max() > 1.0
+        assert parity.rel_err(h["Js"][:, None, :7 * nres], Jo[:, None, :7 * nres]) < parity.TOL
+        assert not h["Js"][:, 7 * nres:].any()          # the time offset of these measurements stays locked
+        n_checked += n
+    assert n_checked > 50

@@ -660,3 +660,32 @@ def test_add_measurement_checks_the_widened_span_of_an_unlocked_time_offset():
         est.add_measurement(GyroscopeMeasurement(imu, traj.min_time + 0.01, np.zeros(3)))
     with pytest.raises(ValueError):
         est.add_measurement(GyroscopeMeasurement(imu, traj.max_time - 0.01, np.zeros(3)))
+
+
+@pytest.mark.parametrize("cls", [NewtonRsCameraMeasurement, LiftingRsCameraMeasurement])
+def test_solve_recovers_camera_relative_pose_under_span_measurements(cls):
+    """The camera's relative pose unlocked under NewtonRs / LiftingRs measurements (sensors.h:135-165; the reference instantiates every measurement
+    with every sensor state): structure generated with the true pose, the estimator starts from a displaced one with trajectory and landmarks
+    locked, and the sensor-block columns (k_span_sensor) bring it back."""
+    traj = smooth_se3(n=40, dt=0.1)
+    K = np.array([[900., 0, 960], [0, 900, 540], [0, 0, 1]])
+    cam = PinholeCamera(1080, 1920, 0.026, K)
+    lms = _small_sfm(traj, cam, n_lm=30, n_views=6, seed=5)
+    q_true, p_true = cam.relative_pose                       # (w, x, y, z), p
+    ax = np.array([0.004, -0.003, 0.002])
+    w1, x1, y1, z1 = q_true; x2, y2, z2 = 0.5 * ax; w2 = np.sqrt(1.0 - 0.25 * ax @ ax)
+    q_bad = np.array([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2])
+    cam.relative_pose = (q_bad, p_true + np.array([0.02, -0.01, 0.015]))
+    cam.relative_position_locked = cam.relative_orientation_locked = False
+    est = kontiki.TrajectoryEstimator(traj)
+    for L in lms:
+        L.locked = True
+        for o in L.observations:
+            if not o.is_reference:
+                est.add_measurement(cls(cam, o))
+    traj.locked = True
+    s = est.solve(max_iterations=30, progress=False)
+    assert s.final_cost < 1e-3 * s.initial_cost
+    qe, pe = cam.relative_pose
+    assert np.abs(pe - p_true).max() < 2e-3
+    assert min(np.abs(qe - q_true).max(), np.abs(qe + q_true).max()) < 5e-4
