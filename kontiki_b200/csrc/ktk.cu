@@ -1010,11 +1010,12 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
     if (d < 0) continue;
     const double* src = smem + rr * kNewtonStage;
     double* dst = a.J + (size_t)d * row_len;
+    const int lo = 56 + 14 * sh, tail0 = 56 + 14 * a.W;      // the four active blocks are one run of 56 doubles at `lo`
     for (int c = lane; c < row_len; c += 32) {
       double v;
       if (c < 56) v = src[c];
-      else if (c < 56 + 14 * a.W) { const int b = (c - 56) / 14 - sh; v = (b >= 0 && b < 4) ? src[56 + 14 * b + (c - 56) % 14] : 0.0; }
-      else v = src[112 + (c - 56 - 14 * a.W)];
+      else if (c >= tail0) v = src[112 + (c - tail0)];
+      else v = (unsigned)(c - lo) < 56u ? src[56 + (c - lo)] : 0.0;
       dst[c] = v;
     }
   }
@@ -1105,11 +1106,12 @@ __global__ void __launch_bounds__(32) k_lifting_rs(const NewtonArgs a, const dou
     if (d < 0) continue;
     const double* src = smem + rr * kLiftStage;
     double* dst = a.J + (size_t)d * row_len;
+    const int lo = 84 + 21 * sh, tail0 = 84 + 21 * a.W;      // the four active blocks are one run of 84 doubles at `lo`; no division per element
     for (int c = lane; c < row_len; c += 32) {
       double v;
       if (c < 84) v = src[c];
-      else if (c < 84 + 21 * a.W) { const int b = (c - 84) / 21 - sh; v = (b >= 0 && b < 4) ? src[84 + 21 * b + (c - 84) % 21] : 0.0; }
-      else v = src[168 + (c - 84 - 21 * a.W)];
+      else if (c >= tail0) v = src[168 + (c - tail0)];
+      else v = (unsigned)(c - lo) < 84u ? src[84 + (c - lo)] : 0.0;
       dst[c] = v;
     }
   }
