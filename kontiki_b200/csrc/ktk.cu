@@ -1197,7 +1197,11 @@ struct ktk_problem {
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   int imu_resident_tiles = 0;     // ... of the IMU-row kernels
   bool newton_fast = true;        // KTK_NEWTON_FAST=0: every Newton-RS row through the forward-mode kernel (A/B, cross-check)
-  int fuse_short = 1;             // 1: all IMU-like groups of an evaluation in one launch (k_short_batch); 2: + the landmark tables (measured slower, r2g); 0: off.  KTK_FUSE_SHORT overrides (A/B)
+  // -1 (default): the IMU-like groups of an evaluation go out in ONE launch (k_short_batch) when the problem has no camera rows -- a chain of
+  // one-wave kernels is launch-bound (C2 -2.6 %, C1: 3 kernels) -- and as one launch per group next to camera rows, where the fused launch measured
+  // SLOWER under graph replay (H1 0.2648 -> 0.2571 ms, C4 0.2931 -> 0.2868 ms; profiles/r2x).  0 / 1: force; 2: + the landmark tables
+  // (slower still).  KTK_FUSE_SHORT overrides (A/B).
+  int fuse_short = -1;
   ShortBatch short_batch;
   cudaGraphExec_t graph_exec = nullptr;
   std::vector<uint64_t> graph_key;
@@ -1777,7 +1781,12 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
   // All short kernels in one launch (k_short_batch) when they fit its fixed-size argument block and no per-group event timing is wanted;
   // otherwise group by group as before.
   bool batched = false;
-  if (!p->profiling && p->fuse_short) {
+  int fuse_short = p->fuse_short;
+  if (fuse_short < 0) {
+    fuse_short = 1;
+    for (auto g : p->groups) if (is_camera(g->kind) && g->n > 0) fuse_short = 0;
+  }
+  if (!p->profiling && fuse_short) {
     ShortBatch* b = &p->short_batch;
     b->n_imu = b->n_ref = 0;
     bool fits = true;
@@ -1800,7 +1809,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
           b->which[b->n_imu] = which; b->first[b->n_imu] = cta; b->n_imu += 1;
           cta += (int)((g.n + 31) / 32);
           smem = std::max(smem, (size_t)32 * imu_stride(which) * 8);
-        } else if (pass == 1 && p->fuse_short >= 2 && is_camera(g.kind) && g.n_ref > 0) {
+        } else if (pass == 1 && fuse_short >= 2 && is_camera(g.kind) && g.n_ref > 0) {
           if (b->n_ref == kShortMaxRef) { fits = false; break; }
           RefArgs& ra = b->ref[b->n_ref];
           ra.sp = p->sp; fill_camera_consts(g.cam, ra.cam);
@@ -1826,7 +1835,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       const ktk_group_out& o = outs[gi];
       cudaEvent_t ev0 = nullptr, ev1 = nullptr;
       if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
-      if (!batched || (is_camera(g.kind) && p->fuse_short < 2)) launch_short(g, o, s);
+      if (!batched || (is_camera(g.kind) && fuse_short < 2)) launch_short(g, o, s);
       launch_rows(g, o);
       if (p->profiling) KTK_CUDA(cudaEventRecord(ev1, s));
       { const int sj = launch_sensor_jacobians(p, g, o, flags, d_rho, nullptr); if (sj) return sj; }

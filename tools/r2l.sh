@@ -2,11 +2,5 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 {
-tools/ab_env.sh H1 KTK_LIB=gpurun_variants/libktk_l1win0.so
-tools/ab_env.sh H1 KTK_X=intree
-tools/ab_env.sh H1 KTK_LIB=gpurun_variants/libktk_l1win3.so
-tools/ab_env.sh H1 KTK_LIB=gpurun_variants/libktk_l1win0.so
-tools/ab_env.sh H1 KTK_X=intree
-tools/ab_env.sh H1 KTK_LIB=gpurun_variants/libktk_l1win3.so
-BENCH_EXTRA="--row-order device" tools/ab_env.sh H1 KTK_X=intree ROW=device
-} 2>&1 | tee gpurun_out/r2w_l1win_ab2.log
+for wl in C4 C2 C1 H1; do for f in 0 1 0 1; do tools/ab_env.sh $wl KTK_FUSE_SHORT=$f; done; done
+} 2>&1 | tee gpurun_out/r2x_fuse_rule_ab.log
