@@ -726,16 +726,29 @@ __global__ void __launch_bounds__(kCamThreads, KTK_CAM_MINB) k_static_rs_split(c
       for (int c = 0; c < 24; ++c) row[72 + c] = row[80 + c];
     }
     const size_t dst = (size_t)perm;
-    if (wantJ) *reinterpret_cast<double2*>(a.J + dst * grow + (grow - 2)) = make_double2(jrho[0], jrho[1]);
+    if (wantJ) {
+      if (local) *reinterpret_cast<double2*>(a.J + dst * grow + (grow - 2)) = make_double2(jrho[0], jrho[1]);
+      else { row[112] = jrho[0]; row[113] = jrho[1]; }      // ambient rows leave whole (below)
+    }
     if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
 #pragma unroll
     for (int k = 0; k < 4; ++k) if (a.idx[k]) a.idx[k][dst] = idx[k];
   }
-  __syncwarp();
-  if (wantJ) {
-    if (local) warp_scatter_rows<96, kCamSplitStride, 98>(wbase, a.J, perm, lane);
-    else warp_scatter_rows<kCamStage, kCamSplitStride, kCamRow>(wbase, a.J, perm, lane);
+  if (!wantJ) return;
+  if (local) {
+    __syncwarp();
+    warp_scatter_rows<96, kCamSplitStride, 98>(wbase, a.J, perm, lane);
+    return;
   }
+  // ambient rows: the staged 114-double row is the packed row; it leaves with one TMA bulk store like the SE3 kernel's (one per tile in device order)
+  fence_async_smem();
+  __syncwarp();
+  if (a.flags & KTK_EVAL_DEVICE_ORDER) {
+    if (lane == 0) bulk_store(a.J + (size_t)tile * 32 * kCamRow, wbase, (unsigned)(min(32, a.n - tile * 32) * kCamRow * 8));
+  } else if (perm >= 0) {
+    bulk_store(a.J + (size_t)perm * kCamRow, row, (unsigned)(kCamRow * 8));
+  }
+  bulk_store_wait_read();
 }
 
 __global__ void k_traj_eval_se3(SplineConst sp, const double* __restrict__ knots, const double* __restrict__ pairs, int n, const double* __restrict__ t,

@@ -1,6 +1,12 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 {
-for wl in C4 C2 C1 H1; do for f in 0 1 0 1; do tools/ab_env.sh $wl KTK_FUSE_SHORT=$f; done; done
-} 2>&1 | tee gpurun_out/r2x_fuse_rule_ab.log
+tools/ab_env.sh C5 KTK_LIB=gpurun_variants/libktk_base.so
+tools/ab_env.sh C5 KTK_X=intree
+tools/ab_env.sh C5 KTK_LIB=gpurun_variants/libktk_base.so
+tools/ab_env.sh C5 KTK_X=intree
+BENCH_EXTRA="--row-order device" tools/ab_env.sh C5 KTK_LIB=gpurun_variants/libktk_base.so ROW=device
+BENCH_EXTRA="--row-order device" tools/ab_env.sh C5 KTK_X=intree ROW=device
+} 2>&1 | tee gpurun_out/r2y_split_tma_ab.log
