@@ -244,11 +244,24 @@ __device__ __forceinline__ void imu_tile(const ImuArgs& a, int tile, double* wba
     }
     if (a.i0) a.i0[dst] = i0;
   }
+#ifndef KTK_IMU_TMA
+#define KTK_IMU_TMA 1
+#endif
+#if KTK_IMU_TMA      // every finished row leaves with one TMA bulk store (672 / 576 / 224 / 192 B), like the camera rows
+  fence_async_smem();
+  __syncwarp();
+  if (wantJ && cur.perm >= 0) {
+    const int len = local ? LROW : ROW;
+    bulk_store(a.J + (size_t)cur.perm * len, row, (unsigned)(len * 8));
+    bulk_store_wait_read();
+  }
+#else
   __syncwarp();
   if (wantJ) {
     if (local) warp_scatter_rows<LROW, STRIDE, LROW>(wbase, a.J, cur.perm, lane);
     else warp_scatter_rows<ROW, STRIDE, ROW>(wbase, a.J, cur.perm, lane);
   }
+#endif
 }
 template <int WHICH>
 __global__ void __launch_bounds__(kThreads, WHICH == 0 ? KTK_GYRO_MINB : KTK_ACCEL_MINB) k_imu(const ImuArgs a) {
