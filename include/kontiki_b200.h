@@ -167,7 +167,8 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
 /* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static
  * measurement.  The row time is found by the reference's 5-step Newton iteration (:62-117) and the Jacobian is the
  * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  UniformSE3SplineTrajectory only; the camera's
- * relative pose may be unlocked (KTK_EVAL_SENSOR_JACOBIANS), its time offset not (KTK_EUNSUPPORTED); KTK_EVAL_LOCAL is not built for it. */
+ * relative pose may be unlocked (KTK_EVAL_SENSOR_JACOBIANS), its time offset not (KTK_EUNSUPPORTED).  KTK_EVAL_LOCAL rows:
+ * [ref 4 x (2x6) | obs W x (2x6) | rho 2] (ktk_group_row_size_local). */
 int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* LiftingRsCameraMeasurement::AddToEstimator (measurements/lifting_rscamera_measurement.h:151-229), same arrays as the static measurement.
@@ -176,8 +177,8 @@ int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
  * ktk_set_group_vt feeds the current row times (caller order) like ktk_set_group_sensor feeds sensor parameters.  Packed row
  * [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles (ktk_group_row_size), W and i0_b as for the Newton
  * rows (whole observation span; the four active knot blocks sit at their place inside it, the others are zero); r is 3 per row.
- * UniformSE3SplineTrajectory only; relative pose of the camera may be unlocked (Js: 24 per row), its time offset not; no KTK_EVAL_LOCAL,
- * no matrix-free products (KTK_EUNSUPPORTED). */
+ * UniformSE3SplineTrajectory only; relative pose of the camera may be unlocked (Js: 24 per row), its time offset not; KTK_EVAL_LOCAL rows
+ * [ref 4 x (3x6) | obs W x (3x6) | vt 3 | rho 3]; no matrix-free products (KTK_EUNSUPPORTED). */
 int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                        const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 int ktk_set_group_vt(ktk_problem* p, int32_t group, const double* vt);

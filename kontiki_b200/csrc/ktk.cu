@@ -653,6 +653,8 @@ __global__ void __launch_bounds__(kThreads) k_imu_split(const ImuSplitArgs a) {
     if (a.i0_r3) a.i0_r3[dst] = ia;
     if (a.i0_so3) a.i0_so3[dst] = ib;
   }
+  // (cooperative 16-byte scatter: the split rows are short -- 384 / 672 B -- and one TMA bulk store per row measured slower here:
+  //  C5 gyroscope 0.0517 -> 0.0531 ms, accelerometer 0.0699 -> 0.0756 ms, profiles/r2y)
   __syncwarp();
   if (wantJ) {
     if (local && WHICH != 2) warp_scatter_rows<ROW - 4 * NR, STRIDE, ROW - 4 * NR>(wbase, a.J, perm, lane);      // the four SO3 blocks shrink from NR x 4 to NR x 3
@@ -962,6 +964,28 @@ __global__ void k_static_rs_sensor(const CamSensorArgs a) {
 // (newton_math.cuh); 29 + 7 W directions per row, no staging -- thread (row, dir) owns two doubles of the packed row.
 // The landmark side comes from the same k_landmark_ref records as the static measurement.
 // =====================================================================================================================
+// KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs measurements: the span rows are evaluated in ambient coordinates into a scratch buffer and every knot
+// block is then taken through the knot's LocalParameterization (localize_se3_blocks: J_local = J_ambient dPlus/ddelta, uniform_se3_spline_trajectory.h:25-48)
+// by one thread per (row, block); local row = [ref 4 x (nres x 6) | obs W x (nres x 6) | tail].  Cold path.
+__global__ void k_span_localize(const double* __restrict__ Jamb, const int* __restrict__ i0r, const int* __restrict__ i0o, const double* __restrict__ knots,
+                                int n_knots, int n, int W, int nres, int tail, double* __restrict__ Jloc) {
+  const int nb = 4 + W + 1;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / nb), b = (int)(tid % nb);
+  if (i >= n) return;
+  const size_t la = (size_t)(4 + W) * nres * 7 + tail, ll = (size_t)(4 + W) * nres * 6 + tail;
+  const double* src = Jamb + (size_t)i * la;
+  double* dst = Jloc + (size_t)i * ll;
+  if (b == 4 + W) { for (int c = 0; c < tail; ++c) dst[(size_t)(4 + W) * nres * 6 + c] = src[(size_t)(4 + W) * nres * 7 + c]; return; }
+  const int first = b < 4 ? i0r[i] : i0o[i];
+  int k = first < 0 ? 0 : first + (b < 4 ? b : b - 4);      // blocks past the end of the spline are zero in the ambient row: any knot does
+  if (k >= n_knots) k = n_knots - 1;
+  double blk[21];
+  for (int c = 0; c < nres * 7; ++c) blk[c] = src[(size_t)b * nres * 7 + c];
+  if (nres == 3) localize_se3_blocks<3>(blk, 1, knots + (size_t)k * kKnotStride); else localize_se3_blocks<2>(blk, 1, knots + (size_t)k * kKnotStride);
+  for (int c = 0; c < nres * 6; ++c) dst[(size_t)b * nres * 6 + c] = blk[c];
+}
+
 // Sensor-block columns of NewtonRs / LiftingRs rows (newton_math.cuh "sensor-block columns"): one thread per (row, column 0..6) in forward mode.
 // Js per row: [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero)], nres = 2 / 3.  Cold path.
 struct SpanSensorArgs {
@@ -1189,6 +1213,7 @@ struct Group {
   double bias[3] = {0.0, 0.0, 0.0};
   std::vector<double> vt; DevBuf<double> d_vt; bool vt_dirty = true;      // LiftingRs: current frame-normalised row times, caller order (ktk_set_group_vt)
   DevBuf<double> o_Js;
+  DevBuf<double> o_amb; DevBuf<int> o_amb_i0, o_amb_i0b;      // span cameras, KTK_EVAL_LOCAL: ambient rows / window indices before k_span_localize
   DevBuf<int> d_slow;             // Newton-RS rows that need the forward-mode kernel (more than one Newton evaluation): [count | row indices]
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
@@ -1384,8 +1409,8 @@ int newton_window(const ktk_problem* p, const Group& g) {
 }
 int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
-  if (g.kind == KTK_NEWTON_RS) return 58 + 14 * newton_window(p, g);
-  if (g.kind == KTK_LIFTING_RS) return 90 + 21 * newton_window(p, g);
+  if (g.kind == KTK_NEWTON_RS) return local ? 2 + 12 * (4 + newton_window(p, g)) : 58 + 14 * newton_window(p, g);
+  if (g.kind == KTK_LIFTING_RS) return local ? 6 + 18 * (4 + newton_window(p, g)) : 90 + 21 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
   if (p->traj == 1 && g.kind == KTK_POSITION) return kPosSplitRow;
   if (g.kind == KTK_ORIENTATION) return p->traj == 1 ? (local ? 12 : kOriSplitRow) : (local ? 24 : 28);
@@ -1692,7 +1717,10 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       g->vt_dirty = false;
     }
     if (g->kind == KTK_NEWTON_RS && g->n > 0 && (st = g->d_slow.resize((size_t)g->n + 1))) return st;
-    if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs camera measurements are not built");
+    if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL) && (flags & KTK_EVAL_JACOBIANS) && g->n > 0) {      // scratch of k_span_localize (outside any capture)
+      if ((st = g->o_amb.resize((size_t)g->n * row_doubles(p, *g)))) return st;
+      if ((st = g->o_amb_i0.resize((size_t)g->n)) || (st = g->o_amb_i0b.resize((size_t)g->n))) return st;
+    }
     if (is_span_camera(g->kind) && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
@@ -1788,6 +1816,12 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
       na.sp = a.sp; na.cam = a.cam; na.knots = a.knots; na.pairs = a.pairs; na.recs = a.recs;
       na.obs_uv = a.obs_uv; na.obs_t0 = a.obs_t0; na.ref_t0 = a.ref_t0; na.ref_idx = a.ref_idx; na.w = a.w; na.huber = a.huber; na.perm = a.perm;
       na.n = a.n; na.W = newton_window(p, g); na.flags = flags; na.r = a.r; na.J = a.J; na.i0r = a.i0r; na.i0o = a.i0o; na.err = a.err;
+      const bool localize = (flags & KTK_EVAL_LOCAL) && a.J && (flags & KTK_EVAL_JACOBIANS);
+      if (localize) {      // ambient rows and the window indices into scratch; k_span_localize below writes the caller's local rows
+        na.flags = flags & ~(uint32_t)KTK_EVAL_LOCAL; na.J = g.o_amb.p;
+        if (!na.i0r) na.i0r = g.o_amb_i0.p;
+        if (!na.i0o) na.i0o = g.o_amb_i0b.p;
+      }
       if (g.kind == KTK_LIFTING_RS) {
         k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
       } else {
@@ -1798,6 +1832,12 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
           p->launches += 1;
         }
         k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr);
+      }
+      if (localize) {
+        const int nres = g.kind == KTK_LIFTING_RS ? 3 : 2, tail = g.kind == KTK_LIFTING_RS ? 6 : 2;
+        const long long threads = (long long)g.n * (4 + na.W + 1);
+        k_span_localize<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(g.o_amb.p, na.i0r, na.i0o, p->d_knots8.p, p->sp.n_knots, (int)g.n, na.W, nres, tail, a.J);
+        p->launches += 1;
       }
     }
     else if (!(flags & KTK_EVAL_LOCAL)) k_static_rs<<<blocks, kCamThreads, kCamThreads * kCamDevStride * 8, s>>>(a);

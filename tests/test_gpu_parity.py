@@ -504,6 +504,30 @@ def _camera_group(cfg, method, atan, p=None):
     return p, g, ocam
 
 
+def _check_span_rows_local(p, g, knots, rho, flags, nres):
+    """KTK_EVAL_LOCAL rows of a NewtonRs / LiftingRs group: [ref 4 x (nres x 6) | obs W x (nres x 6) | tail] = the ambient row's knot blocks times
+    dPlus/ddelta of their knots (k_span_localize), in caller and in device order."""
+    from kontiki_b200.estimator import _se3_plus_jacobian
+    amb = p.evaluate(knots, rho, flags)[g]
+    loc = p.evaluate(knots, rho, flags | _lib.EVAL_LOCAL)[g]
+    n, la = amb["J"].shape
+    tail = 2 if nres == 2 else 6
+    W = (la - tail) // (7 * nres) - 4
+    assert loc["J"].shape == (n, 6 * nres * (4 + W) + tail) and np.array_equal(loc["r"], amb["r"]) and np.array_equal(loc["i0_b"], amb["i0_b"])
+    P = _se3_plus_jacobian(knots)
+    ok = amb["i0"] >= 0
+    assert ok.sum() > 0.9 * n
+    kr = amb["i0"][ok][:, None] + np.arange(4)
+    ko = np.minimum(amb["i0_b"][ok][:, None] + np.arange(W), len(knots) - 1)
+    ref_r = np.einsum("nkra,nkad->nkrd", amb["J"][ok, :28 * nres].reshape(-1, 4, nres, 7), P[kr])
+    ref_o = np.einsum("nkra,nkad->nkrd", amb["J"][ok, 28 * nres:la - tail].reshape(-1, W, nres, 7), P[ko])
+    assert parity.rel_err(loc["J"][ok, :24 * nres].reshape(-1, 4, nres, 6), ref_r) < 1e-12
+    assert parity.rel_err(loc["J"][ok, 24 * nres:-tail].reshape(-1, W, nres, 6), ref_o) < 1e-12
+    assert np.array_equal(loc["J"][:, -tail:], amb["J"][:, -tail:])
+    dev = p.evaluate(knots, rho, flags | _lib.EVAL_LOCAL | _lib.EVAL_DEVICE_ORDER)[g]
+    assert np.array_equal(dev["J"], loc["J"][p.get_row_order(g)], equal_nan=True)
+
+
 @pytest.mark.parametrize("method,atan,robust", [("static", True, False), ("static", True, True), ("newton", False, False), ("newton", True, True)])
 def test_newton_and_atan_rows_match_oracle(method, atan, robust):
     cfg = syn.make_config("C3", scale=0.004)                      # 2000 rows on 5k knots (dt 0.02: Newton spans cover 5-6 knots)
@@ -565,9 +589,8 @@ def test_newton_rows_without_noise_equal_static_rows_and_unsupported_modes():
     for i in range(0, len(k), 5):
         a, b = n["J"][i, 56 + 14 * k[i]:56 + 14 * (k[i] + 4)], s["J"][i, 56:112]
         assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()
-    with pytest.raises(NotImplementedError):
-        p.evaluate(cfg["knots"], c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_LOCAL)
-    with pytest.raises(NotImplementedError):
+    _check_span_rows_local(p, gn, cfg["knots"], c["rho"], _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS, 2)
+    with pytest.raises(NotImplementedError):      # the time offset of these measurements stays locked (the reference moves both spans with it)
         p.add_newton_rs(_lib.make_camera(c["rows"], c["cols"], c["readout"], c["K"], time_offset_locked=False), c["obs_uv"], c["obs_t0"], c["ref_uv"],
                         c["ref_t0"], c["lm_idx"])
 
@@ -726,8 +749,7 @@ def test_lifting_rows_match_oracle(atan, robust):
         dev = p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_DEVICE_ORDER)[g]
         order = p.get_row_order(g)
         assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order])
-    with pytest.raises(NotImplementedError):
-        p.evaluate(cfg["knots"], c["rho"], flags | _lib.EVAL_LOCAL)
+    _check_span_rows_local(p, g, cfg["knots"], c["rho"], flags, 3)
 
 
 
