@@ -166,7 +166,7 @@ int ktk_add_static_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
                       const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
 /* NewtonRsCameraMeasurement::AddToEstimator (measurements/newton_rscamera_measurement.h:201-262), same arrays as the static
  * measurement.  The row time is found by the reference's 5-step Newton iteration (:62-117) and the Jacobian is the
- * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  UniformSE3SplineTrajectory only; the camera's
+ * forward-mode derivative THROUGH that iteration, exactly as ceres::Jet produces it.  On a UniformSE3SplineTrajectory the camera's
  * relative pose may be unlocked (KTK_EVAL_SENSOR_JACOBIANS), its time offset not (KTK_EUNSUPPORTED).  KTK_EVAL_LOCAL rows:
  * [ref 4 x (2x6) | obs W x (2x6) | rho 2] (ktk_group_row_size_local). */
 int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
@@ -177,7 +177,7 @@ int ktk_add_newton_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const do
  * ktk_set_group_vt feeds the current row times (caller order) like ktk_set_group_sensor feeds sensor parameters.  Packed row
  * [ref 4 x (3x7) | obs W x (3x7) | d r/d vt (3) | d r/d rho (3)] = 90 + 21 W doubles (ktk_group_row_size), W and i0_b as for the Newton
  * rows (whole observation span; the four active knot blocks sit at their place inside it, the others are zero); r is 3 per row.
- * UniformSE3SplineTrajectory only; relative pose of the camera may be unlocked (Js: 24 per row), its time offset not; KTK_EVAL_LOCAL rows
+ * On a UniformSE3SplineTrajectory the relative pose of the camera may be unlocked (Js: 24 per row), its time offset not; KTK_EVAL_LOCAL rows
  * [ref 4 x (3x6) | obs W x (3x6) | vt 3 | rho 3]; no matrix-free products (KTK_EUNSUPPORTED). */
 int ktk_add_lifting_rs(ktk_problem* p, const ktk_camera* cam, int64_t n, const double* obs_uv, const double* obs_t0,
                        const double* ref_uv, const double* ref_t0, const int32_t* lm_idx, const double* weight, const double* huber_c);
@@ -194,6 +194,13 @@ int64_t ktk_group_size(const ktk_problem* p, int32_t group);
 int32_t ktk_group_kind(const ktk_problem* p, int32_t group);
 int32_t ktk_group_row_size(const ktk_problem* p, int32_t group);   /* doubles per packed Jacobian row (84 / 114 / 48; Newton-RS 58 + 14 W) */
 int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t group);   /* ... with KTK_EVAL_LOCAL */
+/* NewtonRs / LiftingRs groups: knots of the widest observation span on the current spline(s) -- W (SE3: *w_a, *w_b = 0) or Wa / Wb of the
+ * R3 / SO3 splines of a split trajectory, whose rows are packed
+ *   [ref R3 4 x (nres x 3) | ref SO3 4 x (nres x 4) | obs R3 Wa x (nres x 3) | obs SO3 Wb x (nres x 4) | (d r/d vt nres) | d r/d rho nres]
+ * with i0 / i0_b = first knot of the reference window / of the observation span on the R3 spline and i0_c / i0_d the same on the SO3 spline
+ * (newton_rscamera_measurement.h:201-262 and lifting_rscamera_measurement.h:151-229 instantiated on SplitTrajectory; forward mode,
+ * csrc/newton_math.cuh).  On a split trajectory these rows take locked camera parameters and ambient coordinates only. */
+int ktk_group_span_windows(const ktk_problem* p, int32_t group, int32_t* w_a, int32_t* w_b);
 int64_t ktk_num_knot_doubles(const ktk_problem* p);                /* length of the `knots` argument of ktk_evaluate */
 
 /* One batched evaluation at the parameter point (knots[n_knots*7], rho[n_rho]) with HOST buffers: uploads the point,

@@ -37,7 +37,7 @@ EXPORTS = ["ktk_last_error", "ktk_problem_create", "ktk_problem_destroy", "ktk_s
            "ktk_add_accelerometer", "ktk_add_static_rs", "ktk_num_groups", "ktk_group_size", "ktk_group_kind", "ktk_evaluate",
            "ktk_evaluate_device", "ktk_synchronize", "ktk_launch_count", "ktk_host_alloc", "ktk_host_free", "ktk_get_structure",
            "ktk_expand_static_rs", "ktk_set_profiling", "ktk_read_profile", "ktk_set_split_spline", "ktk_group_row_size", "ktk_num_knot_doubles",
-           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation", "ktk_add_lifting_rs", "ktk_set_group_vt",
+           "ktk_get_structure_so3", "ktk_traj_evaluate", "ktk_num_parameters", "ktk_j_apply", "ktk_jt_apply", "ktk_jtj_diagonal", "ktk_jtj_diagonal_local", "ktk_set_graphs", "ktk_set_group_sensor", "ktk_set_group_bias", "ktk_group_row_size_local", "ktk_se3_evaluate_matrices", "ktk_get_row_order", "ktk_add_newton_rs", "ktk_add_position", "ktk_add_orientation", "ktk_add_lifting_rs", "ktk_set_group_vt", "ktk_group_span_windows",
            "ktk_gn_prepare", "ktk_gn_cost", "ktk_gn_linearize_local", "ktk_gn_gradient_local", "ktk_gn_linearize_rhs", "ktk_gn_pcg_begin", "ktk_gn_product", "ktk_gn_pcg_update",
            "ktk_gn_pcg_status", "ktk_gn_finish_local", "ktk_gn_finish_mask", "ktk_gn_model_local", "ktk_gn_retract", "ktk_gn_buffer"]
 
@@ -89,6 +89,7 @@ def lib():
         L.ktk_set_split_spline.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_double, C.c_int32]
         L.ktk_group_row_size.argtypes = [C.c_void_p, C.c_int32]
         L.ktk_group_row_size_local.argtypes = [C.c_void_p, C.c_int32]
+        L.ktk_group_span_windows.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.ktk_num_knot_doubles.argtypes = [C.c_void_p]
         L.ktk_num_knot_doubles.restype = C.c_int64
         L.ktk_get_structure_so3.argtypes = L.ktk_get_structure.argtypes
@@ -201,6 +202,12 @@ class Problem:
 
     def group_row_size(self, g):
         return lib().ktk_group_row_size(self._h, g)
+
+    def group_span_windows(self, g):
+        """NewtonRs / LiftingRs groups: (W, 0) on SE3, (Wa, Wb) = widest observation span on the R3 / SO3 spline of a split trajectory."""
+        wa, wb = C.c_int32(0), C.c_int32(0)
+        check(lib().ktk_group_span_windows(self._h, int(g), C.byref(wa), C.byref(wb)))
+        return wa.value, wb.value
 
     def _add_imu(self, fn, sensor, t, y, weight):
         t, y = _f64(t), _f64(y).reshape(-1, 3)

@@ -986,6 +986,51 @@ __global__ void k_span_localize(const double* __restrict__ Jamb, const int* __re
   for (int c = 0; c < nres * 6; ++c) dst[(size_t)b * nres * 6 + c] = blk[c];
 }
 
+// NewtonRs / LiftingRs rows on a SPLIT trajectory (newton_math.cuh "rows on a SPLIT trajectory"): forward mode, one thread per (row, direction);
+// every direction writes its own column of the packed row, direction 0 the residual and the four window indices.  Cold path.
+struct SpanSplitArgs {
+  SplitConst sp; CameraConst cam; const double* vecs; const double* quats; const double* pairs; const double* recs;
+  const double* obs_uv; const double* obs_t0; const double* ref_t0; const int* ref_idx; const double* w; const double* huber; const double* vt;
+  const int* perm; int n, Wa, Wb, lifting; uint32_t flags;
+  double* r; double* J; int* idx[4]; int* err;
+};
+__global__ void __launch_bounds__(128) k_span_rs_split(const SpanSplitArgs a) {
+  const bool lifting = a.lifting != 0;
+  const int ndir = span_split_ndir(lifting, a.Wa, a.Wb), len = span_split_row_len(lifting, a.Wa, a.Wb), nres = lifting ? 3 : 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / ndir), dir = (int)(tid % ndir);
+  if (i >= a.n) return;
+  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
+  if (!wantJ && dir != 0) return;
+  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+  const double obs_t0 = a.obs_t0[i];
+  const int ridx = a.ref_idx[i];
+  const int ka = span_window_base(a.sp.t0_r3, a.sp.dt_r3, obs_t0), kb = span_window_base(a.sp.t0_so3, a.sp.dt_so3, obs_t0);
+  int st = kStatusRange, ira = -1, irb = -1;
+  double r[3] = {nan(""), nan(""), nan("")};
+  double* Jrow = wantJ ? a.J + dst * len : nullptr;
+  if (ridx >= 0) {
+    const double* rec = a.recs + (size_t)ridx * kRefSplitStride;
+    ira = (int)rec[7]; irb = (int)rec[8];
+    if (ira >= 0)
+      st = span_split_column(lifting, a.sp, a.cam, a.vecs, a.quats, a.pairs, rec, ouv, obs_t0, a.ref_t0[i], lifting ? a.vt[i] : 0.0, ka, a.Wa, kb, a.Wb,
+                             a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, dir, r, Jrow);
+  }
+  if (st != 0) {
+    atomicMin(a.err, st);
+    r[0] = r[1] = r[2] = nan(""); ira = irb = -1;
+    if (Jrow) { int stride; const int off = span_split_dir_offset(lifting, a.Wa, a.Wb, dir, stride); for (int rr = 0; rr < nres; ++rr) Jrow[off + rr * stride] = nan(""); }
+  }
+  if (dir == 0) {
+    if (a.r) for (int rr = 0; rr < nres; ++rr) a.r[nres * dst + rr] = r[rr];
+    if (a.idx[0]) a.idx[0][dst] = ira;
+    if (a.idx[1]) a.idx[1][dst] = st == 0 ? ka : -1;
+    if (a.idx[2]) a.idx[2][dst] = irb;
+    if (a.idx[3]) a.idx[3][dst] = st == 0 ? kb : -1;
+  }
+}
+
 // Sensor-block columns of NewtonRs / LiftingRs rows (newton_math.cuh "sensor-block columns"): one thread per (row, column 0..6) in forward mode.
 // Js per row: [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero)], nres = 2 / 3.  Cold path.
 struct SpanSensorArgs {
@@ -1203,6 +1248,7 @@ struct Group {
   int ny = 3;                     // doubles of y per row: 3 (gyroscope / accelerometer / position), 4 (orientation: q)
   ktk_sensor sensor{}; ktk_camera cam{};
   int newton_W = 0;               // Newton-RS groups: knots of the widest observation span (0 = not computed for the current spline)
+  int span_W[2] = {0, 0};         // ... on a split trajectory: R3 / SO3 spline
   // caller-order host copies (structure queries) and sorted device copies
   std::vector<double> t, y, w, obs_uv, obs_t0, ref_uv, ref_t0, huber;
   std::vector<int> lm, perm; int lm_max = -1, lm_min = 0;
@@ -1399,6 +1445,16 @@ int upload_group(ktk_problem* p, Group& g) {
 
 // doubles per packed Jacobian row / per residual of a group (include/kontiki_b200.h "Layouts")
 // Newton-RS groups: knots of the widest observation span {t0_obs - 1e-3, t0_obs + readout + 1e-3} on the current spline
+// ... on a split trajectory: the widest span of the R3 (which = 0) / SO3 (1) spline
+int span_window_split(const ktk_problem* p, const Group& g, int which) {
+  int& cached = const_cast<Group&>(g).span_W[which];
+  if (cached > 0) return cached;
+  const double t0 = which == 0 ? p->spl.t0_r3 : p->spl.t0_so3, dt = which == 0 ? p->spl.dt_r3 : p->spl.dt_so3;
+  int W = 4;
+  for (int64_t i = 0; i < g.n; ++i) W = std::max(W, span_window_size(t0, dt, g.cam.readout, g.obs_t0[i]));
+  cached = W;
+  return W;
+}
 int newton_window(const ktk_problem* p, const Group& g) {
   if (g.newton_W > 0) return g.newton_W;
   CameraConst cc; fill_camera_consts(g.cam, cc);
@@ -1409,6 +1465,7 @@ int newton_window(const ktk_problem* p, const Group& g) {
 }
 int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
+  if (is_span_camera(g.kind) && p->traj == 1) return span_split_row_len(g.kind == KTK_LIFTING_RS, span_window_split(p, g, 0), span_window_split(p, g, 1));
   if (g.kind == KTK_NEWTON_RS) return local ? 2 + 12 * (4 + newton_window(p, g)) : 58 + 14 * newton_window(p, g);
   if (g.kind == KTK_LIFTING_RS) return local ? 6 + 18 * (4 + newton_window(p, g)) : 90 + 21 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
@@ -1499,7 +1556,7 @@ int ktk_set_se3_spline(ktk_problem* p, double dt, double t0, int32_t n_knots, in
   if (n_knots < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->sp.t0 = t0; p->sp.dt = dt; p->sp.n_knots = n_knots; p->sp.compat_zero_dB = compat;
   p->traj = 0; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->vt_dirty = true; }   // the sort key depends on (t0, dt)
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->span_W[0] = g->span_W[1] = 0; g->vt_dirty = true; }   // the sort key depends on (t0, dt)
   return KTK_OK;
 }
 
@@ -1509,7 +1566,7 @@ int ktk_set_split_spline(ktk_problem* p, double dt_r3, double t0_r3, int32_t n_r
   if (n_r3 < 4 || n_so3 < 4) return fail(KTK_ERANGE, "Spline had too few control points");   // spline_base.h:57-61
   p->spl = SplitConst{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
   p->traj = 1; p->have_spline = true; drop_graph(p);
-  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->vt_dirty = true; }
+  for (auto g : p->groups) { g->uploaded = false; g->newton_W = 0; g->span_W[0] = g->span_W[1] = 0; g->vt_dirty = true; }
   return KTK_OK;
 }
 
@@ -1595,6 +1652,15 @@ int64_t ktk_group_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 &&
 int32_t ktk_group_kind(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? p->groups[g]->kind : -1; }
 int64_t ktk_launch_count(const ktk_problem* p) { return p ? p->launches : 0; }
 int32_t ktk_group_row_size(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? row_doubles(p, *p->groups[g]) : -1; }
+int ktk_group_span_windows(const ktk_problem* p, int32_t g, int32_t* w_a, int32_t* w_b) {
+  if (!p || g < 0 || g >= (int)p->groups.size() || !w_a || !w_b) return fail(KTK_EINVAL, "bad argument");
+  const Group& grp = *p->groups[g];
+  if (!is_span_camera(grp.kind)) return fail(KTK_EINVAL, "not a NewtonRs / LiftingRs group");
+  if (!p->have_spline) return fail(KTK_EINVAL, "a trajectory must be set first");
+  if (p->traj == 1) { *w_a = span_window_split(p, grp, 0); *w_b = span_window_split(p, grp, 1); }
+  else { *w_a = newton_window(p, grp); *w_b = 0; }
+  return KTK_OK;
+}
 int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t g) { return (p && g >= 0 && g < (int)p->groups.size()) ? row_doubles(p, *p->groups[g], KTK_EVAL_LOCAL) : -1; }
 int64_t ktk_num_knot_doubles(const ktk_problem* p) {
   if (!p || !p->have_spline) return 0;
@@ -1662,11 +1728,11 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
     Group& g = *p->groups[gi];
     if (g.n == 0) continue;
     const ktk_group_out& o = outs[gi];
-    const int tpb = g.kind == KTK_STATIC_RS ? kCamThreads : kThreads;
+    const int tpb = is_camera(g.kind) ? kCamThreads : kThreads;
     const int blocks = (int)((g.n + tpb - 1) / tpb);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profiling) { KTK_CUDA(cudaEventCreate(&ev0)); KTK_CUDA(cudaEventCreate(&ev1)); g.prof.push_back({ev0, ev1}); KTK_CUDA(cudaEventRecord(ev0, s)); }
-    if (g.kind == KTK_STATIC_RS) {
+    if (is_camera(g.kind)) {
       RefSplitArgs ra;
       ra.sp = sp; fill_camera_consts(g.cam, ra.cam);
       ra.vecs = p->d_vecs4.p; ra.quats = d_quats; ra.pairs = p->d_so3pairs.p; ra.rho = d_rho;
@@ -1679,7 +1745,16 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
       a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_t0 = g.d_ref_t0.p; a.ref_idx = g.d_ref_idx.p; a.w = g.d_w.p; a.huber = g.d_huber.p;
       a.perm = g.d_perm.p; a.n = (int)g.n; a.flags = flags;
       a.r = o.r; a.J = o.J; a.idx[0] = o.i0; a.idx[1] = o.i0_b; a.idx[2] = o.i0_c; a.idx[3] = o.i0_d; a.err = p->d_err.p;
-      k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamSplitWarpSmem * 8, s>>>(a);
+      if (is_span_camera(g.kind)) {
+        SpanSplitArgs sa;
+        sa.sp = sp; sa.cam = ra.cam; sa.vecs = a.vecs; sa.quats = a.quats; sa.pairs = a.pairs; sa.recs = a.recs;
+        sa.obs_uv = a.obs_uv; sa.obs_t0 = a.obs_t0; sa.ref_t0 = a.ref_t0; sa.ref_idx = a.ref_idx; sa.w = a.w; sa.huber = a.huber; sa.vt = g.d_vt.p;
+        sa.perm = a.perm; sa.n = a.n; sa.Wa = span_window_split(p, g, 0); sa.Wb = span_window_split(p, g, 1); sa.lifting = g.kind == KTK_LIFTING_RS;
+        sa.flags = flags; sa.r = o.r; sa.J = o.J; for (int c = 0; c < 4; ++c) sa.idx[c] = a.idx[c]; sa.err = p->d_err.p;
+        const long long threads = (long long)g.n * span_split_ndir(sa.lifting != 0, sa.Wa, sa.Wb);
+        k_span_rs_split<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(sa);
+      }
+      else k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamSplitWarpSmem * 8, s>>>(a);
     } else {
       ImuSplitArgs a;
       a.sp = sp; fill_sensor_consts(g.sensor, a.imu);
@@ -1721,7 +1796,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       if ((st = g->o_amb.resize((size_t)g->n * row_doubles(p, *g)))) return st;
       if ((st = g->o_amb_i0.resize((size_t)g->n)) || (st = g->o_amb_i0b.resize((size_t)g->n))) return st;
     }
-    if (is_span_camera(g->kind) && p->traj == 1) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
+    if (is_span_camera(g->kind) && p->traj == 1 && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");
@@ -2059,6 +2134,7 @@ static int apply_products(ktk_problem* p, int mode, uint32_t flags, const ktk_gr
     for (int w = 0; w < a.w.nwin; ++w) if (!a.idx[a.w.slot[w]]) return fail(KTK_EINVAL, "the group's index arrays are missing");
     if (mode == 3 && g.kind == KTK_NEWTON_RS) return fail(KTK_EUNSUPPORTED, "ktk_jtj_diagonal_local over NewtonRsCameraMeasurement rows is not built");
     if (g.kind == KTK_LIFTING_RS) return fail(KTK_EUNSUPPORTED, "the matrix-free products do not cover LiftingRs rows (their row-time blocks are per measurement)");
+    if (is_span_camera(g.kind) && p->traj == 1) return fail(KTK_EUNSUPPORTED, "the matrix-free products do not cover NewtonRs rows on a split trajectory");
     if (is_camera(g.kind)) {        // landmark index of every row, in the order the rows were written
       if (flags & KTK_EVAL_DEVICE_ORDER) {
         if (g.perm.size() != (size_t)g.n) return fail(KTK_EINVAL, "device-order rows need an evaluation first");

@@ -665,4 +665,189 @@ KB_HD int lifting_rs_row_packed(const SplineConst& sp, const CameraConst& cam, c
   return 0;
 }
 
+// =====================================================================================================================================
+// NewtonRs / LiftingRs rows on a SPLIT trajectory (UniformR3 + UniformSO3 splines; split_trajectory.h:41-58): forward mode, one direction at a
+// time, like the SE3 rows above.  The R3 spline is linear in its knots (uniform_r3_spline_trajectory.h:34-101); the SO3 spline is evaluated
+// exactly as the reference does (uniform_so3_spline_trajectory.h:46-125: q = q0 prod expq(B_j omega_j), dq by the product rule, angular
+// velocity 2 (dq conj(q)).vec) on the hoisted half-angle vectors omega_j = logq(conj(q_{j-1}) q_j) of the SO3 prepass, whose 3 x 8 ambient
+// Jacobians seed the knot directions.  Packed rows (nres = 2 Newton, 3 Lifting):
+//   [ref R3 4 x (nres x 3) | ref SO3 4 x (nres x 4) | obs R3 Wa x (nres x 3) | obs SO3 Wb x (nres x 4) | (vt nres) | rho nres]
+// Directions, in that order: 12 + 16 + 3 Wa + 4 Wb (+ vt) + rho.
+// =====================================================================================================================================
+template <class T> KB_HD TQ<T> expq_t(const TV3<T>& v) {      // quaternion_math.h:61-86 with a zero scalar part (exp(0) = 1)
+  const T v2 = tdot(v, v);
+  T ka(1.0), kv(1.0);
+  if (value(v2) > kEpsLogq) { const T vn = t_sqrt(v2); ka = t_cos(vn); kv = t_sin(vn) / vn; }
+  TQ<T> q; q.x = kv * v.x; q.y = kv * v.y; q.z = kv * v.z; q.w = ka;
+  return q;
+}
+struct SplitSeed { int spline, knot, comp; };      // spline: 0 none, 1 R3, 2 SO3
+// position / velocity of the R3 spline and orientation / world angular velocity of the SO3 spline at (ia, ua) / (ib, ub); td = d t / d seed
+template <class T> KB_HD TEval<T> split_eval_t(const SplitConst& sp, const double* vecs, const double* quats, const double* so3pairs, int ia, double ua0,
+                                               int ib, double ub0, double td, const SplitSeed& sd) {
+  TEval<T> r;
+  {      // R3: p = sum (U M)_k c_k, v = sum (dU M)_k c_k
+    const T u = T(ua0, td / sp.dt_r3), u2 = u * u, u3 = u2 * u;
+    const T di = T(1.0 / sp.dt_r3), s6 = T(1.0 / 6.0);
+    T Bp[4], Bv[4];
+    Bp[0] = (T(1.0) - T(3.0) * u + T(3.0) * u2 - u3) * s6; Bp[1] = (T(4.0) - T(6.0) * u2 + T(3.0) * u3) * s6;
+    Bp[2] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(3.0) * u3) * s6; Bp[3] = u3 * s6;
+    Bv[0] = di * (T(-3.0) + T(6.0) * u - T(3.0) * u2) * s6; Bv[1] = di * (T(-12.0) * u + T(9.0) * u2) * s6;
+    Bv[2] = di * (T(3.0) + T(6.0) * u - T(9.0) * u2) * s6; Bv[3] = di * (T(3.0) * u2) * s6;
+    r.p = tv3<T>(T(0.0), T(0.0), T(0.0)); r.v = r.p;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double* c = vecs + (size_t)(ia + k) * kVecStride;
+      const bool hit = sd.spline == 1 && sd.knot == ia + k;
+      const TV3<T> cp = tv3<T>(T(c[0], hit && sd.comp == 0 ? 1.0 : 0.0), T(c[1], hit && sd.comp == 1 ? 1.0 : 0.0), T(c[2], hit && sd.comp == 2 ? 1.0 : 0.0));
+      r.p = r.p + Bp[k] * cp; r.v = r.v + Bv[k] * cp;
+    }
+  }
+  {      // SO3
+    const T u = T(ub0, td / sp.dt_so3), u2 = u * u, u3 = u2 * u;
+    const T di = T(1.0 / sp.dt_so3), s6 = T(1.0 / 6.0);
+    T B[3], dB[3];
+    B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * s6; B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * s6; B[2] = u3 * s6;
+    dB[0] = di * (T(3.0) - T(6.0) * u + T(3.0) * u2) * s6; dB[1] = di * (T(3.0) + T(6.0) * u - T(6.0) * u2) * s6; dB[2] = di * (T(3.0) * u2) * s6;
+    const double* q0d = quats + (size_t)ib * kQuatStride;
+    const bool hit0 = sd.spline == 2 && sd.knot == ib;
+    TQ<T> q0; q0.x = T(q0d[0], hit0 && sd.comp == 0 ? 1.0 : 0.0); q0.y = T(q0d[1], hit0 && sd.comp == 1 ? 1.0 : 0.0);
+    q0.z = T(q0d[2], hit0 && sd.comp == 2 ? 1.0 : 0.0); q0.w = T(q0d[3], hit0 && sd.comp == 3 ? 1.0 : 0.0);
+    TQ<T> q = q0, parts[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) { parts[m].x = T(0.0); parts[m].y = T(0.0); parts[m].z = T(0.0); parts[m].w = T(1.0); }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int pidx = ib + 1 + j;                                         // pair (knot pidx - 1, knot pidx)
+      const double* pr = so3pairs + (size_t)pidx * kSo3PairStride;
+      const double* D = sd.spline != 2 ? nullptr : (sd.knot == pidx - 1 ? pr + kSo3PairDOff : (sd.knot == pidx ? pr + kSo3PairDOff + kSo3PairSide : nullptr));
+      const TV3<T> om = tv3<T>(T(pr[0], D ? D[0 * 4 + sd.comp] : 0.0), T(pr[1], D ? D[1 * 4 + sd.comp] : 0.0), T(pr[2], D ? D[2 * 4 + sd.comp] : 0.0));
+      const TQ<T> e = expq_t<T>(B[j] * om);
+      q = tqmul(q, e);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        if (m == j) { TQ<T> w; w.x = om.x * dB[j]; w.y = om.y * dB[j]; w.z = om.z * dB[j]; w.w = T(0.0); parts[m] = tqmul(parts[m], w); }
+        parts[m] = tqmul(parts[m], e);
+      }
+    }
+    TQ<T> sum; sum.x = parts[0].x + parts[1].x + parts[2].x; sum.y = parts[0].y + parts[1].y + parts[2].y;
+    sum.z = parts[0].z + parts[1].z + parts[2].z; sum.w = parts[0].w + parts[1].w + parts[2].w;
+    const TQ<T> dq = tqmul(q0, sum);
+    const TQ<T> wq = tqmul(dq, tqconj(q));
+    r.q = q; r.w = tv3<T>(T(2.0) * wq.x, T(2.0) * wq.y, T(2.0) * wq.z);
+  }
+  return r;
+}
+// observation span of one spline (newton_rscamera_measurement.h:210-236 with the time offset locked): first knot and number of knots
+KB_HD int span_window_base(double t0, double dt, double obs_t0) { return knot_floor(sub_rn(obs_t0, 1e-3), t0, dt); }
+KB_HD int span_window_size(double t0, double dt, double readout, double obs_t0) { return knot_floor(add_rn(add_rn(obs_t0, readout), 1e-3), t0, dt) + 4 - span_window_base(t0, dt, obs_t0); }
+KB_HD int span_split_ndir(bool lifting, int Wa, int Wb) { return 28 + 3 * Wa + 4 * Wb + (lifting ? 2 : 1); }
+KB_HD int span_split_row_len(bool lifting, int Wa, int Wb) { return (lifting ? 3 : 2) * (28 + 3 * Wa + 4 * Wb) + (lifting ? 6 : 2); }
+// where direction `dir` lands in the packed row (residual row 0; the next residual rows are `stride` further on)
+KB_HD int span_split_dir_offset(bool lifting, int Wa, int Wb, int dir, int& stride) {
+  const int nres = lifting ? 3 : 2;
+  if (dir < 12) { stride = 3; return nres * 3 * (dir / 3) + dir % 3; }
+  if (dir < 28) { const int d = dir - 12; stride = 4; return nres * 12 + nres * 4 * (d / 4) + d % 4; }
+  if (dir < 28 + 3 * Wa) { const int d = dir - 28; stride = 3; return nres * 28 + nres * 3 * (d / 3) + d % 3; }
+  if (dir < 28 + 3 * Wa + 4 * Wb) { const int d = dir - 28 - 3 * Wa; stride = 4; return nres * (28 + 3 * Wa) + nres * 4 * (d / 4) + d % 4; }
+  stride = 1;
+  return nres * (28 + 3 * Wa + 4 * Wb) + nres * (dir - 28 - 3 * Wa - 4 * Wb);
+}
+// One direction of a NewtonRs (lifting = false) / LiftingRs row on a split trajectory.  rec: landmark record of k_landmark_ref_split.
+struct SpanSplitRow { double y[2], dy[2], dvt; int iterations; };
+KB_HD int span_split_direction(bool lifting, const SplitConst& sp, const CameraConst& cam, const double* vecs, const double* quats, const double* so3pairs,
+                               const double* rec, const double* obs_uv, double obs_t0, double ref_t0, double vt, int ka, int Wa, int kb, int Wb,
+                               int dir, SpanSplitRow& out) {
+  typedef D1 T;
+  Segment a0, a1, b0, b1;
+  const int nsa = static_rs_segments_split(sp, cam, ref_t0, obs_t0, sp.t0_r3, sp.dt_r3, a0, a1);
+  const int nsb = static_rs_segments_split(sp, cam, ref_t0, obs_t0, sp.t0_so3, sp.dt_so3, b0, b1);
+  if (nsa == 0 || nsb == 0) return kStatusRange;
+  const int d_obs_a = 28, d_obs_b = 28 + 3 * Wa, d_tail = 28 + 3 * Wa + 4 * Wb;
+  const int vt_dir = lifting ? d_tail : -1, rho_dir = lifting ? d_tail + 1 : d_tail;
+  TV3<T> X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
+  T rho = T(rec[6]);
+  SplitSeed sd; sd.spline = 0; sd.knot = -1; sd.comp = 0;
+  if (dir >= 0 && dir < 12) { const double v = rec[kRefSplitBp + dir / 3]; const int c = dir % 3; if (c == 0) X.x.d = v; else if (c == 1) X.y.d = v; else X.z.d = v; }
+  else if (dir >= 12 && dir < 28) { const double* d = rec + kRefSplitDq + 12 * ((dir - 12) / 4) + (dir - 12) % 4; X.x.d = d[0]; X.y.d = d[4]; X.z.d = d[8]; }
+  else if (dir >= d_obs_a && dir < d_obs_b) { sd.spline = 1; sd.knot = ka + (dir - d_obs_a) / 3; sd.comp = (dir - d_obs_a) % 3; }
+  else if (dir >= d_obs_b && dir < d_tail) { sd.spline = 2; sd.knot = kb + (dir - d_obs_b) / 4; sd.comp = (dir - d_obs_b) % 4; }
+  else if (dir == rho_dir) { X.x.d = rec[3]; X.y.d = rec[4]; X.z.d = rec[5]; rho.d = 1.0; }
+  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
+  const TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  out.iterations = 0; out.dvt = 0.0;
+  if (lifting) {
+    const T t_obs = T(add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(vt, cam.readout)), dir == vt_dir ? cam.readout : 0.0);
+    out.dvt = dir == vt_dir ? 1.0 : 0.0;
+    int ia, ib; double ua, ub;
+    if (locate_in_segments(nsa, a0, a1, t_obs.a, sp.t0_r3, sp.dt_r3, ia, ua) < 0 || locate_in_segments(nsb, b0, b1, t_obs.a, sp.t0_so3, sp.dt_so3, ib, ub) < 0) return kStatusRange;
+    if (ia < ka || ia + 4 > ka + Wa || ib < kb || ib + 4 > kb + Wb) return kStatusRange;
+    const TEval<T> ev = split_eval_t<T>(sp, vecs, quats, so3pairs, ia, ua, ib, ub, t_obs.d, sd);
+    const TV3<T> X_obs = tqrot(tqconj(ev.q), X - rho * ev.p);
+    const TV3<T> X_cam = tqrot(qct, X_obs) + rho * pct;
+    T y[2], dy[2];
+    camera_project_t<T>(cam, X_cam, tv3<T>(T(0.0), T(0.0), T(0.0)), y, dy);
+    out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+    return 0;
+  }
+  const double rows = (double)cam.rows;
+  const double t0_obs = add_rn(obs_t0, cam.time_offset);
+  T t_obs = T(static_rs_time(cam, obs_t0, obs_uv[1]));
+  const double max_dt = 0.5 * cam.readout / rows, max_dt2 = max_dt * max_dt;
+  const double min_bound = t0_obs, max_bound = add_rn(t0_obs, cam.readout);
+  T y[2] = {T(0.0), T(0.0)};
+  for (int iter = 0; iter < 5; ++iter) {
+    int ia, ib; double ua, ub;
+    if (locate_in_segments(nsa, a0, a1, t_obs.a, sp.t0_r3, sp.dt_r3, ia, ua) < 0 || locate_in_segments(nsb, b0, b1, t_obs.a, sp.t0_so3, sp.dt_so3, ib, ub) < 0) return kStatusRange;
+    if (ia < ka || ia + 4 > ka + Wa || ib < kb || ib + 4 > kb + Wb) return kStatusRange;
+    const TEval<T> ev = split_eval_t<T>(sp, vecs, quats, so3pairs, ia, ua, ib, ub, t_obs.d, sd);
+    TQ<T> wq; wq.x = ev.w.x; wq.y = ev.w.y; wq.z = ev.w.z; wq.w = T(0.0);
+    TQ<T> dq = tqmul(wq, ev.q); dq.x = T(0.5) * dq.x; dq.y = T(0.5) * dq.y; dq.z = T(0.5) * dq.z; dq.w = T(0.5) * dq.w;
+    const TQ<T> dq_inv = tqconj(dq), q_inv = tqconj(ev.q);
+    const TV3<T> s = X - rho * ev.p;
+    const TV3<T> ds = (T(0.0) - rho) * ev.v;
+    const TV3<T> X_obs = tqrot(q_inv, s);
+    const TV3<T> X_cam = tqrot(qct, X_obs) + rho * pct;
+    TQ<T> sq; sq.x = s.x; sq.y = s.y; sq.z = s.z; sq.w = T(0.0);
+    TQ<T> dsq; dsq.x = ds.x; dsq.y = ds.y; dsq.z = ds.z; dsq.w = T(0.0);
+    const TQ<T> a1q = tqmul(tqmul(dq_inv, sq), ev.q), a2q = tqmul(tqmul(q_inv, dsq), ev.q), a3q = tqmul(tqmul(q_inv, sq), dq);
+    const TV3<T> dX_obs = tv3<T>(a1q.x + a2q.x + a3q.x, a1q.y + a2q.y + a3q.y, a1q.z + a2q.z + a3q.z);
+    const TV3<T> dX_cam = tqrot(qct, dX_obs) + rho * pct;                    // sic (newton_rscamera_measurement.h:92)
+    T dy[2];
+    camera_project_t<T>(cam, X_cam, dX_cam, y, dy);
+    const T f = y[1] - (T(rows) * (t_obs - T(t0_obs)) / T(cam.readout));
+    const T df = dy[1] - T(rows / cam.readout);
+    const T dt = f / df;
+    t_obs = t_obs - dt;
+    out.iterations = iter + 1;
+    if (dt.a * dt.a < max_dt2) break;
+    if (t_obs.a < min_bound) t_obs = T(min_bound);
+    else if (t_obs.a > max_bound) t_obs = T(max_bound);
+  }
+  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+  return 0;
+}
+// residual and one Jacobian column of a split span row (Huber-corrected like the SE3 rows), written at its place in the packed row
+KB_HD int span_split_column(bool lifting, const SplitConst& sp, const CameraConst& cam, const double* vecs, const double* quats, const double* so3pairs,
+                            const double* rec, const double* obs_uv, double obs_t0, double ref_t0, double vt, int ka, int Wa, int kb, int Wb,
+                            double weight, double huber_c, int dir, double* r, double* Jrow) {
+  SpanSplitRow o;
+  const int st = span_split_direction(lifting, sp, cam, vecs, quats, so3pairs, rec, obs_uv, obs_t0, ref_t0, vt, ka, Wa, kb, Wb, dir, o);
+  if (st != 0) return st;
+  double j[3];
+  if (lifting) {
+    LiftingRow lo; lo.y[0] = o.y[0]; lo.y[1] = o.y[1]; lo.dy[0] = o.dy[0]; lo.dy[1] = o.dy[1]; lo.dvt = o.dvt;
+    lifting_rs_finish(lo, cam, obs_uv, vt, weight, huber_c, r, j);
+  } else {
+    NewtonRow no; no.y[0] = o.y[0]; no.y[1] = o.y[1]; no.dy[0] = o.dy[0]; no.dy[1] = o.dy[1]; no.iterations = o.iterations;
+    newton_rs_finish(no, obs_uv, weight, huber_c, r, j);
+  }
+  if (Jrow && dir >= 0) {
+    int stride;
+    const int off = span_split_dir_offset(lifting, Wa, Wb, dir, stride);
+    for (int rr = 0; rr < (lifting ? 3 : 2); ++rr) Jrow[off + rr * stride] = j[rr];
+  }
+  return 0;
+}
+
 }  // namespace kb

@@ -352,7 +352,24 @@ class TrajectoryEstimator:
         for grp in self._groups:
             o = outs[grp["g"]]
             n = len(o["r"])
-            if grp["kind"] == "cam" and grp.get("lifting"):
+            if grp["kind"] == "cam" and split and (grp.get("lifting") or grp.get("newton")):
+                # span rows on a split trajectory: [ref R3 4x(nres x 3) | ref SO3 4x(nres x 4) | obs R3 Wa x(..) | obs SO3 Wb x(..) | (vt nres) | rho nres]
+                J = o["J"].reshape(n, -1)
+                nres = 3 if grp.get("lifting") else 2
+                Wa, Wb = self._problem.group_span_windows(grp["g"])
+                o_rb, o_oa, o_ob, o_t = nres * 12, nres * 28, nres * (28 + 3 * Wa), nres * (28 + 3 * Wa + 4 * Wb)
+                add_blocks(J[:, :o_rb].reshape(n, 4, nres, 3), o["i0"], 3, "r3", nres)
+                add_blocks(J[:, o_rb:o_oa].reshape(n, 4, nres, 4), o["i0_c"], 4, "so3", nres)
+                add_blocks(J[:, o_oa:o_ob].reshape(n, Wa, nres, 3), o["i0_b"], 3, "r3", nres)
+                add_blocks(J[:, o_ob:o_t].reshape(n, Wb, nres, 4), o["i0_d"], 4, "so3", nres)
+                r_idx = row0 + nres * np.arange(n)[:, None] + np.arange(nres)[None, :]
+                if grp.get("lifting"):
+                    rows_i.append(r_idx.reshape(-1)); cols_i.append(np.repeat(grp["vt_col0"] + np.arange(n), 3)); vals.append(J[:, o_t:o_t + 3].reshape(-1))
+                    o_t += 3
+                col = self._lm_col[grp["lm"]]
+                free = col >= 0
+                rows_i.append(r_idx[free].reshape(-1)); cols_i.append(np.repeat(col[free], nres)); vals.append(J[free, o_t:o_t + nres].reshape(-1))
+            elif grp["kind"] == "cam" and grp.get("lifting"):
                 J = o["J"].reshape(n, -1)
                 nrow = J.shape[1]                                  # 90 + 21 W: [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3]
                 add_blocks(J[:, :84].reshape(n, 4, 3, 7), o["i0"], 7, "se3", 3)

@@ -224,6 +224,43 @@ void hc_static_rs_split(double t0_r3, double dt_r3, int n_r3, double t0_so3, dou
 }
 
 
+// NewtonRs (lifting = 0) / LiftingRs (1) rows on a split trajectory: what k_landmark_ref_split + k_span_rs_split do, one (row, direction) at a time.
+// J: n x span_split_row_len; idx [n][4] = ref R3 first knot, obs R3 span base, ref SO3 first knot, obs SO3 span base.
+int hc_span_split_row_len(int lifting, int Wa, int Wb) { return span_split_row_len(lifting != 0, Wa, Wb); }
+int hc_span_window(double t0, double dt, double readout, double obs_t0) { return span_window_size(t0, dt, readout, obs_t0); }
+void hc_span_rs_split(int lifting, double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, const double* K, const double* Kinv,
+                      const double* q_ct, const double* p_ct, double time_offset, double max_time_offset, int locked, double readout, int rows,
+                      const double* vecs4, const double* quats, const double* pairs, int n, const double* obs_uv, const double* obs_t0,
+                      const double* ref_uv, const double* ref_t0, const int* lm_idx, const double* rho, const double* vt, const double* w,
+                      const double* huber_c, int Wa, int Wb, double* r, double* J, int* idx, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  camera_set_pose(cam, q_ct, p_ct);
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  const int nres = lifting ? 3 : 2, len = span_split_row_len(lifting != 0, Wa, Wb), ndir = span_split_ndir(lifting != 0, Wa, Wb);
+  for (int i = 0; i < n; ++i) {
+    for (int c = 0; c < 4; ++c) idx[4 * i + c] = -1;
+    double rec[kRefSplitStride];
+    const double tr = static_rs_time(cam, ref_t0[i], ref_uv[2 * i + 1]);
+    Segment a0, a1, b0, b1; int ia, ib; double ua, ub;
+    const int na = static_rs_segments_split(sp, cam, ref_t0[i], obs_t0[i], sp.t0_r3, sp.dt_r3, a0, a1);
+    const int nb = static_rs_segments_split(sp, cam, ref_t0[i], obs_t0[i], sp.t0_so3, sp.dt_so3, b0, b1);
+    const int wa = na == 0 ? -1 : locate_in_segments(na, a0, a1, tr, sp.t0_r3, sp.dt_r3, ia, ua);
+    const int wb = nb == 0 ? -1 : locate_in_segments(nb, b0, b1, tr, sp.t0_so3, sp.dt_so3, ib, ub);
+    if (wa < 0 || wb < 0) { status[i] = kStatusRange; continue; }
+    const Segment& sa = wa == 0 ? a0 : a1; const Segment& sb = wb == 0 ? b0 : b1;
+    status[i] = landmark_ref_row_split(sp, cam, vecs4, quats, pairs, ref_uv + 2 * i, ref_t0[i], sa.start, sa.n, sb.start, sb.n, rho[lm_idx[i]], rec);
+    if (status[i] != 0) continue;
+    const int ka = span_window_base(sp.t0_r3, sp.dt_r3, obs_t0[i]), kb = span_window_base(sp.t0_so3, sp.dt_so3, obs_t0[i]);
+    for (int dir = 0; dir < ndir && status[i] == 0; ++dir)
+      status[i] = span_split_column(lifting != 0, sp, cam, vecs4, quats, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], lifting ? vt[i] : 0.0, ka, Wa, kb, Wb,
+                                    w[i], huber_c ? huber_c[i] : 0.0, dir, r + nres * i, J + (size_t)len * i);
+    idx[4 * i] = (int)rec[7]; idx[4 * i + 1] = ka; idx[4 * i + 2] = (int)rec[8]; idx[4 * i + 3] = kb;
+  }
+}
 void hc_traj_eval_se3(double t0, double dt, int n_knots, int compat, const double* knots8, const double* pairs, int n, const double* t, double* out, int* status) {
   SplineConst sp{t0, dt, n_knots, compat};
   for (int i = 0; i < n; ++i) status[i] = traj_eval_se3(sp, knots8, pairs, t[i], out + 16 * i);

@@ -213,6 +213,34 @@ def static_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs
     return dict(r=r, J=J, idx=idx, status=st)
 
 
+def span_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, lifting=False, vt=None, w=None, huber_c=None):
+    """NewtonRs / LiftingRs rows on a split trajectory, packed [ref R3 4x(nres x 3) | ref SO3 4x(nres x 4) | obs R3 Wa x(..) | obs SO3 Wb x(..) | (vt) | rho];
+    idx (n, 4) = ref R3 first knot, obs R3 span base, ref SO3 first knot, obs SO3 span base."""
+    _set_camera_model(cam)
+    v4, q4, pairs, st0 = split_prepass(vecs3, quats)
+    obs_uv, ref_uv = _f(obs_uv).reshape(-1, 2), _f(ref_uv).reshape(-1, 2)
+    obs_t0, ref_t0, rho = _f(obs_t0), _f(ref_t0), _f(rho)
+    lm_idx = np.ascontiguousarray(lm_idx, np.int32)
+    n = len(obs_t0)
+    vt = np.ascontiguousarray(obs_uv[:, 1] / float(cam.rows) if vt is None else _f(vt), np.float64)
+    w = np.ones(n) if w is None else _f(w)
+    hc = None if huber_c is None else _f(huber_c)
+    K = _f(cam.K).reshape(-1)
+    Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
+    lib().hc_span_window.argtypes = [C.c_double] * 4
+    Wa = max(int(lib().hc_span_window(t0_r3, dt_r3, cam.readout, float(t))) for t in obs_t0)
+    Wb = max(int(lib().hc_span_window(t0_so3, dt_so3, cam.readout, float(t))) for t in obs_t0)
+    nres = 3 if lifting else 2
+    row = int(lib().hc_span_split_row_len(int(bool(lifting)), Wa, Wb))
+    r, J = np.zeros((n, nres)), np.zeros((n, row))
+    idx, st = np.zeros((n, 4), np.int32), np.zeros(n, np.int32)
+    lib().hc_span_rs_split(int(bool(lifting)), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(K), _p(Kinv),
+                           _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked),
+                           C.c_double(cam.readout), int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0),
+                           _p(lm_idx), _p(rho), _p(vt), _p(w), _p(hc), Wa, Wb, _p(r), _p(J), _p(idx), _p(st))
+    return dict(r=r, J=J, idx=idx, status=st, Wa=Wa, Wb=Wb, vt=vt)
+
+
 def traj_eval_se3(knots7, dt, t0, t, compat=False):
     k8, pairs = prepass(knots7)
     t = _f(np.atleast_1d(t))

@@ -62,3 +62,24 @@ def scatter_lifting(Jp, i0_ref, i0_obs, ids, W):
                     assert not blk.any(), "non-zero block outside the residual's structural knots"
     return out, Jp[:, row - 6:row - 3], Jp[:, row - 3:row]
 
+
+
+def scatter_span_split(Jp, idx, ids_a, ids_b, Wa, Wb, nres):
+    """Packed span row on a split trajectory [ref R3 4x(nres x 3) | ref SO3 4x(nres x 4) | obs R3 Wa x(..) | obs SO3 Wb x(..) | tail] ->
+    (R3 blocks (n, cap, nres, 3), SO3 blocks (n, cap, nres, 4), tail (n, tail)); idx (n, 4) = ref R3, obs R3 base, ref SO3, obs SO3 base."""
+    n, cap_a = ids_a.shape
+    cap_b = ids_b.shape[1]
+    Ja, Jb = np.zeros((n, cap_a, nres, 3)), np.zeros((n, cap_b, nres, 4))
+    Jp = np.asarray(Jp).reshape(n, -1)
+    o_ra, o_rb, o_oa, o_ob, o_t = 0, nres * 12, nres * 28, nres * (28 + 3 * Wa), nres * (28 + 3 * Wa + 4 * Wb)
+    for i in range(n):
+        pa = {int(k): j for j, k in enumerate(ids_a[i]) if k >= 0}
+        pb = {int(k): j for j, k in enumerate(ids_b[i]) if k >= 0}
+        for base, off, nk, w, pos, out in ((idx[i, 0], o_ra, 4, 3, pa, Ja), (idx[i, 1], o_oa, Wa, 3, pa, Ja), (idx[i, 2], o_rb, 4, 4, pb, Jb), (idx[i, 3], o_ob, Wb, 4, pb, Jb)):
+            for k in range(nk):
+                blk = Jp[i, off + nres * w * k: off + nres * w * (k + 1)].reshape(nres, w)
+                if int(base) + k in pos:
+                    out[i, pos[int(base) + k]] += blk
+                else:
+                    assert not blk.any(), "non-zero block outside the residual's structural knots"
+    return Ja, Jb, Jp[:, o_t:]

@@ -801,3 +801,64 @@ def test_span_camera_unlocked_relative_pose_matches_oracle(method, atan, robust)
     assert not out["Js"][:, 7 * nres:].any()
     dev = p.evaluate(cfg["knots"], c["rho"], base | _lib.EVAL_SENSOR_JACOBIANS | _lib.EVAL_DEVICE_ORDER)[g]
     assert np.array_equal(dev["Js"], out["Js"][p.get_row_order(g)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,same_grid,robust", [("newton", True, False), ("newton", False, True), ("lifting", False, False), ("lifting", True, True)])
+def test_span_camera_rows_on_split_trajectory_match_oracle(method, same_grid, robust):
+    """NewtonRsCameraMeasurement / LiftingRsCameraMeasurement on a SplitTrajectory (python/src/kontiki/measurements/measurement_defs.h:40-85: every
+    measurement is instantiated with every trajectory) through the C ABI: k_landmark_ref_split + k_span_rs_split (forward mode, one thread per
+    row and direction), rows [ref R3 | ref SO3 | obs R3 span | obs SO3 span | (vt) | rho], windows bit-exact, structure vs the oracle's block lists."""
+    c = _split_case(n_lm=120, scale_imu=10, same_grid=same_grid)
+    cam = c["cam"]
+    rng = np.random.default_rng(5)
+    n = len(cam["lm_idx"])
+    cam["obs_uv"] += rng.normal(0, 1.0, cam["obs_uv"].shape)
+    cam["obs_uv"][:, 1] = np.clip(cam["obs_uv"][:, 1], 0, cam["rows"] - 1e-6)
+    p = _lib.Problem(0)
+    p.set_split_spline(c["dt_a"], c["t0_a"], len(c["vecs"]), c["dt_b"], c["t0_b"], len(c["quats"]))
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    add = p.add_newton_rs if method == "newton" else p.add_lifting_rs
+    g = add(_lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"], q_ct=q_ct, p_ct=p_ct), cam["obs_uv"], cam["obs_t0"], cam["ref_uv"],
+            cam["ref_t0"], cam["lm_idx"], cam["weight"], cam["huber_c"])
+    traj = kto.Traj(kto.SPLIT, c["dt_a"], c["t0_a"], c["vecs"], c["dt_b"], c["t0_b"], c["quats"])
+    ocam = kto.Camera(cam["rows"], cam["cols"], cam["readout"], K=cam["K"], method="newton" if method == "newton" else "static", q_ct=q_ct, p_ct=p_ct)
+    nres = 2 if method == "newton" else 3
+    args = (cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["rho"])
+    if method == "lifting":
+        vt = np.clip(cam["obs_uv"][:, 1] / cam["rows"] + rng.uniform(-0.2, 0.2, n), 0.0, 1.0)
+        p.set_group_vt(g, vt)
+        o = kto.lifting_rs_residuals(traj, ocam, *args, vt=vt, weight=cam["weight"], jac_mode=2, cap=24)
+        tail_o = np.concatenate([o["Jvt"], o["Jrho"]], axis=1)
+    else:
+        o = kto.static_rs_residuals(traj, ocam, *args, cam["weight"], jac_mode=2, cap=24)
+        tail_o = o["Jrho"]
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    out = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags)[g]
+    Wa, Wb = p.group_span_windows(g)
+    assert out["J"].shape == (n, nres * (28 + 3 * Wa + 4 * Wb) + (2 if nres == 2 else 6)) and out["r"].shape == (n, nres)
+    assert (out["i0"] == o["i0_ref_a"]).all() and (out["i0_c"] == o["i0_ref_b"]).all()                  # bit-exact indexing of the reference window
+    ids_a, _ = p.get_structure(g, cap=24)
+    ids_b, _ = p.get_structure_so3(g, cap=24)
+    assert (ids_a == o["ids_a"]).all() and (ids_b == o["ids_b"]).all()
+    idx = np.stack([out["i0"], out["i0_b"], out["i0_c"], out["i0_d"]], axis=1)
+    Ja, Jb, tail = parity.scatter_span_split(out["J"], idx, o["ids_a"], o["ids_b"], Wa, Wb, nres)
+    if not robust:
+        assert np.abs(out["r"] - o["r"]).max() < parity.CAM_R_TOL
+        assert parity.rel_err(Ja, o["Ja"]) < parity.TOL and parity.rel_err(Jb, o["Jb"]) < parity.TOL and parity.rel_err(tail, tail_o) < parity.TOL
+    else:
+        n_out = 0
+        for i in range(0, n, 3):
+            ma, mb = int((o["ids_a"][i] >= 0).sum()), int((o["ids_b"][i] >= 0).sum())
+            Jfull = np.concatenate([o["Ja"][i, k] for k in range(ma)] + [o["Jb"][i, k] for k in range(mb)] + [tail_o[i].reshape(-1, nres).T], axis=1)
+            _, r2, J2 = kto.huber_correct(cam["huber_c"][i], o["r"][i], Jfull)
+            Jmine = np.concatenate([Ja[i, k] for k in range(ma)] + [Jb[i, k] for k in range(mb)] + [tail[i].reshape(-1, nres).T], axis=1)
+            assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+            assert np.abs(out["r"][i] - r2).max() <= parity.CAM_R_TOL
+            n_out += np.linalg.norm(o["r"][i]) > cam["huber_c"][i]
+        assert n_out > 3
+    dev = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags | _lib.EVAL_DEVICE_ORDER)[g]
+    order = p.get_row_order(g)
+    assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order]) and np.array_equal(dev["i0_d"], out["i0_d"][order])
+    with pytest.raises(NotImplementedError):
+        p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags | _lib.EVAL_LOCAL)

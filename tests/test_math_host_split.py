@@ -118,3 +118,51 @@ def test_split_orientation_rows_match_oracle():
     assert np.abs(o["r"][:, 0] - ang).max() < 1e-9 and np.abs(h["r"] - o["r"]).max() < parity.TOL
     assert parity.rel_err(h["J"].reshape(-1, 4, 1, 4), o["Jb"][:, :4]) < parity.TOL
     assert not o["Ja"].any()
+
+
+@pytest.mark.parametrize("lifting,atan,robust", [(False, False, False), (False, True, True), (True, False, True), (True, True, False)])
+def test_split_span_camera_rows_match_oracle(lifting, atan, robust):
+    """NewtonRsCameraMeasurement / LiftingRsCameraMeasurement on a SplitTrajectory (the reference instantiates every measurement with every
+    trajectory, python/src/kontiki/measurements/measurement_defs.h:40-85): forward mode through the R3 spline and the reference's SO3
+    evaluation (uniform_so3_spline_trajectory.h:46-125) on the hoisted pair logs, different grids for the two splines."""
+    vecs, quats, traj, k = _traj(dt_b=0.04, t0_b=0.0)
+    s = syn.make_static_rs(k, 0.05, 30, obs_per_landmark=5, seed=7, noise_px=1.5)
+    rng = np.random.default_rng(2)
+    n = len(s["lm_idx"])
+    out = rng.random(n) < 0.2
+    s["obs_uv"][out] += rng.normal(0, 40, (out.sum(), 2))
+    s["obs_uv"][:, 1] = np.clip(s["obs_uv"][:, 1], 0, s["rows"] - 1e-6)
+    w = rng.uniform(0.5, 2, n)
+    kw = dict(wc=(0.02, -0.01), gamma=0.9) if atan else {}
+    cam = kto.Camera(s["rows"], s["cols"], s["readout"], K=s["K"], method="static" if lifting else "newton",
+                     q_ct=fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), p_ct=np.array([0.05, -0.02, 0.1]), **kw)
+    args = (s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"])
+    nres = 3 if lifting else 2
+    if lifting:
+        vt = np.clip(s["obs_uv"][:, 1] / s["rows"] + rng.uniform(-0.2, 0.2, n), 0.0, 1.0)
+        o = kto.lifting_rs_residuals(traj, cam, *args, vt=vt, weight=w, jac_mode=2, cap=24)
+        tail_o = np.concatenate([o["Jvt"], o["Jrho"]], axis=1)
+    else:
+        vt = None
+        o = kto.static_rs_residuals(traj, cam, *args, w, jac_mode=2, cap=24)
+        tail_o = o["Jrho"]
+    c = np.full(n, 2.0) if robust else None
+    h = hc.span_rs_split(vecs, 0.05, 0.0, quats, 0.04, 0.0, cam, *args, lifting=lifting, vt=vt, w=w, huber_c=c)
+    assert (h["status"] == 0).all()
+    idx = h["idx"]
+    assert (idx[:, 0] == o["i0_ref_a"]).all() and (idx[:, 2] == o["i0_ref_b"]).all()
+    Ja, Jb, tail = parity.scatter_span_split(h["J"], idx, o["ids_a"], o["ids_b"], h["Wa"], h["Wb"], nres)
+    if not robust:
+        assert np.abs(h["r"] - o["r"]).max() < parity.CAM_R_TOL
+        assert parity.rel_err(Ja, o["Ja"]) < parity.TOL and parity.rel_err(Jb, o["Jb"]) < parity.TOL and parity.rel_err(tail, tail_o) < parity.TOL
+        return
+    n_out = 0
+    for i in range(n):
+        ma, mb = int((o["ids_a"][i] >= 0).sum()), int((o["ids_b"][i] >= 0).sum())
+        Jfull = np.concatenate([o["Ja"][i, kk] for kk in range(ma)] + [o["Jb"][i, kk] for kk in range(mb)] + [tail_o[i].reshape(-1, nres).T], axis=1)
+        _, r2, J2 = kto.huber_correct(2.0, o["r"][i], Jfull)
+        Jmine = np.concatenate([Ja[i, kk] for kk in range(ma)] + [Jb[i, kk] for kk in range(mb)] + [tail[i].reshape(-1, nres).T], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(h["r"][i] - r2).max() <= parity.CAM_R_TOL
+        n_out += float(np.dot(o["r"][i], o["r"][i])) > 4.0
+    assert n_out > 3
