@@ -199,7 +199,7 @@ int32_t ktk_group_row_size_local(const ktk_problem* p, int32_t group);   /* ... 
  *   [ref R3 4 x (nres x 3) | ref SO3 4 x (nres x 4) | obs R3 Wa x (nres x 3) | obs SO3 Wb x (nres x 4) | (d r/d vt nres) | d r/d rho nres]
  * with i0 / i0_b = first knot of the reference window / of the observation span on the R3 spline and i0_c / i0_d the same on the SO3 spline
  * (newton_rscamera_measurement.h:201-262 and lifting_rscamera_measurement.h:151-229 instantiated on SplitTrajectory; forward mode,
- * csrc/newton_math.cuh).  On a split trajectory these rows take locked camera parameters and ambient coordinates only. */
+ * csrc/newton_math.cuh).  KTK_EVAL_LOCAL: [ref R3 4 x (nres x 3) | ref SO3 4 x (nres x 3) | obs R3 Wa x (nres x 3) | obs SO3 Wb x (nres x 3) | tail]. */
 int ktk_group_span_windows(const ktk_problem* p, int32_t group, int32_t* w_a, int32_t* w_b);
 int64_t ktk_num_knot_doubles(const ktk_problem* p);                /* length of the `knots` argument of ktk_evaluate */
 

@@ -986,6 +986,32 @@ __global__ void k_span_localize(const double* __restrict__ Jamb, const int* __re
   for (int c = 0; c < nres * 6; ++c) dst[(size_t)b * nres * 6 + c] = blk[c];
 }
 
+// ... the same for span rows on a split trajectory: R3 blocks are already local (R^3 is its own tangent space), every SO3 block goes through
+// EigenQuaternionParameterization (localize_so3_blocks).  Local row [ref R3 4 x (nres x 3) | ref SO3 4 x (nres x 3) | obs R3 Wa x .. | obs SO3 Wb x .. | tail].
+__global__ void k_span_localize_split(const double* __restrict__ Jamb, const int* __restrict__ i0c, const int* __restrict__ i0d, const double* __restrict__ quats,
+                                      int n_so3, int n, int Wa, int Wb, int nres, int tail, double* __restrict__ Jloc) {
+  const int nb = 8 + Wa + Wb + 1;      // blocks in row order: 4 ref R3, 4 ref SO3, Wa obs R3, Wb obs SO3, tail
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (int)(tid / nb), b = (int)(tid % nb);
+  if (i >= n) return;
+  const size_t la = (size_t)nres * (28 + 3 * Wa + 4 * Wb) + tail, ll = (size_t)nres * 3 * (8 + Wa + Wb) + tail;
+  const double* src = Jamb + (size_t)i * la;
+  double* dst = Jloc + (size_t)i * ll;
+  if (b == nb - 1) { for (int c = 0; c < tail; ++c) dst[ll - tail + c] = src[la - tail + c]; return; }
+  int so3, k, first, soff, doff;      // which spline, knot within its window, first knot, ambient / local offsets of the block
+  if (b < 4) { so3 = 0; k = b; first = 0; soff = nres * 3 * k; doff = nres * 3 * k; }
+  else if (b < 8) { so3 = 1; k = b - 4; first = i0c[i]; soff = nres * 12 + nres * 4 * k; doff = nres * 12 + nres * 3 * k; }
+  else if (b < 8 + Wa) { so3 = 0; k = b - 8; first = 0; soff = nres * 28 + nres * 3 * k; doff = nres * 24 + nres * 3 * k; }
+  else { so3 = 1; k = b - 8 - Wa; first = i0d[i]; soff = nres * (28 + 3 * Wa) + nres * 4 * k; doff = nres * (24 + 3 * Wa) + nres * 3 * k; }
+  if (!so3) { for (int c = 0; c < nres * 3; ++c) dst[doff + c] = src[soff + c]; return; }
+  int kn = first < 0 ? 0 : first + k;
+  if (kn >= n_so3) kn = n_so3 - 1;
+  double blk[12];
+  for (int c = 0; c < nres * 4; ++c) blk[c] = src[soff + c];
+  if (nres == 3) localize_so3_blocks<3>(blk, 1, quats + (size_t)kn * kQuatStride); else localize_so3_blocks<2>(blk, 1, quats + (size_t)kn * kQuatStride);
+  for (int c = 0; c < nres * 3; ++c) dst[doff + c] = blk[c];
+}
+
 // NewtonRs / LiftingRs rows on a SPLIT trajectory (newton_math.cuh "rows on a SPLIT trajectory"): forward mode, one thread per (row, direction);
 // every direction writes its own column of the packed row, direction 0 the residual and the four window indices.  Cold path.
 struct SpanSplitArgs {
@@ -1034,6 +1060,7 @@ __global__ void __launch_bounds__(128) k_span_rs_split(const SpanSplitArgs a) {
 // Sensor-block columns of NewtonRs / LiftingRs rows (newton_math.cuh "sensor-block columns"): one thread per (row, column 0..6) in forward mode.
 // Js per row: [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero)], nres = 2 / 3.  Cold path.
 struct SpanSensorArgs {
+  int traj; SplitConst spl; const double* vecs; const double* quats; const double* so3pairs; int Wa, Wb;      // split trajectory (traj == 1)
   SplineConst sp; CameraConst cam; const double* knots; const double* pairs; const double* rho;
   const double* obs_uv; const double* obs_t0; const double* ref_uv; const double* ref_t0; const int* lm; const double* w; const double* huber;
   const double* vt; const int* perm; int n, W, lifting; uint32_t flags; double* Js; int* err;
@@ -1046,9 +1073,16 @@ __global__ void k_span_sensor(const SpanSensorArgs a) {
   const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]}, ruv[2] = {a.ref_uv[2 * (size_t)i], a.ref_uv[2 * (size_t)i + 1]};
   const double hub = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
   double* dst = a.Js + (size_t)8 * nres * (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
-  const int kbase = newton_obs_window_base(a.sp, a.cam, a.obs_t0[i]);
-  const int st = span_sensor_column(a.lifting != 0, a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.rho[a.lm[i]], ouv, a.obs_t0[i],
-                                    a.lifting ? a.vt[i] : 0.0, kbase, a.W, a.w[i], hub, c, dst);
+  int st;
+  if (a.traj == 1) {
+    const int ka = span_window_base(a.spl.t0_r3, a.spl.dt_r3, a.obs_t0[i]), kb = span_window_base(a.spl.t0_so3, a.spl.dt_so3, a.obs_t0[i]);
+    st = span_split_sensor_column(a.lifting != 0, a.spl, a.cam, a.vecs, a.quats, a.so3pairs, ruv, a.ref_t0[i], a.rho[a.lm[i]], ouv, a.obs_t0[i],
+                                  a.lifting ? a.vt[i] : 0.0, ka, a.Wa, kb, a.Wb, a.w[i], hub, c, dst);
+  } else {
+    const int kbase = newton_obs_window_base(a.sp, a.cam, a.obs_t0[i]);
+    st = span_sensor_column(a.lifting != 0, a.sp, a.cam, a.knots, a.pairs, ruv, a.ref_t0[i], a.rho[a.lm[i]], ouv, a.obs_t0[i],
+                            a.lifting ? a.vt[i] : 0.0, kbase, a.W, a.w[i], hub, c, dst);
+  }
   if (st != 0) {
     atomicMin(a.err, st);
     for (int rr = 0; rr < nres; ++rr) { if (c < 4) dst[4 * rr + c] = nan(""); else dst[4 * nres + 3 * rr + (c - 4)] = nan(""); if (c == 0) dst[7 * nres + rr] = nan(""); }
@@ -1465,7 +1499,10 @@ int newton_window(const ktk_problem* p, const Group& g) {
 }
 int row_doubles(const ktk_problem* p, const Group& g, uint32_t flags = 0) {
   const bool local = (flags & KTK_EVAL_LOCAL) != 0;
-  if (is_span_camera(g.kind) && p->traj == 1) return span_split_row_len(g.kind == KTK_LIFTING_RS, span_window_split(p, g, 0), span_window_split(p, g, 1));
+  if (is_span_camera(g.kind) && p->traj == 1) {
+    const int Wa = span_window_split(p, g, 0), Wb = span_window_split(p, g, 1), nres = g.kind == KTK_LIFTING_RS ? 3 : 2;
+    return local ? nres * 3 * (8 + Wa + Wb) + (nres == 3 ? 6 : 2) : span_split_row_len(nres == 3, Wa, Wb);
+  }
   if (g.kind == KTK_NEWTON_RS) return local ? 2 + 12 * (4 + newton_window(p, g)) : 58 + 14 * newton_window(p, g);
   if (g.kind == KTK_LIFTING_RS) return local ? 6 + 18 * (4 + newton_window(p, g)) : 90 + 21 * newton_window(p, g);
   if (g.kind == KTK_STATIC_RS) return local ? 98 : kCamRow;
@@ -1678,14 +1715,15 @@ static int launch_sensor_jacobians(ktk_problem* p, Group& g, const ktk_group_out
   if (g.sensor.q_locked && g.sensor.p_locked && g.sensor.time_offset_locked) return KTK_OK;
   if (!is_camera(g.kind) && g.sensor.time_offset_locked) return KTK_OK;              // an IMU's relative pose is not applied (TODO.md:6): only the time offset has columns
   if (is_span_camera(g.kind)) {
-    if (p->traj != 0) return fail(KTK_EUNSUPPORTED, "NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (!g.sensor.time_offset_locked) return fail(KTK_EUNSUPPORTED, "an unlocked time offset under NewtonRs / LiftingRs camera measurements is not built (relative pose: yes)");
     if (g.d_ref_uv_sorted.n != (size_t)2 * g.n) return fail(KTK_EINVAL, "sensor Jacobians requested for a camera whose blocks are all locked");
     SpanSensorArgs a;
+    a.traj = p->traj; a.spl = p->spl; a.vecs = p->d_vecs4.p; a.quats = d_quats; a.so3pairs = p->d_so3pairs.p;
+    a.Wa = p->traj == 1 ? span_window_split(p, g, 0) : 0; a.Wb = p->traj == 1 ? span_window_split(p, g, 1) : 0;
     a.sp = p->sp; fill_camera_consts(g.cam, a.cam);
     a.knots = p->d_knots8.p; a.pairs = p->d_pairs.p; a.rho = d_rho;
     a.obs_uv = g.d_obs_uv.p; a.obs_t0 = g.d_obs_t0.p; a.ref_uv = g.d_ref_uv_sorted.p; a.ref_t0 = g.d_ref_t0.p; a.lm = g.d_lm_sorted.p; a.w = g.d_w.p;
-    a.huber = g.d_huber.p; a.vt = g.d_vt.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.W = newton_window(p, g); a.lifting = g.kind == KTK_LIFTING_RS;
+    a.huber = g.d_huber.p; a.vt = g.d_vt.p; a.perm = g.d_perm.p; a.n = (int)g.n; a.W = p->traj == 1 ? 0 : newton_window(p, g); a.lifting = g.kind == KTK_LIFTING_RS;
     a.flags = flags; a.Js = o.Js; a.err = p->d_err.p;
     const long long threads = (long long)g.n * 7;
     k_span_sensor<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(a);
@@ -1751,8 +1789,21 @@ static int evaluate_device_split(ktk_problem* p, const double* d_knots, const do
         sa.obs_uv = a.obs_uv; sa.obs_t0 = a.obs_t0; sa.ref_t0 = a.ref_t0; sa.ref_idx = a.ref_idx; sa.w = a.w; sa.huber = a.huber; sa.vt = g.d_vt.p;
         sa.perm = a.perm; sa.n = a.n; sa.Wa = span_window_split(p, g, 0); sa.Wb = span_window_split(p, g, 1); sa.lifting = g.kind == KTK_LIFTING_RS;
         sa.flags = flags; sa.r = o.r; sa.J = o.J; for (int c = 0; c < 4; ++c) sa.idx[c] = a.idx[c]; sa.err = p->d_err.p;
+        const bool localize = (flags & KTK_EVAL_LOCAL) && o.J && (flags & KTK_EVAL_JACOBIANS);
+        if (localize) {      // ambient rows and the SO3 window indices into scratch; k_span_localize_split writes the caller's local rows
+          sa.flags = flags & ~(uint32_t)KTK_EVAL_LOCAL; sa.J = g.o_amb.p;
+          if (!sa.idx[2]) sa.idx[2] = g.o_amb_i0.p;
+          if (!sa.idx[3]) sa.idx[3] = g.o_amb_i0b.p;
+        }
         const long long threads = (long long)g.n * span_split_ndir(sa.lifting != 0, sa.Wa, sa.Wb);
         k_span_rs_split<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(sa);
+        if (localize) {
+          const int nres = sa.lifting ? 3 : 2;
+          const long long th2 = (long long)g.n * (8 + sa.Wa + sa.Wb + 1);
+          k_span_localize_split<<<(unsigned)((th2 + 127) / 128), 128, 0, s>>>(g.o_amb.p, sa.idx[2], sa.idx[3], d_quats, sp.n_so3, (int)g.n, sa.Wa, sa.Wb, nres,
+                                                                            nres == 3 ? 6 : 2, o.J);
+          p->launches += 1;
+        }
       }
       else k_static_rs_split<<<blocks, kCamThreads, (kCamThreads / 32) * kCamSplitWarpSmem * 8, s>>>(a);
     } else {
@@ -1796,7 +1847,6 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       if ((st = g->o_amb.resize((size_t)g->n * row_doubles(p, *g)))) return st;
       if ((st = g->o_amb_i0.resize((size_t)g->n)) || (st = g->o_amb_i0b.resize((size_t)g->n))) return st;
     }
-    if (is_span_camera(g->kind) && p->traj == 1 && (flags & KTK_EVAL_LOCAL)) return fail(KTK_EUNSUPPORTED, "KTK_EVAL_LOCAL rows of NewtonRs / LiftingRs camera measurements on a split trajectory are not built");
     if (is_camera(g->kind)) {
       if (!d_rho) return fail(KTK_EINVAL, "rho is NULL but the problem has camera measurements");
       if (g->n > 0 && (g->lm_min < 0 || g->lm_max >= n_rho)) return fail(KTK_EINVAL, "landmark index out of range of rho");

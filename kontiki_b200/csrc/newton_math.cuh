@@ -755,9 +755,11 @@ KB_HD int span_split_dir_offset(bool lifting, int Wa, int Wb, int dir, int& stri
 }
 // One direction of a NewtonRs (lifting = false) / LiftingRs row on a split trajectory.  rec: landmark record of k_landmark_ref_split.
 struct SpanSplitRow { double y[2], dy[2], dvt; int iterations; };
+// sensor_c >= 0 (with dir < 0, rec == nullptr): column sensor_c of the camera's relative pose (0..3 q_ct, 4..6 p_ct) -- the landmark X(t_ref) is then
+// evaluated here on the dual number from (ref_uv, rho_v), because it depends on the camera pose too.
 KB_HD int span_split_direction(bool lifting, const SplitConst& sp, const CameraConst& cam, const double* vecs, const double* quats, const double* so3pairs,
                                const double* rec, const double* obs_uv, double obs_t0, double ref_t0, double vt, int ka, int Wa, int kb, int Wb,
-                               int dir, SpanSplitRow& out) {
+                               int dir, SpanSplitRow& out, int sensor_c = -1, const double* ref_uv = nullptr, double rho_v = 0.0) {
   typedef D1 T;
   Segment a0, a1, b0, b1;
   const int nsa = static_rs_segments_split(sp, cam, ref_t0, obs_t0, sp.t0_r3, sp.dt_r3, a0, a1);
@@ -765,16 +767,31 @@ KB_HD int span_split_direction(bool lifting, const SplitConst& sp, const CameraC
   if (nsa == 0 || nsb == 0) return kStatusRange;
   const int d_obs_a = 28, d_obs_b = 28 + 3 * Wa, d_tail = 28 + 3 * Wa + 4 * Wb;
   const int vt_dir = lifting ? d_tail : -1, rho_dir = lifting ? d_tail + 1 : d_tail;
-  TV3<T> X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
-  T rho = T(rec[6]);
   SplitSeed sd; sd.spline = 0; sd.knot = -1; sd.comp = 0;
-  if (dir >= 0 && dir < 12) { const double v = rec[kRefSplitBp + dir / 3]; const int c = dir % 3; if (c == 0) X.x.d = v; else if (c == 1) X.y.d = v; else X.z.d = v; }
+  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
+  TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  TV3<T> X;
+  T rho;
+  if (sensor_c >= 0) {
+    const SensorSeed<T> ss = camera_sensor_seed(cam, sensor_c);
+    qct = ss.qct; pct = ss.pct; rho = T(rho_v);
+    int ia, ib; double ua, ub;
+    const double tr = static_rs_time(cam, ref_t0, ref_uv[1]);
+    if (locate_in_segments(nsa, a0, a1, tr, sp.t0_r3, sp.dt_r3, ia, ua) < 0 || locate_in_segments(nsb, b0, b1, tr, sp.t0_so3, sp.dt_so3, ib, ub) < 0) return kStatusRange;
+    if (ia < 0 || ia + 3 >= sp.n_r3 || ib < 0 || ib + 3 >= sp.n_so3) return kStatusRange;
+    const TEval<T> er = split_eval_t<T>(sp, vecs, quats, so3pairs, ia, ua, ib, ub, 0.0, sd);
+    const V3 yh = camera_unproject(cam, ref_uv[0], ref_uv[1]);
+    X = tqrot(er.q, tqrot(tqconj(qct), tv3<T>(T(yh.x), T(yh.y), T(yh.z)) - rho * pct)) + rho * er.p;
+  } else {
+    X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
+    rho = T(rec[6]);
+  }
+  if (sensor_c >= 0) { /* knots and rho unseeded */ }
+  else if (dir >= 0 && dir < 12) { const double v = rec[kRefSplitBp + dir / 3]; const int c = dir % 3; if (c == 0) X.x.d = v; else if (c == 1) X.y.d = v; else X.z.d = v; }
   else if (dir >= 12 && dir < 28) { const double* d = rec + kRefSplitDq + 12 * ((dir - 12) / 4) + (dir - 12) % 4; X.x.d = d[0]; X.y.d = d[4]; X.z.d = d[8]; }
   else if (dir >= d_obs_a && dir < d_obs_b) { sd.spline = 1; sd.knot = ka + (dir - d_obs_a) / 3; sd.comp = (dir - d_obs_a) % 3; }
   else if (dir >= d_obs_b && dir < d_tail) { sd.spline = 2; sd.knot = kb + (dir - d_obs_b) / 4; sd.comp = (dir - d_obs_b) % 4; }
   else if (dir == rho_dir) { X.x.d = rec[3]; X.y.d = rec[4]; X.z.d = rec[5]; rho.d = 1.0; }
-  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
-  const TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
   out.iterations = 0; out.dvt = 0.0;
   if (lifting) {
     const T t_obs = T(add_rn(add_rn(obs_t0, cam.time_offset), mul_rn(vt, cam.readout)), dir == vt_dir ? cam.readout : 0.0);
@@ -846,6 +863,29 @@ KB_HD int span_split_column(bool lifting, const SplitConst& sp, const CameraCons
     int stride;
     const int off = span_split_dir_offset(lifting, Wa, Wb, dir, stride);
     for (int rr = 0; rr < (lifting ? 3 : 2); ++rr) Jrow[off + rr * stride] = j[rr];
+  }
+  return 0;
+}
+
+// Column c (0..6) of the sensor blocks of a split span row into Js_row = [q_ct (nres x 4) | p_ct (nres x 3) | time offset (nres, zero)]
+KB_HD int span_split_sensor_column(bool lifting, const SplitConst& sp, const CameraConst& cam, const double* vecs, const double* quats, const double* so3pairs,
+                                   const double* ref_uv, double ref_t0, double rho, const double* obs_uv, double obs_t0, double vt, int ka, int Wa, int kb,
+                                   int Wb, double weight, double huber_c, int c, double* Js_row) {
+  const int nres = lifting ? 3 : 2;
+  SpanSplitRow o;
+  const int st = span_split_direction(lifting, sp, cam, vecs, quats, so3pairs, nullptr, obs_uv, obs_t0, ref_t0, vt, ka, Wa, kb, Wb, -1, o, c, ref_uv, rho);
+  if (st != 0) return st;
+  double r[3], j[3];
+  if (lifting) {
+    LiftingRow lo; lo.y[0] = o.y[0]; lo.y[1] = o.y[1]; lo.dy[0] = o.dy[0]; lo.dy[1] = o.dy[1]; lo.dvt = 0.0;
+    lifting_rs_finish(lo, cam, obs_uv, vt, weight, huber_c, r, j);
+  } else {
+    NewtonRow no; no.y[0] = o.y[0]; no.y[1] = o.y[1]; no.dy[0] = o.dy[0]; no.dy[1] = o.dy[1]; no.iterations = o.iterations;
+    newton_rs_finish(no, obs_uv, weight, huber_c, r, j);
+  }
+  for (int rr = 0; rr < nres; ++rr) {
+    if (c < 4) Js_row[4 * rr + c] = j[rr]; else Js_row[4 * nres + 3 * rr + (c - 4)] = j[rr];
+    if (c == 0) Js_row[7 * nres + rr] = 0.0;
   }
   return 0;
 }

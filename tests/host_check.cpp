@@ -261,6 +261,28 @@ void hc_span_rs_split(int lifting, double t0_r3, double dt_r3, int n_r3, double 
     idx[4 * i] = (int)rec[7]; idx[4 * i + 1] = ka; idx[4 * i + 2] = (int)rec[8]; idx[4 * i + 3] = kb;
   }
 }
+// ... and their sensor-block columns (relative pose of the camera): Js n x 16 / n x 24
+void hc_span_sensor_split(int lifting, double t0_r3, double dt_r3, int n_r3, double t0_so3, double dt_so3, int n_so3, const double* K, const double* Kinv,
+                          const double* q_ct, const double* p_ct, double time_offset, double max_time_offset, int locked, double readout, int rows,
+                          const double* vecs4, const double* quats, const double* pairs, int n, const double* obs_uv, const double* obs_t0,
+                          const double* ref_uv, const double* ref_t0, const int* lm_idx, const double* rho, const double* vt, const double* w,
+                          const double* huber_c, int Wa, int Wb, double* Js, int* status) {
+  SplitConst sp{t0_r3, dt_r3, n_r3, t0_so3, dt_so3, n_so3};
+  CameraConst cam;
+  for (int i = 0; i < 9; ++i) { cam.K[i] = K[i]; cam.Kinv[i] = Kinv[i]; }
+  camera_set_pose(cam, q_ct, p_ct);
+  cam.time_offset = time_offset; cam.row_delta = readout / (double)rows; cam.readout = readout; cam.max_time_offset = max_time_offset;
+  cam.time_offset_locked = locked;
+  finish_cam(cam, rows);
+  const int nres = lifting ? 3 : 2;
+  for (int i = 0; i < n; ++i) {
+    const int ka = span_window_base(sp.t0_r3, sp.dt_r3, obs_t0[i]), kb = span_window_base(sp.t0_so3, sp.dt_so3, obs_t0[i]);
+    status[i] = 0;
+    for (int c = 0; c < 7 && status[i] == 0; ++c)
+      status[i] = span_split_sensor_column(lifting != 0, sp, cam, vecs4, quats, pairs, ref_uv + 2 * i, ref_t0[i], rho[lm_idx[i]], obs_uv + 2 * i, obs_t0[i],
+                                           lifting ? vt[i] : 0.0, ka, Wa, kb, Wb, w[i], huber_c ? huber_c[i] : 0.0, c, Js + (size_t)8 * nres * i);
+  }
+}
 void hc_traj_eval_se3(double t0, double dt, int n_knots, int compat, const double* knots8, const double* pairs, int n, const double* t, double* out, int* status) {
   SplineConst sp{t0, dt, n_knots, compat};
   for (int i = 0; i < n; ++i) status[i] = traj_eval_se3(sp, knots8, pairs, t[i], out + 16 * i);

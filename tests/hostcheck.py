@@ -213,7 +213,7 @@ def static_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs
     return dict(r=r, J=J, idx=idx, status=st)
 
 
-def span_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, lifting=False, vt=None, w=None, huber_c=None):
+def span_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, lifting=False, vt=None, w=None, huber_c=None, sensor=False):
     """NewtonRs / LiftingRs rows on a split trajectory, packed [ref R3 4x(nres x 3) | ref SO3 4x(nres x 4) | obs R3 Wa x(..) | obs SO3 Wb x(..) | (vt) | rho];
     idx (n, 4) = ref R3 first knot, obs R3 span base, ref SO3 first knot, obs SO3 span base."""
     _set_camera_model(cam)
@@ -238,7 +238,15 @@ def span_rs_split(vecs3, dt_r3, t0_r3, quats, dt_so3, t0_so3, cam, obs_uv, obs_t
                            _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked),
                            C.c_double(cam.readout), int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0),
                            _p(lm_idx), _p(rho), _p(vt), _p(w), _p(hc), Wa, Wb, _p(r), _p(J), _p(idx), _p(st))
-    return dict(r=r, J=J, idx=idx, status=st, Wa=Wa, Wb=Wb, vt=vt)
+    Js = None
+    if sensor:
+        Js, st2 = np.zeros((n, 8 * nres)), np.zeros(n, np.int32)
+        lib().hc_span_sensor_split(int(bool(lifting)), C.c_double(t0_r3), C.c_double(dt_r3), len(v4), C.c_double(t0_so3), C.c_double(dt_so3), len(q4), _p(K), _p(Kinv),
+                                   _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset), C.c_double(cam.max_time_offset), int(cam.d_locked),
+                                   C.c_double(cam.readout), int(cam.rows), _p(v4), _p(q4), _p(pairs), n, _p(obs_uv), _p(obs_t0), _p(ref_uv), _p(ref_t0),
+                                   _p(lm_idx), _p(rho), _p(vt), _p(w), _p(hc), Wa, Wb, _p(Js), _p(st2))
+        assert (st2 == st).all()
+    return dict(r=r, J=J, idx=idx, status=st, Wa=Wa, Wb=Wb, vt=vt, Js=Js)
 
 
 def traj_eval_se3(knots7, dt, t0, t, compat=False):

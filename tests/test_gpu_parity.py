@@ -860,5 +860,58 @@ def test_span_camera_rows_on_split_trajectory_match_oracle(method, same_grid, ro
     dev = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags | _lib.EVAL_DEVICE_ORDER)[g]
     order = p.get_row_order(g)
     assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order]) and np.array_equal(dev["i0_d"], out["i0_d"][order])
-    with pytest.raises(NotImplementedError):
-        p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags | _lib.EVAL_LOCAL)
+    # KTK_EVAL_LOCAL: R3 blocks unchanged, SO3 blocks times dPlus/ddelta of their knots (k_span_localize_split)
+    from kontiki_b200.estimator import _quat_plus_jacobian
+    loc = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags | _lib.EVAL_LOCAL)[g]
+    tl = 2 if nres == 2 else 6
+    assert loc["J"].shape == (n, nres * 3 * (8 + Wa + Wb) + tl) and np.array_equal(loc["r"], out["r"])
+    Pq = _quat_plus_jacobian(c["quats"])
+    A, L = out["J"], loc["J"]
+    assert np.array_equal(L[:, :nres * 12], A[:, :nres * 12]) and np.array_equal(L[:, -tl:], A[:, -tl:])
+    assert np.array_equal(L[:, nres * 24:nres * (24 + 3 * Wa)], A[:, nres * 28:nres * (28 + 3 * Wa)])
+    kr = out["i0_c"][:, None] + np.arange(4)
+    ko = np.minimum(out["i0_d"][:, None] + np.arange(Wb), len(c["quats"]) - 1)
+    ref = np.einsum("nkra,nkad->nkrd", A[:, nres * 12:nres * 28].reshape(n, 4, nres, 4), Pq[kr])
+    assert parity.rel_err(L[:, nres * 12:nres * 24].reshape(n, 4, nres, 3), ref) < 1e-12
+    ref = np.einsum("nkra,nkad->nkrd", A[:, nres * (28 + 3 * Wa):-tl].reshape(n, Wb, nres, 4), Pq[ko])
+    assert parity.rel_err(L[:, nres * (24 + 3 * Wa):-tl].reshape(n, Wb, nres, 3), ref) < 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,robust", [("newton", True), ("lifting", False)])
+def test_span_camera_unlocked_relative_pose_on_split_trajectory(method, robust):
+    """... and the same sensor blocks when the trajectory is a SplitTrajectory (k_span_sensor, split branch)."""
+    c = _split_case(n_lm=100, scale_imu=10, same_grid=False)
+    cam = c["cam"]
+    rng = np.random.default_rng(6)
+    n = len(cam["lm_idx"])
+    cam["obs_uv"] += rng.normal(0, 1.0, cam["obs_uv"].shape)
+    cam["obs_uv"][:, 1] = np.clip(cam["obs_uv"][:, 1], 0, cam["rows"] - 1e-6)
+    p = _lib.Problem(0)
+    p.set_split_spline(c["dt_a"], c["t0_a"], len(c["vecs"]), c["dt_b"], c["t0_b"], len(c["quats"]))
+    q_ct, p_ct = fx.so3_exp_xyzw(np.array([0.1, -0.2, 0.05])), np.array([0.05, -0.02, 0.1])
+    add = p.add_newton_rs if method == "newton" else p.add_lifting_rs
+    g = add(_lib.make_camera(cam["rows"], cam["cols"], cam["readout"], cam["K"], q_ct=q_ct, p_ct=p_ct, q_locked=False, p_locked=False), cam["obs_uv"],
+            cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["weight"], cam["huber_c"])
+    traj = kto.Traj(kto.SPLIT, c["dt_a"], c["t0_a"], c["vecs"], c["dt_b"], c["t0_b"], c["quats"])
+    ocam = kto.Camera(cam["rows"], cam["cols"], cam["readout"], K=cam["K"], method="newton" if method == "newton" else "static", q_ct=q_ct, p_ct=p_ct,
+                      q_locked=False, p_locked=False)
+    nres = 2 if method == "newton" else 3
+    args = (cam["obs_uv"], cam["obs_t0"], cam["ref_uv"], cam["ref_t0"], cam["lm_idx"], cam["rho"])
+    if method == "lifting":
+        vt = np.clip(cam["obs_uv"][:, 1] / cam["rows"] + rng.uniform(-0.2, 0.2, n), 0.0, 1.0)
+        p.set_group_vt(g, vt)
+        o = kto.lifting_rs_residuals(traj, ocam, *args, vt=vt, weight=cam["weight"], jac_mode=2, cap=24)
+    else:
+        o = kto.static_rs_residuals(traj, ocam, *args, cam["weight"], jac_mode=2, cap=24)
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_SENSOR_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    out = p.evaluate((c["vecs"], c["quats"]), cam["rho"], flags)[g]
+    Jo = o["Js"].copy()
+    if robust:
+        for i in range(n):
+            cols = np.concatenate([Jo[i, :4 * nres].reshape(nres, 4), Jo[i, 4 * nres:7 * nres].reshape(nres, 3), Jo[i, 7 * nres:].reshape(nres, 1)], axis=1)
+            _, _, J2 = kto.huber_correct(cam["huber_c"][i], o["r"][i], cols)
+            Jo[i] = np.concatenate([J2[:, :4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7].reshape(-1)])
+    assert out["Js"].shape == (n, 8 * nres) and np.abs(Jo[:, :7 * nres]).max() > 1.0
+    assert parity.rel_err(out["Js"][:, None, :7 * nres], Jo[:, None, :7 * nres]) < parity.TOL
+    assert not out["Js"][:, 7 * nres:].any()

@@ -147,8 +147,17 @@ def test_split_span_camera_rows_match_oracle(lifting, atan, robust):
         o = kto.static_rs_residuals(traj, cam, *args, w, jac_mode=2, cap=24)
         tail_o = o["Jrho"]
     c = np.full(n, 2.0) if robust else None
-    h = hc.span_rs_split(vecs, 0.05, 0.0, quats, 0.04, 0.0, cam, *args, lifting=lifting, vt=vt, w=w, huber_c=c)
+    cam.q_locked = cam.p_locked = False          # the knot columns do not depend on the lock state; the oracle then also returns the sensor blocks
+    h = hc.span_rs_split(vecs, 0.05, 0.0, quats, 0.04, 0.0, cam, *args, lifting=lifting, vt=vt, w=w, huber_c=c, sensor=True)
     assert (h["status"] == 0).all()
+    o2 = kto.lifting_rs_residuals(traj, cam, *args, vt=vt, weight=w, jac_mode=2, cap=24) if lifting else kto.static_rs_residuals(traj, cam, *args, w, jac_mode=2, cap=24)
+    Jo = o2["Js"].copy()
+    if robust:
+        for i in range(n):
+            cols = np.concatenate([Jo[i, :4 * nres].reshape(nres, 4), Jo[i, 4 * nres:7 * nres].reshape(nres, 3), Jo[i, 7 * nres:].reshape(nres, 1)], axis=1)
+            _, _, J2 = kto.huber_correct(2.0, o2["r"][i], cols)
+            Jo[i] = np.concatenate([J2[:, :4].reshape(-1), J2[:, 4:7].reshape(-1), J2[:, 7].reshape(-1)])
+    assert np.abs(Jo[:, :7 * nres]).max() > 1.0 and parity.rel_err(h["Js"][:, None, :7 * nres], Jo[:, None, :7 * nres]) < parity.TOL
     idx = h["idx"]
     assert (idx[:, 0] == o["i0_ref_a"]).all() and (idx[:, 2] == o["i0_ref_b"]).all()
     Ja, Jb, tail = parity.scatter_span_split(h["J"], idx, o["ids_a"], o["ids_b"], h["Wa"], h["Wb"], nres)
