@@ -406,6 +406,47 @@ def main():
         step_device()
     p.synchronize()
     barrier()
+    strong_graph = None
+    if ne is not None and os.environ.get("KTK_STRONG_GRAPH", "1") != "0":
+        # The strong-scaling step is ~25 short kernels, three all-reduces and a dozen torch ops: with the rows split over 8 GPUs the device work
+        # shrinks to ~0.15 ms and the step was bound by the HOST issuing it (Python + ctypes launches, ~0.4 ms).  Every stretch between two
+        # collectives is captured once in a CUDA graph (kernels of the library + the torch ops; the library's own per-evaluation graph is off
+        # inside: graphs do not nest) and a step is 4 graph replays + 3 eager ncclAllReduce calls.  The collectives stay OUTSIDE the graphs.
+        try:
+            p.set_graphs(False)
+            lc0 = p.launch_count
+            step_device()
+            torch.cuda.synchronize()
+            launches_per_eager_step = p.launch_count - lc0      # kernels of the library in one step (the graphs replay exactly these)
+            barrier()
+            segments = [lambda: (ne.evaluate(cost=False), ne.linearize_local()),
+                        lambda: ne.linearize_rhs(GN_RADIUS),
+                        lambda: (ne.p.gn_call("pcg_begin", C.c_double(GN_RADIUS), C.c_double(1e-6), C.c_int32(100)), ne.p.gn_call("product")),
+                        lambda: ne.p.gn_call("pcg_update")]
+            graphs = []
+            for seg in segments:
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=stream):
+                    seg()
+                graphs.append(gph)
+            torch.cuda.synchronize()
+            reduces = [("lin",), ("qq",), ("qq",)]
+            eager_step = step_device
+
+            def step_device():      # noqa: F811  (the timed loops below call this name)
+                for k_, gph in enumerate(graphs):
+                    gph.replay()
+                    if k_ < 3:
+                        ne._reduce(*reduces[k_])
+            strong_graph = graphs
+            for _ in range(3):
+                step_device()
+            torch.cuda.synchronize()
+            barrier()
+        except Exception as e:      # capture refused: keep the eager step, say so
+            strong_graph = None
+            sys.stderr.write(f"strong-scaling step not captured in CUDA graphs: {e}\n")
+            p.set_graphs(True)
     l0 = p.launch_count
     # (1) the timed region: EXACTLY K steps between two events on the launching stream (each evaluation = one CUDA-graph launch), barrier +
     #     synchronize on both sides.  Nothing else runs on the host meanwhile: the nvidia-smi sampler (a fork per sample, and a driver query that
@@ -416,7 +457,7 @@ def main():
         step_device()
         ev[k + 1].record(stream)
     barrier()
-    launches = p.launch_count - l0
+    launches = p.launch_count - l0 if strong_graph is None else launches_per_eager_step * a.steps
     ms_total = ev[0].elapsed_time(ev[-1])
     per_step = np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)])
     with ClockSampler(local_rank) as clocks:
@@ -437,7 +478,7 @@ def main():
         #     roofline of the dominant kernel
         p.set_profiling(True)
         for _ in range(min(a.steps, 50)):
-            step_device()
+            (eager_step if strong_graph is not None else step_device)()
         p.synchronize()
         prof = {name: p.read_profile(g) for name, g in groups.items()}
         p.set_profiling(False)
@@ -468,11 +509,13 @@ def main():
             if dist is not None:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return float(t.item())
+        # the pieces are timed EAGERLY (host-issued, one call after the other): their sum exceeds the graph-replayed step by the host's issue time
         parts = {"evaluate": timed(lambda: ne.evaluate(cost=False)), "linearize": timed(lambda: gn_linearize(ne)), "schur_product": timed(lambda: gn_product(ne))}
         ar = {"linearize": ("lin",), "rhs": ("qq",), "product": ("qq",)}
         ar_bytes = {k_: int(sum(ne.buf(n_).numel() for n_ in v_) * 8) for k_, v_ in ar.items()}
         ar_ms = {k_: (timed(lambda v_=v_: ne._reduce(*v_), 50) if world > 1 else 0.0) for k_, v_ in ar.items()}
-        strong_info = {"collective": ("ncclAllReduce(sum, fp64) of parameter-sized buffers: landmark blocks + gradient + diagonal knot blocks once per linearisation, "
+        strong_info = {"cuda_graphs_between_collectives": strong_graph is not None,
+                       "collective": ("ncclAllReduce(sum, fp64) of parameter-sized buffers: landmark blocks + gradient + diagonal knot blocks once per linearisation, "
                                       "the reduced right-hand side once, S p once per CG iteration; each exchange is ONE collective on a contiguous buffer") if world > 1 else "none (one rank)",
                        "allreduce_bytes": ar_bytes, "allreduce_ms": ar_ms, "ms": parts, "rows_this_rank": int(n_meas), "rows_total": int(n_total),
                        "step": "evaluation + LM linearisation (c, g_rho, B_kk, gradient, reduced rhs, block-Jacobi preconditioner) + one implicit-Schur product and CG update"}

@@ -207,10 +207,20 @@ class DeviceSchurSolver:
 
     def linearize(self, radius):
         """Normal equations at the current point (the rows of the last evaluate() must be the current point's); returns max |gradient|."""
+        self.linearize_local()
+        self._reduce("lin")               # [c | grho | blocks_a | blocks_b | z_a | z_b] in ONE collective
+        gmax = self.linearize_rhs(radius)
+        self._reduce("qq")
+        return gmax
+
+    # the two rank-local halves of linearize(), callable on their own (bench.py captures each stretch between two collectives in a CUDA graph)
+    def linearize_local(self):
         import ctypes as C
         self.p.gn_call("linearize_local", C.c_void_p(self.knots.data_ptr()), C.c_void_p(self.rho.data_ptr()) if self.n_rho else None)
         self.p.gn_call("gradient_local")
-        self._reduce("lin")               # [c | grho | blocks_a | blocks_b | z_a | z_b] in ONE collective
+
+    def linearize_rhs(self, radius):
+        import ctypes as C
         gmax = torch.zeros(1, dtype=torch.float64, device=self.dev)
         for name, locked in (("z_a", self.lock_a), ("z_b", self.lock_b)):
             t = self.buf(name)
@@ -221,7 +231,6 @@ class DeviceSchurSolver:
             free = torch.ones_like(g) if self.lm_locked is None else torch.from_numpy(1.0 - np.asarray(self.lm_locked, np.float64)).to(self.dev)
             gmax = torch.maximum(gmax, (g * free).abs().max().reshape(1))
         self.p.gn_call("linearize_rhs", C.c_double(radius))
-        self._reduce("qq")
         return gmax
 
     def solve(self, radius, tol=1e-6, max_iter=300, check_every=8):
