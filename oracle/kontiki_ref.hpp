@@ -5,10 +5,13 @@
 // ceres::DynamicAutoDiffCostFunction).  Every function cites the reference file:line it follows;
 // paths are relative to /root/reference/cpplib/include/kontiki/.
 //
-// PARITY STATUS: values are pinned by the reference's own property tests
-// re-expressed in tests/test_oracle_pinning.py; JACOBIANS ARE "parity unpinned" -- no test of the
-// reference ever reads a Jacobian and Ceres/Sophus/Eigen cannot be built here -- they are by
-// construction the forward-mode derivative of these formulas (the reference's own definition).
+// PARITY STATUS.  The reference holds no golden vectors for this path and cannot be built here (Ceres 1.x,
+// Sophus, Eigen absent), so this restatement is pinned from two independent sides, values AND Jacobians:
+//   * the reference's own property tests, restated on its own fixture knots (tests/test_oracle_pinning.py, tests/fixtures_ref.py);
+//   * a 60-digit mpmath transcription of the reference headers written from the published Sophus / Eigen formulas, sharing no code
+//     with this file (tests/mp_reference.py): values directly, Jacobians by central differences of the 60-digit residual, SE3 poses
+//     also by 4x4 expm / logm (tests/test_oracle_independent.py; committed vectors tests/golden/mp_v1.npz, tests/test_mp_golden.py).
+// What stays an assumption is the semantics of the un-vendored dependencies themselves.
 #pragma once
 #include <memory>
 #include <sstream>

@@ -7,8 +7,8 @@
 //      measurements/accelerometer_measurement.h:77-108, measurements/static_rscamera_measurement.h:130-198)
 //   2. evaluation            = ceres::DynamicAutoDiffCostFunction<Residual>::Evaluate (double pass when no
 //      Jacobian is requested, ceil(#active/4) Jet<double,4> passes otherwise)
-// Only step 2 is timed (eval_seconds).  PARITY: values pinned by the reference's property tests,
-// Jacobians "parity unpinned" (see kontiki_ref.hpp header).
+// Only step 2 is timed (eval_seconds).  PARITY: values and Jacobians pinned by the reference's restated property tests and by the
+// independent 60-digit transcription tests/mp_reference.py (see kontiki_ref.hpp header).
 #include <chrono>
 #include <cstring>
 #include <string>
