@@ -2,19 +2,23 @@
 //
 // Kernels per evaluation point:
 //   k_pair_prepass   K0: n_knots x 7 (reference layout) -> 64-B knot records; omega_p = log(P_{p-1}^-1 P_p) and its 6x14 ambient Jacobian,
-//                    one thread per (pair, direction)
-//   k_imu<0|1>       gyroscope / accelerometer rows  (residual 3, packed Jacobian 4x3x7)
-//   k_landmark_ref   reference side of the static-RS rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
+//                    one thread per (pair, direction); clears the status word
+//   k_imu<0..3>      gyroscope / accelerometer / position / orientation rows (residual 3 or 1, packed Jacobian 4x3x7); k_short_batch runs all
+//                    IMU-like groups of a problem WITHOUT camera rows in one launch
+//   k_landmark_ref   reference side of the camera rows, ONCE per landmark reference: X, dX/drho, dX/d(4 knots)
 //   k_static_rs      static rolling-shutter camera rows (residual 2, packed Jacobian 2x(28+28+1)); the warp gathers its 32
-//                    landmark records into the row buffers with LDGSTS copies that overlap the observation-pose math, every
-//                    thread builds its whole 912-B row in shared memory and the row leaves with ONE TMA bulk store to the
-//                    caller's row index (one store per 32-row tile with KTK_EVAL_DEVICE_ORDER)
+//                    landmark records into the row buffers with LDGSTS copies and prefetches the row's knot / pair records into L1,
+//                    both under the observation-pose math; every thread builds its whole 912-B row in shared memory and the row
+//                    leaves with ONE TMA bulk store to the caller's row index (one store per 32-row tile with KTK_EVAL_DEVICE_ORDER)
 //   k_static_rs_local  the same rows in tangent coordinates (KTK_EVAL_LOCAL), staged in two halves and scattered cooperatively
-//   k_newton_rs      NewtonRsCameraMeasurement rows, one forward-mode direction per thread (newton_math.cuh)
+//   k_newton_rs_fast / k_newton_rs, k_lifting_rs   NewtonRs rows (closed form where the iteration stops at once, forward mode else), LiftingRs rows
+//   k_*_split        the same measurements on a split (R3 + SO3) trajectory; k_span_rs_split: NewtonRs / LiftingRs there (forward mode)
+//   k_imu_sensor, k_static_rs_sensor, k_span_sensor   columns of the sensors' own parameter blocks (KTK_EVAL_SENSOR_JACOBIANS); k_span_localize*: local rows
+//   k_gn_* (gn_device.cuh)   Gauss-Newton / LM step on the rows left in device memory
 // Measurement records are sorted once (first evaluation) by their first active knot so that a warp touches one or two
-// knot windows; IMU threads build their Jacobian row in shared memory, then the warp writes the 32 rows cooperatively
-// (16-byte chunks, one contiguous 672-B run per row) at the CALLER's row indices, so rows come out in insertion
-// order at full sector efficiency without a second pass.
+// knot windows; a thread builds its Jacobian row in shared memory and the finished row leaves with one TMA bulk store
+// (cp.async.bulk.global.shared::cta) at the CALLER's row index, so rows come out in insertion order without a second pass
+// (the short rows of the split IMU kernels and the local camera rows use a cooperative 16-byte scatter instead).
 #include <cuda_runtime.h>
 
 #include <algorithm>
