@@ -1107,7 +1107,9 @@ struct NewtonArgs {
 // is exactly the static row's Jacobian (bit for bit: tests/test_gpu_parity.py).  One thread per row runs the iteration once on values only;
 // single-evaluation rows get the closed-form static row (written into the span layout), the others are flagged for the forward-mode kernel.
 constexpr int kNewtonStage = 116;      // [Jref 56 | Jobs 56 | rho 2] + pad
-__global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* __restrict__ slow /* [0] = count, [1 + k] = row of the k-th slow row */) {
+__global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* __restrict__ slow /* [0] = count, [1 + k] = row of the k-th slow row */,
+                                                       double* __restrict__ slow_aux /* 6 per list slot: mode (0 forward mode, 2 two-evaluation row) | y(t_1) 2 | pi'(t_1) 2 */,
+                                                       int allow_two) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
   double* row = smem + lane * kNewtonStage;
@@ -1116,49 +1118,39 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
   const int row_len = 58 + 14 * a.W;
   int perm = -1, rel = 0;
   unsigned char slow_lane = 0;
+  double aux[4] = {0.0, 0.0, 0.0, 0.0};
+  int mode = -1;
   if (i < a.n) {
     const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
     const double obs_t0 = a.obs_t0[i], ref_t0 = a.ref_t0[i];
     const int ridx = a.ref_idx[i];
     const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
-    unsigned char is_slow = 1;
     if (ridx >= 0) {
-      const double* rec = a.recs + (size_t)ridx * kRefStride;
-      NewtonRow o;
-      const int st0 = ((int)rec[7] >= 0) ? newton_rs_direction(a.sp, a.cam, a.knots, a.pairs, rec, ouv, obs_t0, ref_t0, kbase, a.W, -1, o) : kStatusRange;
-      if (st0 == 0 && o.iterations == 1) {
-        ObsForward f; f.status = kStatusRange; f.io = -1;
-        double uo;
-        if (static_rs_row_locate_u(a.sp, a.cam, ouv, obs_t0, ref_t0, f.io, uo) && f.io >= kbase && f.io + 4 <= kbase + a.W) {
-          f.status = 0; f.bo = cumulative_basis(uo, a.sp.dt);
-          static_rs_row_pose(a.knots, a.pairs, f);
-          double r[2], jrho[2];
-          int ir = -1, io = -1;
-          ObsAdjoint adj;
-          for (int c = 0; c < kRefStride; ++c) row[kRefInRowDev + c] = rec[c];      // the record, where the in-place reference half expects it
-          const int st = static_rs_row_ref_half(a.cam, f, row + kRefInRowDev, ouv, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, row, jrho, &ir, &io, adj);
-          if (st == 0) {
-            static_rs_row_obs_half(a.knots, a.pairs, f, adj, row + kCamHalf);
-            row[112] = jrho[0]; row[113] = jrho[1];
-            is_slow = 0;
-            perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
-            rel = io - kbase;
-            const size_t dst = (size_t)perm;
-            if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
-            if (a.i0r) a.i0r[dst] = ir;
-            if (a.i0o) a.i0o[dst] = kbase;
-          }
-        }
+      double r[2];
+      int ir = -1;
+      mode = newton_rs_row_closed(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)ridx * kRefStride, ouv, obs_t0, ref_t0, kbase, a.W, a.w[i],
+                                  (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, allow_two != 0, row, r, &ir, &rel, aux);
+      if (mode >= 0) {
+        perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
+        const size_t dst = (size_t)perm;
+        if (a.r) { a.r[2 * dst] = r[0]; a.r[2 * dst + 1] = r[1]; }
+        if (a.i0r) a.i0r[dst] = ir;
+        if (a.i0o) a.i0o[dst] = kbase;
       }
     }
-    slow_lane = is_slow;
+    slow_lane = mode != 0;      // forward mode (-1) and two-evaluation rows (2: their columns still get the d t_1 / d theta term) go on the list
   }
   {   // compact list of the rows the forward-mode kernel has to do (their order in the list does not matter: rows are independent)
     const unsigned m = __ballot_sync(0xffffffffu, slow_lane != 0);
     int base = 0;
     if (lane == 0 && m) base = atomicAdd(slow, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (slow_lane) slow[1 + base + __popc(m & ((1u << lane) - 1u))] = i;
+    if (slow_lane) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      slow[1 + slot] = i;
+      double* ax = slow_aux + 6 * (size_t)slot;
+      ax[0] = mode == 2 ? 2.0 : 0.0; ax[1] = aux[0]; ax[2] = aux[1]; ax[3] = aux[2]; ax[4] = aux[3]; ax[5] = 0.0;
+    }
   }
   if (!wantJ) return;
   for (int rr = 0; rr < 32; ++rr) {
@@ -1177,13 +1169,37 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
   }
 }
 
-__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow) {
+// Rows of the list whose iteration stopped after its second evaluation (mode 2): k_newton_rs_fast wrote the static row at t_1; every column gets
+// + finish(pi'(t_1) d t_1 / d theta) from ONE dual evaluation at the initial row time (newton_math.cuh "newton_rs_two_step_column").
+__global__ void __launch_bounds__(128) k_newton_rs_two(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+  const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (int)(tid / ndir), dir = (int)(tid % ndir);
+  if (k >= a.n || k >= slow[0]) return;
+  const double* ax = slow_aux + 6 * (size_t)k;
+  if (ax[0] != 2.0 || !(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
+  const int i = slow[1 + k];
+  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+  const double obs_t0 = a.obs_t0[i];
+  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+  double j[2];
+  const int st = newton_rs_two_step_column(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)a.ref_idx[i] * kRefStride, ouv, obs_t0, a.ref_t0[i], kbase, a.W, a.w[i],
+                                           (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, ax + 1, dir, j);
+  int stride;
+  const int off = newton_dir_offset(dir, a.W, stride);
+  double* Jr = a.J + dst * row_len;
+  if (st != 0) { atomicMin(a.err, st); Jr[off] = nan(""); Jr[off + stride] = nan(""); }
+  else { Jr[off] += j[0]; Jr[off + stride] += j[1]; }
+}
+__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
   const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int i = (int)(tid / ndir);
   const int dir = (int)(tid % ndir);
   if (i >= a.n) return;
-  if (slow) { if (i >= slow[0]) return; i = slow[1 + i]; }      // only the rows the fast path left (compact list)
+  const double* ax = nullptr;
+  if (slow) { if (i >= slow[0]) return; ax = slow_aux + 6 * (size_t)i; i = slow[1 + i]; }      // only the rows the fast path left (compact list)
   const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
   if (!wantJ && dir != 0) return;
   const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
@@ -1191,6 +1207,7 @@ __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int
   const double obs_t0 = a.obs_t0[i];
   const int ridx = a.ref_idx[i];
   const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+  if (ax && ax[0] == 2.0) return;      // two-evaluation row: k_newton_rs_fast + k_newton_rs_two
   int st = kStatusRange;
   double r[2] = {nan(""), nan("")}, j[2] = {nan(""), nan("")};
   int ir = -1;
@@ -1299,6 +1316,7 @@ struct Group {
   DevBuf<double> o_Js;
   DevBuf<double> o_amb; DevBuf<int> o_amb_i0, o_amb_i0b;      // span cameras, KTK_EVAL_LOCAL: ambient rows / window indices before k_span_localize
   DevBuf<int> d_slow;             // Newton-RS rows that need the forward-mode kernel (more than one Newton evaluation): [count | row indices]
+  DevBuf<double> d_slow_aux;      // ... 6 doubles per list slot (k_newton_rs_fast)
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
   DevBuf<double> d_rr_uv, d_rr_t0, d_recs;
@@ -1331,7 +1349,8 @@ struct ktk_problem {
   bool graphs_enabled = true;
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   int imu_resident_tiles = 0;     // ... of the IMU-row kernels
-  bool newton_fast = true;        // KTK_NEWTON_FAST=0: every Newton-RS row through the forward-mode kernel (A/B, cross-check)
+  int newton_fast = 2;            // 2: rows that stop after one OR two evaluations in closed form (+ one dual evaluation per direction for the latter);
+                                  // 1: only one-evaluation rows; 0: every Newton-RS row through the forward-mode kernel (KTK_NEWTON_FAST, A/B and cross-check)
   // -1 (default): the IMU-like groups of an evaluation go out in ONE launch (k_short_batch) when the problem has no camera rows -- a chain of
   // one-wave kernels is launch-bound (C2 -2.6 %, C1: 3 kernels) -- and as one launch per group next to camera rows, where the fused launch measured
   // SLOWER under graph replay (H1 0.2648 -> 0.2571 ms, C4 0.2931 -> 0.2868 ms; profiles/r2x).  0 / 1: force; 2: + the landmark tables
@@ -1567,7 +1586,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   cudaFuncSetAttribute(k_short_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kAccelRowStride * 8);
   if (const char* v = getenv("KTK_FUSE_SHORT")) p->fuse_short = atoi(v);
-  if (const char* v = getenv("KTK_NEWTON_FAST")) p->newton_fast = atoi(v) != 0;
+  if (const char* v = getenv("KTK_NEWTON_FAST")) p->newton_fast = atoi(v);
   cudaFuncSetAttribute(k_newton_rs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kNewtonStage * 8);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
     int per_sm = 0;
@@ -1846,7 +1865,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       KTK_CUDA(cudaStreamSynchronize(s));
       g->vt_dirty = false;
     }
-    if (g->kind == KTK_NEWTON_RS && g->n > 0 && (st = g->d_slow.resize((size_t)g->n + 1))) return st;
+    if (g->kind == KTK_NEWTON_RS && g->n > 0 && ((st = g->d_slow.resize((size_t)g->n + 1)) || (st = g->d_slow_aux.resize((size_t)6 * g->n)))) return st;
     if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL) && (flags & KTK_EVAL_JACOBIANS) && g->n > 0) {      // scratch of k_span_localize (outside any capture)
       if ((st = g->o_amb.resize((size_t)g->n * row_doubles(p, *g)))) return st;
       if ((st = g->o_amb_i0.resize((size_t)g->n)) || (st = g->o_amb_i0b.resize((size_t)g->n))) return st;
@@ -1957,10 +1976,11 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         if (p->newton_fast) {
           cudaMemsetAsync(g.d_slow.p, 0, sizeof(int), s);
-          k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p);
+          k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p, g.d_slow_aux.p, p->newton_fast >= 2 ? 1 : 0);
           p->launches += 1;
         }
-        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr);
+        if (p->newton_fast >= 2) { k_newton_rs_two<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr, g.d_slow_aux.p);
       }
       if (localize) {
         const int nres = g.kind == KTK_LIFTING_RS ? 3 : 2, tail = g.kind == KTK_LIFTING_RS ? 6 : 2;

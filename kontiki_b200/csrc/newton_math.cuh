@@ -183,86 +183,145 @@ template <class T> KB_HD void camera_project_t(const CameraConst& cam, const TV3
 //   28 + 7 W           rho
 //   anything else      values only
 // Returns 0 or kStatusRange; y = projection y_out (2), dy = its derivative along the seed.
-struct NewtonRow { double y[2], dy[2]; int iterations; };
+struct NewtonRow { double y[2], dy[2]; int iterations; double t_last; int clamped_last; };      // t_last: row time of the LAST evaluation (the one y comes from)
+// The seeds of one direction: the landmark X and rho (reference side, from the record), the observation knot / component that carries the unit
+// derivative, the camera's relative pose (plain values here).
+struct NewtonSeeds { TV3<D1> X; D1 rho; int ok, oc; TQ<D1> qct; TV3<D1> pct; };
+KB_HD NewtonSeeds newton_seeds(const CameraConst& cam, const double* rec, int kbase, int W, int dir) {
+  typedef D1 T;
+  NewtonSeeds sd;
+  const int rho_dir = 28 + 7 * W;
+  // record: X(3) | dX/drho(3) | rho | i0_ref | dX/dknots [4][3][7]
+  sd.X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
+  sd.rho = T(rec[6]);
+  if (dir >= 0 && dir < 28) { const double* d = rec + kRefDOff + 21 * (dir / 7) + dir % 7; sd.X.x.d = d[0]; sd.X.y.d = d[7]; sd.X.z.d = d[14]; }
+  else if (dir == rho_dir) { sd.X.x.d = rec[3]; sd.X.y.d = rec[4]; sd.X.z.d = rec[5]; sd.rho.d = 1.0; }
+  sd.ok = (dir >= 28 && dir < rho_dir) ? kbase + (dir - 28) / 7 : -1;      // observation-window knot of this direction
+  sd.oc = (dir - 28) % 7;
+  sd.qct.x = T(cam.q_ct[0]); sd.qct.y = T(cam.q_ct[1]); sd.qct.z = T(cam.q_ct[2]); sd.qct.w = T(cam.q_ct[3]);
+  sd.pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  return sd;
+}
+// ONE evaluation of the iteration's body (newton_rscamera_measurement.h:62-103) at row time t_obs: projection y, f and df on the dual number.
+struct NewtonEval { D1 y[2], f, df; };
+KB_HD int newton_rs_eval(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, int nseg, const Segment& s0, const Segment& s1,
+                         const NewtonSeeds& sd, int kbase, int W, double t0_obs, D1 t_obs, NewtonEval& e) {
+  typedef D1 T;
+  const double rows = (double)cam.rows;
+  // trajectory.Evaluate(t_obs): SplineView::Evaluate + CalculateIndexAndInterpolationAmount (floor drops the derivative)
+  int i0; double u0;
+  if (locate_in_segments(nseg, s0, s1, t_obs.a, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
+  if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;               // outside the observation span's knots
+  const T u = T(u0, t_obs.d / sp.dt);
+  const T u2 = u * u, u3 = u2 * u;
+  const double di = 1.0 / sp.dt;
+  T B[3], dB[3];
+  B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
+  B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
+  B[2] = u3 * T(1.0 / 6.0);
+  dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
+  dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
+  dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
+  T k0[7], om[3][6];
+  const double* kn = knots + (size_t)i0 * kKnotStride;
+#pragma unroll
+  for (int c = 0; c < 7; ++c) k0[c] = T(kn[c], (sd.ok == i0 && sd.oc == c) ? 1.0 : 0.0);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int p = i0 + 1 + j;                                              // pair (knot p-1, knot p)
+    const double* pr = pairs + (size_t)p * kPairStride;
+    const double* D = sd.ok == p - 1 ? pr + kPairDOff : (sd.ok == p ? pr + kPairDOff + kPairSide : nullptr);
+#pragma unroll
+    for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m], D ? D[m * 8 + sd.oc] : 0.0);
+  }
+  const TEval<T> ev = se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
+  // :66-96
+  TQ<T> wq; wq.x = ev.w.x; wq.y = ev.w.y; wq.z = ev.w.z; wq.w = T(0.0);
+  TQ<T> dq = tqmul(wq, ev.q); dq.x = T(0.5) * dq.x; dq.y = T(0.5) * dq.y; dq.z = T(0.5) * dq.z; dq.w = T(0.5) * dq.w;
+  const TQ<T> dq_inv = tqconj(dq), q_inv = tqconj(ev.q);
+  const TV3<T> s = sd.X - sd.rho * ev.p;
+  const TV3<T> ds = (T(0.0) - sd.rho) * ev.v;
+  const TV3<T> X_obs = tqrot(q_inv, s);
+  const TV3<T> X_cam = tqrot(sd.qct, X_obs) + sd.rho * sd.pct;
+  TQ<T> sq; sq.x = s.x; sq.y = s.y; sq.z = s.z; sq.w = T(0.0);
+  TQ<T> dsq; dsq.x = ds.x; dsq.y = ds.y; dsq.z = ds.z; dsq.w = T(0.0);
+  const TQ<T> a1 = tqmul(tqmul(dq_inv, sq), ev.q), a2 = tqmul(tqmul(q_inv, dsq), ev.q), a3 = tqmul(tqmul(q_inv, sq), dq);
+  const TV3<T> dX_obs = tv3<T>(a1.x + a2.x + a3.x, a1.y + a2.y + a3.y, a1.z + a2.z + a3.z);
+  const TV3<T> dX_cam = tqrot(sd.qct, dX_obs) + sd.rho * sd.pct;                    // sic (:92)
+  T dy[2];
+  camera_project_t<T>(cam, X_cam, dX_cam, e.y, dy);
+  // :101-104
+  e.f = e.y[1] - (T(rows) * (t_obs - T(t0_obs)) / T(cam.readout));
+  e.df = dy[1] - T(rows / cam.readout);
+  return 0;
+}
 KB_HD int newton_rs_direction(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
                               const double* obs_uv, double obs_t0, double ref_t0, int kbase, int W, int dir, NewtonRow& out) {
   typedef D1 T;
   Segment s0, s1;
   const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
   if (nseg == 0) return kStatusRange;
-  const int rho_dir = 28 + 7 * W;
-  // seeds of the reference side (record: X(3) | dX/drho(3) | rho | i0_ref | dX/dknots [4][3][7])
-  TV3<T> X = tv3<T>(T(rec[0]), T(rec[1]), T(rec[2]));
-  T rho = T(rec[6]);
-  if (dir >= 0 && dir < 28) { const double* d = rec + kRefDOff + 21 * (dir / 7) + dir % 7; X.x.d = d[0]; X.y.d = d[7]; X.z.d = d[14]; }
-  else if (dir == rho_dir) { X.x.d = rec[3]; X.y.d = rec[4]; X.z.d = rec[5]; rho.d = 1.0; }
-  const int ok = (dir >= 28 && dir < rho_dir) ? kbase + (dir - 28) / 7 : -1;      // observation-window knot of this direction
-  const int oc = (dir - 28) % 7;
-  TQ<T> qct; qct.x = T(cam.q_ct[0]); qct.y = T(cam.q_ct[1]); qct.z = T(cam.q_ct[2]); qct.w = T(cam.q_ct[3]);
-  const TV3<T> pct = tv3<T>(T(cam.p_ct[0]), T(cam.p_ct[1]), T(cam.p_ct[2]));
+  const NewtonSeeds sd = newton_seeds(cam, rec, kbase, W, dir);
   // newton_rscamera_measurement.h:37-58
   const double rows = (double)cam.rows;
   const double t0_obs = add_rn(obs_t0, cam.time_offset);
   T t_obs = T(static_rs_time(cam, obs_t0, obs_uv[1]));                      // not FMA-contracted: it fixes the first knot index
   const double max_dt = 0.5 * cam.readout / rows, max_dt2 = max_dt * max_dt;
   const double min_bound = t0_obs, max_bound = add_rn(t0_obs, cam.readout);
-  T y[2] = {T(0.0), T(0.0)};
-  out.iterations = 0;
+  NewtonEval e; e.y[0] = T(0.0); e.y[1] = T(0.0);
+  out.iterations = 0; out.clamped_last = 0; out.t_last = t_obs.a;
+  int clamped = 0;
   for (int iter = 0; iter < 5; ++iter) {
-    // trajectory.Evaluate(t_obs): SplineView::Evaluate + CalculateIndexAndInterpolationAmount (floor drops the derivative)
-    int i0; double u0;
-    if (locate_in_segments(nseg, s0, s1, t_obs.a, sp.t0, sp.dt, i0, u0) < 0) return kStatusRange;
-    if (i0 < kbase || i0 + 4 > kbase + W) return kStatusRange;               // outside the observation span's knots
-    const T u = T(u0, t_obs.d / sp.dt);
-    const T u2 = u * u, u3 = u2 * u;
-    const double di = 1.0 / sp.dt;
-    T B[3], dB[3];
-    B[0] = (T(5.0) + T(3.0) * u - T(3.0) * u2 + u3) * T(1.0 / 6.0);
-    B[1] = (T(1.0) + T(3.0) * u + T(3.0) * u2 - T(2.0) * u3) * T(1.0 / 6.0);
-    B[2] = u3 * T(1.0 / 6.0);
-    dB[0] = T(di) * (T(3.0) - T(6.0) * u + T(3.0) * u2) * T(1.0 / 6.0);
-    dB[1] = T(di) * (T(3.0) + T(6.0) * u - T(6.0) * u2) * T(1.0 / 6.0);
-    dB[2] = T(di) * (T(3.0) * u2) * T(1.0 / 6.0);
-    T k0[7], om[3][6];
-    const double* kn = knots + (size_t)i0 * kKnotStride;
-#pragma unroll
-    for (int c = 0; c < 7; ++c) k0[c] = T(kn[c], (ok == i0 && oc == c) ? 1.0 : 0.0);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const int p = i0 + 1 + j;                                              // pair (knot p-1, knot p)
-      const double* pr = pairs + (size_t)p * kPairStride;
-      const double* D = ok == p - 1 ? pr + kPairDOff : (ok == p ? pr + kPairDOff + kPairSide : nullptr);
-#pragma unroll
-      for (int m = 0; m < 6; ++m) om[j][m] = T(pr[m], D ? D[m * 8 + oc] : 0.0);
-    }
-    const TEval<T> ev = se3_eval_t<T>(k0, om[0], om[1], om[2], B, dB);
-    // :66-96
-    TQ<T> wq; wq.x = ev.w.x; wq.y = ev.w.y; wq.z = ev.w.z; wq.w = T(0.0);
-    TQ<T> dq = tqmul(wq, ev.q); dq.x = T(0.5) * dq.x; dq.y = T(0.5) * dq.y; dq.z = T(0.5) * dq.z; dq.w = T(0.5) * dq.w;
-    const TQ<T> dq_inv = tqconj(dq), q_inv = tqconj(ev.q);
-    const TV3<T> s = X - rho * ev.p;
-    const TV3<T> ds = (T(0.0) - rho) * ev.v;
-    const TV3<T> X_obs = tqrot(q_inv, s);
-    const TV3<T> X_cam = tqrot(qct, X_obs) + rho * pct;
-    TQ<T> sq; sq.x = s.x; sq.y = s.y; sq.z = s.z; sq.w = T(0.0);
-    TQ<T> dsq; dsq.x = ds.x; dsq.y = ds.y; dsq.z = ds.z; dsq.w = T(0.0);
-    const TQ<T> a1 = tqmul(tqmul(dq_inv, sq), ev.q), a2 = tqmul(tqmul(q_inv, dsq), ev.q), a3 = tqmul(tqmul(q_inv, sq), dq);
-    const TV3<T> dX_obs = tv3<T>(a1.x + a2.x + a3.x, a1.y + a2.y + a3.y, a1.z + a2.z + a3.z);
-    const TV3<T> dX_cam = tqrot(qct, dX_obs) + rho * pct;                    // sic (:92)
-    T dy[2];
-    camera_project_t<T>(cam, X_cam, dX_cam, y, dy);
-    // :101-117
-    const T f = y[1] - (T(rows) * (t_obs - T(t0_obs)) / T(cam.readout));
-    const T df = dy[1] - T(rows / cam.readout);
-    const T dt = f / df;
+    out.t_last = t_obs.a; out.clamped_last = clamped;
+    const int st = newton_rs_eval(sp, cam, knots, pairs, nseg, s0, s1, sd, kbase, W, t0_obs, t_obs, e);
+    if (st != 0) return st;
+    // :105-117
+    const T dt = e.f / e.df;
     t_obs = t_obs - dt;
     out.iterations = iter + 1;
     if (dt.a * dt.a < max_dt2) break;
-    if (t_obs.a < min_bound) t_obs = T(min_bound);
-    else if (t_obs.a > max_bound) t_obs = T(max_bound);
+    clamped = 0;
+    if (t_obs.a < min_bound) { t_obs = T(min_bound); clamped = 1; }
+    else if (t_obs.a > max_bound) { t_obs = T(max_bound); clamped = 1; }
   }
-  out.y[0] = y[0].a; out.y[1] = y[1].a; out.dy[0] = y[0].d; out.dy[1] = y[1].d;
+  out.y[0] = e.y[0].a; out.y[1] = e.y[1].a; out.dy[0] = e.y[0].d; out.dy[1] = e.y[1].d;
   return 0;
+}
+// Rows whose iteration stops after its SECOND evaluation (nearly all rows that iterate at all: the first step lands within a fraction of a
+// row) do not need forward mode through both evaluations: y_out = pi(theta, t_1(theta)) with t_1 = t_0 - f/df at t_0, so
+//   d y_out / d theta = d pi / d theta at t_1 (the static row at t_1, closed form)  +  pi'(t_1) * d t_1 / d theta,
+// and only d t_1 / d theta = -d(f/df)/d theta at t_0 needs the dual number: ONE evaluation per direction instead of two.
+// (a) d(f/df)/d theta along `dir` at the initial row time:
+KB_HD int newton_rs_first_step_d(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                 const double* obs_uv, double obs_t0, double ref_t0, int kbase, int W, int dir, double& dtd) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const NewtonSeeds sd = newton_seeds(cam, rec, kbase, W, dir);
+  NewtonEval e;
+  const int st = newton_rs_eval(sp, cam, knots, pairs, nseg, s0, s1, sd, kbase, W, add_rn(obs_t0, cam.time_offset), D1(static_rs_time(cam, obs_t0, obs_uv[1])), e);
+  if (st != 0) return st;
+  dtd = (e.f / e.df).d;
+  return 0;
+}
+// (b) pi'(t): the TRUE time derivative of the projection at row time t (not the hand-written dy of :76-96, which carries the rho p_ct slip)
+KB_HD int newton_rs_time_derivative(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                    double obs_t0, double ref_t0, int kbase, int W, double t, double* pd) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const NewtonSeeds sd = newton_seeds(cam, rec, kbase, W, -1);
+  NewtonEval e;
+  const int st = newton_rs_eval(sp, cam, knots, pairs, nseg, s0, s1, sd, kbase, W, add_rn(obs_t0, cam.time_offset), D1(t, 1.0), e);
+  if (st != 0) return st;
+  pd[0] = e.y[0].d; pd[1] = e.y[1].d;
+  return 0;
+}
+// (c) first knot and interpolation amount at an arbitrary row time inside the residual's spans (what the closed-form row at t_1 is built on)
+KB_HD bool newton_locate(const SplineConst& sp, const CameraConst& cam, double obs_t0, double ref_t0, double t, int& io, double& uo) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  return nseg != 0 && locate_in_segments(nseg, s0, s1, t, sp.t0, sp.dt, io, uo) >= 0;
 }
 
 // Knots of the observation span {t0_obs - 1e-3, t0_obs + readout + 1e-3} of the residual (newton_rscamera_measurement.h:210-236,
@@ -305,6 +364,75 @@ KB_HD int newton_rs_row(const SplineConst& sp, const CameraConst& cam, const dou
     const int off = newton_dir_offset(dir, W, stride);
     J[off] = j[0]; J[off + stride] = j[1];
     *iterations = o.iterations;
+  }
+  return 0;
+}
+
+// The closed-form part of a Newton-RS row (what k_newton_rs_fast does per row).  `row`: 114 staged doubles [Jref 56 | Jobs 56 | rho 2] (the landmark
+// record is copied to row + 22 and rewritten in place like in k_static_rs).  Returns
+//    0  the iteration stopped after ONE evaluation: the row is the static row at the observed row time, complete;
+//    2  it stopped after TWO: `row` holds the static row at t_1 and aux = {y(t_1) (2), pi'(t_1) (2)}; every column still needs
+//       + finish(pi'(t_1) * d t_1 / d theta)  with  d t_1 / d theta = -newton_rs_first_step_d  (zero when t_1 was clamped to the readout interval);
+//   -1  anything else: the row goes through forward mode (newton_rs_direction per direction).
+// rel = position of the row's four active observation knots inside the span (first active knot - kbase).
+KB_HD int newton_rs_row_closed(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* ouv,
+                               double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, bool allow_two, double* row, double* r,
+                               int* ir_out, int* rel, double* aux) {
+  NewtonRow o;
+  if ((int)rec[7] < 0 || newton_rs_direction(sp, cam, knots, pairs, rec, ouv, obs_t0, ref_t0, kbase, W, -1, o) != 0) return -1;
+  if (!(o.iterations == 1 || (allow_two && o.iterations == 2))) return -1;
+  ObsForward f; f.status = kStatusRange; f.io = -1;
+  double uo;
+  const bool ok = o.iterations == 1 ? static_rs_row_locate_u(sp, cam, ouv, obs_t0, ref_t0, f.io, uo) : newton_locate(sp, cam, obs_t0, ref_t0, o.t_last, f.io, uo);
+  if (!ok || f.io < kbase || f.io + 4 > kbase + W) return -1;
+  f.status = 0; f.bo = cumulative_basis(uo, sp.dt);
+  static_rs_row_pose(knots, pairs, f);
+  double jrho[2];
+  int ir = -1, io = -1;
+  ObsAdjoint adj;
+  for (int c = 0; c < kRefStride; ++c) row[22 + c] = rec[c];
+  if (static_rs_row_ref_half(cam, f, row + 22, ouv, weight, huber_c, r, row, jrho, &ir, &io, adj) != 0) return -1;
+  static_rs_row_obs_half(knots, pairs, f, adj, row + 56);
+  row[112] = jrho[0]; row[113] = jrho[1];
+  *ir_out = ir; *rel = io - kbase;
+  if (o.iterations == 1) return 0;
+  aux[0] = o.y[0]; aux[1] = o.y[1]; aux[2] = 0.0; aux[3] = 0.0;
+  if (!o.clamped_last && newton_rs_time_derivative(sp, cam, knots, pairs, rec, obs_t0, ref_t0, kbase, W, o.t_last, aux + 2) != 0) return -1;
+  return 2;
+}
+// ... and the correction of one column of such a row (mode 2): j (2) to ADD at newton_dir_offset(dir)
+KB_HD int newton_rs_two_step_column(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* ouv,
+                                    double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, const double* aux, int dir, double* j) {
+  j[0] = j[1] = 0.0;
+  if (aux[2] == 0.0 && aux[3] == 0.0) return 0;
+  double dtd;
+  const int st = newton_rs_first_step_d(sp, cam, knots, pairs, rec, ouv, obs_t0, ref_t0, kbase, W, dir, dtd);
+  if (st != 0) return st;
+  NewtonRow oo; oo.y[0] = aux[0]; oo.y[1] = aux[1]; oo.dy[0] = -aux[2] * dtd; oo.dy[1] = -aux[3] * dtd; oo.iterations = 2;      // d t_1 = -d(f/df)
+  double r[2];
+  newton_rs_finish(oo, ouv, weight, huber_c, r, j);
+  return 0;
+}
+// A whole row the way the two kernels produce it (host check): closed form where the iteration stops after one or two evaluations.
+KB_HD int newton_rs_row_fast(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* obs_uv,
+                             double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, double* r, double* J, int* iterations) {
+  double row[114], aux[4];
+  int ir = -1, rel = 0;
+  const int mode = newton_rs_row_closed(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, true, row, r, &ir, &rel, aux);
+  if (mode < 0) return newton_rs_row(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, r, J, iterations);
+  const int row_len = 58 + 14 * W;
+  for (int c = 0; c < row_len; ++c) J[c] = 0.0;
+  for (int c = 0; c < 56; ++c) { J[c] = row[c]; J[56 + 14 * rel + c] = row[56 + c]; }
+  J[56 + 14 * W] = row[112]; J[57 + 14 * W] = row[113];
+  *iterations = mode == 0 ? 1 : 2;
+  if (mode == 2) {
+    for (int dir = 0; dir < 29 + 7 * W; ++dir) {
+      double j[2]; int stride;
+      const int st = newton_rs_two_step_column(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, aux, dir, j);
+      if (st != 0) return st;
+      const int off = newton_dir_offset(dir, W, stride);
+      J[off] += j[0]; J[off + stride] += j[1];
+    }
   }
   return 0;
 }

@@ -80,7 +80,7 @@ def newton_window(t0, dt, readout, obs_t0):
     return max(int(lib().hc_newton_window(t0, dt, readout, float(t))) for t in np.atleast_1d(obs_t0))
 
 
-def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None):
+def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, w=None, huber_c=None, fast=False):
     """NewtonRsCameraMeasurement rows in the packed layout [ref 4x(2x7) | obs W x(2x7) | rho 2]; W = widest observation span."""
     _set_camera_model(cam)
     k8, pairs = prepass(knots7)
@@ -93,6 +93,7 @@ def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
     K = _f(cam.K).reshape(-1)
     Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
     W = newton_window(t0, dt, cam.readout, obs_t0)
+    lib().hc_set_newton_fast(int(bool(fast)))      # fast: the rows as k_newton_rs_fast + k_newton_rs produce them (closed form for one / two evaluations)
     r, J = np.zeros((n, 2)), np.zeros((n, 58 + 14 * W))
     ir, kb, it, st = (np.zeros(n, np.int32) for _ in range(4))
     lib().hc_newton_rs(C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset),

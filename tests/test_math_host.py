@@ -250,6 +250,14 @@ def test_newton_rs_rows_match_oracle(dt, atan):
     assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
     it = np.bincount(h["iterations"], minlength=6)
     assert it[1] > 0 and it[2:].sum() > 0          # rows that stop after one step AND rows that iterate
+    # ... and the rows as the two kernels produce them: closed form where the iteration stops after one or two evaluations (static row at
+    # t_1 + pi'(t_1) d t_1 / d theta, one dual evaluation per direction instead of two)
+    hf = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], fast=True)
+    assert (hf["status"] == 0).all() and (hf["i0_ref"] == o["i0_ref_a"]).all()
+    assert np.abs(hf["r"] - o["r"]).max() < parity.CAM_R_TOL
+    Jf, Jrf = parity.scatter_cam(hf["J"], hf["i0_ref"], hf["i0_obs"], o["ids_a"], hf["W"])
+    assert parity.rel_err(Jf, o["Ja"]) < parity.TOL and parity.rel_err(Jrf, o["Jrho"]) < parity.TOL
+    assert (h["iterations"] == 2).sum() > 5
 
 
 def test_newton_rs_one_step_rows_equal_static_rows():
@@ -276,15 +284,16 @@ def test_newton_rs_huber_corrector_matches_oracle():
     n = len(s["lm_idx"])
     o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
                                 s["weight"], jac_mode=2, cap=24)
-    h = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], huber_c=np.full(n, 5.0))
-    for i in range(n):
-        m = int((o["ids_a"][i] >= 0).sum())
-        Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
-        _, r2, J2 = kto.huber_correct(5.0, o["r"][i], Jfull)
-        Js, Jr = parity.scatter_cam(h["J"][i:i + 1], h["i0_ref"][i:i + 1], h["i0_obs"][i:i + 1], o["ids_a"][i:i + 1], h["W"])
-        Jmine = np.concatenate([Js[0, k] for k in range(m)] + [Jr[0].reshape(2, 1)], axis=1)
-        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
-        assert np.abs(h["r"][i] - r2).max() <= parity.CAM_R_TOL
+    for fast in (False, True):
+        h = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], huber_c=np.full(n, 5.0), fast=fast)
+        for i in range(n):
+            m = int((o["ids_a"][i] >= 0).sum())
+            Jfull = np.concatenate([o["Ja"][i, k] for k in range(m)] + [o["Jrho"][i].reshape(2, 1)], axis=1)
+            _, r2, J2 = kto.huber_correct(5.0, o["r"][i], Jfull)
+            Js, Jr = parity.scatter_cam(h["J"][i:i + 1], h["i0_ref"][i:i + 1], h["i0_obs"][i:i + 1], o["ids_a"][i:i + 1], h["W"])
+            Jmine = np.concatenate([Js[0, k] for k in range(m)] + [Jr[0].reshape(2, 1)], axis=1)
+            assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+            assert np.abs(h["r"][i] - r2).max() <= parity.CAM_R_TOL
 
 
 def test_position_rows_match_oracle():
