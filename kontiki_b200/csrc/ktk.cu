@@ -1173,11 +1173,13 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
 // + finish(pi'(t_1) d t_1 / d theta) from ONE dual evaluation at the initial row time (newton_math.cuh "newton_rs_two_step_column").
 __global__ void __launch_bounds__(128) k_newton_rs_two(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
   const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (!(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
+  // the list's length is only known on the device: a fixed grid strides over (listed rows) x (directions) instead of launching n x ndir threads
+  const long long total = (long long)slow[0] * ndir;
+  for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) {
   const int k = (int)(tid / ndir), dir = (int)(tid % ndir);
-  if (k >= a.n || k >= slow[0]) return;
   const double* ax = slow_aux + 6 * (size_t)k;
-  if (ax[0] != 2.0 || !(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
+  if (ax[0] != 2.0) continue;
   const int i = slow[1 + k];
   const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
   const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
@@ -1191,10 +1193,53 @@ __global__ void __launch_bounds__(128) k_newton_rs_two(const NewtonArgs a, const
   double* Jr = a.J + dst * row_len;
   if (st != 0) { atomicMin(a.err, st); Jr[off] = nan(""); Jr[off + stride] = nan(""); }
   else { Jr[off] += j[0]; Jr[off + stride] += j[1]; }
+  }
 }
-__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+// The same correction, one WARP per listed row and 32 dual evaluations instead of 29 + 7 W (newton_math.cuh "newton_rs_first_step_lane"): lanes 0..27 the
+// four observation knots active at the initial row time, lanes 28..31 the gradient of f/df with respect to the landmark X and rho, from which the 28
+// reference-window columns and the rho column follow by the chain rule through the landmark record.  Lane L < 28 writes its observation column and
+// reference column L, lane 28 the rho column: every column has one writer, no atomics.
+__global__ void __launch_bounds__(128) k_newton_rs_two_w(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+  if (!(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
+  const int row_len = 58 + 14 * a.W, lane = threadIdx.x & 31;
+  const int nlist = slow[0], wstride = (int)((gridDim.x * blockDim.x) >> 5);
+  for (int k = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); k < nlist; k += wstride) {
+    const double* ax = slow_aux + 6 * (size_t)k;
+    if (ax[0] != 2.0 || (ax[3] == 0.0 && ax[4] == 0.0)) continue;      // not a two-evaluation row / t_1 clamped: no correction (warp-uniform)
+    const int i = slow[1 + k];
+    const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
+    const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+    const double obs_t0 = a.obs_t0[i], weight = a.w[i], huber_c = (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0;
+    const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+    const double* rec = a.recs + (size_t)a.ref_idx[i] * kRefStride;
+    int io = kbase;
+    double dtd = 0.0;
+    const int st = newton_rs_first_step_lane(a.sp, a.cam, a.knots, a.pairs, rec, ouv, obs_t0, a.ref_t0[i], kbase, a.W, lane, &io, dtd);
+    double g[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) g[c] = __shfl_sync(0xffffffffu, dtd, 28 + c);
+    double* Jr = a.J + dst * row_len;
+    if (st != 0) {                                                        // the row time is outside the span for every lane alike
+      if (lane == 0) atomicMin(a.err, st);
+      for (int c = lane; c < row_len; c += 32) Jr[c] = nan("");
+      continue;
+    }
+    double j[2];
+    int stride;
+    if (lane < 28) {
+      newton_rs_two_step_finish(ouv, weight, huber_c, ax + 1, dtd, j);
+      const int off = newton_dir_offset(28 + 7 * (io - kbase) + lane, a.W, stride);
+      Jr[off] += j[0]; Jr[off + stride] += j[1];
+    }
+    if (lane < 29) {
+      newton_rs_two_step_finish(ouv, weight, huber_c, ax + 1, newton_rs_ref_chain(rec, g, lane), j);
+      const int off = newton_dir_offset(lane < 28 ? lane : 28 + 7 * a.W, a.W, stride);
+      Jr[off] += j[0]; Jr[off + stride] += j[1];
+    }
+  }
+}
+__device__ __forceinline__ void newton_rs_item(const NewtonArgs& a, const int* __restrict__ slow, const double* __restrict__ slow_aux, long long tid) {
   const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int i = (int)(tid / ndir);
   const int dir = (int)(tid % ndir);
   if (i >= a.n) return;
@@ -1232,6 +1277,10 @@ __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int
     double* Jr = a.J + dst * row_len;
     Jr[off] = j[0]; Jr[off + stride] = j[1];
   }
+}
+__global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+  const long long total = (long long)(slow ? slow[0] : a.n) * (29 + 7 * a.W);      // fixed grid, strided (see k_newton_rs_two)
+  for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) newton_rs_item(a, slow, slow_aux, tid);
 }
 
 // LiftingRsCameraMeasurement rows in closed form (newton_math.cuh "LiftingRs rows in CLOSED FORM"): one thread per row like the static kernel,
@@ -1349,7 +1398,9 @@ struct ktk_problem {
   bool graphs_enabled = true;
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   int imu_resident_tiles = 0;     // ... of the IMU-row kernels
-  int newton_fast = 2;            // 2: rows that stop after one OR two evaluations in closed form (+ one dual evaluation per direction for the latter);
+  int sm_count = 148;
+  int newton_fast = 3;            // 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
+                                  //    k_newton_rs_two_w); 2: the same with one dual evaluation per direction (29 + 7 W per row, k_newton_rs_two);
                                   // 1: only one-evaluation rows; 0: every Newton-RS row through the forward-mode kernel (KTK_NEWTON_FAST, A/B and cross-check)
   // -1 (default): the IMU-like groups of an evaluation go out in ONE launch (k_short_batch) when the problem has no camera rows -- a chain of
   // one-wave kernels is launch-bound (C2 -2.6 %, C1: 3 kernels) -- and as one launch per group next to camera rows, where the fused launch measured
@@ -1593,6 +1644,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
       p->cam_resident_tiles = per_sm * (kCamThreads / 32) * prop.multiProcessorCount;
     if (const char* v = getenv("KTK_CAM_AHEAD")) p->cam_resident_tiles = atoi(v);      // A/B switch (0 = off)
+    p->sm_count = prop.multiProcessorCount;
     p->imu_resident_tiles = 8 * prop.multiProcessorCount;                              // 8 one-warp CTAs per SM (register-limited)
     if (const char* v = getenv("KTK_IMU_AHEAD")) p->imu_resident_tiles = atoi(v);
   }
@@ -1979,8 +2031,10 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
           k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p, g.d_slow_aux.p, p->newton_fast >= 2 ? 1 : 0);
           p->launches += 1;
         }
-        if (p->newton_fast >= 2) { k_newton_rs_two<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
-        k_newton_rs<<<(unsigned)((threads + 127) / 128), 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr, g.d_slow_aux.p);
+        const unsigned grid = (unsigned)std::min<long long>((threads + 127) / 128, (long long)p->sm_count * 32);
+        if (p->newton_fast >= 3) { k_newton_rs_two_w<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        else if (p->newton_fast == 2) { k_newton_rs_two<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        k_newton_rs<<<grid, 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr, g.d_slow_aux.p);
       }
       if (localize) {
         const int nres = g.kind == KTK_LIFTING_RS ? 3 : 2, tail = g.kind == KTK_LIFTING_RS ? 6 : 2;

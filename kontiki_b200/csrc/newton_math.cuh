@@ -413,6 +413,66 @@ KB_HD int newton_rs_two_step_column(const SplineConst& sp, const CameraConst& ca
   newton_rs_finish(oo, ouv, weight, huber_c, r, j);
   return 0;
 }
+// The same correction with 32 dual evaluations per row instead of 29 + 7 W (what k_newton_rs_two runs, one warp per row).  f/df at the initial row
+// time sees the reference window and rho only THROUGH the landmark X (and rho directly), so its derivative along the 28 reference directions is the
+// chain rule g_X . dX/dknot[:, c] with g_X from three evaluations seeded on the components of X, along rho g_X . dX/drho + g_rho; and of the 7 W
+// observation directions only the four knots active at the initial row time have a derivative at all.  Lane layout:
+//   [0, 28) component lane % 7 of active observation knot io + lane / 7 | 28, 29, 30: X.x, X.y, X.z | 31: rho alone.
+KB_HD int newton_rs_first_step_lane(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                    const double* obs_uv, double obs_t0, double ref_t0, int kbase, int W, int lane, int* io_out, double& dtd) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const double t = static_rs_time(cam, obs_t0, obs_uv[1]);
+  int io; double uo;
+  if (locate_in_segments(nseg, s0, s1, t, sp.t0, sp.dt, io, uo) < 0) return kStatusRange;
+  *io_out = io;
+  NewtonSeeds sd = newton_seeds(cam, rec, kbase, W, -1);
+  if (lane < 28) { sd.ok = io + lane / 7; sd.oc = lane % 7; }
+  else if (lane == 28) sd.X.x.d = 1.0;
+  else if (lane == 29) sd.X.y.d = 1.0;
+  else if (lane == 30) sd.X.z.d = 1.0;
+  else sd.rho.d = 1.0;
+  NewtonEval e;
+  const int st = newton_rs_eval(sp, cam, knots, pairs, nseg, s0, s1, sd, kbase, W, add_rn(obs_t0, cam.time_offset), D1(t), e);
+  if (st != 0) return st;
+  dtd = (e.f / e.df).d;
+  return 0;
+}
+// d(f/df) along a reference-window direction (c < 28) or rho (c == 28) from the gradient g = {g_X (3), g_rho} and the landmark record
+KB_HD double newton_rs_ref_chain(const double* rec, const double* g, int c) {
+  if (c < 28) { const double* d = rec + kRefDOff + 21 * (c / 7) + c % 7; return g[0] * d[0] + g[1] * d[7] + g[2] * d[14]; }
+  return g[0] * rec[3] + g[1] * rec[4] + g[2] * rec[5] + g[3];
+}
+// finish(pi'(t_1) * d t_1 / d theta) for one column, d t_1 = -d(f/df)
+KB_HD void newton_rs_two_step_finish(const double* ouv, double weight, double huber_c, const double* aux, double dtd, double* j) {
+  NewtonRow oo; oo.y[0] = aux[0]; oo.y[1] = aux[1]; oo.dy[0] = -aux[2] * dtd; oo.dy[1] = -aux[3] * dtd; oo.iterations = 2;
+  double r[2];
+  newton_rs_finish(oo, ouv, weight, huber_c, r, j);
+}
+// Host form of the warp's work: all 32 lanes, then every column that has a correction.
+KB_HD int newton_rs_two_step_row_lanes(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* ouv,
+                                       double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, const double* aux, double* J) {
+  if (aux[2] == 0.0 && aux[3] == 0.0) return 0;
+  double dtd[32];
+  int io = -1;
+  for (int lane = 0; lane < 32; ++lane) {
+    const int st = newton_rs_first_step_lane(sp, cam, knots, pairs, rec, ouv, obs_t0, ref_t0, kbase, W, lane, &io, dtd[lane]);
+    if (st != 0) return st;
+  }
+  for (int lane = 0; lane < 29; ++lane) {
+    double j[2]; int stride;
+    if (lane < 28) {
+      newton_rs_two_step_finish(ouv, weight, huber_c, aux, dtd[lane], j);
+      const int off = newton_dir_offset(28 + 7 * (io - kbase) + lane, W, stride);
+      J[off] += j[0]; J[off + stride] += j[1];
+    }
+    newton_rs_two_step_finish(ouv, weight, huber_c, aux, newton_rs_ref_chain(rec, dtd + 28, lane), j);
+    const int off = newton_dir_offset(lane < 28 ? lane : 28 + 7 * W, W, stride);
+    J[off] += j[0]; J[off + stride] += j[1];
+  }
+  return 0;
+}
 // A whole row the way the two kernels produce it (host check): closed form where the iteration stops after one or two evaluations.
 KB_HD int newton_rs_row_fast(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* obs_uv,
                              double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, double* r, double* J, int* iterations) {
@@ -425,15 +485,7 @@ KB_HD int newton_rs_row_fast(const SplineConst& sp, const CameraConst& cam, cons
   for (int c = 0; c < 56; ++c) { J[c] = row[c]; J[56 + 14 * rel + c] = row[56 + c]; }
   J[56 + 14 * W] = row[112]; J[57 + 14 * W] = row[113];
   *iterations = mode == 0 ? 1 : 2;
-  if (mode == 2) {
-    for (int dir = 0; dir < 29 + 7 * W; ++dir) {
-      double j[2]; int stride;
-      const int st = newton_rs_two_step_column(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, aux, dir, j);
-      if (st != 0) return st;
-      const int off = newton_dir_offset(dir, W, stride);
-      J[off] += j[0]; J[off + stride] += j[1];
-    }
-  }
+  if (mode == 2) return newton_rs_two_step_row_lanes(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, aux, J);
   return 0;
 }
 
