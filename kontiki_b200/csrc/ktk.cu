@@ -1107,6 +1107,7 @@ struct NewtonArgs {
 // is exactly the static row's Jacobian (bit for bit: tests/test_gpu_parity.py).  One thread per row runs the iteration once on values only;
 // single-evaluation rows get the closed-form static row (written into the span layout), the others are flagged for the forward-mode kernel.
 constexpr int kNewtonStage = 116;      // [Jref 56 | Jobs 56 | rho 2] + pad
+constexpr int kNewtonRevSmemMax = 160 * 1024;      // k_newton_rs_rev stages d t_last / d theta (29 + 7 W doubles per row): W <= 86; wider spans take the dual-number kernels
 __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* __restrict__ slow /* [0] = count, [1 + k] = row of the k-th slow row */,
                                                        double* __restrict__ slow_aux /* 6 per list slot: mode (0 forward mode, 2 two-evaluation row) | y(t_1) 2 | pi'(t_1) 2 */,
                                                        int allow_two) {
@@ -1128,8 +1129,12 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
     if (ridx >= 0) {
       double r[2];
       int ir = -1;
-      mode = newton_rs_row_closed(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)ridx * kRefStride, ouv, obs_t0, ref_t0, kbase, a.W, a.w[i],
-                                  (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, allow_two != 0, row, r, &ir, &rel, aux);
+      if (allow_two >= 2)
+        mode = newton_rs_row_closed_any(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)ridx * kRefStride, ouv, obs_t0, ref_t0, kbase, a.W, a.w[i],
+                                        (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, row, r, &ir, &rel, aux);
+      else
+        mode = newton_rs_row_closed(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)ridx * kRefStride, ouv, obs_t0, ref_t0, kbase, a.W, a.w[i],
+                                    (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, allow_two != 0, row, r, &ir, &rel, aux);
       if (mode >= 0) {
         perm = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
         const size_t dst = (size_t)perm;
@@ -1236,6 +1241,54 @@ __global__ void __launch_bounds__(128) k_newton_rs_two_w(const NewtonArgs a, con
       const int off = newton_dir_offset(lane < 28 ? lane : 28 + 7 * a.W, a.W, stride);
       Jr[off] += j[0]; Jr[off + stride] += j[1];
     }
+  }
+}
+// KTK_NEWTON_FAST >= 4: the listed rows (two or more evaluations) in CLOSED FORM, one thread per row: the iteration is run again on values with
+// D = d t_last / d theta accumulated by one reverse sweep per evaluation (newton_math.cuh "NewtonRs rows in CLOSED FORM for any number of
+// evaluations"), then the warp adds jfin (x) D to the static rows k_newton_rs_fast wrote, row after row with coalesced read-modify-writes.
+__global__ void __launch_bounds__(32) k_newton_rs_rev(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+  extern __shared__ __align__(16) double smem[];
+  if (!(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
+  const int lane = threadIdx.x & 31, nD = 29 + 7 * a.W, dstride = nD | 1, row_len = 58 + 14 * a.W, tail0 = 56 + 14 * a.W;
+  double* D = smem + lane * dstride;
+  const int nlist = slow[0];
+  for (int base = blockIdx.x * 32; base < nlist; base += gridDim.x * 32) {
+    const int k = base + lane;
+    long long dst = -1;
+    double jf0 = 0.0, jf1 = 0.0;
+    if (k < nlist) {
+      const double* ax = slow_aux + 6 * (size_t)k;
+      if (ax[0] == 2.0 && (ax[3] != 0.0 || ax[4] != 0.0)) {
+        const int i = slow[1 + k];
+        const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
+        const double obs_t0 = a.obs_t0[i];
+        const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
+        NewtonIter it;
+        const int st = newton_rs_iterate(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)a.ref_idx[i] * kRefStride, ouv, obs_t0, a.ref_t0[i], kbase, a.W, it, D);
+        dst = (a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i];
+        if (st != 0) { atomicMin(a.err, st); jf0 = jf1 = nan(""); }
+        else {
+          double jfin[2];
+          newton_rs_shift_column(it, ouv, a.w[i], (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, jfin);
+          jf0 = jfin[0]; jf1 = jfin[1];
+        }
+      }
+    }
+    __syncwarp();
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long d = __shfl_sync(0xffffffffu, dst, rr);
+      if (d < 0) continue;
+      const double j0 = __shfl_sync(0xffffffffu, jf0, rr), j1 = __shfl_sync(0xffffffffu, jf1, rr);
+      const double* Ds = smem + rr * dstride;
+      double* Jr = a.J + (size_t)d * row_len;
+      for (int c = lane; c < row_len; c += 32) {
+        double v;
+        if (c >= tail0) v = (c == tail0 ? j0 : j1) * Ds[nD - 1];
+        else { const int blk = c / 14, w = c - 14 * blk; v = w < 7 ? j0 * Ds[7 * blk + w] : j1 * Ds[7 * blk + w - 7]; }
+        Jr[c] += v;
+      }
+    }
+    __syncwarp();
   }
 }
 __device__ __forceinline__ void newton_rs_item(const NewtonArgs& a, const int* __restrict__ slow, const double* __restrict__ slow_aux, long long tid) {
@@ -1399,7 +1452,9 @@ struct ktk_problem {
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   int imu_resident_tiles = 0;     // ... of the IMU-row kernels
   int sm_count = 148;
-  int newton_fast = 3;            // 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
+  int newton_fast = 4;            // 4: every row in closed form whatever its number of evaluations: static row at t_last (k_newton_rs_fast) + jfin (x) d t_last / d theta
+                                  //    by one reverse sweep per evaluation (k_newton_rs_rev); forward mode only where that fails (out-of-range rows);
+                                  // 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
                                   //    k_newton_rs_two_w); 2: the same with one dual evaluation per direction (29 + 7 W per row, k_newton_rs_two);
                                   // 1: only one-evaluation rows; 0: every Newton-RS row through the forward-mode kernel (KTK_NEWTON_FAST, A/B and cross-check)
   // -1 (default): the IMU-like groups of an evaluation go out in ONE launch (k_short_batch) when the problem has no camera rows -- a chain of
@@ -1639,6 +1694,7 @@ int ktk_problem_create(int device, ktk_problem** out) {
   if (const char* v = getenv("KTK_FUSE_SHORT")) p->fuse_short = atoi(v);
   if (const char* v = getenv("KTK_NEWTON_FAST")) p->newton_fast = atoi(v);
   cudaFuncSetAttribute(k_newton_rs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kNewtonStage * 8);
+  cudaFuncSetAttribute(k_newton_rs_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, kNewtonRevSmemMax);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_static_rs, kCamThreads, kCamThreads * kCamDevStride * 8) == cudaSuccess)
@@ -2026,14 +2082,20 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
       } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
+        const int rev_smem = 32 * ((29 + 7 * na.W) | 1) * 8;
+        const int nf = (p->newton_fast >= 4 && rev_smem > kNewtonRevSmemMax) ? 3 : p->newton_fast;
         if (p->newton_fast) {
           cudaMemsetAsync(g.d_slow.p, 0, sizeof(int), s);
-          k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p, g.d_slow_aux.p, p->newton_fast >= 2 ? 1 : 0);
+          k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p, g.d_slow_aux.p, nf >= 4 ? 2 : nf >= 2 ? 1 : 0);
           p->launches += 1;
         }
         const unsigned grid = (unsigned)std::min<long long>((threads + 127) / 128, (long long)p->sm_count * 32);
-        if (p->newton_fast >= 3) { k_newton_rs_two_w<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
-        else if (p->newton_fast == 2) { k_newton_rs_two<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        if (nf >= 4) {
+          const unsigned gr = (unsigned)std::min<long long>((g.n + 31) / 32, (long long)p->sm_count * 16);
+          k_newton_rs_rev<<<gr, 32, rev_smem, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1;
+        }
+        else if (nf == 3) { k_newton_rs_two_w<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        else if (nf == 2) { k_newton_rs_two<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
         k_newton_rs<<<grid, 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr, g.d_slow_aux.p);
       }
       if (localize) {

@@ -489,6 +489,271 @@ KB_HD int newton_rs_row_fast(const SplineConst& sp, const CameraConst& cam, cons
   return 0;
 }
 
+// ---- NewtonRs rows in CLOSED FORM for any number of evaluations (reverse mode) ----------------------------------------------------------------
+// With h(theta, t) = f/df the iteration is t_{k+1} = t_k - h(theta, t_k) and y_out = pi(theta, t_last(theta)), so
+//   d y_out / d theta = d pi / d theta |t_last   (the static row at t_last, closed form)   +   pi'(t_last) * D,      D = d t_last / d theta,
+//   D_0 = 0,   D_{k+1} = D_k (1 - dh/dt |t_k) - grad_theta h |t_k,   D_{k+1} = 0 when t_{k+1} was clamped to the readout interval
+// (the Jets of the reference carry exactly this through `t_obs = t_obs - dt`; a clamped time is a constant).  grad_theta h is ONE reverse sweep:
+// on unit quaternions the body of the iteration (newton_rscamera_measurement.h:62-103) is
+//   X_obs = R^T (X - rho p),   dX_obs = X_obs x w_b - rho v_b   (the three quaternion products of :76-90 with dq = w q / 2, ds = -rho v),
+//   X_cam = R_ct X_obs + rho p_ct,   dX_cam = R_ct dX_obs + rho p_ct (sic, :92),   (y, dy) = projection,   f = y_v - rows (t - t0)/readout,  df = dy_v - rows/readout,
+// a scalar function of the pose (R, p), the BODY twist (v_b, w_b), the landmark X and rho.  Its adjoints with respect to the pose go through
+// pose_backward<1> (the static row's sweep), those with respect to the body twist through twist_backward<1> (the accelerometer's recursion
+// s_j = Ad(A_j^-1) s_{j-1} + dB_j omega_j without its second-derivative part), the reference window and rho follow from grad_X through the landmark
+// record.  The radial component along the raw quaternion of knot i0 (the Jacobian is ambient) has three sources: p (inside
+// pose_backward), v = R(q0 raw) M_t => dv/ds = 2 (v - R0^T v), and w = vee(R(q0 raw) M_R R^T) => dw/ds = 2 w - vee2(R0^T hat(w)) (as in gyro_se3).
+// Second derivatives of the camera model: the gradient of h with respect to (X_cam, dX_cam) is taken by six dual evaluations of the PROJECTION alone.
+#if defined(__CUDA_ARCH__)
+#define KB_SEQ() asm volatile("" ::: "memory")
+#else
+#define KB_SEQ() ((void)0)
+#endif
+template <int N>
+KB_HD void twist_backward(const double* p1, const double* p2, const double* p3, const Basis& bs, const Mr<N>& Gv, const Mr<N>& Gw, double scale, double* J) {
+  // one exp part alive at a time (the reverse order needs A3 first): A2 is rebuilt for its level, like in the accelerometer's sweep
+  V3 y2u, y2w, y3u, y3w;
+  ExpPart e;
+  {
+    const V3 u1 = v3(p1[0], p1[1], p1[2]), f1 = v3(p1[3], p1[4], p1[5]);
+    const V3 u2 = v3(p2[0], p2[1], p2[2]), f2 = v3(p2[3], p2[4], p2[5]);
+    const V3 s1u = bs.dB[0] * u1, s1w = bs.dB[0] * f1;
+    exp_part(p2, bs.B[1], true, false, e);
+    y2w = mul_t(e.E, s1w); y2u = mul_t(e.E, s1u - cross(e.a, s1w));
+    const V3 s2u = y2u + bs.dB[1] * u2, s2w = y2w + bs.dB[1] * f2;
+    exp_part(p3, bs.B[2], true, true, e);
+    y3w = mul_t(e.E, s2w); y3u = mul_t(e.E, s2u - cross(e.a, s2w));
+  }
+  G6<N> gs, gj;
+  gs.U = Gv; gs.W = Gw;
+  gj = gadd(gscale(bs.dB[2], gs), mul_Jr6(mul_ad(gs, y3u, y3w), e, bs.B[2]));
+  contract_pair<N, true>(J + 3 * N * 7, gj, p3 + kPairDOff + kPairSide, scale);
+  contract_pair<N, true>(J + 2 * N * 7, gj, p3 + kPairDOff, scale);
+  gs = mul_Adinv(gs, e.E, e.a);
+  exp_part(p2, bs.B[1], true, true, e);
+  gj = gadd(gscale(bs.dB[1], gs), mul_Jr6(mul_ad(gs, y2u, y2w), e, bs.B[1]));
+  contract_pair<N, true>(J + 2 * N * 7, gj, p2 + kPairDOff + kPairSide, scale);
+  contract_pair<N, true>(J + 1 * N * 7, gj, p2 + kPairDOff, scale);
+  gs = mul_Adinv(gs, e.E, e.a);
+  gj = gscale(bs.dB[0], gs);
+  contract_pair<N, true>(J + 1 * N * 7, gj, p1 + kPairDOff + kPairSide, scale);
+  contract_pair<N, true>(J + 0 * N * 7, gj, p1 + kPairDOff, scale);
+}
+// One evaluation of the iteration's body at row time t, plain doubles, on the hoisted structure.
+struct NewtonPoint { int io; double uo; Basis bs; Pose P; V3 vb, wb, Xobs, dXobs, Xc, dXc; double y[2], dy[2], f, df, frow; };
+KB_HD int newton_point(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, int nseg, const Segment& s0,
+                       const Segment& s1, int kbase, int W, double t0_obs, double t, NewtonPoint& e) {
+  if (locate_in_segments(nseg, s0, s1, t, sp.t0, sp.dt, e.io, e.uo) < 0) return kStatusRange;
+  if (e.io < kbase || e.io + 4 > kbase + W) return kStatusRange;
+  e.bs = cumulative_basis(e.uo, sp.dt);
+  const double* k0 = knots + (size_t)e.io * kKnotStride;
+  const double* p1 = pairs + (size_t)(e.io + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  pose_forward(k0, p1, p2, p3, e.bs, e.P);
+  KB_SEQ();
+  V3 dvb;
+  se3_body_twist(p1, p2, p3, e.bs, e.vb, e.wb, dvb);
+  KB_SEQ();
+  const V3 X = v3(rec[0], rec[1], rec[2]);
+  const double rho = rec[6];
+  const M3 Rct = load_m3(cam.Rct);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  e.Xobs = mul_t(e.P.R, X - rho * e.P.p);
+  e.dXobs = cross(e.Xobs, e.wb) - rho * e.vb;
+  e.Xc = Rct * e.Xobs + rho * pct;
+  e.dXc = Rct * e.dXobs + rho * pct;                                               // sic (:92)
+  camera_project_t<double>(cam, tv3<double>(e.Xc.x, e.Xc.y, e.Xc.z), tv3<double>(e.dXc.x, e.dXc.y, e.dXc.z), e.y, e.dy);
+  const double rows = (double)cam.rows;
+  e.frow = rows * (t - t0_obs) / cam.readout;
+  e.f = e.y[1] - e.frow;
+  e.df = e.dy[1] - rows / cam.readout;
+  return 0;
+}
+// grad h at the point e: gobs [4][7] with respect to the four active observation knots, g = {grad_X (3), d h / d rho at fixed X}
+KB_HD void newton_h_gradient(const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const NewtonPoint& e, double* gobs, double* g) {
+  const double rows = (double)cam.rows, rho = rec[6];
+  double a[6];
+#pragma unroll 1
+  for (int k = 0; k < 6; ++k) {
+    TV3<D1> Xd = tv3<D1>(D1(e.Xc.x, k == 0 ? 1.0 : 0.0), D1(e.Xc.y, k == 1 ? 1.0 : 0.0), D1(e.Xc.z, k == 2 ? 1.0 : 0.0));
+    TV3<D1> dXd = tv3<D1>(D1(e.dXc.x, k == 3 ? 1.0 : 0.0), D1(e.dXc.y, k == 4 ? 1.0 : 0.0), D1(e.dXc.z, k == 5 ? 1.0 : 0.0));
+    D1 y[2], dy[2];
+    camera_project_t<D1>(cam, Xd, dXd, y, dy);
+    a[k] = ((y[1] - D1(e.frow)) / (dy[1] - D1(rows / cam.readout))).d;
+  }
+  const M3 Rct = load_m3(cam.Rct);
+  const V3 pct = v3(cam.p_ct[0], cam.p_ct[1], cam.p_ct[2]);
+  const V3 aXc = v3(a[0], a[1], a[2]), adXc = v3(a[3], a[4], a[5]);
+  const V3 adXobs = mul_t(Rct, adXc);
+  const V3 aXobs = mul_t(Rct, aXc) + cross(e.wb, adXobs);
+  const V3 awb = cross(adXobs, e.Xobs), avb = (-rho) * adXobs;
+  const V3 gX = e.P.R * aXobs;
+  g[0] = gX.x; g[1] = gX.y; g[2] = gX.z;
+  g[3] = -dot(aXobs, mul_t(e.P.R, e.P.p)) - dot(adXobs, e.vb) + dot(aXc + adXc, pct);
+  const double* k0 = knots + (size_t)e.io * kKnotStride;
+  const double* p1 = pairs + (size_t)(e.io + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  // radial terms of the world velocity and angular velocity (raw R(q0) on the left of P'): one scalar, formed BEFORE the sweeps so that nothing of
+  // the forward pass but the basis stays live across them
+  double grad[1];
+  {
+    const M3 R0 = quat_to_rot(k0[0], k0[1], k0[2], k0[3]);
+    const V3 v = e.P.R * e.vb, w = e.P.R * e.wb, av = e.P.R * avb, aw = e.P.R * awb;
+    const M3 Mm = mul_tn(R0, hat(w));
+    const V3 dw = 2.0 * w - v3(Mm.a[7] - Mm.a[5], Mm.a[2] - Mm.a[6], Mm.a[3] - Mm.a[1]);
+    grad[0] = dot(av, 2.0 * (v - mul_t(R0, v))) + dot(aw, dw);
+  }
+  Mr<1> Gp, GpR, Gth, Gv, Gw;
+  Gp.a[0] = -rho * gX.x; Gp.a[1] = -rho * gX.y; Gp.a[2] = -rho * gX.z;
+  GpR.a[0] = -rho * aXobs.x; GpR.a[1] = -rho * aXobs.y; GpR.a[2] = -rho * aXobs.z;
+  { const V3 th = cross(aXobs, e.Xobs); Gth.a[0] = th.x; Gth.a[1] = th.y; Gth.a[2] = th.z; }      // Go hat(Xobs): the row crossed with Xobs
+  Gv.a[0] = avb.x; Gv.a[1] = avb.y; Gv.a[2] = avb.z;
+  Gw.a[0] = awb.x; Gw.a[1] = awb.y; Gw.a[2] = awb.z;
+  const Basis bs = e.bs;
+  // The two sweeps are independent until they meet in gobs, and left alone the compiler interleaves them for instruction-level parallelism: 168 registers
+  // and 2.7 KB of spill per thread.  KB_SEQ keeps them one after the other: 254 registers, no spill.
+  KB_SEQ();
+  pose_backward<1>(k0, p1, p2, p3, bs, Gp, GpR, Gth, 1.0, gobs);
+  KB_SEQ();
+  twist_backward<1>(p1, p2, p3, bs, Gv, Gw, 1.0, gobs);
+  KB_SEQ();
+  Mr<1> zero; zero.a[0] = zero.a[1] = zero.a[2] = 0.0;
+  add_q0_block<1>(gobs, zero, grad, k0, 1.0);
+}
+// dh/dt at fixed theta: one time-seeded dual evaluation.  Out of line on the device: only rows with three or more evaluations come here, and the
+// dual-number evaluation must not set the register budget of the closed-form kernels.
+KB_COLD int newton_h_time_derivative(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                     double obs_t0, double ref_t0, int kbase, int W, double t, double* ht) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const NewtonSeeds sd = newton_seeds(cam, rec, kbase, W, -1);
+  NewtonEval ev;
+  const int st = newton_rs_eval(sp, cam, knots, pairs, nseg, s0, s1, sd, kbase, W, add_rn(obs_t0, cam.time_offset), D1(t, 1.0), ev);
+  if (st != 0) return st;
+  *ht = (ev.f / ev.df).d;
+  return 0;
+}
+// The iteration on values, and (D != nullptr) D = d t_last / d theta in the span layout [ref 4 x 7 | obs W x 7 | rho] along the way.
+struct NewtonIter { int iterations, clamped_last, io; double t_last, uo, y[2], pd[2]; };
+KB_HD int newton_rs_iterate(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* obs_uv,
+                            double obs_t0, double ref_t0, int kbase, int W, NewtonIter& it, double* D) {
+  Segment s0, s1;
+  const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
+  if (nseg == 0) return kStatusRange;
+  const double rows = (double)cam.rows;
+  const double t0_obs = add_rn(obs_t0, cam.time_offset);
+  double t = static_rs_time(cam, obs_t0, obs_uv[1]);
+  const double max_dt = 0.5 * cam.readout / rows, max_dt2 = max_dt * max_dt;
+  const double min_bound = t0_obs, max_bound = add_rn(t0_obs, cam.readout);
+  const int nD = 29 + 7 * W;
+  bool Dzero = true;
+  if (D) for (int c = 0; c < nD; ++c) D[c] = 0.0;
+  int clamped = 0;
+  it.iterations = 0; it.pd[0] = it.pd[1] = 0.0;
+#pragma unroll 1
+  for (int iter = 0; iter < 5; ++iter) {
+    it.t_last = t; it.clamped_last = clamped;
+    NewtonPoint e;
+    const int st = newton_point(sp, cam, knots, pairs, rec, nseg, s0, s1, kbase, W, t0_obs, t, e);
+    if (st != 0) return st;
+    const double h = e.f / e.df;
+    it.iterations = iter + 1;
+    if (h * h < max_dt2 || iter == 4) {
+      it.y[0] = e.y[0]; it.y[1] = e.y[1]; it.io = e.io; it.uo = e.uo;
+      if (iter > 0 && !clamped) {                       // pi'(t_last): the TRUE time derivative (X_cam' = R_ct dX_obs, without the rho p_ct slip of :92)
+        const V3 dX = load_m3(cam.Rct) * e.dXobs;
+        D1 y[2], dy[2];
+        const TV3<D1> Xd = tv3<D1>(D1(e.Xc.x, dX.x), D1(e.Xc.y, dX.y), D1(e.Xc.z, dX.z)), z = tv3<D1>(D1(0.0), D1(0.0), D1(0.0));
+        camera_project_t<D1>(cam, Xd, z, y, dy);
+        it.pd[0] = y[0].d; it.pd[1] = y[1].d;
+      }
+      break;
+    }
+    if (D) {
+      if (!Dzero) {                                     // dh/dt at fixed theta (rows with three or more evaluations only)
+        double ht;
+        const int st2 = newton_h_time_derivative(sp, cam, knots, pairs, rec, obs_t0, ref_t0, kbase, W, t, &ht);
+        if (st2 != 0) return st2;
+        const double keep = 1.0 - ht;
+        for (int c = 0; c < nD; ++c) D[c] *= keep;
+      }
+      double gobs[28], g[4];
+      KB_SEQ();
+      newton_h_gradient(cam, knots, pairs, rec, e, gobs, g);
+      KB_SEQ();
+#pragma unroll 1
+      for (int c = 0; c < 29; ++c) D[c < 28 ? c : nD - 1] -= newton_rs_ref_chain(rec, g, c);
+      double* Do = D + 28 + 7 * (e.io - kbase);
+#pragma unroll
+      for (int c = 0; c < 28; ++c) Do[c] -= gobs[c];
+      Dzero = false;
+    }
+    t = t - h;
+    clamped = 0;
+    if (t < min_bound) { t = min_bound; clamped = 1; }
+    else if (t > max_bound) { t = max_bound; clamped = 1; }
+    if (clamped && D && !Dzero) { for (int c = 0; c < nD; ++c) D[c] = 0.0; Dzero = true; }
+  }
+  return 0;
+}
+// What finish() makes of a unit of d t_last / d theta: the two entries every column's D is multiplied with (the corrector is linear in the column)
+KB_HD void newton_rs_shift_column(const NewtonIter& it, const double* ouv, double weight, double huber_c, double* jfin) {
+  NewtonRow oo; oo.y[0] = it.y[0]; oo.y[1] = it.y[1]; oo.dy[0] = it.pd[0]; oo.dy[1] = it.pd[1]; oo.iterations = it.iterations;
+  double r[2];
+  newton_rs_finish(oo, ouv, weight, huber_c, r, jfin);
+}
+// The closed-form part of a row for ANY number of evaluations (k_newton_rs_fast with KTK_NEWTON_FAST >= 4): `row` = the static row at t_last, staged
+// like in newton_rs_row_closed.  Returns 0: complete (one evaluation, or t_last clamped: D has no effect); 2: aux = {y(t_last), pi'(t_last)} and the row
+// still needs + jfin (x) D (k_newton_rs_rev); -1: forward mode.
+KB_HD int newton_rs_row_closed_any(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* ouv,
+                                   double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, double* row, double* r,
+                                   int* ir_out, int* rel, double* aux) {
+  if ((int)rec[7] < 0) return -1;
+  NewtonIter it;
+  if (newton_rs_iterate(sp, cam, knots, pairs, rec, ouv, obs_t0, ref_t0, kbase, W, it, nullptr) != 0) return -1;
+  ObsForward f; f.status = 0; f.io = it.io; f.bo = cumulative_basis(it.uo, sp.dt);
+  static_rs_row_pose(knots, pairs, f);
+  double jrho[2];
+  int ir = -1, io = -1;
+  ObsAdjoint adj;
+  for (int c = 0; c < kRefStride; ++c) row[22 + c] = rec[c];
+  if (static_rs_row_ref_half(cam, f, row + 22, ouv, weight, huber_c, r, row, jrho, &ir, &io, adj) != 0) return -1;
+  static_rs_row_obs_half(knots, pairs, f, adj, row + 56);
+  row[112] = jrho[0]; row[113] = jrho[1];
+  *ir_out = ir; *rel = io - kbase;
+  if (it.pd[0] == 0.0 && it.pd[1] == 0.0) return 0;
+  aux[0] = it.y[0]; aux[1] = it.y[1]; aux[2] = it.pd[0]; aux[3] = it.pd[1];
+  return 2;
+}
+// A whole row in closed form (host check of what k_newton_rs_fast + k_newton_rs_rev produce): static row at t_last + jfin (x) D.
+KB_HD int newton_rs_row_reverse(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* obs_uv,
+                                double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, double* r, double* J, int* iterations) {
+  double D[29 + 7 * 16];
+  if (W > 16 || (int)rec[7] < 0) return newton_rs_row(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, weight, huber_c, r, J, iterations);
+  NewtonIter it;
+  const int st = newton_rs_iterate(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, kbase, W, it, D);
+  if (st != 0) return st;
+  ObsForward f; f.status = 0; f.io = it.io; f.bo = cumulative_basis(it.uo, sp.dt);
+  static_rs_row_pose(knots, pairs, f);
+  double row[114], jrho[2];
+  int ir = -1, io = -1;
+  ObsAdjoint adj;
+  for (int c = 0; c < kRefStride; ++c) row[22 + c] = rec[c];
+  if (static_rs_row_ref_half(cam, f, row + 22, obs_uv, weight, huber_c, r, row, jrho, &ir, &io, adj) != 0) return kStatusRange;
+  static_rs_row_obs_half(knots, pairs, f, adj, row + 56);
+  const int row_len = 58 + 14 * W, rel = it.io - kbase;
+  for (int c = 0; c < row_len; ++c) J[c] = 0.0;
+  for (int c = 0; c < 56; ++c) { J[c] = row[c]; J[56 + 14 * rel + c] = row[56 + c]; }
+  J[56 + 14 * W] = jrho[0]; J[57 + 14 * W] = jrho[1];
+  *iterations = it.iterations;
+  if (it.pd[0] != 0.0 || it.pd[1] != 0.0) {
+    double jfin[2];
+    newton_rs_shift_column(it, obs_uv, weight, huber_c, jfin);
+    for (int k = 0; k < 4 + W; ++k)
+      for (int c = 0; c < 7; ++c) { J[14 * k + c] += jfin[0] * D[7 * k + c]; J[14 * k + 7 + c] += jfin[1] * D[7 * k + c]; }
+    J[56 + 14 * W] += jfin[0] * D[28 + 7 * W]; J[57 + 14 * W] += jfin[1] * D[28 + 7 * W];
+  }
+  return 0;
+}
+
 // ---- LiftingRsCameraMeasurement (measurements/lifting_rscamera_measurement.h:21-56, :98-118) ---------------------------------------------
 // The static projection with the observation evaluated at the LIFTED time t_obs = t0_obs + time_offset + vt * readout, vt in [0, 1] a
 // parameter block of the measurement; 3 residuals weight * [uv - y ; rows (vt - vt_orig)].  Same forward-mode machinery as the Newton

@@ -72,7 +72,7 @@ void hc_static_rs(double t0, double dt, int n_knots, const double* K, const doub
   }
 }
 
-static int g_newton_fast = 0;      // 0: every row in forward mode (k_newton_rs alone); 1: closed form for rows that stop after one or two evaluations (k_newton_rs_fast + k_newton_rs)
+static int g_newton_fast = 0;      // 2: every row in closed form, any number of evaluations (k_newton_rs_fast + k_newton_rs_rev); 0: every row in forward mode (k_newton_rs alone); 1: closed form for rows that stop after one or two evaluations (k_newton_rs_fast + k_newton_rs)
 void hc_set_newton_fast(int on) { g_newton_fast = on; }
 // NewtonRsCameraMeasurement rows: what k_landmark_ref + k_newton_rs do, one (row, direction) at a time.
 // J: n x (58 + 14 W) packed [ref 4x(2x7) | obs W x(2x7) | rho 2]; kbase = first knot of the observation span.
@@ -101,7 +101,7 @@ void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const doub
     status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
     if (status[i] != 0) continue;
     const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
-    status[i] = (g_newton_fast ? newton_rs_row_fast : newton_rs_row)(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], kbase, W, w[i],
+    status[i] = (g_newton_fast == 2 ? newton_rs_row_reverse : g_newton_fast ? newton_rs_row_fast : newton_rs_row)(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], kbase, W, w[i],
                                                                       huber_c ? huber_c[i] : 0.0, r + 2 * i, J + (size_t)row_len * i, iterations + i);
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }

@@ -93,7 +93,7 @@ def newton_rs(knots7, dt, t0, cam, obs_uv, obs_t0, ref_uv, ref_t0, lm_idx, rho, 
     K = _f(cam.K).reshape(-1)
     Kinv = _f(kinv_cofactor(cam.K)).reshape(-1)
     W = newton_window(t0, dt, cam.readout, obs_t0)
-    lib().hc_set_newton_fast(int(bool(fast)))      # fast: the rows as k_newton_rs_fast + k_newton_rs produce them (closed form for one / two evaluations)
+    lib().hc_set_newton_fast(int(fast))      # fast: the rows as k_newton_rs_fast + k_newton_rs produce them (closed form for one / two evaluations)
     r, J = np.zeros((n, 2)), np.zeros((n, 58 + 14 * W))
     ir, kb, it, st = (np.zeros(n, np.int32) for _ in range(4))
     lib().hc_newton_rs(C.c_double(t0), C.c_double(dt), len(k8), _p(K), _p(Kinv), _p(_f(cam.q_ct)), _p(_f(cam.p_ct)), C.c_double(cam.time_offset),

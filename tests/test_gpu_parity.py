@@ -566,6 +566,53 @@ def test_newton_and_atan_rows_match_oracle(method, atan, robust):
     assert np.array_equal(dev["J"], out["J"][order]) and np.array_equal(dev["r"], out["r"][order]) and np.array_equal(dev["i0_b"], out["i0_b"][order])
 
 
+@pytest.mark.parametrize("atan,robust", [(False, True), (True, False)])
+def test_newton_rows_closed_form_equals_forward_mode_for_any_number_of_evaluations(atan, robust, monkeypatch):
+    """Observed rows anywhere in the image: the iteration takes two, three and more evaluations and is clamped to the readout interval for some rows.
+    The closed-form rows (k_newton_rs_fast + k_newton_rs_rev, reverse mode: D = d t_last / d theta carried through the iteration) against the oracle's
+    autodiff through the iteration, and against the library's own forward-mode kernel (KTK_NEWTON_FAST=0) and its dual-number variants (2, 3)."""
+    cfg = syn.make_config("C3", scale=0.004)
+    c = cfg["cam"]
+    rng = np.random.default_rng(71)
+    c["obs_uv"][:, 1] = rng.uniform(1.0, c["rows"] - 2.0, len(c["lm_idx"]))
+    c["weight"] = rng.uniform(0.5, 2, len(c["lm_idx"]))
+    flags = _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | (_lib.EVAL_ROBUST if robust else 0)
+    outs = {}
+    for mode in ("4", "0", "2", "3"):
+        monkeypatch.setenv("KTK_NEWTON_FAST", mode)                # read when the problem is created
+        p, g, ocam = _camera_group(cfg, "newton", atan)
+        outs[mode] = p.evaluate(cfg["knots"], c["rho"], flags)[g]
+    monkeypatch.delenv("KTK_NEWTON_FAST")
+    out = outs["4"]
+    ok = out["i0"] >= 0
+    assert ok.sum() > 0.9 * len(ok)
+    for mode in ("0", "2", "3"):
+        o2 = outs[mode]
+        assert np.array_equal(o2["i0"], out["i0"]) and np.array_equal(o2["i0_b"], out["i0_b"])
+        assert np.abs(o2["r"][ok] - out["r"][ok]).max() < parity.CAM_R_TOL
+        sc = np.abs(o2["J"][ok]).max(axis=1, keepdims=True)
+        assert (np.abs(o2["J"][ok] - out["J"][ok]) / sc).max() < parity.TOL
+        assert np.array_equal(np.isnan(o2["J"]), np.isnan(out["J"]))
+    traj = kto.Traj(kto.SE3, cfg["dt"], cfg["t0"], cfg["knots"])
+    sub = np.flatnonzero(ok)[::3]
+    o = kto.static_rs_residuals(traj, ocam, c["obs_uv"][sub], c["obs_t0"][sub], c["ref_uv"][sub], c["ref_t0"][sub], c["lm_idx"][sub], c["rho"], c["weight"][sub],
+                                jac_mode=2, cap=24)
+    assert (out["i0"][sub] == o["i0_ref_a"]).all() and (out["i0_b"][sub] == o["i0_obs_a"]).all()
+    row = p.group_row_size(g)
+    ids, nids = p.get_structure(g, cap=24)
+    Js = p.expand_static_rs(g, ids, out["J"], out["i0"], out["i0_b"])[sub]
+    Jrho = out["J"][sub, row - 2:row]
+    for a, i in enumerate(sub):
+        m = int(nids[i])
+        Jfull = np.concatenate([o["Ja"][a, k] for k in range(m)] + [o["Jrho"][a].reshape(2, 1)], axis=1)
+        r2, J2 = o["r"][a], Jfull
+        if robust:
+            _, r2, J2 = kto.huber_correct(c["huber_c"][i], o["r"][a], Jfull)
+        Jmine = np.concatenate([Js[a, k] for k in range(m)] + [Jrho[a].reshape(2, 1)], axis=1)
+        assert np.abs(Jmine - J2).max() <= parity.TOL * np.abs(J2).max()
+        assert np.abs(out["r"][i] - r2).max() <= parity.CAM_R_TOL
+
+
 def test_newton_rows_without_noise_equal_static_rows_and_unsupported_modes():
     """Exact observations: the first Newton step is below half a row, so every row is the static row inside a wider span."""
     cfg = syn.make_config("C3", scale=0.002)

@@ -260,6 +260,32 @@ def test_newton_rs_rows_match_oracle(dt, atan):
     assert (h["iterations"] == 2).sum() > 5
 
 
+@pytest.mark.parametrize("seed", [21, 24, 48, 22, 23])
+def test_newton_rs_rows_closed_form_for_any_number_of_evaluations(seed):
+    """Reverse mode (newton_math.cuh "NewtonRs rows in CLOSED FORM for any number of evaluations"): static row at t_last + jfin (x) d t_last / d theta, with
+    d t_last / d theta carried through the iteration by one reverse sweep (pose + body twist) per evaluation.  Observed rows anywhere in the image, so that
+    rows with two, three and more evaluations occur; against forward mode through the iteration (same harness) and against the oracle's autodiff."""
+    dt, atan = (0.02, 0.05, 0.1)[seed % 3], bool(seed & 1)
+    knots, s, cam = _camera_case_model(dt, seed, atan, "newton")
+    rng = np.random.default_rng(seed)
+    uv = s["obs_uv"].copy()
+    uv[:, 1] = rng.uniform(1.0, cam.rows - 2.0, len(uv))
+    args = (knots, dt, 0.0, cam, uv, s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"])
+    h0, h2 = hc.newton_rs(*args), hc.newton_rs(*args, fast=2)
+    assert (h0["status"] == h2["status"]).all()
+    ok = h0["status"] == 0
+    assert ok.sum() > 0.8 * len(ok) and (h0["iterations"][ok] == h2["iterations"][ok]).all()
+    assert dt != 0.02 or (h0["iterations"][ok] >= 3).sum() >= 10
+    sc = np.abs(h0["J"][ok]).max(axis=1, keepdims=True)
+    assert (np.abs(h2["J"][ok] - h0["J"][ok]) / sc).max() < 1e-11
+    assert np.abs(h2["r"][ok] - h0["r"][ok]).max() < parity.CAM_R_TOL
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, uv[ok], s["obs_t0"][ok], s["ref_uv"][ok], s["ref_t0"][ok], s["lm_idx"][ok], s["rho"],
+                                s["weight"][ok], jac_mode=2, cap=24)
+    assert (h2["i0_ref"][ok] == o["i0_ref_a"]).all() and (h2["i0_obs"][ok] == o["i0_obs_a"]).all()
+    Js, Jrho = parity.scatter_cam(h2["J"][ok], h2["i0_ref"][ok], h2["i0_obs"][ok], o["ids_a"], h2["W"])
+    assert parity.rel_err(Js, o["Ja"]) < parity.TOL and parity.rel_err(Jrho, o["Jrho"]) < parity.TOL
+
+
 def test_newton_rs_one_step_rows_equal_static_rows():
     """A row whose first Newton step is below half a row time returns the projection at the observed row: the static-RS row."""
     dt = 0.05
@@ -284,7 +310,7 @@ def test_newton_rs_huber_corrector_matches_oracle():
     n = len(s["lm_idx"])
     o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, 0.0, knots), cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"],
                                 s["weight"], jac_mode=2, cap=24)
-    for fast in (False, True):
+    for fast in (0, 1, 2):
         h = hc.newton_rs(knots, dt, 0.0, cam, s["obs_uv"], s["obs_t0"], s["ref_uv"], s["ref_t0"], s["lm_idx"], s["rho"], s["weight"], huber_c=np.full(n, 5.0), fast=fast)
         for i in range(n):
             m = int((o["ids_a"][i] >= 0).sum())
