@@ -1150,6 +1150,9 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
     int base = 0;
     if (lane == 0 && m) base = atomicAdd(slow, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
+    // ... and how many of them are forward-mode rows (slow[n + 1]): k_newton_rs leaves at once when there are none, instead of walking the list
+    const unsigned mf = __ballot_sync(0xffffffffu, slow_lane != 0 && mode < 0);
+    if (lane == 0 && mf) atomicAdd(slow + a.n + 1, __popc(mf));
     if (slow_lane) {
       const int slot = base + __popc(m & ((1u << lane) - 1u));
       slow[1 + slot] = i;
@@ -1332,6 +1335,7 @@ __device__ __forceinline__ void newton_rs_item(const NewtonArgs& a, const int* _
   }
 }
 __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
+  if (slow && slow[a.n + 1] == 0) return;      // every listed row was finished in closed form
   const long long total = (long long)(slow ? slow[0] : a.n) * (29 + 7 * a.W);      // fixed grid, strided (see k_newton_rs_two)
   for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) newton_rs_item(a, slow, slow_aux, tid);
 }
@@ -1417,7 +1421,7 @@ struct Group {
   std::vector<double> vt; DevBuf<double> d_vt; bool vt_dirty = true;      // LiftingRs: current frame-normalised row times, caller order (ktk_set_group_vt)
   DevBuf<double> o_Js;
   DevBuf<double> o_amb; DevBuf<int> o_amb_i0, o_amb_i0b;      // span cameras, KTK_EVAL_LOCAL: ambient rows / window indices before k_span_localize
-  DevBuf<int> d_slow;             // Newton-RS rows that need the forward-mode kernel (more than one Newton evaluation): [count | row indices]
+  DevBuf<int> d_slow;             // Newton-RS rows k_newton_rs_fast did not finish (more than one Newton evaluation): [count | row indices (n) | count of forward-mode rows]
   DevBuf<double> d_slow_aux;      // ... 6 doubles per list slot (k_newton_rs_fast)
   // landmark-reference records (static RS): one per distinct (landmark, segment origin of the reference evaluation)
   int64_t n_ref = 0;
@@ -1973,7 +1977,7 @@ int ktk_evaluate_device(ktk_problem* p, const double* d_knots, const double* d_r
       KTK_CUDA(cudaStreamSynchronize(s));
       g->vt_dirty = false;
     }
-    if (g->kind == KTK_NEWTON_RS && g->n > 0 && ((st = g->d_slow.resize((size_t)g->n + 1)) || (st = g->d_slow_aux.resize((size_t)6 * g->n)))) return st;
+    if (g->kind == KTK_NEWTON_RS && g->n > 0 && ((st = g->d_slow.resize((size_t)g->n + 2)) || (st = g->d_slow_aux.resize((size_t)6 * g->n)))) return st;
     if (is_span_camera(g->kind) && (flags & KTK_EVAL_LOCAL) && (flags & KTK_EVAL_JACOBIANS) && g->n > 0) {      // scratch of k_span_localize (outside any capture)
       if ((st = g->o_amb.resize((size_t)g->n * row_doubles(p, *g)))) return st;
       if ((st = g->o_amb_i0.resize((size_t)g->n)) || (st = g->o_amb_i0b.resize((size_t)g->n))) return st;
@@ -2086,6 +2090,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         const int nf = (p->newton_fast >= 4 && rev_smem > kNewtonRevSmemMax) ? 3 : p->newton_fast;
         if (p->newton_fast) {
           cudaMemsetAsync(g.d_slow.p, 0, sizeof(int), s);
+          cudaMemsetAsync(g.d_slow.p + g.n + 1, 0, sizeof(int), s);      // [0] listed rows, [n + 1] forward-mode rows among them
           k_newton_rs_fast<<<(unsigned)((g.n + 31) / 32), 32, 32 * kNewtonStage * 8, s>>>(na, g.d_slow.p, g.d_slow_aux.p, nf >= 4 ? 2 : nf >= 2 ? 1 : 0);
           p->launches += 1;
         }

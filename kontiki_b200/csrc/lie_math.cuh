@@ -23,6 +23,13 @@ struct V3 { double x, y, z; };
 template <int N> struct Mr { double a[3 * N]; };   // N x 3, row-major
 using M3 = Mr<3>;
 
+// A sequence point for the compiler: independent chains of fp64 work on either side are not interleaved (interleaving two reverse sweeps for
+// instruction-level parallelism doubled the live state and cost kilobytes of spill per thread in the 255-register kernels).
+#if defined(__CUDA_ARCH__) && !defined(KTK_NO_SEQ)      // -DKTK_NO_SEQ: A/B builds (tools/build_variant.sh)
+#define KB_SEQ() asm volatile("" ::: "memory")
+#else
+#define KB_SEQ() ((void)0)
+#endif
 KB_HD V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
 KB_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 KB_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }

@@ -503,11 +503,6 @@ KB_HD int newton_rs_row_fast(const SplineConst& sp, const CameraConst& cam, cons
 // record.  The radial component along the raw quaternion of knot i0 (the Jacobian is ambient) has three sources: p (inside
 // pose_backward), v = R(q0 raw) M_t => dv/ds = 2 (v - R0^T v), and w = vee(R(q0 raw) M_R R^T) => dw/ds = 2 w - vee2(R0^T hat(w)) (as in gyro_se3).
 // Second derivatives of the camera model: the gradient of h with respect to (X_cam, dX_cam) is taken by six dual evaluations of the PROJECTION alone.
-#if defined(__CUDA_ARCH__)
-#define KB_SEQ() asm volatile("" ::: "memory")
-#else
-#define KB_SEQ() ((void)0)
-#endif
 template <int N>
 KB_HD void twist_backward(const double* p1, const double* p2, const double* p3, const Basis& bs, const Mr<N>& Gv, const Mr<N>& Gw, double scale, double* J) {
   // one exp part alive at a time (the reverse order needs A3 first): A2 is rebuilt for its level, like in the accelerometer's sweep
@@ -1044,8 +1039,10 @@ KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam,
   const double* p1 = pairs + (size_t)(io + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
   Pose P;
   pose_forward(k0, p1, p2, p3, bs, P);
+  KB_SEQ();
   V3 vb, wb, dvb;
   se3_body_twist(p1, p2, p3, bs, vb, wb, dvb);
+  KB_SEQ();
   const V3 X = v3(rec[0], rec[1], rec[2]), dXr = v3(rec[3], rec[4], rec[5]);
   const double rho = rec[6];
   const M3 Rct = load_m3(cam.Rct);
@@ -1082,6 +1079,7 @@ KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam,
     Jrho[i] = Jp.a[3 * i] * dXc.x + Jp.a[3 * i + 1] * dXc.y + Jp.a[3 * i + 2] * dXc.z;
     Jvt[i] = cam.readout * (Go.a[3 * i] * dXobs_dt.x + Go.a[3 * i + 1] * dXobs_dt.y + Go.a[3 * i + 2] * dXobs_dt.z) + C[3 * i + 2] * (weight * rows);
   }
+  KB_SEQ();
   // reference-window blocks: GX (3x3) * dX/dknot_k (3x7)
   const double* dXk = rec + kRefDOff;
 #pragma unroll
@@ -1091,6 +1089,7 @@ KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam,
 #pragma unroll
       for (int c = 0; c < 7; ++c)
         Jref[21 * k + 7 * i + c] = GX.a[3 * i] * dXk[21 * k + c] + GX.a[3 * i + 1] * dXk[21 * k + 7 + c] + GX.a[3 * i + 2] * dXk[21 * k + 14 + c];
+  KB_SEQ();
   pose_backward<3>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, Jobs);
   return 0;
 }

@@ -400,6 +400,7 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
   // (988 B of spill per thread in round 1).  The adjoints the NEXT level needs are formed as soon as their inputs exist and PARKED in the
   // part of the output row that is not written yet (J[0..36) during level 3, J[0..18) during level 2 -- the row is built back to front), so
   // that only gj and t are live across the expensive part.
+  KB_SEQ();
   G6<3> gs, gd, gj, t;
   gs.U = hat(wb); gs.W = (-1.0) * hat(vb);
   gd.U = m3_identity(); gd.W = m3_zero();
@@ -419,6 +420,7 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
     contract_pair<3, false>(J + 42, gj, p3 + kPairDOff, sc);
     T = e.E;
   }
+  KB_SEQ();
   {
     exp_part(p2, bs.B[1], true, true, e);
 #pragma unroll
@@ -438,6 +440,7 @@ KB_HD void accel_se3(const double* knot0, const double* p1, const double* p2, co
     contract_pair<3, false>(J + 21, gj, p2 + kPairDOff, sc);
     T = e.E * T;
   }
+  KB_SEQ();
   {
     exp_part(p1, bs.B[0], false, false, e);
 #pragma unroll
