@@ -626,7 +626,7 @@ def main():
                     "api": "ktk_evaluate (C ABI, pinned host buffers; every residual, Jacobian row and index copied back)", "numa": numa},
             "gpu_launches": int(launches),
             "clocks": dict(clocks.summary(), sampled="under the same steps, immediately after the timed region (sampler outside the event pair)"),
-            "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_newton_rs", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
+            "roofline": {"bound": "hbm", "kernel": {"cam": dict(newton="k_landmark_ref + k_newton_rs_fast + k_newton_rs_rev (+ k_newton_rs)", lifting="k_lifting_rs").get(a.camera_method, "k_static_rs"), "accel": "k_imu<1>", "gyro": "k_imu<0>"}[dom],
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                          "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,

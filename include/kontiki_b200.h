@@ -105,7 +105,8 @@ typedef struct {
 typedef ktk_camera ktk_pinhole_camera;   /* model = KTK_CAMERA_PINHOLE */
 
 /* Per measurement group output pointers (any may be NULL).  Host pointers for ktk_evaluate, device pointers for
- * ktk_evaluate_device.  Sizes for n rows: r n*3 (IMU, position) / n*2 (camera) / n (orientation); J n*84 / n*114 / n*28
+ * ktk_evaluate_device.  Device J pointers must be 16-byte aligned (rows leave the SM as TMA bulk stores; cudaMalloc and
+ * torch allocations are): KTK_EINVAL otherwise.  Sizes for n rows: r n*3 (IMU, position) / n*2 (camera) / n (orientation); J n*84 / n*114 / n*28
  * (ktk_group_row_size); i0 n; i0_b n (camera: obs). */
 typedef struct {
   double* r;

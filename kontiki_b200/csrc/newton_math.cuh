@@ -1022,9 +1022,14 @@ KB_HD int span_sensor_column(bool lifting, const SplineConst& sp, const CameraCo
 // (v_b, w_b) of the spline at t_obs:  d Xobs / d t = -w_b x Xobs - rho v_b   (Xobs = R^T (X - rho p)),  so
 //   d r / d vt = (d r / d Xc) R_ct (d Xobs / d t) readout + C [:, 2] weight rows.
 // Outputs: r (3), Jref [4][3][7] (84), Jobs [4][3][7] (84: the ACTIVE window, first knot *i0_obs), Jvt (3), Jrho (3).
-KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
-                                  const double* obs_uv, double obs_t0, double ref_t0, double vt, double weight, double huber_c,
-                                  double* r, double* Jref, double* Jobs, double* Jvt, double* Jrho, int* i0_ref, int* i0_obs) {
+// Two parts, so that a kernel can stage the landmark record INSIDE the row it builds (k_lifting_rs_t): the first part consumes the record (residual,
+// reference-window blocks, the two tail columns as values), the second is the reverse sweep into the observation blocks and needs none of it.
+struct LiftingMid { Mr<3> Gp, GpR, Gth; double jvt[3], jrho[3]; int io; double uo; };
+KB_HD int lifting_rs_row_first(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                               const double* obs_uv, double obs_t0, double ref_t0, double vt, double weight, double huber_c,
+                               double* r, double* Jref, int* i0_ref, LiftingMid& mid) {
+  double* Jvt = mid.jvt; double* Jrho = mid.jrho;
+  int i0_obs_v; int* i0_obs = &i0_obs_v;
   Segment s0, s1;
   const int nseg = static_rs_segments(sp, cam, ref_t0, obs_t0, s0, s1);
   if (nseg == 0) return kStatusRange;
@@ -1089,8 +1094,52 @@ KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam,
 #pragma unroll
       for (int c = 0; c < 7; ++c)
         Jref[21 * k + 7 * i + c] = GX.a[3 * i] * dXk[21 * k + c] + GX.a[3 * i + 1] * dXk[21 * k + 7 + c] + GX.a[3 * i + 2] * dXk[21 * k + 14 + c];
+  mid.Gp = rscale(-rho, GX); mid.GpR = rscale(-rho, Go); mid.Gth = rmul_hat(Go, Xobs); mid.io = io; mid.uo = uo;
+  return 0;
+}
+KB_HD void lifting_rs_row_second(const SplineConst& sp, const double* knots, const double* pairs, const LiftingMid& mid, double* Jobs) {
+  const Basis bs = cumulative_basis(mid.uo, sp.dt);
+  const double* k0 = knots + (size_t)mid.io * kKnotStride;
+  const double* p1 = pairs + (size_t)(mid.io + 1) * kPairStride; const double* p2 = p1 + kPairStride; const double* p3 = p2 + kPairStride;
+  pose_backward<3>(k0, p1, p2, p3, bs, mid.Gp, mid.GpR, mid.Gth, 1.0, Jobs);
+}
+KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
+                                  const double* obs_uv, double obs_t0, double ref_t0, double vt, double weight, double huber_c,
+                                  double* r, double* Jref, double* Jobs, double* Jvt, double* Jrho, int* i0_ref, int* i0_obs) {
+  LiftingMid mid;
+  const int st = lifting_rs_row_first(sp, cam, knots, pairs, rec, obs_uv, obs_t0, ref_t0, vt, weight, huber_c, r, Jref, i0_ref, mid);
+  if (st != 0) return st;
+  *i0_obs = mid.io;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { Jvt[c] = mid.jvt[c]; Jrho[c] = mid.jrho[c]; }
   KB_SEQ();
-  pose_backward<3>(k0, p1, p2, p3, bs, rscale(-rho, GX), rscale(-rho, Go), rmul_hat(Go, Xobs), 1.0, Jobs);
+  lifting_rs_row_second(sp, knots, pairs, mid, Jobs);
+  return 0;
+}
+// The row as k_lifting_rs_t builds it: `row` (>= max(176, 90 + 21 W) doubles) holds the landmark record at row + 84 on entry and the finished packed row
+// [ref 4 x (3 x 7) | obs W x (3 x 7) | vt 3 | rho 3] on return -- observation blocks written in place at their position inside the span, zeros elsewhere.
+// On failure the row is NaN where a healthy row has its reference and first four observation blocks and its tails (zeros elsewhere), like k_lifting_rs.
+KB_HD int lifting_rs_row_staged(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* obs_uv, double obs_t0,
+                                double ref_t0, double vt, int kbase, int W, double weight, double huber_c, double* r, double* row, int* i0_ref) {
+  LiftingMid mid;
+  int st = lifting_rs_row_first(sp, cam, knots, pairs, row + 84, obs_uv, obs_t0, ref_t0, vt, weight, huber_c, r, row, i0_ref, mid);
+  if (st == 0 && (mid.io < kbase || mid.io + 4 > kbase + W)) st = kStatusRange;
+  KB_SEQ();                                             // the record is consumed: its place becomes the observation span
+  const int tail0 = 84 + 21 * W;
+#pragma unroll 1
+  for (int c = 84; c < tail0; ++c) row[c] = 0.0;
+  if (st != 0) {
+    const double qn = nan("");
+    r[0] = r[1] = r[2] = qn; *i0_ref = -1;
+#pragma unroll 1
+    for (int c = 0; c < 168; ++c) row[c] = qn;
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) row[tail0 + c] = qn;
+    return st;
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { row[tail0 + c] = mid.jvt[c]; row[tail0 + 3 + c] = mid.jrho[c]; }
+  lifting_rs_row_second(sp, knots, pairs, mid, row + 84 + 21 * (mid.io - kbase));
   return 0;
 }
 // ... packed into the C ABI's row [ref 4 x (3x7) | obs W x (3x7) | vt 3 | rho 3] (the blocks of the span outside the active window are zero)
