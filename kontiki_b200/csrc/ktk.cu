@@ -11,7 +11,9 @@
 //                    both under the observation-pose math; every thread builds its whole 912-B row in shared memory and the row
 //                    leaves with ONE TMA bulk store to the caller's row index (one store per 32-row tile with KTK_EVAL_DEVICE_ORDER)
 //   k_static_rs_local  the same rows in tangent coordinates (KTK_EVAL_LOCAL), staged in two halves and scattered cooperatively
-//   k_newton_rs_fast / k_newton_rs, k_lifting_rs   NewtonRs rows (closed form where the iteration stops at once, forward mode else), LiftingRs rows
+//   k_newton_rs_fast + k_newton_rs_rev   NewtonRs rows in closed form: static row at the last row time of the iteration + pi'(t_last) (x) d t_last / d theta
+//                    (one reverse sweep per evaluation); k_newton_rs: forward mode through the iteration for the rows that path cannot do
+//   k_lifting_rs (k_lifting_rs_t: built in place, one TMA bulk store per row)   LiftingRs rows, closed form
 //   k_*_split        the same measurements on a split (R3 + SO3) trajectory; k_span_rs_split: NewtonRs / LiftingRs there (forward mode)
 //   k_imu_sensor, k_static_rs_sensor, k_span_sensor   columns of the sensors' own parameter blocks (KTK_EVAL_SENSOR_JACOBIANS); k_span_localize*: local rows
 //   k_gn_* (gn_device.cuh)   Gauss-Newton / LM step on the rows left in device memory
@@ -1178,32 +1180,8 @@ __global__ void __launch_bounds__(32) k_newton_rs_fast(const NewtonArgs a, int* 
 }
 
 // Rows of the list whose iteration stopped after its second evaluation (mode 2): k_newton_rs_fast wrote the static row at t_1; every column gets
-// + finish(pi'(t_1) d t_1 / d theta) from ONE dual evaluation at the initial row time (newton_math.cuh "newton_rs_two_step_column").
-__global__ void __launch_bounds__(128) k_newton_rs_two(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
-  const int ndir = 29 + 7 * a.W, row_len = 58 + 14 * a.W;
-  if (!(a.J && (a.flags & KTK_EVAL_JACOBIANS))) return;
-  // the list's length is only known on the device: a fixed grid strides over (listed rows) x (directions) instead of launching n x ndir threads
-  const long long total = (long long)slow[0] * ndir;
-  for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) {
-  const int k = (int)(tid / ndir), dir = (int)(tid % ndir);
-  const double* ax = slow_aux + 6 * (size_t)k;
-  if (ax[0] != 2.0) continue;
-  const int i = slow[1 + k];
-  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
-  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
-  const double obs_t0 = a.obs_t0[i];
-  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
-  double j[2];
-  const int st = newton_rs_two_step_column(a.sp, a.cam, a.knots, a.pairs, a.recs + (size_t)a.ref_idx[i] * kRefStride, ouv, obs_t0, a.ref_t0[i], kbase, a.W, a.w[i],
-                                           (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, ax + 1, dir, j);
-  int stride;
-  const int off = newton_dir_offset(dir, a.W, stride);
-  double* Jr = a.J + dst * row_len;
-  if (st != 0) { atomicMin(a.err, st); Jr[off] = nan(""); Jr[off + stride] = nan(""); }
-  else { Jr[off] += j[0]; Jr[off + stride] += j[1]; }
-  }
-}
-// The same correction, one WARP per listed row and 32 dual evaluations instead of 29 + 7 W (newton_math.cuh "newton_rs_first_step_lane"): lanes 0..27 the
+// + finish(pi'(t_1) d t_1 / d theta).  KTK_NEWTON_FAST=2 / 3 (kept as the cross-check of the closed form and for spans too wide for its staging):
+// one WARP per listed row and 32 dual evaluations instead of 29 + 7 W (newton_math.cuh "newton_rs_first_step_lane"): lanes 0..27 the
 // four observation knots active at the initial row time, lanes 28..31 the gradient of f/df with respect to the landmark X and rho, from which the 28
 // reference-window columns and the rho column follow by the chain rule through the landmark record.  Lane L < 28 writes its observation column and
 // reference column L, lane 28 the rho column: every column has one writer, no atomics.
@@ -1308,7 +1286,7 @@ __device__ __forceinline__ void newton_rs_item(const NewtonArgs& a, const int* _
   const double obs_t0 = a.obs_t0[i];
   const int ridx = a.ref_idx[i];
   const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
-  if (ax && ax[0] == 2.0) return;      // two-evaluation row: k_newton_rs_fast + k_newton_rs_two
+  if (ax && ax[0] == 2.0) return;      // finished by k_newton_rs_fast + k_newton_rs_rev (or k_newton_rs_two_w)
   int st = kStatusRange;
   double r[2] = {nan(""), nan("")}, j[2] = {nan(""), nan("")};
   int ir = -1;
@@ -1336,7 +1314,7 @@ __device__ __forceinline__ void newton_rs_item(const NewtonArgs& a, const int* _
 }
 __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int* __restrict__ slow, const double* __restrict__ slow_aux) {
   if (slow && slow[a.n + 1] == 0) return;      // every listed row was finished in closed form
-  const long long total = (long long)(slow ? slow[0] : a.n) * (29 + 7 * a.W);      // fixed grid, strided (see k_newton_rs_two)
+  const long long total = (long long)(slow ? slow[0] : a.n) * (29 + 7 * a.W);      // fixed grid striding over the device-side list (its length is only known on the device)
   for (long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (long long)gridDim.x * blockDim.x) newton_rs_item(a, slow, slow_aux, tid);
 }
 
@@ -1500,8 +1478,8 @@ struct ktk_problem {
   int lift_tma = 0;               // KTK_LIFT_TMA=1: LiftingRs rows built in place and sent with one TMA bulk store per row (k_lifting_rs_t)
   int newton_fast = 4;            // 4: every row in closed form whatever its number of evaluations: static row at t_last (k_newton_rs_fast) + jfin (x) d t_last / d theta
                                   //    by one reverse sweep per evaluation (k_newton_rs_rev); forward mode only where that fails (out-of-range rows);
-                                  // 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
-                                  //    k_newton_rs_two_w); 2: the same with one dual evaluation per direction (29 + 7 W per row, k_newton_rs_two);
+                                  // 2, 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
+                                  //    k_newton_rs_two_w);
                                   // 1: only one-evaluation rows; 0: every Newton-RS row through the forward-mode kernel (KTK_NEWTON_FAST, A/B and cross-check)
   // -1 (default): the IMU-like groups of an evaluation go out in ONE launch (k_short_batch) when the problem has no camera rows -- a chain of
   // one-wave kernels is launch-bound (C2 -2.6 %, C1: 3 kernels) -- and as one launch per group next to camera rows, where the fused launch measured
@@ -2151,8 +2129,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
           const unsigned gr = (unsigned)std::min<long long>((g.n + 31) / 32, (long long)p->sm_count * 16);
           k_newton_rs_rev<<<gr, 32, rev_smem, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1;
         }
-        else if (nf == 3) { k_newton_rs_two_w<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
-        else if (nf == 2) { k_newton_rs_two<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
+        else if (nf >= 2) { k_newton_rs_two_w<<<grid, 128, 0, s>>>(na, g.d_slow.p, g.d_slow_aux.p); p->launches += 1; }
         k_newton_rs<<<grid, 128, 0, s>>>(na, p->newton_fast ? g.d_slow.p : nullptr, g.d_slow_aux.p);
       }
       if (localize) {

@@ -400,20 +400,7 @@ KB_HD int newton_rs_row_closed(const SplineConst& sp, const CameraConst& cam, co
   if (!o.clamped_last && newton_rs_time_derivative(sp, cam, knots, pairs, rec, obs_t0, ref_t0, kbase, W, o.t_last, aux + 2) != 0) return -1;
   return 2;
 }
-// ... and the correction of one column of such a row (mode 2): j (2) to ADD at newton_dir_offset(dir)
-KB_HD int newton_rs_two_step_column(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec, const double* ouv,
-                                    double obs_t0, double ref_t0, int kbase, int W, double weight, double huber_c, const double* aux, int dir, double* j) {
-  j[0] = j[1] = 0.0;
-  if (aux[2] == 0.0 && aux[3] == 0.0) return 0;
-  double dtd;
-  const int st = newton_rs_first_step_d(sp, cam, knots, pairs, rec, ouv, obs_t0, ref_t0, kbase, W, dir, dtd);
-  if (st != 0) return st;
-  NewtonRow oo; oo.y[0] = aux[0]; oo.y[1] = aux[1]; oo.dy[0] = -aux[2] * dtd; oo.dy[1] = -aux[3] * dtd; oo.iterations = 2;      // d t_1 = -d(f/df)
-  double r[2];
-  newton_rs_finish(oo, ouv, weight, huber_c, r, j);
-  return 0;
-}
-// The same correction with 32 dual evaluations per row instead of 29 + 7 W (what k_newton_rs_two runs, one warp per row).  f/df at the initial row
+// ... and the correction of such a row (mode 2) with 32 dual evaluations per row instead of 29 + 7 W (what k_newton_rs_two_w runs, one warp per row).  f/df at the initial row
 // time sees the reference window and rho only THROUGH the landmark X (and rho directly), so its derivative along the 28 reference directions is the
 // chain rule g_X . dX/dknot[:, c] with g_X from three evaluations seeded on the components of X, along rho g_X . dX/drho + g_rho; and of the 7 W
 // observation directions only the four knots active at the initial row time have a derivative at all.  Lane layout:
