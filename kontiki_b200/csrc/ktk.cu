@@ -13,7 +13,7 @@
 //   k_static_rs_local  the same rows in tangent coordinates (KTK_EVAL_LOCAL), staged in two halves and scattered cooperatively
 //   k_newton_rs_fast + k_newton_rs_rev   NewtonRs rows in closed form: static row at the last row time of the iteration + pi'(t_last) (x) d t_last / d theta
 //                    (one reverse sweep per evaluation); k_newton_rs: forward mode through the iteration for the rows that path cannot do
-//   k_lifting_rs (k_lifting_rs_t: built in place, one TMA bulk store per row)   LiftingRs rows, closed form
+//   k_lifting_rs     LiftingRs rows, closed form
 //   k_*_split        the same measurements on a split (R3 + SO3) trajectory; k_span_rs_split: NewtonRs / LiftingRs there (forward mode)
 //   k_imu_sensor, k_static_rs_sensor, k_span_sensor   columns of the sensors' own parameter blocks (KTK_EVAL_SENSOR_JACOBIANS); k_span_localize*: local rows
 //   k_gn_* (gn_device.cuh)   Gauss-Newton / LM step on the rows left in device memory
@@ -1323,7 +1323,6 @@ __global__ void __launch_bounds__(128) k_newton_rs(const NewtonArgs a, const int
 // [Jref 84 | Jobs 84 | vt 3 | rho 3] in shared memory; the warp then writes the 32 packed rows [ref 4 x (3x7) | obs W x (3x7) | vt 3 | rho 3]
 // cooperatively (8-byte stores, consecutive lanes on consecutive doubles), the active window at its place inside the W-knot span and zeros elsewhere.
 constexpr int kLiftStage = 176;      // 174 staged doubles per row, padded to a 16-byte multiple
-constexpr int kLiftTmaSmemMax = 100 * 1024;      // k_lifting_rs_t keeps the whole packed row (90 + 21 W doubles) per lane: W <= 14; wider spans take k_lifting_rs
 __global__ void __launch_bounds__(32) k_lifting_rs(const NewtonArgs a, const double* __restrict__ vt) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31;
@@ -1375,45 +1374,6 @@ __global__ void __launch_bounds__(32) k_lifting_rs(const NewtonArgs a, const dou
   }
 }
 
-// The same rows built IN PLACE (KTK_LIFT_TMA, even W): the warp gathers its 32 landmark records into the rows' own buffers (coalesced; a thread reading its
-// 736-B record by itself touches 32 sectors per load instruction), the thread consumes the record, zeroes the observation span where the record was, lets
-// the reverse sweep write the four active blocks at their final position, and the finished packed row (90 + 21 W doubles, a multiple of 16 B for even W)
-// leaves with ONE TMA bulk store like the static rows: no scatter loop (224 iterations of ~14 instructions per tile in k_lifting_rs).
-__global__ void __launch_bounds__(32) k_lifting_rs_t(const NewtonArgs a, const double* __restrict__ vt, int stride) {
-  extern __shared__ __align__(16) double smem[];
-  const int lane = threadIdx.x & 31;
-  double* row = smem + (size_t)lane * stride;
-  const int i = blockIdx.x * 32 + lane;
-  const bool wantJ = a.J && (a.flags & KTK_EVAL_JACOBIANS);
-  const int row_len = 90 + 21 * a.W;
-  const int ridx = i < a.n ? a.ref_idx[i] : -1;
-  for (int rr = 0; rr < 32; ++rr) {
-    const int rx = __shfl_sync(0xffffffffu, ridx, rr);
-    if (rx < 0) continue;
-    const double* src = a.recs + (size_t)rx * kRefStride;
-    double* dst = smem + (size_t)rr * stride + 84;
-    for (int c = lane; c < kRefStride; c += 32) dst[c] = src[c];
-  }
-  __syncwarp();
-  if (i >= a.n) return;
-  const size_t dst = (size_t)((a.flags & KTK_EVAL_DEVICE_ORDER) ? i : a.perm[i]);
-  const double ouv[2] = {a.obs_uv[2 * (size_t)i], a.obs_uv[2 * (size_t)i + 1]};
-  const double obs_t0 = a.obs_t0[i];
-  const int kbase = newton_obs_window_base(a.sp, a.cam, obs_t0);
-  int ir = -1;
-  double r[3];
-  if (ridx < 0) row[84 + 7] = -1.0;            // no landmark record: the row fails on its reference index like a record that is out of range
-  const int st = lifting_rs_row_staged(a.sp, a.cam, a.knots, a.pairs, ouv, obs_t0, a.ref_t0[i], vt[i], kbase, a.W, a.w[i],
-                                       (a.flags & KTK_EVAL_ROBUST) ? a.huber[i] : 0.0, r, row, &ir);
-  if (st != 0) atomicMin(a.err, st);
-  if (a.r) { a.r[3 * dst] = r[0]; a.r[3 * dst + 1] = r[1]; a.r[3 * dst + 2] = r[2]; }
-  if (a.i0r) a.i0r[dst] = ir;
-  if (a.i0o) a.i0o[dst] = st == 0 ? kbase : -1;
-  if (!wantJ) return;
-  fence_async_smem();
-  bulk_store(a.J + dst * row_len, row, (unsigned)(row_len * 8));
-  bulk_store_wait_read();
-}
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 template <class T> struct DevBuf {
@@ -1475,7 +1435,6 @@ struct ktk_problem {
   int cam_resident_tiles = 0;     // prefetch distance of k_static_rs (tiles), see ktk_problem_create
   int imu_resident_tiles = 0;     // ... of the IMU-row kernels
   int sm_count = 148;
-  int lift_tma = 0;               // KTK_LIFT_TMA=1: LiftingRs rows built in place and sent with one TMA bulk store per row (k_lifting_rs_t)
   int newton_fast = 4;            // 4: every row in closed form whatever its number of evaluations: static row at t_last (k_newton_rs_fast) + jfin (x) d t_last / d theta
                                   //    by one reverse sweep per evaluation (k_newton_rs_rev); forward mode only where that fails (out-of-range rows);
                                   // 2, 3: rows that stop after one OR two evaluations in closed form; the latter + 32 dual evaluations per row (one warp per row,
@@ -1713,12 +1672,10 @@ int ktk_problem_create(int device, ktk_problem** out) {
   cudaFuncSetAttribute(k_static_rs_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamThreads / 32) * kCamWarpSmem * 8);
   cudaFuncSetAttribute(k_landmark_ref, cudaFuncAttributeMaxDynamicSharedMemorySize, kThreads * kRefStride * 8);
   cudaFuncSetAttribute(k_lifting_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kLiftStage * 8);
-  cudaFuncSetAttribute(k_lifting_rs_t, cudaFuncAttributeMaxDynamicSharedMemorySize, kLiftTmaSmemMax);
   cudaFuncSetAttribute(k_static_rs, cudaFuncAttributeMaxDynamicSharedMemorySize, kCamThreads * kCamDevStride * 8);
   cudaFuncSetAttribute(k_short_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kAccelRowStride * 8);
   if (const char* v = getenv("KTK_FUSE_SHORT")) p->fuse_short = atoi(v);
   if (const char* v = getenv("KTK_NEWTON_FAST")) p->newton_fast = atoi(v);
-  if (const char* v = getenv("KTK_LIFT_TMA")) p->lift_tma = atoi(v);
   cudaFuncSetAttribute(k_newton_rs_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * kNewtonStage * 8);
   cudaFuncSetAttribute(k_newton_rs_rev, cudaFuncAttributeMaxDynamicSharedMemorySize, kNewtonRevSmemMax);
   {   // tiles of k_static_rs resident on the chip = the distance of its input prefetch (7 warps x 148 SMs = 1036 on a B200)
@@ -2107,13 +2064,7 @@ static int evaluate_device_se3(ktk_problem* p, const double* d_knots, const doub
         if (!na.i0o) na.i0o = g.o_amb_i0b.p;
       }
       if (g.kind == KTK_LIFTING_RS) {
-        // rows built in place + one TMA bulk store per row: needs 16-byte rows (even W) and the row (>= 176 doubles, stride = 2 mod 4 against bank
-        // conflicts) in shared memory
-        int lstride = std::max(176, 90 + 21 * na.W); lstride += (lstride & 1); if ((lstride & 3) == 0) lstride += 2;
-        if (p->lift_tma && (na.W & 1) == 0 && 32 * lstride * 8 <= kLiftTmaSmemMax)
-          k_lifting_rs_t<<<(unsigned)((g.n + 31) / 32), 32, 32 * lstride * 8, s>>>(na, g.d_vt.p, lstride);
-        else
-          k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
+        k_lifting_rs<<<(unsigned)((g.n + 31) / 32), 32, 32 * kLiftStage * 8, s>>>(na, g.d_vt.p);
       } else {
         const long long threads = (long long)g.n * (29 + 7 * na.W);
         const int rev_smem = 32 * ((29 + 7 * na.W) | 1) * 8;

@@ -1009,8 +1009,8 @@ KB_HD int span_sensor_column(bool lifting, const SplineConst& sp, const CameraCo
 // (v_b, w_b) of the spline at t_obs:  d Xobs / d t = -w_b x Xobs - rho v_b   (Xobs = R^T (X - rho p)),  so
 //   d r / d vt = (d r / d Xc) R_ct (d Xobs / d t) readout + C [:, 2] weight rows.
 // Outputs: r (3), Jref [4][3][7] (84), Jobs [4][3][7] (84: the ACTIVE window, first knot *i0_obs), Jvt (3), Jrho (3).
-// Two parts, so that a kernel can stage the landmark record INSIDE the row it builds (k_lifting_rs_t): the first part consumes the record (residual,
-// reference-window blocks, the two tail columns as values), the second is the reverse sweep into the observation blocks and needs none of it.
+// Two parts: the first consumes the landmark record (residual, reference-window blocks, the two tail columns as values), the second is the reverse sweep
+// into the observation blocks and needs none of it (a kernel may reuse the record's staging space in between; a sequence point keeps them apart).
 struct LiftingMid { Mr<3> Gp, GpR, Gth; double jvt[3], jrho[3]; int io; double uo; };
 KB_HD int lifting_rs_row_first(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* rec,
                                const double* obs_uv, double obs_t0, double ref_t0, double vt, double weight, double huber_c,
@@ -1101,32 +1101,6 @@ KB_HD int lifting_rs_row_analytic(const SplineConst& sp, const CameraConst& cam,
   for (int c = 0; c < 3; ++c) { Jvt[c] = mid.jvt[c]; Jrho[c] = mid.jrho[c]; }
   KB_SEQ();
   lifting_rs_row_second(sp, knots, pairs, mid, Jobs);
-  return 0;
-}
-// The row as k_lifting_rs_t builds it: `row` (>= max(176, 90 + 21 W) doubles) holds the landmark record at row + 84 on entry and the finished packed row
-// [ref 4 x (3 x 7) | obs W x (3 x 7) | vt 3 | rho 3] on return -- observation blocks written in place at their position inside the span, zeros elsewhere.
-// On failure the row is NaN where a healthy row has its reference and first four observation blocks and its tails (zeros elsewhere), like k_lifting_rs.
-KB_HD int lifting_rs_row_staged(const SplineConst& sp, const CameraConst& cam, const double* knots, const double* pairs, const double* obs_uv, double obs_t0,
-                                double ref_t0, double vt, int kbase, int W, double weight, double huber_c, double* r, double* row, int* i0_ref) {
-  LiftingMid mid;
-  int st = lifting_rs_row_first(sp, cam, knots, pairs, row + 84, obs_uv, obs_t0, ref_t0, vt, weight, huber_c, r, row, i0_ref, mid);
-  if (st == 0 && (mid.io < kbase || mid.io + 4 > kbase + W)) st = kStatusRange;
-  KB_SEQ();                                             // the record is consumed: its place becomes the observation span
-  const int tail0 = 84 + 21 * W;
-#pragma unroll 1
-  for (int c = 84; c < tail0; ++c) row[c] = 0.0;
-  if (st != 0) {
-    const double qn = nan("");
-    r[0] = r[1] = r[2] = qn; *i0_ref = -1;
-#pragma unroll 1
-    for (int c = 0; c < 168; ++c) row[c] = qn;
-#pragma unroll 1
-    for (int c = 0; c < 6; ++c) row[tail0 + c] = qn;
-    return st;
-  }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { row[tail0 + c] = mid.jvt[c]; row[tail0 + 3 + c] = mid.jrho[c]; }
-  lifting_rs_row_second(sp, knots, pairs, mid, row + 84 + 21 * (mid.io - kbase));
   return 0;
 }
 // ... packed into the C ABI's row [ref 4 x (3x7) | obs W x (3x7) | vt 3 | rho 3] (the blocks of the span outside the active window are zero)

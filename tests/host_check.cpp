@@ -106,7 +106,7 @@ void hc_newton_rs(double t0, double dt, int n_knots, const double* K, const doub
     i0_ref[i] = (int)rec[7]; kbase_out[i] = kbase;
   }
 }
-static int g_lifting_analytic = 0;      // 0: forward-mode directions (k_lifting_rs_fwd), 1: closed form (k_lifting_rs), 2: closed form staged in the row (k_lifting_rs_t)
+static int g_lifting_analytic = 0;      // 0: forward-mode directions (k_lifting_rs_fwd), 1: closed form (k_lifting_rs)
 void hc_set_lifting_analytic(int on) { g_lifting_analytic = on; }
 // LiftingRsCameraMeasurement rows: what k_landmark_ref + k_lifting_rs do.  J: n x (90 + 21 W) packed [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3].
 void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const double* Kinv, const double* q_ct, const double* p_ct,
@@ -134,15 +134,7 @@ void hc_lifting_rs(double t0, double dt, int n_knots, const double* K, const dou
     status[i] = landmark_ref_row(sp, cam, knots8, pairs, ref_uv + 2 * i, ref_t0[i], sr.start, sr.n, rho[lm_idx[i]], rec);
     if (status[i] != 0) continue;
     const int kbase = newton_obs_window_base(sp, cam, obs_t0[i]);
-    if (g_lifting_analytic == 2) {          // the row as k_lifting_rs_t builds it: landmark record staged inside the row, observation blocks written in place
-      std::vector<double> row((size_t)std::max(176, row_len) + 2);
-      for (int c = 0; c < kRefStride; ++c) row[84 + c] = rec[c];
-      int ir = -1;
-      status[i] = lifting_rs_row_staged(sp, cam, knots8, pairs, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
-                                        r + 3 * i, row.data(), &ir);
-      for (int c = 0; c < row_len; ++c) J[(size_t)row_len * i + c] = row[c];
-    }
-    else if (g_lifting_analytic)
+    if (g_lifting_analytic)
       status[i] = lifting_rs_row_packed(sp, cam, knots8, pairs, rec, obs_uv + 2 * i, obs_t0[i], ref_t0[i], vt[i], kbase, W, w[i], huber_c ? huber_c[i] : 0.0,
                                         r + 3 * i, J + (size_t)row_len * i);
     else

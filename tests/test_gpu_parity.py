@@ -749,31 +749,6 @@ def test_orientation_rows_match_oracle(split, local):
         p2.evaluate(syn.smooth_se3_knots(300, 0.05))
 
 
-def test_lifting_rows_built_in_place_equal_the_scattered_rows(monkeypatch):
-    """KTK_LIFT_TMA=1 (k_lifting_rs_t: landmark records gathered into the rows' buffers, observation blocks written at their final place, one TMA bulk
-    store per row) produces the rows of k_lifting_rs bit for bit, in caller and in device order, with and without the loss."""
-    cfg = syn.make_config("C3", scale=0.004)
-    c = cfg["cam"]
-    rng = np.random.default_rng(36)
-    n = len(c["lm_idx"])
-    c["weight"] = rng.uniform(0.5, 2, n)
-    vt = np.clip(c["obs_uv"][:, 1] / c["rows"] + rng.uniform(-0.3, 0.3, n), 0.0, 1.0)
-    outs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("KTK_LIFT_TMA", mode)
-        p, g, _ = _camera_group(cfg, "lifting", False)
-        p.set_group_vt(g, vt)
-        for flags in (_lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_ROBUST, _lib.EVAL_RESIDUALS | _lib.EVAL_JACOBIANS | _lib.EVAL_DEVICE_ORDER):
-            outs[mode, flags] = p.evaluate(cfg["knots"], c["rho"], flags)[g]
-    monkeypatch.delenv("KTK_LIFT_TMA")
-    for (mode, flags), o in outs.items():
-        if mode == "1":
-            ref = outs["0", flags]
-            assert np.isfinite(ref["J"]).all(axis=1).sum() > 0.9 * n
-            for key in ("r", "J", "i0", "i0_b"):
-                assert np.array_equal(o[key], ref[key], equal_nan=True), key
-
-
 @pytest.mark.parametrize("atan,robust", [(False, False), (True, True)])
 def test_lifting_rows_match_oracle(atan, robust):
     """LiftingRsCameraMeasurement (lifting_rscamera_measurement.h) through the C ABI: 3 residuals, rows [ref 4x(3x7) | obs W x(3x7) | vt 3 | rho 3];
