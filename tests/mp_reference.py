@@ -21,6 +21,12 @@ Reference sites transcribed (relative to cpplib/include/kontiki/):
   sensors/imu.h:47-59, constants.h:13,24                gyroscope / accelerometer model
   sensors/pinhole_camera.h:47-67, measurements/static_rscamera_measurement.h:21-55, 89-94
   measurements/gyroscope_measurement.h:36-38, accelerometer_measurement.h:37-39
+Widening rows, same rules:
+  sensors/atan_camera.h:54-103 (EvaluateProjection / Unproject), sensors/pinhole_camera.h:47-61 (dy)
+  measurements/newton_rscamera_measurement.h:23-120 (reproject_newton: the Newton iteration on the row time, df from the hand-written first
+    derivatives, math/quaternion_math.h:103-115 dq_from_angular_velocity / vector_sandwich), :150-155 (Error)
+  measurements/lifting_rscamera_measurement.h:21-56 (reproject_lifting), :98-112 (Error, three residuals)
+  measurements/position_measurement.h:22-31, orientation_measurement.h:24-32 (Eigen 3.3 angularDistance = 2 atan2(|vec(d)|, |d.w|), d = q conj(qhat))
 """
 import mpmath as mp
 
@@ -341,6 +347,133 @@ def static_rs_residual(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, rho, weight=1)
     X_cam = [Xc0[i] + p_ct[i] * rho for i in range(3)]
     y = pinhole_project(K, X_cam)
     return [mp.mpf(weight) * (ouv[i] - y[i]) for i in range(2)], er["i0"], eo["i0"]
+
+
+# ---- widening rows: AtanCamera, NewtonRs / LiftingRs camera measurements, Position / Orientation measurements -------------------------------
+def _cam_K(cam):
+    return mp.matrix([[mp.mpf(float(v)) for v in row] for row in cam["K"]])
+
+
+def camera_project(cam, X, dX=None):
+    """EvaluateProjection(X, dX, derive): pinhole_camera.h:47-61, atan_camera.h:54-90 (cam["model"] == "atan": wc, gamma).  Returns (y, dy or None)."""
+    K = _cam_K(cam)
+    if cam.get("model", "pinhole") != "atan":
+        p = K * mp.matrix(X)
+        y = [p[0] / p[2], p[1] / p[2]]
+        if dX is None:
+            return y, None
+        dp = K * mp.matrix(dX)
+        den = p[2] * p[2] + mp.mpf("1e-32")
+        return y, [(dp[0] * p[2] - p[0] * dp[2]) / den, (dp[1] * p[2] - p[1] * dp[2]) / den]
+    eps, gamma, wc = mp.mpf("1e-32"), mp.mpf(cam["gamma"]), mpv(cam["wc"])
+    A = [X[0] / (X[2] + eps), X[1] / (X[2] + eps)]
+    L = [A[0] - wc[0], A[1] - wc[1]]
+    r = mp.sqrt(L[0] * L[0] + L[1] * L[1] + eps)
+    f = mp.atan(r * gamma) / gamma
+    g = [L[0] / r, L[1] / r]
+    Y = mp.matrix([wc[0] + f * g[0], wc[1] + f * g[1], ONE])
+    yy = K * Y
+    y = [yy[0], yy[1]]                                     # "Normalization not needed since Y(2) == 1"
+    if dX is None:
+        return y, None
+    dx = (dX[0] * X[2] - X[0] * dX[2]) / (X[2] * X[2] + eps)
+    dyy = (dX[1] * X[2] - X[1] * dX[2]) / (X[2] * X[2] + eps)
+    common = g[0] * dx + g[1] * dyy
+    df = common / (ONE + gamma * gamma * r * r)
+    du = f * ((dx * r - L[0] * common) / (r * r)) + df * g[0]
+    dv = f * ((dyy * r - L[1] * common) / (r * r)) + df * g[1]
+    d = K * mp.matrix([du, dv, ZERO])
+    return y, [d[0], d[1]]
+
+
+def camera_unproject(cam, y):
+    """pinhole_camera.h:63-67 / atan_camera.h:92-103"""
+    x = mp.inverse(_cam_K(cam)) * mp.matrix([y[0], y[1], ONE])
+    if cam.get("model", "pinhole") != "atan":
+        return [x[0], x[1], x[2]]
+    eps, gamma, wc = mp.mpf("1e-32"), mp.mpf(cam["gamma"]), mpv(cam["wc"])
+    L = [x[0] - wc[0], x[1] - wc[1]]
+    r = mp.sqrt(L[0] * L[0] + L[1] * L[1] + eps)
+    f = mp.tan(r * gamma) / gamma
+    return [wc[0] + f * L[0] / r, wc[1] + f * L[1] / r, ONE]
+
+
+def _landmark(traj, cam, ref_uv, ref_t0, rho):
+    """X = R(t_ref) q_ct^-1 (unproject(ref) - rho p_ct) + rho p(t_ref): the lines the three camera measurements share."""
+    q_ct, p_ct = mpv(cam.get("q_ct", (0, 0, 0, 1))), mpv(cam.get("p_ct", (0, 0, 0)))
+    d = mp.mpf(cam.get("time_offset", 0.0))
+    row_delta = mp.mpf(cam["readout"]) / mp.mpf(cam["rows"])
+    ruv = mpv(ref_uv)
+    er = traj.evaluate(mp.mpf(ref_t0) + d + ruv[1] * row_delta)
+    yh = camera_unproject(cam, ruv)
+    Xr = q_rot(er["orientation"], q_rot(q_conj(q_ct), [yh[i] - rho * p_ct[i] for i in range(3)]))
+    return [Xr[i] + er["position"][i] * rho for i in range(3)], er["i0"], q_ct, p_ct, d, row_delta
+
+
+def _sandwich(qa, x, qb):      # quaternion_math.h:108-115: vec(qa * (x, 0) * qb)
+    return q_mul(q_mul(qa, [x[0], x[1], x[2], ZERO]), qb)[:3]
+
+
+def newton_rs_residual(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, rho, weight=1, max_iterations=5):
+    """newton_rscamera_measurement.h:23-120, :150-155.  Returns (r (2), i0_ref, number of evaluations of the iteration's body)."""
+    X, i0_ref, q_ct, p_ct, d, row_delta = _landmark(traj, cam, ref_uv, ref_t0, rho)
+    ouv = mpv(obs_uv)
+    rows, readout = mp.mpf(cam["rows"]), mp.mpf(cam["readout"])
+    t0_obs = mp.mpf(obs_t0) + d
+    t_obs = t0_obs + ouv[1] * row_delta
+    max_dt2 = (HALF * readout / rows) ** 2
+    lo, hi = t0_obs, t0_obs + readout
+    y, n_eval = None, 0
+    for _ in range(max_iterations):
+        e = traj.evaluate(t_obs)
+        n_eval += 1
+        p, dp, q, w = e["position"], e["velocity"], e["orientation"], e["angular_velocity"]
+        dq = [HALF * v for v in q_mul([w[0], w[1], w[2], ZERO], q)]          # quaternion_math.h:103-106
+        dq_inv, q_inv = q_conj(dq), q_conj(q)
+        s = [X[i] - rho * p[i] for i in range(3)]
+        ds = [-rho * dp[i] for i in range(3)]
+        X_obs = q_rot(q_inv, s)
+        Xc0 = q_rot(q_ct, X_obs)
+        X_cam = [Xc0[i] + rho * p_ct[i] for i in range(3)]
+        a1, a2, a3 = _sandwich(dq_inv, s, q), _sandwich(q_inv, ds, q), _sandwich(q_inv, s, dq)
+        dX_obs = [a1[i] + a2[i] + a3[i] for i in range(3)]
+        dXc0 = q_rot(q_ct, dX_obs)
+        dX_cam = [dXc0[i] + rho * p_ct[i] for i in range(3)]               # sic (:92)
+        y, dy = camera_project(cam, X_cam, dX_cam)
+        f = y[1] - rows * (t_obs - t0_obs) / readout
+        df = dy[1] - rows / readout
+        dt = f / df
+        t_obs = t_obs - dt
+        if dt * dt < max_dt2:
+            break
+        if t_obs < lo:
+            t_obs = lo
+        elif t_obs > hi:
+            t_obs = hi
+    return [mp.mpf(weight) * (ouv[i] - y[i]) for i in range(2)], i0_ref, n_eval
+
+
+def lifting_rs_residual(traj, cam, obs_uv, obs_t0, ref_uv, ref_t0, rho, vt, weight=1):
+    """lifting_rscamera_measurement.h:21-56, :98-112; vt_orig = obs.v / rows (:68).  Returns (r (3), i0_ref, i0 of the lifted evaluation)."""
+    X, i0_ref, q_ct, p_ct, d, _ = _landmark(traj, cam, ref_uv, ref_t0, rho)
+    ouv = mpv(obs_uv)
+    rows = mp.mpf(cam["rows"])
+    eo = traj.evaluate(mp.mpf(obs_t0) + d + vt * mp.mpf(cam["readout"]))
+    X_obs = q_rot(q_conj(eo["orientation"]), [X[i] - rho * eo["position"][i] for i in range(3)])
+    Xc0 = q_rot(q_ct, X_obs)
+    y, _ = camera_project(cam, [Xc0[i] + p_ct[i] * rho for i in range(3)])
+    e = [ouv[0] - y[0], ouv[1] - y[1], rows * (vt - ouv[1] / rows)]
+    return [mp.mpf(weight) * v for v in e], i0_ref, eo["i0"]
+
+
+def position_residual(traj, t, p):                 # position_measurement.h:22-31
+    e = traj.evaluate(mp.mpf(t))
+    return [mp.mpf(float(p[i])) - e["position"][i] for i in range(3)]
+
+
+def orientation_residual(traj, t, q):              # orientation_measurement.h:24-32; Eigen 3.3 Quaternion::angularDistance
+    d = q_mul(mpv(q), q_conj(traj.evaluate(mp.mpf(t))["orientation"]))
+    return [TWO * mp.atan2(mp.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), abs(d[3]))]
 
 
 def jacobian(fun, handles, h=mp.mpf("1e-25")):

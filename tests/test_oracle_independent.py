@@ -205,3 +205,137 @@ def test_split_static_rs_residual_and_jacobian():
         Jb = np.array(mr.jacobian(fun, [(mt.so3, b, c) for b in idb for c in range(4)])).reshape(2, len(idb), 4).transpose(1, 0, 2)
         assert rel(o["Ja"][k, :len(ida)], Ja) < JAC_TOL and rel(o["Jb"][k, :len(idb)], Jb) < JAC_TOL
         assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(2)) < JAC_TOL
+
+
+# ---- widening rows: AtanCamera, NewtonRs / LiftingRs camera measurements, Position / Orientation ------------
+ATAN = dict(model="atan", wc=(0.02, -0.01), gamma=0.9)
+REL = dict(q_ct=tuple(np.array([0.1, -0.05, 0.2, 0.97]) / np.linalg.norm([0.1, -0.05, 0.2, 0.97])), p_ct=(0.05, -0.02, 0.1), time_offset=0.004)
+
+
+def span_camera_case(knots, dt, t0, seed, atan, noise_rows):
+    """Reference / observation pairs of ONE landmark each whose observation is (nearly) where the landmark projects: rho and the observed pixel from a
+    forward simulation with the 60-digit reference, the observed row then displaced by `noise_rows` so that the Newton iteration has work to do."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[900., 0, 960], [0, 900., 540], [0, 0, 1]])
+    cam = dict(K=K, rows=1080, readout=0.026, **REL, **(ATAN if atan else {}))
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    lo, hi = t0 + 0.3 * dt, t0 + (len(knots) - 3.3) * dt - 0.03
+    rows = []
+    while len(rows) < 3:
+        ref_t0 = rng.uniform(lo, hi)
+        obs_t0 = float(np.clip(ref_t0 + rng.uniform(-0.8, 0.8) * dt, lo, hi))
+        ref_uv = rng.uniform([300, 200], [1600, 900])
+        rho = rng.uniform(0.05, 0.4)
+        # where does it project at mid-frame?  use the lifting projection (a plain projection at a given row time) to find a consistent pixel
+        r, _, _ = mr.lifting_rs_residual(mt, cam, (0.0, 540.0), obs_t0, ref_uv, ref_t0, mp.mpf(rho), mp.mpf(0.5))
+        u, v = -float(r[0]), 540.0 - float(r[1])
+        if not (50 < u < 1870 and 100 < v < 980):
+            continue
+        rows.append((np.array([u + rng.normal(0, 0.5), v + rng.normal(0, noise_rows)]), obs_t0, ref_uv, ref_t0, rho))
+    obs_uv, obs_t0, ref_uv, ref_t0, rho = (np.array(x) for x in zip(*rows))
+    return cam, obs_uv, obs_t0, ref_uv, ref_t0, rho
+
+
+def oracle_camera(cam, method):
+    kw = dict(wc=cam["wc"], gamma=cam["gamma"]) if cam.get("model") == "atan" else {}
+    return kto.Camera(cam["rows"], 1920, cam["readout"], K=cam["K"], method=method, q_ct=cam["q_ct"], p_ct=cam["p_ct"], time_offset=cam["time_offset"], **kw)
+
+
+def test_atan_camera_projection_and_static_rs_rows():
+    knots, dt, t0 = SE3_CASES["random"]
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(knots, dt, t0, 3, True, 2.0)
+    # projection / unprojection round trip of the transcription itself, then the oracle's camera against it
+    y = mr.mpv((700.0, 300.0))
+    Y = mr.camera_unproject(cam, y)
+    y2, _ = mr.camera_project(cam, [2 * v for v in Y])
+    assert max(abs(float(a - b)) for a, b in zip(y, y2)) < 1e-25
+    ocam = oracle_camera(cam, "static")
+    yo = kto.camera_project(ocam, np.array([float(v) for v in Y]) * 2)
+    assert rel(np.asarray(yo).reshape(-1)[:2], f(y2)) < 1e-13
+
+
+@pytest.mark.parametrize("atan", [False, True])
+@pytest.mark.parametrize("case", list(SE3_CASES))
+def test_se3_newton_rs_residual_and_jacobian(case, atan):
+    """NewtonRsCameraMeasurement: value of the iteration AND its derivative through the iteration (central differences of the whole loop at 60 digits:
+    the perturbation is far too small to change the number of evaluations, exactly the function a Jet differentiates)."""
+    knots, dt, t0 = SE3_CASES[case]
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(knots, dt, t0, 11 + atan, atan, 8.0)
+    n = len(rho)
+    o = kto.static_rs_residuals(kto.Traj(kto.SE3, dt, t0, knots), oracle_camera(cam, "newton"), obs_uv, obs_t0, ref_uv, ref_t0, np.arange(n, dtype=np.int32), rho,
+                                jac_mode=2, cap=32)
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    evals = []
+    for k in range(n):
+        box = [[mp.mpf(float(rho[k]))]]
+        fun = lambda: mr.newton_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])[0]
+        r, ir, ne = mr.newton_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])
+        evals.append(ne)
+        assert np.abs(o["r"][k] - f(r)).max() < 1e-9                           # pixels
+        assert int(o["i0_ref_a"][k]) == ir
+        ids = [int(v) for v in o["ids_a"][k] if v >= 0]
+        J = np.array(mr.jacobian(fun, [(mt.knots, b, c) for b in ids for c in range(7)])).reshape(2, len(ids), 7).transpose(1, 0, 2)
+        assert rel(o["Ja"][k, :len(ids)], J) < JAC_TOL, (case, atan, k)
+        assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(2)) < JAC_TOL
+        rest = [(mt.knots, b, c) for b in range(len(knots)) if b not in ids for c in (0, 5)]
+        if rest:
+            assert np.abs(np.array(mr.jacobian(fun, rest))).max() == 0.0
+    assert max(evals) >= 2                                                      # the derivative through a step of the iteration was exercised
+
+
+@pytest.mark.parametrize("atan", [False, True])
+def test_se3_lifting_rs_residual_and_jacobian(atan):
+    knots, dt, t0 = SE3_CASES["random"]
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(knots, dt, t0, 21 + atan, atan, 3.0)
+    n = len(rho)
+    vt = np.clip(obs_uv[:, 1] / cam["rows"] + np.array([0.07, -0.05, 0.11]), 0.0, 1.0)
+    o = kto.lifting_rs_residuals(kto.Traj(kto.SE3, dt, t0, knots), oracle_camera(cam, "static"), obs_uv, obs_t0, ref_uv, ref_t0, np.arange(n, dtype=np.int32), rho,
+                                 vt=vt, jac_mode=2, cap=32)
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    for k in range(n):
+        box = [[mp.mpf(float(rho[k])), mp.mpf(float(vt[k]))]]
+        fun = lambda: mr.lifting_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0], box[0][1])[0]
+        r, ir, io = fun(), *mr.lifting_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0], box[0][1])[1:]
+        assert np.abs(o["r"][k] - f(r)).max() < 1e-9 and int(o["i0_ref_a"][k]) == ir
+        ids = [int(v) for v in o["ids_a"][k] if v >= 0]
+        assert io in ids and io + 3 in ids
+        J = np.array(mr.jacobian(fun, [(mt.knots, b, c) for b in ids for c in range(7)])).reshape(3, len(ids), 7).transpose(1, 0, 2)
+        assert rel(o["Ja"][k, :len(ids)], J) < JAC_TOL, (atan, k)
+        assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(3)) < JAC_TOL
+        assert rel(o["Jvt"][k], np.array(mr.jacobian(fun, [(box, 0, 1)])).reshape(3)) < JAC_TOL
+
+
+@pytest.mark.parametrize("kind", ["se3", "split"])
+def test_position_and_orientation_residual_and_jacobian(kind):
+    """PositionMeasurement / OrientationMeasurement (the reference has no test of its own for the latter): values and ambient Jacobians."""
+    rng = np.random.default_rng(8)
+    if kind == "se3":
+        knots, dt, t0 = SE3_CASES["random"]
+        ot, mt = kto.Traj(kto.SE3, dt, t0, knots), mr.Trajectory("se3", dt, t0, knots=knots)
+        t = times_in(knots, dt, t0, 3, 5)
+    else:
+        r3, so3 = random_split(9, 23)
+        dt, t0 = 0.41, 0.3
+        ot, mt = kto.Traj(kto.SPLIT, dt, t0, r3, dt, t0, so3), mr.Trajectory("split", dt, t0, r3=r3, so3=so3)
+        t = times_in(r3, dt, t0, 3, 6)
+    imu = kto.Sensor()
+    p_meas = rng.normal(0, 1, (3, 3))
+    q_meas = rng.normal(0, 1, (3, 4))
+    q_meas /= np.linalg.norm(q_meas, axis=1, keepdims=True)
+    for which, y, fun_of in ((2, p_meas, mr.position_residual), (3, q_meas, mr.orientation_residual)):
+        o = kto.imu_residuals(ot, imu, which, t, y, jac_mode=2)
+        for k in range(3):
+            fun = lambda: fun_of(mt, float(t[k]), y[k])
+            assert rel(o["r"][k], f(fun())) < 1e-12
+            if kind == "se3":
+                ids = [int(v) for v in o["ids_a"][k] if v >= 0]
+                J = np.array(mr.jacobian(fun, [(mt.knots, b, c) for b in ids for c in range(7)])).reshape(-1, len(ids), 7).transpose(1, 0, 2)
+                assert rel(o["Ja"][k, :len(ids)], J) < JAC_TOL, (which, k)
+            else:
+                ida, idb = [int(v) for v in o["ids_a"][k] if v >= 0], [int(v) for v in o["ids_b"][k] if v >= 0]
+                Ja = np.array(mr.jacobian(fun, [(mt.r3, b, c) for b in ida for c in range(3)])).reshape(-1, len(ida), 3).transpose(1, 0, 2)
+                Jb = np.array(mr.jacobian(fun, [(mt.so3, b, c) for b in idb for c in range(4)])).reshape(-1, len(idb), 4).transpose(1, 0, 2)
+                if which == 2:
+                    assert rel(o["Ja"][k, :len(ida)], Ja) < JAC_TOL and np.abs(Jb).max() == 0.0
+                else:
+                    assert rel(o["Jb"][k, :len(idb)], Jb) < JAC_TOL and np.abs(Ja).max() == 0.0
