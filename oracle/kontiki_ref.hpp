@@ -11,6 +11,8 @@
 //   * a 60-digit mpmath transcription of the reference headers written from the published Sophus / Eigen formulas, sharing no code
 //     with this file (tests/mp_reference.py): values directly, Jacobians by central differences of the 60-digit residual, SE3 poses
 //     also by 4x4 expm / logm (tests/test_oracle_independent.py; committed vectors tests/golden/mp_v1.npz, tests/test_mp_golden.py).
+//     Covered: SE3 / split trajectories x gyroscope / accelerometer / static-RS rows (the hot path) and the widening rows -- AtanCamera,
+//     NewtonRs (value of the iteration and the derivative through it), LiftingRs (incl. the row-time column), Position / Orientation.
 // What stays an assumption is the semantics of the un-vendored dependencies themselves.
 #pragma once
 #include <memory>
