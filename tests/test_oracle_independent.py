@@ -212,7 +212,7 @@ ATAN = dict(model="atan", wc=(0.02, -0.01), gamma=0.9)
 REL = dict(q_ct=tuple(np.array([0.1, -0.05, 0.2, 0.97]) / np.linalg.norm([0.1, -0.05, 0.2, 0.97])), p_ct=(0.05, -0.02, 0.1), time_offset=0.004)
 
 
-def span_camera_case(knots, dt, t0, seed, atan, noise_rows):
+def span_camera_case(knots, dt, t0, seed, atan, noise_rows, n=3):
     """Reference / observation pairs of ONE landmark each whose observation is (nearly) where the landmark projects: rho and the observed pixel from a
     forward simulation with the 60-digit reference, the observed row then displaced by `noise_rows` so that the Newton iteration has work to do."""
     rng = np.random.default_rng(seed)
@@ -221,7 +221,7 @@ def span_camera_case(knots, dt, t0, seed, atan, noise_rows):
     mt = mr.Trajectory("se3", dt, t0, knots=knots)
     lo, hi = t0 + 0.3 * dt, t0 + (len(knots) - 3.3) * dt - 0.03
     rows = []
-    while len(rows) < 3:
+    while len(rows) < n:
         ref_t0 = rng.uniform(lo, hi)
         obs_t0 = float(np.clip(ref_t0 + rng.uniform(-0.8, 0.8) * dt, lo, hi))
         ref_uv = rng.uniform([300, 200], [1600, 900])
