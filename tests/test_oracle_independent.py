@@ -212,13 +212,13 @@ ATAN = dict(model="atan", wc=(0.02, -0.01), gamma=0.9)
 REL = dict(q_ct=tuple(np.array([0.1, -0.05, 0.2, 0.97]) / np.linalg.norm([0.1, -0.05, 0.2, 0.97])), p_ct=(0.05, -0.02, 0.1), time_offset=0.004)
 
 
-def span_camera_case(knots, dt, t0, seed, atan, noise_rows, n=3):
+def span_camera_case(knots, dt, t0, seed, atan, noise_rows, n=3, split=False):
     """Reference / observation pairs of ONE landmark each whose observation is (nearly) where the landmark projects: rho and the observed pixel from a
     forward simulation with the 60-digit reference, the observed row then displaced by `noise_rows` so that the Newton iteration has work to do."""
     rng = np.random.default_rng(seed)
     K = np.array([[900., 0, 960], [0, 900., 540], [0, 0, 1]])
     cam = dict(K=K, rows=1080, readout=0.026, **REL, **(ATAN if atan else {}))
-    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    mt = mr.Trajectory("split", dt, t0, r3=knots[:, 4:], so3=knots[:, :4]) if split else mr.Trajectory("se3", dt, t0, knots=knots)
     lo, hi = t0 + 0.3 * dt, t0 + (len(knots) - 3.3) * dt - 0.03
     rows = []
     while len(rows) < n:
@@ -339,3 +339,37 @@ def test_position_and_orientation_residual_and_jacobian(kind):
                     assert rel(o["Ja"][k, :len(ida)], Ja) < JAC_TOL and np.abs(Jb).max() == 0.0
                 else:
                     assert rel(o["Jb"][k, :len(idb)], Jb) < JAC_TOL and np.abs(Ja).max() == 0.0
+
+
+@pytest.mark.parametrize("kind", ["newton", "lifting"])
+def test_split_newton_and_lifting_residual_and_jacobian(kind):
+    """The span camera rows on a SplitTrajectory (the reference instantiates every measurement with every trajectory, measurement_defs.h:40-85):
+    R3 and SO3 blocks of the oracle against central differences of the 60-digit residual."""
+    se3 = random_se3_knots(9, 17, step=0.25)
+    r3, so3 = se3[:, 4:].copy(), se3[:, :4].copy()
+    dt, t0 = 0.41, 0.3
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(se3, dt, t0, 41, kind == "lifting", 6.0, n=2, split=True)
+    n = len(rho)
+    vt = np.clip(obs_uv[:, 1] / cam["rows"] + np.array([0.05, -0.07]), 0.0, 1.0)
+    traj = kto.Traj(kto.SPLIT, dt, t0, r3, dt, t0, so3)
+    lm = np.arange(n, dtype=np.int32)
+    if kind == "newton":
+        o = kto.static_rs_residuals(traj, oracle_camera(cam, "newton"), obs_uv, obs_t0, ref_uv, ref_t0, lm, rho, jac_mode=2, cap=32)
+    else:
+        o = kto.lifting_rs_residuals(traj, oracle_camera(cam, "static"), obs_uv, obs_t0, ref_uv, ref_t0, lm, rho, vt=vt, jac_mode=2, cap=32)
+    mt = mr.Trajectory("split", dt, t0, r3=r3, so3=so3)
+    nres = 2 if kind == "newton" else 3
+    for k in range(n):
+        box = [[mp.mpf(float(rho[k])), mp.mpf(float(vt[k]))]]
+        if kind == "newton":
+            fun = lambda: mr.newton_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0])[0]
+        else:
+            fun = lambda: mr.lifting_rs_residual(mt, cam, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), box[0][0], box[0][1])[0]
+        assert np.abs(o["r"][k] - f(fun())).max() < 1e-9
+        ida, idb = [int(v) for v in o["ids_a"][k] if v >= 0], [int(v) for v in o["ids_b"][k] if v >= 0]
+        Ja = np.array(mr.jacobian(fun, [(mt.r3, b, c) for b in ida for c in range(3)])).reshape(nres, len(ida), 3).transpose(1, 0, 2)
+        Jb = np.array(mr.jacobian(fun, [(mt.so3, b, c) for b in idb for c in range(4)])).reshape(nres, len(idb), 4).transpose(1, 0, 2)
+        assert rel(o["Ja"][k, :len(ida)], Ja) < JAC_TOL and rel(o["Jb"][k, :len(idb)], Jb) < JAC_TOL, (kind, k)
+        assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(nres)) < JAC_TOL
+        if kind == "lifting":
+            assert rel(o["Jvt"][k], np.array(mr.jacobian(fun, [(box, 0, 1)])).reshape(3)) < JAC_TOL
