@@ -373,3 +373,72 @@ def test_split_newton_and_lifting_residual_and_jacobian(kind):
         assert rel(o["Jrho"][k], np.array(mr.jacobian(fun, [(box, 0, 0)])).reshape(nres)) < JAC_TOL
         if kind == "lifting":
             assert rel(o["Jvt"][k], np.array(mr.jacobian(fun, [(box, 0, 1)])).reshape(3)) < JAC_TOL
+
+
+# ---- sensor parameter blocks: relative pose and time offset of the camera, time offset and biases of the IMU ------------
+def _mp_cam(cam):
+    """camera dict whose relative pose and time offset are lists of mpf that jacobian() can nudge: [[q_ct (4)], [p_ct (3)], [time_offset]]"""
+    box = [mr.mpv(cam["q_ct"]), mr.mpv(cam["p_ct"]), [mp.mpf(float(cam["time_offset"]))]]
+    live = dict(cam)
+    return box, live
+
+
+@pytest.mark.parametrize("method", ["static", "newton", "lifting"])
+def test_camera_sensor_blocks_against_central_differences(method):
+    """d r / d (q_ct, p_ct, time offset) of the three camera measurements (sensors.h:135-165 puts them into the residual's parameter list when unlocked):
+    the oracle's Js against central differences of the 60-digit residual, ambient in q_ct."""
+    knots, dt, t0 = SE3_CASES["random"]
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(knots, dt, t0, 51, method == "newton", 4.0, n=2)
+    n = len(rho)
+    vt = np.clip(obs_uv[:, 1] / cam["rows"] + np.array([0.05, -0.06]), 0.0, 1.0)
+    kw = dict(wc=cam["wc"], gamma=cam["gamma"]) if cam.get("model") == "atan" else {}
+    ocam = kto.Camera(cam["rows"], 1920, cam["readout"], K=cam["K"], method="newton" if method == "newton" else "static", q_ct=cam["q_ct"], p_ct=cam["p_ct"],
+                      time_offset=cam["time_offset"], max_time_offset=0.02, q_locked=False, p_locked=False, d_locked=False, **kw)
+    traj, lm = kto.Traj(kto.SE3, dt, t0, knots), np.arange(n, dtype=np.int32)
+    if method == "lifting":
+        o = kto.lifting_rs_residuals(traj, ocam, obs_uv, obs_t0, ref_uv, ref_t0, lm, rho, vt=vt, jac_mode=2, cap=40)
+    else:
+        o = kto.static_rs_residuals(traj, ocam, obs_uv, obs_t0, ref_uv, ref_t0, lm, rho, jac_mode=2, cap=40)
+    nres = 3 if method == "lifting" else 2
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    box, live = _mp_cam(cam)
+    for k in range(n):
+        def fun():
+            live["q_ct"], live["p_ct"], live["time_offset"] = box[0], box[1], box[2][0]
+            a = (mt, live, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), mp.mpf(float(rho[k])))
+            if method == "static":
+                return mr.static_rs_residual(*a)[0]
+            if method == "newton":
+                return mr.newton_rs_residual(*a)[0]
+            return mr.lifting_rs_residual(*a, mp.mpf(float(vt[k])))[0]
+        assert np.abs(o["r"][k] - f(fun())).max() < 1e-9
+        J = np.array(mr.jacobian(fun, [(box, 0, c) for c in range(4)] + [(box, 1, c) for c in range(3)] + [(box, 2, 0)]))      # (nres, 8)
+        Js = o["Js"][k]
+        mine = np.concatenate([Js[:4 * nres].reshape(nres, 4), Js[4 * nres:7 * nres].reshape(nres, 3), Js[7 * nres:8 * nres].reshape(nres, 1)], axis=1)
+        for blk in (slice(0, 4), slice(4, 7), slice(7, 8)):
+            assert rel(mine[:, blk], J[:, blk]) < JAC_TOL, (method, k, blk)
+
+
+@pytest.mark.parametrize("which", [0, 1])
+def test_imu_sensor_blocks_against_central_differences(which):
+    """Time offset of the IMU (imu.h:47-59: the trajectory is evaluated at t + time_offset) and the biases of a ConstantBiasImu
+    (constant_bias_imu.h:100-119): the oracle's Js [q_ct 3x4 | p_ct 3x3 | time offset 3 | accelerometer bias 3x3 | gyroscope bias 3x3]."""
+    knots, dt, t0 = SE3_CASES["random"]
+    t = times_in(knots, dt, t0, 3, 9)
+    rng = np.random.default_rng(2)
+    y = rng.normal(0, 1, (3, 3))
+    ab, gb, d = np.array([0.05, -0.02, 0.03]), np.array([-0.01, 0.02, 0.015]), 0.003
+    imu = kto.Sensor(time_offset=d, max_time_offset=0.02, d_locked=False, abias=ab, gbias=gb, abias_locked=False, gbias_locked=False)
+    o = kto.imu_residuals(kto.Traj(kto.SE3, dt, t0, knots), imu, which, t, y, jac_mode=2)
+    mt = mr.Trajectory("se3", dt, t0, knots=knots)
+    box = [[mp.mpf(d)], mr.mpv(ab), mr.mpv(gb)]
+    for k in range(3):
+        def fun():
+            m = mr.gyroscope(mt, mp.mpf(float(t[k])), box[0][0]) if which == 0 else mr.accelerometer(mt, mp.mpf(float(t[k])), box[0][0])
+            bias = box[2] if which == 0 else box[1]                      # constant_bias_imu.h: measurement = standard model + bias
+            return [mp.mpf(float(y[k][i])) - (m[i] + bias[i]) for i in range(3)]
+        assert rel(o["r"][k], f(fun())) < 1e-12
+        J = np.array(mr.jacobian(fun, [(box, 0, 0)] + [(box, 1, c) for c in range(3)] + [(box, 2, c) for c in range(3)]))      # (3, 7)
+        Js = o["Js"][k]
+        assert rel(Js[21:24].reshape(3, 1), J[:, 0:1]) < JAC_TOL, (which, k)
+        assert np.abs(Js[24:33].reshape(3, 3) - J[:, 1:4]).max() < 1e-12 and np.abs(Js[33:42].reshape(3, 3) - J[:, 4:7]).max() < 1e-12
