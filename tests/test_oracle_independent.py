@@ -442,3 +442,42 @@ def test_imu_sensor_blocks_against_central_differences(which):
         Js = o["Js"][k]
         assert rel(Js[21:24].reshape(3, 1), J[:, 0:1]) < JAC_TOL, (which, k)
         assert np.abs(Js[24:33].reshape(3, 3) - J[:, 1:4]).max() < 1e-12 and np.abs(Js[33:42].reshape(3, 3) - J[:, 4:7]).max() < 1e-12
+
+
+def test_local_parameterization_jacobians_against_central_differences():
+    """What Ceres multiplies the ambient blocks with, and what KTK_EVAL_LOCAL / the device Gauss-Newton step apply on the GPU: d Plus(x, delta) / d delta at 0.
+    SE3 knots: Plus(T, delta) = T * SE3::exp(delta), delta = [upsilon; omega] (uniform_se3_spline_trajectory.h:20-31; the reference takes the Jacobian from
+    Sophus' Dx_this_mul_exp_x_at_0).  SO3 knots: ceres::EigenQuaternionParameterization, Plus(q, d) = (sin|d| d/|d|, cos|d|) * q
+    (uniform_so3_spline_trajectory.h:21).  The closed forms of kontiki_b200.estimator (the reference of the GPU local-row tests) against central differences
+    of the 60-digit group operations."""
+    from kontiki_b200.estimator import _quat_plus_jacobian, _se3_plus_jacobian
+    knots = random_se3_knots(4, 31)
+    P = _se3_plus_jacobian(knots)
+    h = mp.mpf("1e-25")
+    for k, kn in enumerate(knots):
+        q, t = mr.mpv(kn[:4]), mr.mpv(kn[4:])
+        num = np.zeros((7, 6))
+        for c in range(6):
+            out = []
+            for s in (1, -1):
+                d = [mp.mpf(0)] * 6
+                d[c] = s * h
+                qe, te = mr.se3_exp(d)
+                qq, tt = mr.se3_mul(q, t, qe, te)
+                out.append(list(qq) + list(tt))
+            num[:, c] = [float((a - b) / (2 * h)) for a, b in zip(*out)]
+        assert np.abs(P[k] - num).max() < 1e-14, k
+    Q = _quat_plus_jacobian(knots[:, :4])
+    for k, kn in enumerate(knots):
+        q = mr.mpv(kn[:4])
+        num = np.zeros((4, 3))
+        for c in range(3):
+            out = []
+            for s in (1, -1):
+                d = [mp.mpf(0)] * 3
+                d[c] = s * h
+                n = mp.sqrt(sum(v * v for v in d))
+                qd = [mp.sin(n) * v / n for v in d] + [mp.cos(n)]
+                out.append(mr.q_mul(qd, q))
+            num[:, c] = [float((a - b) / (2 * h)) for a, b in zip(*out)]
+        assert np.abs(Q[k] - num).max() < 1e-14, k
