@@ -481,3 +481,41 @@ def test_local_parameterization_jacobians_against_central_differences():
                 out.append(mr.q_mul(qd, q))
             num[:, c] = [float((a - b) / (2 * h)) for a, b in zip(*out)]
         assert np.abs(Q[k] - num).max() < 1e-14, k
+
+
+def test_split_sensor_blocks_against_central_differences():
+    """The same sensor blocks on a SplitTrajectory (split_trajectory.h:117-123; the verdict's f-2 remainder): camera relative pose / time offset of static rows,
+    time offset and bias of the IMU."""
+    se3 = random_se3_knots(9, 19, step=0.25)
+    r3, so3 = se3[:, 4:].copy(), se3[:, :4].copy()
+    dt, t0 = 0.41, 0.3
+    traj, mt = kto.Traj(kto.SPLIT, dt, t0, r3, dt, t0, so3), mr.Trajectory("split", dt, t0, r3=r3, so3=so3)
+    cam, obs_uv, obs_t0, ref_uv, ref_t0, rho = span_camera_case(se3, dt, t0, 61, False, 2.0, n=2, split=True)
+    ocam = kto.Camera(cam["rows"], 1920, cam["readout"], K=cam["K"], q_ct=cam["q_ct"], p_ct=cam["p_ct"], time_offset=cam["time_offset"], max_time_offset=0.02,
+                      q_locked=False, p_locked=False, d_locked=False)
+    o = kto.static_rs_residuals(traj, ocam, obs_uv, obs_t0, ref_uv, ref_t0, np.arange(2, dtype=np.int32), rho, jac_mode=2, cap=40)
+    box, live = _mp_cam(cam)
+    for k in range(2):
+        def fun():
+            live["q_ct"], live["p_ct"], live["time_offset"] = box[0], box[1], box[2][0]
+            return mr.static_rs_residual(mt, live, obs_uv[k], float(obs_t0[k]), ref_uv[k], float(ref_t0[k]), mp.mpf(float(rho[k])))[0]
+        assert np.abs(o["r"][k] - f(fun())).max() < 1e-9
+        J = np.array(mr.jacobian(fun, [(box, 0, c) for c in range(4)] + [(box, 1, c) for c in range(3)] + [(box, 2, 0)]))
+        Js = o["Js"][k]
+        mine = np.concatenate([Js[:8].reshape(2, 4), Js[8:14].reshape(2, 3), Js[14:16].reshape(2, 1)], axis=1)
+        for blk in (slice(0, 4), slice(4, 7), slice(7, 8)):
+            assert rel(mine[:, blk], J[:, blk]) < JAC_TOL, (k, blk)
+    t = times_in(r3, dt, t0, 2, 4)
+    y = np.random.default_rng(5).normal(0, 1, (2, 3))
+    ab, gb, d = np.array([0.05, -0.02, 0.03]), np.array([-0.01, 0.02, 0.015]), 0.003
+    imu = kto.Sensor(time_offset=d, max_time_offset=0.02, d_locked=False, abias=ab, gbias=gb, abias_locked=False, gbias_locked=False)
+    for which in (0, 1):
+        oi = kto.imu_residuals(traj, imu, which, t, y, jac_mode=2)
+        ibox = [[mp.mpf(d)]]
+        for k in range(2):
+            def fun():
+                m = mr.gyroscope(mt, mp.mpf(float(t[k])), ibox[0][0]) if which == 0 else mr.accelerometer(mt, mp.mpf(float(t[k])), ibox[0][0])
+                bias = gb if which == 0 else ab
+                return [mp.mpf(float(y[k][i])) - (m[i] + mp.mpf(float(bias[i]))) for i in range(3)]
+            assert rel(oi["r"][k], f(fun())) < 1e-12
+            assert rel(oi["Js"][k][21:24].reshape(3, 1), np.array(mr.jacobian(fun, [(ibox, 0, 0)]))) < JAC_TOL, (which, k)
